@@ -1,0 +1,196 @@
+"""Known-answer pins for the oracle's linear system and CG.
+
+The reference ships no golden vectors ("parity unpinned"), so the oracle is pinned by analytic
+properties of the system it must assemble:  (M_u + 2 dt D^T K M_tau U D) u = M_u u^n  (AV.cpp:424-427).
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from adaptiveviscositysolver_b200.scenes import sphere_drop
+from oracle import avs_oracle as orc
+
+P = orc.OracleParams
+
+
+def test_k1_k2_symmetric_positive_definite():
+    sc = sphere_drop(32, 11, noise=0.01)
+    r = orc.OracleRun(sc, P(octree_levels=4), stop_after_stage=9)
+    A = r.scipy_matrix()
+    assert r.levels >= 3
+    assert abs(A - A.T).max() <= 1e-14 * abs(A).max()
+    lam = spla.eigsh(A.tocsc(), k=1, sigma=0, which="LM", return_eigenvectors=False)
+    assert lam[0] > 0
+    assert (A.diagonal() > 0).all()
+
+
+@pytest.mark.parametrize("n,R,L,res,c", [(32, 10, 1, None, (0.5,) * 3), (64, 24, 6, None, (0.5,) * 3),
+                                         (64, 14, 5, (48, 64, 40), (0.375, 0.5, 0.3125))])
+def test_k3_translation_invariance(n, R, L, res, c):
+    """Every row of D sums to zero, also across T-junctions => constant velocity is a fixed point."""
+    sc = sphere_drop(n, R, res=res, center=c, velocity="constant")
+    r = orc.OracleRun(sc, P(octree_levels=L, tolerance=1e-8))
+    A, b, x0 = r.scipy_matrix(), r.rhs(), r.x0()
+    assert abs(b - A @ x0).max() <= 1e-12 * abs(b).max() * 10
+    assert r.iterations == 0
+    assert np.allclose(r.solution(), x0)
+    keys = r.face_keys()
+    for ax, v in enumerate((0.3, -0.2, 0.1)):     # K7: restriction weights sum to one
+        assert np.allclose(x0[keys[:, 1] == ax], np.float32(v), rtol=0, atol=1e-7)
+
+
+def test_k4_zero_viscosity_is_identity():
+    sc = sphere_drop(32, 10, mu=0.0)
+    r = orc.OracleRun(sc, P(octree_levels=4))
+    A = r.scipy_matrix()
+    assert (A - sp.diags(A.diagonal())).nnz == 0 or abs(A - sp.diags(A.diagonal())).max() == 0
+    assert r.iterations == 0
+    assert np.array_equal(r.solution(), r.x0())
+
+
+def test_k5_uniform_fifteen_point_row():
+    """interior level-0 row = diag rho+8a, -2a (x2), -a (x4), +-a (x8), a = dt mu / h^2."""
+    n, mu, rho, dt = 32, 200.0, 1000.0, 1.0 / 24
+    sc = sphere_drop(n, 12, mu=mu, rho=rho)
+    r = orc.OracleRun(sc, P(octree_levels=1, dt=dt), stop_after_stage=9)
+    A = r.scipy_matrix().tocsr()
+    keys = r.face_keys()
+    a = dt * mu * n * n
+    f = r.face_index(0, 0)
+    i = int(f[16, 16, 16])
+    assert i >= 0
+    row = A.getrow(i)
+    cols, vals = row.indices, row.data
+    assert len(cols) == 15
+    d = dict(zip(cols.tolist(), vals.tolist()))
+    assert d[i] == pytest.approx(rho + 8 * a, rel=1e-13)
+    assert d[int(f[16, 16, 15])] == pytest.approx(-2 * a, rel=1e-13)
+    assert d[int(f[16, 16, 17])] == pytest.approx(-2 * a, rel=1e-13)
+    for (k, j) in ((16, 15), (16, 17), (15, 16), (17, 16)):
+        assert d[int(f[k, j, 16])] == pytest.approx(-a, rel=1e-13)
+    fy, fz = r.face_index(0, 1), r.face_index(0, 2)
+    # v faces around the two z-edges of the u-face (i=16,j=16,k=16): v(i-1,j), v(i,j), v(i-1,j+1), v(i,j+1)
+    assert d[int(fy[16, 16, 15])] == pytest.approx(-a, rel=1e-13)
+    assert d[int(fy[16, 16, 16])] == pytest.approx(+a, rel=1e-13)
+    assert d[int(fy[16, 17, 15])] == pytest.approx(+a, rel=1e-13)
+    assert d[int(fy[16, 17, 16])] == pytest.approx(-a, rel=1e-13)
+    assert d[int(fz[16, 16, 15])] == pytest.approx(-a, rel=1e-13)
+    assert d[int(fz[16, 16, 16])] == pytest.approx(+a, rel=1e-13)
+    assert d[int(fz[17, 16, 15])] == pytest.approx(+a, rel=1e-13)
+    assert d[int(fz[17, 16, 16])] == pytest.approx(-a, rel=1e-13)
+    assert sum(vals) == pytest.approx(rho, rel=1e-9)
+    assert r.rhs()[i] == pytest.approx(rho * r.x0()[i], rel=1e-14)
+    assert keys[i].tolist() == [0, 0, 16, 16, 16]
+
+
+def test_k6_all_fine_band_equals_uniform():
+    sc = sphere_drop(32, 10)
+    u = orc.OracleRun(sc, P(octree_levels=1, tolerance=1e-10))
+    o = orc.OracleRun(sc, P(octree_levels=4, fine_bandwidth=64, tolerance=1e-10))
+    assert o.levels == 1 and o.n_face == u.n_face
+    assert abs(o.scipy_matrix() - u.scipy_matrix()).max() == 0
+    assert np.array_equal(o.solution(), u.solution())
+
+
+def test_k8_control_volumes_tile_space():
+    """Sum of face control volumes over all levels ~ liquid volume, per axis."""
+    n, R = 64, 24
+    sc = sphere_drop(n, R, velocity="constant", constant_velocity=(1.0, 1.0, 1.0))
+    r = orc.OracleRun(sc, P(octree_levels=5), stop_after_stage=9)
+    keys, b = r.face_keys(), r.rhs()
+    vol = 4.0 / 3.0 * np.pi * R ** 3
+    for ax in range(3):
+        V = b[keys[:, 1] == ax].sum() / 1000.0
+        assert V == pytest.approx(vol, rel=0.02)
+
+
+def _eigen_cg_numpy(A, b, x0, tol, maxit):
+    """Independent restatement of Eigen's conjugate_gradient + DiagonalPreconditioner."""
+    x = x0.copy()
+    d = A.diagonal()
+    inv = np.where(d != 0, 1.0 / d, 1.0)
+    r = b - A @ x
+    rhs2 = b @ b
+    if rhs2 == 0:
+        return np.zeros_like(x), 0, 0.0
+    thr = max(tol * tol * rhs2, np.finfo(np.float64).tiny)
+    r2 = r @ r
+    if r2 < thr:
+        return x, 0, np.sqrt(r2 / rhs2)
+    p = inv * r
+    absnew = r @ p
+    i = 0
+    while i < maxit:
+        t = A @ p
+        alpha = absnew / (p @ t)
+        x += alpha * p
+        r -= alpha * t
+        r2 = r @ r
+        if r2 < thr:
+            break
+        z = inv * r
+        absold = absnew
+        absnew = r @ z
+        p = z + (absnew / absold) * p
+        i += 1
+    return x, i, np.sqrt(r2 / rhs2)
+
+
+@pytest.mark.parametrize("L,tol", [(1, 1e-3), (4, 1e-3), (4, 1e-8)])
+def test_cg_matches_independent_restatement(L, tol):
+    sc = sphere_drop(32, 11)
+    r = orc.OracleRun(sc, P(octree_levels=L, tolerance=tol))
+    A, b, x0 = r.scipy_matrix(), r.rhs(), r.x0()
+    x, it, err = _eigen_cg_numpy(A, b, x0, tol, 2500)
+    assert abs(it - r.iterations) <= 1
+    assert err < tol and r.error < tol
+    assert np.allclose(x, r.solution(), rtol=0, atol=max(tol, 1e-9) * abs(x).max())
+    # and the solve really solves the system
+    xs = r.solution()
+    assert np.linalg.norm(b - A @ xs) <= tol * np.linalg.norm(b) * 1.0000001
+    # stand-alone entry point used by the CPU baseline
+    ptr, col, val = r.csr()
+    x2, it2, err2 = orc.cg(ptr, col, val, b, x0, tol, 2500)
+    assert it2 == r.iterations and np.array_equal(x2, xs)
+    assert np.allclose(orc.spmv(ptr, col, val, x0), A @ x0, rtol=1e-13, atol=1e-9)
+
+
+def test_cg_max_iterations_and_zero_rhs():
+    sc = sphere_drop(32, 10)
+    r = orc.OracleRun(sc, P(octree_levels=3, tolerance=1e-12, max_iterations=5))
+    assert r.iterations == 5 and r.error > 1e-12
+    ptr, col, val = r.csr()
+    x, it, err = orc.cg(ptr, col, val, np.zeros(r.n_face), r.x0(), 1e-6, 100)
+    assert it == 0 and err == 0 and not x.any()       # ||b|| = 0 => x = 0 (Eigen)
+
+
+def test_single_precision_path():
+    """USESINGLEPRECISION (UTIL.h:25-37): same system solved in fp32."""
+    sc = sphere_drop(32, 10)
+    d = orc.OracleRun(sc, P(octree_levels=3, tolerance=1e-4))
+    s = orc.OracleRun(sc, P(octree_levels=3, tolerance=1e-4, single_precision=True))
+    assert s.error < 1e-4
+    assert np.allclose(s.solution(), d.solution(), rtol=0, atol=2e-3)
+
+
+def test_solid_ground_rows():
+    """Solid faces drop out of the unknowns, feed the rhs through boundary terms (AV.cpp:1896-1905,
+    1952-1961, 2453-2456) and the system stays SPD; a solid moving with the liquid is a fixed point."""
+    v = (0.3, -0.2, 0.1)
+    sc = sphere_drop(32, 9, center=(0.5, 0.34, 0.5), velocity="constant", constant_velocity=v,
+                     ground_height=0.125, ground_velocity=v)
+    r = orc.OracleRun(sc, P(octree_levels=3, tolerance=1e-8))
+    solid = sum(int((r.face_index(0, ax) == orc.SOLIDBOUNDARY).sum()) for ax in range(3))
+    assert solid > 0
+    A, b, x0 = r.scipy_matrix(), r.rhs(), r.x0()
+    assert abs(A - A.T).max() <= 1e-14 * abs(A).max()
+    # NOTE: edge stencils sample collision-velocity component `axis` (the edge axis) as written in
+    # the reference (AV.cpp:1901), so only a solid velocity with equal components is an exact fixed
+    # point; here we only require the centre-stress terms (correct component) to be consistent.
+    sc2 = sphere_drop(32, 9, center=(0.5, 0.34, 0.5), velocity="constant", constant_velocity=(0.2, 0.2, 0.2),
+                      ground_height=0.125, ground_velocity=(0.2, 0.2, 0.2))
+    r2 = orc.OracleRun(sc2, P(octree_levels=3, tolerance=1e-8))
+    A2, b2, x2 = r2.scipy_matrix(), r2.rhs(), r2.x0()
+    assert abs(b2 - A2 @ x2).max() <= 1e-11 * abs(b2).max()
+    assert r2.iterations == 0
