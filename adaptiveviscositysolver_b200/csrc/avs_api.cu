@@ -1,0 +1,491 @@
+// avs_api.cu -- the extern "C" surface declared in include/avs.h: context life cycle, the staged
+// pipeline that replaces HDK_AdaptiveViscosity.cpp:233-707, and host read-back for parity tests.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "avs_context.h"
+
+static thread_local char g_lastError[512] = "";
+
+void avs_set_last_error(const char *what, cudaError_t e, const char *file, int line) {
+    snprintf(g_lastError, sizeof(g_lastError), "%s failed: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+    cudaGetLastError();
+}
+
+extern "C" {
+
+int avs_abi_version(void) { return AVS_ABI_VERSION; }
+
+const char *avs_last_error(void) { return g_lastError; }
+
+const char *avs_status_string(int s) {
+    switch (s) {
+        case AVS_OK: return "ok";
+        case AVS_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case AVS_ERR_MISSING_FIELD: return "field missing";
+        case AVS_ERR_MISALIGNED_FIELD: return "field not aligned";
+        case AVS_ERR_ALLOC: return "device allocation failed";
+        case AVS_ERR_CUDA: return "CUDA error";
+        case AVS_ERR_NCCL: return "NCCL error";
+        case AVS_ERR_CANCELLED: return "cancelled";
+        case AVS_ERR_BREAKDOWN: return "conjugate gradient breakdown";
+        case AVS_ERR_NO_DEVICE: return "no CUDA device";
+        case AVS_ERR_UNSUPPORTED: return "unsupported configuration";
+    }
+    return "unknown status";
+}
+
+void avs_default_params(AvsParams *p) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->size = sizeof(AvsParams);
+    p->dt = 1.0 / 24.0;
+    p->tolerance = 1e-3;
+    p->extrapolation = 0.5;
+    p->max_iterations = 2500;
+    p->number_super_samples = 3;
+    p->octree_levels = 4;
+    p->fine_bandwidth = 0;
+    p->use_enhanced_gradients = 1;
+    p->do_apply_solid_weights = 0;
+    p->precision = AVS_PRECISION_F64;
+    p->check_every = 0;
+    p->cancel = nullptr;
+}
+
+int avs_create(const AvsDeviceConfig *cfg, AvsContext **out) {
+    if (!out) return AVS_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        snprintf(g_lastError, sizeof(g_lastError), "no CUDA device visible: this library has no CPU path");
+        return AVS_ERR_NO_DEVICE;
+    }
+    AvsContext *c = new (std::nothrow) AvsContext();
+    if (!c) return AVS_ERR_ALLOC;
+    if (cfg) {
+        if (cfg->size != sizeof(AvsDeviceConfig)) { delete c; return AVS_ERR_INVALID_ARGUMENT; }
+        c->device = cfg->device;
+        c->rank = cfg->rank;
+        c->nranks = std::max(1, cfg->nranks);
+        c->nccl = cfg->nccl_comm;
+        c->timeSpmv = cfg->time_spmv != 0;
+        c->stream = (cudaStream_t)cfg->stream;
+    }
+    if (c->device < 0 || c->device >= ndev || c->rank < 0 || c->rank >= c->nranks) { delete c; return AVS_ERR_INVALID_ARGUMENT; }
+    if (cudaSetDevice(c->device) != cudaSuccess) { delete c; return AVS_ERR_CUDA; }
+    if (!c->stream) {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return AVS_ERR_CUDA; }
+        c->ownStream = true;
+    }
+    cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, c->device);
+    for (auto &e : c->ev) cudaEventCreate(&e);
+    cudaEventCreateWithFlags(&c->evPoll[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->evPoll[1], cudaEventDisableTiming);
+    if (cudaHostAlloc(&c->hostScalars, 512, cudaHostAllocDefault) != cudaSuccess) { delete c; return AVS_ERR_ALLOC; }
+    if (c->timeSpmv) {
+        c->spmvEvents.resize(2 * 4096);
+        for (auto &e : c->spmvEvents) cudaEventCreate(&e);
+    }
+    if (c->counters.reserve(64 * sizeof(unsigned long long))) { delete c; return AVS_ERR_ALLOC; }
+    memset(&c->S, 0, sizeof(c->S));
+    *out = c;
+    return AVS_OK;
+}
+
+void avs_destroy(AvsContext *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf *bufs[] = {&c->inSurface, &c->inVisc, &c->inDens, &c->inColl, &c->centerW, &c->tiles, &c->brickCount, &c->brickOffset,
+                      &c->scanTmp, &c->counters, &c->rowKeys, &c->x0, &c->rhs, &c->solution, &c->rowCount, &c->rowOffset,
+                      &c->csrPtr, &c->csrCol, &c->csrVal, &c->A.sliceOff, &c->A.val, &c->A.col, &c->A.invDiag, &c->A.meta,
+                      &c->cg.x, &c->cg.r, &c->cg.p, &c->cg.t, &c->cg.partials, &c->cg.scalars, &c->cgRhs};
+    for (DevBuf *b : bufs) b->release();
+    for (int a = 0; a < 3; ++a) {
+        c->inVel[a].release(); c->inFaceW[a].release(); c->inCollVel[a].release(); c->edgeW[a].release(); c->regular[a].release();
+    }
+    for (int l = 0; l < AVS_MAX_LEVELS; ++l) {
+        c->label[l].release(); c->center[l].release();
+        for (int a = 0; a < 3; ++a) { c->face[l][a].release(); c->edge[l][a].release(); }
+    }
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : c->evPoll) if (e) cudaEventDestroy(e);
+    for (auto &e : c->spmvEvents) if (e) cudaEventDestroy(e);
+    if (c->hostScalars) cudaFreeHost(c->hostScalars);
+    if (c->ownStream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+}  // extern "C"
+
+// ---- stage 0: host -> device ------------------------------------------------------------------
+static int uploadField(AvsContext *c, DevBuf &buf, DField &d, const AvsField &f) {
+    for (int a = 0; a < 3; ++a) { d.n[a] = f.res[a]; d.org[a] = f.org[a]; }
+    d.dx = f.dx;
+    d.constant = f.constant;
+    if (!f.data) {
+        d.d = nullptr;
+        d.n[0] = d.n[1] = d.n[2] = 1;
+        return AVS_OK;
+    }
+    if (f.res[0] <= 0 || f.res[1] <= 0 || f.res[2] <= 0 || !(f.dx > 0)) return AVS_ERR_INVALID_ARGUMENT;
+    size_t bytes = (size_t)f.res[0] * f.res[1] * f.res[2] * sizeof(float);
+    if (buf.reserve(bytes)) return AVS_ERR_ALLOC;
+    AVS_CUDA_CHECK(cudaMemcpyAsync(buf.p, f.data, bytes, f.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    d.d = buf.as<float>();
+    return AVS_OK;
+}
+
+static bool aligned(const AvsField &f, const int res[3], const double org[3], double dx) {
+    if (!f.data) return true;  // constant fields are aligned with anything
+    for (int a = 0; a < 3; ++a) {
+        if (f.res[a] != res[a]) return false;
+        if (std::fabs(f.org[a] - org[a]) > 1e-6 * dx) return false;
+    }
+    return std::fabs(f.dx - dx) <= 1e-9 * dx;
+}
+
+int avs_stage_upload(AvsContext *c, const AvsFields *in, const AvsParams *p) {
+    if (!in || in->size != sizeof(AvsFields) || !p || p->size != sizeof(AvsParams)) return AVS_ERR_INVALID_ARGUMENT;
+    if (in->res[0] <= 0 || in->res[1] <= 0 || in->res[2] <= 0 || !(in->dx > 0)) return AVS_ERR_INVALID_ARGUMENT;
+    if (p->number_super_samples < 1 || p->octree_levels < 1 || p->max_iterations < 0) return AVS_ERR_INVALID_ARGUMENT;
+    // the reference's validation (AV.cpp:152-229): missing fields and alignment
+    if (!in->surface.data) return AVS_ERR_MISSING_FIELD;
+    for (int a = 0; a < 3; ++a)
+        if (!in->vel[a].data || !in->face_weights[a].data) return AVS_ERR_MISSING_FIELD;
+    double corg[3];
+    for (int a = 0; a < 3; ++a) corg[a] = in->origin[a] + 0.5 * in->dx;
+    if (!aligned(in->surface, in->res, corg, in->dx)) return AVS_ERR_MISALIGNED_FIELD;
+    if (!aligned(in->viscosity, in->res, corg, in->dx)) return AVS_ERR_MISALIGNED_FIELD;  // AV.cpp:210
+    if (!aligned(in->density, in->res, corg, in->dx)) return AVS_ERR_MISALIGNED_FIELD;    // AV.cpp:225
+    for (int a = 0; a < 3; ++a) {
+        int fres[3] = {in->res[0], in->res[1], in->res[2]};
+        fres[a] += 1;
+        double forg[3];
+        for (int k = 0; k < 3; ++k) forg[k] = in->origin[k] + (k == a ? 0.0 : 0.5 * in->dx);
+        if (!aligned(in->vel[a], fres, forg, in->dx)) return AVS_ERR_MISALIGNED_FIELD;           // AV.cpp:157 (face sampled)
+        if (!aligned(in->face_weights[a], fres, forg, in->dx)) return AVS_ERR_MISALIGNED_FIELD;  // AV.cpp:169
+    }
+    DeviceScene &S = c->S;
+    for (int a = 0; a < 3; ++a) { S.N[a] = in->res[a]; S.origin[a] = in->origin[a]; }
+    S.dx0 = (double)(float)in->dx;  // getVoxelSize() is a float32 vector (AV.cpp:242)
+    S.dt = p->dt;
+    S.extrap = S.dx0 * p->extrapolation;  // AV.cpp:243
+    S.enhanced = p->use_enhanced_gradients ? 1 : 0;
+    int rc;
+    if ((rc = uploadField(c, c->inSurface, S.surface, in->surface))) return rc;
+    for (int a = 0; a < 3; ++a) {
+        if ((rc = uploadField(c, c->inVel[a], S.vel[a], in->vel[a]))) return rc;
+        if ((rc = uploadField(c, c->inFaceW[a], S.faceW[a], in->face_weights[a]))) return rc;
+        if ((rc = uploadField(c, c->inCollVel[a], S.collisionVel[a], in->collision_vel[a]))) return rc;
+    }
+    if ((rc = uploadField(c, c->inVisc, S.viscosity, in->viscosity))) return rc;
+    if ((rc = uploadField(c, c->inDens, S.density, in->density))) return rc;
+    if ((rc = uploadField(c, c->inColl, S.collision, in->collision))) return rc;
+    return AVS_OK;
+}
+
+static void fillCounts(AvsContext *c, AvsResult *res) {
+    res->levels = c->S.levels;
+    res->octree_dofs = c->nRows;
+    res->regular_dofs = c->nRegular;
+    res->edge_dofs = c->nEdge;
+    res->center_dofs = c->nCenter;
+    res->nnz = c->nnz;
+    res->local_rows = c->rowEnd - c->rowBegin;
+    res->kernel_launches = c->launches;
+    res->spmv_launches = c->spmvLaunches;
+}
+
+static void collectStageTimes(AvsContext *c, AvsResult *res, int first, int last) {
+    // ev[i] is recorded at the START of stage i; ev[last+1] after the last stage
+    cudaEventSynchronize(c->ev[last + 1]);
+    float total = 0;
+    for (int i = first; i <= last; ++i) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]);
+        res->stage_ms[i] = ms;
+        total += ms;
+    }
+    res->stage_ms[AVS_STAGE_TOTAL] += total;
+}
+
+static int runAssemble(AvsContext *c, const AvsFields *in, const AvsParams *p, AvsResult *res) {
+    int rc;
+    c->haveSystem = c->haveSolution = false;
+    cudaEventRecord(c->ev[AVS_STAGE_UPLOAD], c->stream);
+    if ((rc = avs_stage_upload(c, in, p))) return rc;
+    cudaEventRecord(c->ev[AVS_STAGE_SURFACE_WEIGHTS], c->stream);
+    if ((rc = avs_stage_weights(c, p))) return rc;
+    cudaEventRecord(c->ev[AVS_STAGE_OCTREE], c->stream);
+    if ((rc = avs_stage_octree(c, p))) return rc;
+    cudaEventRecord(c->ev[AVS_STAGE_REGULAR_LABELS], c->stream);
+    if ((rc = avs_stage_regular_labels(c))) return rc;
+    cudaEventRecord(c->ev[AVS_STAGE_OCTREE_LABELS], c->stream);
+    if ((rc = avs_stage_octree_labels(c))) return rc;
+    cudaEventRecord(c->ev[AVS_STAGE_RESTRICTION], c->stream);
+    if ((rc = avs_stage_restriction(c))) return rc;
+    cudaEventRecord(c->ev[AVS_STAGE_SYSTEM], c->stream);
+    if ((rc = avs_stage_system(c, p))) return rc;
+    // the CG's matrix format is part of "Build Octree Linear System" (the reference's setFromTriplets, AV.cpp:614)
+    if ((rc = avs_sell_from_csr(c, c->A, c->rowEnd - c->rowBegin, c->csrPtr.as<int64_t>(), c->csrCol.as<int32_t>(),
+                                c->csrVal.as<double>(), p->precision))) return rc;
+    cudaEventRecord(c->ev[AVS_STAGE_SOLVE], c->stream);
+    collectStageTimes(c, res, AVS_STAGE_UPLOAD, AVS_STAGE_SYSTEM);
+    fillCounts(c, res);
+    return AVS_OK;
+}
+
+static int runSolve(AvsContext *c, const AvsParams *p, AvsResult *res) {
+    if (!c->haveSystem) return AVS_ERR_INVALID_ARGUMENT;
+    if (c->nranks > 1) return AVS_ERR_UNSUPPORTED;  // multi-GPU CG goes through avs_solve_resident once NCCL is wired (round 1: single GPU)
+    const long long n = c->rowEnd - c->rowBegin;
+    if (c->solution.reserve((size_t)std::max<long long>(n, 1) * sizeof(double))) return AVS_ERR_ALLOC;
+    c->spmvEventsUsed = 0;
+    c->spmvMs = 0;
+    const int64_t spmv0 = c->spmvLaunches;
+    cudaEventRecord(c->ev[AVS_STAGE_SOLVE], c->stream);
+    int rc = avs_cg_run(c, c->A, c->rhs.as<double>(), c->x0.as<double>() + c->rowBegin, c->solution.as<double>(), p, res);
+    cudaEventRecord(c->ev[AVS_STAGE_SOLVE + 1], c->stream);
+    collectStageTimes(c, res, AVS_STAGE_SOLVE, AVS_STAGE_SOLVE);
+    if (c->timeSpmv) {
+        float total = 0;
+        for (size_t i = 0; i + 1 < c->spmvEventsUsed; i += 2) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->spmvEvents[i], c->spmvEvents[i + 1]);
+            total += ms;
+        }
+        res->spmv_ms = total;
+        res->spmv_launches = (int64_t)(c->spmvEventsUsed / 2);
+    } else {
+        res->spmv_launches = c->spmvLaunches - spmv0;
+    }
+    res->kernel_launches = c->launches;
+    if (rc == AVS_OK) c->haveSolution = true;
+    return rc;
+}
+
+static int runApply(AvsContext *c, AvsVelocityOut *out, AvsResult *res) {
+    if (!c->haveSolution || !out) return AVS_ERR_INVALID_ARGUMENT;
+    cudaEventRecord(c->ev[AVS_STAGE_APPLY], c->stream);
+    float *dOut[3];
+    DevBuf tmp[3];
+    for (int a = 0; a < 3; ++a) {
+        if (!out->vel[a]) return AVS_ERR_INVALID_ARGUMENT;
+        size_t bytes = c->S.regular[a].count() * sizeof(float);
+        if (out->on_device) dOut[a] = out->vel[a];
+        else {
+            // start from the caller's current values so untouched faces stay untouched (AV.cpp:2843-2890)
+            if (tmp[a].reserve(bytes)) return AVS_ERR_ALLOC;
+            AVS_CUDA_CHECK(cudaMemcpyAsync(tmp[a].p, out->vel[a], bytes, cudaMemcpyHostToDevice, c->stream));
+            dOut[a] = tmp[a].as<float>();
+        }
+    }
+    unsigned long long pending = 0;
+    int rc = avs_apply_regular(c, dOut, &pending);
+    if (rc) return rc;
+    cudaEventRecord(c->ev[AVS_STAGE_DOWNLOAD], c->stream);
+    if (!out->on_device)
+        for (int a = 0; a < 3; ++a)
+            AVS_CUDA_CHECK(cudaMemcpyAsync(out->vel[a], dOut[a], c->S.regular[a].count() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    cudaEventRecord(c->ev[AVS_STAGE_DOWNLOAD + 1], c->stream);
+    collectStageTimes(c, res, AVS_STAGE_APPLY, AVS_STAGE_DOWNLOAD);
+    for (int a = 0; a < 3; ++a) tmp[a].release();
+    res->kernel_launches = c->launches;
+    res->pending_interpolated_faces = (int64_t)pending;
+    return AVS_OK;
+}
+
+extern "C" {
+
+int avs_assemble(AvsContext *c, const AvsFields *in, const AvsParams *p, AvsResult *res) {
+    if (!c || !res || res->size != sizeof(AvsResult)) return AVS_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(c->device);
+    memset(res->stage_ms, 0, sizeof(res->stage_ms));
+    c->launches = 0;
+    c->spmvLaunches = 0;
+    int rc = runAssemble(c, in, p, res);
+    res->status = rc;
+    return rc;
+}
+
+int avs_solve_resident(AvsContext *c, const AvsParams *p, AvsResult *res) {
+    if (!c || !p || p->size != sizeof(AvsParams) || !res || res->size != sizeof(AvsResult)) return AVS_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(c->device);
+    fillCounts(c, res);
+    int rc = runSolve(c, p, res);
+    res->status = rc;
+    return rc;
+}
+
+int avs_apply(AvsContext *c, AvsVelocityOut *out, AvsResult *res) {
+    if (!c || !res || res->size != sizeof(AvsResult)) return AVS_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(c->device);
+    int rc = runApply(c, out, res);
+    res->status = rc;
+    return rc;
+}
+
+int avs_solve(AvsContext *c, const AvsFields *in, const AvsParams *p, AvsVelocityOut *out, AvsResult *res) {
+    if (!c || !res || res->size != sizeof(AvsResult)) return AVS_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(c->device);
+    memset(res->stage_ms, 0, sizeof(res->stage_ms));
+    c->launches = 0;
+    c->spmvLaunches = 0;
+    int rc = runAssemble(c, in, p, res);
+    if (rc == AVS_OK) rc = runSolve(c, p, res);
+    if (rc == AVS_OK && out) rc = runApply(c, out, res);
+    res->status = rc;
+    return rc;
+}
+
+// ---- read-back ------------------------------------------------------------------------------
+int avs_get_sizes(AvsContext *c, int64_t *nRows, int64_t *nnz, int32_t *levels) {
+    if (!c) return AVS_ERR_INVALID_ARGUMENT;
+    if (nRows) *nRows = c->nRows;
+    if (nnz) *nnz = c->nnz;
+    if (levels) *levels = c->S.levels;
+    return AVS_OK;
+}
+
+int avs_get_keys(AvsContext *c, int32_t *keys) {
+    if (!c || !keys) return AVS_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(c->device);
+    AVS_CUDA_CHECK(cudaMemcpyAsync(keys, c->rowKeys.p, (size_t)c->nRows * sizeof(RowKey), cudaMemcpyDeviceToHost, c->stream));
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return AVS_OK;
+}
+
+int avs_get_system_csr(AvsContext *c, int64_t *rowPtr, int32_t *col, double *val, double *rhs, double *x0) {
+    if (!c || !c->haveSystem) return AVS_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(c->device);
+    const long long n = c->rowEnd - c->rowBegin;
+    if (rowPtr) AVS_CUDA_CHECK(cudaMemcpyAsync(rowPtr, c->csrPtr.p, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    if (col) AVS_CUDA_CHECK(cudaMemcpyAsync(col, c->csrCol.p, (size_t)c->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (val) AVS_CUDA_CHECK(cudaMemcpyAsync(val, c->csrVal.p, (size_t)c->nnz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (rhs) AVS_CUDA_CHECK(cudaMemcpyAsync(rhs, c->rhs.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (x0) AVS_CUDA_CHECK(cudaMemcpyAsync(x0, c->x0.p, (size_t)c->nRows * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return AVS_OK;
+}
+
+int avs_get_solution(AvsContext *c, double *x) {
+    if (!c || !c->haveSolution || !x) return AVS_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(c->device);
+    AVS_CUDA_CHECK(cudaMemcpyAsync(x, c->solution.p, (size_t)(c->rowEnd - c->rowBegin) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return AVS_OK;
+}
+
+int avs_get_grid(AvsContext *c, int kind, int level, int axis, void *out, int32_t *res, int64_t *nbytes) {
+    if (!c || axis < 0 || axis > 2) return AVS_ERR_INVALID_ARGUMENT;
+    if (kind >= 0 && kind <= 3 && (level < 0 || level >= c->S.levels)) return AVS_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(c->device);
+    const DeviceScene &S = c->S;
+    const void *src = nullptr;
+    const int *n = nullptr;
+    size_t elem = 1;
+    switch (kind) {
+        case 0: src = S.label[level].d; n = S.label[level].n; elem = 1; break;
+        case 1: src = S.face[level][axis].d; n = S.face[level][axis].n; elem = 4; break;
+        case 2: src = S.edge[level][axis].d; n = S.edge[level][axis].n; elem = 1; break;
+        case 3: src = S.center[level].d; n = S.center[level].n; elem = 1; break;
+        case 4: src = S.regular[axis].d; n = S.regular[axis].n; elem = 1; break;
+        case 5: src = S.centerW.d; n = S.centerW.n; elem = 4; break;
+        case 6: src = S.edgeW[axis].d; n = S.edgeW[axis].n; elem = 4; break;
+        default: return AVS_ERR_INVALID_ARGUMENT;
+    }
+    if (!src) return AVS_ERR_INVALID_ARGUMENT;
+    size_t bytes = (size_t)n[0] * n[1] * n[2] * elem;
+    if (res) { res[0] = n[0]; res[1] = n[1]; res[2] = n[2]; }
+    if (nbytes) *nbytes = (int64_t)bytes;
+    if (out) {
+        AVS_CUDA_CHECK(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+        AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+    return AVS_OK;
+}
+
+// ---- stand-alone linear algebra on a caller CSR ---------------------------------------------
+static int uploadCsr(AvsContext *c, int64_t n, const int64_t *rowPtr, const int32_t *col, const double *val, int precision) {
+    if (n < 0 || !rowPtr) return AVS_ERR_INVALID_ARGUMENT;
+    const int64_t nnz = rowPtr[n];
+    if (nnz > 0 && (!col || !val)) return AVS_ERR_INVALID_ARGUMENT;
+    if (c->csrPtr.reserve((size_t)(n + 1) * sizeof(int64_t)) || c->csrCol.reserve((size_t)std::max<int64_t>(nnz, 1) * sizeof(int32_t)) ||
+        c->csrVal.reserve((size_t)std::max<int64_t>(nnz, 1) * sizeof(double)))
+        return AVS_ERR_ALLOC;
+    AVS_CUDA_CHECK(cudaMemcpyAsync(c->csrPtr.p, rowPtr, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    if (nnz > 0) {
+        AVS_CUDA_CHECK(cudaMemcpyAsync(c->csrCol.p, col, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        AVS_CUDA_CHECK(cudaMemcpyAsync(c->csrVal.p, val, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
+    c->nRows = n;
+    c->nnz = nnz;
+    c->rowBegin = 0;
+    c->rowEnd = n;
+    c->haveSystem = false;  // no geometry behind this matrix
+    c->haveSolution = false;
+    return avs_sell_from_csr(c, c->A, n, c->csrPtr.as<int64_t>(), c->csrCol.as<int32_t>(), c->csrVal.as<double>(), precision);
+}
+
+int avs_cg_csr(AvsContext *c, int64_t n, const int64_t *rowPtr, const int32_t *col, const double *val, const double *rhs, double *x,
+               const AvsParams *p, AvsResult *res) {
+    if (!c || !p || p->size != sizeof(AvsParams) || !res || res->size != sizeof(AvsResult) || !rhs || !x) return AVS_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(c->device);
+    memset(res->stage_ms, 0, sizeof(res->stage_ms));
+    c->launches = 0;
+    c->spmvLaunches = 0;
+    int rc = uploadCsr(c, n, rowPtr, col, val, p->precision);
+    if (rc) { res->status = rc; return rc; }
+    const size_t vb = (size_t)std::max<int64_t>(n, 1) * sizeof(double);
+    if (c->rhs.reserve(vb) || c->x0.reserve(vb) || c->solution.reserve(vb)) return AVS_ERR_ALLOC;
+    AVS_CUDA_CHECK(cudaMemcpyAsync(c->rhs.p, rhs, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    AVS_CUDA_CHECK(cudaMemcpyAsync(c->x0.p, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    c->spmvEventsUsed = 0;
+    cudaEventRecord(c->ev[AVS_STAGE_SOLVE], c->stream);
+    rc = avs_cg_run(c, c->A, c->rhs.as<double>(), c->x0.as<double>(), c->solution.as<double>(), p, res);
+    cudaEventRecord(c->ev[AVS_STAGE_SOLVE + 1], c->stream);
+    collectStageTimes(c, res, AVS_STAGE_SOLVE, AVS_STAGE_SOLVE);
+    AVS_CUDA_CHECK(cudaMemcpyAsync(x, c->solution.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    res->octree_dofs = n;
+    res->nnz = c->nnz;
+    res->local_rows = n;
+    res->kernel_launches = c->launches;
+    res->spmv_launches = c->spmvLaunches;
+    res->status = rc;
+    return rc;
+}
+
+int avs_spmv_csr(AvsContext *c, int64_t n, const int64_t *rowPtr, const int32_t *col, const double *val, const double *x, double *y,
+                 int precision, int repeats, float *msPerLaunch) {
+    if (!c || !x || !y) return AVS_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(c->device);
+    int rc = uploadCsr(c, n, rowPtr, col, val, precision);
+    if (rc) return rc;
+    const size_t vb = (size_t)std::max<int64_t>(n, 1) * sizeof(double);
+    if (c->x0.reserve(vb) || c->solution.reserve(vb)) return AVS_ERR_ALLOC;
+    AVS_CUDA_CHECK(cudaMemcpyAsync(c->x0.p, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    rc = avs_spmv_once(c, c->A, c->x0.as<double>(), c->solution.as<double>());
+    if (rc) return rc;
+    AVS_CUDA_CHECK(cudaMemcpyAsync(y, c->solution.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (repeats > 0 && msPerLaunch) rc = avs_spmv_time(c, c->A, repeats, msPerLaunch);
+    return rc;
+}
+
+int avs_time_spmv_resident(AvsContext *c, int precision, int repeats, float *msPerLaunch, double *algorithmicBytes) {
+    if (!c || !msPerLaunch || c->A.n == 0) return AVS_ERR_INVALID_ARGUMENT;
+    (void)precision;
+    cudaSetDevice(c->device);
+    const double s = c->A.precision == AVS_PRECISION_F32 ? 4.0 : 8.0;
+    if (algorithmicBytes) *algorithmicBytes = (double)c->A.nnz * (s + 4.0) + (double)(c->A.n + 1) * 4.0 + 2.0 * (double)c->A.n * s;
+    return avs_spmv_time(c, c->A, repeats, msPerLaunch);
+}
+
+}  // extern "C"

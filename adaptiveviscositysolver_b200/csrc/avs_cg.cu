@@ -1,0 +1,512 @@
+// avs_cg.cu -- stage 10: the Jacobi-preconditioned conjugate-gradient solve the reference hands to
+// Eigen::ConjugateGradient<SparseMatrix<SolveType>, Lower|Upper> (HDK_AdaptiveViscosity.cpp:611-630).
+// The iteration follows upstream Eigen's conjugate_gradient() + DiagonalPreconditioner exactly
+// (SURVEY.md section 8a row a15), including "break before the iteration counter is bumped".
+//
+// Matrix format: SJDS-32 ("sliced jagged diagonals, paired").  Rows are grouped in slices of 32
+// (one warp); inside a slice rows are sorted by length, and the slice stores, for pair index j, the
+// c_j rows that still have entries -- contiguously, no padding.  One lane owns one row and reads
+// two consecutive non-zeros per step with one 128-bit value load and one 64-bit column load; the
+// loads of a warp are one contiguous segment.  Rows of this system have 2..46 entries (mean ~16),
+// so a padded ELL/SELL layout would move ~1.6x the bytes (measured on the oracle's matrices).
+//
+// Per CG iteration: 3 kernels (SpMV + p.Ap | x,r update + r.r, r.z | p update), all scalars stay on
+// the device, dot products are reduced per CTA and finished in fixed order by the consumer kernel
+// (deterministic, no atomics), convergence is a device-side flag that turns later launches into
+// no-ops, so the host only polls every `check_every` iterations without changing the result.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+
+#include "avs_context.h"
+
+#define CG_THREADS 256
+#define CG_CTAS_PER_SM 8
+
+// ---- SJDS build ---------------------------------------------------------------------------------
+// meta[slice*32 + q] = (original lane << 8) | number of pairs, q = position after sorting by length
+__global__ void k_sjds_count(long long n, const long long *ptr, long long nslices, int32_t *meta, int32_t *slicePairs) {
+    long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (s >= nslices) return;
+    long long r = s * 32 + lane;
+    int len = (r < n) ? (int)(ptr[r + 1] - ptr[r]) : 0;
+    int np = (len + 1) >> 1;
+    int rank = 0, total = 0;
+    for (int o = 0; o < 32; ++o) {
+        int other = __shfl_sync(0xffffffffu, np, o);
+        rank += (other > np) || (other == np && o < lane);
+        total += other;
+    }
+    meta[s * 32 + rank] = (lane << 8) | np;
+    if (lane == 0) slicePairs[s] = total;
+}
+
+template <class T, class T2>
+__global__ void k_sjds_fill(long long n, const long long *ptr, const int32_t *col, const double *val, long long nslices,
+                            const int32_t *meta, const long long *sliceOff, T2 *val2, int2 *col2) {
+    long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (s >= nslices) return;
+    int m = meta[s * 32 + lane];
+    int np = m & 0xff, orig = m >> 8;
+    long long r = s * 32 + orig;
+    long long p0 = (r < n) ? ptr[r] : 0;
+    int len = (r < n) ? (int)(ptr[r + 1] - p0) : 0;
+    long long base = sliceOff[s];
+    int maxnp = __shfl_sync(0xffffffffu, np, 0);
+    long long off = 0;
+    for (int j = 0; j < maxnp; ++j) {
+        bool active = j < np;
+        int cnt = __popc(__ballot_sync(0xffffffffu, active));
+        if (active) {
+            int k0 = 2 * j, k1 = 2 * j + 1;
+            T2 v;
+            int2 cc;
+            v.x = (T)val[p0 + k0];
+            cc.x = col[p0 + k0];
+            if (k1 < len) { v.y = (T)val[p0 + k1]; cc.y = col[p0 + k1]; }
+            else { v.y = (T)0; cc.y = cc.x; }  // odd row length: a zero paired with a harmless column
+            val2[base + off + lane] = v;
+            col2[base + off + lane] = cc;
+        }
+        off += cnt;
+    }
+}
+
+// DiagonalPreconditioner::factorize: invdiag = 1/A_jj when the diagonal exists and is non-zero, else 1
+template <class T>
+__global__ void k_inv_diag(long long n, const long long *ptr, const int32_t *col, const double *val, long long colOfRow0, T *invDiag) {
+    long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    double d = 0;
+    bool found = false;
+    for (long long k = ptr[r]; k < ptr[r + 1]; ++k)
+        if (col[k] == (int32_t)(r + colOfRow0)) { d = val[k]; found = true; break; }
+    invDiag[r] = (found && d != 0.0) ? (T)(1.0 / d) : (T)1;
+}
+
+int avs_sell_from_csr(AvsContext *c, SellMatrix &A, int64_t n, const int64_t *dPtr, const int32_t *dCol, const double *dVal,
+                      int precision) {
+    A.n = n;
+    A.precision = precision;
+    A.nslices = (n + 31) / 32;
+    const size_t vs = precision == AVS_PRECISION_F32 ? sizeof(float) : sizeof(double);
+    DevBuf pairs;
+    if (A.sliceOff.reserve((size_t)(A.nslices + 1) * sizeof(long long))) return AVS_ERR_ALLOC;
+    if (pairs.reserve((size_t)std::max<int64_t>(A.nslices, 1) * sizeof(int32_t))) return AVS_ERR_ALLOC;
+    if (A.meta.reserve((size_t)std::max<int64_t>(A.nslices, 1) * 32 * sizeof(int32_t))) return AVS_ERR_ALLOC;
+    int32_t *dMeta = A.meta.as<int32_t>();
+    if (A.invDiag.reserve((size_t)std::max<int64_t>(n, 1) * vs)) return AVS_ERR_ALLOC;
+    A.nnz = 0;
+    A.padded = 0;
+    if (n == 0) return AVS_OK;
+    unsigned blocks = (unsigned)((A.nslices * 32 + 255) / 256);
+    k_sjds_count<<<blocks, 256, 0, c->stream>>>(n, (const long long *)dPtr, A.nslices, dMeta, pairs.as<int32_t>());
+    ++c->launches;
+    int64_t totalPairs = 0;
+    int rc = avs_exclusive_scan_i32_to_i64(c, pairs.as<int32_t>(), A.sliceOff.as<int64_t>(), A.nslices, &totalPairs);
+    if (rc) return rc;
+    AVS_CUDA_CHECK(cudaMemcpyAsync(A.sliceOff.as<long long>() + A.nslices, &totalPairs, sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    long long nnz = 0;
+    AVS_CUDA_CHECK(cudaMemcpyAsync(&nnz, (const long long *)dPtr + n, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    A.nnz = nnz;
+    A.padded = totalPairs * 2;
+    if (A.val.reserve((size_t)std::max<int64_t>(totalPairs, 1) * 2 * vs)) return AVS_ERR_ALLOC;
+    if (A.col.reserve((size_t)std::max<int64_t>(totalPairs, 1) * sizeof(int2))) return AVS_ERR_ALLOC;
+    if (precision == AVS_PRECISION_F32) {
+        k_sjds_fill<float, float2><<<blocks, 256, 0, c->stream>>>(n, (const long long *)dPtr, dCol, dVal, A.nslices, dMeta,
+                                                                 A.sliceOff.as<long long>(), A.val.as<float2>(), A.col.as<int2>());
+        k_inv_diag<float><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, (const long long *)dPtr, dCol, dVal, 0, A.invDiag.as<float>());
+    } else {
+        k_sjds_fill<double, double2><<<blocks, 256, 0, c->stream>>>(n, (const long long *)dPtr, dCol, dVal, A.nslices, dMeta,
+                                                                   A.sliceOff.as<long long>(), A.val.as<double2>(), A.col.as<int2>());
+        k_inv_diag<double><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, (const long long *)dPtr, dCol, dVal, 0, A.invDiag.as<double>());
+    }
+    c->launches += 2;
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    AVS_CUDA_CHECK(cudaGetLastError());
+    pairs.release();
+    return AVS_OK;
+}
+
+// ---- block reduction helpers -------------------------------------------------------------------
+__device__ __forceinline__ double warpSum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+// sum over the CTA; result valid in thread 0
+__device__ __forceinline__ double blockSum(double v, double *sh /* [CG_THREADS/32] */) {
+    v = warpSum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0;
+    if (threadIdx.x == 0)
+        for (int i = 0; i < CG_THREADS / 32; ++i) t += sh[i];
+    return t;
+}
+// every thread of the CTA gets sum(parts[0..n)) in a fixed order (independent of gridDim of the consumer)
+__device__ __forceinline__ double reduceParts(const double *parts, int n, double *sh /* [CG_THREADS/32 + 1] */) {
+    double v = 0;
+    for (int i = threadIdx.x; i < n; i += CG_THREADS) v += parts[i];
+    v = warpSum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int i = 0; i < CG_THREADS / 32; ++i) t += sh[i];
+        sh[CG_THREADS / 32] = t;
+    }
+    __syncthreads();
+    return sh[CG_THREADS / 32];
+}
+
+// device-resident CG state
+struct CgScalars {
+    double rho[2];        // absNew, double buffered by iteration parity
+    double threshold;     // max(tol^2 |b|^2, min)
+    double rhsNorm2;
+    double residualNorm2;
+    int done;             // 1 once |r|^2 < threshold (or breakdown / zero rhs)
+    int iters;            // Eigen's `i`
+    int breakdown;
+    int zeroRhs;
+};
+
+// ---- SpMV: y = A x, fused partial dot x.y -------------------------------------------------------
+template <class T, class T2, bool DOT>
+__global__ void __launch_bounds__(CG_THREADS) k_spmv_sjds(long long nrows, long long nslices, const long long *__restrict__ sliceOff,
+                                                          const int32_t *__restrict__ meta, const T2 *__restrict__ val2,
+                                                          const int2 *__restrict__ col2, const T *__restrict__ x, T *__restrict__ y,
+                                                          double *__restrict__ parts, const CgScalars *sc) {
+    if (sc && sc->done) return;
+    __shared__ double sh[CG_THREADS / 32 + 1];
+    const int lane = threadIdx.x & 31;
+    const long long warpsTotal = ((long long)gridDim.x * CG_THREADS) >> 5;
+    double dot = 0;
+    for (long long s = ((long long)blockIdx.x * CG_THREADS + threadIdx.x) >> 5; s < nslices; s += warpsTotal) {
+        const int m = meta[s * 32 + lane];
+        const int np = m & 0xff;
+        const long long r = s * 32 + (m >> 8);
+        const long long base = sliceOff[s] + lane;
+        const int maxnp = __shfl_sync(0xffffffffu, np, 0);
+        T acc = 0;
+        long long off = 0;
+#pragma unroll 4
+        for (int j = 0; j < maxnp; ++j) {
+            const bool active = j < np;
+            const int cnt = __popc(__ballot_sync(0xffffffffu, active));
+            if (active) {
+                const T2 v = val2[base + off];
+                const int2 cc = col2[base + off];
+                acc += v.x * __ldg(x + cc.x);
+                acc += v.y * __ldg(x + cc.y);
+            }
+            off += cnt;
+        }
+        if (r < nrows) {
+            y[r] = acc;
+            if (DOT) dot += (double)__ldg(x + r) * (double)acc;
+        }
+    }
+    if (DOT) {
+        double t = blockSum(dot, sh);
+        if (threadIdx.x == 0) parts[blockIdx.x] = t;
+    }
+}
+
+// ---- CG vector kernels --------------------------------------------------------------------------
+// init: r = b - t (t = A x0), p = invdiag r; partial b.b, r.r, r.p
+template <class T>
+__global__ void __launch_bounds__(CG_THREADS) k_cg_init(long long n, const T *__restrict__ b, const T *__restrict__ t, const T *__restrict__ invDiag,
+                                                        T *__restrict__ r, T *__restrict__ p, double *parts, int nparts) {
+    __shared__ double sh[CG_THREADS / 32 + 1];
+    double bb = 0, rr = 0, rp = 0;
+    for (long long i = (long long)blockIdx.x * CG_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * CG_THREADS) {
+        T bi = b[i];
+        T ri = bi - t[i];
+        T pi = invDiag[i] * ri;
+        r[i] = ri;
+        p[i] = pi;
+        bb += (double)bi * (double)bi;
+        rr += (double)ri * (double)ri;
+        rp += (double)ri * (double)pi;
+    }
+    double s0 = blockSum(bb, sh), s1 = blockSum(rr, sh), s2 = blockSum(rp, sh);
+    if (threadIdx.x == 0) {
+        parts[blockIdx.x] = s0;
+        parts[nparts + blockIdx.x] = s1;
+        parts[2 * nparts + blockIdx.x] = s2;
+    }
+}
+__global__ void __launch_bounds__(CG_THREADS) k_cg_init_scalars(const double *parts, int nparts, double tol, double tiny, CgScalars *sc) {
+    __shared__ double sh[CG_THREADS / 32 + 1];
+    double bb = reduceParts(parts, nparts, sh);
+    double rr = reduceParts(parts + nparts, nparts, sh);
+    double rp = reduceParts(parts + 2 * nparts, nparts, sh);
+    if (threadIdx.x == 0) {
+        sc->rhsNorm2 = bb;
+        sc->residualNorm2 = rr;
+        sc->rho[0] = rp;
+        sc->rho[1] = rp;
+        sc->iters = 0;
+        sc->breakdown = 0;
+        sc->zeroRhs = 0;
+        sc->done = 0;
+        double thr = tol * tol * bb;
+        if (thr < tiny) thr = tiny;
+        sc->threshold = thr;
+        if (bb == 0) { sc->zeroRhs = 1; sc->done = 1; sc->residualNorm2 = 0; }  // Eigen: x = 0, 0 iterations
+        else if (rr < thr) sc->done = 1;
+    }
+}
+// x += alpha p; r -= alpha t; partial r.r and r.z with z = invdiag r
+template <class T>
+__global__ void __launch_bounds__(CG_THREADS) k_cg_update_xr(long long n, const T *__restrict__ p, const T *__restrict__ t,
+                                                             const T *__restrict__ invDiag, T *__restrict__ x, T *__restrict__ r,
+                                                             const double *ptParts, int nptParts, double *parts, int nparts,
+                                                             CgScalars *sc, int parity) {
+    if (sc->done) return;
+    __shared__ double sh[CG_THREADS / 32 + 1];
+    const double pt = reduceParts(ptParts, nptParts, sh);
+    const double alphaD = sc->rho[parity] / pt;
+    if (!isfinite(alphaD)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) sc->breakdown = 1;  // becomes `done` in k_cg_update_p
+        // fall through with a harmless alpha so every CTA takes the same path
+    }
+    const T alpha = isfinite(alphaD) ? (T)alphaD : (T)0;
+    double rr = 0, rz = 0;
+    for (long long i = (long long)blockIdx.x * CG_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * CG_THREADS) {
+        T pi = p[i];
+        T ri = r[i] - alpha * t[i];
+        x[i] += alpha * pi;
+        r[i] = ri;
+        T zi = invDiag[i] * ri;
+        rr += (double)ri * (double)ri;
+        rz += (double)ri * (double)zi;
+    }
+    double s0 = blockSum(rr, sh), s1 = blockSum(rz, sh);
+    if (threadIdx.x == 0) {
+        parts[blockIdx.x] = s0;
+        parts[nparts + blockIdx.x] = s1;
+    }
+}
+// convergence test, then p = z + beta p
+template <class T>
+__global__ void __launch_bounds__(CG_THREADS) k_cg_update_p(long long n, const T *__restrict__ r, const T *__restrict__ invDiag, T *__restrict__ p,
+                                                            const double *parts, int nparts, CgScalars *sc, int parity) {
+    if (sc->done) return;
+    __shared__ double sh[CG_THREADS / 32 + 1];
+    const double rr = reduceParts(parts, nparts, sh);
+    const double rz = reduceParts(parts + nparts, nparts, sh);
+    const bool stop = (rr < sc->threshold) || sc->breakdown;
+    const double beta = rz / sc->rho[parity];
+    __syncthreads();
+    // CTA 0 publishes the new state.  No other CTA reads residualNorm2 / rho[parity^1] / iters in this
+    // kernel; `done` is only ever written when `stop` holds, and then every CTA returns without touching
+    // p whether it saw the old or the new value of `done`.
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc->residualNorm2 = rr;
+        sc->rho[parity ^ 1] = rz;
+        if (stop) sc->done = 1;       // Eigen: break before ++i
+        else sc->iters += 1;
+    }
+    if (stop) return;
+    const T b = (T)beta;
+    for (long long i = (long long)blockIdx.x * CG_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * CG_THREADS)
+        p[i] = invDiag[i] * r[i] + b * p[i];
+}
+
+template <class T>
+__global__ void k_convert_in(long long n, const double *in, T *out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (T)in[i];
+}
+template <class T>
+__global__ void k_convert_out(long long n, const T *in, double *out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)in[i];
+}
+
+template <class T, class T2, bool DOT>
+static void launchSpmv(AvsContext *c, SellMatrix &A, const T *x, T *y, double *parts, const CgScalars *sc, int grid) {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->timeSpmv && c->spmvEventsUsed + 2 <= c->spmvEvents.size()) {
+        e0 = c->spmvEvents[c->spmvEventsUsed++];
+        e1 = c->spmvEvents[c->spmvEventsUsed++];
+        cudaEventRecord(e0, c->stream);
+    }
+    k_spmv_sjds<T, T2, DOT><<<grid, CG_THREADS, 0, c->stream>>>(A.n, A.nslices, A.sliceOff.as<long long>(), A.meta.as<int32_t>(),
+                                                                 A.val.as<T2>(), A.col.as<int2>(), x, y, parts, sc);
+    if (e1) cudaEventRecord(e1, c->stream);
+    ++c->launches;
+    ++c->spmvLaunches;
+}
+
+static int cgGrid(AvsContext *c, long long n) {
+    long long want = (n + CG_THREADS - 1) / CG_THREADS;
+    long long cap = (long long)c->numSMs * CG_CTAS_PER_SM;
+    return (int)std::max<long long>(1, std::min(want, cap));
+}
+
+template <class T, class T2>
+static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double *dX0, double *dXout, const AvsParams *p, AvsResult *res) {
+    const long long n = A.n;
+    CgWork &w = c->cg;
+    const int grid = cgGrid(c, n);
+    const size_t vb = (size_t)std::max<long long>(n, 1) * sizeof(T);
+    if (w.x.reserve(vb) || w.r.reserve(vb) || w.p.reserve(vb) || w.t.reserve(vb)) return AVS_ERR_ALLOC;
+    DevBuf &bbuf = c->cgRhs;
+    if (bbuf.reserve(vb)) return AVS_ERR_ALLOC;
+    if (w.partials.reserve((size_t)grid * 4 * sizeof(double))) return AVS_ERR_ALLOC;
+    if (w.scalars.reserve(sizeof(CgScalars))) return AVS_ERR_ALLOC;
+    T *x = w.x.as<T>(), *r = w.r.as<T>(), *pp = w.p.as<T>(), *t = w.t.as<T>(), *b = bbuf.as<T>();
+    double *parts = w.partials.as<double>();
+    double *ptParts = parts + 3 * (size_t)grid;
+    CgScalars *sc = w.scalars.as<CgScalars>();
+    res->iterations = 0;
+    res->error = 0;
+    if (n == 0) return AVS_OK;
+    const unsigned eb = (unsigned)((n + 255) / 256);
+    k_convert_in<T><<<eb, 256, 0, c->stream>>>(n, dRhs, b);
+    k_convert_in<T><<<eb, 256, 0, c->stream>>>(n, dX0, x);
+    c->launches += 2;
+    // residual = rhs - A x0 (Eigen: VectorType residual = rhs - mat * x)
+    AVS_CUDA_CHECK(cudaMemsetAsync(sc, 0, sizeof(CgScalars), c->stream));
+    launchSpmv<T, T2, false>(c, A, x, t, nullptr, nullptr, grid);
+    k_cg_init<T><<<grid, CG_THREADS, 0, c->stream>>>(n, b, t, A.invDiag.as<T>(), r, pp, parts, grid);
+    const double tiny = (sizeof(T) == 4) ? (double)FLT_MIN : DBL_MIN;
+    k_cg_init_scalars<<<1, CG_THREADS, 0, c->stream>>>(parts, grid, p->tolerance, tiny, sc);
+    c->launches += 2;
+
+    const int maxIters = p->max_iterations;
+    int checkEvery = p->check_every > 0 ? p->check_every : 32;
+    CgScalars *hs = (CgScalars *)c->hostScalars;  // pinned
+    int launched = 0;
+    bool done = false;
+    // the flag copy of batch k is awaited only after batch k+1 has been enqueued, so the GPU never idles
+    cudaEvent_t evPrev = nullptr;
+    int slot = 0;
+    while (!done) {
+        int batch = std::min(checkEvery, maxIters - launched);
+        for (int it = 0; it < batch; ++it) {
+            const int parity = (launched + it) & 1;
+            launchSpmv<T, T2, true>(c, A, pp, t, ptParts, sc, grid);
+            k_cg_update_xr<T><<<grid, CG_THREADS, 0, c->stream>>>(n, pp, t, A.invDiag.as<T>(), x, r, ptParts, grid, parts, grid, sc, parity);
+            k_cg_update_p<T><<<grid, CG_THREADS, 0, c->stream>>>(n, r, A.invDiag.as<T>(), pp, parts, grid, sc, parity);
+            c->launches += 3;
+        }
+        launched += batch;
+        AVS_CUDA_CHECK(cudaMemcpyAsync(&hs[slot], sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, c->stream));
+        AVS_CUDA_CHECK(cudaEventRecord(c->evPoll[slot], c->stream));
+        if (evPrev) {
+            AVS_CUDA_CHECK(cudaEventSynchronize(evPrev));
+            if (hs[slot ^ 1].done) done = true;
+        }
+        evPrev = c->evPoll[slot];
+        slot ^= 1;
+        if (launched >= maxIters || batch == 0) {
+            AVS_CUDA_CHECK(cudaEventSynchronize(evPrev));
+            break;
+        }
+        if (p->cancel && *p->cancel) {
+            AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            return AVS_ERR_CANCELLED;
+        }
+    }
+    AVS_CUDA_CHECK(cudaMemcpyAsync(&hs[0], sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, c->stream));
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    CgScalars fin = hs[0];
+    if (fin.zeroRhs) {
+        AVS_CUDA_CHECK(cudaMemsetAsync(dXout, 0, (size_t)n * sizeof(double), c->stream));
+        res->iterations = 0;
+        res->error = 0;
+        return AVS_OK;
+    }
+    k_convert_out<T><<<eb, 256, 0, c->stream>>>(n, x, dXout);
+    ++c->launches;
+    res->iterations = fin.iters;
+    res->error = std::sqrt(fin.residualNorm2 / fin.rhsNorm2);
+    AVS_CUDA_CHECK(cudaGetLastError());
+    if (fin.breakdown) return AVS_ERR_BREAKDOWN;
+    return AVS_OK;
+}
+
+int avs_cg_run(AvsContext *c, SellMatrix &A, const double *dRhs, const double *dX0, double *dXout, const AvsParams *p, AvsResult *res) {
+    if (A.precision == AVS_PRECISION_F32) return cgRunT<float, float2>(c, A, dRhs, dX0, dXout, p, res);
+    return cgRunT<double, double2>(c, A, dRhs, dX0, dXout, p, res);
+}
+
+// y = A x once (parity tests)
+int avs_spmv_once(AvsContext *c, SellMatrix &A, const double *dX, double *dY) {
+    const long long n = A.n;
+    if (n == 0) return AVS_OK;
+    const int grid = cgGrid(c, n);
+    const unsigned eb = (unsigned)((n + 255) / 256);
+    if (A.precision == AVS_PRECISION_F32) {
+        DevBuf xb, yb;
+        if (xb.reserve((size_t)n * 4) || yb.reserve((size_t)n * 4)) return AVS_ERR_ALLOC;
+        k_convert_in<float><<<eb, 256, 0, c->stream>>>(n, dX, xb.as<float>());
+        launchSpmv<float, float2, false>(c, A, xb.as<float>(), yb.as<float>(), nullptr, nullptr, grid);
+        k_convert_out<float><<<eb, 256, 0, c->stream>>>(n, yb.as<float>(), dY);
+        AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        xb.release();
+        yb.release();
+    } else {
+        launchSpmv<double, double2, false>(c, A, dX, dY, nullptr, nullptr, grid);
+        AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+    AVS_CUDA_CHECK(cudaGetLastError());
+    return AVS_OK;
+}
+
+// Times `repeats` launches of the CG's SpMV (with the fused dot, as in the solve) with CUDA events
+// on the library stream.  x is filled with ones; the matrix is far larger than L2 for the bench configs.
+template <class T>
+__global__ void k_fill(long long n, T v, T *out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+int avs_spmv_time(AvsContext *c, SellMatrix &A, int repeats, float *msPerLaunch) {
+    const long long n = A.n;
+    *msPerLaunch = 0;
+    if (n == 0 || repeats <= 0) return AVS_OK;
+    const int grid = cgGrid(c, n);
+    const size_t vs = A.precision == AVS_PRECISION_F32 ? 4 : 8;
+    CgWork &w = c->cg;
+    if (w.p.reserve((size_t)n * vs) || w.t.reserve((size_t)n * vs) || w.partials.reserve((size_t)grid * 4 * sizeof(double))) return AVS_ERR_ALLOC;
+    const unsigned eb = (unsigned)((n + 255) / 256);
+    bool saved = c->timeSpmv;
+    c->timeSpmv = false;
+    cudaEvent_t e0, e1;
+    AVS_CUDA_CHECK(cudaEventCreate(&e0));
+    AVS_CUDA_CHECK(cudaEventCreate(&e1));
+    for (int pass = 0; pass < 2; ++pass) {  // pass 0 = warm-up
+        int reps = pass == 0 ? 3 : repeats;
+        if (pass == 1) AVS_CUDA_CHECK(cudaEventRecord(e0, c->stream));
+        for (int i = 0; i < reps; ++i) {
+            if (A.precision == AVS_PRECISION_F32) {
+                if (pass == 0 && i == 0) k_fill<float><<<eb, 256, 0, c->stream>>>(n, 1.f, w.p.as<float>());
+                launchSpmv<float, float2, true>(c, A, w.p.as<float>(), w.t.as<float>(), w.partials.as<double>(), nullptr, grid);
+            } else {
+                if (pass == 0 && i == 0) k_fill<double><<<eb, 256, 0, c->stream>>>(n, 1.0, w.p.as<double>());
+                launchSpmv<double, double2, true>(c, A, w.p.as<double>(), w.t.as<double>(), w.partials.as<double>(), nullptr, grid);
+            }
+        }
+        if (pass == 1) AVS_CUDA_CHECK(cudaEventRecord(e1, c->stream));
+    }
+    AVS_CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0;
+    AVS_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    *msPerLaunch = ms / (float)repeats;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    c->timeSpmv = saved;
+    AVS_CUDA_CHECK(cudaGetLastError());
+    return AVS_OK;
+}

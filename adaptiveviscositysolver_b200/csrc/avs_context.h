@@ -1,0 +1,119 @@
+// avs_context.h -- host-side state of one solver context (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/avs.h"
+#include "avs_common.cuh"
+
+// Growable device buffer: allocations are cached in the context across solves (the reference
+// rebuilds everything per call, HDK_AdaptiveViscosity.cpp:233-707; here only the contents are).
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            cudaGetLastError();
+            if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); p = nullptr; return -1; }
+            want = bytes;
+        }
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+// SJDS-32 "paired" sparse matrix (layout described at the top of avs_cg.cu).
+struct SellMatrix {
+    int64_t n = 0;          // rows (local)
+    int64_t nnz = 0;        // true non-zeros (for the roofline figure)
+    int64_t nslices = 0;
+    int64_t padded = 0;     // stored entries
+    DevBuf sliceOff;        // int64[nslices+1], in pairs
+    DevBuf val;             // double2 / float2 [padded/2]
+    DevBuf col;             // int2 [padded/2]
+    DevBuf invDiag;         // Jacobi preconditioner (DiagonalPreconditioner)
+    DevBuf meta;            // int32[nslices*32]: (original lane << 8) | pairs, per sorted lane
+    int precision = AVS_PRECISION_F64;
+};
+
+struct CgWork {
+    DevBuf x, r, p, t;      // CG vectors
+    DevBuf partials;        // per-CTA partial sums
+    DevBuf scalars;         // device-resident CG scalars
+};
+
+struct AvsContext {
+    int device = 0;
+    int rank = 0, nranks = 1;
+    void *nccl = nullptr;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    bool timeSpmv = false;
+    int numSMs = 148;
+    std::string lastError;
+
+    // ---- device copies of the inputs
+    DevBuf inSurface, inVel[3], inFaceW[3], inVisc, inDens, inColl, inCollVel[3];
+    // ---- stage outputs
+    DevBuf centerW, edgeW[3];
+    DevBuf label[AVS_MAX_LEVELS], face[AVS_MAX_LEVELS][3], edge[AVS_MAX_LEVELS][3], center[AVS_MAX_LEVELS], regular[3];
+    DevBuf tiles;           // tile-occupancy scratch
+    DevBuf brickCount, brickOffset, scanTmp, counters;
+    DevBuf rowKeys;         // RowKey[n]
+    DevBuf x0, rhs, solution;  // fp64 [n]
+    DevBuf rowCount, rowOffset; // assembly scratch (int32 / int64)
+    DevBuf csrPtr, csrCol, csrVal;  // canonical CSR of the local rows (int64 / int32 / fp64)
+    DeviceScene S;          // host copy of the descriptor handed to kernels
+    bool haveSystem = false, haveSolution = false;
+
+    int levelsAllocated = 0;
+    int64_t nRows = 0, nnz = 0, nEdge = 0, nCenter = 0, nRegular = 0;
+    int64_t rowBegin = 0, rowEnd = 0;  // rows owned by this rank
+
+    SellMatrix A;
+    CgWork cg;
+    DevBuf cgRhs;
+    void *hostScalars = nullptr;   // pinned, 2 x CgScalars
+    cudaEvent_t evPoll[2] = {};
+    std::vector<cudaEvent_t> spmvEvents;  // pairs, only when timeSpmv
+    size_t spmvEventsUsed = 0;
+
+    int64_t launches = 0, spmvLaunches = 0;
+    float spmvMs = 0.f;
+    cudaEvent_t ev[AVS_STAGE_COUNT + 2] = {};
+};
+
+// stage entry points implemented in the .cu files
+int avs_stage_upload(AvsContext *c, const AvsFields *in, const AvsParams *p);
+int avs_stage_weights(AvsContext *c, const AvsParams *p);
+int avs_stage_octree(AvsContext *c, const AvsParams *p);
+int avs_stage_regular_labels(AvsContext *c);
+int avs_stage_octree_labels(AvsContext *c);
+int avs_stage_restriction(AvsContext *c);
+int avs_stage_system(AvsContext *c, const AvsParams *p);
+int avs_stage_solve(AvsContext *c, const AvsParams *p, AvsResult *res);
+int avs_apply_regular(AvsContext *c, float *dOut[3], unsigned long long *hostPending);
+
+int avs_sell_from_csr(AvsContext *c, SellMatrix &A, int64_t n, const int64_t *dPtr, const int32_t *dCol,
+                      const double *dVal, int precision);
+int avs_cg_run(AvsContext *c, SellMatrix &A, const double *dRhs, const double *dX0, double *dXout,
+               const AvsParams *p, AvsResult *res);
+int avs_spmv_time(AvsContext *c, SellMatrix &A, int repeats, float *msPerLaunch);
+int avs_spmv_once(AvsContext *c, SellMatrix &A, const double *dX, double *dY);
+
+// generic device helpers (avs_labels.cu)
+int avs_exclusive_scan_i32_to_i64(AvsContext *c, const int32_t *dIn, int64_t *dOut, int64_t n, int64_t *hostTotal);

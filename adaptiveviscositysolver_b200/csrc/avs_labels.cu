@@ -1,0 +1,763 @@
+// avs_labels.cu -- stages 1-5 of the viscosity solve on the GPU:
+//   integration weights  (HDK_AdaptiveViscosity.cpp:712-791)
+//   refinement mask + octree label pyramid (HDK_AdaptiveViscosity.cpp:793-871, HDK_OctreeGrid.cpp:4-243)
+//   regular-grid face labels (HDK_AdaptiveViscosity.cpp:1087-1165, 1445-1512)
+//   octree face / edge / centre labels + DOF numbering (HDK_AdaptiveViscosity.cpp:1167-1443, 1514-1715)
+//
+// All kernels are streaming passes over dense x-fastest grids (HBM-bound, coalesced along x).
+// The reference's serial numbering sweeps (AV.cpp:1563-1591) become count -> scan -> assign over
+// 8^3-cell bricks in Morton order, so consecutive rows are spatial neighbours (SpMV gather locality).
+// Compiled with -fmad=false: sign tests on interpolated SDF values must round like the CPU oracle.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "avs_context.h"
+
+#define LAUNCH_1D(ctx, kernel, count, ...)                                                     \
+    do {                                                                                       \
+        size_t _n = (size_t)(count);                                                           \
+        if (_n > 0) {                                                                          \
+            unsigned _b = (unsigned)((_n + 255) / 256);                                        \
+            kernel<<<_b, 256, 0, (ctx)->stream>>>(__VA_ARGS__);                                \
+            ++(ctx)->launches;                                                                 \
+        }                                                                                      \
+    } while (0)
+
+static_assert(sizeof(DeviceScene) <= 4000, "DeviceScene must fit the kernel parameter space");
+
+// ------------------------------------------------------------------------------------------------
+// Stage 1: computeSDFWeightsSampled restated: fraction of the n^3 sub-samples at
+// offsets ((k+1/2)/n - 1/2) dx whose interpolated sdf (minus dilate) is negative.
+// Early-out: the trilinear interpolant is a convex combination of the voxels it touches, so when
+// every voxel under the sample's box has the same sign the count is n^3 or 0 without sampling.
+__global__ void k_sdf_weights(Grid3<float> w, DField sdf, double off0, double off1, double off2, double o0,
+                              double o1, double o2, double dx0, int n, double dilate) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= w.count()) return;
+    int x = (int)(idx % w.n[0]);
+    int y = (int)((idx / w.n[0]) % w.n[1]);
+    int z = (int)(idx / ((size_t)w.n[0] * w.n[1]));
+    double c[3] = {o0 + (x + off0) * dx0, o1 + (y + off1) * dx0, o2 + (z + off2) * dx0};
+    if (!sdf.d) {
+        w.d[idx] = ((double)sdf.constant - dilate < 0.0) ? 1.f : 0.f;
+        return;
+    }
+    const double inv = 1.0 / (double)n;
+    const double h = (0.5 - 0.5 * inv) * dx0;
+    int lo[3], hi[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double gl = (c[a] - h - sdf.org[a]) / sdf.dx - 1e-9;
+        double gh = (c[a] + h - sdf.org[a]) / sdf.dx + 1e-9;
+        double top = (double)(sdf.n[a] - 1);
+        gl = fmin(fmax(gl, 0.0), top);
+        gh = fmin(fmax(gh, 0.0), top);
+        lo[a] = (int)floor(gl);
+        hi[a] = min((int)floor(gh) + 1, sdf.n[a] - 1);
+    }
+    bool allNeg = true, allPos = true;
+    const float dl = (float)dilate;  // exact for dilate == 0; conservative test below otherwise
+    for (int kz = lo[2]; kz <= hi[2]; ++kz)
+        for (int ky = lo[1]; ky <= hi[1]; ++ky)
+            for (int kx = lo[0]; kx <= hi[0]; ++kx) {
+                double v = (double)sdf.d[(size_t)kx + (size_t)sdf.n[0] * ((size_t)ky + (size_t)sdf.n[1] * kz)] - dilate;
+                allNeg = allNeg && (v < 0.0);
+                allPos = allPos && (v >= 0.0);
+            }
+    (void)dl;
+    if (allNeg) { w.d[idx] = 1.f; return; }
+    if (allPos) { w.d[idx] = 0.f; return; }
+    int count = 0;
+    for (int sz = 0; sz < n; ++sz)
+        for (int sy = 0; sy < n; ++sy)
+            for (int sx = 0; sx < n; ++sx) {
+                double p[3] = {c[0] + ((sx + 0.5) * inv - 0.5) * dx0, c[1] + ((sy + 0.5) * inv - 0.5) * dx0,
+                               c[2] + ((sz + 0.5) * inv - 0.5) * dx0};
+                if (sdf.value(p) - dilate < 0.0) ++count;
+            }
+    const double total = (double)n * n * n;
+    w.d[idx] = (float)((double)count / total);
+}
+
+// setScaleDivideThreshold(1, nullptr, &b, 0): a /= b where b > 0 (AV.cpp:781-789)
+__global__ void k_divide_where_positive(float *a, const float *b, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && b[i] > 0.f) a[i] = a[i] / b[i];
+}
+
+static int weightsFor(AvsContext *c, DevBuf &buf, Grid3<float> &g, const DField &sdf, const double off[3],
+                      const int res[3], int n, double dilate) {
+    g.n[0] = res[0]; g.n[1] = res[1]; g.n[2] = res[2];
+    if (buf.reserve(g.count() * sizeof(float))) return AVS_ERR_ALLOC;
+    g.d = buf.as<float>();
+    LAUNCH_1D(c, k_sdf_weights, g.count(), g, sdf, off[0], off[1], off[2], c->S.origin[0], c->S.origin[1],
+              c->S.origin[2], c->S.dx0, n, dilate);
+    return AVS_OK;
+}
+
+int avs_stage_weights(AvsContext *c, const AvsParams *p) {
+    DeviceScene &S = c->S;
+    const int n = p->number_super_samples;
+    const double offC[3] = {0.5, 0.5, 0.5};
+    int rc = weightsFor(c, c->centerW, S.centerW, S.surface, offC, S.N, n, 0.0);
+    if (rc) return rc;
+    for (int a = 0; a < 3; ++a) {
+        double off[3] = {0, 0, 0};
+        off[a] = 0.5;  // an a-directed edge is centred along a only (HDK_Utilities.h:13-15)
+        int res[3] = {S.N[0] + 1, S.N[1] + 1, S.N[2] + 1};
+        res[a] -= 1;
+        rc = weightsFor(c, c->edgeW[a], S.edgeW[a], S.surface, off, res, n, 0.0);
+        if (rc) return rc;
+    }
+    if (p->do_apply_solid_weights) {  // AV.cpp:772-790
+        DevBuf tmp;
+        Grid3<float> g;
+        rc = weightsFor(c, tmp, g, S.collision, offC, S.N, n, -S.extrap);
+        if (rc) return rc;
+        LAUNCH_1D(c, k_divide_where_positive, g.count(), S.centerW.d, g.d, g.count());
+        for (int a = 0; a < 3; ++a) {
+            double off[3] = {0, 0, 0};
+            off[a] = 0.5;
+            rc = weightsFor(c, tmp, g, S.collision, off, S.edgeW[a].n, n, -S.extrap);
+            if (rc) return rc;
+            LAUNCH_1D(c, k_divide_where_positive, g.count(), S.edgeW[a].d, g.d, g.count());
+        }
+        AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        tmp.release();
+    }
+    AVS_CUDA_CHECK(cudaGetLastError());
+    return AVS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 2+3a: refinement mask (AV.cpp:839-860) fused with setBaseGridLabels (OG.cpp:310-392):
+// mask 0 -> ACTIVE, < 0 -> UP, > 0 (or outside the un-padded grid) -> INACTIVE.
+__global__ void k_base_labels(const __grid_constant__ DeviceScene S, double inner, double outer) {
+    const Grid3<uint8_t> lab = S.label[0];
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= lab.count()) return;
+    int x = (int)(idx % lab.n[0]);
+    int y = (int)((idx / lab.n[0]) % lab.n[1]);
+    int z = (int)(idx / ((size_t)lab.n[0] * lab.n[1]));
+    uint8_t out = L_INACTIVE;
+    if (x < S.N[0] && y < S.N[1] && z < S.N[2]) {
+        double sdf = (double)S.surface.raw(x, y, z);
+        if (sdf > 0 && sdf < outer) out = L_ACTIVE;
+        else if (sdf <= 0.) {
+            if (sdf > -inner) out = L_ACTIVE;
+            else {
+                double p[3];
+                S.centerPos(mk3(x, y, z), 0, p);
+                out = (S.collision.value(p) > (-inner - S.extrap)) ? L_ACTIVE : L_UP;
+            }
+        }
+    }
+    lab.d[idx] = out;
+}
+
+// pass 1, setActiveCellsAndParentList (OG.cpp:394-565): one thread per 2x2x2 sibling block.
+__global__ void k_octree_pass1(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= par.count()) return;
+    int px = (int)(idx % par.n[0]);
+    int py = (int)((idx / par.n[0]) % par.n[1]);
+    int pz = (int)(idx / ((size_t)par.n[0] * par.n[1]));
+    uint8_t v[8];
+    bool any = false;
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+        v[ch] = cur.d[cur.lin(2 * px + (ch & 1), 2 * py + ((ch >> 1) & 1), 2 * pz + (ch >> 2))];
+        any = any || (v[ch] == L_ACTIVE);
+    }
+    if (!any) return;
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch)
+        if (v[ch] == L_UP) cur.d[cur.lin(2 * px + (ch & 1), 2 * py + ((ch >> 1) & 1), 2 * pz + (ch >> 2))] = L_ACTIVE;
+    par.d[idx] = L_DOWN;
+}
+
+// pass 2, setFaceGrading (OG.cpp:656-754). The reference applies its DOWN list before its ACTIVE
+// list (OG.cpp:145, 162); two kernels keep that order.
+__global__ void k_octree_pass2_down(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= cur.count()) return;
+    if (cur.d[idx] != L_DOWN) return;
+    int x = (int)(idx % cur.n[0]);
+    int y = (int)((idx / cur.n[0]) % cur.n[1]);
+    int z = (int)(idx / ((size_t)cur.n[0] * cur.n[1]));
+    par.d[par.lin(x >> 1, y >> 1, z >> 1)] = L_DOWN;
+}
+__global__ void k_octree_pass2_active(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= cur.count()) return;
+    if (cur.d[idx] != L_ACTIVE) return;
+    I3 c = mk3((int)(idx % cur.n[0]), (int)((idx / cur.n[0]) % cur.n[1]), (int)(idx / ((size_t)cur.n[0] * cur.n[1])));
+#pragma unroll
+    for (int axis = 0; axis < 3; ++axis)
+#pragma unroll
+        for (int dir = 0; dir < 2; ++dir) {
+            I3 a = cellToCell(c, axis, dir);
+            if (a[axis] < 0 || a[axis] >= cur.n[axis]) continue;
+            if (cur.at(a) == L_UP) par.d[par.lin(a[0] >> 1, a[1] >> 1, a[2] >> 1)] = L_ACTIVE;
+        }
+}
+// pass 3, setParentsUp (OG.cpp:756-840)
+__global__ void k_octree_pass3(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= cur.count()) return;
+    if (cur.d[idx] != L_UP) return;
+    int x = (int)(idx % cur.n[0]);
+    int y = (int)((idx / cur.n[0]) % cur.n[1]);
+    int z = (int)(idx / ((size_t)cur.n[0] * cur.n[1]));
+    size_t pi = par.lin(x >> 1, y >> 1, z >> 1);
+    if (par.d[pi] == L_INACTIVE) par.d[pi] = L_UP;
+}
+// setTopLevel (OG.cpp:843-875)
+__global__ void k_octree_top(Grid3<uint8_t> g) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < g.count() && g.d[idx] == L_UP) g.d[idx] = L_ACTIVE;
+}
+
+template <class T>
+__global__ void k_count_equal(const T *d, size_t n, T value, unsigned long long *counter) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool hit = idx < n && d[idx] == value;
+    unsigned m = __ballot_sync(0xffffffffu, hit);
+    __shared__ int s[8];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < 8; ++i) t += s[i];
+        if (t) atomicAdd(counter, (unsigned long long)t);
+    }
+}
+template <class T>
+__global__ void k_count_nonneg(const T *d, size_t n, unsigned long long *counter) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool hit = idx < n && d[idx] >= 0;
+    unsigned m = __ballot_sync(0xffffffffu, hit);
+    __shared__ int s[8];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < 8; ++i) t += s[i];
+        if (t) atomicAdd(counter, (unsigned long long)t);
+    }
+}
+
+static int ilog2(int v) {
+    int l = 0;
+    while ((1 << (l + 1)) <= v) ++l;
+    return l;
+}
+
+int avs_stage_octree(AvsContext *c, const AvsParams *p) {
+    DeviceScene &S = c->S;
+    for (int a = 0; a < 3; ++a) {  // OG.cpp:18-24
+        int pad = 1;
+        while (pad < S.N[a]) pad <<= 1;
+        S.Pad[a] = pad;
+    }
+    int L = p->octree_levels;  // OG.cpp:32-40
+    for (int a = 0; a < 3; ++a) L = std::min(L, ilog2(S.Pad[a]));
+    if (L < 1) L = 1;
+    if (L > AVS_MAX_LEVELS) L = AVS_MAX_LEVELS;
+    c->levelsAllocated = L;
+    for (int l = 0; l < L; ++l) {
+        Grid3<uint8_t> &g = S.label[l];
+        for (int a = 0; a < 3; ++a) g.n[a] = S.Pad[a] >> l;
+        if (c->label[l].reserve(g.count())) return AVS_ERR_ALLOC;
+        g.d = c->label[l].as<uint8_t>();
+        if (l > 0) AVS_CUDA_CHECK(cudaMemsetAsync(g.d, L_INACTIVE, g.count(), c->stream));
+    }
+    const double fineVoxelWidth = std::max(2.0, (double)p->fine_bandwidth);  // AV.cpp:259
+    const double inner = S.dx0 * fineVoxelWidth, outer = 3.0 * S.dx0;         // AV.cpp:261-262
+    LAUNCH_1D(c, k_base_labels, S.label[0].count(), S, inner, outer);
+    for (int l = 0; l < L - 1; ++l) {
+        Grid3<uint8_t> cur = S.label[l], par = S.label[l + 1];
+        LAUNCH_1D(c, k_octree_pass1, par.count(), cur, par);
+        if (l > 0) LAUNCH_1D(c, k_octree_pass2_down, cur.count(), cur, par);
+        LAUNCH_1D(c, k_octree_pass2_active, cur.count(), cur, par);
+        LAUNCH_1D(c, k_octree_pass3, cur.count(), cur, par);
+    }
+    LAUNCH_1D(c, k_octree_top, S.label[L - 1].count(), S.label[L - 1]);
+    // level capping (OG.cpp:198-211): first level without an ACTIVE cell
+    if (c->counters.reserve(64 * sizeof(unsigned long long))) return AVS_ERR_ALLOC;
+    unsigned long long *cnt = c->counters.as<unsigned long long>();
+    AVS_CUDA_CHECK(cudaMemsetAsync(cnt, 0, 64 * sizeof(unsigned long long), c->stream));
+    for (int l = 0; l < L; ++l)
+        LAUNCH_1D(c, k_count_equal<uint8_t>, S.label[l].count(), S.label[l].d, S.label[l].count(), (uint8_t)L_ACTIVE, cnt + l);
+    unsigned long long h[AVS_MAX_LEVELS];
+    AVS_CUDA_CHECK(cudaMemcpyAsync(h, cnt, L * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    int capped = 0;
+    for (; capped < L; ++capped)
+        if (h[capped] == 0) break;
+    S.levels = capped;
+    return AVS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 4/5: labelling.  The reference only classifies inside 16^3 tiles it found "occupied"
+// (findOccupied*Tiles, AV.cpp:886-1057); everything else keeps UNASSIGNED.  Tile maps are uint8.
+__device__ __forceinline__ void markTile(const Grid3<uint8_t> &t, const I3 &c) {
+    t.d[t.lin(c[0] / AVS_TILE, c[1] / AVS_TILE, c[2] / AVS_TILE)] = 1;
+}
+__device__ __forceinline__ bool tileOccupied(const Grid3<uint8_t> &t, int x, int y, int z) {
+    return t.d[t.lin(x / AVS_TILE, y / AVS_TILE, z / AVS_TILE)] != 0;
+}
+
+// findOccupiedRegularVelocityTiles (AV.cpp:886-943): both faces of every cell with sdf < 2 dx
+__global__ void k_mark_surface_tiles(const __grid_constant__ DeviceScene S, Grid3<uint8_t> t0, Grid3<uint8_t> t1,
+                                     Grid3<uint8_t> t2) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t n = (size_t)S.N[0] * S.N[1] * S.N[2];
+    if (idx >= n) return;
+    int x = (int)(idx % S.N[0]);
+    int y = (int)((idx / S.N[0]) % S.N[1]);
+    int z = (int)(idx / ((size_t)S.N[0] * S.N[1]));
+    if (!((double)S.surface.raw(x, y, z) < 2.0 * S.dx0)) return;
+    I3 c = mk3(x, y, z);
+    markTile(t0, c); markTile(t0, cellToFace(c, 0, 1));
+    markTile(t1, c); markTile(t1, cellToFace(c, 1, 1));
+    markTile(t2, c); markTile(t2, cellToFace(c, 2, 1));
+}
+
+// face activity test shared by AV.cpp:1127-1150 and AV.cpp:1235-1258
+__device__ __forceinline__ bool faceHasWeight(const DeviceScene &S, const I3 &face, int axis) {
+    I3 b = faceToCell(face, axis, 0), f = faceToCell(face, axis, 1);
+    if (S.centerW.get(b) > 0.f || S.centerW.get(f) > 0.f) return true;
+#pragma unroll
+    for (int ea = 0; ea < 3; ++ea) {
+        if (ea == axis) continue;
+#pragma unroll
+        for (int dir = 0; dir < 2; ++dir)
+            if (S.edgeW[ea].get(faceToEdge(face, axis, ea, dir)) > 0.f) return true;
+    }
+    return false;
+}
+
+// classifyRegularVelocityFaces (AV.cpp:1087-1165)
+__global__ void k_classify_regular(const __grid_constant__ DeviceScene S, int axis, Grid3<uint8_t> tiles) {
+    const Grid3<int8_t> g = S.regular[axis];
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= g.count()) return;
+    int x = (int)(idx % g.n[0]);
+    int y = (int)((idx / g.n[0]) % g.n[1]);
+    int z = (int)(idx / ((size_t)g.n[0] * g.n[1]));
+    int8_t out = F_UNASSIGNED;
+    I3 face = mk3(x, y, z);
+    if (tileOccupied(tiles, x, y, z) && face[axis] - 1 >= 0 && face[axis] < S.N[axis]) {
+        if (faceHasWeight(S, face, axis)) {
+            double p[3];
+            S.facePos(face, axis, 0, p);
+            out = (S.collision.value(p) > -S.extrap) ? F_SOLID : F_FLUID;
+        }
+    }
+    g.d[idx] = out;
+}
+
+// classifyOctreeVelocityFaces (AV.cpp:1167-1323)
+__global__ void k_classify_faces(const __grid_constant__ DeviceScene S, int level, int axis, Grid3<uint8_t> tiles) {
+    const Grid3<int32_t> g = S.face[level][axis];
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= g.count()) return;
+    int x = (int)(idx % g.n[0]);
+    int y = (int)((idx / g.n[0]) % g.n[1]);
+    int z = (int)(idx / ((size_t)g.n[0] * g.n[1]));
+    int32_t out = F_UNASSIGNED;
+    I3 face = mk3(x, y, z);
+    const Grid3<uint8_t> &lab = S.label[level];
+    const int vr = (level == 0) ? S.N[axis] : lab.n[axis];  // AV.cpp:1185-1189
+    if (level > 0 || tileOccupied(tiles, x, y, z)) {
+        I3 b = faceToCell(face, axis, 0), f = face;
+        if (b[axis] < 0 || f[axis] >= vr) {
+            if (level == 0) out = F_OUTSIDE;  // AV.cpp:1210-1215
+        } else {
+            const int bl = lab.get(b), fl = lab.get(f);
+            if (level == 0) {
+                if (bl == L_ACTIVE && fl == L_ACTIVE) {
+                    if (faceHasWeight(S, face, axis)) {
+                        double p[3];
+                        S.facePos(face, axis, 0, p);
+                        out = (S.collision.value(p) > -S.extrap) ? F_SOLID : F_FLUID;
+                    } else out = F_OUTSIDE;
+                } else if (bl == L_INACTIVE || fl == L_INACTIVE) out = F_OUTSIDE;
+                else if ((bl == L_UP && fl == L_ACTIVE) || (bl == L_ACTIVE && fl == L_UP)) out = F_FLUID;
+            } else if ((bl == L_ACTIVE && fl == L_ACTIVE) || (bl == L_UP && fl == L_ACTIVE) || (bl == L_ACTIVE && fl == L_UP))
+                out = F_FLUID;
+        }
+    }
+    g.d[idx] = out;
+}
+
+// findOccupiedEdgeStressTiles (AV.cpp:1002-1057): the 4 a-edges of every ACTIVE cell, a = 0,1,2
+__global__ void k_mark_edge_tiles(Grid3<uint8_t> lab, Grid3<uint8_t> t0, Grid3<uint8_t> t1, Grid3<uint8_t> t2) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= lab.count()) return;
+    if (lab.d[idx] != L_ACTIVE) return;
+    I3 c = mk3((int)(idx % lab.n[0]), (int)((idx / lab.n[0]) % lab.n[1]), (int)(idx / ((size_t)lab.n[0] * lab.n[1])));
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        markTile(t0, cellToEdge(c, 0, e));
+        markTile(t1, cellToEdge(c, 1, e));
+        markTile(t2, cellToEdge(c, 2, e));
+    }
+}
+
+// classifyEdgeStresses (AV.cpp:1325-1405)
+__global__ void k_classify_edges(const __grid_constant__ DeviceScene S, int level, int axis, Grid3<uint8_t> tiles) {
+    const Grid3<int8_t> g = S.edge[level][axis];
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= g.count()) return;
+    int x = (int)(idx % g.n[0]);
+    int y = (int)((idx / g.n[0]) % g.n[1]);
+    int z = (int)(idx / ((size_t)g.n[0] * g.n[1]));
+    int8_t out = F_UNASSIGNED;
+    if (tileOccupied(tiles, x, y, z)) {
+        const Grid3<uint8_t> &lab = S.label[level];
+        I3 edge = mk3(x, y, z);
+        int vr[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) vr[a] = (level == 0) ? S.N[a] : lab.n[a];  // AV.cpp:1340-1344
+        bool active = false;
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+            I3 cc = edgeToCell(edge, axis, ci);
+            if (cc[0] < 0 || cc[1] < 0 || cc[2] < 0 || cc[0] >= vr[0] || cc[1] >= vr[1] || cc[2] >= vr[2]) {
+                out = F_OUTSIDE;  // AV.cpp:1365-1370 (isStressActive keeps its value, as in the reference)
+                break;
+            }
+            uint8_t l = lab.get(cc);
+            if (l == L_DOWN) { active = false; break; }
+            else if (l == L_ACTIVE) active = true;
+        }
+        if (active) {
+            if (level == 0) out = (S.edgeW[axis].get(edge) > 0.f) ? F_FLUID : F_OUTSIDE;
+            else out = F_FLUID;
+        }
+    }
+    g.d[idx] = out;
+}
+
+// classifyCenterStresses (AV.cpp:1407-1443)
+__global__ void k_classify_centers(const __grid_constant__ DeviceScene S, int level) {
+    const Grid3<int8_t> g = S.center[level];
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= g.count()) return;
+    int8_t out = F_UNASSIGNED;
+    if (S.label[level].d[idx] == L_ACTIVE) {
+        if (level != 0) out = F_FLUID;
+        else {
+            I3 c = mk3((int)(idx % g.n[0]), (int)((idx / g.n[0]) % g.n[1]), (int)(idx / ((size_t)g.n[0] * g.n[1])));
+            if (S.centerW.get(c) > 0.f) out = F_FLUID;
+        }
+    }
+    g.d[idx] = out;
+}
+
+static int tileGrid(AvsContext *c, DevBuf &buf, Grid3<uint8_t> t[3], const int res[3][3]) {
+    size_t total = 0, off[3];
+    for (int a = 0; a < 3; ++a) {
+        for (int k = 0; k < 3; ++k) t[a].n[k] = (res[a][k] + AVS_TILE - 1) / AVS_TILE;
+        off[a] = total;
+        total += (t[a].count() + 255) / 256 * 256;
+    }
+    if (buf.reserve(total)) return AVS_ERR_ALLOC;
+    for (int a = 0; a < 3; ++a) t[a].d = buf.as<uint8_t>() + off[a];
+    AVS_CUDA_CHECK(cudaMemsetAsync(buf.p, 0, total, c->stream));
+    return AVS_OK;
+}
+
+int avs_stage_regular_labels(AvsContext *c) {
+    DeviceScene &S = c->S;
+    int res[3][3];
+    for (int a = 0; a < 3; ++a) {
+        for (int k = 0; k < 3; ++k) { S.regular[a].n[k] = S.N[k] + (k == a); res[a][k] = S.Pad[k] + 1; }
+        if (c->regular[a].reserve(S.regular[a].count())) return AVS_ERR_ALLOC;
+        S.regular[a].d = c->regular[a].as<int8_t>();
+    }
+    // One tile map per axis, dimensioned for the padded face grids; tile coordinates (idx/16) are the
+    // same for the regular grid and for octree level 0, so stage 5 reuses these maps.
+    Grid3<uint8_t> t[3];
+    int rc = tileGrid(c, c->tiles, t, res);
+    if (rc) return rc;
+    LAUNCH_1D(c, k_mark_surface_tiles, (size_t)S.N[0] * S.N[1] * S.N[2], S, t[0], t[1], t[2]);
+    for (int a = 0; a < 3; ++a) LAUNCH_1D(c, k_classify_regular, S.regular[a].count(), S, a, t[a]);
+    unsigned long long *cnt = c->counters.as<unsigned long long>();
+    AVS_CUDA_CHECK(cudaMemsetAsync(cnt + 16, 0, sizeof(unsigned long long), c->stream));
+    for (int a = 0; a < 3; ++a)
+        LAUNCH_1D(c, k_count_equal<int8_t>, S.regular[a].count(), S.regular[a].d, S.regular[a].count(), (int8_t)F_FLUID, cnt + 16);
+    return AVS_OK;
+}
+
+// ---- DOF numbering: count -> scan -> assign over 8^3-cell bricks in Morton order -----------------
+struct BrickLayout {
+    int bits[AVS_MAX_LEVELS][3];   // log2(bricks per axis)
+    long long base[AVS_MAX_LEVELS + 1];
+    int levels;
+};
+#define BRICK 8
+
+__device__ __forceinline__ void brickCoord(const BrickLayout &bl, int level, long long code, int b[3]) {
+    b[0] = b[1] = b[2] = 0;
+    int bit = 0;
+    for (int k = 0; k < 10; ++k)
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            if (k < bl.bits[level][a]) {
+                b[a] |= (int)((code >> bit) & 1) << k;
+                ++bit;
+            }
+}
+
+// slot order inside a brick: cell-major (z, y, x), the three axes' faces of one cell adjacent
+__device__ __forceinline__ int brickThreadCount(const DeviceScene &S, int level, const int b[3], int t, int32_t vals[6]) {
+    int n = 0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        int cellLocal = t * 2 + q;
+        int x = b[0] * BRICK + (cellLocal & 7), y = b[1] * BRICK + ((cellLocal >> 3) & 7), z = b[2] * BRICK + (cellLocal >> 6);
+        const Grid3<uint8_t> &lab = S.label[level];
+        bool in = x < lab.n[0] && y < lab.n[1] && z < lab.n[2];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            int32_t v = F_UNASSIGNED;
+            if (in) v = S.face[level][a].d[S.face[level][a].lin(x, y, z)];
+            vals[q * 3 + a] = v;
+            n += (v >= 0);
+        }
+    }
+    return n;
+}
+
+__global__ void k_brick_count(const __grid_constant__ DeviceScene S, const __grid_constant__ BrickLayout bl, int level, int32_t *brickCount) {
+    long long code = blockIdx.x;
+    int b[3];
+    brickCoord(bl, level, code, b);
+    int32_t vals[6];
+    int n = brickThreadCount(S, level, b, threadIdx.x, vals);
+    __shared__ int s[8];
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_down_sync(0xffffffffu, n, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = n;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < 8; ++i) t += s[i];
+        brickCount[bl.base[level] + code] = t;
+    }
+}
+
+__global__ void k_brick_assign(const __grid_constant__ DeviceScene S, const __grid_constant__ BrickLayout bl, int level,
+                               const int32_t *brickCount, const long long *brickOffset, RowKey *keys) {
+    long long code = blockIdx.x;
+    if (brickCount[bl.base[level] + code] == 0) return;
+    int b[3];
+    brickCoord(bl, level, code, b);
+    int32_t vals[6];
+    int n = brickThreadCount(S, level, b, threadIdx.x, vals);
+    // block-wide exclusive scan of n
+    __shared__ int warpSum[8];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = n;
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) warpSum[wid] = inc;
+    __syncthreads();
+    int wbase = 0;
+    for (int i = 0; i < wid; ++i) wbase += warpSum[i];
+    long long idx = brickOffset[bl.base[level] + code] + wbase + inc - n;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        int cellLocal = threadIdx.x * 2 + q;
+        int x = b[0] * BRICK + (cellLocal & 7), y = b[1] * BRICK + ((cellLocal >> 3) & 7), z = b[2] * BRICK + (cellLocal >> 6);
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            if (vals[q * 3 + a] >= 0) {
+                S.face[level][a].d[S.face[level][a].lin(x, y, z)] = (int32_t)idx;
+                RowKey k;
+                k.level = level; k.axis = a; k.i = x; k.j = y; k.k = z;
+                keys[idx] = k;
+                ++idx;
+            }
+    }
+}
+
+// ---- exclusive scan int32 -> int64 (three phases, 2048 elements per block) ----------------------
+#define SCAN_BLOCK 256
+#define SCAN_ITEMS 8
+__global__ void k_scan_block_sums(const int32_t *in, long long n, long long *blockSums) {
+    long long base = (long long)blockIdx.x * SCAN_BLOCK * SCAN_ITEMS;
+    long long s = 0;
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        long long j = base + (long long)i * SCAN_BLOCK + threadIdx.x;
+        if (j < n) s += in[j];
+    }
+    __shared__ long long sh[SCAN_BLOCK];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = SCAN_BLOCK / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) blockSums[blockIdx.x] = sh[0];
+}
+__global__ void k_scan_sums_serial(long long *blockSums, long long nb, long long *total) {
+    // nb is a few thousand at most: one thread, exact and deterministic
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        long long run = 0;
+        for (long long i = 0; i < nb; ++i) {
+            long long v = blockSums[i];
+            blockSums[i] = run;
+            run += v;
+        }
+        *total = run;
+    }
+}
+__global__ void k_scan_apply(const int32_t *in, long long n, const long long *blockSums, long long *out) {
+    // each thread owns SCAN_ITEMS consecutive elements
+    long long base = (long long)blockIdx.x * SCAN_BLOCK * SCAN_ITEMS + (long long)threadIdx.x * SCAN_ITEMS;
+    long long v[SCAN_ITEMS], s = 0;
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        long long j = base + i;
+        v[i] = (j < n) ? in[j] : 0;
+        s += v[i];
+    }
+    __shared__ long long sh[SCAN_BLOCK];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over the 256 thread sums
+    for (int o = 1; o < SCAN_BLOCK; o <<= 1) {
+        long long t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    long long run = blockSums[blockIdx.x] + sh[threadIdx.x] - s;
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        long long j = base + i;
+        if (j < n) out[j] = run;
+        run += v[i];
+    }
+}
+
+int avs_exclusive_scan_i32_to_i64(AvsContext *c, const int32_t *dIn, int64_t *dOut, int64_t n, int64_t *hostTotal) {
+    if (n <= 0) { if (hostTotal) *hostTotal = 0; return AVS_OK; }
+    long long nb = (n + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS);
+    if (c->scanTmp.reserve((size_t)(nb + 1) * sizeof(long long))) return AVS_ERR_ALLOC;
+    long long *sums = c->scanTmp.as<long long>();
+    k_scan_block_sums<<<(unsigned)nb, SCAN_BLOCK, 0, c->stream>>>(dIn, n, sums);
+    k_scan_sums_serial<<<1, 32, 0, c->stream>>>(sums, nb, sums + nb);
+    k_scan_apply<<<(unsigned)nb, SCAN_BLOCK, 0, c->stream>>>(dIn, n, sums, (long long *)dOut);
+    c->launches += 3;
+    if (hostTotal) {
+        long long t = 0;
+        AVS_CUDA_CHECK(cudaMemcpyAsync(&t, sums + nb, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+        AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        *hostTotal = t;
+    }
+    return AVS_OK;
+}
+
+int avs_stage_octree_labels(AvsContext *c) {
+    DeviceScene &S = c->S;
+    const int L = S.levels;
+    // allocate + classify, level by level
+    Grid3<uint8_t> t0[3];
+    {   // level-0 face tile maps were produced by avs_stage_regular_labels and still live in c->tiles
+        int res[3][3];
+        size_t total = 0;
+        for (int a = 0; a < 3; ++a) {
+            for (int k = 0; k < 3; ++k) { res[a][k] = S.Pad[k] + 1; t0[a].n[k] = (res[a][k] + AVS_TILE - 1) / AVS_TILE; }
+            t0[a].d = c->tiles.as<uint8_t>() + total;
+            total += (t0[a].count() + 255) / 256 * 256;
+        }
+    }
+    DevBuf edgeTiles;
+    for (int l = 0; l < L; ++l) {
+        const Grid3<uint8_t> &lab = S.label[l];
+        for (int a = 0; a < 3; ++a) {
+            Grid3<int32_t> &f = S.face[l][a];
+            Grid3<int8_t> &e = S.edge[l][a];
+            for (int k = 0; k < 3; ++k) { f.n[k] = lab.n[k] + (k == a); e.n[k] = lab.n[k] + (k != a); }
+            if (c->face[l][a].reserve(f.count() * sizeof(int32_t))) return AVS_ERR_ALLOC;
+            if (c->edge[l][a].reserve(e.count())) return AVS_ERR_ALLOC;
+            f.d = c->face[l][a].as<int32_t>();
+            e.d = c->edge[l][a].as<int8_t>();
+        }
+        Grid3<int8_t> &ce = S.center[l];
+        for (int k = 0; k < 3; ++k) ce.n[k] = lab.n[k];
+        if (c->center[l].reserve(ce.count())) return AVS_ERR_ALLOC;
+        ce.d = c->center[l].as<int8_t>();
+    }
+    for (int l = 0; l < L; ++l) {
+        for (int a = 0; a < 3; ++a) LAUNCH_1D(c, k_classify_faces, S.face[l][a].count(), S, l, a, t0[a]);
+        Grid3<uint8_t> te[3];
+        int res[3][3];
+        for (int a = 0; a < 3; ++a)
+            for (int k = 0; k < 3; ++k) res[a][k] = S.edge[l][a].n[k];
+        int rc = tileGrid(c, edgeTiles, te, res);
+        if (rc) return rc;
+        LAUNCH_1D(c, k_mark_edge_tiles, S.label[l].count(), S.label[l], te[0], te[1], te[2]);
+        for (int a = 0; a < 3; ++a) LAUNCH_1D(c, k_classify_edges, S.edge[l][a].count(), S, l, a, te[a]);
+        LAUNCH_1D(c, k_classify_centers, S.center[l].count(), S, l);
+    }
+    // counts of stress DOFs (the reference numbers them, AV.cpp:1632-1715; only the counts are reported here)
+    unsigned long long *cnt = c->counters.as<unsigned long long>();
+    AVS_CUDA_CHECK(cudaMemsetAsync(cnt + 17, 0, 2 * sizeof(unsigned long long), c->stream));
+    for (int l = 0; l < L; ++l) {
+        for (int a = 0; a < 3; ++a)
+            LAUNCH_1D(c, k_count_equal<int8_t>, S.edge[l][a].count(), S.edge[l][a].d, S.edge[l][a].count(), (int8_t)F_FLUID, cnt + 17);
+        LAUNCH_1D(c, k_count_equal<int8_t>, S.center[l].count(), S.center[l].d, S.center[l].count(), (int8_t)F_FLUID, cnt + 18);
+    }
+    // numbering
+    BrickLayout bl;
+    memset(&bl, 0, sizeof(bl));
+    bl.levels = L;
+    long long total = 0;
+    for (int l = 0; l < L; ++l) {
+        long long nb = 1;
+        for (int a = 0; a < 3; ++a) {
+            int bricks = std::max(1, S.label[l].n[a] / BRICK);
+            bl.bits[l][a] = ilog2(bricks);
+            nb *= bricks;
+        }
+        bl.base[l] = total;
+        total += nb;
+    }
+    bl.base[L] = total;
+    if (c->brickCount.reserve((size_t)total * sizeof(int32_t))) return AVS_ERR_ALLOC;
+    if (c->brickOffset.reserve((size_t)total * sizeof(long long))) return AVS_ERR_ALLOC;
+    for (int l = 0; l < L; ++l) {
+        unsigned nb = (unsigned)(bl.base[l + 1] - bl.base[l]);
+        k_brick_count<<<nb, 256, 0, c->stream>>>(S, bl, l, c->brickCount.as<int32_t>());
+        ++c->launches;
+    }
+    int64_t nRows = 0;
+    int rc = avs_exclusive_scan_i32_to_i64(c, c->brickCount.as<int32_t>(), c->brickOffset.as<int64_t>(), total, &nRows);
+    if (rc) return rc;
+    c->nRows = nRows;
+    if (nRows >= (int64_t)2147483000) return AVS_ERR_UNSUPPORTED;  // int32 DOF indices
+    if (c->rowKeys.reserve((size_t)std::max<int64_t>(nRows, 1) * sizeof(RowKey))) return AVS_ERR_ALLOC;
+    for (int l = 0; l < L; ++l) {
+        unsigned nb = (unsigned)(bl.base[l + 1] - bl.base[l]);
+        k_brick_assign<<<nb, 256, 0, c->stream>>>(S, bl, l, c->brickCount.as<int32_t>(), c->brickOffset.as<long long>(),
+                                                  c->rowKeys.as<RowKey>());
+        ++c->launches;
+    }
+    unsigned long long h[3];
+    AVS_CUDA_CHECK(cudaMemcpyAsync(h, cnt + 16, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->nRegular = (int64_t)h[0];
+    c->nEdge = (int64_t)h[1];
+    c->nCenter = (int64_t)h[2];
+    edgeTiles.release();
+    AVS_CUDA_CHECK(cudaGetLastError());
+    return AVS_OK;
+}

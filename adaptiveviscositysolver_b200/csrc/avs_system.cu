@@ -1,0 +1,531 @@
+// avs_system.cu -- stages 6-9 and 11 on the GPU:
+//   stress stencils + control volumes (HDK_AdaptiveViscosity.cpp:1717-2289), evaluated on the fly
+//   restriction of u^n to the octree faces (HDK_AdaptiveViscosity.cpp:2291-2402)
+//   SPD assembly  A = M_u + sum_s w_s d_s d_s^T,  rhs  (HDK_AdaptiveViscosity.cpp:2404-2777)
+//   scatter of the solution to the regular grid (HDK_AdaptiveViscosity.cpp:2779-2894, level-0 part)
+//
+// One thread owns one matrix row (one velocity face).  The reference materialises every row of D in
+// heap arrays (AV.cpp:429-436) and merges per-thread triplet lists serially (AV.cpp:587-593, 614);
+// here a row of D is a pure function of the flattened label/index grids, so each row thread
+// re-evaluates the <= ~12 stencils that touch it, merges duplicates in registers/local memory and
+// writes its CSR segment directly (count pass -> scan -> fill pass).
+#include <algorithm>
+#include <cstdio>
+
+#include "avs_context.h"
+
+#define MAX_ROW 64
+#define MAX_STENCIL 40
+
+struct Stencil {
+    int n, nb;
+    int32_t idx[MAX_STENCIL];
+    double coef[MAX_STENCIL];
+    double bnd[8];
+    __device__ __forceinline__ void add(int32_t i, double c) {
+        if (n < MAX_STENCIL) { idx[n] = i; coef[n] = c; ++n; }
+    }
+    __device__ __forceinline__ void addB(double b) {
+        if (nb < 8) bnd[nb++] = b;
+    }
+};
+
+// getEdgeStressFaces (AV.cpp:1717-1908)
+__device__ void edgeStressFaces(const DeviceScene &S, Stencil &st, const I3 &edge, int axis, int level) {
+    st.n = st.nb = 0;
+    const double dx = S.levelDx(level);  // AV.cpp:1733
+    bool isAtTransition[3] = {false, false, false};
+    bool isFaceOutside[3] = {false, false, false};
+    float gradientDx[3] = {0.f, 0.f, 0.f};  // UT_Vector3 (float32), AV.cpp:1738
+    for (int faceAxis = 0; faceAxis < 3; ++faceAxis) {
+        if (faceAxis == axis) continue;
+        const Grid3<int32_t> &fg = S.face[level][faceAxis];
+        for (int dir = 0; dir < 2; ++dir) {
+            I3 face = edgeToFace(edge, axis, faceAxis, dir);
+            const int g = 3 - faceAxis - axis;
+            if (face[g] < 0 || face[g] >= fg.n[g]) {
+                gradientDx[g] = (float)((double)gradientDx[g] + .5 * dx);
+                isFaceOutside[g] = true;
+            } else {
+                int32_t vi = fg.get(face);
+                if (vi >= 0) gradientDx[g] = (float)((double)gradientDx[g] + .5 * dx);
+                else if (vi == F_OUTSIDE || vi == F_SOLID) {
+                    gradientDx[g] = (float)((double)gradientDx[g] + .5 * dx);
+                    isFaceOutside[g] = true;
+                } else {  // UNASSIGNED: a coarser face sits there (AV.cpp:1777-1782)
+                    gradientDx[g] = (float)((double)gradientDx[g] + dx);
+                    if (S.enhanced) isAtTransition[g] = true;
+                }
+            }
+        }
+    }
+    for (int faceAxis = 0; faceAxis < 3; ++faceAxis) {
+        if (faceAxis == axis) continue;
+        const Grid3<int32_t> &fg = S.face[level][faceAxis];
+        for (int dir = 0; dir < 2; ++dir) {
+            I3 face = edgeToFace(edge, axis, faceAxis, dir);
+            const int g = 3 - faceAxis - axis;
+            const double sign = (dir == 0) ? -1 : 1;
+            const double gdx = (double)gradientDx[g];
+            if (face[g] < 0 || face[g] >= fg.n[g]) continue;
+            int32_t vi = fg.get(face);
+            if (vi >= 0) {
+                if (isAtTransition[g] && !isFaceOutside[g]) {  // AV.cpp:1814-1824
+                    I3 sib = face;
+                    sib[axis] += (edge[axis] % 2 == 0) ? 1 : -1;
+                    int32_t si = fg.get(sib);
+                    st.add(si, .25 * sign / gdx);
+                    st.add(vi, .25 * sign / gdx);
+                } else
+                    st.add(vi, .5 * sign / gdx);
+            } else if (vi == F_UNASSIGNED) {
+                if (edge[faceAxis] % 2 != 0) {  // dangling edge, AV.cpp:1835-1884
+                    for (int off = -1; off <= 1; off += 2) {
+                        I3 of = face;
+                        of[faceAxis] += off;
+                        I3 pf = parentOf(of);
+                        int32_t pi = (level + 1 < S.levels) ? S.face[level + 1][faceAxis].get(pf) : F_OUTSIDE;
+                        if (pi >= 0) st.add(pi, .25 * sign / gdx);
+                        else if (pi == F_UNASSIGNED) {
+                            for (int ch = 0; ch < 4; ++ch) {
+                                int32_t ci = fg.get(childFace(pf, faceAxis, ch));
+                                if (ci >= 0) st.add(ci, .0625 * sign / gdx);
+                            }
+                        }
+                    }
+                } else {  // AV.cpp:1886-1894
+                    I3 pf = parentOf(face);
+                    int32_t pi = (level + 1 < S.levels) ? S.face[level + 1][faceAxis].get(pf) : F_OUTSIDE;
+                    st.add(pi, .5 * sign / gdx);
+                }
+            } else if (vi == F_SOLID) {  // AV.cpp:1896-1905: component `axis`, as written in the reference
+                double p[3];
+                S.facePos(face, faceAxis, level, p);
+                double lv = S.collisionVel[axis].value(p);
+                st.addB(.5 * sign * lv / gdx);
+            }
+        }
+    }
+}
+
+// getCenterStressFaces (AV.cpp:1910-1963)
+__device__ void centerStressFaces(const DeviceScene &S, Stencil &st, const I3 &cell, int axis, int level) {
+    st.n = st.nb = 0;
+    const double dx = S.levelDx(level);
+    for (int dir = 0; dir < 2; ++dir) {
+        I3 face = cellToFace(cell, axis, dir);
+        const double sign = (dir == 0) ? -1 : 1;
+        int32_t vi = S.face[level][axis].get(face);
+        if (vi >= 0) st.add(vi, sign / dx);
+        else if (vi == F_UNASSIGNED) {
+            if (level > 0)
+                for (int ch = 0; ch < 4; ++ch) st.add(S.face[level - 1][axis].get(childFace(face, axis, ch)), .25 * sign / dx);
+        } else if (vi == F_SOLID) {
+            double p[3];
+            S.facePos(face, axis, level, p);
+            st.addB(sign * S.collisionVel[axis].value(p) / dx);
+        }
+    }
+}
+
+// faceOctreeVolumes (AV.cpp:1965-2002)
+__device__ double faceOctreeVolume(const DeviceScene &S, const I3 &face, int axis, int level) {
+    const Grid3<uint8_t> &lab = S.label[level];
+    const double dx = (double)(1 << level);
+    double g = 0;
+    for (int dir = 0; dir < 2; ++dir) {
+        I3 c = faceToCell(face, axis, dir);
+        if (c[axis] < 0 || c[axis] >= lab.n[axis]) g += .5 * dx;
+        else {
+            uint8_t l = lab.get(c);
+            g += (l == L_ACTIVE || l == L_INACTIVE) ? .5 * dx : dx;
+        }
+    }
+    return dx * dx * g;
+}
+
+// edgeOctreeVolumes (AV.cpp:2004-2057)
+__device__ double edgeOctreeVolume(const DeviceScene &S, const I3 &edge, int axis, int level) {
+    const double dx = (double)(1 << level);
+    float v[3] = {0.f, 0.f, 0.f};
+    v[axis] = (float)dx;
+    for (int faceAxis = 0; faceAxis < 3; ++faceAxis) {
+        if (faceAxis == axis) continue;
+        const Grid3<int32_t> &fg = S.face[level][faceAxis];
+        for (int dir = 0; dir < 2; ++dir) {
+            I3 face = edgeToFace(edge, axis, faceAxis, dir);
+            const int g = 3 - faceAxis - axis;
+            if (face[g] < 0 || face[g] >= fg.n[g]) v[g] = (float)((double)v[g] + .5 * dx);
+            else {
+                int32_t vi = fg.get(face);
+                v[g] = (float)((double)v[g] + ((vi == F_UNASSIGNED) ? dx : .5 * dx));
+            }
+        }
+    }
+    return (double)(v[0] * v[1] * v[2]);
+}
+
+// stress weights: AV.cpp:2124-2155 (edges), AV.cpp:2223-2289 (centres)
+__device__ double edgeStressWeight(const DeviceScene &S, const I3 &edge, int axis, int level) {
+    double w;
+    if (level == 0) {
+        w = (double)S.edgeW[axis].get(edge);
+        if (w == 1.) w = edgeOctreeVolume(S, edge, axis, level);
+    } else w = edgeOctreeVolume(S, edge, axis, level);
+    if (!S.viscosity.d) w *= (double)S.viscosity.constant;
+    else {
+        double p[3];
+        S.edgePos(edge, axis, level, p);
+        w *= S.viscosity.value(p);
+    }
+    return 4. * S.dt * w;
+}
+__device__ double centerStressWeight(const DeviceScene &S, const I3 &cell, int level) {
+    double w;
+    if (level == 0) w = (double)S.centerW.get(cell);
+    else { double dx = (double)(1 << level); w = dx * dx * dx; }
+    if (!S.viscosity.d) w *= (double)S.viscosity.constant;
+    else {
+        double p[3];
+        S.centerPos(cell, level, p);
+        w *= S.viscosity.value(p);
+    }
+    return 2. * S.dt * w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 8: buildVelocityMapping (AV.cpp:2291-2402).  Level 0 copies the regular face value; level l
+// sums 12^l leaves with weights (1/16, 1/8, 1/16) per child and in-axis offset.
+__device__ __forceinline__ double restrictLeaf(const DeviceScene &S, int axis, int level, I3 face, long long q, double &wOut) {
+    // q enumerates the 12^level leaves in depth-first order (base-12 digits, most significant first)
+    double w = 1.0;
+    long long div = 1;
+    for (int d = 1; d < level; ++d) div *= 12;
+    for (int d = 0; d < level; ++d) {
+        int digit = (int)(q / div);
+        q -= (long long)digit * div;
+        div /= 12;
+        int ch = digit / 3, o = digit % 3 - 1;
+        face = childFace(face, axis, ch);
+        face[axis] += o;
+        w = (double)(float)(((o == 0) ? 0.125 : 0.0625) * w);  // weight kept as fpreal32 (AV.cpp:2318)
+    }
+    wOut = w;
+    return (double)S.vel[axis].raw(face[0], face[1], face[2]);
+}
+
+// levels 0 and 1: one thread per row, leaves added in the reference's order (bit-identical to the oracle)
+__global__ void k_restrict_fine(const __grid_constant__ DeviceScene S, const RowKey *keys, long long n, double *x0) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RowKey k = keys[i];
+    if (k.level > 1) return;
+    I3 face = mk3(k.i, k.j, k.k);
+    if (k.level == 0) {
+        x0[i] = 1.0 * (double)S.vel[k.axis].raw(face[0], face[1], face[2]);
+        return;
+    }
+    double acc = 0;
+    for (int q = 0; q < 12; ++q) {
+        double w;
+        double v = restrictLeaf(S, k.axis, 1, face, q, w);
+        acc += w * v;
+    }
+    x0[i] = acc;
+}
+// levels >= 2: one CTA per row, leaves strided over the threads, fixed-order tree reduction
+__global__ void k_restrict_coarse(const __grid_constant__ DeviceScene S, const RowKey *keys, const int32_t *rows, double *x0) {
+    long long i = rows[blockIdx.x];
+    RowKey k = keys[i];
+    I3 face = mk3(k.i, k.j, k.k);
+    long long leaves = 1;
+    for (int d = 0; d < k.level; ++d) leaves *= 12;
+    double acc = 0;
+    for (long long q = threadIdx.x; q < leaves; q += blockDim.x) {
+        double w;
+        double v = restrictLeaf(S, k.axis, k.level, face, q, w);
+        acc += w * v;
+    }
+    __shared__ double sh[256];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) x0[i] = sh[0];
+}
+__global__ void k_collect_coarse_rows(const RowKey *keys, long long n, int32_t *rows, unsigned long long *counter) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (keys[i].level >= 2) {
+        unsigned long long slot = atomicAdd(counter, 1ull);
+        rows[slot] = (int32_t)i;  // order is irrelevant: every row is written exactly once
+    }
+}
+
+int avs_stage_restriction(AvsContext *c) {
+    const long long n = c->nRows;
+    if (c->x0.reserve((size_t)std::max<long long>(n, 1) * sizeof(double))) return AVS_ERR_ALLOC;
+    if (n == 0) return AVS_OK;
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    k_restrict_fine<<<blocks, 256, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), n, c->x0.as<double>());
+    ++c->launches;
+    if (c->S.levels > 2) {
+        // rows of level >= 2 are few (a few percent): compact their ids, then one CTA per row
+        if (c->rowCount.reserve((size_t)n * sizeof(int32_t))) return AVS_ERR_ALLOC;
+        unsigned long long *cnt = c->counters.as<unsigned long long>() + 24;
+        AVS_CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
+        k_collect_coarse_rows<<<blocks, 256, 0, c->stream>>>(c->rowKeys.as<RowKey>(), n, c->rowCount.as<int32_t>(), cnt);
+        ++c->launches;
+        unsigned long long h = 0;
+        AVS_CUDA_CHECK(cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (h > 0) {
+            k_restrict_coarse<<<(unsigned)h, 256, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->rowCount.as<int32_t>(), c->x0.as<double>());
+            ++c->launches;
+        }
+    }
+    AVS_CUDA_CHECK(cudaGetLastError());
+    return AVS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 9: one matrix row.
+struct RowAcc {
+    int n;
+    int overflow;
+    int32_t col[MAX_ROW];
+    double val[MAX_ROW];
+    __device__ __forceinline__ void add(int32_t c, double v) {
+        for (int i = 0; i < n; ++i)
+            if (col[i] == c) { val[i] += v; return; }  // setFromTriplets sums duplicates (AV.cpp:614)
+        if (n < MAX_ROW) { col[n] = c; val[n] = v; ++n; }
+        else overflow = 1;
+    }
+};
+
+// applyToMatrix (AV.cpp:2404-2457)
+__device__ __forceinline__ void applyToMatrix(RowAcc &row, double &rhsI, double &diag, double coefficient, int32_t vi, const Stencil &st) {
+    for (int i = 0; i < st.n; ++i)
+        if (st.idx[i] == vi) { coefficient *= st.coef[i]; break; }
+    for (int i = 0; i < st.n; ++i) {
+        double el = coefficient * st.coef[i];
+        if (st.idx[i] == vi) diag += el;
+        else row.add(st.idx[i], el);
+    }
+    for (int i = 0; i < st.nb; ++i) rhsI -= coefficient * st.bnd[i];
+}
+
+// buildOctreeSystemFromStencilsPartial (AV.cpp:2459-2777) for row vi
+__device__ void buildRow(const DeviceScene &S, int32_t vi, const RowKey &k, double x0i, RowAcc &row, double &rhsI) {
+    const int level = k.level, axis = k.axis;
+    const I3 face = mk3(k.i, k.j, k.k);
+    const Grid3<uint8_t> &lab = S.label[level];
+    const Grid3<int32_t> &fgrid = S.face[level][axis];
+    double diag = 0;
+    Stencil st;
+    for (int dir = 0; dir < 2; ++dir) {
+        I3 cell = faceToCell(face, axis, dir);
+        if (cell[axis] < 0 || cell[axis] >= lab.n[axis]) continue;
+        I3 sc;
+        int sl;
+        if (lab.get(cell) == L_ACTIVE) { sc = cell; sl = level; }
+        else { sc = parentOf(cell); sl = level + 1; }  // face grading: the parent is ACTIVE (AV.cpp:2562-2572)
+        if (sl >= S.levels) continue;
+        if (S.center[sl].get(sc) >= 0) {
+            centerStressFaces(S, st, sc, axis, sl);
+            applyToMatrix(row, rhsI, diag, centerStressWeight(S, sc, sl), vi, st);
+        }
+        // T-junction ghost stresses (AV.cpp:2614-2649)
+        for (int fa = 0; fa < 3; ++fa) {
+            if (fa == axis) continue;
+            for (int fd = 0; fd < 2; ++fd) {
+                I3 af = cellToFace(sc, fa, fd);
+                if (sl > 0 && S.face[sl][fa].get(af) == F_UNASSIGNED) {
+                    const int ea = 3 - fa - axis;
+                    for (int ins = 0; ins < 2; ++ins) {
+                        I3 e = childEdgeInFace(af, fa, ea, ins);
+                        if (S.edge[sl - 1][ea].get(e) >= 0) {
+                            edgeStressFaces(S, st, e, ea, sl - 1);
+                            applyToMatrix(row, rhsI, diag, edgeStressWeight(S, e, ea, sl - 1), vi, st);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    for (int ea = 0; ea < 3; ++ea) {
+        if (ea == axis) continue;
+        const Grid3<int8_t> &eg = S.edge[level][ea];
+        for (int dir = 0; dir < 2; ++dir) {
+            I3 e = faceToEdge(face, axis, ea, dir);
+            int8_t ei = eg.get(e);
+            if (ei >= 0) {
+                if (S.enhanced) {  // AV.cpp:2664-2697
+                    const int ta = 3 - ea - axis;
+                    I3 af = face;
+                    af[ta] += (dir == 0) ? -1 : 1;
+                    if (af[ta] >= 0 && af[ta] < fgrid.n[ta] && fgrid.get(af) == F_UNASSIGNED) {
+                        I3 se = e;
+                        se[ea] += (e[ea] % 2 == 0) ? 1 : -1;
+                        if (eg.get(se) >= 0) {
+                            edgeStressFaces(S, st, se, ea, level);
+                            applyToMatrix(row, rhsI, diag, edgeStressWeight(S, se, ea, level), vi, st);
+                        }
+                    }
+                }
+                edgeStressFaces(S, st, e, ea, level);
+                applyToMatrix(row, rhsI, diag, edgeStressWeight(S, e, ea, level), vi, st);
+            } else if (ei == F_UNASSIGNED && level > 0) {  // AV.cpp:2714-2742
+                for (int ch = 0; ch < 2; ++ch) {
+                    I3 ce = childEdge(e, ea, ch);
+                    if (S.edge[level - 1][ea].get(ce) >= 0) {
+                        edgeStressFaces(S, st, ce, ea, level - 1);
+                        applyToMatrix(row, rhsI, diag, edgeStressWeight(S, ce, ea, level - 1), vi, st);
+                    }
+                }
+            }
+        }
+    }
+    // velocity control volume (AV.cpp:2748-2772)
+    double fw;
+    if (level == 0) {
+        fw = (double)S.faceW[axis].raw(face[0], face[1], face[2]);
+        if (fw == 1.) fw = faceOctreeVolume(S, face, axis, level);
+    } else fw = faceOctreeVolume(S, face, axis, level);
+    if (!S.density.d) fw *= (double)S.density.constant;
+    else {
+        double p[3];
+        S.facePos(face, axis, level, p);
+        fw *= S.density.value(p);
+    }
+    row.add(vi, fw + diag);
+    rhsI += fw * x0i;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_assemble(const __grid_constant__ DeviceScene S, const RowKey *keys, const double *x0,
+                                                  long long rowBegin, long long nLocal, int32_t *rowCount,
+                                                  const long long *rowOffset, int32_t *col, double *val, double *rhs,
+                                                  int *overflowFlag) {
+    long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nLocal) return;
+    const long long gi = rowBegin + r;
+    RowAcc row;
+    row.n = 0;
+    row.overflow = 0;
+    double rhsI = 0;
+    buildRow(S, (int32_t)gi, keys[gi], x0[gi], row, rhsI);
+    if (row.overflow) *overflowFlag = 1;
+    if (!FILL) {
+        rowCount[r] = row.n;
+        return;
+    }
+    // sort the row by column (insertion sort; rows have 2..46 entries)
+    for (int i = 1; i < row.n; ++i) {
+        int32_t cc = row.col[i];
+        double vv = row.val[i];
+        int j = i - 1;
+        while (j >= 0 && row.col[j] > cc) {
+            row.col[j + 1] = row.col[j];
+            row.val[j + 1] = row.val[j];
+            --j;
+        }
+        row.col[j + 1] = cc;
+        row.val[j + 1] = vv;
+    }
+    long long o = rowOffset[r];
+    for (int i = 0; i < row.n; ++i) {
+        col[o + i] = row.col[i];
+        val[o + i] = row.val[i];
+    }
+    rhs[r] = rhsI;
+}
+
+int avs_stage_system(AvsContext *c, const AvsParams *p) {
+    (void)p;
+    const long long n = c->nRows;
+    // row partition for the multi-GPU CG: contiguous, equal row counts
+    c->rowBegin = n * c->rank / c->nranks;
+    c->rowEnd = n * (c->rank + 1) / c->nranks;
+    const long long nLocal = c->rowEnd - c->rowBegin;
+    if (c->rowCount.reserve((size_t)std::max<long long>(nLocal, 1) * sizeof(int32_t))) return AVS_ERR_ALLOC;
+    if (c->csrPtr.reserve((size_t)(nLocal + 1) * sizeof(long long))) return AVS_ERR_ALLOC;
+    if (c->rhs.reserve((size_t)std::max<long long>(nLocal, 1) * sizeof(double))) return AVS_ERR_ALLOC;
+    int *flag = (int *)(c->counters.as<unsigned long long>() + 25);
+    AVS_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(unsigned long long), c->stream));
+    c->nnz = 0;
+    if (nLocal > 0) {
+        unsigned blocks = (unsigned)((nLocal + 127) / 128);
+        k_assemble<false><<<blocks, 128, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->x0.as<double>(), c->rowBegin, nLocal,
+                                                         c->rowCount.as<int32_t>(), nullptr, nullptr, nullptr, nullptr, flag);
+        ++c->launches;
+        int64_t nnz = 0;
+        int rc = avs_exclusive_scan_i32_to_i64(c, c->rowCount.as<int32_t>(), c->csrPtr.as<int64_t>(), nLocal, &nnz);
+        if (rc) return rc;
+        c->nnz = nnz;
+        AVS_CUDA_CHECK(cudaMemcpyAsync(c->csrPtr.as<long long>() + nLocal, &c->nnz, sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+        if (c->csrCol.reserve((size_t)std::max<int64_t>(nnz, 1) * sizeof(int32_t))) return AVS_ERR_ALLOC;
+        if (c->csrVal.reserve((size_t)std::max<int64_t>(nnz, 1) * sizeof(double))) return AVS_ERR_ALLOC;
+        k_assemble<true><<<blocks, 128, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->x0.as<double>(), c->rowBegin, nLocal,
+                                                        c->rowCount.as<int32_t>(), c->csrPtr.as<long long>(), c->csrCol.as<int32_t>(),
+                                                        c->csrVal.as<double>(), c->rhs.as<double>(), flag);
+        ++c->launches;
+        int h = 0;
+        AVS_CUDA_CHECK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (h) {
+            c->lastError = "a matrix row exceeded MAX_ROW entries";
+            return AVS_ERR_UNSUPPORTED;
+        }
+    } else {
+        long long z = 0;
+        AVS_CUDA_CHECK(cudaMemcpyAsync(c->csrPtr.p, &z, sizeof(z), cudaMemcpyHostToDevice, c->stream));
+    }
+    AVS_CUDA_CHECK(cudaGetLastError());
+    c->haveSystem = true;
+    c->haveSolution = false;
+    return AVS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 11 (level-0 part of applyVelocitiesToRegularGrid, AV.cpp:2815-2894): regular faces with a
+// co-located octree DOF take the solution, SOLIDBOUNDARY faces take the solid velocity.  Regular
+// faces that sit inside a coarse cell (octree label UNASSIGNED) need the octree interpolator
+// (HDK_OctreeVectorFieldInterpolator) and are counted, not written.
+__global__ void k_apply_regular(const __grid_constant__ DeviceScene S, int axis, const double *sol, float *out,
+                                unsigned long long *pending) {
+    const Grid3<int8_t> g = S.regular[axis];
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= g.count()) return;
+    int8_t lab = g.d[idx];
+    if (lab == F_UNASSIGNED || lab == F_OUTSIDE) return;
+    I3 face = mk3((int)(idx % g.n[0]), (int)((idx / g.n[0]) % g.n[1]), (int)(idx / ((size_t)g.n[0] * g.n[1])));
+    double p[3];
+    if (lab == F_SOLID) {  // AV.cpp:2881-2890
+        S.facePos(face, axis, 0, p);
+        out[idx] = (float)S.collisionVel[axis].value(p);
+        return;
+    }
+    int32_t oi = S.face[0][axis].get(face);
+    if (oi >= 0) out[idx] = (float)sol[oi];  // AV.cpp:2856-2857
+    else if (oi == F_SOLID) {                // AV.cpp:2860-2867
+        S.facePos(face, axis, 0, p);
+        out[idx] = (float)S.collisionVel[axis].value(p);
+    } else if (oi == F_UNASSIGNED)
+        atomicAdd(pending, 1ull);
+}
+
+int avs_apply_regular(AvsContext *c, float *dOut[3], unsigned long long *hostPending) {
+    unsigned long long *cnt = c->counters.as<unsigned long long>() + 26;
+    AVS_CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
+    for (int a = 0; a < 3; ++a) {
+        size_t n = c->S.regular[a].count();
+        k_apply_regular<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->S, a, c->solution.as<double>(), dOut[a], cnt);
+        ++c->launches;
+    }
+    AVS_CUDA_CHECK(cudaMemcpyAsync(hostPending, cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return AVS_OK;
+}

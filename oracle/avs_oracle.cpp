@@ -817,26 +817,31 @@ struct Oracle {
 
     // ---------------------------------------------------------------- stage 8
     // buildVelocityMapping (AV.cpp:2291-2402): recursive 4 children x 3 in-axis offsets
-    double restrictFace(const I3 &face, int axis, int level, double weight) const {
-        if (level == 0) return weight * (double)S.vel[axis].raw(face[0], face[1], face[2]);
+    // The reference walks a FIFO queue and adds weight*leaf into one running sum (AV.cpp:2349-2395);
+    // all leaves sit at depth `level`, so queue order == depth-first order of the leaves.
+    void restrictFace(double &acc, const I3 &face, int axis, int level, double weight) const {
+        if (level == 0) {
+            acc += weight * (double)S.vel[axis].raw(face[0], face[1], face[2]);
+            return;
+        }
         static const double inAxis[3] = {1. / 16., 1. / 8., 1. / 16.};
-        double s = 0;
         for (int ch = 0; ch < 4; ++ch) {
             I3 cf = childFace(face, axis, ch);
             for (int o = -1; o < 2; ++o) {
                 I3 af = cf;
                 af[axis] += o;
-                s += restrictFace(af, axis, level - 1, (double)(float)(inAxis[o + 1] * weight));  // weight stored as fpreal32 (AV.cpp:2318)
+                restrictFace(acc, af, axis, level - 1, (double)(float)(inAxis[o + 1] * weight));  // weight stored as fpreal32 (AV.cpp:2318)
             }
         }
-        return s;
     }
     void buildVelocityMapping() {
         x0.assign((size_t)nFace, 0.0);
 #pragma omp parallel for schedule(dynamic, 4096)
         for (exint i = 0; i < nFace; ++i) {
             const int32_t *k = &faceKey[(size_t)i * 5];
-            x0[(size_t)i] = restrictFace(mk(k[2], k[3], k[4]), k[1], k[0], 1.0);
+            double acc = 0;
+            restrictFace(acc, mk(k[2], k[3], k[4]), k[1], k[0], 1.0);
+            x0[(size_t)i] = acc;
         }
     }
 

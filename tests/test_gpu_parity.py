@@ -1,0 +1,234 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the CPU oracle on the same inputs.
+
+Bars (north star): bit-exact for labels / indices / integration weights; <= 1e-12 relative for matrix, rhs
+and restricted velocities (summation order differs); velocity L-inf < 1e-6 after both CGs converge to a
+tight tolerance (so the comparison measures arithmetic, not the stopping point).
+"""
+import numpy as np
+import pytest
+
+from adaptiveviscositysolver_b200.scenes import sphere_drop
+from oracle import avs_oracle as orc
+from tests.util import csr_permuted, perm_gpu_to_oracle
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "c1_uniform32": dict(scene=dict(n=32, radius_cells=10), levels=1),
+    "sphere32_l4": dict(scene=dict(n=32, radius_cells=10), levels=4),
+    "sphere64_l6_noise": dict(scene=dict(n=64, radius_cells=26, noise=0.01), levels=6),
+    "padded_48x64x40": dict(scene=dict(n=64, radius_cells=14, res=(48, 64, 40), center=(0.375, 0.5, 0.3125)), levels=5),
+    "variable_mu_rho": dict(scene=dict(n=64, radius_cells=22, variable_viscosity=True, variable_density=True), levels=4),
+    "solid_ground": dict(scene=dict(n=32, radius_cells=9, center=(0.5, 0.34, 0.5), ground_height=0.125,
+                                    ground_velocity=(0.1, 0.0, -0.2)), levels=3),
+    "no_enhanced_gradients": dict(scene=dict(n=32, radius_cells=11), levels=4, enhanced=False),
+}
+
+
+@pytest.fixture(scope="module")
+def solver():
+    from adaptiveviscositysolver_b200.solver import Solver
+    s = Solver(device=0)
+    yield s
+    s.close()
+
+
+def _params(case, tol=1e-10, **kw):
+    from adaptiveviscositysolver_b200.solver import Params
+    return (Params(octree_levels=case["levels"], tolerance=tol, use_enhanced_gradients=case.get("enhanced", True), **kw),
+            orc.OracleParams(octree_levels=case["levels"], tolerance=tol,
+                             use_enhanced_gradients=case.get("enhanced", True), **kw))
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_labels_bit_exact(solver, name):
+    case = CASES[name]
+    sc = sphere_drop(**case["scene"])
+    gp, op = _params(case)
+    info = solver.assemble(sc, gp)
+    ref = orc.OracleRun(sc, op, stop_after_stage=5)
+    assert info.levels == ref.levels
+    assert (info.octree_dofs, info.edge_dofs, info.center_dofs, info.regular_dofs) == \
+        (ref.n_face, ref.n_edge, ref.n_center, ref.regular_dofs)
+    assert np.array_equal(solver.center_weights(), ref.center_weights())
+    for a in range(3):
+        assert np.array_equal(solver.edge_weights(a), ref.edge_weights(a))
+        rg, ro = solver.regular_labels(a), ref.regular_index(a)
+        assert np.array_equal(rg >= 0, ro >= 0) and np.array_equal(rg[rg < 0], ro[ro < 0])
+    for l in range(ref.levels):
+        assert np.array_equal(solver.labels(l), ref.labels(l)), f"cell labels differ at level {l}"
+        cg, co = solver.center_labels(l), ref.center_index(l)
+        assert np.array_equal(np.minimum(cg, 0), np.minimum(co, 0))
+        for a in range(3):
+            fg, fo = solver.face_labels(l, a), ref.face_index(l, a)
+            assert np.array_equal(np.minimum(fg, 0), np.minimum(fo, 0)), f"face labels differ at level {l} axis {a}"
+            eg, eo = solver.edge_labels(l, a), ref.edge_index(l, a)
+            assert np.array_equal(np.minimum(eg, 0), np.minimum(eo, 0)), f"edge labels differ at level {l} axis {a}"
+    # the GPU numbering is a bijection onto the same key set
+    keys = solver.keys()
+    perm_gpu_to_oracle(keys, ref.face_keys())
+    for l in range(ref.levels):
+        for a in range(3):
+            fg = solver.face_labels(l, a)
+            m = (keys[:, 0] == l) & (keys[:, 1] == a)
+            assert np.array_equal(fg[keys[m, 4], keys[m, 3], keys[m, 2]], np.nonzero(m)[0])
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_system_parity(solver, name):
+    case = CASES[name]
+    sc = sphere_drop(**case["scene"])
+    gp, op = _params(case)
+    solver.assemble(sc, gp)
+    ref = orc.OracleRun(sc, op, stop_after_stage=9)
+    perm = perm_gpu_to_oracle(solver.keys(), ref.face_keys())
+    ptr, col, val, rhs, x0 = solver.system()
+    n = ref.n_face
+    # restriction: levels 0/1 bit-exact, coarser levels to rounding (different summation tree)
+    assert np.allclose(x0, ref.x0()[perm], rtol=1e-13, atol=1e-15)
+    lv = solver.keys()[:, 0]
+    assert np.array_equal(x0[lv <= 1], ref.x0()[perm][lv <= 1])
+    A = csr_permuted(ptr, col, val, perm, n)
+    Ao = ref.scipy_matrix()
+    assert A.nnz == Ao.nnz
+    D = (A - Ao).tocoo()
+    scale = abs(Ao).max()
+    assert (D.nnz == 0) or abs(D.data).max() <= 1e-12 * scale
+    # identical sparsity pattern
+    A.sort_indices(); Ao.sort_indices()
+    assert np.array_equal(A.indptr, Ao.indptr) and np.array_equal(A.indices, Ao.indices)
+    assert np.allclose(A.data, Ao.data, rtol=1e-12, atol=1e-12 * scale)
+    b = np.empty(n); b[perm] = rhs
+    assert np.allclose(b, ref.rhs(), rtol=1e-12, atol=1e-12 * abs(ref.rhs()).max())
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_solve_parity(solver, name):
+    """Velocity L-inf < 1e-6 vs the fp64 oracle, both converged to 1e-10 (north star M3)."""
+    case = CASES[name]
+    sc = sphere_drop(**case["scene"])
+    gp, op = _params(case, tol=1e-10)
+    out = [v.data.copy() for v in sc.vel]
+    info = solver.solve(sc, gp, out)
+    ref = orc.OracleRun(sc, op)
+    perm = perm_gpu_to_oracle(solver.keys(), ref.face_keys())
+    x, xo = solver.solution(), ref.solution()[perm]
+    assert info.error < 1e-10 and ref.error < 1e-10
+    assert abs(info.iterations - ref.iterations) <= max(2, ref.iterations // 50)
+    assert np.abs(x - xo).max() < 1e-6
+    assert np.abs(x - xo).max() <= 1e-7 * max(1.0, np.abs(xo).max())
+    # output scatter: every level-0 regular face that has a co-located octree DOF carries the solution
+    keys = solver.keys()
+    for a in range(3):
+        m = (keys[:, 0] == 0) & (keys[:, 1] == a)
+        k = keys[m]
+        reg = ref.regular_index(a)
+        inside = (k[:, 2] < reg.shape[2]) & (k[:, 3] < reg.shape[1]) & (k[:, 4] < reg.shape[0])
+        k, xs = k[inside], x[m][inside]
+        isreg = reg[k[:, 4], k[:, 3], k[:, 2]] >= 0
+        got = out[a][k[isreg, 4], k[isreg, 3], k[isreg, 2]]
+        assert np.array_equal(got, xs[isreg].astype(np.float32))
+        # faces the reference would not touch keep the input value (AV.cpp:2843-2890)
+        untouched = (reg == orc.UNASSIGNED) | (reg == orc.OUTSIDE)
+        assert np.array_equal(out[a][untouched], sc.vel[a].data[untouched])
+    if case["levels"] == 1:
+        assert info.pending_interpolated_faces == 0
+
+
+def test_default_tolerance_iterations_match(solver):
+    """At the reference's default tolerance the iteration count follows Eigen's loop exactly (+-1 for rounding)."""
+    from adaptiveviscositysolver_b200.solver import Params
+    sc = sphere_drop(64, 26)
+    info = solver.solve(sc, Params(octree_levels=4, tolerance=1e-3))
+    ref = orc.OracleRun(sc, orc.OracleParams(octree_levels=4, tolerance=1e-3))
+    assert abs(info.iterations - ref.iterations) <= 1
+    assert info.error < 1e-3
+    assert info.error == pytest.approx(ref.error, rel=1e-3) or abs(info.iterations - ref.iterations) == 1
+
+
+def test_translation_invariance_zero_iterations(solver):
+    """K3 on the GPU system: constant velocity => b - A x0 = 0 => Eigen returns after 0 iterations."""
+    from adaptiveviscositysolver_b200.solver import Params
+    sc = sphere_drop(64, 24, velocity="constant")
+    info = solver.solve(sc, Params(octree_levels=5, tolerance=1e-8))
+    assert info.iterations == 0
+    ptr, col, val, rhs, x0 = solver.system()
+    import scipy.sparse as sp
+    A = sp.csr_matrix((val, col, ptr), shape=(len(rhs),) * 2)
+    assert abs(rhs - A @ x0).max() <= 1e-11 * abs(rhs).max()
+    assert abs(A - A.T).max() <= 1e-14 * abs(A).max()
+    assert np.array_equal(solver.solution(), x0)
+
+
+def test_max_iterations_and_fp32(solver):
+    from adaptiveviscositysolver_b200.solver import Params
+    sc = sphere_drop(32, 10)
+    info = solver.solve(sc, Params(octree_levels=3, tolerance=1e-12, max_iterations=7, check_every=3))
+    assert info.iterations == 7 and info.error > 1e-12
+    ref = orc.OracleRun(sc, orc.OracleParams(octree_levels=3, tolerance=1e-12, max_iterations=7))
+    perm = perm_gpu_to_oracle(solver.keys(), ref.face_keys())
+    assert np.abs(solver.solution() - ref.solution()[perm]).max() < 1e-9
+    # USESINGLEPRECISION
+    info32 = solver.solve(sc, Params(octree_levels=3, tolerance=1e-4, single_precision=True))
+    d = orc.OracleRun(sc, orc.OracleParams(octree_levels=3, tolerance=1e-8))
+    perm = perm_gpu_to_oracle(solver.keys(), d.face_keys())
+    assert info32.error < 1e-4
+    assert np.abs(solver.solution() - d.solution()[perm]).max() < 5e-3
+
+
+def test_standalone_spmv_and_cg(solver):
+    """avs_spmv_csr / avs_cg_csr on the oracle's matrix (the CG hot loop by itself)."""
+    from adaptiveviscositysolver_b200.solver import Params
+    sc = sphere_drop(64, 26, noise=0.01)
+    ref = orc.OracleRun(sc, orc.OracleParams(octree_levels=5, tolerance=1e-9))
+    ptr, col, val = ref.csr()
+    rng = np.random.default_rng(7)
+    x = rng.normal(size=ref.n_face)
+    y, _ = solver.spmv_csr(ptr, col, val, x)
+    yo = orc.spmv(ptr, col, val, x)
+    assert np.allclose(y, yo, rtol=1e-13, atol=1e-13 * abs(yo).max())
+    y32, _ = solver.spmv_csr(ptr, col, val, x, single_precision=True)
+    assert np.allclose(y32, yo, rtol=1e-4, atol=1e-5 * abs(yo).max())
+    xs, info = solver.cg_csr(ptr, col, val, ref.rhs(), ref.x0(), Params(tolerance=1e-9))
+    assert abs(info.iterations - ref.iterations) <= 2
+    assert np.abs(xs - ref.solution()).max() < 1e-7
+    # zero right-hand side: Eigen returns x = 0 without iterating
+    xz, iz = solver.cg_csr(ptr, col, val, np.zeros(ref.n_face), ref.x0(), Params(tolerance=1e-6))
+    assert iz.iterations == 0 and iz.error == 0 and not xz.any()
+    # ragged / tiny inputs
+    import scipy.sparse as sp
+    for n in (1, 31, 33):
+        M = sp.random(n, n, density=0.3, random_state=n, format="csr")
+        M = (M + M.T + sp.identity(n) * (n + 1)).tocsr()
+        M.sort_indices()
+        v = rng.normal(size=n)
+        yy, _ = solver.spmv_csr(M.indptr, M.indices, M.data, v)
+        assert np.allclose(yy, M @ v, rtol=1e-13, atol=1e-13)
+
+
+def test_operator_interface_errors_and_solve():
+    """The reference-facing operator: same option names, addError + False on missing / misaligned fields."""
+    from adaptiveviscositysolver_b200.solver import HDK_AdaptiveViscosity, SIM_Object
+    from adaptiveviscositysolver_b200.scenes import SampledField
+    sc = sphere_drop(32, 10)
+    op = HDK_AdaptiveViscosity(octreeLevels=1, tolerance=1e-10)
+    obj = SIM_Object.from_scene(sc)
+    missing = SIM_Object.from_scene(sc); del missing.fields["viscosity"]
+    assert op.solveGasSubclass(None, missing, 0.0, 1 / 24) is False and op.errors == ["Viscosity field is missing"]
+    bad = SIM_Object.from_scene(sc)
+    bad.fields["massdensity"] = SampledField(np.ones((16, 16, 16), np.float32), sc.surface.org, sc.dx)
+    assert op.solveGasSubclass(None, bad, 0.0, 1 / 24) is False
+    assert op.errors == ["Density field must align with the surface volume"]
+    before = [v.data.copy() for v in sc.vel]
+    assert op.solveGasSubclass(None, obj, 0.0, 1 / 24) is True and not op.errors
+    assert op.extra_info.startswith("iterations=")
+    ref = orc.OracleRun(sphere_drop(32, 10), orc.OracleParams(octree_levels=1, tolerance=1e-10))
+    keys, xo = ref.face_keys(), ref.solution()
+    for a in range(3):
+        m = keys[:, 1] == a
+        k = keys[m]
+        got = sc.vel[a].data[k[:, 4], k[:, 3], k[:, 2]]
+        assert np.abs(got - xo[m]).max() < 1e-6          # stored as fp32 like the reference (UTIL.h:229-232)
+        changed = sc.vel[a].data != before[a]
+        reg = ref.regular_index(a)
+        assert not changed[(reg == orc.UNASSIGNED)].any()
