@@ -134,9 +134,13 @@ static int uploadField(AvsContext *c, DevBuf &buf, DField &d, const AvsField &f)
         return AVS_OK;
     }
     if (f.res[0] <= 0 || f.res[1] <= 0 || f.res[2] <= 0 || !(f.dx > 0)) return AVS_ERR_INVALID_ARGUMENT;
+    if (f.on_device) {  // already resident in HBM: read it in place, the kernels never write input fields
+        d.d = f.data;
+        return AVS_OK;
+    }
     size_t bytes = (size_t)f.res[0] * f.res[1] * f.res[2] * sizeof(float);
     if (buf.reserve(bytes)) return AVS_ERR_ALLOC;
-    AVS_CUDA_CHECK(cudaMemcpyAsync(buf.p, f.data, bytes, f.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    AVS_CUDA_CHECK(cudaMemcpyAsync(buf.p, f.data, bytes, cudaMemcpyHostToDevice, c->stream));
     d.d = buf.as<float>();
     return AVS_OK;
 }
@@ -337,9 +341,17 @@ int avs_solve(AvsContext *c, const AvsFields *in, const AvsParams *p, AvsVelocit
     memset(res->stage_ms, 0, sizeof(res->stage_ms));
     c->launches = 0;
     c->spmvLaunches = 0;
+    cudaEventRecord(c->ev[AVS_STAGE_COUNT], c->stream);
     int rc = runAssemble(c, in, p, res);
     if (rc == AVS_OK) rc = runSolve(c, p, res);
     if (rc == AVS_OK && out) rc = runApply(c, out, res);
+    // total = first enqueue to last completion on the stream (includes the host gaps between stages)
+    cudaEventRecord(c->ev[AVS_STAGE_COUNT + 1], c->stream);
+    if (cudaEventSynchronize(c->ev[AVS_STAGE_COUNT + 1]) == cudaSuccess) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev[AVS_STAGE_COUNT], c->ev[AVS_STAGE_COUNT + 1]);
+        res->stage_ms[AVS_STAGE_TOTAL] = ms;
+    }
     res->status = rc;
     return rc;
 }

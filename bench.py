@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- viscosity-solve throughput (DOF*iters/s) and CG-SpMV roofline on B200.
+
+A "step" is one pass of the hot path over one synthetic sphere-drop scene: labelling + assembly + CG to
+the configured tolerance (everything HDK_AdaptiveViscosity::solveGasSubclass does after validation,
+HDK_AdaptiveViscosity.cpp:233-707).
+
+  value   N * CG iterations / device time of a step with the fields already resident in HBM
+  e2e     the same through the host-buffer C-ABI call (avs_solve): pinned host inputs -> H2D -> solve ->
+          D2H of the velocity, all inside the timed region
+  roofline  the SpMV kernel of the CG: algorithmic bytes nnz*(s+4)+(N+1)*4+2*N*s divided by the average
+          launch duration measured with CUDA events on the library's stream during the timed steps
+  cpu_baseline  the oracle's Eigen-equivalent Jacobi-PCG (OpenMP, all host cores) on the same matrix,
+          a bounded number of iterations
+
+`--impl reference` times the CPU restatement of the reference path (oracle/) on the host cores: the
+reference itself needs Houdini + Eigen and cannot be built.
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (n, radius_cells, octree_levels, tolerance, description)  -- BASELINE.md section 4
+    "c1": dict(n=32, R=10, L=1, tol=1e-3, desc="C1 32^3 uniform (octree depth 1) sphere drop"),
+    "c2": dict(n=256, R=82, L=5, tol=1e-6, desc="C2 (DOF-matched) 256^3 R=82 octree depth 5, ~1.1 M DOF"),
+    "c2lit": dict(n=128, R=56, L=5, tol=1e-6, desc="C2 (literal) 128^3 R=56 octree depth 5, ~0.5 M DOF"),
+    "c3": dict(n=512, R=246, L=7, tol=1e-6, desc="C3 512^3 R=246 octree depth 7, ~10 M DOF"),
+    "c3lit": dict(n=256, R=120, L=7, tol=1e-6, desc="C3 (literal) 256^3 R=120 octree depth 7, ~2.4 M DOF"),
+}
+METRIC = "viscosity_solve_dof_iters_per_s"
+UNIT = "DOF*iters/s"
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        self.device = device
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def make_scene(w):
+    from adaptiveviscositysolver_b200.scenes import sphere_drop
+    return sphere_drop(w["n"], w["R"])
+
+
+def to_device_scene(scene, torch, dev):
+    """Same Scene, every dense field as a CUDA tensor (inputs resident in HBM before the timed region)."""
+    from adaptiveviscositysolver_b200.scenes import SampledField, Scene
+
+    def mv(f):
+        if f.data is None:
+            return f
+        return SampledField(torch.from_numpy(f.data).to(dev), f.org, f.dx, f.constant)
+
+    return Scene(scene.res, scene.origin, scene.dx, mv(scene.surface), [mv(v) for v in scene.vel],
+                 [mv(v) for v in scene.face_weights], mv(scene.viscosity), mv(scene.density), mv(scene.collision),
+                 [mv(v) for v in scene.collision_vel])
+
+
+def to_pinned_scene(scene, torch):
+    from adaptiveviscositysolver_b200.scenes import SampledField, Scene
+
+    def mv(f):
+        if f.data is None:
+            return f
+        t = torch.from_numpy(f.data).pin_memory()
+        return SampledField(t, f.org, f.dx, f.constant)
+
+    return Scene(scene.res, scene.origin, scene.dx, mv(scene.surface), [mv(v) for v in scene.vel],
+                 [mv(v) for v in scene.face_weights], mv(scene.viscosity), mv(scene.density), mv(scene.collision),
+                 [mv(v) for v in scene.collision_vel])
+
+
+def dense_bytes(scene):
+    n = 0
+    for f in [scene.surface, scene.viscosity, scene.density, scene.collision, *scene.vel, *scene.face_weights, *scene.collision_vel]:
+        if f.data is not None:
+            n += int(np.prod(f.data.shape)) * 4
+    return n
+
+
+def run_reference(args, w):
+    """CPU arm: the restated reference path (oracle) on the host cores. A step = `m` Eigen-CG iterations on
+    the oracle-assembled system of the same workload (bounded sample; the full solve takes `iters` of them)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import avs_oracle as orc
+    cores = orc.num_threads()
+    t0 = time.time()
+    scene = make_scene(w)
+    run = orc.OracleRun(scene, orc.OracleParams(octree_levels=w["L"], tolerance=w["tol"]), stop_after_stage=9)
+    t_asm = time.time() - t0
+    ptr, col, val = run.csr()
+    b, x0 = run.rhs(), run.x0()
+    n = run.n_face
+    # size the sample: ~2 s of CG per step
+    t = time.time(); orc.cg(ptr, col, val, b, x0, 0.0, 2); per_it = (time.time() - t) / 2
+    m = int(max(2, min(200, 2.0 / max(per_it, 1e-6))))
+    for _ in range(args.warmup):
+        orc.cg(ptr, col, val, b, x0, 0.0, m)
+    t = time.time()
+    for _ in range(args.steps):
+        orc.cg(ptr, col, val, b, x0, 0.0, m)
+    dt = (time.time() - t) / args.steps
+    value = n * m / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["desc"], "N": int(n), "nnz": int(run.nnz), "levels": int(run.levels), "tolerance": w["tol"],
+                   "oracle_assembly_s": round(t_asm, 2)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{m} Jacobi-PCG iterations per step on the oracle-assembled system (N={n}), OpenMP {cores} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
+    ap.add_argument("--fp32", action="store_true", help="USESINGLEPRECISION solve (C3's ncu capture config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from adaptiveviscositysolver_b200.solver import Params, Solver
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    peak, peak_src = peaks()
+    scene = make_scene(w)
+    params = Params(octree_levels=w["L"], tolerance=w["tol"], single_precision=args.fp32)
+    solver = Solver(device=local, rank=rank, nranks=world, time_spmv=True)
+    dscene = to_device_scene(scene, torch, dev)
+    dout = [v.data.clone() for v in dscene.vel]
+    stream = None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident steps -------------------------------------------------------------------
+    for _ in range(args.warmup):
+        info = solver.solve(dscene, params, dout)
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    step_ms, spmv_ms, spmv_n, launches = [], 0.0, 0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        info = solver.solve(dscene, params, dout)       # returns after the stream has drained (stage events)
+        step_ms.append(info.stage_ms["total"])
+        spmv_ms += info.spmv_ms
+        spmv_n += info.spmv_launches
+        launches += info.kernel_launches
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    clk = clocks.stop()
+    dev_ms = float(np.mean(step_ms))
+    t = torch.tensor([dev_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    N, iters, nnz = info.octree_dofs, info.iterations, info.nnz
+    value = N * iters / (dev_ms * 1e-3)
+
+    s = 4 if args.fp32 else 8
+    alg_bytes = nnz * (s + 4) + (N + 1) * 4 + 2 * N * s
+    spmv_avg_ms = spmv_ms / max(spmv_n, 1)
+    achieved = alg_bytes / (spmv_avg_ms * 1e-3) / 1e9 if spmv_n else 0.0
+    # cold-ish re-measurement of the same kernel, back to back, for reference
+    iso_ms, _ = solver.time_spmv_resident(20)
+
+    # ---- end to end through the host-buffer call --------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        pscene = to_pinned_scene(scene, torch)
+        pout = [torch.from_numpy(v.data.copy()).pin_memory() for v in scene.vel]
+        h2d = dense_bytes(scene) + sum(int(np.prod(v.data.shape)) * 4 for v in scene.vel)  # fields + current vel for in-place semantics
+        d2h = sum(int(np.prod(v.data.shape)) * 4 for v in scene.vel)
+        solver.solve(pscene, params, pout)
+        barrier()
+        t0 = time.perf_counter()
+        k = max(1, min(args.steps, 2))
+        for _ in range(k):
+            einfo = solver.solve(pscene, params, pout)
+        torch.cuda.synchronize()
+        e_ms = (time.perf_counter() - t0) * 1e3 / k
+        e2e = {"value": N * einfo.iterations / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": e_ms,
+               "stage_ms": {k2: round(v, 3) for k2, v in einfo.stage_ms.items()}}
+        del pscene, pout
+
+    # ---- CPU baseline: oracle CG on the same matrix ------------------------------------------------
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import avs_oracle as orc
+        ptr, col, val, rhs, x0 = solver.system()
+        cores = orc.num_threads()
+        t = time.time(); orc.cg(ptr, col, val, rhs, x0, 0.0, 2); per_it = (time.time() - t) / 2
+        m = int(max(3, min(400, 12.0 / max(per_it, 1e-6))))
+        t = time.time(); orc.cg(ptr, col, val, rhs, x0, 0.0, m); dt = time.time() - t
+        cpu = {"value": N * m / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{m} Eigen-equivalent Jacobi-PCG iterations of the oracle (OpenMP, {cores} threads) on the GPU-assembled "
+                         f"matrix of this workload (N={N}, nnz={nnz}); {dt:.1f} s",
+               "spmv_gbs": None}
+        del ptr, col, val
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32" if args.fp32 else "f64", "data": "synthetic",
+            "config": {"workload": w["desc"], "N": int(N), "nnz": int(nnz), "levels": int(info.levels), "iterations": int(iters),
+                       "rel_error": info.error, "tolerance": w["tol"], "regular_dofs": int(info.regular_dofs),
+                       "l2": "matrix+vectors per SpMV = %.0f MB vs 126 MB L2 (inputs larger than L2, no flush)" % (alg_bytes / 1e6),
+                       "wall_ms_per_step": wall_ms,
+                       "stage_ms": {k2: round(v, 3) for k2, v in info.stage_ms.items()}},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "k_spmv_sjds (CG SpMV + fused p.Ap)", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": spmv_avg_ms, "launches_timed": int(spmv_n),
+                         "back_to_back_ms": iso_ms,
+                         "cg_iteration_frac": (N * iters * (alg_bytes / N + 11 * s)) / (info.stage_ms["solve"] * 1e-3) / 1e9 / peak},
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "clocks": clk,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -66,6 +66,7 @@ def lib():
         L.orc_create.argtypes = [C.POINTER(_Scene), C.POINTER(_Params)]
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_run.argtypes = [C.c_void_p, C.c_int]
+        L.orc_set_weight_shortcut.argtypes = [C.c_void_p, C.c_int]
         L.orc_levels.argtypes = [C.c_void_p]
         L.orc_levels_allocated.argtypes = [C.c_void_p]
         L.orc_padded_res.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
@@ -146,7 +147,7 @@ class OracleParams:
 class OracleRun:
     """One execution of the restated reference pipeline; exposes every intermediate."""
 
-    def __init__(self, scene, params: OracleParams | None = None, stop_after_stage: int = 0):
+    def __init__(self, scene, params: OracleParams | None = None, stop_after_stage: int = 0, weight_shortcut: bool = True):
         params = params or OracleParams()
         self._L = lib()
         keep = []
@@ -157,6 +158,7 @@ class OracleRun:
                     int(params.single_precision), stop_after_stage)
         self._h = self._L.orc_create(C.byref(sc), C.byref(p))
         del keep  # the oracle copies its inputs
+        self._L.orc_set_weight_shortcut(self._h, int(weight_shortcut))
         self._L.orc_run(self._h, stop_after_stage)
         self.stage = stop_after_stage if stop_after_stage > 0 else 10
 

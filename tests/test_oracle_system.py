@@ -194,3 +194,15 @@ def test_solid_ground_rows():
     A2, b2, x2 = r2.scipy_matrix(), r2.rhs(), r2.x0()
     assert abs(b2 - A2 @ x2).max() <= 1e-11 * abs(b2).max()
     assert r2.iterations == 0
+
+
+def test_weight_shortcut_is_exact():
+    """The sign-of-neighbourhood early-out in the supersampler equals brute-force sampling."""
+    sc = sphere_drop(32, 10, center=(0.47, 0.52, 0.5), ground_height=0.2)
+    a = orc.OracleRun(sc, P(octree_levels=3, do_apply_solid_weights=True), stop_after_stage=1, weight_shortcut=True)
+    b = orc.OracleRun(sc, P(octree_levels=3, do_apply_solid_weights=True), stop_after_stage=1, weight_shortcut=False)
+    assert np.array_equal(a.center_weights(), b.center_weights())
+    for ax in range(3):
+        assert np.array_equal(a.edge_weights(ax), b.edge_weights(ax))
+    w = a.center_weights()
+    assert ((w > 0) & (w < 1)).any() and (w == 1).any() and (w == 0).any()
