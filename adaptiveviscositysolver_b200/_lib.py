@@ -54,6 +54,7 @@ class AvsResult(C.Structure):
                 ("edge_dofs", C.c_int64), ("center_dofs", C.c_int64), ("nnz", C.c_int64), ("local_rows", C.c_int64),
                 ("spmv_launches", C.c_int64), ("kernel_launches", C.c_int64),
                 ("stage_ms", C.c_float * AVS_STAGE_COUNT), ("spmv_ms", C.c_float),
+                ("cg_update_xr_ms", C.c_float), ("cg_update_p_ms", C.c_float),
                 ("pending_interpolated_faces", C.c_int64)]
 
 

@@ -90,6 +90,8 @@ int avs_create(const AvsDeviceConfig *cfg, AvsContext **out) {
     if (c->timeSpmv) {
         c->spmvEvents.resize(2 * 4096);
         for (auto &e : c->spmvEvents) cudaEventCreate(&e);
+        c->auxEvents.resize(3 * 4096);
+        for (auto &e : c->auxEvents) cudaEventCreate(&e);
     }
     if (c->counters.reserve(64 * sizeof(unsigned long long))) { delete c; return AVS_ERR_ALLOC; }
     memset(&c->S, 0, sizeof(c->S));
@@ -104,7 +106,8 @@ void avs_destroy(AvsContext *c) {
     DevBuf *bufs[] = {&c->inSurface, &c->inVisc, &c->inDens, &c->inColl, &c->centerW, &c->tiles, &c->brickCount, &c->brickOffset,
                       &c->scanTmp, &c->counters, &c->rowKeys, &c->x0, &c->rhs, &c->solution, &c->rowCount, &c->rowOffset,
                       &c->csrPtr, &c->csrCol, &c->csrVal, &c->A.sliceOff, &c->A.val, &c->A.col, &c->A.invDiag, &c->A.meta,
-                      &c->cg.x, &c->cg.r, &c->cg.p, &c->cg.t, &c->cg.partials, &c->cg.scalars, &c->cgRhs};
+                      &c->cg.x, &c->cg.r, &c->cg.p, &c->cg.t, &c->cg.partials, &c->cg.scalars, &c->cgRhs,
+                      &c->stageCol, &c->stageVal, &c->diag, &c->slicePairs, &c->edgeTiles, &c->solidW};
     for (DevBuf *b : bufs) b->release();
     for (int a = 0; a < 3; ++a) {
         c->inVel[a].release(); c->inFaceW[a].release(); c->inCollVel[a].release(); c->edgeW[a].release(); c->regular[a].release();
@@ -116,6 +119,7 @@ void avs_destroy(AvsContext *c) {
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->evPoll) if (e) cudaEventDestroy(e);
     for (auto &e : c->spmvEvents) if (e) cudaEventDestroy(e);
+    for (auto &e : c->auxEvents) if (e) cudaEventDestroy(e);
     if (c->hostScalars) cudaFreeHost(c->hostScalars);
     if (c->ownStream) cudaStreamDestroy(c->stream);
     delete c;
@@ -237,8 +241,8 @@ static int runAssemble(AvsContext *c, const AvsFields *in, const AvsParams *p, A
     cudaEventRecord(c->ev[AVS_STAGE_SYSTEM], c->stream);
     if ((rc = avs_stage_system(c, p))) return rc;
     // the CG's matrix format is part of "Build Octree Linear System" (the reference's setFromTriplets, AV.cpp:614)
-    if ((rc = avs_sell_from_csr(c, c->A, c->rowEnd - c->rowBegin, c->csrPtr.as<int64_t>(), c->csrCol.as<int32_t>(),
-                                c->csrVal.as<double>(), p->precision))) return rc;
+    if ((rc = avs_sell_from_stage(c, c->A, c->rowEnd - c->rowBegin, c->nnz, c->rowCount.as<int32_t>(), c->stageCol.as<int32_t>(),
+                                  c->stageVal.as<double>(), c->stageStride, c->diag.as<double>(), p->precision))) return rc;
     cudaEventRecord(c->ev[AVS_STAGE_SOLVE], c->stream);
     collectStageTimes(c, res, AVS_STAGE_UPLOAD, AVS_STAGE_SYSTEM);
     fillCounts(c, res);
@@ -251,24 +255,41 @@ static int runSolve(AvsContext *c, const AvsParams *p, AvsResult *res) {
     const long long n = c->rowEnd - c->rowBegin;
     if (c->solution.reserve((size_t)std::max<long long>(n, 1) * sizeof(double))) return AVS_ERR_ALLOC;
     c->spmvEventsUsed = 0;
+    c->auxEventsUsed = 0;
     c->spmvMs = 0;
     const int64_t spmv0 = c->spmvLaunches;
     cudaEventRecord(c->ev[AVS_STAGE_SOLVE], c->stream);
     int rc = avs_cg_run(c, c->A, c->rhs.as<double>(), c->x0.as<double>() + c->rowBegin, c->solution.as<double>(), p, res);
     cudaEventRecord(c->ev[AVS_STAGE_SOLVE + 1], c->stream);
     collectStageTimes(c, res, AVS_STAGE_SOLVE, AVS_STAGE_SOLVE);
+    // Launches after convergence are no-ops (device-side `done` flag): only the launches that did work count.
+    // Event pair 0 is the residual SpMV (r = b - A x0), pairs 1..iters+1 are the CG iterations incl. the one that broke out.
+    const int64_t realCg = std::min<int64_t>((int64_t)res->iterations + 1, std::max<int64_t>(p->max_iterations, 0));
     if (c->timeSpmv) {
+        const size_t pairs = std::min<size_t>(c->spmvEventsUsed / 2, (size_t)(realCg + 1));
         float total = 0;
-        for (size_t i = 0; i + 1 < c->spmvEventsUsed; i += 2) {
+        for (size_t i = 0; i < pairs; ++i) {
             float ms = 0;
-            cudaEventElapsedTime(&ms, c->spmvEvents[i], c->spmvEvents[i + 1]);
+            cudaEventElapsedTime(&ms, c->spmvEvents[2 * i], c->spmvEvents[2 * i + 1]);
             total += ms;
         }
         res->spmv_ms = total;
-        res->spmv_launches = (int64_t)(c->spmvEventsUsed / 2);
+        res->spmv_launches = (int64_t)pairs;
+        const size_t triples = std::min<size_t>(c->auxEventsUsed / 3, (size_t)realCg);
+        float xr = 0, pu = 0;
+        for (size_t i = 0; i < triples; ++i) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, c->auxEvents[3 * i], c->auxEvents[3 * i + 1]);
+            cudaEventElapsedTime(&b, c->auxEvents[3 * i + 1], c->auxEvents[3 * i + 2]);
+            xr += a;
+            pu += b;
+        }
+        res->cg_update_xr_ms = xr;
+        res->cg_update_p_ms = pu;
     } else {
-        res->spmv_launches = c->spmvLaunches - spmv0;
+        res->spmv_launches = realCg + 1;
     }
+    (void)spmv0;
     res->kernel_launches = c->launches;
     if (rc == AVS_OK) c->haveSolution = true;
     return rc;
@@ -283,8 +304,11 @@ static int runApply(AvsContext *c, AvsVelocityOut *out, AvsResult *res) {
         if (!out->vel[a]) return AVS_ERR_INVALID_ARGUMENT;
         size_t bytes = c->S.regular[a].count() * sizeof(float);
         if (out->on_device) dOut[a] = out->vel[a];
-        else {
-            // start from the caller's current values so untouched faces stay untouched (AV.cpp:2843-2890)
+        else if (c->S.vel[a].d == c->inVel[a].as<float>() && c->inVel[a].p) {
+            // host caller: the library's own device copy of the input velocity is the "in place" target
+            // (solveGasSubclass updates `vel` in place, AV.cpp:698); untouched faces keep the input value.
+            dOut[a] = c->inVel[a].as<float>();
+        } else {
             if (tmp[a].reserve(bytes)) return AVS_ERR_ALLOC;
             AVS_CUDA_CHECK(cudaMemcpyAsync(tmp[a].p, out->vel[a], bytes, cudaMemcpyHostToDevice, c->stream));
             dOut[a] = tmp[a].as<float>();
@@ -377,6 +401,10 @@ int avs_get_system_csr(AvsContext *c, int64_t *rowPtr, int32_t *col, double *val
     if (!c || !c->haveSystem) return AVS_ERR_INVALID_ARGUMENT;
     cudaSetDevice(c->device);
     const long long n = c->rowEnd - c->rowBegin;
+    if (col || val) {
+        int rc = avs_build_csr(c);
+        if (rc) return rc;
+    }
     if (rowPtr) AVS_CUDA_CHECK(cudaMemcpyAsync(rowPtr, c->csrPtr.p, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
     if (col) AVS_CUDA_CHECK(cudaMemcpyAsync(col, c->csrCol.p, (size_t)c->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     if (val) AVS_CUDA_CHECK(cudaMemcpyAsync(val, c->csrVal.p, (size_t)c->nnz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -441,6 +469,7 @@ static int uploadCsr(AvsContext *c, int64_t n, const int64_t *rowPtr, const int3
     c->rowBegin = 0;
     c->rowEnd = n;
     c->haveSystem = false;  // no geometry behind this matrix
+    c->csrValid = true;
     c->haveSolution = false;
     return avs_sell_from_csr(c, c->A, n, c->csrPtr.as<int64_t>(), c->csrCol.as<int32_t>(), c->csrVal.as<double>(), precision);
 }

@@ -23,15 +23,20 @@
 
 #define CG_THREADS 256
 #define CG_CTAS_PER_SM 8
+#define SPMV_U 4
 
 // ---- SJDS build ---------------------------------------------------------------------------------
 // meta[slice*32 + q] = (original lane << 8) | number of pairs, q = position after sorting by length
-__global__ void k_sjds_count(long long n, const long long *ptr, long long nslices, int32_t *meta, int32_t *slicePairs) {
+__global__ void k_row_lengths(long long n, const long long *ptr, int32_t *len) {
+    long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) len[r] = (int32_t)(ptr[r + 1] - ptr[r]);
+}
+__global__ void k_sjds_count(long long n, const int32_t *rowLen, long long nslices, int32_t *meta, int32_t *slicePairs) {
     long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (s >= nslices) return;
     long long r = s * 32 + lane;
-    int len = (r < n) ? (int)(ptr[r + 1] - ptr[r]) : 0;
+    int len = (r < n) ? rowLen[r] : 0;
     int np = (len + 1) >> 1;
     int rank = 0, total = 0;
     for (int o = 0; o < 32; ++o) {
@@ -41,6 +46,43 @@ __global__ void k_sjds_count(long long n, const long long *ptr, long long nslice
     }
     meta[s * 32 + rank] = (lane << 8) | np;
     if (lane == 0) slicePairs[s] = total;
+}
+
+// fill from the assembly staging area (entry j of row r at j*stride + r)
+template <class T, class T2>
+__global__ void k_sjds_fill_stage(long long n, const int32_t *rowLen, const int32_t *stageCol, const double *stageVal, long long stride,
+                                  long long nslices, const int32_t *meta, const long long *sliceOff, T2 *val2, int2 *col2) {
+    long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (s >= nslices) return;
+    int m = meta[s * 32 + lane];
+    int np = m & 0xff, orig = m >> 8;
+    long long r = s * 32 + orig;
+    int len = (r < n) ? rowLen[r] : 0;
+    long long base = sliceOff[s];
+    int maxnp = __shfl_sync(0xffffffffu, np, 0);
+    long long off = 0;
+    for (int j = 0; j < maxnp; ++j) {
+        bool active = j < np;
+        int cnt = __popc(__ballot_sync(0xffffffffu, active));
+        if (active) {
+            long long k0 = (long long)(2 * j) * stride + r, k1 = k0 + stride;
+            T2 v;
+            int2 cc;
+            v.x = (T)stageVal[k0];
+            cc.x = stageCol[k0];
+            if (2 * j + 1 < len) { v.y = (T)stageVal[k1]; cc.y = stageCol[k1]; }
+            else { v.y = (T)0; cc.y = cc.x; }
+            val2[base + off + lane] = v;
+            col2[base + off + lane] = cc;
+        }
+        off += cnt;
+    }
+}
+template <class T>
+__global__ void k_inv_diag_from_array(long long n, const double *diag, T *invDiag) {
+    long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) invDiag[r] = (diag[r] != 0.0) ? (T)(1.0 / diag[r]) : (T)1;
 }
 
 template <class T, class T2>
@@ -87,48 +129,81 @@ __global__ void k_inv_diag(long long n, const long long *ptr, const int32_t *col
     invDiag[r] = (found && d != 0.0) ? (T)(1.0 / d) : (T)1;
 }
 
-int avs_sell_from_csr(AvsContext *c, SellMatrix &A, int64_t n, const int64_t *dPtr, const int32_t *dCol, const double *dVal,
-                      int precision) {
+// common part: slice metadata + offsets from the row lengths; returns the number of pairs
+static int sjdsLayout(AvsContext *c, SellMatrix &A, int64_t n, const int32_t *dLen, int precision, int64_t *totalPairsOut) {
     A.n = n;
     A.precision = precision;
     A.nslices = (n + 31) / 32;
     const size_t vs = precision == AVS_PRECISION_F32 ? sizeof(float) : sizeof(double);
-    DevBuf pairs;
     if (A.sliceOff.reserve((size_t)(A.nslices + 1) * sizeof(long long))) return AVS_ERR_ALLOC;
-    if (pairs.reserve((size_t)std::max<int64_t>(A.nslices, 1) * sizeof(int32_t))) return AVS_ERR_ALLOC;
+    if (c->slicePairs.reserve((size_t)std::max<int64_t>(A.nslices, 1) * sizeof(int32_t))) return AVS_ERR_ALLOC;
     if (A.meta.reserve((size_t)std::max<int64_t>(A.nslices, 1) * 32 * sizeof(int32_t))) return AVS_ERR_ALLOC;
-    int32_t *dMeta = A.meta.as<int32_t>();
     if (A.invDiag.reserve((size_t)std::max<int64_t>(n, 1) * vs)) return AVS_ERR_ALLOC;
-    A.nnz = 0;
     A.padded = 0;
+    *totalPairsOut = 0;
     if (n == 0) return AVS_OK;
     unsigned blocks = (unsigned)((A.nslices * 32 + 255) / 256);
-    k_sjds_count<<<blocks, 256, 0, c->stream>>>(n, (const long long *)dPtr, A.nslices, dMeta, pairs.as<int32_t>());
+    k_sjds_count<<<blocks, 256, 0, c->stream>>>(n, dLen, A.nslices, A.meta.as<int32_t>(), c->slicePairs.as<int32_t>());
     ++c->launches;
     int64_t totalPairs = 0;
-    int rc = avs_exclusive_scan_i32_to_i64(c, pairs.as<int32_t>(), A.sliceOff.as<int64_t>(), A.nslices, &totalPairs);
+    int rc = avs_exclusive_scan_i32_to_i64(c, c->slicePairs.as<int32_t>(), A.sliceOff.as<int64_t>(), A.nslices, &totalPairs);
     if (rc) return rc;
     AVS_CUDA_CHECK(cudaMemcpyAsync(A.sliceOff.as<long long>() + A.nslices, &totalPairs, sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    A.padded = totalPairs * 2;
+    if (A.val.reserve((size_t)std::max<int64_t>(totalPairs, 1) * 2 * vs)) return AVS_ERR_ALLOC;
+    if (A.col.reserve((size_t)std::max<int64_t>(totalPairs, 1) * sizeof(int2))) return AVS_ERR_ALLOC;
+    *totalPairsOut = totalPairs;
+    return AVS_OK;
+}
+
+int avs_sell_from_csr(AvsContext *c, SellMatrix &A, int64_t n, const int64_t *dPtr, const int32_t *dCol, const double *dVal,
+                      int precision) {
+    A.nnz = 0;
+    if (c->rowCount.reserve((size_t)std::max<int64_t>(n, 1) * sizeof(int32_t))) return AVS_ERR_ALLOC;
+    if (n > 0) {
+        k_row_lengths<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, (const long long *)dPtr, c->rowCount.as<int32_t>());
+        ++c->launches;
+    }
+    int64_t totalPairs = 0;
+    int rc = sjdsLayout(c, A, n, c->rowCount.as<int32_t>(), precision, &totalPairs);
+    if (rc || n == 0) return rc;
     long long nnz = 0;
     AVS_CUDA_CHECK(cudaMemcpyAsync(&nnz, (const long long *)dPtr + n, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     A.nnz = nnz;
-    A.padded = totalPairs * 2;
-    if (A.val.reserve((size_t)std::max<int64_t>(totalPairs, 1) * 2 * vs)) return AVS_ERR_ALLOC;
-    if (A.col.reserve((size_t)std::max<int64_t>(totalPairs, 1) * sizeof(int2))) return AVS_ERR_ALLOC;
+    unsigned blocks = (unsigned)((A.nslices * 32 + 255) / 256);
     if (precision == AVS_PRECISION_F32) {
-        k_sjds_fill<float, float2><<<blocks, 256, 0, c->stream>>>(n, (const long long *)dPtr, dCol, dVal, A.nslices, dMeta,
+        k_sjds_fill<float, float2><<<blocks, 256, 0, c->stream>>>(n, (const long long *)dPtr, dCol, dVal, A.nslices, A.meta.as<int32_t>(),
                                                                  A.sliceOff.as<long long>(), A.val.as<float2>(), A.col.as<int2>());
         k_inv_diag<float><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, (const long long *)dPtr, dCol, dVal, 0, A.invDiag.as<float>());
     } else {
-        k_sjds_fill<double, double2><<<blocks, 256, 0, c->stream>>>(n, (const long long *)dPtr, dCol, dVal, A.nslices, dMeta,
+        k_sjds_fill<double, double2><<<blocks, 256, 0, c->stream>>>(n, (const long long *)dPtr, dCol, dVal, A.nslices, A.meta.as<int32_t>(),
                                                                    A.sliceOff.as<long long>(), A.val.as<double2>(), A.col.as<int2>());
         k_inv_diag<double><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, (const long long *)dPtr, dCol, dVal, 0, A.invDiag.as<double>());
     }
     c->launches += 2;
-    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     AVS_CUDA_CHECK(cudaGetLastError());
-    pairs.release();
+    return AVS_OK;
+}
+
+int avs_sell_from_stage(AvsContext *c, SellMatrix &A, int64_t n, int64_t nnz, const int32_t *dCount, const int32_t *dStageCol,
+                        const double *dStageVal, long long stride, const double *dDiag, int precision) {
+    A.nnz = nnz;
+    int64_t totalPairs = 0;
+    int rc = sjdsLayout(c, A, n, dCount, precision, &totalPairs);
+    if (rc || n == 0) return rc;
+    unsigned blocks = (unsigned)((A.nslices * 32 + 255) / 256);
+    if (precision == AVS_PRECISION_F32) {
+        k_sjds_fill_stage<float, float2><<<blocks, 256, 0, c->stream>>>(n, dCount, dStageCol, dStageVal, stride, A.nslices, A.meta.as<int32_t>(),
+                                                                       A.sliceOff.as<long long>(), A.val.as<float2>(), A.col.as<int2>());
+        k_inv_diag_from_array<float><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, dDiag, A.invDiag.as<float>());
+    } else {
+        k_sjds_fill_stage<double, double2><<<blocks, 256, 0, c->stream>>>(n, dCount, dStageCol, dStageVal, stride, A.nslices, A.meta.as<int32_t>(),
+                                                                         A.sliceOff.as<long long>(), A.val.as<double2>(), A.col.as<int2>());
+        k_inv_diag_from_array<double><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, dDiag, A.invDiag.as<double>());
+    }
+    c->launches += 2;
+    AVS_CUDA_CHECK(cudaGetLastError());
     return AVS_OK;
 }
 
@@ -197,17 +272,36 @@ __global__ void __launch_bounds__(CG_THREADS) k_spmv_sjds(long long nrows, long 
         const int maxnp = __shfl_sync(0xffffffffu, np, 0);
         T acc = 0;
         long long off = 0;
-#pragma unroll 4
-        for (int j = 0; j < maxnp; ++j) {
-            const bool active = j < np;
-            const int cnt = __popc(__ballot_sync(0xffffffffu, active));
-            if (active) {
-                const T2 v = val2[base + off];
-                const int2 cc = col2[base + off];
-                acc += v.x * __ldg(x + cc.x);
-                acc += v.y * __ldg(x + cc.y);
+        // SPMV_U pair-steps per trip: offsets first (warp ballots, pure ALU), then all matrix loads, then all
+        // gathers of x, then the FMAs -- so one lane keeps 2*SPMV_U independent loads in flight.
+        for (int j0 = 0; j0 < maxnp; j0 += SPMV_U) {
+            long long o[SPMV_U];
+            bool act[SPMV_U];
+#pragma unroll
+            for (int u = 0; u < SPMV_U; ++u) {
+                act[u] = (j0 + u) < np;
+                o[u] = base + off;
+                off += __popc(__ballot_sync(0xffffffffu, act[u]));
             }
-            off += cnt;
+            T2 v[SPMV_U];
+            int2 cc[SPMV_U];
+#pragma unroll
+            for (int u = 0; u < SPMV_U; ++u) {
+                v[u].x = 0; v[u].y = 0;
+                cc[u].x = 0; cc[u].y = 0;
+                if (act[u]) { v[u] = val2[o[u]]; cc[u] = col2[o[u]]; }
+            }
+            T xa[SPMV_U], xb[SPMV_U];
+#pragma unroll
+            for (int u = 0; u < SPMV_U; ++u) {
+                xa[u] = 0; xb[u] = 0;
+                if (act[u]) { xa[u] = __ldg(x + cc[u].x); xb[u] = __ldg(x + cc[u].y); }
+            }
+#pragma unroll
+            for (int u = 0; u < SPMV_U; ++u) {
+                acc += v[u].x * xa[u];
+                acc += v[u].y * xb[u];
+            }
         }
         if (r < nrows) {
             y[r] = acc;
@@ -348,6 +442,19 @@ static void launchSpmv(AvsContext *c, SellMatrix &A, const T *x, T *y, double *p
     ++c->spmvLaunches;
 }
 
+// persistent SpMV grid: exactly the number of CTAs that are resident at once (one wave)
+template <class T, class T2>
+static int spmvGrid(AvsContext *c, long long nslices) {
+    int perSM = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_spmv_sjds<T, T2, true>, CG_THREADS, 0) != cudaSuccess || perSM < 1) {
+        cudaGetLastError();
+        perSM = 4;
+    }
+    long long want = (nslices * 32 + CG_THREADS - 1) / CG_THREADS;
+    long long cap = (long long)c->numSMs * perSM;
+    return (int)std::max<long long>(1, std::min(want, cap));
+}
+
 static int cgGrid(AvsContext *c, long long n) {
     long long want = (n + CG_THREADS - 1) / CG_THREADS;
     long long cap = (long long)c->numSMs * CG_CTAS_PER_SM;
@@ -359,11 +466,12 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
     const long long n = A.n;
     CgWork &w = c->cg;
     const int grid = cgGrid(c, n);
+    const int sgrid = spmvGrid<T, T2>(c, A.nslices);
     const size_t vb = (size_t)std::max<long long>(n, 1) * sizeof(T);
     if (w.x.reserve(vb) || w.r.reserve(vb) || w.p.reserve(vb) || w.t.reserve(vb)) return AVS_ERR_ALLOC;
     DevBuf &bbuf = c->cgRhs;
     if (bbuf.reserve(vb)) return AVS_ERR_ALLOC;
-    if (w.partials.reserve((size_t)grid * 4 * sizeof(double))) return AVS_ERR_ALLOC;
+    if (w.partials.reserve(((size_t)grid * 3 + (size_t)sgrid) * sizeof(double))) return AVS_ERR_ALLOC;
     if (w.scalars.reserve(sizeof(CgScalars))) return AVS_ERR_ALLOC;
     T *x = w.x.as<T>(), *r = w.r.as<T>(), *pp = w.p.as<T>(), *t = w.t.as<T>(), *b = bbuf.as<T>();
     double *parts = w.partials.as<double>();
@@ -378,7 +486,7 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
     c->launches += 2;
     // residual = rhs - A x0 (Eigen: VectorType residual = rhs - mat * x)
     AVS_CUDA_CHECK(cudaMemsetAsync(sc, 0, sizeof(CgScalars), c->stream));
-    launchSpmv<T, T2, false>(c, A, x, t, nullptr, nullptr, grid);
+    launchSpmv<T, T2, false>(c, A, x, t, nullptr, nullptr, sgrid);
     k_cg_init<T><<<grid, CG_THREADS, 0, c->stream>>>(n, b, t, A.invDiag.as<T>(), r, pp, parts, grid);
     const double tiny = (sizeof(T) == 4) ? (double)FLT_MIN : DBL_MIN;
     k_cg_init_scalars<<<1, CG_THREADS, 0, c->stream>>>(parts, grid, p->tolerance, tiny, sc);
@@ -396,9 +504,16 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
         int batch = std::min(checkEvery, maxIters - launched);
         for (int it = 0; it < batch; ++it) {
             const int parity = (launched + it) & 1;
-            launchSpmv<T, T2, true>(c, A, pp, t, ptParts, sc, grid);
-            k_cg_update_xr<T><<<grid, CG_THREADS, 0, c->stream>>>(n, pp, t, A.invDiag.as<T>(), x, r, ptParts, grid, parts, grid, sc, parity);
+            launchSpmv<T, T2, true>(c, A, pp, t, ptParts, sc, sgrid);
+            cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+            if (c->timeSpmv && c->auxEventsUsed + 3 <= c->auxEvents.size()) {
+                e0 = c->auxEvents[c->auxEventsUsed++]; e1 = c->auxEvents[c->auxEventsUsed++]; e2 = c->auxEvents[c->auxEventsUsed++];
+                cudaEventRecord(e0, c->stream);
+            }
+            k_cg_update_xr<T><<<grid, CG_THREADS, 0, c->stream>>>(n, pp, t, A.invDiag.as<T>(), x, r, ptParts, sgrid, parts, grid, sc, parity);
+            if (e1) cudaEventRecord(e1, c->stream);
             k_cg_update_p<T><<<grid, CG_THREADS, 0, c->stream>>>(n, r, A.invDiag.as<T>(), pp, parts, grid, sc, parity);
+            if (e2) cudaEventRecord(e2, c->stream);
             c->launches += 3;
         }
         launched += batch;
@@ -446,7 +561,7 @@ int avs_cg_run(AvsContext *c, SellMatrix &A, const double *dRhs, const double *d
 int avs_spmv_once(AvsContext *c, SellMatrix &A, const double *dX, double *dY) {
     const long long n = A.n;
     if (n == 0) return AVS_OK;
-    const int grid = cgGrid(c, n);
+    const int grid = A.precision == AVS_PRECISION_F32 ? spmvGrid<float, float2>(c, A.nslices) : spmvGrid<double, double2>(c, A.nslices);
     const unsigned eb = (unsigned)((n + 255) / 256);
     if (A.precision == AVS_PRECISION_F32) {
         DevBuf xb, yb;
@@ -476,7 +591,7 @@ int avs_spmv_time(AvsContext *c, SellMatrix &A, int repeats, float *msPerLaunch)
     const long long n = A.n;
     *msPerLaunch = 0;
     if (n == 0 || repeats <= 0) return AVS_OK;
-    const int grid = cgGrid(c, n);
+    const int grid = A.precision == AVS_PRECISION_F32 ? spmvGrid<float, float2>(c, A.nslices) : spmvGrid<double, double2>(c, A.nslices);
     const size_t vs = A.precision == AVS_PRECISION_F32 ? 4 : 8;
     CgWork &w = c->cg;
     if (w.p.reserve((size_t)n * vs) || w.t.reserve((size_t)n * vs) || w.partials.reserve((size_t)grid * 4 * sizeof(double))) return AVS_ERR_ALLOC;

@@ -76,7 +76,11 @@ struct AvsContext {
     DevBuf rowKeys;         // RowKey[n]
     DevBuf x0, rhs, solution;  // fp64 [n]
     DevBuf rowCount, rowOffset; // assembly scratch (int32 / int64)
-    DevBuf csrPtr, csrCol, csrVal;  // canonical CSR of the local rows (int64 / int32 / fp64)
+    DevBuf csrPtr, csrCol, csrVal;  // canonical CSR of the local rows (int64 / int32 / fp64); col/val built lazily
+    DevBuf stageCol, stageVal, diag; // assembly staging area (column-major, MAX_ROW deep) and the diagonal
+    DevBuf slicePairs, edgeTiles, solidW; // per-solve scratch kept across calls (no cudaMalloc/cudaFree in steady state)
+    long long stageStride = 0;
+    bool csrValid = false;
     DeviceScene S;          // host copy of the descriptor handed to kernels
     bool haveSystem = false, haveSolution = false;
 
@@ -91,6 +95,8 @@ struct AvsContext {
     cudaEvent_t evPoll[2] = {};
     std::vector<cudaEvent_t> spmvEvents;  // pairs, only when timeSpmv
     size_t spmvEventsUsed = 0;
+    std::vector<cudaEvent_t> auxEvents;   // triples around the two CG vector kernels, only when timeSpmv
+    size_t auxEventsUsed = 0;
 
     int64_t launches = 0, spmvLaunches = 0;
     float spmvMs = 0.f;
@@ -112,6 +118,9 @@ int avs_sell_from_csr(AvsContext *c, SellMatrix &A, int64_t n, const int64_t *dP
                       const double *dVal, int precision);
 int avs_cg_run(AvsContext *c, SellMatrix &A, const double *dRhs, const double *dX0, double *dXout,
                const AvsParams *p, AvsResult *res);
+int avs_sell_from_stage(AvsContext *c, SellMatrix &A, int64_t n, int64_t nnz, const int32_t *dCount, const int32_t *dStageCol,
+                        const double *dStageVal, long long stride, const double *dDiag, int precision);
+int avs_build_csr(AvsContext *c);
 int avs_spmv_time(AvsContext *c, SellMatrix &A, int repeats, float *msPerLaunch);
 int avs_spmv_once(AvsContext *c, SellMatrix &A, const double *dX, double *dY);
 

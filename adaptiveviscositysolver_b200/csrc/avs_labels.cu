@@ -112,7 +112,7 @@ int avs_stage_weights(AvsContext *c, const AvsParams *p) {
         if (rc) return rc;
     }
     if (p->do_apply_solid_weights) {  // AV.cpp:772-790
-        DevBuf tmp;
+        DevBuf &tmp = c->solidW;
         Grid3<float> g;
         rc = weightsFor(c, tmp, g, S.collision, offC, S.N, n, -S.extrap);
         if (rc) return rc;
@@ -124,8 +124,6 @@ int avs_stage_weights(AvsContext *c, const AvsParams *p) {
             if (rc) return rc;
             LAUNCH_1D(c, k_divide_where_positive, g.count(), S.edgeW[a].d, g.d, g.count());
         }
-        AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        tmp.release();
     }
     AVS_CUDA_CHECK(cudaGetLastError());
     return AVS_OK;
@@ -679,7 +677,7 @@ int avs_stage_octree_labels(AvsContext *c) {
             total += (t0[a].count() + 255) / 256 * 256;
         }
     }
-    DevBuf edgeTiles;
+    DevBuf &edgeTiles = c->edgeTiles;
     for (int l = 0; l < L; ++l) {
         const Grid3<uint8_t> &lab = S.label[l];
         for (int a = 0; a < 3; ++a) {
@@ -757,7 +755,6 @@ int avs_stage_octree_labels(AvsContext *c) {
     c->nRegular = (int64_t)h[0];
     c->nEdge = (int64_t)h[1];
     c->nCenter = (int64_t)h[2];
-    edgeTiles.release();
     AVS_CUDA_CHECK(cudaGetLastError());
     return AVS_OK;
 }

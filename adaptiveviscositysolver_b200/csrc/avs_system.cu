@@ -214,38 +214,58 @@ __device__ __forceinline__ double restrictLeaf(const DeviceScene &S, int axis, i
     return (double)S.vel[axis].raw(face[0], face[1], face[2]);
 }
 
-// levels 0 and 1: one thread per row, leaves added in the reference's order (bit-identical to the oracle)
+// Closed form for level >= 2 (same leaves, regrouped): the in-axis offsets of the 12^l leaves are
+// D = sum_m 2^(l-m) o_m with o_m in {-1,0,1} weighted (1/4,1/2,1/4), i.e. the difference of two uniform
+// l-bit integers, so the weight of in-axis offset d is the hat (2^l - |d|) / 4^l; transverse positions are
+// the 2^l x 2^l block, each weighted 4^-l.  (2^(l+1)-1) * 4^l distinct reads instead of 12^l; all weights are
+// dyadic, so only the order of the fp64 additions differs from the reference's flat sum (<= 1e-13 relative).
+__device__ __forceinline__ double restrictHatTerm(const DeviceScene &S, int axis, int level, const I3 &face, long long q) {
+    const int side = 1 << level;
+    const int t1 = (int)(q % side);
+    const int t2 = (int)((q / side) % side);
+    const int d = (int)(q / ((long long)side * side)) - (side - 1);
+    I3 f;
+    const int a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
+    f[axis] = face[axis] * side + d;
+    f[a1] = face[a1] * side + t1;
+    f[a2] = face[a2] * side + t2;
+    const double w = (double)(side - (d < 0 ? -d : d));
+    return w * (double)S.vel[axis].raw(f[0], f[1], f[2]);
+}
+
+// levels 0 and 1: leaves added in the reference's order (bit-identical to the oracle); level 2: hat form
 __global__ void k_restrict_fine(const __grid_constant__ DeviceScene S, const RowKey *keys, long long n, double *x0) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     RowKey k = keys[i];
-    if (k.level > 1) return;
+    if (k.level > 2) return;
     I3 face = mk3(k.i, k.j, k.k);
     if (k.level == 0) {
         x0[i] = 1.0 * (double)S.vel[k.axis].raw(face[0], face[1], face[2]);
         return;
     }
     double acc = 0;
-    for (int q = 0; q < 12; ++q) {
-        double w;
-        double v = restrictLeaf(S, k.axis, 1, face, q, w);
-        acc += w * v;
+    if (k.level == 1) {
+        for (int q = 0; q < 12; ++q) {
+            double w;
+            double v = restrictLeaf(S, k.axis, 1, face, q, w);
+            acc += w * v;
+        }
+        x0[i] = acc;
+        return;
     }
-    x0[i] = acc;
+    for (int q = 0; q < 7 * 16; ++q) acc += restrictHatTerm(S, k.axis, 2, face, q);
+    x0[i] = acc * (1.0 / 256.0);  // 16^-l
 }
-// levels >= 2: one CTA per row, leaves strided over the threads, fixed-order tree reduction
+// levels >= 3: one CTA per row, terms strided over the threads, fixed-order tree reduction
 __global__ void k_restrict_coarse(const __grid_constant__ DeviceScene S, const RowKey *keys, const int32_t *rows, double *x0) {
     long long i = rows[blockIdx.x];
     RowKey k = keys[i];
     I3 face = mk3(k.i, k.j, k.k);
-    long long leaves = 1;
-    for (int d = 0; d < k.level; ++d) leaves *= 12;
+    const long long side = 1ll << k.level;
+    const long long terms = (2 * side - 1) * side * side;
     double acc = 0;
-    for (long long q = threadIdx.x; q < leaves; q += blockDim.x) {
-        double w;
-        double v = restrictLeaf(S, k.axis, k.level, face, q, w);
-        acc += w * v;
-    }
+    for (long long q = threadIdx.x; q < terms; q += blockDim.x) acc += restrictHatTerm(S, k.axis, k.level, face, q);
     __shared__ double sh[256];
     sh[threadIdx.x] = acc;
     __syncthreads();
@@ -253,12 +273,12 @@ __global__ void k_restrict_coarse(const __grid_constant__ DeviceScene S, const R
         if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) x0[i] = sh[0];
+    if (threadIdx.x == 0) x0[i] = sh[0] / (double)(side * side * side * side);  // 16^-l, exact power of two
 }
 __global__ void k_collect_coarse_rows(const RowKey *keys, long long n, int32_t *rows, unsigned long long *counter) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (keys[i].level >= 2) {
+    if (keys[i].level >= 3) {
         unsigned long long slot = atomicAdd(counter, 1ull);
         rows[slot] = (int32_t)i;  // order is irrelevant: every row is written exactly once
     }
@@ -271,8 +291,8 @@ int avs_stage_restriction(AvsContext *c) {
     unsigned blocks = (unsigned)((n + 255) / 256);
     k_restrict_fine<<<blocks, 256, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), n, c->x0.as<double>());
     ++c->launches;
-    if (c->S.levels > 2) {
-        // rows of level >= 2 are few (a few percent): compact their ids, then one CTA per row
+    if (c->S.levels > 3) {
+        // rows of level >= 3 are few (a few percent): compact their ids, then one CTA per row
         if (c->rowCount.reserve((size_t)n * sizeof(int32_t))) return AVS_ERR_ALLOC;
         unsigned long long *cnt = c->counters.as<unsigned long long>() + 24;
         AVS_CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
@@ -404,10 +424,13 @@ __device__ void buildRow(const DeviceScene &S, int32_t vi, const RowKey &k, doub
     rhsI += fw * x0i;
 }
 
-template <bool FILL>
+// One pass: every row thread writes its merged entries into a column-major staging area
+// (entry j of local row r at j*stride + r, so a warp's writes are coalesced), its entry count, its
+// rhs and its diagonal.  The CG's SJDS matrix is filled straight from the staging area; a canonical
+// CSR (sorted columns) is only built when a caller asks to read the system back.
 __global__ void __launch_bounds__(128) k_assemble(const __grid_constant__ DeviceScene S, const RowKey *keys, const double *x0,
-                                                  long long rowBegin, long long nLocal, int32_t *rowCount,
-                                                  const long long *rowOffset, int32_t *col, double *val, double *rhs,
+                                                  long long rowBegin, long long nLocal, long long stride, int32_t *rowCount,
+                                                  int32_t *stageCol, double *stageVal, double *rhs, double *diagOut,
                                                   int *overflowFlag) {
     long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nLocal) return;
@@ -418,29 +441,33 @@ __global__ void __launch_bounds__(128) k_assemble(const __grid_constant__ Device
     double rhsI = 0;
     buildRow(S, (int32_t)gi, keys[gi], x0[gi], row, rhsI);
     if (row.overflow) *overflowFlag = 1;
-    if (!FILL) {
-        rowCount[r] = row.n;
-        return;
-    }
-    // sort the row by column (insertion sort; rows have 2..46 entries)
-    for (int i = 1; i < row.n; ++i) {
-        int32_t cc = row.col[i];
-        double vv = row.val[i];
-        int j = i - 1;
-        while (j >= 0 && row.col[j] > cc) {
-            row.col[j + 1] = row.col[j];
-            row.val[j + 1] = row.val[j];
-            --j;
-        }
-        row.col[j + 1] = cc;
-        row.val[j + 1] = vv;
-    }
-    long long o = rowOffset[r];
+    rowCount[r] = row.n;
     for (int i = 0; i < row.n; ++i) {
-        col[o + i] = row.col[i];
-        val[o + i] = row.val[i];
+        stageCol[(long long)i * stride + r] = row.col[i];
+        stageVal[(long long)i * stride + r] = row.val[i];
     }
     rhs[r] = rhsI;
+    diagOut[r] = row.val[row.n - 1];  // buildRow adds the diagonal last and it is unique (AV.cpp:2768)
+}
+
+// canonical CSR from the staging area (lazy: only for read-back)
+__global__ void k_csr_from_stage(long long nLocal, long long stride, const int32_t *rowCount, const long long *ptr,
+                                 const int32_t *stageCol, const double *stageVal, int32_t *col, double *val) {
+    long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nLocal) return;
+    int n = rowCount[r];
+    int32_t c[MAX_ROW];
+    double v[MAX_ROW];
+    for (int i = 0; i < n; ++i) {  // insertion sort by column while loading
+        int32_t cc = stageCol[(long long)i * stride + r];
+        double vv = stageVal[(long long)i * stride + r];
+        int j = i - 1;
+        while (j >= 0 && c[j] > cc) { c[j + 1] = c[j]; v[j + 1] = v[j]; --j; }
+        c[j + 1] = cc;
+        v[j + 1] = vv;
+    }
+    long long o = ptr[r];
+    for (int i = 0; i < n; ++i) { col[o + i] = c[i]; val[o + i] = v[i]; }
 }
 
 int avs_stage_system(AvsContext *c, const AvsParams *p) {
@@ -450,28 +477,29 @@ int avs_stage_system(AvsContext *c, const AvsParams *p) {
     c->rowBegin = n * c->rank / c->nranks;
     c->rowEnd = n * (c->rank + 1) / c->nranks;
     const long long nLocal = c->rowEnd - c->rowBegin;
+    const long long stride = (nLocal + 31) / 32 * 32;
+    c->stageStride = stride;
+    c->csrValid = false;
     if (c->rowCount.reserve((size_t)std::max<long long>(nLocal, 1) * sizeof(int32_t))) return AVS_ERR_ALLOC;
     if (c->csrPtr.reserve((size_t)(nLocal + 1) * sizeof(long long))) return AVS_ERR_ALLOC;
     if (c->rhs.reserve((size_t)std::max<long long>(nLocal, 1) * sizeof(double))) return AVS_ERR_ALLOC;
+    if (c->diag.reserve((size_t)std::max<long long>(nLocal, 1) * sizeof(double))) return AVS_ERR_ALLOC;
+    if (c->stageCol.reserve((size_t)std::max<long long>(stride, 32) * MAX_ROW * sizeof(int32_t))) return AVS_ERR_ALLOC;
+    if (c->stageVal.reserve((size_t)std::max<long long>(stride, 32) * MAX_ROW * sizeof(double))) return AVS_ERR_ALLOC;
     int *flag = (int *)(c->counters.as<unsigned long long>() + 25);
     AVS_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(unsigned long long), c->stream));
     c->nnz = 0;
     if (nLocal > 0) {
         unsigned blocks = (unsigned)((nLocal + 127) / 128);
-        k_assemble<false><<<blocks, 128, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->x0.as<double>(), c->rowBegin, nLocal,
-                                                         c->rowCount.as<int32_t>(), nullptr, nullptr, nullptr, nullptr, flag);
+        k_assemble<<<blocks, 128, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->x0.as<double>(), c->rowBegin, nLocal, stride,
+                                                  c->rowCount.as<int32_t>(), c->stageCol.as<int32_t>(), c->stageVal.as<double>(),
+                                                  c->rhs.as<double>(), c->diag.as<double>(), flag);
         ++c->launches;
         int64_t nnz = 0;
         int rc = avs_exclusive_scan_i32_to_i64(c, c->rowCount.as<int32_t>(), c->csrPtr.as<int64_t>(), nLocal, &nnz);
         if (rc) return rc;
         c->nnz = nnz;
         AVS_CUDA_CHECK(cudaMemcpyAsync(c->csrPtr.as<long long>() + nLocal, &c->nnz, sizeof(long long), cudaMemcpyHostToDevice, c->stream));
-        if (c->csrCol.reserve((size_t)std::max<int64_t>(nnz, 1) * sizeof(int32_t))) return AVS_ERR_ALLOC;
-        if (c->csrVal.reserve((size_t)std::max<int64_t>(nnz, 1) * sizeof(double))) return AVS_ERR_ALLOC;
-        k_assemble<true><<<blocks, 128, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->x0.as<double>(), c->rowBegin, nLocal,
-                                                        c->rowCount.as<int32_t>(), c->csrPtr.as<long long>(), c->csrCol.as<int32_t>(),
-                                                        c->csrVal.as<double>(), c->rhs.as<double>(), flag);
-        ++c->launches;
         int h = 0;
         AVS_CUDA_CHECK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -486,6 +514,25 @@ int avs_stage_system(AvsContext *c, const AvsParams *p) {
     AVS_CUDA_CHECK(cudaGetLastError());
     c->haveSystem = true;
     c->haveSolution = false;
+    return AVS_OK;
+}
+
+// Builds csrCol / csrVal of the resident system on demand (avs_get_system_csr).
+int avs_build_csr(AvsContext *c) {
+    if (c->csrValid) return AVS_OK;
+    const long long nLocal = c->rowEnd - c->rowBegin;
+    if (c->csrCol.reserve((size_t)std::max<int64_t>(c->nnz, 1) * sizeof(int32_t))) return AVS_ERR_ALLOC;
+    if (c->csrVal.reserve((size_t)std::max<int64_t>(c->nnz, 1) * sizeof(double))) return AVS_ERR_ALLOC;
+    if (nLocal > 0) {
+        k_csr_from_stage<<<(unsigned)((nLocal + 127) / 128), 128, 0, c->stream>>>(nLocal, c->stageStride, c->rowCount.as<int32_t>(),
+                                                                                 c->csrPtr.as<long long>(), c->stageCol.as<int32_t>(),
+                                                                                 c->stageVal.as<double>(), c->csrCol.as<int32_t>(),
+                                                                                 c->csrVal.as<double>());
+        ++c->launches;
+    }
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    AVS_CUDA_CHECK(cudaGetLastError());
+    c->csrValid = true;
     return AVS_OK;
 }
 

@@ -72,13 +72,15 @@ class SolveInfo:
     stage_ms: Dict[str, float]
     spmv_ms: float
     pending_interpolated_faces: int
+    cg_update_xr_ms: float = 0.0
+    cg_update_p_ms: float = 0.0
 
     @staticmethod
     def from_c(r: AvsResult) -> "SolveInfo":
         return SolveInfo(r.status, r.iterations, r.error, r.levels, r.octree_dofs, r.regular_dofs, r.edge_dofs,
                          r.center_dofs, r.nnz, r.local_rows, r.spmv_launches, r.kernel_launches,
                          {STAGE_NAMES[i]: float(r.stage_ms[i]) for i in range(11)}, float(r.spmv_ms),
-                         r.pending_interpolated_faces)
+                         r.pending_interpolated_faces, float(r.cg_update_xr_ms), float(r.cg_update_p_ms))
 
 
 def _new_result() -> AvsResult:

@@ -94,8 +94,10 @@ typedef struct AvsParams {
 } AvsParams;
 
 /* Caller-allocated output velocity, same layout as AvsFields.vel (AV.cpp:696-706). Only faces the
- * reference would write (regular label >= 0 or SOLIDBOUNDARY, AV.cpp:2843-2890) are modified; the
- * caller pre-fills the arrays with the input velocity (solveGasSubclass updates `vel` in place). */
+ * reference would write (regular label >= 0 or SOLIDBOUNDARY, AV.cpp:2843-2890) differ from the INPUT
+ * velocity (AvsFields.vel): solveGasSubclass updates `vel` in place (AV.cpp:698), so on return the arrays
+ * hold the input velocity with the solved faces overwritten. Device callers (on_device = 1) pre-fill the
+ * arrays themselves (typically out == in). */
 typedef struct AvsVelocityOut {
     float *vel[3];
     int32_t on_device;
@@ -130,10 +132,12 @@ typedef struct AvsResult {
     int64_t center_dofs;      /* centerStressDOFCount (AV.cpp:408)       */
     int64_t nnz;              /* non-zeros of the assembled matrix       */
     int64_t local_rows;       /* rows owned by this rank                 */
-    int64_t spmv_launches;    /* SpMV kernel launches inside the solve   */
+    int64_t spmv_launches;    /* SpMV launches that did work (residual + CG iterations; launches after convergence are no-ops) */
     int64_t kernel_launches;  /* all kernels this call launched          */
     float stage_ms[AVS_STAGE_COUNT];
     float spmv_ms;            /* accumulated device time of the SpMV launches (only with AvsDeviceConfig.time_spmv) */
+    float cg_update_xr_ms;    /* accumulated device time of the x,r update kernel (time_spmv only) */
+    float cg_update_p_ms;     /* accumulated device time of the p update kernel (time_spmv only)   */
     int64_t pending_interpolated_faces; /* regular faces inside coarse cells that still need the octree interpolator
                                           (HDK_OctreeVectorFieldInterpolator); 0 when depth == 1 */
 } AvsResult;
