@@ -72,7 +72,6 @@ int avs_create(const AvsDeviceConfig *cfg, AvsContext **out) {
         c->device = cfg->device;
         c->rank = cfg->rank;
         c->nranks = std::max(1, cfg->nranks);
-        c->nccl = cfg->nccl_comm;
         c->timeSpmv = cfg->time_spmv != 0;
         c->stream = (cudaStream_t)cfg->stream;
     }
@@ -95,6 +94,14 @@ int avs_create(const AvsDeviceConfig *cfg, AvsContext **out) {
     }
     if (c->counters.reserve(64 * sizeof(unsigned long long))) { delete c; return AVS_ERR_ALLOC; }
     memset(&c->S, 0, sizeof(c->S));
+    if (c->nranks > 1) {
+        int rc = avs_dist_init(c, cfg ? cfg->nccl_unique_id : nullptr);
+        if (rc != AVS_OK) {
+            snprintf(g_lastError, sizeof(g_lastError), "%s", c->lastError.c_str());
+            avs_destroy(c);
+            return rc;
+        }
+    }
     *out = c;
     return AVS_OK;
 }
@@ -103,7 +110,8 @@ void avs_destroy(AvsContext *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = {&c->inSurface, &c->inVisc, &c->inDens, &c->inColl, &c->centerW, &c->tiles, &c->brickCount, &c->brickOffset,
+    avs_dist_destroy(c);
+    DevBuf *bufs[] = {&c->fullSolution, &c->inSurface, &c->inVisc, &c->inDens, &c->inColl, &c->centerW, &c->tiles, &c->brickCount, &c->brickOffset,
                       &c->scanTmp, &c->counters, &c->rowKeys, &c->x0, &c->rhs, &c->solution, &c->rowCount, &c->rowOffset,
                       &c->csrPtr, &c->csrCol, &c->csrVal, &c->A.sliceOff, &c->A.val, &c->A.col, &c->A.invDiag, &c->A.meta,
                       &c->cg.x, &c->cg.r, &c->cg.p, &c->cg.t, &c->cg.partials, &c->cg.scalars, &c->cgRhs,
@@ -241,8 +249,12 @@ static int runAssemble(AvsContext *c, const AvsFields *in, const AvsParams *p, A
     cudaEventRecord(c->ev[AVS_STAGE_SYSTEM], c->stream);
     if ((rc = avs_stage_system(c, p))) return rc;
     // the CG's matrix format is part of "Build Octree Linear System" (the reference's setFromTriplets, AV.cpp:614)
+    c->nHalo = 0;
+    c->haloIndex = nullptr;
+    if (c->nranks > 1 && (rc = avs_dist_build_halo(c))) return rc;
     if ((rc = avs_sell_from_stage(c, c->A, c->rowEnd - c->rowBegin, c->nnz, c->rowCount.as<int32_t>(), c->stageCol.as<int32_t>(),
-                                  c->stageVal.as<double>(), c->stageStride, c->diag.as<double>(), p->precision))) return rc;
+                                  c->stageVal.as<double>(), c->stageStride, c->diag.as<double>(), p->precision,
+                                  c->rowBegin, c->rowEnd, c->haloIndex))) return rc;
     cudaEventRecord(c->ev[AVS_STAGE_SOLVE], c->stream);
     collectStageTimes(c, res, AVS_STAGE_UPLOAD, AVS_STAGE_SYSTEM);
     fillCounts(c, res);
@@ -251,7 +263,6 @@ static int runAssemble(AvsContext *c, const AvsFields *in, const AvsParams *p, A
 
 static int runSolve(AvsContext *c, const AvsParams *p, AvsResult *res) {
     if (!c->haveSystem) return AVS_ERR_INVALID_ARGUMENT;
-    if (c->nranks > 1) return AVS_ERR_UNSUPPORTED;  // multi-GPU CG goes through avs_solve_resident once NCCL is wired (round 1: single GPU)
     const long long n = c->rowEnd - c->rowBegin;
     if (c->solution.reserve((size_t)std::max<long long>(n, 1) * sizeof(double))) return AVS_ERR_ALLOC;
     c->spmvEventsUsed = 0;
@@ -313,6 +324,11 @@ static int runApply(AvsContext *c, AvsVelocityOut *out, AvsResult *res) {
             AVS_CUDA_CHECK(cudaMemcpyAsync(tmp[a].p, out->vel[a], bytes, cudaMemcpyHostToDevice, c->stream));
             dOut[a] = tmp[a].as<float>();
         }
+    }
+    if (c->nranks > 1) {
+        if (c->fullSolution.reserve((size_t)std::max<int64_t>(c->nRows, 1) * sizeof(double))) return AVS_ERR_ALLOC;
+        int rcg = avs_dist_allgather_solution(c, c->solution.as<double>(), c->fullSolution.as<double>());
+        if (rcg) return rcg;
     }
     unsigned long long pending = 0;
     int rc = avs_apply_regular(c, dOut, &pending);
@@ -386,6 +402,13 @@ int avs_get_sizes(AvsContext *c, int64_t *nRows, int64_t *nnz, int32_t *levels) 
     if (nRows) *nRows = c->nRows;
     if (nnz) *nnz = c->nnz;
     if (levels) *levels = c->S.levels;
+    return AVS_OK;
+}
+
+int avs_get_local_range(AvsContext *c, int64_t *b, int64_t *e) {
+    if (!c) return AVS_ERR_INVALID_ARGUMENT;
+    if (b) *b = c->rowBegin;
+    if (e) *e = c->rowEnd;
     return AVS_OK;
 }
 
@@ -477,6 +500,7 @@ static int uploadCsr(AvsContext *c, int64_t n, const int64_t *rowPtr, const int3
 int avs_cg_csr(AvsContext *c, int64_t n, const int64_t *rowPtr, const int32_t *col, const double *val, const double *rhs, double *x,
                const AvsParams *p, AvsResult *res) {
     if (!c || !p || p->size != sizeof(AvsParams) || !res || res->size != sizeof(AvsResult) || !rhs || !x) return AVS_ERR_INVALID_ARGUMENT;
+    if (c->nranks > 1) return AVS_ERR_UNSUPPORTED;  // caller matrices are single-GPU only
     cudaSetDevice(c->device);
     memset(res->stage_ms, 0, sizeof(res->stage_ms));
     c->launches = 0;
@@ -506,6 +530,7 @@ int avs_cg_csr(AvsContext *c, int64_t n, const int64_t *rowPtr, const int32_t *c
 int avs_spmv_csr(AvsContext *c, int64_t n, const int64_t *rowPtr, const int32_t *col, const double *val, const double *x, double *y,
                  int precision, int repeats, float *msPerLaunch) {
     if (!c || !x || !y) return AVS_ERR_INVALID_ARGUMENT;
+    if (c->nranks > 1) return AVS_ERR_UNSUPPORTED;
     cudaSetDevice(c->device);
     int rc = uploadCsr(c, n, rowPtr, col, val, precision);
     if (rc) return rc;

@@ -51,7 +51,8 @@ __global__ void k_sjds_count(long long n, const int32_t *rowLen, long long nslic
 // fill from the assembly staging area (entry j of row r at j*stride + r)
 template <class T, class T2>
 __global__ void k_sjds_fill_stage(long long n, const int32_t *rowLen, const int32_t *stageCol, const double *stageVal, long long stride,
-                                  long long nslices, const int32_t *meta, const long long *sliceOff, T2 *val2, int2 *col2) {
+                                  long long nslices, const int32_t *meta, const long long *sliceOff, T2 *val2, int2 *col2,
+                                  long long rowBegin, long long rowEnd, const long long *haloIndex) {
     long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (s >= nslices) return;
@@ -73,6 +74,9 @@ __global__ void k_sjds_fill_stage(long long n, const int32_t *rowLen, const int3
             cc.x = stageCol[k0];
             if (2 * j + 1 < len) { v.y = (T)stageVal[k1]; cc.y = stageCol[k1]; }
             else { v.y = (T)0; cc.y = cc.x; }
+            // global column -> local index: owned rows first, then the halo slots (multi-GPU row partition)
+            cc.x = (cc.x >= rowBegin && cc.x < rowEnd) ? (int)(cc.x - rowBegin) : (int)((rowEnd - rowBegin) + haloIndex[cc.x]);
+            cc.y = (cc.y >= rowBegin && cc.y < rowEnd) ? (int)(cc.y - rowBegin) : (int)((rowEnd - rowBegin) + haloIndex[cc.y]);
             val2[base + off + lane] = v;
             col2[base + off + lane] = cc;
         }
@@ -187,7 +191,8 @@ int avs_sell_from_csr(AvsContext *c, SellMatrix &A, int64_t n, const int64_t *dP
 }
 
 int avs_sell_from_stage(AvsContext *c, SellMatrix &A, int64_t n, int64_t nnz, const int32_t *dCount, const int32_t *dStageCol,
-                        const double *dStageVal, long long stride, const double *dDiag, int precision) {
+                        const double *dStageVal, long long stride, const double *dDiag, int precision,
+                        long long rowBegin, long long rowEnd, const long long *haloIndex) {
     A.nnz = nnz;
     int64_t totalPairs = 0;
     int rc = sjdsLayout(c, A, n, dCount, precision, &totalPairs);
@@ -195,11 +200,11 @@ int avs_sell_from_stage(AvsContext *c, SellMatrix &A, int64_t n, int64_t nnz, co
     unsigned blocks = (unsigned)((A.nslices * 32 + 255) / 256);
     if (precision == AVS_PRECISION_F32) {
         k_sjds_fill_stage<float, float2><<<blocks, 256, 0, c->stream>>>(n, dCount, dStageCol, dStageVal, stride, A.nslices, A.meta.as<int32_t>(),
-                                                                       A.sliceOff.as<long long>(), A.val.as<float2>(), A.col.as<int2>());
+                                                                       A.sliceOff.as<long long>(), A.val.as<float2>(), A.col.as<int2>(), rowBegin, rowEnd, haloIndex);
         k_inv_diag_from_array<float><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, dDiag, A.invDiag.as<float>());
     } else {
         k_sjds_fill_stage<double, double2><<<blocks, 256, 0, c->stream>>>(n, dCount, dStageCol, dStageVal, stride, A.nslices, A.meta.as<int32_t>(),
-                                                                         A.sliceOff.as<long long>(), A.val.as<double2>(), A.col.as<int2>());
+                                                                         A.sliceOff.as<long long>(), A.val.as<double2>(), A.col.as<int2>(), rowBegin, rowEnd, haloIndex);
         k_inv_diag_from_array<double><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, dDiag, A.invDiag.as<double>());
     }
     c->launches += 2;
@@ -467,29 +472,43 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
     CgWork &w = c->cg;
     const int grid = cgGrid(c, n);
     const int sgrid = spmvGrid<T, T2>(c, A.nslices);
+    const bool dist = c->dist != nullptr;
+    const long long nHalo = dist ? c->nHalo : 0;
     const size_t vb = (size_t)std::max<long long>(n, 1) * sizeof(T);
-    if (w.x.reserve(vb) || w.r.reserve(vb) || w.p.reserve(vb) || w.t.reserve(vb)) return AVS_ERR_ALLOC;
+    if (w.x.reserve(vb) || w.r.reserve(vb) || w.t.reserve(vb)) return AVS_ERR_ALLOC;
+    if (w.p.reserve((size_t)std::max<long long>(n + nHalo, 1) * sizeof(T))) return AVS_ERR_ALLOC;  // owned rows + halo slots
     DevBuf &bbuf = c->cgRhs;
     if (bbuf.reserve(vb)) return AVS_ERR_ALLOC;
-    if (w.partials.reserve(((size_t)grid * 3 + (size_t)sgrid) * sizeof(double))) return AVS_ERR_ALLOC;
+    if (w.partials.reserve(((size_t)grid * 3 + (size_t)sgrid + 16) * sizeof(double))) return AVS_ERR_ALLOC;
     if (w.scalars.reserve(sizeof(CgScalars))) return AVS_ERR_ALLOC;
     T *x = w.x.as<T>(), *r = w.r.as<T>(), *pp = w.p.as<T>(), *t = w.t.as<T>(), *b = bbuf.as<T>();
     double *parts = w.partials.as<double>();
     double *ptParts = parts + 3 * (size_t)grid;
+    double *red = ptParts + sgrid;  // 16 doubles: globally reduced scalars (multi-GPU)
     CgScalars *sc = w.scalars.as<CgScalars>();
     res->iterations = 0;
     res->error = 0;
-    if (n == 0) return AVS_OK;
-    const unsigned eb = (unsigned)((n + 255) / 256);
+    if (n == 0 && !dist) return AVS_OK;
+    const unsigned eb = (unsigned)((std::max<long long>(n, 1) + 255) / 256);
     k_convert_in<T><<<eb, 256, 0, c->stream>>>(n, dRhs, b);
     k_convert_in<T><<<eb, 256, 0, c->stream>>>(n, dX0, x);
     c->launches += 2;
     // residual = rhs - A x0 (Eigen: VectorType residual = rhs - mat * x)
     AVS_CUDA_CHECK(cudaMemsetAsync(sc, 0, sizeof(CgScalars), c->stream));
-    launchSpmv<T, T2, false>(c, A, x, t, nullptr, nullptr, sgrid);
+    int rcd;
+    if (dist) {  // the SpMV reads its input with halo slots: stage x0 in p's buffer and exchange
+        AVS_CUDA_CHECK(cudaMemcpyAsync(pp, x, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, c->stream));
+        if ((rcd = avs_dist_halo_exchange(c, pp, A.precision))) return rcd;
+        launchSpmv<T, T2, false>(c, A, pp, t, nullptr, nullptr, sgrid);
+    } else
+        launchSpmv<T, T2, false>(c, A, x, t, nullptr, nullptr, sgrid);
     k_cg_init<T><<<grid, CG_THREADS, 0, c->stream>>>(n, b, t, A.invDiag.as<T>(), r, pp, parts, grid);
     const double tiny = (sizeof(T) == 4) ? (double)FLT_MIN : DBL_MIN;
-    k_cg_init_scalars<<<1, CG_THREADS, 0, c->stream>>>(parts, grid, p->tolerance, tiny, sc);
+    if (dist) {
+        if ((rcd = avs_dist_allreduce_parts(c, parts, grid, 3, red + 4))) return rcd;
+        k_cg_init_scalars<<<1, CG_THREADS, 0, c->stream>>>(red + 4, 1, p->tolerance, tiny, sc);
+    } else
+        k_cg_init_scalars<<<1, CG_THREADS, 0, c->stream>>>(parts, grid, p->tolerance, tiny, sc);
     c->launches += 2;
 
     const int maxIters = p->max_iterations;
@@ -504,15 +523,28 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
         int batch = std::min(checkEvery, maxIters - launched);
         for (int it = 0; it < batch; ++it) {
             const int parity = (launched + it) & 1;
+            if (dist && (rcd = avs_dist_halo_exchange(c, pp, A.precision))) return rcd;
             launchSpmv<T, T2, true>(c, A, pp, t, ptParts, sc, sgrid);
+            const double *ptSrc = ptParts, *rrSrc = parts;
+            int ptN = sgrid, rrN = grid;
+            if (dist) {
+                if ((rcd = avs_dist_allreduce_parts(c, ptParts, sgrid, 1, red))) return rcd;
+                ptSrc = red;
+                ptN = 1;
+            }
             cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
             if (c->timeSpmv && c->auxEventsUsed + 3 <= c->auxEvents.size()) {
                 e0 = c->auxEvents[c->auxEventsUsed++]; e1 = c->auxEvents[c->auxEventsUsed++]; e2 = c->auxEvents[c->auxEventsUsed++];
                 cudaEventRecord(e0, c->stream);
             }
-            k_cg_update_xr<T><<<grid, CG_THREADS, 0, c->stream>>>(n, pp, t, A.invDiag.as<T>(), x, r, ptParts, sgrid, parts, grid, sc, parity);
+            k_cg_update_xr<T><<<grid, CG_THREADS, 0, c->stream>>>(n, pp, t, A.invDiag.as<T>(), x, r, ptSrc, ptN, parts, grid, sc, parity);
             if (e1) cudaEventRecord(e1, c->stream);
-            k_cg_update_p<T><<<grid, CG_THREADS, 0, c->stream>>>(n, r, A.invDiag.as<T>(), pp, parts, grid, sc, parity);
+            if (dist) {
+                if ((rcd = avs_dist_allreduce_parts(c, parts, grid, 2, red + 1))) return rcd;
+                rrSrc = red + 1;
+                rrN = 1;
+            }
+            k_cg_update_p<T><<<grid, CG_THREADS, 0, c->stream>>>(n, r, A.invDiag.as<T>(), pp, rrSrc, rrN, sc, parity);
             if (e2) cudaEventRecord(e2, c->stream);
             c->launches += 3;
         }

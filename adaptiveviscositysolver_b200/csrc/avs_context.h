@@ -59,7 +59,9 @@ struct CgWork {
 struct AvsContext {
     int device = 0;
     int rank = 0, nranks = 1;
-    void *nccl = nullptr;
+    void *dist = nullptr;            // DistState (avs_dist.cu) when nranks > 1
+    long long nHalo = 0;              // off-rank columns referenced by the local rows
+    const long long *haloIndex = nullptr;  // device: global column -> halo slot (valid where flagged)
     cudaStream_t stream = nullptr;
     bool ownStream = false;
     bool timeSpmv = false;
@@ -74,7 +76,7 @@ struct AvsContext {
     DevBuf tiles;           // tile-occupancy scratch
     DevBuf brickCount, brickOffset, scanTmp, counters;
     DevBuf rowKeys;         // RowKey[n]
-    DevBuf x0, rhs, solution;  // fp64 [n]
+    DevBuf x0, rhs, solution, fullSolution;  // fp64: x0 [N], rhs/solution [local rows], fullSolution [N] (multi-GPU apply)
     DevBuf rowCount, rowOffset; // assembly scratch (int32 / int64)
     DevBuf csrPtr, csrCol, csrVal;  // canonical CSR of the local rows (int64 / int32 / fp64); col/val built lazily
     DevBuf stageCol, stageVal, diag; // assembly staging area (column-major, MAX_ROW deep) and the diagonal
@@ -119,8 +121,15 @@ int avs_sell_from_csr(AvsContext *c, SellMatrix &A, int64_t n, const int64_t *dP
 int avs_cg_run(AvsContext *c, SellMatrix &A, const double *dRhs, const double *dX0, double *dXout,
                const AvsParams *p, AvsResult *res);
 int avs_sell_from_stage(AvsContext *c, SellMatrix &A, int64_t n, int64_t nnz, const int32_t *dCount, const int32_t *dStageCol,
-                        const double *dStageVal, long long stride, const double *dDiag, int precision);
+                        const double *dStageVal, long long stride, const double *dDiag, int precision,
+                        long long rowBegin, long long rowEnd, const long long *haloIndex);
 int avs_build_csr(AvsContext *c);
+int avs_dist_init(AvsContext *c, const void *uniqueId128);
+void avs_dist_destroy(AvsContext *c);
+int avs_dist_build_halo(AvsContext *c);
+int avs_dist_halo_exchange(AvsContext *c, void *p, int precision);
+int avs_dist_allreduce_parts(AvsContext *c, const double *parts, int nparts, int count, double *out);
+int avs_dist_allgather_solution(AvsContext *c, const double *local, double *full);
 int avs_spmv_time(AvsContext *c, SellMatrix &A, int repeats, float *msPerLaunch);
 int avs_spmv_once(AvsContext *c, SellMatrix &A, const double *dX, double *dY);
 

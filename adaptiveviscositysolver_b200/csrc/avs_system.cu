@@ -569,7 +569,7 @@ int avs_apply_regular(AvsContext *c, float *dOut[3], unsigned long long *hostPen
     AVS_CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
     for (int a = 0; a < 3; ++a) {
         size_t n = c->S.regular[a].count();
-        k_apply_regular<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->S, a, c->solution.as<double>(), dOut[a], cnt);
+        k_apply_regular<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->S, a, c->nranks > 1 ? c->fullSolution.as<double>() : c->solution.as<double>(), dOut[a], cnt);
         ++c->launches;
     }
     AVS_CUDA_CHECK(cudaMemcpyAsync(hostPending, cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));

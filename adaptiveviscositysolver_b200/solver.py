@@ -138,15 +138,32 @@ def fields_to_c(scene: Scene, keep: list) -> AvsFields:
     return s
 
 
+def nccl_unique_id() -> bytes:
+    """128-byte NCCL unique id (call on rank 0, broadcast to every rank, pass to ``Solver``)."""
+    buf = C.create_string_buffer(128)
+    rc = _lib.load().avs_nccl_unique_id(buf)
+    if rc != AVS_OK:
+        raise AvsError(rc, "avs_nccl_unique_id")
+    return buf.raw
+
+
 class Solver:
     """One ``AvsContext``: a single-threaded solver bound to one GPU (include/avs.h)."""
 
-    def __init__(self, device: int = 0, rank: int = 0, nranks: int = 1, time_spmv: bool = False, stream: int = 0):
+    def __init__(self, device: int = 0, rank: int = 0, nranks: int = 1, time_spmv: bool = False, stream: int = 0,
+                 nccl_unique_id: Optional[bytes] = None):
         self._L = _lib.load()
         cfg = AvsDeviceConfig()
         cfg.size = C.sizeof(AvsDeviceConfig)
         cfg.device, cfg.rank, cfg.nranks = device, rank, nranks
-        cfg.nccl_comm = None
+        self._idbuf = None
+        if nranks > 1:
+            if nccl_unique_id is None or len(nccl_unique_id) != 128:
+                raise ValueError("nranks > 1 needs the 128-byte id from nccl_unique_id() on rank 0")
+            self._idbuf = C.create_string_buffer(bytes(nccl_unique_id), 128)
+            cfg.nccl_unique_id = C.cast(self._idbuf, C.c_void_p)
+        else:
+            cfg.nccl_unique_id = None
         cfg.stream = stream or None
         cfg.time_spmv = int(time_spmv)
         h = C.c_void_p()
@@ -229,6 +246,11 @@ class Solver:
         self._check(self._L.avs_get_sizes(self._h, C.byref(n), C.byref(nnz), C.byref(lv)), "avs_get_sizes")
         return n.value, nnz.value, lv.value
 
+    def local_range(self):
+        b, e = C.c_int64(), C.c_int64()
+        self._check(self._L.avs_get_local_range(self._h, C.byref(b), C.byref(e)), "avs_get_local_range")
+        return b.value, e.value
+
     def keys(self) -> np.ndarray:
         n, _, _ = self.sizes()
         k = np.empty((n, 5), np.int32)
@@ -238,18 +260,19 @@ class Solver:
     def system(self):
         """(row_ptr, col, val, rhs, x0) of the resident system (canonical CSR, columns sorted)."""
         n, nnz, _ = self.sizes()
-        ptr = np.empty(n + 1, np.int64)
+        b, e = self.local_range()
+        ptr = np.empty(e - b + 1, np.int64)
         col = np.empty(nnz, np.int32)
         val = np.empty(nnz, np.float64)
-        rhs = np.empty(n, np.float64)
+        rhs = np.empty(e - b, np.float64)
         x0 = np.empty(n, np.float64)
         self._check(self._L.avs_get_system_csr(self._h, ptr.ctypes.data, col.ctypes.data, val.ctypes.data,
                                                rhs.ctypes.data, x0.ctypes.data), "avs_get_system_csr")
         return ptr, col, val, rhs, x0
 
     def solution(self) -> np.ndarray:
-        n, _, _ = self.sizes()
-        x = np.empty(n, np.float64)
+        b, e = self.local_range()
+        x = np.empty(e - b, np.float64)
         self._check(self._L.avs_get_solution(self._h, x.ctypes.data), "avs_get_solution")
         return x
 

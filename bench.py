@@ -213,7 +213,13 @@ def main():
     peak, peak_src = peaks()
     scene = make_scene(w)
     params = Params(octree_levels=w["L"], tolerance=w["tol"], single_precision=args.fp32)
-    solver = Solver(device=local, rank=rank, nranks=world, time_spmv=not args.no_spmv_events)
+    uid = None
+    if world > 1:
+        from adaptiveviscositysolver_b200.solver import nccl_unique_id
+        box = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+    solver = Solver(device=local, rank=rank, nranks=world, time_spmv=not args.no_spmv_events, nccl_unique_id=uid)
     dscene = to_device_scene(scene, torch, dev)
     dout = [v.data.clone() for v in dscene.vel]
     stream = None
@@ -246,10 +252,17 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
     N, iters, nnz = info.octree_dofs, info.iterations, info.nnz
+    n_local = info.local_rows
+    if world > 1:
+        tn = torch.tensor([nnz], device=dev, dtype=torch.int64)
+        dist.all_reduce(tn)
+        nnz_total = int(tn.item())
+    else:
+        nnz_total = nnz
     value = N * iters / (dev_ms * 1e-3)
 
     s = 4 if args.fp32 else 8
-    alg_bytes = nnz * (s + 4) + (N + 1) * 4 + 2 * N * s
+    alg_bytes = nnz * (s + 4) + (n_local + 1) * 4 + 2 * n_local * s   # this rank's SpMV
     # the same kernel launched back to back (matrix >> L2), for reference / when events are off
     iso_ms, _ = solver.time_spmv_resident(20)
     spmv_avg_ms = spmv_ms / max(spmv_n, 1) if spmv_ms > 0 else iso_ms
@@ -270,6 +283,10 @@ def main():
             einfo = solver.solve(pscene, params, pout)
         torch.cuda.synchronize()
         e_ms = (time.perf_counter() - t0) * 1e3 / k
+        if world > 1:
+            te = torch.tensor([e_ms], device=dev)
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            e_ms = float(te.item())
         e2e = {"value": N * einfo.iterations / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": e_ms,
                "stage_ms": {k2: round(v, 3) for k2, v in einfo.stage_ms.items()}}
@@ -277,7 +294,7 @@ def main():
 
     # ---- CPU baseline: oracle CG on the same matrix ------------------------------------------------
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import avs_oracle as orc
         ptr, col, val, rhs, x0 = solver.system()
         cores = orc.num_threads()
@@ -295,7 +312,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32" if args.fp32 else "f64", "data": "synthetic",
-            "config": {"workload": w["desc"], "N": int(N), "nnz": int(nnz), "levels": int(info.levels), "iterations": int(iters),
+            "config": {"workload": w["desc"], "N": int(N), "nnz": int(nnz_total), "rows_per_rank": int(n_local), "levels": int(info.levels), "iterations": int(iters),
                        "rel_error": info.error, "tolerance": w["tol"], "regular_dofs": int(info.regular_dofs),
                        "l2": "matrix+vectors per SpMV = %.0f MB vs 126 MB L2 (inputs larger than L2, no flush)" % (alg_bytes / 1e6),
                        "wall_ms_per_step": wall_ms,
@@ -305,7 +322,7 @@ def main():
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": spmv_avg_ms, "launches_timed": int(spmv_n),
                          "back_to_back_ms": iso_ms, "cg_update_xr_ms_per_iter": info.cg_update_xr_ms / max(info.spmv_launches - 1, 1),
                          "cg_update_p_ms_per_iter": info.cg_update_p_ms / max(info.spmv_launches - 1, 1),
-                         "cg_iteration_frac": (N * iters * (alg_bytes / N + 11 * s)) / (info.stage_ms["solve"] * 1e-3) / 1e9 / peak},
+                         "cg_iteration_frac": (iters * (alg_bytes + 11 * n_local * s)) / (info.stage_ms["solve"] * 1e-3) / 1e9 / peak},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": int(launches),

@@ -147,7 +147,8 @@ typedef struct AvsDeviceConfig {
     int32_t device;           /* CUDA device ordinal                                        */
     int32_t rank;             /* this process' rank in the row partition (0 when nranks==1) */
     int32_t nranks;           /* number of ranks sharing one solve (1 = single GPU)         */
-    void *nccl_comm;          /* ncclComm_t created by the host (torch.distributed / NCCL); NULL when nranks==1 */
+    const void *nccl_unique_id; /* 128-byte ncclUniqueId from avs_nccl_unique_id() on rank 0, broadcast by the host;
+                                 NULL when nranks==1. The library creates its own communicator from it. */
     void *stream;             /* cudaStream_t to run on; NULL = the library creates its own */
     int32_t time_spmv;        /* 1: bracket every SpMV launch with CUDA events (bench only) */
 } AvsDeviceConfig;
@@ -156,6 +157,7 @@ typedef struct AvsContext AvsContext;
 
 /* life cycle */
 int avs_abi_version(void);
+int avs_nccl_unique_id(void *out128);  /* rank 0: fill 128 bytes; the host broadcasts them to every rank */
 int avs_create(const AvsDeviceConfig *cfg, AvsContext **out);
 void avs_destroy(AvsContext *ctx);
 const char *avs_status_string(int status);
@@ -179,9 +181,11 @@ int avs_apply(AvsContext *ctx, AvsVelocityOut *out, AvsResult *res);
  * keys: n x 5 int32 (level, axis, i, j, k) -- DOF numbering is NOT part of the parity contract,
  * results are compared by geometric key. */
 int avs_get_sizes(AvsContext *ctx, int64_t *n_rows, int64_t *nnz, int32_t *levels);
+int avs_get_local_range(AvsContext *ctx, int64_t *row_begin, int64_t *row_end);  /* rows owned by this rank */
 int avs_get_keys(AvsContext *ctx, int32_t *keys);
+/* row_ptr/col/val/rhs cover the rows this rank owns (global column ids); x0 is the full restricted u^n [n_rows] */
 int avs_get_system_csr(AvsContext *ctx, int64_t *row_ptr, int32_t *col, double *val, double *rhs, double *x0);
-int avs_get_solution(AvsContext *ctx, double *x);
+int avs_get_solution(AvsContext *ctx, double *x);   /* the rows this rank owns: [N*rank/nranks, N*(rank+1)/nranks) */
 /* kind: 0 cell labels (uint8 INACTIVE/ACTIVE/UP/DOWN), 1 face labels, 2 edge labels, 3 centre labels,
  * 4 regular-grid face labels (int32: >=0 DOF, -1 UNASSIGNED, -2 SOLIDBOUNDARY, -3 OUTSIDE; for kinds 2,3
  * active entries read 0), 5 centre weights (float32), 6 edge weights (float32).
