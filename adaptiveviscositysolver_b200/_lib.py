@@ -18,7 +18,7 @@ STAGE_NAMES = ["upload", "surface_weights", "octree", "regular_labels", "octree_
                "system", "solve", "apply", "download", "total", "_"]
 
 EXPORTS = [
-    "avs_abi_version", "avs_nccl_unique_id", "avs_get_local_range", "avs_create", "avs_destroy", "avs_status_string", "avs_last_error", "avs_default_params",
+    "avs_abi_version", "avs_nccl_unique_id", "avs_get_local_range", "avs_get_row_starts", "avs_create", "avs_destroy", "avs_status_string", "avs_last_error", "avs_default_params",
     "avs_solve", "avs_assemble", "avs_solve_resident", "avs_apply", "avs_get_sizes", "avs_get_keys",
     "avs_get_system_csr", "avs_get_solution", "avs_get_grid", "avs_cg_csr", "avs_spmv_csr", "avs_time_spmv_resident",
 ]
@@ -55,6 +55,7 @@ class AvsResult(C.Structure):
                 ("spmv_launches", C.c_int64), ("kernel_launches", C.c_int64),
                 ("stage_ms", C.c_float * AVS_STAGE_COUNT), ("spmv_ms", C.c_float),
                 ("cg_update_xr_ms", C.c_float), ("cg_update_p_ms", C.c_float),
+                ("dist_mode", C.c_int32), ("reserved0", C.c_int32), ("halo_columns", C.c_int64),
                 ("pending_interpolated_faces", C.c_int64)]
 
 
@@ -99,6 +100,7 @@ def load():
     L.avs_get_keys.argtypes = [vp, vp]
     L.avs_get_local_range.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.avs_nccl_unique_id.argtypes = [vp]
+    L.avs_get_row_starts.argtypes = [vp, vp]
     L.avs_get_system_csr.argtypes = [vp, vp, vp, vp, vp, vp]
     L.avs_get_solution.argtypes = [vp, vp]
     L.avs_get_grid.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]

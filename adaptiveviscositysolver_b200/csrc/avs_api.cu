@@ -115,7 +115,7 @@ void avs_destroy(AvsContext *c) {
                       &c->scanTmp, &c->counters, &c->rowKeys, &c->x0, &c->rhs, &c->solution, &c->rowCount, &c->rowOffset,
                       &c->csrPtr, &c->csrCol, &c->csrVal, &c->A.sliceOff, &c->A.val, &c->A.col, &c->A.invDiag, &c->A.meta,
                       &c->cg.x, &c->cg.r, &c->cg.p, &c->cg.t, &c->cg.partials, &c->cg.scalars, &c->cgRhs,
-                      &c->stageCol, &c->stageVal, &c->diag, &c->slicePairs, &c->edgeTiles, &c->solidW};
+                      &c->stageCol, &c->stageVal, &c->diag, &c->slicePairs, &c->edgeTiles, &c->solidW, &c->signA, &c->signB, &c->brickCost, &c->brickCostPrefix};
     for (DevBuf *b : bufs) b->release();
     for (int a = 0; a < 3; ++a) {
         c->inVel[a].release(); c->inFaceW[a].release(); c->inCollVel[a].release(); c->edgeW[a].release(); c->regular[a].release();
@@ -216,6 +216,8 @@ static void fillCounts(AvsContext *c, AvsResult *res) {
     res->local_rows = c->rowEnd - c->rowBegin;
     res->kernel_launches = c->launches;
     res->spmv_launches = c->spmvLaunches;
+    res->dist_mode = avs_dist_mode(c);
+    res->halo_columns = c->nHalo;
 }
 
 static void collectStageTimes(AvsContext *c, AvsResult *res, int first, int last) {
@@ -412,6 +414,12 @@ int avs_get_local_range(AvsContext *c, int64_t *b, int64_t *e) {
     return AVS_OK;
 }
 
+int avs_get_row_starts(AvsContext *c, int64_t *starts) {
+    if (!c || !starts || c->rowStarts.empty()) return AVS_ERR_INVALID_ARGUMENT;
+    for (int q = 0; q <= c->nranks; ++q) starts[q] = c->rowStarts[q];
+    return AVS_OK;
+}
+
 int avs_get_keys(AvsContext *c, int32_t *keys) {
     if (!c || !keys) return AVS_ERR_INVALID_ARGUMENT;
     cudaSetDevice(c->device);
@@ -491,6 +499,8 @@ static int uploadCsr(AvsContext *c, int64_t n, const int64_t *rowPtr, const int3
     c->nnz = nnz;
     c->rowBegin = 0;
     c->rowEnd = n;
+    c->rowStarts.assign(2, 0);
+    c->rowStarts[1] = n;
     c->haveSystem = false;  // no geometry behind this matrix
     c->csrValid = true;
     c->haveSolution = false;

@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 
 #include "avs_context.h"
@@ -482,6 +483,12 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
     if (w.partials.reserve(((size_t)grid * 3 + (size_t)sgrid + 16) * sizeof(double))) return AVS_ERR_ALLOC;
     if (w.scalars.reserve(sizeof(CgScalars))) return AVS_ERR_ALLOC;
     T *x = w.x.as<T>(), *r = w.r.as<T>(), *pp = w.p.as<T>(), *t = w.t.as<T>(), *b = bbuf.as<T>();
+    if (dist) {  // peer-memory mode: p lives in the region the peers have mapped
+        int rcp = AVS_OK;
+        void *shared = avs_dist_prepare_p(c, &rcp);
+        if (rcp) return rcp;
+        if (shared) pp = (T *)shared;
+    }
     double *parts = w.partials.as<double>();
     double *ptParts = parts + 3 * (size_t)grid;
     double *red = ptParts + sgrid;  // 16 doubles: globally reduced scalars (multi-GPU)
@@ -498,19 +505,22 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
     int rcd;
     if (dist) {  // the SpMV reads its input with halo slots: stage x0 in p's buffer and exchange
         AVS_CUDA_CHECK(cudaMemcpyAsync(pp, x, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, c->stream));
-        if ((rcd = avs_dist_halo_exchange(c, pp, A.precision))) return rcd;
+        if ((rcd = avs_dist_halo_exchange(c, pp, A.precision, nullptr))) return rcd;
         launchSpmv<T, T2, false>(c, A, pp, t, nullptr, nullptr, sgrid);
+        // barrier: peers may still be pulling the staged x0 out of this buffer; k_cg_init overwrites it
+        if ((rcd = avs_dist_allreduce_parts(c, parts, 0, 1, red + 8, nullptr))) return rcd;
     } else
         launchSpmv<T, T2, false>(c, A, x, t, nullptr, nullptr, sgrid);
     k_cg_init<T><<<grid, CG_THREADS, 0, c->stream>>>(n, b, t, A.invDiag.as<T>(), r, pp, parts, grid);
     const double tiny = (sizeof(T) == 4) ? (double)FLT_MIN : DBL_MIN;
     if (dist) {
-        if ((rcd = avs_dist_allreduce_parts(c, parts, grid, 3, red + 4))) return rcd;
+        if ((rcd = avs_dist_allreduce_parts(c, parts, grid, 3, red + 4, nullptr))) return rcd;
         k_cg_init_scalars<<<1, CG_THREADS, 0, c->stream>>>(red + 4, 1, p->tolerance, tiny, sc);
     } else
         k_cg_init_scalars<<<1, CG_THREADS, 0, c->stream>>>(parts, grid, p->tolerance, tiny, sc);
     c->launches += 2;
 
+    const int *doneFlag = (const int *)((const char *)sc + offsetof(CgScalars, done));
     const int maxIters = p->max_iterations;
     int checkEvery = p->check_every > 0 ? p->check_every : 32;
     CgScalars *hs = (CgScalars *)c->hostScalars;  // pinned
@@ -523,12 +533,12 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
         int batch = std::min(checkEvery, maxIters - launched);
         for (int it = 0; it < batch; ++it) {
             const int parity = (launched + it) & 1;
-            if (dist && (rcd = avs_dist_halo_exchange(c, pp, A.precision))) return rcd;
+            if (dist && (rcd = avs_dist_halo_exchange(c, pp, A.precision, doneFlag))) return rcd;
             launchSpmv<T, T2, true>(c, A, pp, t, ptParts, sc, sgrid);
             const double *ptSrc = ptParts, *rrSrc = parts;
             int ptN = sgrid, rrN = grid;
             if (dist) {
-                if ((rcd = avs_dist_allreduce_parts(c, ptParts, sgrid, 1, red))) return rcd;
+                if ((rcd = avs_dist_allreduce_parts(c, ptParts, sgrid, 1, red, doneFlag))) return rcd;
                 ptSrc = red;
                 ptN = 1;
             }
@@ -540,7 +550,7 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
             k_cg_update_xr<T><<<grid, CG_THREADS, 0, c->stream>>>(n, pp, t, A.invDiag.as<T>(), x, r, ptSrc, ptN, parts, grid, sc, parity);
             if (e1) cudaEventRecord(e1, c->stream);
             if (dist) {
-                if ((rcd = avs_dist_allreduce_parts(c, parts, grid, 2, red + 1))) return rcd;
+                if ((rcd = avs_dist_allreduce_parts(c, parts, grid, 2, red + 1, doneFlag))) return rcd;
                 rrSrc = red + 1;
                 rrN = 1;
             }

@@ -74,7 +74,8 @@ struct AvsContext {
     DevBuf centerW, edgeW[3];
     DevBuf label[AVS_MAX_LEVELS], face[AVS_MAX_LEVELS][3], edge[AVS_MAX_LEVELS][3], center[AVS_MAX_LEVELS], regular[3];
     DevBuf tiles;           // tile-occupancy scratch
-    DevBuf brickCount, brickOffset, scanTmp, counters;
+    DevBuf signA, signB;    // sign classes of the surface SDF neighbourhoods (weights shortcut)
+    DevBuf brickCount, brickCost, brickCostPrefix, brickOffset, scanTmp, counters;
     DevBuf rowKeys;         // RowKey[n]
     DevBuf x0, rhs, solution, fullSolution;  // fp64: x0 [N], rhs/solution [local rows], fullSolution [N] (multi-GPU apply)
     DevBuf rowCount, rowOffset; // assembly scratch (int32 / int64)
@@ -89,6 +90,7 @@ struct AvsContext {
     int levelsAllocated = 0;
     int64_t nRows = 0, nnz = 0, nEdge = 0, nCenter = 0, nRegular = 0;
     int64_t rowBegin = 0, rowEnd = 0;  // rows owned by this rank
+    std::vector<long long> rowStarts;  // [nranks+1] first row of every rank's block (brick-granular, cost-balanced, identical on all ranks)
 
     SellMatrix A;
     CgWork cg;
@@ -127,8 +129,10 @@ int avs_build_csr(AvsContext *c);
 int avs_dist_init(AvsContext *c, const void *uniqueId128);
 void avs_dist_destroy(AvsContext *c);
 int avs_dist_build_halo(AvsContext *c);
-int avs_dist_halo_exchange(AvsContext *c, void *p, int precision);
-int avs_dist_allreduce_parts(AvsContext *c, const double *parts, int nparts, int count, double *out);
+int avs_dist_halo_exchange(AvsContext *c, void *p, int precision, const int *done);
+void *avs_dist_prepare_p(AvsContext *c, int *rcOut);
+int avs_dist_mode(AvsContext *c);
+int avs_dist_allreduce_parts(AvsContext *c, const double *parts, int nparts, int count, double *out, const int *done);
 int avs_dist_allgather_solution(AvsContext *c, const double *local, double *full);
 int avs_spmv_time(AvsContext *c, SellMatrix &A, int repeats, float *msPerLaunch);
 int avs_spmv_once(AvsContext *c, SellMatrix &A, const double *dX, double *dY);

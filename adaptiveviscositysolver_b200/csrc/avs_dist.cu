@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -73,8 +74,31 @@ static bool loadNccl() {
         }                                                                                                \
     } while (0)
 
+// Peer-memory ("p2p") mode: every rank exports one cudaMalloc region through CUDA IPC
+//   [ header: ready flag, all-reduce mailboxes + sequence flags | the CG's p vector (owned rows, then halo slots) ]
+// and maps the regions of all peers.  The hot loop then needs no NCCL call: halo values are LOADED from the owners'
+// p vectors over NVLink by k_p2p_halo_pull, and the scalar all-reduce is P remote STORES into the peers' mailboxes
+// followed by a local spin (k_p2p_allreduce) -- both inside our own kernels.
+#define P2P_MAX_RANKS 16
+#define P2P_HEADER_BYTES 8192
+struct P2PHeader {
+    unsigned long long ready;                               // sequence number of the p vector that is complete
+    unsigned long long pad[15];
+    unsigned long long flag[2][P2P_MAX_RANKS];              // mailbox sequence flags, written by the peers
+    double mail[2][P2P_MAX_RANKS][4];                       // mailbox payload (<= 3 doubles used)
+};
+static_assert(sizeof(P2PHeader) <= P2P_HEADER_BYTES, "header too large");
+
 struct DistState {
     ncclComm_t comm = nullptr;
+    // peer-memory mode
+    bool p2p = false;
+    void *region = nullptr;                // my exported region
+    size_t regionBytes = 0;
+    void *peerRegion[P2P_MAX_RANKS] = {};  // mapped regions (peerRegion[rank] == region)
+    DevBuf peerTable;                      // device copy of peerRegion[]
+    DevBuf haloSrc;                        // int2 per halo slot: (owner rank, index in the owner's p)
+    unsigned long long seqReady = 0, seqReduce = 0;
     DevBuf flag, index, haloCols, sendIdx, sendBuf, counts, scal;
     std::vector<int> recvCnt, recvOff, sendCnt, sendOff;
     long long nHalo = 0, nSend = 0;
@@ -104,13 +128,20 @@ int avs_dist_init(AvsContext *c, const void *uniqueId128) {
     d->sendCnt.assign(c->nranks, 0);
     d->sendOff.assign(c->nranks + 1, 0);
     if (d->scal.reserve(64 * sizeof(double))) return AVS_ERR_ALLOC;
+    const char *mode = getenv("AVS_DIST_MODE");   // "p2p" (default) or "nccl"
+    d->p2p = !(mode && strcmp(mode, "nccl") == 0) && c->nranks <= P2P_MAX_RANKS;
     return AVS_OK;
 }
 
 void avs_dist_destroy(AvsContext *c) {
     DistState *d = (DistState *)c->dist;
     if (!d) return;
-    if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
+    for (int q = 0; q < c->nranks && q < P2P_MAX_RANKS; ++q)
+        if (q != c->rank && d->peerRegion[q]) cudaIpcCloseMemHandle(d->peerRegion[q]);
+    if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);   // also orders "close" before the peers' "free"
+    if (d->region) cudaFree(d->region);
+    d->peerTable.release();
+    d->haloSrc.release();
     DevBuf *bufs[] = {&d->flag, &d->index, &d->haloCols, &d->sendIdx, &d->sendBuf, &d->counts, &d->scal};
     for (DevBuf *b : bufs) b->release();
     delete d;
@@ -185,7 +216,7 @@ int avs_dist_build_halo(AvsContext *c) {
     // halo slots are sorted by global column, hence grouped by owner: counts per owner from the scan at the block boundaries
     std::vector<long long> bnd(P + 1);
     for (int q = 0; q <= P; ++q) {
-        long long row = N * q / P;
+        long long row = c->rowStarts[q];
         AVS_CUDA_CHECK(cudaMemcpyAsync(&bnd[q], d->index.as<long long>() + row, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     }
     AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -225,6 +256,163 @@ int avs_dist_build_halo(AvsContext *c) {
     return AVS_OK;
 }
 
+// ---- peer-memory mode ------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ldVolatile(const unsigned long long *p) { return *(const volatile unsigned long long *)p; }
+
+struct RowStarts { long long v[P2P_MAX_RANKS + 1]; };
+__global__ void k_halo_sources(long long nHalo, const int32_t *haloCols, const __grid_constant__ RowStarts starts, int P, int2 *src) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nHalo) return;
+    long long col = haloCols[i];
+    int q = 0;
+    while (q + 1 < P && starts.v[q + 1] <= col) ++q;   // owner of global row `col`
+    src[i] = make_int2(q, (int)(col - starts.v[q]));
+}
+
+// halo slot i of my p  <-  p of its owner, read over NVLink.  `seq` identifies the p vector (CG iteration).
+template <class T>
+__global__ void k_p2p_halo_pull(long long nHalo, const int2 *src, void *const *peerRegion, int myRank, int P,
+                                unsigned long long seq, unsigned neighbourMask, long long nLocal, const int *done) {
+    if (done && *done) return;  // converged: every rank holds identical scalars, so every rank skips consistently
+    P2PHeader *mine = (P2PHeader *)peerRegion[myRank];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // my p (written by the previous kernel on this stream) is complete: publish
+        __threadfence_system();
+        *(volatile unsigned long long *)&mine->ready = seq;
+    }
+    if (threadIdx.x < P && ((neighbourMask >> threadIdx.x) & 1u)) {
+        const P2PHeader *peer = (const P2PHeader *)peerRegion[threadIdx.x];
+        while (ldVolatile(&peer->ready) < seq) __nanosleep(200);
+    }
+    __syncthreads();
+    __threadfence_system();
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nHalo) return;
+    int2 s = src[i];
+    const T *peerP = (const T *)((const char *)peerRegion[s.x] + P2P_HEADER_BYTES);
+    T *myP = (T *)((char *)mine + P2P_HEADER_BYTES);
+    myP[nLocal + i] = *(const volatile T *)(peerP + s.y);
+}
+
+// out[0..count) = sum over ranks (in rank order) of this rank's sum over CTAs of parts[q*nparts + i].
+// One CTA.  Remote stores into every peer's mailbox, then a local spin until all P contributions arrived.
+__global__ void k_p2p_allreduce(const double *parts, int nparts, int count, void *const *peerRegion, int myRank, int P,
+                                unsigned long long seq, double *out, const int *done) {
+    if (done && *done) return;
+    __shared__ double sh[256];
+    __shared__ double local[4];
+    for (int q = 0; q < count; ++q) {
+        double v = 0;
+        for (int i = threadIdx.x; i < nparts; i += 256) v += parts[(size_t)q * nparts + i];
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) local[q] = sh[0];
+        __syncthreads();
+    }
+    const int par = (int)(seq & 1ull);
+    if (threadIdx.x < P) {
+        P2PHeader *peer = (P2PHeader *)peerRegion[threadIdx.x];
+        for (int q = 0; q < count; ++q) *(volatile double *)&peer->mail[par][myRank][q] = local[q];
+        __threadfence_system();
+        *(volatile unsigned long long *)&peer->flag[par][myRank] = seq;
+    }
+    P2PHeader *mine = (P2PHeader *)peerRegion[myRank];
+    if (threadIdx.x < P) {
+        while (ldVolatile(&mine->flag[par][threadIdx.x]) != seq) __nanosleep(100);
+    }
+    __syncthreads();
+    __threadfence_system();
+    if (threadIdx.x < count) {
+        double t = 0;
+        for (int r = 0; r < P; ++r) t += *(const volatile double *)&mine->mail[par][r][threadIdx.x];
+        out[threadIdx.x] = t;
+    }
+}
+
+// (Re)creates the exported region so that it can hold `elems` vector elements of 8 bytes; collective.
+static int p2pEnsureRegion(AvsContext *c, size_t elems) {
+    DistState *d = (DistState *)c->dist;
+    const int P = c->nranks;
+    // agree on the capacity: max over ranks
+    unsigned long long need = (unsigned long long)(P2P_HEADER_BYTES + elems * 8 + 256);
+    unsigned long long *dNeed = (unsigned long long *)d->scal.as<double>() + 32;
+    AVS_CUDA_CHECK(cudaMemcpyAsync(dNeed, &need, sizeof(need), cudaMemcpyHostToDevice, c->stream));
+    NCCL_CHECK(c, g_nccl.AllReduce(dNeed, dNeed, 1, ncclUint64, ncclMax, d->comm, c->stream));
+    AVS_CUDA_CHECK(cudaMemcpyAsync(&need, dNeed, sizeof(need), cudaMemcpyDeviceToHost, c->stream));
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (d->region && need <= d->regionBytes) return AVS_OK;
+    // tear down the old mappings (everyone closes before anyone frees: the all-reduce above/below orders it)
+    for (int q = 0; q < P; ++q)
+        if (q != c->rank && d->peerRegion[q]) { cudaIpcCloseMemHandle(d->peerRegion[q]); d->peerRegion[q] = nullptr; }
+    NCCL_CHECK(c, g_nccl.AllReduce(dNeed, dNeed, 1, ncclUint64, ncclMax, d->comm, c->stream));
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (d->region) cudaFree(d->region);
+    d->region = nullptr;
+    size_t bytes = (size_t)(need + need / 4);
+    if (cudaMalloc(&d->region, bytes) != cudaSuccess) { cudaGetLastError(); return AVS_ERR_ALLOC; }
+    d->regionBytes = bytes;
+    AVS_CUDA_CHECK(cudaMemsetAsync(d->region, 0, P2P_HEADER_BYTES, c->stream));
+    d->seqReady = 0;
+    d->seqReduce = 0;
+    // exchange IPC handles
+    cudaIpcMemHandle_t mine;
+    AVS_CUDA_CHECK(cudaIpcGetMemHandle(&mine, d->region));
+    DevBuf hb;
+    if (hb.reserve((size_t)(P + 1) * sizeof(cudaIpcMemHandle_t))) return AVS_ERR_ALLOC;
+    char *dAll = hb.as<char>(), *dMine = dAll + (size_t)P * sizeof(cudaIpcMemHandle_t);
+    AVS_CUDA_CHECK(cudaMemcpyAsync(dMine, &mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream));
+    NCCL_CHECK(c, g_nccl.AllGather(dMine, dAll, sizeof(mine), ncclUint8, d->comm, c->stream));
+    std::vector<cudaIpcMemHandle_t> all(P);
+    AVS_CUDA_CHECK(cudaMemcpyAsync(all.data(), dAll, (size_t)P * sizeof(mine), cudaMemcpyDeviceToHost, c->stream));
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    hb.release();
+    int okLocal = 1;
+    for (int q = 0; q < P; ++q) {
+        if (q == c->rank) { d->peerRegion[q] = d->region; continue; }
+        if (cudaIpcOpenMemHandle(&d->peerRegion[q], all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            d->peerRegion[q] = nullptr;
+            okLocal = 0;
+        }
+    }
+    // every rank must agree on the mode
+    unsigned long long ok = (unsigned long long)okLocal;
+    AVS_CUDA_CHECK(cudaMemcpyAsync(dNeed, &ok, sizeof(ok), cudaMemcpyHostToDevice, c->stream));
+    NCCL_CHECK(c, g_nccl.AllReduce(dNeed, dNeed, 1, ncclUint64, ncclMin, d->comm, c->stream));
+    AVS_CUDA_CHECK(cudaMemcpyAsync(&ok, dNeed, sizeof(ok), cudaMemcpyDeviceToHost, c->stream));
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (!ok) { d->p2p = false; return AVS_OK; }
+    if (d->peerTable.reserve(P2P_MAX_RANKS * sizeof(void *))) return AVS_ERR_ALLOC;
+    AVS_CUDA_CHECK(cudaMemcpyAsync(d->peerTable.p, d->peerRegion, P2P_MAX_RANKS * sizeof(void *), cudaMemcpyHostToDevice, c->stream));
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return AVS_OK;
+}
+
+// Called once per solve after the halo is known.  Returns the p vector the CG must use (inside the exported region)
+// or nullptr when the NCCL path is active.
+void *avs_dist_prepare_p(AvsContext *c, int *rcOut) {
+    DistState *d = (DistState *)c->dist;
+    *rcOut = AVS_OK;
+    if (!d || !d->p2p) return nullptr;
+    const long long nLocal = c->rowEnd - c->rowBegin;
+    int rc = p2pEnsureRegion(c, (size_t)(nLocal + d->nHalo + 64));
+    if (rc) { *rcOut = rc; return nullptr; }
+    if (!d->p2p) return nullptr;
+    if (d->haloSrc.reserve((size_t)std::max<long long>(d->nHalo, 1) * sizeof(int2))) { *rcOut = AVS_ERR_ALLOC; return nullptr; }
+    if (d->nHalo > 0) {
+        RowStarts rs;
+        for (int q = 0; q <= c->nranks; ++q) rs.v[q] = c->rowStarts[q];
+        k_halo_sources<<<(unsigned)((d->nHalo + 255) / 256), 256, 0, c->stream>>>(d->nHalo, d->haloCols.as<int32_t>(), rs, c->nranks,
+                                                                                 d->haloSrc.as<int2>());
+        ++c->launches;
+    }
+    return (char *)d->region + P2P_HEADER_BYTES;
+}
+
 // p[nLocal + slot] <- owner's p for every halo slot
 template <class T>
 int avs_dist_halo_exchange_t(AvsContext *c, T *p) {
@@ -245,14 +433,38 @@ int avs_dist_halo_exchange_t(AvsContext *c, T *p) {
     NCCL_CHECK(c, g_nccl.GroupEnd());
     return AVS_OK;
 }
-int avs_dist_halo_exchange(AvsContext *c, void *p, int precision) {
+int avs_dist_halo_exchange(AvsContext *c, void *p, int precision, const int *done) {
     if (!c->dist) return AVS_OK;
+    DistState *d = (DistState *)c->dist;
+    if (d->p2p) {
+        const long long nLocal = c->rowEnd - c->rowBegin;
+        unsigned mask = 0;
+        for (int q = 0; q < c->nranks; ++q)
+            if (q != c->rank && d->recvCnt[q] > 0) mask |= 1u << q;
+        ++d->seqReady;
+        unsigned blocks = (unsigned)std::max<long long>(1, (d->nHalo + 255) / 256);
+        if (precision == AVS_PRECISION_F32)
+            k_p2p_halo_pull<float><<<blocks, 256, 0, c->stream>>>(d->nHalo, d->haloSrc.as<int2>(), d->peerTable.as<void *>(), c->rank, c->nranks,
+                                                                  d->seqReady, mask, nLocal, done);
+        else
+            k_p2p_halo_pull<double><<<blocks, 256, 0, c->stream>>>(d->nHalo, d->haloSrc.as<int2>(), d->peerTable.as<void *>(), c->rank, c->nranks,
+                                                                   d->seqReady, mask, nLocal, done);
+        ++c->launches;
+        (void)p;
+        return AVS_OK;
+    }
     return precision == AVS_PRECISION_F32 ? avs_dist_halo_exchange_t<float>(c, (float *)p) : avs_dist_halo_exchange_t<double>(c, (double *)p);
 }
 
 // out[0..count) = sum over ranks of sum over CTAs of parts[q*nparts + i]; identical bits on every rank
-int avs_dist_allreduce_parts(AvsContext *c, const double *parts, int nparts, int count, double *out) {
+int avs_dist_allreduce_parts(AvsContext *c, const double *parts, int nparts, int count, double *out, const int *done) {
     DistState *d = (DistState *)c->dist;
+    if (d && d->p2p) {
+        ++d->seqReduce;
+        k_p2p_allreduce<<<1, 256, 0, c->stream>>>(parts, nparts, count, d->peerTable.as<void *>(), c->rank, c->nranks, d->seqReduce, out, done);
+        ++c->launches;
+        return AVS_OK;
+    }
     k_reduce_parts<<<1, 256, 0, c->stream>>>(parts, nparts, count, out);
     ++c->launches;
     if (d) NCCL_CHECK(c, g_nccl.AllReduce(out, out, (size_t)count, ncclFloat64, ncclSum, d->comm, c->stream));
@@ -263,14 +475,20 @@ int avs_dist_allreduce_parts(AvsContext *c, const double *parts, int nparts, int
 int avs_dist_allgather_solution(AvsContext *c, const double *local, double *full) {
     DistState *d = (DistState *)c->dist;
     const int P = c->nranks;
-    const long long N = c->nRows;
     if (!d) return AVS_OK;
     AVS_CUDA_CHECK(cudaMemcpyAsync(full + c->rowBegin, local, (size_t)(c->rowEnd - c->rowBegin) * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     NCCL_CHECK(c, g_nccl.GroupStart());
     for (int q = 0; q < P; ++q) {
-        long long b = N * q / P, e = N * (q + 1) / P;
+        long long b = c->rowStarts[q], e = c->rowStarts[q + 1];
         if (e > b) NCCL_CHECK(c, g_nccl.Broadcast(full + b, full + b, (size_t)(e - b), ncclFloat64, q, d->comm, c->stream));
     }
     NCCL_CHECK(c, g_nccl.GroupEnd());
     return AVS_OK;
+}
+
+// 0 = single GPU, 1 = NCCL hot loop, 2 = peer-memory hot loop
+int avs_dist_mode(AvsContext *c) {
+    DistState *d = (DistState *)c->dist;
+    if (!d) return 0;
+    return d->p2p ? 2 : 1;
 }

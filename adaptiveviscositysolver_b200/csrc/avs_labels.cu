@@ -27,22 +27,46 @@
 
 static_assert(sizeof(DeviceScene) <= 4000, "DeviceScene must fit the kernel parameter space");
 
+// Grid kernels are launched as (ceil(nx/128), ny, nz) x 128 threads: x from the thread index, y/z from the block
+// index -- no 64-bit div/mod per thread (that cost more than the memory traffic of these streaming passes).
+#define LAUNCH_3D(ctx, kernel, n3, ...)                                                        \
+    do {                                                                                       \
+        if ((n3)[0] > 0 && (n3)[1] > 0 && (n3)[2] > 0) {                                        \
+            dim3 _g((unsigned)(((n3)[0] + 127) / 128), (unsigned)(n3)[1], (unsigned)(n3)[2]);    \
+            kernel<<<_g, 128, 0, (ctx)->stream>>>(__VA_ARGS__);                                \
+            ++(ctx)->launches;                                                                 \
+        }                                                                                      \
+    } while (0)
+__device__ __forceinline__ bool cell3(const int n[3], int &x, int &y, int &z, size_t &idx) {
+    x = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    y = (int)blockIdx.y;
+    z = (int)blockIdx.z;
+    idx = (size_t)x + (size_t)n[0] * ((size_t)y + (size_t)n[1] * (size_t)z);
+    return x < n[0];
+}
+
 // ------------------------------------------------------------------------------------------------
 // Stage 1: computeSDFWeightsSampled restated: fraction of the n^3 sub-samples at
 // offsets ((k+1/2)/n - 1/2) dx whose interpolated sdf (minus dilate) is negative.
 // Early-out: the trilinear interpolant is a convex combination of the voxels it touches, so when
 // every voxel under the sample's box has the same sign the count is n^3 or 0 without sampling.
 __global__ void k_sdf_weights(Grid3<float> w, DField sdf, double off0, double off1, double off2, double o0,
-                              double o1, double o2, double dx0, int n, double dilate) {
-    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= w.count()) return;
-    int x = (int)(idx % w.n[0]);
-    int y = (int)((idx / w.n[0]) % w.n[1]);
-    int z = (int)(idx / ((size_t)w.n[0] * w.n[1]));
+                              double o1, double o2, double dx0, int n, double dilate, const uint8_t *signClass) {
+    size_t idx;
+    int x, y, z;
+    if (!cell3(w.n, x, y, z, idx)) return;
     double c[3] = {o0 + (x + off0) * dx0, o1 + (y + off1) * dx0, o2 + (z + off2) * dx0};
     if (!sdf.d) {
         w.d[idx] = ((double)sdf.constant - dilate < 0.0) ? 1.f : 0.f;
         return;
+    }
+    // Aligned sdf grid (the liquid surface always is): the voxels under this sample's box are a subset of
+    // the 3x3x3 neighbourhood of cell (x,y,z) clamped into the grid, whose sign class was precomputed.
+    if (signClass) {
+        int cx = min(x, sdf.n[0] - 1), cy = min(y, sdf.n[1] - 1), cz = min(z, sdf.n[2] - 1);
+        uint8_t cls = signClass[(size_t)cx + (size_t)sdf.n[0] * ((size_t)cy + (size_t)sdf.n[1] * cz)];
+        if (cls == 0) { w.d[idx] = 1.f; return; }
+        if (cls == 1) { w.d[idx] = 0.f; return; }
     }
     const double inv = 1.0 / (double)n;
     const double h = (0.5 - 0.5 * inv) * dx0;
@@ -81,6 +105,29 @@ __global__ void k_sdf_weights(Grid3<float> w, DField sdf, double off0, double of
     w.d[idx] = (float)((double)count / total);
 }
 
+// ---- sign classes of the 3x3x3 voxel neighbourhood (clamped), separable: x, then y, then z ------------
+// class 0: every voxel < 0, 1: every voxel >= 0, 2: mixed.  One byte per voxel of the sdf grid.
+__device__ __forceinline__ uint8_t combine3(uint8_t a, uint8_t b, uint8_t c) { return (a == b && b == c) ? a : (uint8_t)2; }
+__global__ void k_sign_x(const float *sdf, int nx, int ny, int nz, uint8_t *out) {
+    const int n3[3] = {nx, ny, nz};
+    size_t idx;
+    int x, y, z;
+    if (!cell3(n3, x, y, z, idx)) return;
+    size_t row = idx - x;
+    uint8_t a = sdf[row + max(x - 1, 0)] < 0.f ? 0 : 1, b = sdf[idx] < 0.f ? 0 : 1, c = sdf[row + min(x + 1, nx - 1)] < 0.f ? 0 : 1;
+    out[idx] = combine3(a, b, c);
+}
+__global__ void k_sign_axis(const uint8_t *in, int nx, int ny, int nz, int axis, uint8_t *out) {
+    const int n3[3] = {nx, ny, nz};
+    size_t idx;
+    int x, y, z;
+    if (!cell3(n3, x, y, z, idx)) return;
+    size_t stride = axis == 1 ? (size_t)nx : (size_t)nx * ny;
+    int pos = axis == 1 ? y : z, top = axis == 1 ? ny - 1 : nz - 1;
+    uint8_t a = in[pos > 0 ? idx - stride : idx], b = in[idx], c = in[pos < top ? idx + stride : idx];
+    out[idx] = combine3(a, b, c);
+}
+
 // setScaleDivideThreshold(1, nullptr, &b, 0): a /= b where b > 0 (AV.cpp:781-789)
 __global__ void k_divide_where_positive(float *a, const float *b, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -88,12 +135,12 @@ __global__ void k_divide_where_positive(float *a, const float *b, size_t n) {
 }
 
 static int weightsFor(AvsContext *c, DevBuf &buf, Grid3<float> &g, const DField &sdf, const double off[3],
-                      const int res[3], int n, double dilate) {
+                      const int res[3], int n, double dilate, const uint8_t *signClass) {
     g.n[0] = res[0]; g.n[1] = res[1]; g.n[2] = res[2];
     if (buf.reserve(g.count() * sizeof(float))) return AVS_ERR_ALLOC;
     g.d = buf.as<float>();
-    LAUNCH_1D(c, k_sdf_weights, g.count(), g, sdf, off[0], off[1], off[2], c->S.origin[0], c->S.origin[1],
-              c->S.origin[2], c->S.dx0, n, dilate);
+    LAUNCH_3D(c, k_sdf_weights, g.n, g, sdf, off[0], off[1], off[2], c->S.origin[0], c->S.origin[1],
+              c->S.origin[2], c->S.dx0, n, dilate, signClass);
     return AVS_OK;
 }
 
@@ -101,26 +148,37 @@ int avs_stage_weights(AvsContext *c, const AvsParams *p) {
     DeviceScene &S = c->S;
     const int n = p->number_super_samples;
     const double offC[3] = {0.5, 0.5, 0.5};
-    int rc = weightsFor(c, c->centerW, S.centerW, S.surface, offC, S.N, n, 0.0);
+    // sign classes of the surface SDF (only valid as a shortcut when the field sits on the scene grid with dilate = 0,
+    // which avs_stage_upload has validated for `surface`)
+    const uint8_t *cls = nullptr;
+    if (S.surface.d && n >= 1) {
+        const size_t cells = (size_t)S.N[0] * S.N[1] * S.N[2];
+        if (c->signA.reserve(cells) || c->signB.reserve(cells)) return AVS_ERR_ALLOC;
+        LAUNCH_3D(c, k_sign_x, S.N, S.surface.d, S.N[0], S.N[1], S.N[2], c->signA.as<uint8_t>());
+        LAUNCH_3D(c, k_sign_axis, S.N, c->signA.as<uint8_t>(), S.N[0], S.N[1], S.N[2], 1, c->signB.as<uint8_t>());
+        LAUNCH_3D(c, k_sign_axis, S.N, c->signB.as<uint8_t>(), S.N[0], S.N[1], S.N[2], 2, c->signA.as<uint8_t>());
+        cls = c->signA.as<uint8_t>();
+    }
+    int rc = weightsFor(c, c->centerW, S.centerW, S.surface, offC, S.N, n, 0.0, cls);
     if (rc) return rc;
     for (int a = 0; a < 3; ++a) {
         double off[3] = {0, 0, 0};
         off[a] = 0.5;  // an a-directed edge is centred along a only (HDK_Utilities.h:13-15)
         int res[3] = {S.N[0] + 1, S.N[1] + 1, S.N[2] + 1};
         res[a] -= 1;
-        rc = weightsFor(c, c->edgeW[a], S.edgeW[a], S.surface, off, res, n, 0.0);
+        rc = weightsFor(c, c->edgeW[a], S.edgeW[a], S.surface, off, res, n, 0.0, cls);
         if (rc) return rc;
     }
     if (p->do_apply_solid_weights) {  // AV.cpp:772-790
         DevBuf &tmp = c->solidW;
         Grid3<float> g;
-        rc = weightsFor(c, tmp, g, S.collision, offC, S.N, n, -S.extrap);
+        rc = weightsFor(c, tmp, g, S.collision, offC, S.N, n, -S.extrap, nullptr);
         if (rc) return rc;
         LAUNCH_1D(c, k_divide_where_positive, g.count(), S.centerW.d, g.d, g.count());
         for (int a = 0; a < 3; ++a) {
             double off[3] = {0, 0, 0};
             off[a] = 0.5;
-            rc = weightsFor(c, tmp, g, S.collision, off, S.edgeW[a].n, n, -S.extrap);
+            rc = weightsFor(c, tmp, g, S.collision, off, S.edgeW[a].n, n, -S.extrap, nullptr);
             if (rc) return rc;
             LAUNCH_1D(c, k_divide_where_positive, g.count(), S.edgeW[a].d, g.d, g.count());
         }
@@ -134,11 +192,9 @@ int avs_stage_weights(AvsContext *c, const AvsParams *p) {
 // mask 0 -> ACTIVE, < 0 -> UP, > 0 (or outside the un-padded grid) -> INACTIVE.
 __global__ void k_base_labels(const __grid_constant__ DeviceScene S, double inner, double outer) {
     const Grid3<uint8_t> lab = S.label[0];
-    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= lab.count()) return;
-    int x = (int)(idx % lab.n[0]);
-    int y = (int)((idx / lab.n[0]) % lab.n[1]);
-    int z = (int)(idx / ((size_t)lab.n[0] * lab.n[1]));
+    size_t idx;
+    int x, y, z;
+    if (!cell3(lab.n, x, y, z, idx)) return;
     uint8_t out = L_INACTIVE;
     if (x < S.N[0] && y < S.N[1] && z < S.N[2]) {
         double sdf = (double)S.surface.raw(x, y, z);
@@ -157,11 +213,9 @@ __global__ void k_base_labels(const __grid_constant__ DeviceScene S, double inne
 
 // pass 1, setActiveCellsAndParentList (OG.cpp:394-565): one thread per 2x2x2 sibling block.
 __global__ void k_octree_pass1(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
-    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= par.count()) return;
-    int px = (int)(idx % par.n[0]);
-    int py = (int)((idx / par.n[0]) % par.n[1]);
-    int pz = (int)(idx / ((size_t)par.n[0] * par.n[1]));
+    size_t idx;
+    int px, py, pz;
+    if (!cell3(par.n, px, py, pz, idx)) return;
     uint8_t v[8];
     bool any = false;
 #pragma unroll
@@ -179,19 +233,18 @@ __global__ void k_octree_pass1(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
 // pass 2, setFaceGrading (OG.cpp:656-754). The reference applies its DOWN list before its ACTIVE
 // list (OG.cpp:145, 162); two kernels keep that order.
 __global__ void k_octree_pass2_down(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
-    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= cur.count()) return;
+    size_t idx;
+    int x, y, z;
+    if (!cell3(cur.n, x, y, z, idx)) return;
     if (cur.d[idx] != L_DOWN) return;
-    int x = (int)(idx % cur.n[0]);
-    int y = (int)((idx / cur.n[0]) % cur.n[1]);
-    int z = (int)(idx / ((size_t)cur.n[0] * cur.n[1]));
     par.d[par.lin(x >> 1, y >> 1, z >> 1)] = L_DOWN;
 }
 __global__ void k_octree_pass2_active(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
-    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= cur.count()) return;
+    size_t idx;
+    int x, y, z;
+    if (!cell3(cur.n, x, y, z, idx)) return;
     if (cur.d[idx] != L_ACTIVE) return;
-    I3 c = mk3((int)(idx % cur.n[0]), (int)((idx / cur.n[0]) % cur.n[1]), (int)(idx / ((size_t)cur.n[0] * cur.n[1])));
+    I3 c = mk3(x, y, z);
 #pragma unroll
     for (int axis = 0; axis < 3; ++axis)
 #pragma unroll
@@ -203,12 +256,10 @@ __global__ void k_octree_pass2_active(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
 }
 // pass 3, setParentsUp (OG.cpp:756-840)
 __global__ void k_octree_pass3(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
-    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= cur.count()) return;
+    size_t idx;
+    int x, y, z;
+    if (!cell3(cur.n, x, y, z, idx)) return;
     if (cur.d[idx] != L_UP) return;
-    int x = (int)(idx % cur.n[0]);
-    int y = (int)((idx / cur.n[0]) % cur.n[1]);
-    int z = (int)(idx / ((size_t)cur.n[0] * cur.n[1]));
     size_t pi = par.lin(x >> 1, y >> 1, z >> 1);
     if (par.d[pi] == L_INACTIVE) par.d[pi] = L_UP;
 }
@@ -274,13 +325,13 @@ int avs_stage_octree(AvsContext *c, const AvsParams *p) {
     }
     const double fineVoxelWidth = std::max(2.0, (double)p->fine_bandwidth);  // AV.cpp:259
     const double inner = S.dx0 * fineVoxelWidth, outer = 3.0 * S.dx0;         // AV.cpp:261-262
-    LAUNCH_1D(c, k_base_labels, S.label[0].count(), S, inner, outer);
+    LAUNCH_3D(c, k_base_labels, S.label[0].n, S, inner, outer);
     for (int l = 0; l < L - 1; ++l) {
         Grid3<uint8_t> cur = S.label[l], par = S.label[l + 1];
-        LAUNCH_1D(c, k_octree_pass1, par.count(), cur, par);
-        if (l > 0) LAUNCH_1D(c, k_octree_pass2_down, cur.count(), cur, par);
-        LAUNCH_1D(c, k_octree_pass2_active, cur.count(), cur, par);
-        LAUNCH_1D(c, k_octree_pass3, cur.count(), cur, par);
+        LAUNCH_3D(c, k_octree_pass1, par.n, cur, par);
+        if (l > 0) LAUNCH_3D(c, k_octree_pass2_down, cur.n, cur, par);
+        LAUNCH_3D(c, k_octree_pass2_active, cur.n, cur, par);
+        LAUNCH_3D(c, k_octree_pass3, cur.n, cur, par);
     }
     LAUNCH_1D(c, k_octree_top, S.label[L - 1].count(), S.label[L - 1]);
     // level capping (OG.cpp:198-211): first level without an ACTIVE cell
@@ -312,12 +363,9 @@ __device__ __forceinline__ bool tileOccupied(const Grid3<uint8_t> &t, int x, int
 // findOccupiedRegularVelocityTiles (AV.cpp:886-943): both faces of every cell with sdf < 2 dx
 __global__ void k_mark_surface_tiles(const __grid_constant__ DeviceScene S, Grid3<uint8_t> t0, Grid3<uint8_t> t1,
                                      Grid3<uint8_t> t2) {
-    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t n = (size_t)S.N[0] * S.N[1] * S.N[2];
-    if (idx >= n) return;
-    int x = (int)(idx % S.N[0]);
-    int y = (int)((idx / S.N[0]) % S.N[1]);
-    int z = (int)(idx / ((size_t)S.N[0] * S.N[1]));
+    size_t idx;
+    int x, y, z;
+    if (!cell3(S.N, x, y, z, idx)) return;
     if (!((double)S.surface.raw(x, y, z) < 2.0 * S.dx0)) return;
     I3 c = mk3(x, y, z);
     markTile(t0, c); markTile(t0, cellToFace(c, 0, 1));
@@ -342,11 +390,9 @@ __device__ __forceinline__ bool faceHasWeight(const DeviceScene &S, const I3 &fa
 // classifyRegularVelocityFaces (AV.cpp:1087-1165)
 __global__ void k_classify_regular(const __grid_constant__ DeviceScene S, int axis, Grid3<uint8_t> tiles) {
     const Grid3<int8_t> g = S.regular[axis];
-    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= g.count()) return;
-    int x = (int)(idx % g.n[0]);
-    int y = (int)((idx / g.n[0]) % g.n[1]);
-    int z = (int)(idx / ((size_t)g.n[0] * g.n[1]));
+    size_t idx;
+    int x, y, z;
+    if (!cell3(g.n, x, y, z, idx)) return;
     int8_t out = F_UNASSIGNED;
     I3 face = mk3(x, y, z);
     if (tileOccupied(tiles, x, y, z) && face[axis] - 1 >= 0 && face[axis] < S.N[axis]) {
@@ -362,11 +408,9 @@ __global__ void k_classify_regular(const __grid_constant__ DeviceScene S, int ax
 // classifyOctreeVelocityFaces (AV.cpp:1167-1323)
 __global__ void k_classify_faces(const __grid_constant__ DeviceScene S, int level, int axis, Grid3<uint8_t> tiles) {
     const Grid3<int32_t> g = S.face[level][axis];
-    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= g.count()) return;
-    int x = (int)(idx % g.n[0]);
-    int y = (int)((idx / g.n[0]) % g.n[1]);
-    int z = (int)(idx / ((size_t)g.n[0] * g.n[1]));
+    size_t idx;
+    int x, y, z;
+    if (!cell3(g.n, x, y, z, idx)) return;
     int32_t out = F_UNASSIGNED;
     I3 face = mk3(x, y, z);
     const Grid3<uint8_t> &lab = S.label[level];
@@ -395,10 +439,11 @@ __global__ void k_classify_faces(const __grid_constant__ DeviceScene S, int leve
 
 // findOccupiedEdgeStressTiles (AV.cpp:1002-1057): the 4 a-edges of every ACTIVE cell, a = 0,1,2
 __global__ void k_mark_edge_tiles(Grid3<uint8_t> lab, Grid3<uint8_t> t0, Grid3<uint8_t> t1, Grid3<uint8_t> t2) {
-    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= lab.count()) return;
+    size_t idx;
+    int x, y, z;
+    if (!cell3(lab.n, x, y, z, idx)) return;
     if (lab.d[idx] != L_ACTIVE) return;
-    I3 c = mk3((int)(idx % lab.n[0]), (int)((idx / lab.n[0]) % lab.n[1]), (int)(idx / ((size_t)lab.n[0] * lab.n[1])));
+    I3 c = mk3(x, y, z);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         markTile(t0, cellToEdge(c, 0, e));
@@ -410,11 +455,9 @@ __global__ void k_mark_edge_tiles(Grid3<uint8_t> lab, Grid3<uint8_t> t0, Grid3<u
 // classifyEdgeStresses (AV.cpp:1325-1405)
 __global__ void k_classify_edges(const __grid_constant__ DeviceScene S, int level, int axis, Grid3<uint8_t> tiles) {
     const Grid3<int8_t> g = S.edge[level][axis];
-    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= g.count()) return;
-    int x = (int)(idx % g.n[0]);
-    int y = (int)((idx / g.n[0]) % g.n[1]);
-    int z = (int)(idx / ((size_t)g.n[0] * g.n[1]));
+    size_t idx;
+    int x, y, z;
+    if (!cell3(g.n, x, y, z, idx)) return;
     int8_t out = F_UNASSIGNED;
     if (tileOccupied(tiles, x, y, z)) {
         const Grid3<uint8_t> &lab = S.label[level];
@@ -445,15 +488,13 @@ __global__ void k_classify_edges(const __grid_constant__ DeviceScene S, int leve
 // classifyCenterStresses (AV.cpp:1407-1443)
 __global__ void k_classify_centers(const __grid_constant__ DeviceScene S, int level) {
     const Grid3<int8_t> g = S.center[level];
-    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= g.count()) return;
+    size_t idx;
+    int x, y, z;
+    if (!cell3(g.n, x, y, z, idx)) return;
     int8_t out = F_UNASSIGNED;
     if (S.label[level].d[idx] == L_ACTIVE) {
         if (level != 0) out = F_FLUID;
-        else {
-            I3 c = mk3((int)(idx % g.n[0]), (int)((idx / g.n[0]) % g.n[1]), (int)(idx / ((size_t)g.n[0] * g.n[1])));
-            if (S.centerW.get(c) > 0.f) out = F_FLUID;
-        }
+        else if (S.centerW.get(mk3(x, y, z)) > 0.f) out = F_FLUID;
     }
     g.d[idx] = out;
 }
@@ -484,8 +525,8 @@ int avs_stage_regular_labels(AvsContext *c) {
     Grid3<uint8_t> t[3];
     int rc = tileGrid(c, c->tiles, t, res);
     if (rc) return rc;
-    LAUNCH_1D(c, k_mark_surface_tiles, (size_t)S.N[0] * S.N[1] * S.N[2], S, t[0], t[1], t[2]);
-    for (int a = 0; a < 3; ++a) LAUNCH_1D(c, k_classify_regular, S.regular[a].count(), S, a, t[a]);
+    LAUNCH_3D(c, k_mark_surface_tiles, S.N, S, t[0], t[1], t[2]);
+    for (int a = 0; a < 3; ++a) LAUNCH_3D(c, k_classify_regular, S.regular[a].n, S, a, t[a]);
     unsigned long long *cnt = c->counters.as<unsigned long long>();
     AVS_CUDA_CHECK(cudaMemsetAsync(cnt + 16, 0, sizeof(unsigned long long), c->stream));
     for (int a = 0; a < 3; ++a)
@@ -494,28 +535,52 @@ int avs_stage_regular_labels(AvsContext *c) {
 }
 
 // ---- DOF numbering: count -> scan -> assign over 8^3-cell bricks in Morton order -----------------
+// Bricks of all levels form one octree: a level-l brick (8^3 cells of level l) covers 2 bricks per axis of
+// level l-1 (1 where that level has a single brick on the axis).  Rows are numbered in depth-first order of this
+// tree -- a brick's own rows, then its children in Morton order -- so a coarse face sits next to the fine faces
+// it couples to (T-junction stencils) and every contiguous row range is one compact region holding ALL levels:
+// thin halos for the multi-GPU row partition, and level-0 bricks still appear in Morton order.
 struct BrickLayout {
-    int bits[AVS_MAX_LEVELS][3];   // log2(bricks per axis)
-    long long base[AVS_MAX_LEVELS + 1];
+    int nb[AVS_MAX_LEVELS][3];     // bricks per axis
+    int lf[AVS_MAX_LEVELS][3];     // log2(children per axis) of a level-l brick (0 for l == 0)
+    long long sub[AVS_MAX_LEVELS]; // bricks in the subtree of one level-l brick (itself included)
+    long long total;
     int levels;
 };
 #define BRICK 8
 
-__device__ __forceinline__ void brickCoord(const BrickLayout &bl, int level, long long code, int b[3]) {
-    b[0] = b[1] = b[2] = 0;
-    int bit = 0;
-    for (int k = 0; k < 10; ++k)
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-            if (k < bl.bits[level][a]) {
-                b[a] |= (int)((code >> bit) & 1) << k;
-                ++bit;
-            }
+__device__ __forceinline__ void brickCoord(const BrickLayout &bl, int level, long long lin, int b[3]) {
+    b[0] = (int)(lin % bl.nb[level][0]);
+    b[1] = (int)((lin / bl.nb[level][0]) % bl.nb[level][1]);
+    b[2] = (int)(lin / ((long long)bl.nb[level][0] * bl.nb[level][1]));
 }
 
-// slot order inside a brick: cell-major (z, y, x), the three axes' faces of one cell adjacent
-__device__ __forceinline__ int brickThreadCount(const DeviceScene &S, int level, const int b[3], int t, int32_t vals[6]) {
-    int n = 0;
+// depth-first position of brick b of `level`
+__device__ __forceinline__ long long brickPos(const BrickLayout &bl, int level, const int b[3]) {
+    const int T = bl.levels - 1;
+    long long pos = 0;
+    int sh[3] = {0, 0, 0};  // shift from `level` coordinates to level k-1 coordinates
+    for (int k = level + 1; k <= T; ++k) {
+        int ci = 0, bit = 0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            if (bl.lf[k][a]) {
+                ci |= ((b[a] >> sh[a]) & 1) << bit;
+                ++bit;
+            }
+        pos += 1 + (long long)ci * bl.sub[k - 1];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) sh[a] += bl.lf[k][a];
+    }
+    long long t = (long long)(b[0] >> sh[0]) + (long long)bl.nb[T][0] * ((long long)(b[1] >> sh[1]) + (long long)bl.nb[T][1] * (b[2] >> sh[2]));
+    return pos + t * bl.sub[T];
+}
+
+// Row order inside a brick: axis-major (all x-faces of the brick, then y, then z), cells z,y,x inside an axis.
+// 32 consecutive rows then share their axis, which keeps the assembly kernel's warps on one control path
+// (ncu: 7.3 of 32 lanes active per instruction with the cell-interleaved order).
+__device__ __forceinline__ void brickThreadCount(const DeviceScene &S, int level, const int b[3], int t, int32_t vals[6], int n[3]) {
+    n[0] = n[1] = n[2] = 0;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         int cellLocal = t * 2 + q;
@@ -527,18 +592,19 @@ __device__ __forceinline__ int brickThreadCount(const DeviceScene &S, int level,
             int32_t v = F_UNASSIGNED;
             if (in) v = S.face[level][a].d[S.face[level][a].lin(x, y, z)];
             vals[q * 3 + a] = v;
-            n += (v >= 0);
+            n[a] += (v >= 0);
         }
     }
-    return n;
 }
 
-__global__ void k_brick_count(const __grid_constant__ DeviceScene S, const __grid_constant__ BrickLayout bl, int level, int32_t *brickCount) {
-    long long code = blockIdx.x;
+__global__ void k_brick_count(const __grid_constant__ DeviceScene S, const __grid_constant__ BrickLayout bl, int level, int32_t *brickCount,
+                              int32_t *brickCost) {
     int b[3];
-    brickCoord(bl, level, code, b);
+    brickCoord(bl, level, blockIdx.x, b);
     int32_t vals[6];
-    int n = brickThreadCount(S, level, b, threadIdx.x, vals);
+    int na[3];
+    brickThreadCount(S, level, b, threadIdx.x, vals, na);
+    int n = na[0] + na[1] + na[2];
     __shared__ int s[8];
     for (int o = 16; o > 0; o >>= 1) n += __shfl_down_sync(0xffffffffu, n, o);
     if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = n;
@@ -546,44 +612,58 @@ __global__ void k_brick_count(const __grid_constant__ DeviceScene S, const __gri
     if (threadIdx.x == 0) {
         int t = 0;
         for (int i = 0; i < 8; ++i) t += s[i];
-        brickCount[bl.base[level] + code] = t;
+        long long pos = brickPos(bl, level, b);
+        brickCount[pos] = t;
+        // estimated SpMV cost in units of 1/20 fine row: rows above level 0 carry ~1.65x the non-zeros (T-junction stencils)
+        brickCost[pos] = t * (level == 0 ? 20 : 33);
     }
 }
 
 __global__ void k_brick_assign(const __grid_constant__ DeviceScene S, const __grid_constant__ BrickLayout bl, int level,
                                const int32_t *brickCount, const long long *brickOffset, RowKey *keys) {
-    long long code = blockIdx.x;
-    if (brickCount[bl.base[level] + code] == 0) return;
     int b[3];
-    brickCoord(bl, level, code, b);
+    brickCoord(bl, level, blockIdx.x, b);
+    const long long pos = brickPos(bl, level, b);
+    if (brickCount[pos] == 0) return;
     int32_t vals[6];
-    int n = brickThreadCount(S, level, b, threadIdx.x, vals);
-    // block-wide exclusive scan of n
-    __shared__ int warpSum[8];
-    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int inc = n;
-    for (int o = 1; o < 32; o <<= 1) {
-        int v = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += v;
+    int na[3];
+    brickThreadCount(S, level, b, threadIdx.x, vals, na);
+    // block-wide exclusive scans, one per axis
+    __shared__ int warpSum[3][8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        inc[a] = na[a];
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, inc[a], o);
+            if (lane >= o) inc[a] += v;
+        }
+        if (lane == 31) warpSum[a][wid] = inc[a];
     }
-    if (lane == 31) warpSum[wid] = inc;
     __syncthreads();
-    int wbase = 0;
-    for (int i = 0; i < wid; ++i) wbase += warpSum[i];
-    long long idx = brickOffset[bl.base[level] + code] + wbase + inc - n;
+    long long axisBase = brickOffset[pos];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        int cellLocal = threadIdx.x * 2 + q;
-        int x = b[0] * BRICK + (cellLocal & 7), y = b[1] * BRICK + ((cellLocal >> 3) & 7), z = b[2] * BRICK + (cellLocal >> 6);
+    for (int a = 0; a < 3; ++a) {
+        int wbase = 0, total = 0;
+        for (int i = 0; i < 8; ++i) {
+            if (i < wid) wbase += warpSum[a][i];
+            total += warpSum[a][i];
+        }
+        long long idx = axisBase + wbase + inc[a] - na[a];
 #pragma unroll
-        for (int a = 0; a < 3; ++a)
+        for (int q = 0; q < 2; ++q) {
             if (vals[q * 3 + a] >= 0) {
+                int cellLocal = threadIdx.x * 2 + q;
+                int x = b[0] * BRICK + (cellLocal & 7), y = b[1] * BRICK + ((cellLocal >> 3) & 7), z = b[2] * BRICK + (cellLocal >> 6);
                 S.face[level][a].d[S.face[level][a].lin(x, y, z)] = (int32_t)idx;
                 RowKey k;
                 k.level = level; k.axis = a; k.i = x; k.j = y; k.k = z;
                 keys[idx] = k;
                 ++idx;
             }
+        }
+        axisBase += total;
     }
 }
 
@@ -663,6 +743,22 @@ int avs_exclusive_scan_i32_to_i64(AvsContext *c, const int32_t *dIn, int64_t *dO
     return AVS_OK;
 }
 
+// rank q's block starts at the first brick whose cost prefix reaches total*q/P (brick-granular, contiguous)
+__global__ void k_find_cuts(const long long *costPrefix, const long long *rowOffset, long long nbricks, long long totalCost,
+                            long long nRows, int P, long long *rowStarts) {
+    int q = threadIdx.x;
+    if (q > P) return;
+    if (q == 0) { rowStarts[0] = 0; return; }
+    if (q == P) { rowStarts[P] = nRows; return; }
+    long long target = totalCost * q / P;
+    long long lo = 0, hi = nbricks;  // first brick with prefix >= target
+    while (lo < hi) {
+        long long mid = (lo + hi) >> 1;
+        if (costPrefix[mid] >= target) hi = mid; else lo = mid + 1;
+    }
+    rowStarts[q] = lo < nbricks ? rowOffset[lo] : nRows;
+}
+
 int avs_stage_octree_labels(AvsContext *c) {
     DeviceScene &S = c->S;
     const int L = S.levels;
@@ -695,16 +791,16 @@ int avs_stage_octree_labels(AvsContext *c) {
         ce.d = c->center[l].as<int8_t>();
     }
     for (int l = 0; l < L; ++l) {
-        for (int a = 0; a < 3; ++a) LAUNCH_1D(c, k_classify_faces, S.face[l][a].count(), S, l, a, t0[a]);
+        for (int a = 0; a < 3; ++a) LAUNCH_3D(c, k_classify_faces, S.face[l][a].n, S, l, a, t0[a]);
         Grid3<uint8_t> te[3];
         int res[3][3];
         for (int a = 0; a < 3; ++a)
             for (int k = 0; k < 3; ++k) res[a][k] = S.edge[l][a].n[k];
         int rc = tileGrid(c, edgeTiles, te, res);
         if (rc) return rc;
-        LAUNCH_1D(c, k_mark_edge_tiles, S.label[l].count(), S.label[l], te[0], te[1], te[2]);
-        for (int a = 0; a < 3; ++a) LAUNCH_1D(c, k_classify_edges, S.edge[l][a].count(), S, l, a, te[a]);
-        LAUNCH_1D(c, k_classify_centers, S.center[l].count(), S, l);
+        LAUNCH_3D(c, k_mark_edge_tiles, S.label[l].n, S.label[l], te[0], te[1], te[2]);
+        for (int a = 0; a < 3; ++a) LAUNCH_3D(c, k_classify_edges, S.edge[l][a].n, S, l, a, te[a]);
+        LAUNCH_3D(c, k_classify_centers, S.center[l].n, S, l);
     }
     // counts of stress DOFs (the reference numbers them, AV.cpp:1632-1715; only the counts are reported here)
     unsigned long long *cnt = c->counters.as<unsigned long long>();
@@ -718,23 +814,20 @@ int avs_stage_octree_labels(AvsContext *c) {
     BrickLayout bl;
     memset(&bl, 0, sizeof(bl));
     bl.levels = L;
-    long long total = 0;
-    for (int l = 0; l < L; ++l) {
-        long long nb = 1;
-        for (int a = 0; a < 3; ++a) {
-            int bricks = std::max(1, S.label[l].n[a] / BRICK);
-            bl.bits[l][a] = ilog2(bricks);
-            nb *= bricks;
-        }
-        bl.base[l] = total;
-        total += nb;
-    }
-    bl.base[L] = total;
+    for (int l = 0; l < L; ++l)
+        for (int a = 0; a < 3; ++a) bl.nb[l][a] = std::max(1, S.label[l].n[a] / BRICK);
+    for (int l = 1; l < L; ++l)
+        for (int a = 0; a < 3; ++a) bl.lf[l][a] = ilog2(bl.nb[l - 1][a] / bl.nb[l][a]);
+    bl.sub[0] = 1;
+    for (int l = 1; l < L; ++l) bl.sub[l] = 1 + ((long long)1 << (bl.lf[l][0] + bl.lf[l][1] + bl.lf[l][2])) * bl.sub[l - 1];
+    const long long total = (long long)bl.nb[L - 1][0] * bl.nb[L - 1][1] * bl.nb[L - 1][2] * bl.sub[L - 1];
+    bl.total = total;
     if (c->brickCount.reserve((size_t)total * sizeof(int32_t))) return AVS_ERR_ALLOC;
+    if (c->brickCost.reserve((size_t)total * sizeof(int32_t))) return AVS_ERR_ALLOC;
     if (c->brickOffset.reserve((size_t)total * sizeof(long long))) return AVS_ERR_ALLOC;
     for (int l = 0; l < L; ++l) {
-        unsigned nb = (unsigned)(bl.base[l + 1] - bl.base[l]);
-        k_brick_count<<<nb, 256, 0, c->stream>>>(S, bl, l, c->brickCount.as<int32_t>());
+        unsigned nb = (unsigned)((long long)bl.nb[l][0] * bl.nb[l][1] * bl.nb[l][2]);
+        k_brick_count<<<nb, 256, 0, c->stream>>>(S, bl, l, c->brickCount.as<int32_t>(), c->brickCost.as<int32_t>());
         ++c->launches;
     }
     int64_t nRows = 0;
@@ -744,10 +837,25 @@ int avs_stage_octree_labels(AvsContext *c) {
     if (nRows >= (int64_t)2147483000) return AVS_ERR_UNSUPPORTED;  // int32 DOF indices
     if (c->rowKeys.reserve((size_t)std::max<int64_t>(nRows, 1) * sizeof(RowKey))) return AVS_ERR_ALLOC;
     for (int l = 0; l < L; ++l) {
-        unsigned nb = (unsigned)(bl.base[l + 1] - bl.base[l]);
+        unsigned nb = (unsigned)((long long)bl.nb[l][0] * bl.nb[l][1] * bl.nb[l][2]);
         k_brick_assign<<<nb, 256, 0, c->stream>>>(S, bl, l, c->brickCount.as<int32_t>(), c->brickOffset.as<long long>(),
                                                   c->rowKeys.as<RowKey>());
         ++c->launches;
+    }
+    // multi-GPU row partition: contiguous blocks of the depth-first order, cut at brick
+    // boundaries where the estimated SpMV cost prefix crosses q/P of the total
+    c->rowStarts.assign(c->nranks + 1, 0);
+    c->rowStarts[c->nranks] = nRows;
+    if (c->nranks > 1) {
+        if (c->brickCostPrefix.reserve((size_t)(total + 32) * sizeof(long long))) return AVS_ERR_ALLOC;
+        int64_t totalCost = 0;
+        rc = avs_exclusive_scan_i32_to_i64(c, c->brickCost.as<int32_t>(), c->brickCostPrefix.as<int64_t>(), total, &totalCost);
+        if (rc) return rc;
+        long long *dStarts = c->brickCostPrefix.as<long long>() + total;
+        k_find_cuts<<<1, 32, 0, c->stream>>>(c->brickCostPrefix.as<long long>(), c->brickOffset.as<long long>(), total, totalCost, nRows,
+                                            c->nranks, dStarts);
+        ++c->launches;
+        AVS_CUDA_CHECK(cudaMemcpyAsync(c->rowStarts.data(), dStarts, (size_t)(c->nranks + 1) * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     }
     unsigned long long h[3];
     AVS_CUDA_CHECK(cudaMemcpyAsync(h, cnt + 16, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));

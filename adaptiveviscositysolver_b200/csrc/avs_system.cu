@@ -31,7 +31,7 @@ struct Stencil {
 };
 
 // getEdgeStressFaces (AV.cpp:1717-1908)
-__device__ void edgeStressFaces(const DeviceScene &S, Stencil &st, const I3 &edge, int axis, int level) {
+__device__ __noinline__ void edgeStressFaces(const DeviceScene &S, Stencil &st, const I3 &edge, int axis, int level) {
     st.n = st.nb = 0;
     const double dx = S.levelDx(level);  // AV.cpp:1733
     bool isAtTransition[3] = {false, false, false};
@@ -109,7 +109,7 @@ __device__ void edgeStressFaces(const DeviceScene &S, Stencil &st, const I3 &edg
 }
 
 // getCenterStressFaces (AV.cpp:1910-1963)
-__device__ void centerStressFaces(const DeviceScene &S, Stencil &st, const I3 &cell, int axis, int level) {
+__device__ __noinline__ void centerStressFaces(const DeviceScene &S, Stencil &st, const I3 &cell, int axis, int level) {
     st.n = st.nb = 0;
     const double dx = S.levelDx(level);
     for (int dir = 0; dir < 2; ++dir) {
@@ -166,7 +166,7 @@ __device__ double edgeOctreeVolume(const DeviceScene &S, const I3 &edge, int axi
 }
 
 // stress weights: AV.cpp:2124-2155 (edges), AV.cpp:2223-2289 (centres)
-__device__ double edgeStressWeight(const DeviceScene &S, const I3 &edge, int axis, int level) {
+__device__ __noinline__ double edgeStressWeight(const DeviceScene &S, const I3 &edge, int axis, int level) {
     double w;
     if (level == 0) {
         w = (double)S.edgeW[axis].get(edge);
@@ -326,7 +326,7 @@ struct RowAcc {
 };
 
 // applyToMatrix (AV.cpp:2404-2457)
-__device__ __forceinline__ void applyToMatrix(RowAcc &row, double &rhsI, double &diag, double coefficient, int32_t vi, const Stencil &st) {
+__device__ __noinline__ void applyToMatrix(RowAcc &row, double &rhsI, double &diag, double coefficient, int32_t vi, const Stencil &st) {
     for (int i = 0; i < st.n; ++i)
         if (st.idx[i] == vi) { coefficient *= st.coef[i]; break; }
     for (int i = 0; i < st.n; ++i) {
@@ -473,9 +473,9 @@ __global__ void k_csr_from_stage(long long nLocal, long long stride, const int32
 int avs_stage_system(AvsContext *c, const AvsParams *p) {
     (void)p;
     const long long n = c->nRows;
-    // row partition for the multi-GPU CG: contiguous, equal row counts
-    c->rowBegin = n * c->rank / c->nranks;
-    c->rowEnd = n * (c->rank + 1) / c->nranks;
+    // row partition: computed with the numbering (avs_stage_octree_labels)
+    c->rowBegin = c->rowStarts[c->rank];
+    c->rowEnd = c->rowStarts[c->rank + 1];
     const long long nLocal = c->rowEnd - c->rowBegin;
     const long long stride = (nLocal + 31) / 32 * 32;
     c->stageStride = stride;
@@ -544,11 +544,12 @@ int avs_build_csr(AvsContext *c) {
 __global__ void k_apply_regular(const __grid_constant__ DeviceScene S, int axis, const double *sol, float *out,
                                 unsigned long long *pending) {
     const Grid3<int8_t> g = S.regular[axis];
-    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= g.count()) return;
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
+    if (x >= g.n[0]) return;
+    const size_t idx = g.lin(x, y, z);
     int8_t lab = g.d[idx];
     if (lab == F_UNASSIGNED || lab == F_OUTSIDE) return;
-    I3 face = mk3((int)(idx % g.n[0]), (int)((idx / g.n[0]) % g.n[1]), (int)(idx / ((size_t)g.n[0] * g.n[1])));
+    I3 face = mk3(x, y, z);
     double p[3];
     if (lab == F_SOLID) {  // AV.cpp:2881-2890
         S.facePos(face, axis, 0, p);
@@ -568,8 +569,9 @@ int avs_apply_regular(AvsContext *c, float *dOut[3], unsigned long long *hostPen
     unsigned long long *cnt = c->counters.as<unsigned long long>() + 26;
     AVS_CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
     for (int a = 0; a < 3; ++a) {
-        size_t n = c->S.regular[a].count();
-        k_apply_regular<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->S, a, c->nranks > 1 ? c->fullSolution.as<double>() : c->solution.as<double>(), dOut[a], cnt);
+        const int *n3 = c->S.regular[a].n;
+        dim3 grid((unsigned)((n3[0] + 127) / 128), (unsigned)n3[1], (unsigned)n3[2]);
+        k_apply_regular<<<grid, 128, 0, c->stream>>>(c->S, a, c->nranks > 1 ? c->fullSolution.as<double>() : c->solution.as<double>(), dOut[a], cnt);
         ++c->launches;
     }
     AVS_CUDA_CHECK(cudaMemcpyAsync(hostPending, cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));

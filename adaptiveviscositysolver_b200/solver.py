@@ -74,13 +74,16 @@ class SolveInfo:
     pending_interpolated_faces: int
     cg_update_xr_ms: float = 0.0
     cg_update_p_ms: float = 0.0
+    dist_mode: int = 0
+    halo_columns: int = 0
 
     @staticmethod
     def from_c(r: AvsResult) -> "SolveInfo":
         return SolveInfo(r.status, r.iterations, r.error, r.levels, r.octree_dofs, r.regular_dofs, r.edge_dofs,
                          r.center_dofs, r.nnz, r.local_rows, r.spmv_launches, r.kernel_launches,
                          {STAGE_NAMES[i]: float(r.stage_ms[i]) for i in range(11)}, float(r.spmv_ms),
-                         r.pending_interpolated_faces, float(r.cg_update_xr_ms), float(r.cg_update_p_ms))
+                         r.pending_interpolated_faces, float(r.cg_update_xr_ms), float(r.cg_update_p_ms), r.dist_mode,
+                         r.halo_columns)
 
 
 def _new_result() -> AvsResult:
@@ -250,6 +253,11 @@ class Solver:
         b, e = C.c_int64(), C.c_int64()
         self._check(self._L.avs_get_local_range(self._h, C.byref(b), C.byref(e)), "avs_get_local_range")
         return b.value, e.value
+
+    def row_starts(self, nranks: int) -> list:
+        a = (C.c_int64 * (nranks + 1))()
+        self._check(self._L.avs_get_row_starts(self._h, a), "avs_get_row_starts")
+        return list(a)
 
     def keys(self) -> np.ndarray:
         n, _, _ = self.sizes()

@@ -263,6 +263,12 @@ def main():
 
     s = 4 if args.fp32 else 8
     alg_bytes = nnz * (s + 4) + (n_local + 1) * 4 + 2 * n_local * s   # this rank's SpMV
+    per_rank = None
+    if world > 1:
+        box = [None] * world
+        dist.all_gather_object(box, {"rank": rank, "rows": int(n_local), "nnz": int(nnz), "spmv_ms": spmv_ms / max(spmv_n, 1),
+                                     "halo": int(info.halo_columns), "solve_ms": info.stage_ms["solve"]})
+        per_rank = box
     # the same kernel launched back to back (matrix >> L2), for reference / when events are off
     iso_ms, _ = solver.time_spmv_resident(20)
     spmv_avg_ms = spmv_ms / max(spmv_n, 1) if spmv_ms > 0 else iso_ms
@@ -312,10 +318,10 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32" if args.fp32 else "f64", "data": "synthetic",
-            "config": {"workload": w["desc"], "N": int(N), "nnz": int(nnz_total), "rows_per_rank": int(n_local), "levels": int(info.levels), "iterations": int(iters),
+            "config": {"workload": w["desc"], "N": int(N), "nnz": int(nnz_total), "rows_per_rank": int(n_local), "dist_mode": {0: "single", 1: "nccl", 2: "peer-memory"}[info.dist_mode], "halo_columns": int(info.halo_columns), "levels": int(info.levels), "iterations": int(iters),
                        "rel_error": info.error, "tolerance": w["tol"], "regular_dofs": int(info.regular_dofs),
                        "l2": "matrix+vectors per SpMV = %.0f MB vs 126 MB L2 (inputs larger than L2, no flush)" % (alg_bytes / 1e6),
-                       "wall_ms_per_step": wall_ms,
+                       "wall_ms_per_step": wall_ms, "per_rank": per_rank,
                        "stage_ms": {k2: round(v, 3) for k2, v in info.stage_ms.items()}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "k_spmv_sjds (CG SpMV + fused p.Ap)", "peak_source": peak_src,

@@ -138,6 +138,9 @@ typedef struct AvsResult {
     float spmv_ms;            /* accumulated device time of the SpMV launches (only with AvsDeviceConfig.time_spmv) */
     float cg_update_xr_ms;    /* accumulated device time of the x,r update kernel (time_spmv only) */
     float cg_update_p_ms;     /* accumulated device time of the p update kernel (time_spmv only)   */
+    int32_t dist_mode;        /* 0 single GPU, 1 NCCL hot loop, 2 peer-memory (NVLink loads/stores in our kernels) */
+    int32_t reserved0;
+    int64_t halo_columns;     /* off-rank columns this rank's rows reference */
     int64_t pending_interpolated_faces; /* regular faces inside coarse cells that still need the octree interpolator
                                           (HDK_OctreeVectorFieldInterpolator); 0 when depth == 1 */
 } AvsResult;
@@ -182,6 +185,7 @@ int avs_apply(AvsContext *ctx, AvsVelocityOut *out, AvsResult *res);
  * results are compared by geometric key. */
 int avs_get_sizes(AvsContext *ctx, int64_t *n_rows, int64_t *nnz, int32_t *levels);
 int avs_get_local_range(AvsContext *ctx, int64_t *row_begin, int64_t *row_end);  /* rows owned by this rank */
+int avs_get_row_starts(AvsContext *ctx, int64_t *starts /* [nranks+1] */);  /* first row of every rank's block */
 int avs_get_keys(AvsContext *ctx, int32_t *keys);
 /* row_ptr/col/val/rhs cover the rows this rank owns (global column ids); x0 is the full restricted u^n [n_rows] */
 int avs_get_system_csr(AvsContext *ctx, int64_t *row_ptr, int32_t *col, double *val, double *rhs, double *x0);

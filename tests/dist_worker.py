@@ -16,7 +16,7 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from adaptiveviscositysolver_b200.dist_plan import halo_plan, row_range
+    from adaptiveviscositysolver_b200.dist_plan import halo_plan
     from adaptiveviscositysolver_b200.scenes import sphere_drop
     from adaptiveviscositysolver_b200.solver import Params, Solver, nccl_unique_id
     from tests.util import perm_gpu_to_oracle
@@ -31,7 +31,9 @@ def main():
         out = [v.data.copy() for v in sc.vel]
         info = s.solve(sc, Params(octree_levels=L, tolerance=tol), out)
         rb, re = s.local_range()
-        assert (rb, re) == row_range(info.octree_dofs, rank, world)
+        starts = s.row_starts(world)
+        assert (rb, re) == (starts[rank], starts[rank + 1]) and starts[0] == 0 and starts[-1] == info.octree_dofs
+        assert all(b >= a for a, b in zip(starts, starts[1:]))
         x_local = s.solution()
         parts = [None] * world
         dist.all_gather_object(parts, x_local)
@@ -39,7 +41,8 @@ def main():
         dist.all_gather_object(outs, [o.copy() for o in out])
         # device halo plan == host statement of the plan
         ptr, col, val, rhs, x0 = s.system()
-        halo, _, cnt = halo_plan(ptr, col, rb, re, info.octree_dofs, world)
+        halo, _, cnt = halo_plan(ptr, col, rb, re, info.octree_dofs, world, starts)
+        assert halo.size == info.halo_columns, (halo.size, info.halo_columns)
         halos = [None] * world
         dist.all_gather_object(halos, int(halo.size))
         if rank == 0:
@@ -51,7 +54,7 @@ def main():
             same_out = all(all(np.array_equal(a, b) for a, b in zip(outs[0], o)) for o in outs[1:])
             frac = max(halos) / (info.octree_dofs / world)
             print(f"[dist_worker] world={world} n={n} N={info.octree_dofs} iters={info.iterations} (oracle {ref.iterations}) "
-                  f"max|x-x_oracle|={err:.3e} halo/rows={frac:.3f} outputs_identical={same_out}", flush=True)
+                  f"max|x-x_oracle|={err:.3e} halo/rows={frac:.3f} outputs_identical={same_out} dist_mode={info.dist_mode}", flush=True)
             ok = ok and err < 1e-6 and abs(info.iterations - ref.iterations) <= 2 and same_out and frac < 0.5
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
