@@ -115,7 +115,7 @@ void avs_destroy(AvsContext *c) {
                       &c->scanTmp, &c->counters, &c->rowKeys, &c->x0, &c->rhs, &c->solution, &c->rowCount, &c->rowOffset,
                       &c->csrPtr, &c->csrCol, &c->csrVal, &c->A.sliceOff, &c->A.val, &c->A.col, &c->A.invDiag, &c->A.meta,
                       &c->cg.x, &c->cg.r, &c->cg.p, &c->cg.t, &c->cg.partials, &c->cg.scalars, &c->cgRhs,
-                      &c->stageCol, &c->stageVal, &c->diag, &c->slicePairs, &c->edgeTiles, &c->solidW, &c->signA, &c->signB, &c->brickCost, &c->brickCostPrefix};
+                      &c->stageCol, &c->stageVal, &c->diag, &c->slicePairs, &c->edgeTiles, &c->solidW, &c->signA, &c->signB, &c->bandList, &c->brickCost, &c->brickCostPrefix};
     for (DevBuf *b : bufs) b->release();
     for (int a = 0; a < 3; ++a) {
         c->inVel[a].release(); c->inFaceW[a].release(); c->inCollVel[a].release(); c->edgeW[a].release(); c->regular[a].release();

@@ -32,17 +32,21 @@ static_assert(sizeof(DeviceScene) <= 4000, "DeviceScene must fit the kernel para
 #define LAUNCH_3D(ctx, kernel, n3, ...)                                                        \
     do {                                                                                       \
         if ((n3)[0] > 0 && (n3)[1] > 0 && (n3)[2] > 0) {                                        \
-            dim3 _g((unsigned)(((n3)[0] + 127) / 128), (unsigned)(n3)[1], (unsigned)(n3)[2]);    \
+            dim3 _g((unsigned)(((n3)[0] + 127) / 128), (unsigned)(n3)[1], (unsigned)(((n3)[2] + ZREP - 1) / ZREP));    \
             kernel<<<_g, 128, 0, (ctx)->stream>>>(__VA_ARGS__);                                \
             ++(ctx)->launches;                                                                 \
         }                                                                                      \
     } while (0)
-__device__ __forceinline__ bool cell3(const int n[3], int &x, int &y, int &z, size_t &idx) {
-    x = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    y = (int)blockIdx.y;
-    z = (int)blockIdx.z;
-    idx = (size_t)x + (size_t)n[0] * ((size_t)y + (size_t)n[1] * (size_t)z);
-    return x < n[0];
+#define ZREP 1   // grid cells per thread along z (8 was measured slower: serialises the per-cell loads of a thread)
+template <class F>
+__device__ __forceinline__ void forCells(const int n[3], F f) {
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y;
+    const bool inx = x < n[0];
+    for (int r = 0; r < ZREP; ++r) {
+        const int z = (int)blockIdx.z * ZREP + r;
+        if (z >= n[2]) return;  // uniform over the CTA
+        f(x, y, z, (size_t)x + (size_t)n[0] * ((size_t)y + (size_t)n[1] * (size_t)z), inx);  // inx == false: lane is outside the row
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -50,11 +54,9 @@ __device__ __forceinline__ bool cell3(const int n[3], int &x, int &y, int &z, si
 // offsets ((k+1/2)/n - 1/2) dx whose interpolated sdf (minus dilate) is negative.
 // Early-out: the trilinear interpolant is a convex combination of the voxels it touches, so when
 // every voxel under the sample's box has the same sign the count is n^3 or 0 without sampling.
-__global__ void k_sdf_weights(Grid3<float> w, DField sdf, double off0, double off1, double off2, double o0,
-                              double o1, double o2, double dx0, int n, double dilate, const uint8_t *signClass) {
-    size_t idx;
-    int x, y, z;
-    if (!cell3(w.n, x, y, z, idx)) return;
+__device__ void sdfWeightSample(Grid3<float> w, const DField &sdf, double off0, double off1, double off2, double o0,
+                                double o1, double o2, double dx0, int n, double dilate, const uint8_t *signClass,
+                                int x, int y, int z, size_t idx) {
     double c[3] = {o0 + (x + off0) * dx0, o1 + (y + off1) * dx0, o2 + (z + off2) * dx0};
     if (!sdf.d) {
         w.d[idx] = ((double)sdf.constant - dilate < 0.0) ? 1.f : 0.f;
@@ -94,15 +96,100 @@ __global__ void k_sdf_weights(Grid3<float> w, DField sdf, double off0, double of
     if (allNeg) { w.d[idx] = 1.f; return; }
     if (allPos) { w.d[idx] = 0.f; return; }
     int count = 0;
-    for (int sz = 0; sz < n; ++sz)
-        for (int sy = 0; sy < n; ++sy)
-            for (int sx = 0; sx < n; ++sx) {
-                double p[3] = {c[0] + ((sx + 0.5) * inv - 0.5) * dx0, c[1] + ((sy + 0.5) * inv - 0.5) * dx0,
-                               c[2] + ((sz + 0.5) * inv - 0.5) * dx0};
-                if (sdf.value(p) - dilate < 0.0) ++count;
+    if (n <= 4) {
+        // The sub-sample lattice is separable, so the interpolation indices/weights of DField::value() take only
+        // n distinct values per axis: evaluate those once (same expressions, same rounding) and reuse them.
+        int i0[3][4], i1[3][4];
+        double tt[3][4];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            for (int s = 0; s < n; ++s) {
+                double pa = c[a] + ((s + 0.5) * inv - 0.5) * dx0;
+                double g = (pa - sdf.org[a]) / sdf.dx;
+                double top = (double)(sdf.n[a] - 1);
+                if (g < 0.0) g = 0.0;
+                if (g > top) g = top;
+                double f = floor(g);
+                i0[a][s] = (int)f;
+                i1[a][s] = min((int)f + 1, sdf.n[a] - 1);
+                tt[a][s] = g - f;
             }
+        const size_t sy_ = (size_t)sdf.n[0], sz_ = (size_t)sdf.n[0] * sdf.n[1];
+        const float *b = sdf.d;
+        for (int sz = 0; sz < n; ++sz)
+            for (int sy = 0; sy < n; ++sy)
+                for (int sx = 0; sx < n; ++sx) {
+                    const int x0 = i0[0][sx], x1 = i1[0][sx], y0 = i0[1][sy], y1 = i1[1][sy], z0 = i0[2][sz], z1 = i1[2][sz];
+                    const double tx = tt[0][sx], ty = tt[1][sy], tz = tt[2][sz];
+                    double v000 = b[x0 + sy_ * y0 + sz_ * z0], v100 = b[x1 + sy_ * y0 + sz_ * z0];
+                    double v010 = b[x0 + sy_ * y1 + sz_ * z0], v110 = b[x1 + sy_ * y1 + sz_ * z0];
+                    double v001 = b[x0 + sy_ * y0 + sz_ * z1], v101 = b[x1 + sy_ * y0 + sz_ * z1];
+                    double v011 = b[x0 + sy_ * y1 + sz_ * z1], v111 = b[x1 + sy_ * y1 + sz_ * z1];
+                    double c00 = v000 + tx * (v100 - v000);
+                    double c10 = v010 + tx * (v110 - v010);
+                    double c01 = v001 + tx * (v101 - v001);
+                    double c11 = v011 + tx * (v111 - v011);
+                    double c0 = c00 + ty * (c10 - c00);
+                    double c1 = c01 + ty * (c11 - c01);
+                    if ((c0 + tz * (c1 - c0)) - dilate < 0.0) ++count;
+                }
+    } else {
+        for (int sz = 0; sz < n; ++sz)
+            for (int sy = 0; sy < n; ++sy)
+                for (int sx = 0; sx < n; ++sx) {
+                    double p[3] = {c[0] + ((sx + 0.5) * inv - 0.5) * dx0, c[1] + ((sy + 0.5) * inv - 0.5) * dx0,
+                                   c[2] + ((sz + 0.5) * inv - 0.5) * dx0};
+                    if (sdf.value(p) - dilate < 0.0) ++count;
+                }
+    }
     const double total = (double)n * n * n;
     w.d[idx] = (float)((double)count / total);
+}
+
+// Light pass (aligned sdf grid only): weight = 1 / 0 from the precomputed sign class of the sample's voxel
+// neighbourhood; samples in the mixed band are appended to `list` for k_sdf_weights (few registers, full occupancy:
+// the register-heavy sampler below ran the trivial 98 % of the samples at 12 % occupancy).
+__global__ void k_weights_classify(Grid3<float> w, int sn0, int sn1, int sn2, const uint8_t *signClass, uint32_t *list,
+                                   unsigned long long *listCount) {
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
+    bool band = false;
+    size_t idx = 0;
+    if (x < w.n[0]) {
+        idx = w.lin(x, y, z);
+        int cx = min(x, sn0 - 1), cy = min(y, sn1 - 1), cz = min(z, sn2 - 1);
+        uint8_t cls = signClass[(size_t)cx + (size_t)sn0 * ((size_t)cy + (size_t)sn1 * cz)];
+        if (cls == 0) w.d[idx] = 1.f;
+        else if (cls == 1) w.d[idx] = 0.f;
+        else band = true;
+    }
+    // warp-aggregated append
+    unsigned m = __ballot_sync(0xffffffffu, band);
+    if (m) {
+        int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(listCount, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (band) list[base + __popc(m & ((1u << lane) - 1))] = (uint32_t)idx;
+    }
+}
+
+__global__ void k_sdf_weights(Grid3<float> w, DField sdf, double off0, double off1, double off2, double o0,
+                              double o1, double o2, double dx0, int n, double dilate, const uint8_t *signClass,
+                              const uint32_t *list, const unsigned long long *listCount) {
+    if (list) {  // list-driven: one thread per band sample
+        unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+        if (t >= *listCount) return;
+        size_t idx = list[t];
+        int x = (int)(idx % w.n[0]);
+        int y = (int)((idx / w.n[0]) % w.n[1]);
+        int z = (int)(idx / ((size_t)w.n[0] * w.n[1]));
+        sdfWeightSample(w, sdf, off0, off1, off2, o0, o1, o2, dx0, n, dilate, nullptr, x, y, z, idx);
+        return;
+    }
+    forCells(w.n, [&](int x, int y, int z, size_t idx, bool ok) {
+        if (!ok) return;
+        sdfWeightSample(w, sdf, off0, off1, off2, o0, o1, o2, dx0, n, dilate, signClass, x, y, z, idx);
+    });
 }
 
 // ---- sign classes of the 3x3x3 voxel neighbourhood (clamped), separable: x, then y, then z ------------
@@ -110,22 +197,22 @@ __global__ void k_sdf_weights(Grid3<float> w, DField sdf, double off0, double of
 __device__ __forceinline__ uint8_t combine3(uint8_t a, uint8_t b, uint8_t c) { return (a == b && b == c) ? a : (uint8_t)2; }
 __global__ void k_sign_x(const float *sdf, int nx, int ny, int nz, uint8_t *out) {
     const int n3[3] = {nx, ny, nz};
-    size_t idx;
-    int x, y, z;
-    if (!cell3(n3, x, y, z, idx)) return;
+    forCells(n3, [&](int x, int y, int z, size_t idx, bool ok) {
+        if (!ok) return;
     size_t row = idx - x;
     uint8_t a = sdf[row + max(x - 1, 0)] < 0.f ? 0 : 1, b = sdf[idx] < 0.f ? 0 : 1, c = sdf[row + min(x + 1, nx - 1)] < 0.f ? 0 : 1;
     out[idx] = combine3(a, b, c);
+    });
 }
 __global__ void k_sign_axis(const uint8_t *in, int nx, int ny, int nz, int axis, uint8_t *out) {
     const int n3[3] = {nx, ny, nz};
-    size_t idx;
-    int x, y, z;
-    if (!cell3(n3, x, y, z, idx)) return;
+    forCells(n3, [&](int x, int y, int z, size_t idx, bool ok) {
+        if (!ok) return;
     size_t stride = axis == 1 ? (size_t)nx : (size_t)nx * ny;
     int pos = axis == 1 ? y : z, top = axis == 1 ? ny - 1 : nz - 1;
     uint8_t a = in[pos > 0 ? idx - stride : idx], b = in[idx], c = in[pos < top ? idx + stride : idx];
     out[idx] = combine3(a, b, c);
+    });
 }
 
 // setScaleDivideThreshold(1, nullptr, &b, 0): a /= b where b > 0 (AV.cpp:781-789)
@@ -139,8 +226,26 @@ static int weightsFor(AvsContext *c, DevBuf &buf, Grid3<float> &g, const DField 
     g.n[0] = res[0]; g.n[1] = res[1]; g.n[2] = res[2];
     if (buf.reserve(g.count() * sizeof(float))) return AVS_ERR_ALLOC;
     g.d = buf.as<float>();
+    if (signClass && g.count() < 0xffffffffull) {
+        if (c->bandList.reserve(g.count() * sizeof(uint32_t))) return AVS_ERR_ALLOC;
+        unsigned long long *cnt = c->counters.as<unsigned long long>() + 30;
+        AVS_CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
+        dim3 grid((unsigned)((g.n[0] + 127) / 128), (unsigned)g.n[1], (unsigned)g.n[2]);
+        k_weights_classify<<<grid, 128, 0, c->stream>>>(g, sdf.n[0], sdf.n[1], sdf.n[2], signClass, c->bandList.as<uint32_t>(), cnt);
+        ++c->launches;
+        unsigned long long h = 0;
+        AVS_CUDA_CHECK(cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (h > 0) {
+            k_sdf_weights<<<(unsigned)((h + 127) / 128), 128, 0, c->stream>>>(g, sdf, off[0], off[1], off[2], c->S.origin[0], c->S.origin[1],
+                                                                            c->S.origin[2], c->S.dx0, n, dilate, nullptr,
+                                                                            c->bandList.as<uint32_t>(), cnt);
+            ++c->launches;
+        }
+        return AVS_OK;
+    }
     LAUNCH_3D(c, k_sdf_weights, g.n, g, sdf, off[0], off[1], off[2], c->S.origin[0], c->S.origin[1],
-              c->S.origin[2], c->S.dx0, n, dilate, signClass);
+              c->S.origin[2], c->S.dx0, n, dilate, signClass, nullptr, nullptr);
     return AVS_OK;
 }
 
@@ -192,9 +297,8 @@ int avs_stage_weights(AvsContext *c, const AvsParams *p) {
 // mask 0 -> ACTIVE, < 0 -> UP, > 0 (or outside the un-padded grid) -> INACTIVE.
 __global__ void k_base_labels(const __grid_constant__ DeviceScene S, double inner, double outer) {
     const Grid3<uint8_t> lab = S.label[0];
-    size_t idx;
-    int x, y, z;
-    if (!cell3(lab.n, x, y, z, idx)) return;
+    forCells(lab.n, [&](int x, int y, int z, size_t idx, bool ok) {
+        if (!ok) return;
     uint8_t out = L_INACTIVE;
     if (x < S.N[0] && y < S.N[1] && z < S.N[2]) {
         double sdf = (double)S.surface.raw(x, y, z);
@@ -209,13 +313,13 @@ __global__ void k_base_labels(const __grid_constant__ DeviceScene S, double inne
         }
     }
     lab.d[idx] = out;
+    });
 }
 
 // pass 1, setActiveCellsAndParentList (OG.cpp:394-565): one thread per 2x2x2 sibling block.
 __global__ void k_octree_pass1(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
-    size_t idx;
-    int px, py, pz;
-    if (!cell3(par.n, px, py, pz, idx)) return;
+    forCells(par.n, [&](int px, int py, int pz, size_t idx, bool ok) {
+        if (!ok) return;
     uint8_t v[8];
     bool any = false;
 #pragma unroll
@@ -228,21 +332,21 @@ __global__ void k_octree_pass1(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
     for (int ch = 0; ch < 8; ++ch)
         if (v[ch] == L_UP) cur.d[cur.lin(2 * px + (ch & 1), 2 * py + ((ch >> 1) & 1), 2 * pz + (ch >> 2))] = L_ACTIVE;
     par.d[idx] = L_DOWN;
+    });
 }
 
 // pass 2, setFaceGrading (OG.cpp:656-754). The reference applies its DOWN list before its ACTIVE
 // list (OG.cpp:145, 162); two kernels keep that order.
 __global__ void k_octree_pass2_down(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
-    size_t idx;
-    int x, y, z;
-    if (!cell3(cur.n, x, y, z, idx)) return;
+    forCells(cur.n, [&](int x, int y, int z, size_t idx, bool ok) {
+        if (!ok) return;
     if (cur.d[idx] != L_DOWN) return;
     par.d[par.lin(x >> 1, y >> 1, z >> 1)] = L_DOWN;
+    });
 }
 __global__ void k_octree_pass2_active(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
-    size_t idx;
-    int x, y, z;
-    if (!cell3(cur.n, x, y, z, idx)) return;
+    forCells(cur.n, [&](int x, int y, int z, size_t idx, bool ok) {
+        if (!ok) return;
     if (cur.d[idx] != L_ACTIVE) return;
     I3 c = mk3(x, y, z);
 #pragma unroll
@@ -253,15 +357,16 @@ __global__ void k_octree_pass2_active(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
             if (a[axis] < 0 || a[axis] >= cur.n[axis]) continue;
             if (cur.at(a) == L_UP) par.d[par.lin(a[0] >> 1, a[1] >> 1, a[2] >> 1)] = L_ACTIVE;
         }
+    });
 }
 // pass 3, setParentsUp (OG.cpp:756-840)
 __global__ void k_octree_pass3(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
-    size_t idx;
-    int x, y, z;
-    if (!cell3(cur.n, x, y, z, idx)) return;
+    forCells(cur.n, [&](int x, int y, int z, size_t idx, bool ok) {
+        if (!ok) return;
     if (cur.d[idx] != L_UP) return;
     size_t pi = par.lin(x >> 1, y >> 1, z >> 1);
     if (par.d[pi] == L_INACTIVE) par.d[pi] = L_UP;
+    });
 }
 // setTopLevel (OG.cpp:843-875)
 __global__ void k_octree_top(Grid3<uint8_t> g) {
@@ -353,6 +458,11 @@ int avs_stage_octree(AvsContext *c, const AvsParams *p) {
 // ------------------------------------------------------------------------------------------------
 // Stage 4/5: labelling.  The reference only classifies inside 16^3 tiles it found "occupied"
 // (findOccupied*Tiles, AV.cpp:886-1057); everything else keeps UNASSIGNED.  Tile maps are uint8.
+// warp-aggregated count of lanes whose predicate holds (every lane of the warp must call it)
+__device__ __forceinline__ void countWarp(bool hit, unsigned long long *counter) {
+    unsigned m = __ballot_sync(0xffffffffu, hit);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(counter, (unsigned long long)__popc(m));
+}
 __device__ __forceinline__ void markTile(const Grid3<uint8_t> &t, const I3 &c) {
     t.d[t.lin(c[0] / AVS_TILE, c[1] / AVS_TILE, c[2] / AVS_TILE)] = 1;
 }
@@ -363,14 +473,14 @@ __device__ __forceinline__ bool tileOccupied(const Grid3<uint8_t> &t, int x, int
 // findOccupiedRegularVelocityTiles (AV.cpp:886-943): both faces of every cell with sdf < 2 dx
 __global__ void k_mark_surface_tiles(const __grid_constant__ DeviceScene S, Grid3<uint8_t> t0, Grid3<uint8_t> t1,
                                      Grid3<uint8_t> t2) {
-    size_t idx;
-    int x, y, z;
-    if (!cell3(S.N, x, y, z, idx)) return;
+    forCells(S.N, [&](int x, int y, int z, size_t idx, bool ok) {
+        if (!ok) return;
     if (!((double)S.surface.raw(x, y, z) < 2.0 * S.dx0)) return;
     I3 c = mk3(x, y, z);
     markTile(t0, c); markTile(t0, cellToFace(c, 0, 1));
     markTile(t1, c); markTile(t1, cellToFace(c, 1, 1));
     markTile(t2, c); markTile(t2, cellToFace(c, 2, 1));
+    });
 }
 
 // face activity test shared by AV.cpp:1127-1150 and AV.cpp:1235-1258
@@ -388,12 +498,12 @@ __device__ __forceinline__ bool faceHasWeight(const DeviceScene &S, const I3 &fa
 }
 
 // classifyRegularVelocityFaces (AV.cpp:1087-1165)
-__global__ void k_classify_regular(const __grid_constant__ DeviceScene S, int axis, Grid3<uint8_t> tiles) {
+__global__ void k_classify_regular(const __grid_constant__ DeviceScene S, int axis, Grid3<uint8_t> tiles, unsigned long long *counter) {
     const Grid3<int8_t> g = S.regular[axis];
-    size_t idx;
-    int x, y, z;
-    if (!cell3(g.n, x, y, z, idx)) return;
+    forCells(g.n, [&](int x, int y, int z, size_t idx, bool ok) {
+    const bool in = ok;
     int8_t out = F_UNASSIGNED;
+    if (in) {
     I3 face = mk3(x, y, z);
     if (tileOccupied(tiles, x, y, z) && face[axis] - 1 >= 0 && face[axis] < S.N[axis]) {
         if (faceHasWeight(S, face, axis)) {
@@ -403,14 +513,16 @@ __global__ void k_classify_regular(const __grid_constant__ DeviceScene S, int ax
         }
     }
     g.d[idx] = out;
+    }
+    countWarp(in && out == F_FLUID, counter);
+    });
 }
 
 // classifyOctreeVelocityFaces (AV.cpp:1167-1323)
 __global__ void k_classify_faces(const __grid_constant__ DeviceScene S, int level, int axis, Grid3<uint8_t> tiles) {
     const Grid3<int32_t> g = S.face[level][axis];
-    size_t idx;
-    int x, y, z;
-    if (!cell3(g.n, x, y, z, idx)) return;
+    forCells(g.n, [&](int x, int y, int z, size_t idx, bool ok) {
+        if (!ok) return;
     int32_t out = F_UNASSIGNED;
     I3 face = mk3(x, y, z);
     const Grid3<uint8_t> &lab = S.label[level];
@@ -435,13 +547,13 @@ __global__ void k_classify_faces(const __grid_constant__ DeviceScene S, int leve
         }
     }
     g.d[idx] = out;
+    });
 }
 
 // findOccupiedEdgeStressTiles (AV.cpp:1002-1057): the 4 a-edges of every ACTIVE cell, a = 0,1,2
 __global__ void k_mark_edge_tiles(Grid3<uint8_t> lab, Grid3<uint8_t> t0, Grid3<uint8_t> t1, Grid3<uint8_t> t2) {
-    size_t idx;
-    int x, y, z;
-    if (!cell3(lab.n, x, y, z, idx)) return;
+    forCells(lab.n, [&](int x, int y, int z, size_t idx, bool ok) {
+        if (!ok) return;
     if (lab.d[idx] != L_ACTIVE) return;
     I3 c = mk3(x, y, z);
 #pragma unroll
@@ -450,16 +562,16 @@ __global__ void k_mark_edge_tiles(Grid3<uint8_t> lab, Grid3<uint8_t> t0, Grid3<u
         markTile(t1, cellToEdge(c, 1, e));
         markTile(t2, cellToEdge(c, 2, e));
     }
+    });
 }
 
 // classifyEdgeStresses (AV.cpp:1325-1405)
-__global__ void k_classify_edges(const __grid_constant__ DeviceScene S, int level, int axis, Grid3<uint8_t> tiles) {
+__global__ void k_classify_edges(const __grid_constant__ DeviceScene S, int level, int axis, Grid3<uint8_t> tiles, unsigned long long *counter) {
     const Grid3<int8_t> g = S.edge[level][axis];
-    size_t idx;
-    int x, y, z;
-    if (!cell3(g.n, x, y, z, idx)) return;
+    forCells(g.n, [&](int x, int y, int z, size_t idx, bool ok) {
+    const bool in = ok;
     int8_t out = F_UNASSIGNED;
-    if (tileOccupied(tiles, x, y, z)) {
+    if (in && tileOccupied(tiles, x, y, z)) {
         const Grid3<uint8_t> &lab = S.label[level];
         I3 edge = mk3(x, y, z);
         int vr[3];
@@ -482,21 +594,24 @@ __global__ void k_classify_edges(const __grid_constant__ DeviceScene S, int leve
             else out = F_FLUID;
         }
     }
-    g.d[idx] = out;
+    if (in) g.d[idx] = out;
+    countWarp(in && out == F_FLUID, counter);
+    });
 }
 
 // classifyCenterStresses (AV.cpp:1407-1443)
-__global__ void k_classify_centers(const __grid_constant__ DeviceScene S, int level) {
+__global__ void k_classify_centers(const __grid_constant__ DeviceScene S, int level, unsigned long long *counter) {
     const Grid3<int8_t> g = S.center[level];
-    size_t idx;
-    int x, y, z;
-    if (!cell3(g.n, x, y, z, idx)) return;
+    forCells(g.n, [&](int x, int y, int z, size_t idx, bool ok) {
+    const bool in = ok;
     int8_t out = F_UNASSIGNED;
-    if (S.label[level].d[idx] == L_ACTIVE) {
+    if (in && S.label[level].d[idx] == L_ACTIVE) {
         if (level != 0) out = F_FLUID;
         else if (S.centerW.get(mk3(x, y, z)) > 0.f) out = F_FLUID;
     }
-    g.d[idx] = out;
+    if (in) g.d[idx] = out;
+    countWarp(in && out == F_FLUID, counter);
+    });
 }
 
 static int tileGrid(AvsContext *c, DevBuf &buf, Grid3<uint8_t> t[3], const int res[3][3]) {
@@ -525,12 +640,10 @@ int avs_stage_regular_labels(AvsContext *c) {
     Grid3<uint8_t> t[3];
     int rc = tileGrid(c, c->tiles, t, res);
     if (rc) return rc;
-    LAUNCH_3D(c, k_mark_surface_tiles, S.N, S, t[0], t[1], t[2]);
-    for (int a = 0; a < 3; ++a) LAUNCH_3D(c, k_classify_regular, S.regular[a].n, S, a, t[a]);
     unsigned long long *cnt = c->counters.as<unsigned long long>();
-    AVS_CUDA_CHECK(cudaMemsetAsync(cnt + 16, 0, sizeof(unsigned long long), c->stream));
-    for (int a = 0; a < 3; ++a)
-        LAUNCH_1D(c, k_count_equal<int8_t>, S.regular[a].count(), S.regular[a].d, S.regular[a].count(), (int8_t)F_FLUID, cnt + 16);
+    AVS_CUDA_CHECK(cudaMemsetAsync(cnt + 16, 0, 3 * sizeof(unsigned long long), c->stream));
+    LAUNCH_3D(c, k_mark_surface_tiles, S.N, S, t[0], t[1], t[2]);
+    for (int a = 0; a < 3; ++a) LAUNCH_3D(c, k_classify_regular, S.regular[a].n, S, a, t[a], cnt + 16);
     return AVS_OK;
 }
 
@@ -773,6 +886,7 @@ int avs_stage_octree_labels(AvsContext *c) {
             total += (t0[a].count() + 255) / 256 * 256;
         }
     }
+    unsigned long long *cnt = c->counters.as<unsigned long long>();
     DevBuf &edgeTiles = c->edgeTiles;
     for (int l = 0; l < L; ++l) {
         const Grid3<uint8_t> &lab = S.label[l];
@@ -799,17 +913,10 @@ int avs_stage_octree_labels(AvsContext *c) {
         int rc = tileGrid(c, edgeTiles, te, res);
         if (rc) return rc;
         LAUNCH_3D(c, k_mark_edge_tiles, S.label[l].n, S.label[l], te[0], te[1], te[2]);
-        for (int a = 0; a < 3; ++a) LAUNCH_3D(c, k_classify_edges, S.edge[l][a].n, S, l, a, te[a]);
-        LAUNCH_3D(c, k_classify_centers, S.center[l].n, S, l);
+        for (int a = 0; a < 3; ++a) LAUNCH_3D(c, k_classify_edges, S.edge[l][a].n, S, l, a, te[a], cnt + 17);
+        LAUNCH_3D(c, k_classify_centers, S.center[l].n, S, l, cnt + 18);
     }
-    // counts of stress DOFs (the reference numbers them, AV.cpp:1632-1715; only the counts are reported here)
-    unsigned long long *cnt = c->counters.as<unsigned long long>();
-    AVS_CUDA_CHECK(cudaMemsetAsync(cnt + 17, 0, 2 * sizeof(unsigned long long), c->stream));
-    for (int l = 0; l < L; ++l) {
-        for (int a = 0; a < 3; ++a)
-            LAUNCH_1D(c, k_count_equal<int8_t>, S.edge[l][a].count(), S.edge[l][a].d, S.edge[l][a].count(), (int8_t)F_FLUID, cnt + 17);
-        LAUNCH_1D(c, k_count_equal<int8_t>, S.center[l].count(), S.center[l].d, S.center[l].count(), (int8_t)F_FLUID, cnt + 18);
-    }
+    // (stress DOF counts -- the reference numbers them, AV.cpp:1632-1715 -- were accumulated by the classify kernels)
     // numbering
     BrickLayout bl;
     memset(&bl, 0, sizeof(bl));

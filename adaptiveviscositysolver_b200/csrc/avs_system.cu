@@ -545,24 +545,28 @@ __global__ void k_apply_regular(const __grid_constant__ DeviceScene S, int axis,
                                 unsigned long long *pending) {
     const Grid3<int8_t> g = S.regular[axis];
     const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
-    if (x >= g.n[0]) return;
-    const size_t idx = g.lin(x, y, z);
-    int8_t lab = g.d[idx];
-    if (lab == F_UNASSIGNED || lab == F_OUTSIDE) return;
-    I3 face = mk3(x, y, z);
-    double p[3];
-    if (lab == F_SOLID) {  // AV.cpp:2881-2890
-        S.facePos(face, axis, 0, p);
-        out[idx] = (float)S.collisionVel[axis].value(p);
-        return;
+    bool isPending = false;
+    if (x < g.n[0]) {
+        const size_t idx = g.lin(x, y, z);
+        const int8_t lab = g.d[idx];
+        if (lab == F_SOLID) {  // AV.cpp:2881-2890
+            double p[3];
+            S.facePos(mk3(x, y, z), axis, 0, p);
+            out[idx] = (float)S.collisionVel[axis].value(p);
+        } else if (lab >= 0) {
+            I3 face = mk3(x, y, z);
+            int32_t oi = S.face[0][axis].get(face);
+            if (oi >= 0) out[idx] = (float)sol[oi];  // AV.cpp:2856-2857
+            else if (oi == F_SOLID) {                // AV.cpp:2860-2867
+                double p[3];
+                S.facePos(face, axis, 0, p);
+                out[idx] = (float)S.collisionVel[axis].value(p);
+            } else if (oi == F_UNASSIGNED)
+                isPending = true;
+        }
     }
-    int32_t oi = S.face[0][axis].get(face);
-    if (oi >= 0) out[idx] = (float)sol[oi];  // AV.cpp:2856-2857
-    else if (oi == F_SOLID) {                // AV.cpp:2860-2867
-        S.facePos(face, axis, 0, p);
-        out[idx] = (float)S.collisionVel[axis].value(p);
-    } else if (oi == F_UNASSIGNED)
-        atomicAdd(pending, 1ull);
+    unsigned m = __ballot_sync(0xffffffffu, isPending);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(pending, (unsigned long long)__popc(m));
 }
 
 int avs_apply_regular(AvsContext *c, float *dOut[3], unsigned long long *hostPending) {
