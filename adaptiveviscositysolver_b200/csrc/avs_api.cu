@@ -83,6 +83,9 @@ int avs_create(const AvsDeviceConfig *cfg, AvsContext **out) {
     }
     cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, c->device);
     for (auto &e : c->ev) cudaEventCreate(&e);
+    cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&c->evCopyGate, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->evUploadDone, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->evPoll[0], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->evPoll[1], cudaEventDisableTiming);
     if (cudaHostAlloc(&c->hostScalars, 512, cudaHostAllocDefault) != cudaSuccess) { delete c; return AVS_ERR_ALLOC; }
@@ -128,6 +131,9 @@ void avs_destroy(AvsContext *c) {
     for (auto &e : c->evPoll) if (e) cudaEventDestroy(e);
     for (auto &e : c->spmvEvents) if (e) cudaEventDestroy(e);
     for (auto &e : c->auxEvents) if (e) cudaEventDestroy(e);
+    if (c->evCopyGate) cudaEventDestroy(c->evCopyGate);
+    if (c->evUploadDone) cudaEventDestroy(c->evUploadDone);
+    if (c->copyStream) cudaStreamDestroy(c->copyStream);
     if (c->hostScalars) cudaFreeHost(c->hostScalars);
     if (c->ownStream) cudaStreamDestroy(c->stream);
     delete c;
@@ -136,7 +142,8 @@ void avs_destroy(AvsContext *c) {
 }  // extern "C"
 
 // ---- stage 0: host -> device ------------------------------------------------------------------
-static int uploadField(AvsContext *c, DevBuf &buf, DField &d, const AvsField &f) {
+static int uploadField(AvsContext *c, DevBuf &buf, DField &d, const AvsField &f, cudaStream_t stream = nullptr) {
+    if (!stream) stream = c->stream;
     for (int a = 0; a < 3; ++a) { d.n[a] = f.res[a]; d.org[a] = f.org[a]; }
     d.dx = f.dx;
     d.constant = f.constant;
@@ -152,7 +159,7 @@ static int uploadField(AvsContext *c, DevBuf &buf, DField &d, const AvsField &f)
     }
     size_t bytes = (size_t)f.res[0] * f.res[1] * f.res[2] * sizeof(float);
     if (buf.reserve(bytes)) return AVS_ERR_ALLOC;
-    AVS_CUDA_CHECK(cudaMemcpyAsync(buf.p, f.data, bytes, cudaMemcpyHostToDevice, c->stream));
+    AVS_CUDA_CHECK(cudaMemcpyAsync(buf.p, f.data, bytes, cudaMemcpyHostToDevice, stream));
     d.d = buf.as<float>();
     return AVS_OK;
 }
@@ -194,15 +201,23 @@ int avs_stage_upload(AvsContext *c, const AvsFields *in, const AvsParams *p) {
     S.extrap = S.dx0 * p->extrapolation;  // AV.cpp:243
     S.enhanced = p->use_enhanced_gradients ? 1 : 0;
     int rc;
+    // Labelling (weights, octree, DOF labels) only reads the surface and the collision SDF: those go first on the
+    // compute stream.  Velocity and face weights are first read by the restriction / assembly stages, so their
+    // host->device copies run on the copy stream underneath the labelling kernels (uploadDone gates restriction).
     if ((rc = uploadField(c, c->inSurface, S.surface, in->surface))) return rc;
-    for (int a = 0; a < 3; ++a) {
-        if ((rc = uploadField(c, c->inVel[a], S.vel[a], in->vel[a]))) return rc;
-        if ((rc = uploadField(c, c->inFaceW[a], S.faceW[a], in->face_weights[a]))) return rc;
-        if ((rc = uploadField(c, c->inCollVel[a], S.collisionVel[a], in->collision_vel[a]))) return rc;
-    }
+    if ((rc = uploadField(c, c->inColl, S.collision, in->collision))) return rc;
     if ((rc = uploadField(c, c->inVisc, S.viscosity, in->viscosity))) return rc;
     if ((rc = uploadField(c, c->inDens, S.density, in->density))) return rc;
-    if ((rc = uploadField(c, c->inColl, S.collision, in->collision))) return rc;
+    for (int a = 0; a < 3; ++a)
+        if ((rc = uploadField(c, c->inCollVel[a], S.collisionVel[a], in->collision_vel[a]))) return rc;
+    // the copy stream must not overwrite buffers a previous solve on the compute stream may still be reading
+    AVS_CUDA_CHECK(cudaEventRecord(c->evCopyGate, c->stream));
+    AVS_CUDA_CHECK(cudaStreamWaitEvent(c->copyStream, c->evCopyGate, 0));
+    for (int a = 0; a < 3; ++a) {
+        if ((rc = uploadField(c, c->inVel[a], S.vel[a], in->vel[a], c->copyStream))) return rc;
+        if ((rc = uploadField(c, c->inFaceW[a], S.faceW[a], in->face_weights[a], c->copyStream))) return rc;
+    }
+    AVS_CUDA_CHECK(cudaEventRecord(c->evUploadDone, c->copyStream));
     return AVS_OK;
 }
 
@@ -246,6 +261,7 @@ static int runAssemble(AvsContext *c, const AvsFields *in, const AvsParams *p, A
     if ((rc = avs_stage_regular_labels(c))) return rc;
     cudaEventRecord(c->ev[AVS_STAGE_OCTREE_LABELS], c->stream);
     if ((rc = avs_stage_octree_labels(c))) return rc;
+    cudaStreamWaitEvent(c->stream, c->evUploadDone, 0);  // velocity + face weights have landed
     cudaEventRecord(c->ev[AVS_STAGE_RESTRICTION], c->stream);
     if ((rc = avs_stage_restriction(c))) return rc;
     cudaEventRecord(c->ev[AVS_STAGE_SYSTEM], c->stream);

@@ -26,7 +26,6 @@
 
 #define CG_THREADS 256
 #define CG_CTAS_PER_SM 8
-#define SPMV_U 4
 
 // ---- SJDS build ---------------------------------------------------------------------------------
 // meta[slice*32 + q] = (original lane << 8) | number of pairs, q = position after sorting by length
@@ -262,7 +261,7 @@ struct CgScalars {
 };
 
 // ---- SpMV: y = A x, fused partial dot x.y -------------------------------------------------------
-template <class T, class T2, bool DOT>
+template <class T, class T2, bool DOT, int SPMV_U>
 __global__ void __launch_bounds__(CG_THREADS) k_spmv_sjds(long long nrows, long long nslices, const long long *__restrict__ sliceOff,
                                                           const int32_t *__restrict__ meta, const T2 *__restrict__ val2,
                                                           const int2 *__restrict__ col2, const T *__restrict__ x, T *__restrict__ y,
@@ -435,6 +434,15 @@ __global__ void k_convert_out(long long n, const T *in, double *out) {
     if (i < n) out[i] = (double)in[i];
 }
 
+static int spmvU() {
+    static int u = -1;
+    if (u < 0) {
+        const char *e = getenv("AVS_SPMV_U");
+        u = e ? atoi(e) : 4;
+        if (u != 2 && u != 4 && u != 8) u = 4;
+    }
+    return u;
+}
 template <class T, class T2, bool DOT>
 static void launchSpmv(AvsContext *c, SellMatrix &A, const T *x, T *y, double *parts, const CgScalars *sc, int grid) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -443,8 +451,15 @@ static void launchSpmv(AvsContext *c, SellMatrix &A, const T *x, T *y, double *p
         e1 = c->spmvEvents[c->spmvEventsUsed++];
         cudaEventRecord(e0, c->stream);
     }
-    k_spmv_sjds<T, T2, DOT><<<grid, CG_THREADS, 0, c->stream>>>(A.n, A.nslices, A.sliceOff.as<long long>(), A.meta.as<int32_t>(),
-                                                                 A.val.as<T2>(), A.col.as<int2>(), x, y, parts, sc);
+#define SPMV_LAUNCH(U)                                                                                                            \
+    k_spmv_sjds<T, T2, DOT, U><<<grid, CG_THREADS, 0, c->stream>>>(A.n, A.nslices, A.sliceOff.as<long long>(), A.meta.as<int32_t>(), \
+                                                                    A.val.as<T2>(), A.col.as<int2>(), x, y, parts, sc)
+    switch (spmvU()) {
+        case 2: SPMV_LAUNCH(2); break;
+        case 8: SPMV_LAUNCH(8); break;
+        default: SPMV_LAUNCH(4); break;
+    }
+#undef SPMV_LAUNCH
     if (e1) cudaEventRecord(e1, c->stream);
     ++c->launches;
     ++c->spmvLaunches;
@@ -454,12 +469,21 @@ static void launchSpmv(AvsContext *c, SellMatrix &A, const T *x, T *y, double *p
 template <class T, class T2>
 static int spmvGrid(AvsContext *c, long long nslices) {
     int perSM = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_spmv_sjds<T, T2, true>, CG_THREADS, 0) != cudaSuccess || perSM < 1) {
+    cudaError_t e;
+    switch (spmvU()) {
+        case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_spmv_sjds<T, T2, true, 2>, CG_THREADS, 0); break;
+        case 8: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_spmv_sjds<T, T2, true, 8>, CG_THREADS, 0); break;
+        default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_spmv_sjds<T, T2, true, 4>, CG_THREADS, 0); break;
+    }
+    if (e != cudaSuccess || perSM < 1) {
         cudaGetLastError();
         perSM = 4;
     }
+    const char *env = getenv("AVS_SPMV_WAVES");   // CTAs per SM as a multiple of the resident count (default 1 = one wave)
+    int waves = env ? atoi(env) : 2;  // measured at C3: 2 waves 0.464 ms vs 1 wave 0.473 ms
+    if (waves < 1) waves = 1;
     long long want = (nslices * 32 + CG_THREADS - 1) / CG_THREADS;
-    long long cap = (long long)c->numSMs * perSM;
+    long long cap = (long long)c->numSMs * perSM * waves;
     return (int)std::max<long long>(1, std::min(want, cap));
 }
 

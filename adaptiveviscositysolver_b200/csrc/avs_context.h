@@ -64,6 +64,8 @@ struct AvsContext {
     const long long *haloIndex = nullptr;  // device: global column -> halo slot (valid where flagged)
     cudaStream_t stream = nullptr;
     bool ownStream = false;
+    cudaStream_t copyStream = nullptr;   // host->device copies that overlap the labelling stages
+    cudaEvent_t evCopyGate = nullptr, evUploadDone = nullptr;
     bool timeSpmv = false;
     int numSMs = 148;
     std::string lastError;
