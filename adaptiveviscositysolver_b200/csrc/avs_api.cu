@@ -123,7 +123,9 @@ void avs_destroy(AvsContext *c) {
     for (int a = 0; a < 3; ++a) {
         c->inVel[a].release(); c->inFaceW[a].release(); c->inCollVel[a].release(); c->edgeW[a].release(); c->regular[a].release();
     }
+    c->nodeScene.release();
     for (int l = 0; l < AVS_MAX_LEVELS; ++l) {
+        c->nodes[l].release();
         c->label[l].release(); c->center[l].release();
         for (int a = 0; a < 3; ++a) { c->face[l][a].release(); c->edge[l][a].release(); }
     }
@@ -359,7 +361,7 @@ static int runApply(AvsContext *c, AvsVelocityOut *out, AvsResult *res) {
     collectStageTimes(c, res, AVS_STAGE_APPLY, AVS_STAGE_DOWNLOAD);
     for (int a = 0; a < 3; ++a) tmp[a].release();
     res->kernel_launches = c->launches;
-    res->pending_interpolated_faces = (int64_t)pending;
+    res->interpolated_faces = (int64_t)pending;
     return AVS_OK;
 }
 

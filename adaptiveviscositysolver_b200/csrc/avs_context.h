@@ -76,6 +76,7 @@ struct AvsContext {
     DevBuf centerW, edgeW[3];
     DevBuf label[AVS_MAX_LEVELS], face[AVS_MAX_LEVELS][3], edge[AVS_MAX_LEVELS][3], center[AVS_MAX_LEVELS], regular[3];
     DevBuf tiles;           // tile-occupancy scratch
+    DevBuf nodes[AVS_MAX_LEVELS], nodeScene;  // interpolator node pyramid (stage 11)
     DevBuf bandList;        // indices of the samples whose neighbourhood changes sign (supersampled)
     DevBuf signA, signB;    // sign classes of the surface SDF neighbourhoods (weights shortcut)
     DevBuf brickCount, brickCost, brickCostPrefix, brickOffset, scanTmp, counters;

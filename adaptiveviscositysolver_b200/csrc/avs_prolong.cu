@@ -1,0 +1,373 @@
+// avs_prolong.cu -- stage 11, "Apply Octree Solution to Regular Grid" (HDK_AdaptiveViscosity.cpp:661-707):
+//   HDK_OctreeVectorFieldInterpolator's node pyramid (HDK_OctreeVectorFieldInterpolator.h:30-138,
+//   HDK_OctreeVectorFieldInterpolator.cpp:118-658) and interpSPGrid (.cpp:660-845), then
+//   applyVelocitiesToRegularGrid (HDK_AdaptiveViscosity.cpp:2815-2894).
+//
+// The reference stores node values / weights in fp32 SIM_RawFields and the octree velocities in fp32 fields
+// (setOctreeVelocity, AV.cpp:2779-2813); every store below rounds to float at the same places.  The octree
+// velocity fields are not materialised: vel(level, axis, face) = (float)solution[face index], 0 where there is
+// no DOF.  Node grids are dense per level (label u8, 3 x value f32, 3 x weight f32, flag u16); all kernels are
+// streaming passes over them.  Compiled with -fmad=false like the other parity-critical translation units.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "avs_context.h"
+
+enum : uint8_t { N_INACTIVE = 0, N_ACTIVE = 1, N_DEPENDENT = 2 };
+
+struct NodeLevel {
+    Grid3<uint8_t> label;
+    Grid3<float> val[3], w[3];
+    Grid3<uint16_t> flag;
+};
+struct NodeScene {
+    NodeLevel lv[AVS_MAX_LEVELS];
+};
+
+__device__ __forceinline__ I3 nodeToFace(I3 n, int fa, int fi) {  // UTIL.h:187
+    if (!(fi & 1)) --n[(fa + 1) % 3];
+    if (!(fi & 2)) --n[(fa + 2) % 3];
+    return n;
+}
+__device__ __forceinline__ I3 faceToNode(I3 f, int fa, int ni) {  // UTIL.h:133
+    if (ni & 1) ++f[(fa + 1) % 3];
+    if (ni & 2) ++f[(fa + 2) % 3];
+    return f;
+}
+__device__ __forceinline__ I3 cellToNode(I3 c, int ni) {  // UTIL.h:88
+    if (ni & 1) ++c[0];
+    if (ni & 2) ++c[1];
+    if (ni & 4) ++c[2];
+    return c;
+}
+__device__ __forceinline__ float octVel(const DeviceScene &S, const double *sol, int level, int axis, const I3 &f) {
+    int32_t vi = S.face[level][axis].get(f);
+    return vi >= 0 ? (float)sol[vi] : 0.f;
+}
+
+// setActiveNodes (VFI.cpp:118-188) + sampleActiveNodes (VFI.cpp:190-286)
+__global__ void k_node_sample(const __grid_constant__ DeviceScene S, NodeLevel nl, const double *sol, int level) {
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
+    if (x >= nl.label.n[0]) return;
+    const size_t idx = nl.label.lin(x, y, z);
+    const I3 node = mk3(x, y, z);
+    // cheap reject: a node with an active face is a corner of an ACTIVE cell
+    {
+        const Grid3<uint8_t> &lab = S.label[level];
+        bool any = false;
+        for (int q = 0; q < 8 && !any; ++q) {
+            int cx = x - ((q & 1) ? 0 : 1), cy = y - ((q & 2) ? 0 : 1), cz = z - ((q & 4) ? 0 : 1);
+            if (cx < 0 || cy < 0 || cz < 0 || cx >= lab.n[0] || cy >= lab.n[1] || cz >= lab.n[2]) continue;
+            any = lab.d[lab.lin(cx, cy, cz)] == L_ACTIVE;
+        }
+        if (!any) { nl.label.d[idx] = N_INACTIVE; return; }
+    }
+    int32_t vis[12];
+    bool act = false, inact = false;
+    for (int fa = 0; fa < 3; ++fa) {
+        const Grid3<int32_t> &fg = S.face[level][fa];
+        const int a1 = (fa + 1) % 3, a2 = (fa + 2) % 3;
+        for (int fi = 0; fi < 4; ++fi) {
+            I3 f = nodeToFace(node, fa, fi);
+            int32_t vi;
+            if (f[a1] < 0 || f[a2] < 0 || f[a1] >= fg.n[a1] || f[a2] >= fg.n[a2]) { vi = -100; inact = true; }
+            else {
+                vi = fg.get(f);
+                if (vi >= 0) act = true;
+                else if (vi == F_SOLID || vi == F_OUTSIDE) inact = true;
+            }
+            vis[fa * 4 + fi] = vi;
+        }
+    }
+    // (the reference stops scanning at the first disqualifying face; the outcome -- active iff some face is a
+    //  DOF and none is solid / outside / out of range -- does not depend on the scan order)
+    if (!(act && !inact)) { nl.label.d[idx] = N_INACTIVE; return; }
+    nl.label.d[idx] = N_ACTIVE;
+    const double weight = (double)(1 << (S.levels - level - 1));
+    unsigned flag = 0;
+    for (int fa = 0; fa < 3; ++fa) {
+        double av = 0, aw = 0;
+        for (int fi = 0; fi < 4; ++fi) {
+            int32_t vi = vis[fa * 4 + fi];
+            if (vi >= 0) {
+                av += weight * (double)(float)sol[vi];
+                aw += weight;
+                flag += 1u << (fa * 4 + fi);
+            }  // UNASSIGNED contributes nothing; other labels cannot occur on an active node
+        }
+        nl.val[fa].d[idx] = (float)av;
+        nl.w[fa].d[idx] = (float)aw;
+    }
+    nl.flag.d[idx] = (uint16_t)flag;
+}
+
+// bubbleActiveNodeValues (VFI.cpp:288-355): one thread per PARENT node (its co-located child is unique)
+__global__ void k_node_bubble(NodeLevel child, NodeLevel par) {
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
+    if (x >= par.label.n[0]) return;
+    const int cx = 2 * x, cy = 2 * y, cz = 2 * z;
+    if (cx >= child.label.n[0] || cy >= child.label.n[1] || cz >= child.label.n[2]) return;
+    const size_t pi = par.label.lin(x, y, z), ci = child.label.lin(cx, cy, cz);
+    if (child.label.d[ci] != N_ACTIVE || par.label.d[pi] != N_ACTIVE) return;
+    par.flag.d[pi] = (uint16_t)(child.flag.d[ci] + par.flag.d[pi]);
+    for (int a = 0; a < 3; ++a) {
+        par.w[a].d[pi] = (float)((double)child.w[a].d[ci] + (double)par.w[a].d[pi]);
+        par.val[a].d[pi] = (float)((double)child.val[a].d[ci] + (double)par.val[a].d[pi]);
+    }
+    child.label.d[ci] = N_DEPENDENT;
+}
+
+// finishIncompleteNodes (VFI.cpp:357-567)
+__global__ void k_node_finish(const __grid_constant__ DeviceScene S, NodeLevel nl, const double *sol, int level) {
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
+    if (x >= nl.label.n[0]) return;
+    const size_t idx = nl.label.lin(x, y, z);
+    if (nl.label.d[idx] != N_ACTIVE) return;
+    unsigned flag = nl.flag.d[idx];
+    if (flag == 0xFFF) return;
+    const I3 node = mk3(x, y, z);
+    const int L = S.levels;
+    const double lw = (double)(1 << (L - level - 1));
+    unsigned temp = flag;
+    for (int bit = 0; flag != 0xFFF && bit < 12; ++bit, temp >>= 1) {
+        if (temp & 1u) continue;
+        const int fa = bit / 4, fi = bit % 4;
+        const I3 f = nodeToFace(node, fa, fi);
+        bool found = false;
+        double ghost = 0;
+        if (node[fa] % 2 == 0) {
+            I3 pf = parentOf(f);
+            int32_t pvi = S.face[level + 1][fa].get(pf);
+            if (pvi >= 0) { ghost = (double)(float)sol[pvi]; found = true; }
+        }
+        if (!found) {
+            I3 cell = f;  // HDKfaceToCell(face, faceAxis, 1)
+            int sl = level;
+            while (sl < L && S.label[sl].get(cell) != L_ACTIVE) { cell = parentOf(cell); ++sl; }
+            if (sl >= L) { flag += 1u << bit; continue; }  // asserted impossible in the reference (VFI.cpp:490)
+            double fp[3];
+            S.facePos(f, fa, level, fp);
+            const double idxNode = (fp[fa] - S.origin[fa]) / S.levelDx(sl);
+            const double iw = idxNode - floor(idxNode);
+            for (int dir = 0; dir < 2; ++dir) {
+                I3 of = cellToFace(cell, fa, dir);
+                int32_t ovi = S.face[sl][fa].get(of);
+                const double liw = dir == 0 ? 1. - iw : iw;
+                if (ovi >= 0) ghost += liw * (double)(float)sol[ovi];
+                else if (ovi == F_UNASSIGNED && sl > 0)
+                    for (int ch = 0; ch < 4; ++ch) {
+                        int32_t cvi = S.face[sl - 1][fa].get(childFace(of, fa, ch));
+                        if (cvi >= 0) ghost += .25 * liw * (double)(float)sol[cvi];
+                    }
+            }
+        }
+        double v = (double)nl.val[fa].d[idx];
+        v += lw * ghost;
+        nl.val[fa].d[idx] = (float)v;
+        double w = (double)nl.w[fa].d[idx];
+        w += lw;
+        nl.w[fa].d[idx] = (float)w;
+        flag += 1u << bit;
+    }
+    nl.flag.d[idx] = (uint16_t)flag;
+}
+
+// normalizeActiveNodes (VFI.cpp:569-613)
+__global__ void k_node_normalize(NodeLevel nl) {
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
+    if (x >= nl.label.n[0]) return;
+    const size_t idx = nl.label.lin(x, y, z);
+    if (nl.label.d[idx] != N_ACTIVE) return;
+    for (int a = 0; a < 3; ++a) nl.val[a].d[idx] = (float)((double)nl.val[a].d[idx] / (double)nl.w[a].d[idx]);
+}
+
+// distributeNodeValuesDown (VFI.cpp:615-658)
+__global__ void k_node_distribute(NodeLevel child, NodeLevel par) {
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
+    if (x >= child.label.n[0]) return;
+    const size_t idx = child.label.lin(x, y, z);
+    if (child.label.d[idx] != N_DEPENDENT) return;
+    const I3 pn = mk3(x >> 1, y >> 1, z >> 1);
+    for (int a = 0; a < 3; ++a) child.val[a].d[idx] = par.val[a].get(pn);
+    child.label.d[idx] = N_ACTIVE;
+}
+
+// interpSPGrid (VFI.cpp:660-845)
+__device__ double interpSPGrid(const DeviceScene &S, const NodeScene &NS, const double *sol, const double pos[3], int axis) {
+    const int L = S.levels;
+    I3 cell;
+    for (int a = 0; a < 3; ++a) cell[a] = (int)floor((pos[a] - S.origin[a]) / S.levelDx(0));
+    const int a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
+    for (int level = 0; level < L; ++level) {
+        if (S.label[level].get(cell) == L_ACTIVE) {
+            const double h = S.levelDx(level);
+            double ifp[3];
+            I3 face;
+            for (int a = 0; a < 3; ++a) {
+                ifp[a] = (pos[a] - S.origin[a]) / h - (a == axis ? 0.0 : 0.5);
+                face[a] = (int)floor(ifp[a]);
+            }
+            const Grid3<int32_t> &fg = S.face[level][axis];
+            int32_t vis[8];
+            bool transition = false;
+            for (int q = 0; q < 8; ++q) {
+                vis[q] = fg.get(cellToNode(face, q));
+                if (vis[q] == F_UNASSIGNED) { transition = true; break; }
+            }
+            if (!transition) {
+                float iw[3];  // UT_Vector3 interpolationWeight
+                for (int a = 0; a < 3; ++a) {
+                    iw[a] = (float)(ifp[a] - (double)face[a]);
+                    iw[a] = fminf(fmaxf(iw[a], 0.f), 1.f);
+                }
+                double value = 0;
+                for (int q = 0; q < 8; ++q) {
+                    double w = 1.;
+                    w *= (q & 1) ? (double)iw[0] : (1. - (double)iw[0]);
+                    w *= (q & 2) ? (double)iw[1] : (1. - (double)iw[1]);
+                    w *= (q & 4) ? (double)iw[2] : (1. - (double)iw[2]);
+                    value += w * (double)(vis[q] >= 0 ? (float)sol[vis[q]] : 0.f);
+                }
+                return value;
+            }
+            double ciw = (pos[axis] - S.origin[axis]) / h - (double)cell[axis];
+            ciw = fmin(fmax(ciw, 0.), 1.);
+            double fiv[2] = {0., 0.};
+            for (int dir = 0; dir < 2; ++dir) {
+                I3 af = cellToFace(cell, axis, dir);
+                int fl = level;
+                if (fg.get(af) == F_UNASSIGNED && level > 0) {
+                    const double hc = S.levelDx(level - 1);
+                    const double c1 = (pos[a1] - S.origin[a1]) / hc, c2 = (pos[a2] - S.origin[a2]) / hc;
+                    for (int ch = 0; ch < 4; ++ch) {
+                        I3 cf = childFace(af, axis, ch);
+                        if ((double)cf[a1] <= c1 && (double)cf[a2] <= c2 && (double)(cf[a1] + 1) >= c1 && (double)(cf[a2] + 1) >= c2) {
+                            fl = level - 1;
+                            af = cf;
+                            break;
+                        }
+                    }
+                }
+                const double hf = S.levelDx(fl);
+                const double n1 = (pos[a1] - S.origin[a1]) / hf, n2 = (pos[a2] - S.origin[a2]) / hf;
+                const double w0 = n1 - floor(n1), w1 = n2 - floor(n2);
+                const double faceVelocity = (double)octVel(S, sol, fl, axis, af);
+                double avg = 0;
+                for (int q = 0; q < 4; ++q) {
+                    I3 node = faceToNode(af, axis, q);
+                    double w = 1.;
+                    w *= (node[a1] - af[a1] == 0) ? 1. - w0 : w0;
+                    w *= (node[a2] - af[a2] == 0) ? 1. - w1 : w1;
+                    const double nv = (double)NS.lv[fl].val[axis].get(node);
+                    avg += nv;
+                    fiv[dir] += nv * w;
+                }
+                fiv[dir] += 2. * (faceVelocity - .25 * avg) * fmin(w0, fmin(w1, fmin(1. - w0, 1. - w1)));
+            }
+            return (1. - ciw) * fiv[0] + ciw * fiv[1];
+        }
+        cell = parentOf(cell);
+    }
+    return 0.;
+}
+
+// applyVelocitiesToRegularGrid (AV.cpp:2815-2894)
+__global__ void k_apply_regular(const __grid_constant__ DeviceScene S, const NodeScene *NS, int axis, const double *sol, float *out,
+                                unsigned long long *interpolated) {
+    const Grid3<int8_t> g = S.regular[axis];
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
+    bool interp = false;
+    if (x < g.n[0]) {
+        const size_t idx = g.lin(x, y, z);
+        const int8_t lab = g.d[idx];
+        const I3 face = mk3(x, y, z);
+        double p[3];
+        if (lab == F_SOLID) {  // AV.cpp:2881-2890
+            S.facePos(face, axis, 0, p);
+            out[idx] = (float)S.collisionVel[axis].value(p);
+        } else if (lab >= 0) {
+            int32_t oi = S.face[0][axis].get(face);
+            if (oi >= 0) out[idx] = (float)sol[oi];  // AV.cpp:2856-2857
+            else if (oi == F_SOLID) {                // AV.cpp:2860-2867
+                S.facePos(face, axis, 0, p);
+                out[idx] = (float)S.collisionVel[axis].value(p);
+            } else if (oi == F_UNASSIGNED) {         // AV.cpp:2868-2876
+                S.facePos(face, axis, 0, p);
+                out[idx] = (float)interpSPGrid(S, *NS, sol, p, axis);
+                interp = true;
+            }
+        }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, interp);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(interpolated, (unsigned long long)__popc(m));
+}
+
+static dim3 grid3(const int n[3]) { return dim3((unsigned)((n[0] + 127) / 128), (unsigned)n[1], (unsigned)n[2]); }
+
+int avs_apply_regular(AvsContext *c, float *dOut[3], unsigned long long *hostInterpolated) {
+    const DeviceScene &S = c->S;
+    const int L = S.levels;
+    const double *sol = c->nranks > 1 ? c->fullSolution.as<double>() : c->solution.as<double>();
+    NodeScene NS;
+    memset(&NS, 0, sizeof(NS));
+    const bool needNodes = L > 1;  // a uniform grid has no UNASSIGNED face: nothing to interpolate
+    if (needNodes) {
+        for (int l = 0; l < L; ++l) {
+            NodeLevel &nl = NS.lv[l];
+            int n[3];
+            for (int a = 0; a < 3; ++a) n[a] = S.label[l].n[a] + 1;
+            const size_t cnt = (size_t)n[0] * n[1] * n[2];
+            // one allocation per level: label | flag | 3 val | 3 w
+            const size_t bytes = cnt * (1 + 2 + 24) + 1024;
+            if (c->nodes[l].reserve(bytes)) return AVS_ERR_ALLOC;
+            char *base = c->nodes[l].as<char>();
+            size_t off = 0;
+            auto take = [&](size_t b) { char *p = base + off; off += (b + 255) / 256 * 256; return p; };
+            float *vals[6];
+            for (int k = 0; k < 6; ++k) vals[k] = (float *)take(cnt * 4);
+            uint16_t *fl = (uint16_t *)take(cnt * 2);
+            uint8_t *lb = (uint8_t *)take(cnt);
+            if (off > c->nodes[l].cap) return AVS_ERR_ALLOC;
+            for (int a = 0; a < 3; ++a) {
+                nl.val[a].d = vals[a]; nl.w[a].d = vals[3 + a];
+                for (int k = 0; k < 3; ++k) { nl.val[a].n[k] = n[k]; nl.w[a].n[k] = n[k]; }
+            }
+            nl.flag.d = fl;
+            nl.label.d = lb;
+            for (int k = 0; k < 3; ++k) { nl.flag.n[k] = n[k]; nl.label.n[k] = n[k]; }
+        }
+        for (int l = 0; l < L; ++l) {
+            k_node_sample<<<grid3(NS.lv[l].label.n), 128, 0, c->stream>>>(S, NS.lv[l], sol, l);
+            ++c->launches;
+        }
+        for (int l = 0; l < L - 1; ++l) {
+            k_node_bubble<<<grid3(NS.lv[l + 1].label.n), 128, 0, c->stream>>>(NS.lv[l], NS.lv[l + 1]);
+            ++c->launches;
+        }
+        for (int l = 0; l < L - 1; ++l) {
+            k_node_finish<<<grid3(NS.lv[l].label.n), 128, 0, c->stream>>>(S, NS.lv[l], sol, l);
+            ++c->launches;
+        }
+        for (int l = 0; l < L; ++l) {
+            k_node_normalize<<<grid3(NS.lv[l].label.n), 128, 0, c->stream>>>(NS.lv[l]);
+            ++c->launches;
+        }
+        for (int l = L - 2; l >= 0; --l) {
+            k_node_distribute<<<grid3(NS.lv[l].label.n), 128, 0, c->stream>>>(NS.lv[l], NS.lv[l + 1]);
+            ++c->launches;
+        }
+    }
+    if (c->nodeScene.reserve(sizeof(NodeScene))) return AVS_ERR_ALLOC;
+    AVS_CUDA_CHECK(cudaMemcpyAsync(c->nodeScene.p, &NS, sizeof(NS), cudaMemcpyHostToDevice, c->stream));
+    unsigned long long *cnt = c->counters.as<unsigned long long>() + 26;
+    AVS_CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
+    for (int a = 0; a < 3; ++a) {
+        k_apply_regular<<<grid3(S.regular[a].n), 128, 0, c->stream>>>(S, c->nodeScene.as<NodeScene>(), a, sol, dOut[a], cnt);
+        ++c->launches;
+    }
+    AVS_CUDA_CHECK(cudaMemcpyAsync(hostInterpolated, cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));  // also keeps the stack copy of NS alive until the H2D copy is done
+    AVS_CUDA_CHECK(cudaGetLastError());
+    return AVS_OK;
+}

@@ -536,49 +536,3 @@ int avs_build_csr(AvsContext *c) {
     return AVS_OK;
 }
 
-// ------------------------------------------------------------------------------------------------
-// Stage 11 (level-0 part of applyVelocitiesToRegularGrid, AV.cpp:2815-2894): regular faces with a
-// co-located octree DOF take the solution, SOLIDBOUNDARY faces take the solid velocity.  Regular
-// faces that sit inside a coarse cell (octree label UNASSIGNED) need the octree interpolator
-// (HDK_OctreeVectorFieldInterpolator) and are counted, not written.
-__global__ void k_apply_regular(const __grid_constant__ DeviceScene S, int axis, const double *sol, float *out,
-                                unsigned long long *pending) {
-    const Grid3<int8_t> g = S.regular[axis];
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
-    bool isPending = false;
-    if (x < g.n[0]) {
-        const size_t idx = g.lin(x, y, z);
-        const int8_t lab = g.d[idx];
-        if (lab == F_SOLID) {  // AV.cpp:2881-2890
-            double p[3];
-            S.facePos(mk3(x, y, z), axis, 0, p);
-            out[idx] = (float)S.collisionVel[axis].value(p);
-        } else if (lab >= 0) {
-            I3 face = mk3(x, y, z);
-            int32_t oi = S.face[0][axis].get(face);
-            if (oi >= 0) out[idx] = (float)sol[oi];  // AV.cpp:2856-2857
-            else if (oi == F_SOLID) {                // AV.cpp:2860-2867
-                double p[3];
-                S.facePos(face, axis, 0, p);
-                out[idx] = (float)S.collisionVel[axis].value(p);
-            } else if (oi == F_UNASSIGNED)
-                isPending = true;
-        }
-    }
-    unsigned m = __ballot_sync(0xffffffffu, isPending);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(pending, (unsigned long long)__popc(m));
-}
-
-int avs_apply_regular(AvsContext *c, float *dOut[3], unsigned long long *hostPending) {
-    unsigned long long *cnt = c->counters.as<unsigned long long>() + 26;
-    AVS_CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
-    for (int a = 0; a < 3; ++a) {
-        const int *n3 = c->S.regular[a].n;
-        dim3 grid((unsigned)((n3[0] + 127) / 128), (unsigned)n3[1], (unsigned)n3[2]);
-        k_apply_regular<<<grid, 128, 0, c->stream>>>(c->S, a, c->nranks > 1 ? c->fullSolution.as<double>() : c->solution.as<double>(), dOut[a], cnt);
-        ++c->launches;
-    }
-    AVS_CUDA_CHECK(cudaMemcpyAsync(hostPending, cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    return AVS_OK;
-}

@@ -71,7 +71,7 @@ class SolveInfo:
     kernel_launches: int
     stage_ms: Dict[str, float]
     spmv_ms: float
-    pending_interpolated_faces: int
+    interpolated_faces: int
     cg_update_xr_ms: float = 0.0
     cg_update_p_ms: float = 0.0
     dist_mode: int = 0
@@ -82,7 +82,7 @@ class SolveInfo:
         return SolveInfo(r.status, r.iterations, r.error, r.levels, r.octree_dofs, r.regular_dofs, r.edge_dofs,
                          r.center_dofs, r.nnz, r.local_rows, r.spmv_launches, r.kernel_launches,
                          {STAGE_NAMES[i]: float(r.stage_ms[i]) for i in range(11)}, float(r.spmv_ms),
-                         r.pending_interpolated_faces, float(r.cg_update_xr_ms), float(r.cg_update_p_ms), r.dist_mode,
+                         r.interpolated_faces, float(r.cg_update_xr_ms), float(r.cg_update_p_ms), r.dist_mode,
                          r.halo_columns)
 
 

@@ -141,8 +141,8 @@ typedef struct AvsResult {
     int32_t dist_mode;        /* 0 single GPU, 1 NCCL hot loop, 2 peer-memory (NVLink loads/stores in our kernels) */
     int32_t reserved0;
     int64_t halo_columns;     /* off-rank columns this rank's rows reference */
-    int64_t pending_interpolated_faces; /* regular faces inside coarse cells that still need the octree interpolator
-                                          (HDK_OctreeVectorFieldInterpolator); 0 when depth == 1 */
+    int64_t interpolated_faces; /* regular faces inside coarse cells, filled by the octree interpolator (interpSPGrid,
+                                  HDK_OctreeVectorFieldInterpolator.cpp:660-845); 0 when depth == 1 */
 } AvsResult;
 
 typedef struct AvsDeviceConfig {
@@ -177,7 +177,7 @@ int avs_assemble(AvsContext *ctx, const AvsFields *in, const AvsParams *p, AvsRe
 /* CG on the resident system (stage 10), initial guess = restricted u^n (AV.cpp:627). May be called
  * repeatedly; every call restarts from the initial guess. */
 int avs_solve_resident(AvsContext *ctx, const AvsParams *p, AvsResult *res);
-/* Stage 11 on the resident solution. */
+/* Stage 11 on the resident solution: node pyramid + interpSPGrid + write-back to the regular grid. */
 int avs_apply(AvsContext *ctx, AvsVelocityOut *out, AvsResult *res);
 
 /* Read-back of the resident state, all to HOST buffers (NULL pointers are skipped).

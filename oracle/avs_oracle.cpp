@@ -173,6 +173,19 @@ static inline I3 childEdgeInFace(I3 f, int faceAxis, int edgeAxis, int child) { 
     return r;
 }
 
+static inline I3 nodeToFace(I3 n, int faceAxis, int faceIndex) {                                          // UTIL.h:187
+    for (int o = 0; o < 2; ++o) if (!(faceIndex & (1 << o))) --n[(faceAxis + 1 + o) % 3];
+    return n;
+}
+static inline I3 faceToNode(I3 f, int faceAxis, int nodeIndex) {                                          // UTIL.h:133
+    for (int o = 0; o < 2; ++o) if (nodeIndex & (1 << o)) ++f[(faceAxis + 1 + o) % 3];
+    return f;
+}
+static inline I3 cellToNode(I3 c, int nodeIndex) {                                                        // UTIL.h:88
+    for (int a = 0; a < 3; ++a) if (nodeIndex & (1 << a)) ++c[a];
+    return c;
+}
+
 struct Params {
     double dt = 1.0 / 24;
     double tolerance = 1e-3;       // AV.cpp:62-63
@@ -229,6 +242,13 @@ struct Oracle {
     std::vector<int32_t> colIdx;
     std::vector<double> val;
     std::vector<double> sol;
+    // stage 11 (AV.cpp:661-707, HDK_OctreeVectorFieldInterpolator.*)
+    std::vector<std::vector<Arr3<float>>> octVel;    // [level][axis] setOctreeVelocity (fp32 fields)
+    std::vector<Arr3<uint8_t>> nodeLabel;            // INACTIVENODE / ACTIVENODE / DEPENDENTNODE
+    std::vector<std::vector<Arr3<float>>> nodeVal, nodeW;
+    std::vector<Arr3<exint>> nodeFlag;
+    Arr3<float> outVel[3];                           // regular-grid velocity after the solve
+    exint interpolatedFaces = 0;
     int iterations = 0;
     double error = 0;
     int stage = 0;
@@ -1009,6 +1029,297 @@ struct Oracle {
             }
         }
     }
+
+    // ---------------------------------------------------------------- stage 11
+    // HDK_OctreeVectorFieldInterpolator (VFI.h:30-138, VFI.cpp) + applyVelocitiesToRegularGrid (AV.cpp:2815-2894).
+    // All node fields are SIM_RawField, i.e. float32 storage: every set rounds to float like the reference.
+    enum { INACTIVENODE = 0, ACTIVENODE = 1, DEPENDENTNODE = 2 };
+
+    float octVelAt(int level, int axis, const I3 &f) const { return octVel[level][axis].get(f); }
+
+    void buildInterpolator() {
+        const int L = levels;
+        // setOctreeVelocity (AV.cpp:2779-2813): fp32 fields, 0 where there is no DOF
+        octVel.assign(L, std::vector<Arr3<float>>(3));
+        for (int l = 0; l < L; ++l)
+            for (int a = 0; a < 3; ++a) {
+                const Arr3<exint> &g = faceIdx[l][a];
+                octVel[l][a].init(g.n, 0.f);
+                for (size_t i = 0; i < g.d.size(); ++i)
+                    if (g.d[i] >= 0) octVel[l][a].d[i] = (float)sol[(size_t)g.d[i]];
+            }
+        nodeLabel.assign(L, Arr3<uint8_t>());
+        nodeFlag.assign(L, Arr3<exint>());
+        nodeVal.assign(L, std::vector<Arr3<float>>(3));
+        nodeW.assign(L, std::vector<Arr3<float>>(3));
+        for (int l = 0; l < L; ++l) {
+            I3 cr = cellRes(l);
+            I3 nr = mk(cr[0] + 1, cr[1] + 1, cr[2] + 1);
+            nodeLabel[l].init(nr, INACTIVENODE);
+            nodeFlag[l].init(nr, 0);
+            for (int a = 0; a < 3; ++a) { nodeVal[l][a].init(nr, 0.f); nodeW[l][a].init(nr, 0.f); }
+        }
+        // setActiveNodes (VFI.cpp:118-188) + sampleActiveNodes (VFI.cpp:190-286)
+        for (int l = 0; l < L; ++l) {
+            const I3 nr = nodeLabel[l].n;
+            const double weight = (double)(1 << (L - l - 1));
+#pragma omp parallel for schedule(static)
+            for (int z = 0; z < nr[2]; ++z)
+                for (int y = 0; y < nr[1]; ++y)
+                    for (int x = 0; x < nr[0]; ++x) {
+                        I3 node = mk(x, y, z);
+                        bool act = false, inact = false;
+                        for (int fa = 0; !inact && fa < 3; ++fa) {
+                            const Arr3<exint> &fg = faceIdx[l][fa];
+                            const int a1 = (fa + 1) % 3, a2 = (fa + 2) % 3;
+                            for (int fi = 0; fi < 4; ++fi) {
+                                I3 f = nodeToFace(node, fa, fi);
+                                if (f[a1] < 0 || f[a2] < 0 || f[a1] >= fg.n[a1] || f[a2] >= fg.n[a2]) { inact = true; continue; }
+                                exint vi = fg.get(f);
+                                if (vi >= 0) act = true;
+                                else if (vi == SOLIDBOUNDARY || vi == OUTSIDE) { inact = true; break; }
+                            }
+                        }
+                        if (!(act && !inact)) continue;
+                        nodeLabel[l].at(node) = ACTIVENODE;
+                        exint flag = 0;
+                        for (int fa = 0; fa < 3; ++fa) {
+                            const Arr3<exint> &fg = faceIdx[l][fa];
+                            const int a1 = (fa + 1) % 3, a2 = (fa + 2) % 3;
+                            double av = 0, aw = 0;
+                            for (int fi = 0; fi < 4; ++fi) {
+                                I3 f = nodeToFace(node, fa, fi);
+                                if (f[a1] < 0 || f[a2] < 0 || f[a1] >= fg.n[a1] || f[a2] >= fg.n[a2]) {
+                                    flag += (exint)(1 << (fa * 4 + fi));
+                                    aw += weight;
+                                    continue;
+                                }
+                                exint vi = fg.get(f);
+                                if (vi >= 0) { av += weight * (double)octVelAt(l, fa, f); aw += weight; flag += (exint)(1 << (fa * 4 + fi)); }
+                                else if (vi != UNASSIGNED) { aw += weight; flag += (exint)(1 << (fa * 4 + fi)); }
+                            }
+                            nodeVal[l][fa].at(node) = (float)av;
+                            nodeW[l][fa].at(node) = (float)aw;
+                        }
+                        nodeFlag[l].at(node) = flag;
+                    }
+        }
+        // bubbleActiveNodeValues (VFI.cpp:288-355), level by level
+        for (int l = 0; l < L - 1; ++l) {
+            const I3 nr = nodeLabel[l].n;
+            for (int z = 0; z < nr[2]; z += 2)
+                for (int y = 0; y < nr[1]; y += 2)
+                    for (int x = 0; x < nr[0]; x += 2) {
+                        I3 node = mk(x, y, z);
+                        if (nodeLabel[l].at(node) != ACTIVENODE) continue;
+                        I3 pn = parentOf(node);
+                        if (nodeLabel[l + 1].get(pn) != ACTIVENODE) continue;
+                        nodeFlag[l + 1].at(pn) = nodeFlag[l].at(node) + nodeFlag[l + 1].at(pn);
+                        for (int a = 0; a < 3; ++a) {
+                            double w = nodeW[l][a].at(node), v = nodeVal[l][a].at(node);
+                            double pw = nodeW[l + 1][a].at(pn), pv = nodeVal[l + 1][a].at(pn);
+                            nodeW[l + 1][a].at(pn) = (float)(w + pw);
+                            nodeVal[l + 1][a].at(pn) = (float)(v + pv);
+                        }
+                        nodeLabel[l].at(node) = DEPENDENTNODE;
+                    }
+        }
+        // finishIncompleteNodes (VFI.cpp:357-567)
+        for (int l = 0; l < L - 1; ++l) {
+            const I3 nr = nodeLabel[l].n;
+            const double lw = (double)(1 << (L - l - 1));
+#pragma omp parallel for schedule(static)
+            for (int z = 0; z < nr[2]; ++z)
+                for (int y = 0; y < nr[1]; ++y)
+                    for (int x = 0; x < nr[0]; ++x) {
+                        I3 node = mk(x, y, z);
+                        if (nodeLabel[l].at(node) != ACTIVENODE) continue;
+                        exint flag = nodeFlag[l].at(node);
+                        if (flag == 0xFFF) continue;
+                        exint temp = flag;
+                        for (int bit = 0; flag != 0xFFF && bit < 12; ++bit, temp >>= 1) {
+                            if (temp & 1) continue;
+                            const int fa = bit / 4, fi = bit % 4;
+                            bool found = false;
+                            if (node[fa] % 2 == 0) {
+                                I3 f = nodeToFace(node, fa, fi);
+                                I3 pf = parentOf(f);
+                                if (faceIdx[l + 1][fa].get(pf) >= 0) {
+                                    double ghost = (double)octVelAt(l + 1, fa, pf);
+                                    double v = (double)nodeVal[l][fa].at(node);
+                                    v += lw * ghost;
+                                    nodeVal[l][fa].at(node) = (float)v;
+                                    double w = (double)nodeW[l][fa].at(node);
+                                    w += lw;
+                                    nodeW[l][fa].at(node) = (float)w;
+                                    flag += (exint)(1 << bit);
+                                    found = true;
+                                }
+                            }
+                            if (!found) {
+                                I3 f = nodeToFace(node, fa, fi);
+                                I3 cell = faceToCell(f, fa, 1);
+                                int sl = l;
+                                while (sl < L && labels[sl].get(cell) != ACTIVE) { cell = parentOf(cell); ++sl; }
+                                if (sl >= L) { flag += (exint)(1 << bit); continue; }  // asserted impossible (VFI.cpp:490)
+                                double fp[3];
+                                facePos(f, fa, l, fp);
+                                const double idxNode = (fp[fa] - S.origin[fa]) / levelDx(sl);
+                                const double iw = idxNode - std::floor(idxNode);
+                                double ghost = 0;
+                                for (int dir = 0; dir < 2; ++dir) {
+                                    I3 of = cellToFace(cell, fa, dir);
+                                    exint ovi = faceIdx[sl][fa].get(of);
+                                    const double liw = dir == 0 ? 1. - iw : iw;
+                                    if (ovi >= 0) ghost += liw * (double)octVelAt(sl, fa, of);
+                                    else if (ovi == UNASSIGNED && sl > 0)
+                                        for (int ch = 0; ch < 4; ++ch) {
+                                            I3 cf = childFace(of, fa, ch);
+                                            if (faceIdx[sl - 1][fa].get(cf) >= 0) ghost += .25 * liw * (double)octVelAt(sl - 1, fa, cf);
+                                        }
+                                }
+                                double v = (double)nodeVal[l][fa].at(node);
+                                v += lw * ghost;
+                                nodeVal[l][fa].at(node) = (float)v;
+                                double w = (double)nodeW[l][fa].at(node);
+                                w += lw;
+                                nodeW[l][fa].at(node) = (float)w;
+                                flag += (exint)(1 << bit);
+                            }
+                        }
+                        nodeFlag[l].at(node) = flag;
+                    }
+        }
+        // normalizeActiveNodes (VFI.cpp:569-613)
+        for (int l = 0; l < L; ++l)
+            for (size_t i = 0; i < nodeLabel[l].d.size(); ++i)
+                if (nodeLabel[l].d[i] == ACTIVENODE)
+                    for (int a = 0; a < 3; ++a) nodeVal[l][a].d[i] = (float)((double)nodeVal[l][a].d[i] / (double)nodeW[l][a].d[i]);
+        // distributeNodeValuesDown (VFI.cpp:615-658), top down
+        for (int l = L - 2; l >= 0; --l) {
+            const I3 nr = nodeLabel[l].n;
+            for (int z = 0; z < nr[2]; ++z)
+                for (int y = 0; y < nr[1]; ++y)
+                    for (int x = 0; x < nr[0]; ++x) {
+                        I3 node = mk(x, y, z);
+                        if (nodeLabel[l].at(node) != DEPENDENTNODE) continue;
+                        I3 pn = parentOf(node);
+                        for (int a = 0; a < 3; ++a) nodeVal[l][a].at(node) = nodeVal[l + 1][a].get(pn);
+                        nodeLabel[l].at(node) = ACTIVENODE;
+                    }
+        }
+    }
+
+    // interpSPGrid (VFI.cpp:660-845)
+    double interpSPGrid(const double pos[3], int axis) const {
+        const int L = levels;
+        I3 cell;
+        for (int a = 0; a < 3; ++a) cell[a] = (int)std::floor((pos[a] - S.origin[a]) / levelDx(0));
+        const int a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
+        for (int level = 0; level < L; ++level) {
+            if (labels[level].get(cell) == ACTIVE) {
+                const double h = levelDx(level);
+                double ifp[3];
+                I3 face;
+                for (int a = 0; a < 3; ++a) {
+                    ifp[a] = (pos[a] - S.origin[a]) / h - (a == axis ? 0.0 : 0.5);
+                    face[a] = (int)std::floor(ifp[a]);
+                }
+                const Arr3<exint> &fg = faceIdx[level][axis];
+                bool transition = false;
+                for (int q = 0; q < 8; ++q)
+                    if (fg.get(cellToNode(face, q)) == UNASSIGNED) { transition = true; break; }
+                if (!transition) {
+                    float iw[3];  // UT_Vector3 interpolationWeight (float32)
+                    for (int a = 0; a < 3; ++a) {
+                        iw[a] = (float)(ifp[a] - (double)face[a]);
+                        iw[a] = std::min(std::max(iw[a], 0.f), 1.f);
+                    }
+                    double value = 0;
+                    for (int q = 0; q < 8; ++q) {
+                        I3 nf = cellToNode(face, q);
+                        double w = 1.;
+                        for (int a = 0; a < 3; ++a) w *= (nf[a] - face[a] == 0) ? (1. - (double)iw[a]) : (double)iw[a];
+                        value += w * (double)octVelAt(level, axis, nf);
+                    }
+                    return value;
+                }
+                double ciw = (pos[axis] - S.origin[axis]) / h - (double)cell[axis];
+                ciw = std::min(std::max(ciw, 0.), 1.);
+                double fiv[2] = {0., 0.};
+                for (int dir = 0; dir < 2; ++dir) {
+                    I3 af = cellToFace(cell, axis, dir);
+                    int fl = level;
+                    if (fg.get(af) == UNASSIGNED && level > 0) {
+                        const double hc = levelDx(level - 1);
+                        const double c1 = (pos[a1] - S.origin[a1]) / hc, c2 = (pos[a2] - S.origin[a2]) / hc;
+                        for (int ch = 0; ch < 4; ++ch) {
+                            I3 cf = childFace(af, axis, ch);
+                            if ((double)cf[a1] <= c1 && (double)cf[a2] <= c2 && (double)(cf[a1] + 1) >= c1 && (double)(cf[a2] + 1) >= c2) {
+                                fl = level - 1;
+                                af = cf;
+                                break;
+                            }
+                        }
+                    }
+                    const double hf = levelDx(fl);
+                    const double n1 = (pos[a1] - S.origin[a1]) / hf, n2 = (pos[a2] - S.origin[a2]) / hf;
+                    const double w0 = n1 - std::floor(n1), w1 = n2 - std::floor(n2);
+                    const double faceVelocity = (double)octVelAt(fl, axis, af);
+                    double avg = 0;
+                    for (int q = 0; q < 4; ++q) {
+                        I3 node = faceToNode(af, axis, q);
+                        double w = 1.;
+                        w *= (node[a1] - af[a1] == 0) ? 1. - w0 : w0;
+                        w *= (node[a2] - af[a2] == 0) ? 1. - w1 : w1;
+                        const double nv = (double)nodeVal[fl][axis].get(node);
+                        avg += nv;
+                        fiv[dir] += nv * w;
+                    }
+                    fiv[dir] += 2. * (faceVelocity - .25 * avg) * std::min(w0, std::min(w1, std::min(1. - w0, 1. - w1)));
+                }
+                return (1. - ciw) * fiv[0] + ciw * fiv[1];
+            }
+            cell = parentOf(cell);
+        }
+        return 0.;  // asserted unreachable (VFI.cpp:843)
+    }
+
+    // applyVelocitiesToRegularGrid (AV.cpp:2815-2894)
+    void applyToRegularGrid() {
+        exint count = 0;
+        for (int axis = 0; axis < 3; ++axis) {
+            const Arr3<exint> &rg = regIdx[axis];
+            outVel[axis].init(rg.n, 0.f);
+            for (int z = 0; z < rg.n[2]; ++z)
+                for (int y = 0; y < rg.n[1]; ++y)
+                    for (int x = 0; x < rg.n[0]; ++x) outVel[axis].d[outVel[axis].lin(x, y, z)] = S.vel[axis].raw(x, y, z);
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : count)
+            for (int z = 0; z < rg.n[2]; ++z)
+                for (int y = 0; y < rg.n[1]; ++y)
+                    for (int x = 0; x < rg.n[0]; ++x) {
+                        I3 face = mk(x, y, z);
+                        const exint lab = rg.at(face);
+                        double p[3];
+                        if (lab >= 0) {
+                            const exint oi = faceIdx[0][axis].get(face);
+                            if (oi >= 0) outVel[axis].at(face) = (float)sol[(size_t)oi];
+                            else if (oi == SOLIDBOUNDARY) {
+                                facePos(face, axis, 0, p);
+                                outVel[axis].at(face) = (float)S.collisionVel[axis].value(p);
+                            } else if (oi == UNASSIGNED) {
+                                facePos(face, axis, 0, p);
+                                outVel[axis].at(face) = (float)interpSPGrid(p, axis);
+                                ++count;
+                            }
+                        } else if (lab == SOLIDBOUNDARY) {
+                            facePos(face, axis, 0, p);
+                            outVel[axis].at(face) = (float)S.collisionVel[axis].value(p);
+                        }
+                    }
+        }
+        interpolatedFaces = count;
+    }
 };
 
 // ---------------------------------------------------------------- stage 10
@@ -1199,6 +1510,10 @@ int orc_run(void *h, int stopAfterStage) {
                         o->P.tolerance, o->P.maxIterations, &o->iterations, &o->error);
     }
     o->stage = 10;
+    if (stop <= 10) return 0;
+    o->buildInterpolator();
+    o->applyToRegularGrid();
+    o->stage = 11;
     return 0;
 }
 
@@ -1254,6 +1569,28 @@ void orc_get_vector(void *h, int what, double *out) {
     const std::vector<double> &v = what == 0 ? o->x0 : what == 1 ? o->rhs : o->sol;
     std::memcpy(out, v.data(), v.size() * sizeof(double));
 }
+// regular-grid velocity after stage 11 (float32, shape of the input vel component)
+int64_t orc_get_out_velocity(void *h, int axis, float *out, int *res) {
+    Oracle *o = (Oracle *)h;
+    const Arr3<float> &a = o->outVel[axis];
+    if (res) for (int i = 0; i < 3; ++i) res[i] = a.n[i];
+    if (out) std::memcpy(out, a.d.data(), a.d.size() * sizeof(float));
+    return (int64_t)a.d.size();
+}
+// node data of the interpolator: kind 0 labels (as float), 1..3 node values of axis kind-1
+int64_t orc_get_node_grid(void *h, int kind, int level, float *out, int *res) {
+    Oracle *o = (Oracle *)h;
+    const I3 n = o->nodeLabel[level].n;
+    if (res) for (int i = 0; i < 3; ++i) res[i] = n[i];
+    size_t cnt = o->nodeLabel[level].d.size();
+    if (out) {
+        if (kind == 0) for (size_t i = 0; i < cnt; ++i) out[i] = (float)o->nodeLabel[level].d[i];
+        else std::memcpy(out, o->nodeVal[level][kind - 1].d.data(), cnt * sizeof(float));
+    }
+    return (int64_t)cnt;
+}
+int64_t orc_interpolated_faces(void *h) { return ((Oracle *)h)->interpolatedFaces; }
+
 void orc_get_csr(void *h, int64_t *rowPtr, int32_t *col, double *val) {
     Oracle *o = (Oracle *)h;
     std::memcpy(rowPtr, o->rowPtr.data(), o->rowPtr.size() * sizeof(int64_t));

@@ -83,6 +83,12 @@ def lib():
         L.orc_get_face_keys.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_get_vector.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.orc_get_csr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_get_out_velocity.restype = C.c_int64
+        L.orc_get_out_velocity.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+        L.orc_get_node_grid.restype = C.c_int64
+        L.orc_get_node_grid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+        L.orc_interpolated_faces.restype = C.c_int64
+        L.orc_interpolated_faces.argtypes = [C.c_void_p]
         L.orc_stencil.argtypes = [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p, C.POINTER(C.c_int),
                                                                 C.c_void_p, C.POINTER(C.c_double)]
         L.orc_spmv_f64.argtypes = [C.c_int64] + [C.c_void_p] * 5
@@ -160,7 +166,7 @@ class OracleRun:
         del keep  # the oracle copies its inputs
         self._L.orc_set_weight_shortcut(self._h, int(weight_shortcut))
         self._L.orc_run(self._h, stop_after_stage)
-        self.stage = stop_after_stage if stop_after_stage > 0 else 10
+        self.stage = stop_after_stage if stop_after_stage > 0 else 11
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -268,6 +274,25 @@ class OracleRun:
 
     def solution(self):
         return self._vec(2)
+
+    def out_velocity(self, axis):
+        """Regular-grid velocity component after the solve (what solveGasSubclass leaves in ``vel``)."""
+        r = (C.c_int * 3)()
+        n = self._L.orc_get_out_velocity(self._h, axis, None, r)
+        out = np.empty(n, np.float32)
+        self._L.orc_get_out_velocity(self._h, axis, out.ctypes.data, r)
+        return out.reshape(r[2], r[1], r[0])
+
+    def node_grid(self, kind, level):
+        r = (C.c_int * 3)()
+        n = self._L.orc_get_node_grid(self._h, kind, level, None, r)
+        out = np.empty(n, np.float32)
+        self._L.orc_get_node_grid(self._h, kind, level, out.ctypes.data, r)
+        return out.reshape(r[2], r[1], r[0])
+
+    @property
+    def interpolated_faces(self):
+        return self._L.orc_interpolated_faces(self._h)
 
     def csr(self):
         n, nnz = self.n_face, self.nnz

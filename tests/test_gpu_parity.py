@@ -117,22 +117,25 @@ def test_solve_parity(solver, name):
     assert abs(info.iterations - ref.iterations) <= max(2, ref.iterations // 50)
     assert np.abs(x - xo).max() < 1e-6
     assert np.abs(x - xo).max() <= 1e-7 * max(1.0, np.abs(xo).max())
-    # output scatter: every level-0 regular face that has a co-located octree DOF carries the solution
-    keys = solver.keys()
+    # Stage 11: the whole regular-grid velocity (copy of co-located DOFs, solid velocities, interpSPGrid inside
+    # coarse cells) against the oracle's write-back.  Stored as fp32 like the reference (UTIL.h:229-232); the two
+    # solutions differ by ~1e-10, so a value can round to the neighbouring float: tolerance = north star's 1e-6.
+    assert info.interpolated_faces == ref.interpolated_faces
+    n_bit_equal = n_total = 0
     for a in range(3):
-        m = (keys[:, 0] == 0) & (keys[:, 1] == a)
-        k = keys[m]
+        oo = ref.out_velocity(a)
+        assert oo.shape == out[a].shape
+        assert np.abs(out[a].astype(np.float64) - oo.astype(np.float64)).max() < 1e-6
         reg = ref.regular_index(a)
-        inside = (k[:, 2] < reg.shape[2]) & (k[:, 3] < reg.shape[1]) & (k[:, 4] < reg.shape[0])
-        k, xs = k[inside], x[m][inside]
-        isreg = reg[k[:, 4], k[:, 3], k[:, 2]] >= 0
-        got = out[a][k[isreg, 4], k[isreg, 3], k[isreg, 2]]
-        assert np.array_equal(got, xs[isreg].astype(np.float32))
-        # faces the reference would not touch keep the input value (AV.cpp:2843-2890)
         untouched = (reg == orc.UNASSIGNED) | (reg == orc.OUTSIDE)
-        assert np.array_equal(out[a][untouched], sc.vel[a].data[untouched])
+        assert np.array_equal(out[a][untouched], sc.vel[a].data[untouched])   # AV.cpp:2843-2890
+        n_bit_equal += int((out[a] == oo).sum())
+        n_total += oo.size
+    assert n_bit_equal >= 0.98 * n_total
     if case["levels"] == 1:
-        assert info.pending_interpolated_faces == 0
+        assert info.interpolated_faces == 0
+    else:
+        assert info.interpolated_faces > 0
 
 
 def test_default_tolerance_iterations_match(solver):

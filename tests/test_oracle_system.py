@@ -206,3 +206,58 @@ def test_weight_shortcut_is_exact():
         assert np.array_equal(a.edge_weights(ax), b.edge_weights(ax))
     w = a.center_weights()
     assert ((w > 0) & (w < 1)).any() and (w == 1).any() and (w == 0).any()
+
+
+# ---- stage 11: octree -> regular grid (HDK_OctreeVectorFieldInterpolator + applyVelocitiesToRegularGrid) ----------
+def _linear_scene(n, R):
+    sc = sphere_drop(n, R, velocity="zero", mu=0.0)
+    for a in range(3):
+        f = sc.vel[a]
+        nz, ny, nx = f.data.shape
+        xs, ys, zs = (f.org[k] + f.dx * np.arange(m) for k, m in enumerate((nx, ny, nz)))
+        Z, Y, X = np.meshgrid(zs, ys, xs, indexing="ij")
+        f.data[...] = (0.1 * (a + 1) + 2 * X - Y + 0.5 * Z).astype(np.float32)
+    return sc
+
+
+def test_prolongation_uniform_grid_copies_solution():
+    sc = sphere_drop(32, 10)
+    r = orc.OracleRun(sc, P(octree_levels=1, tolerance=1e-9))
+    assert r.interpolated_faces == 0
+    keys, x = r.face_keys(), r.solution()
+    for a in range(3):
+        out, reg = r.out_velocity(a), r.regular_index(a)
+        m = keys[:, 1] == a
+        k = keys[m]
+        assert np.array_equal(out[k[:, 4], k[:, 3], k[:, 2]], x[m].astype(np.float32))
+        untouched = reg == orc.UNASSIGNED
+        assert np.array_equal(out[untouched], sc.vel[a].data[untouched])
+
+
+def test_prolongation_reproduces_constants_across_levels():
+    """Partition of unity of the node weights, the bilinear face interpolation and the bubble term: a constant
+    octree field interpolates to the same constant (to one float ulp: node values are stored in fp32)."""
+    v = (0.3, -0.2, 0.1)
+    sc = sphere_drop(64, 26, velocity="constant", constant_velocity=v)
+    r = orc.OracleRun(sc, P(octree_levels=6, tolerance=1e-10))
+    assert r.levels >= 4 and r.interpolated_faces > 100000
+    for a in range(3):
+        out, reg = r.out_velocity(a), r.regular_index(a)
+        assert np.abs(out[reg >= 0] - np.float32(v[a])).max() <= 4e-8
+
+
+def test_prolongation_linear_exact_over_one_transition():
+    """With a single fine/coarse transition the scheme reproduces linear fields (mu = 0: solution = restriction of
+    the input).  Over stacked transitions the reference's T-junction ghost values are first-order only."""
+    sc = _linear_scene(64, 26)
+    r = orc.OracleRun(sc, P(octree_levels=2, tolerance=1e-10))
+    assert r.levels == 2 and r.iterations == 0 and r.interpolated_faces > 10000
+    for a in range(3):
+        out, reg = r.out_velocity(a), r.regular_index(a)
+        m = reg >= 0
+        assert np.abs(out[m] - sc.vel[a].data[m]).max() < 5e-7
+    r3 = orc.OracleRun(sc, P(octree_levels=5, tolerance=1e-10))
+    for a in range(3):
+        out, reg = r3.out_velocity(a), r3.regular_index(a)
+        m = reg >= 0
+        assert np.abs(out[m] - sc.vel[a].data[m]).max() < 2.5 * sc.dx     # bounded by O(dx * gradient)
