@@ -498,7 +498,7 @@ __device__ __forceinline__ bool faceHasWeight(const DeviceScene &S, const I3 &fa
 }
 
 // classifyRegularVelocityFaces (AV.cpp:1087-1165)
-__global__ void k_classify_regular(const __grid_constant__ DeviceScene S, int axis, Grid3<uint8_t> tiles, unsigned long long *counter) {
+__global__ void k_classify_regular(const __grid_constant__ DeviceScene S, int axis, Grid3<uint8_t> tiles) {
     const Grid3<int8_t> g = S.regular[axis];
     forCells(g.n, [&](int x, int y, int z, size_t idx, bool ok) {
     const bool in = ok;
@@ -514,7 +514,6 @@ __global__ void k_classify_regular(const __grid_constant__ DeviceScene S, int ax
     }
     g.d[idx] = out;
     }
-    countWarp(in && out == F_FLUID, counter);
     });
 }
 
@@ -643,7 +642,10 @@ int avs_stage_regular_labels(AvsContext *c) {
     unsigned long long *cnt = c->counters.as<unsigned long long>();
     AVS_CUDA_CHECK(cudaMemsetAsync(cnt + 16, 0, 3 * sizeof(unsigned long long), c->stream));
     LAUNCH_3D(c, k_mark_surface_tiles, S.N, S, t[0], t[1], t[2]);
-    for (int a = 0; a < 3; ++a) LAUNCH_3D(c, k_classify_regular, S.regular[a].n, S, a, t[a], cnt + 16);
+    for (int a = 0; a < 3; ++a) LAUNCH_3D(c, k_classify_regular, S.regular[a].n, S, a, t[a]);
+    // regular DOF count (most of the liquid volume: a fused per-warp atomic would serialise on one address)
+    for (int a = 0; a < 3; ++a)
+        LAUNCH_1D(c, k_count_equal<int8_t>, S.regular[a].count(), S.regular[a].d, S.regular[a].count(), (int8_t)F_FLUID, cnt + 16);
     return AVS_OK;
 }
 
@@ -875,6 +877,17 @@ __global__ void k_find_cuts(const long long *costPrefix, const long long *rowOff
 int avs_stage_octree_labels(AvsContext *c) {
     DeviceScene &S = c->S;
     const int L = S.levels;
+    if (L == 0) {  // no ACTIVE cell at all (the reference asserts this away, OG.cpp:206): an empty system
+        c->nRows = 0;
+        c->nEdge = c->nCenter = 0;
+        c->rowStarts.assign(c->nranks + 1, 0);
+        unsigned long long h = 0;
+        AVS_CUDA_CHECK(cudaMemcpyAsync(&h, c->counters.as<unsigned long long>() + 16, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        c->nRegular = (int64_t)h;
+        if (c->rowKeys.reserve(sizeof(RowKey))) return AVS_ERR_ALLOC;
+        return AVS_OK;
+    }
     // allocate + classify, level by level
     Grid3<uint8_t> t0[3];
     {   // level-0 face tile maps were produced by avs_stage_regular_labels and still live in c->tiles

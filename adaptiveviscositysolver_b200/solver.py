@@ -37,6 +37,7 @@ class Params:
     extrapolation: float = 0.5
     single_precision: bool = False
     check_every: int = 0
+    cancel: Optional[object] = None   # ctypes.c_int32 polled between CG batches (UT_Interrupt::opInterrupt)
 
     def to_c(self) -> AvsParams:
         p = AvsParams()
@@ -52,6 +53,7 @@ class Params:
         p.do_apply_solid_weights = int(self.do_apply_solid_weights)
         p.precision = AVS_PRECISION_F32 if self.single_precision else AVS_PRECISION_F64
         p.check_every = int(self.check_every)
+        p.cancel = C.addressof(self.cancel) if self.cancel is not None else None
         return p
 
 

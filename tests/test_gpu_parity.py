@@ -235,3 +235,46 @@ def test_operator_interface_errors_and_solve():
         changed = sc.vel[a].data != before[a]
         reg = ref.regular_index(a)
         assert not changed[(reg == orc.UNASSIGNED)].any()
+
+
+def test_abi_error_paths_and_cancel(solver):
+    """Status codes instead of exceptions/aborts: missing / misaligned fields (AV.cpp:152-229), bad arguments,
+    user cancel (UT_Interrupt) -- and the context stays usable afterwards."""
+    import ctypes
+    from adaptiveviscositysolver_b200._lib import AvsError
+    from adaptiveviscositysolver_b200.scenes import SampledField
+    from adaptiveviscositysolver_b200.solver import Params
+    sc = sphere_drop(32, 10)
+    bad = sphere_drop(32, 10)
+    bad.surface = SampledField.const(1.0)
+    with pytest.raises(AvsError) as e:
+        solver.solve(bad, Params(octree_levels=3))
+    assert e.value.status == -2                                   # AVS_ERR_MISSING_FIELD
+    bad = sphere_drop(32, 10)
+    bad.face_weights[1] = SampledField(np.ones((32, 32, 32), np.float32), bad.face_weights[1].org, bad.dx)
+    with pytest.raises(AvsError) as e:
+        solver.solve(bad, Params(octree_levels=3))
+    assert e.value.status == -3                                   # AVS_ERR_MISALIGNED_FIELD
+    with pytest.raises(AvsError) as e:
+        solver.solve(sc, Params(octree_levels=0))
+    assert e.value.status == -1                                   # AVS_ERR_INVALID_ARGUMENT
+    flag = ctypes.c_int32(1)
+    with pytest.raises(AvsError) as e:
+        solver.solve(sc, Params(octree_levels=3, tolerance=1e-12, check_every=2, cancel=flag))
+    assert e.value.status == -7                                   # AVS_ERR_CANCELLED
+    info = solver.solve(sc, Params(octree_levels=3))              # still works
+    assert info.iterations > 0 and info.error < 1e-3
+
+
+def test_empty_liquid(solver):
+    """No liquid anywhere: zero DOFs, zero iterations, velocity untouched (the reference would build an empty system)."""
+    from adaptiveviscositysolver_b200.solver import Params
+    sc = sphere_drop(32, 10)
+    sc.surface.data[...] = 5.0
+    for a in range(3):
+        sc.face_weights[a].data[...] = 0.0
+    out = [v.data.copy() for v in sc.vel]
+    info = solver.solve(sc, Params(octree_levels=3), out)
+    assert info.octree_dofs == 0 and info.iterations == 0 and info.nnz == 0
+    for a in range(3):
+        assert np.array_equal(out[a], sc.vel[a].data)
