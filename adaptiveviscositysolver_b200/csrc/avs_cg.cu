@@ -47,7 +47,7 @@ __global__ void k_sjds_count(long long n, const int32_t *rowLen, long long nslic
         total += other;
     }
     meta[s * 32 + rank] = (lane << 8) | np;
-    if (lane == 0) slicePairs[s] = total;
+    if (lane == 0) slicePairs[s] = total + (total & 1);  // even: slice starts are 16-byte aligned in val2 AND col2 (bulk copies)
 }
 
 // fill from the assembly staging area (entry j of row r at j*stride + r)
@@ -321,6 +321,168 @@ __global__ void __launch_bounds__(CG_THREADS) k_spmv_sjds(long long nrows, long 
     }
 }
 
+// ---- SpMV, TMA-staged variant --------------------------------------------------------------------
+// Same SJDS-32 matrix, same arithmetic per row, different data movement: the matrix is streamed by the TMA unit.
+// One persistent CTA per SM (16 warps).  A chunk = 16 consecutive slices = 512 rows; its value pairs and column
+// pairs are two contiguous byte ranges, fetched with two 1-D bulk async copies (cp.async.bulk ... mbarrier
+// complete_tx, SASS UBLKCP) into one of two shared-memory stages while the warps work on the other stage.
+// Warps read their slice out of shared memory (conflict-free LDS.128 / LDS.64), gather x through the read-only
+// path, reduce p.Ap with warp shuffles.  Chunks larger than a stage (rows far denser than average) fall back to
+// direct global loads.
+#define TMA_WARPS 16
+#define TMA_THREADS (TMA_WARPS * 32)
+#define TMA_CAP_PAIRS 4608
+
+__device__ __forceinline__ uint32_t smemAddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulkG2S(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dst)),
+                 "l"(src), "r"(bytes), "r"(smemAddr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smemAddr(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// one slice (32 rows) from `v`/`cc` (shared or global), returns this lane's row sum
+template <class T, class T2>
+__device__ __forceinline__ T sliceRowSum(const T2 *__restrict__ v, const int2 *__restrict__ cc, int np, int maxnp, int lane,
+                                         const T *__restrict__ x) {
+    T acc = 0;
+    int off = lane;
+    for (int j0 = 0; j0 < maxnp; j0 += 4) {
+        int o[4];
+        bool act[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            act[u] = (j0 + u) < np;
+            o[u] = off;
+            off += __popc(__ballot_sync(0xffffffffu, act[u]));
+        }
+        T2 vv[4];
+        int2 c4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            vv[u].x = 0; vv[u].y = 0;
+            c4[u].x = 0; c4[u].y = 0;
+            if (act[u]) { vv[u] = v[o[u]]; c4[u] = cc[o[u]]; }
+        }
+        T xa[4], xb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            xa[u] = 0; xb[u] = 0;
+            if (act[u]) { xa[u] = __ldg(x + c4[u].x); xb[u] = __ldg(x + c4[u].y); }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            acc += vv[u].x * xa[u];
+            acc += vv[u].y * xb[u];
+        }
+    }
+    return acc;
+}
+
+template <class T, class T2, bool DOT>
+__global__ void __launch_bounds__(TMA_THREADS, 1) k_spmv_tma(long long nrows, long long nslices, const long long *__restrict__ sliceOff,
+                                                             const int32_t *__restrict__ meta, const T2 *__restrict__ val2,
+                                                             const int2 *__restrict__ col2, const T *__restrict__ x, T *__restrict__ y,
+                                                             double *__restrict__ parts, const CgScalars *sc) {
+    if (sc && sc->done) return;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *bar = (uint64_t *)smem;
+    const size_t stageBytes = (size_t)TMA_CAP_PAIRS * (sizeof(T2) + sizeof(int2));
+    T2 *sval[2];
+    int2 *scol[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        sval[s] = (T2 *)(smem + 128 + s * stageBytes);
+        scol[s] = (int2 *)(smem + 128 + s * stageBytes + (size_t)TMA_CAP_PAIRS * sizeof(T2));
+    }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbarInit(&bar[0], 1);
+        mbarInit(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const long long nChunks = (nslices + TMA_WARPS - 1) / TMA_WARPS;
+    auto chunkRange = [&](long long i, long long &s0, long long &s1, long long &p0, long long &np) {
+        const long long c = (long long)blockIdx.x + i * gridDim.x;
+        s0 = c * TMA_WARPS;
+        s1 = min(s0 + (long long)TMA_WARPS, nslices);
+        p0 = sliceOff[s0];
+        np = sliceOff[s1] - p0;
+    };
+    auto issue = [&](long long i) {  // thread 0 only
+        long long s0, s1, p0, np;
+        chunkRange(i, s0, s1, p0, np);
+        if (np > 0 && np <= TMA_CAP_PAIRS) {
+            const int st = (int)(i & 1);
+            mbarExpectTx(&bar[st], (uint32_t)(np * (sizeof(T2) + sizeof(int2))));
+            bulkG2S(sval[st], val2 + p0, (uint32_t)(np * sizeof(T2)), &bar[st]);
+            bulkG2S(scol[st], col2 + p0, (uint32_t)(np * sizeof(int2)), &bar[st]);
+        }
+    };
+    long long myChunks = 0;
+    if ((long long)blockIdx.x < nChunks) myChunks = (nChunks - 1 - blockIdx.x) / gridDim.x + 1;
+    uint32_t phase[2] = {0, 0};
+    double dot = 0;
+    if (myChunks > 0 && tid == 0) issue(0);
+    for (long long i = 0; i < myChunks; ++i) {
+        if (i + 1 < myChunks && tid == 0) issue(i + 1);
+        long long s0, s1, p0, np;
+        chunkRange(i, s0, s1, p0, np);
+        const int st = (int)(i & 1);
+        const bool staged = np > 0 && np <= TMA_CAP_PAIRS;
+        if (staged) {
+            mbarWait(&bar[st], phase[st]);
+            phase[st] ^= 1u;
+        }
+        const long long s = s0 + warp;
+        if (s < s1) {
+            const int m = meta[s * 32 + lane];
+            const int npl = m & 0xff;
+            const long long r = s * 32 + (m >> 8);
+            const int maxnp = __shfl_sync(0xffffffffu, npl, 0);
+            const long long rel = sliceOff[s] - p0;
+            T acc;
+            if (staged) acc = sliceRowSum<T, T2>(sval[st] + rel, scol[st] + rel, npl, maxnp, lane, x);
+            else acc = sliceRowSum<T, T2>(val2 + p0 + rel, col2 + p0 + rel, npl, maxnp, lane, x);
+            if (r < nrows) {
+                y[r] = acc;
+                if (DOT) dot += (double)__ldg(x + r) * (double)acc;
+            }
+        }
+        __syncthreads();  // every warp is done with stage `st` before iteration i+1 refills it (as chunk i+2)
+    }
+    if (DOT) {
+        __shared__ double red[TMA_WARPS];
+        double v = warpSum(dot);
+        if (lane == 0) red[warp] = v;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0;
+            for (int w = 0; w < TMA_WARPS; ++w) t += red[w];
+            parts[blockIdx.x] = t;
+        }
+    }
+}
+
 // ---- CG vector kernels --------------------------------------------------------------------------
 // init: r = b - t (t = A x0), p = invdiag r; partial b.b, r.r, r.p
 template <class T>
@@ -443,6 +605,17 @@ static int spmvU() {
     }
     return u;
 }
+static bool spmvUseTma() {
+    static int t = -1;
+    if (t < 0) {
+        const char *e = getenv("AVS_SPMV_TMA");
+        t = (e && e[0] == '1') ? 1 : 0;
+    }
+    return t == 1;
+}
+template <class T, class T2>
+static size_t tmaSmemBytes() { return 128 + 2 * (size_t)TMA_CAP_PAIRS * (sizeof(T2) + sizeof(int2)); }
+
 template <class T, class T2, bool DOT>
 static void launchSpmv(AvsContext *c, SellMatrix &A, const T *x, T *y, double *parts, const CgScalars *sc, int grid) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -451,15 +624,26 @@ static void launchSpmv(AvsContext *c, SellMatrix &A, const T *x, T *y, double *p
         e1 = c->spmvEvents[c->spmvEventsUsed++];
         cudaEventRecord(e0, c->stream);
     }
+    if (spmvUseTma()) {
+        static bool attrSet[2] = {false, false};
+        const size_t smem = tmaSmemBytes<T, T2>();
+        if (!attrSet[DOT]) {
+            cudaFuncSetAttribute(k_spmv_tma<T, T2, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attrSet[DOT] = true;
+        }
+        k_spmv_tma<T, T2, DOT><<<grid, TMA_THREADS, smem, c->stream>>>(A.n, A.nslices, A.sliceOff.as<long long>(), A.meta.as<int32_t>(),
+                                                                       A.val.as<T2>(), A.col.as<int2>(), x, y, parts, sc);
+    } else {
 #define SPMV_LAUNCH(U)                                                                                                            \
     k_spmv_sjds<T, T2, DOT, U><<<grid, CG_THREADS, 0, c->stream>>>(A.n, A.nslices, A.sliceOff.as<long long>(), A.meta.as<int32_t>(), \
                                                                     A.val.as<T2>(), A.col.as<int2>(), x, y, parts, sc)
-    switch (spmvU()) {
-        case 2: SPMV_LAUNCH(2); break;
-        case 8: SPMV_LAUNCH(8); break;
-        default: SPMV_LAUNCH(4); break;
-    }
+        switch (spmvU()) {
+            case 2: SPMV_LAUNCH(2); break;
+            case 8: SPMV_LAUNCH(8); break;
+            default: SPMV_LAUNCH(4); break;
+        }
 #undef SPMV_LAUNCH
+    }
     if (e1) cudaEventRecord(e1, c->stream);
     ++c->launches;
     ++c->spmvLaunches;
@@ -468,6 +652,10 @@ static void launchSpmv(AvsContext *c, SellMatrix &A, const T *x, T *y, double *p
 // persistent SpMV grid: exactly the number of CTAs that are resident at once (one wave)
 template <class T, class T2>
 static int spmvGrid(AvsContext *c, long long nslices) {
+    if (spmvUseTma()) {
+        long long chunks = (nslices + TMA_WARPS - 1) / TMA_WARPS;
+        return (int)std::max<long long>(1, std::min<long long>(chunks, c->numSMs));
+    }
     int perSM = 0;
     cudaError_t e;
     switch (spmvU()) {

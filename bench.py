@@ -274,6 +274,14 @@ def main():
     spmv_avg_ms = spmv_ms / max(spmv_n, 1) if spmv_ms > 0 else iso_ms
     achieved = alg_bytes / (spmv_avg_ms * 1e-3) / 1e9
 
+    # DRAM traffic of one SpMV launch from the committed ncu --set full capture (only valid for the same matrix)
+    traffic = None
+    tp = ROOT / "profiles" / "r1_spmv_traffic.json"
+    if tp.exists() and world == 1 and not args.fp32:
+        tj = json.loads(tp.read_text())
+        if tj.get("N") == int(N) and tj.get("nnz") == int(nnz):
+            traffic = tj["traffic_bytes_per_launch"]
+
     # ---- end to end through the host-buffer call --------------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -324,7 +332,7 @@ def main():
                        "wall_ms_per_step": wall_ms, "per_rank": per_rank,
                        "stage_ms": {k2: round(v, 3) for k2, v in info.stage_ms.items()}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_spmv_sjds (CG SpMV + fused p.Ap)", "peak_source": peak_src,
+                         "traffic": traffic, "kernel": "k_spmv_sjds (CG SpMV + fused p.Ap)", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": spmv_avg_ms, "launches_timed": int(spmv_n),
                          "back_to_back_ms": iso_ms, "cg_update_xr_ms_per_iter": info.cg_update_xr_ms / max(info.spmv_launches - 1, 1),
                          "cg_update_p_ms_per_iter": info.cg_update_p_ms / max(info.spmv_launches - 1, 1),
