@@ -21,6 +21,7 @@ EXPORTS = [
     "avs_abi_version", "avs_nccl_unique_id", "avs_get_local_range", "avs_get_row_starts", "avs_create", "avs_destroy", "avs_status_string", "avs_last_error", "avs_default_params",
     "avs_solve", "avs_assemble", "avs_solve_resident", "avs_apply", "avs_get_sizes", "avs_get_keys",
     "avs_get_system_csr", "avs_get_solution", "avs_get_grid", "avs_cg_csr", "avs_spmv_csr", "avs_time_spmv_resident",
+    "avs_build_octree", "avs_get_octree_points",
 ]
 
 
@@ -107,6 +108,8 @@ def load():
     L.avs_cg_csr.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, C.POINTER(AvsParams), C.POINTER(AvsResult)]
     L.avs_spmv_csr.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.avs_time_spmv_resident.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double)]
+    L.avs_build_octree.argtypes = [vp, C.POINTER(AvsFields), C.POINTER(AvsParams), C.POINTER(AvsResult)]
+    L.avs_get_octree_points.argtypes = [vp, C.POINTER(C.c_int64), vp, vp, vp]
     for name in EXPORTS:
         getattr(L, name)  # every symbol of include/avs.h must be exported
     _lib = L

@@ -118,7 +118,8 @@ void avs_destroy(AvsContext *c) {
                       &c->scanTmp, &c->counters, &c->rowKeys, &c->x0, &c->rhs, &c->solution, &c->rowCount, &c->rowOffset,
                       &c->csrPtr, &c->csrCol, &c->csrVal, &c->A.sliceOff, &c->A.val, &c->A.col, &c->A.invDiag, &c->A.meta,
                       &c->cg.x, &c->cg.r, &c->cg.p, &c->cg.t, &c->cg.partials, &c->cg.scalars, &c->cgRhs,
-                      &c->stageCol, &c->stageVal, &c->diag, &c->slicePairs, &c->edgeTiles, &c->solidW, &c->signA, &c->signB, &c->bandList, &c->brickCost, &c->brickCostPrefix};
+                      &c->stageCol, &c->stageVal, &c->diag, &c->slicePairs, &c->edgeTiles, &c->solidW, &c->signA, &c->signB, &c->bandList, &c->brickCost, &c->brickCostPrefix,
+                      &c->geoCount, &c->geoOffset, &c->geoPos, &c->geoScale, &c->geoLevel};
     for (DevBuf *b : bufs) b->release();
     for (int a = 0; a < 3; ++a) {
         c->inVel[a].release(); c->inFaceW[a].release(); c->inCollVel[a].release(); c->edgeW[a].release(); c->regular[a].release();
@@ -250,16 +251,22 @@ static void collectStageTimes(AvsContext *c, AvsResult *res, int first, int last
     res->stage_ms[AVS_STAGE_TOTAL] += total;
 }
 
-static int runAssemble(AvsContext *c, const AvsFields *in, const AvsParams *p, AvsResult *res) {
+static int runAssemble(AvsContext *c, const AvsFields *in, const AvsParams *p, AvsResult *res, bool octreeOnly = false) {
     int rc;
-    c->haveSystem = c->haveSolution = false;
+    c->haveSystem = c->haveSolution = c->haveOctree = false;
     cudaEventRecord(c->ev[AVS_STAGE_UPLOAD], c->stream);
     if ((rc = avs_stage_upload(c, in, p))) return rc;
     cudaEventRecord(c->ev[AVS_STAGE_SURFACE_WEIGHTS], c->stream);
     if ((rc = avs_stage_weights(c, p))) return rc;
     cudaEventRecord(c->ev[AVS_STAGE_OCTREE], c->stream);
     if ((rc = avs_stage_octree(c, p))) return rc;
+    c->haveOctree = true;
     cudaEventRecord(c->ev[AVS_STAGE_REGULAR_LABELS], c->stream);
+    if (octreeOnly) {   // onlyPrintOctree (AV.cpp:292-293): the reference returns right after the geometry dump
+        collectStageTimes(c, res, AVS_STAGE_UPLOAD, AVS_STAGE_OCTREE);
+        res->levels = c->S.levels;
+        return AVS_OK;
+    }
     if ((rc = avs_stage_regular_labels(c))) return rc;
     cudaEventRecord(c->ev[AVS_STAGE_OCTREE_LABELS], c->stream);
     if ((rc = avs_stage_octree_labels(c))) return rc;
@@ -376,6 +383,35 @@ int avs_assemble(AvsContext *c, const AvsFields *in, const AvsParams *p, AvsResu
     int rc = runAssemble(c, in, p, res);
     res->status = rc;
     return rc;
+}
+
+int avs_build_octree(AvsContext *c, const AvsFields *in, const AvsParams *p, AvsResult *res) {
+    if (!c || !res || res->size != sizeof(AvsResult)) return AVS_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(c->device);
+    memset(res->stage_ms, 0, sizeof(res->stage_ms));
+    c->launches = 0;
+    c->spmvLaunches = 0;
+    int rc = runAssemble(c, in, p, res, true);
+    res->kernel_launches = c->launches;
+    res->status = rc;
+    return rc;
+}
+
+int avs_get_octree_points(AvsContext *c, int64_t *count, float *pos, float *pscale, int32_t *level) {
+    if (!c || !count) return AVS_ERR_INVALID_ARGUMENT;
+    if (!c->haveOctree) return AVS_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(c->device);
+    int64_t n = 0;
+    int rc = avs_octree_points(c, &n);
+    if (rc) return rc;
+    *count = n;
+    if (n > 0) {
+        if (pos) AVS_CUDA_CHECK(cudaMemcpyAsync(pos, c->geoPos.p, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        if (pscale) AVS_CUDA_CHECK(cudaMemcpyAsync(pscale, c->geoScale.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        if (level) AVS_CUDA_CHECK(cudaMemcpyAsync(level, c->geoLevel.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    }
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return AVS_OK;
 }
 
 int avs_solve_resident(AvsContext *c, const AvsParams *p, AvsResult *res) {

@@ -86,6 +86,8 @@ struct AvsContext {
     DevBuf csrPtr, csrCol, csrVal;  // canonical CSR of the local rows (int64 / int32 / fp64); col/val built lazily
     DevBuf stageCol, stageVal, diag; // assembly staging area (column-major, MAX_ROW deep) and the diagonal
     DevBuf slicePairs, edgeTiles, solidW; // per-solve scratch kept across calls (no cudaMalloc/cudaFree in steady state)
+    DevBuf geoCount, geoOffset, geoPos, geoScale, geoLevel;  // octree geometry dump (OG.cpp:245-308), built on request
+    bool haveOctree = false;
     long long stageStride = 0;
     bool csrValid = false;
     DeviceScene S;          // host copy of the descriptor handed to kernels
@@ -116,6 +118,7 @@ int avs_stage_upload(AvsContext *c, const AvsFields *in, const AvsParams *p);
 int avs_stage_weights(AvsContext *c, const AvsParams *p);
 int avs_stage_octree(AvsContext *c, const AvsParams *p);
 int avs_stage_regular_labels(AvsContext *c);
+int avs_octree_points(AvsContext *c, int64_t *countOut);
 int avs_stage_octree_labels(AvsContext *c);
 int avs_stage_restriction(AvsContext *c);
 int avs_stage_system(AvsContext *c, const AvsParams *p);

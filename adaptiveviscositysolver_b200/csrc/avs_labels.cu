@@ -986,3 +986,91 @@ int avs_stage_octree_labels(AvsContext *c) {
     AVS_CUDA_CHECK(cudaGetLastError());
     return AVS_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Octree geometry dump (HDK_OctreeGrid::outputOctreeGeometry, OG.cpp:245-308, reached from AV.cpp:283-294 when
+// doPrintOctree is set): one point per ACTIVE cell of every built level, carrying the cell centre, pscale = the
+// level's voxel size and octreeLevel.  The reference appends points while walking tiles; here the order is
+// level-major, x-fastest (deterministic: per-block counts -> exclusive scan -> ordered fill), and the point set
+// is what parity is judged on.
+#define GEO_BLOCK 256
+__global__ void k_geo_count(Grid3<uint8_t> g, int32_t *blockCount) {
+    size_t idx = (size_t)blockIdx.x * GEO_BLOCK + threadIdx.x;
+    bool hit = idx < g.count() && g.d[idx] == L_ACTIVE;
+    unsigned m = __ballot_sync(0xffffffffu, hit);
+    __shared__ int s[GEO_BLOCK / 32];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < GEO_BLOCK / 32; ++i) t += s[i];
+        blockCount[blockIdx.x] = t;
+    }
+}
+__global__ void k_geo_fill(DeviceScene S, int level, const long long *blockOffset, long long base, float *pos, float *pscale,
+                           int32_t *lvl) {
+    const Grid3<uint8_t> &g = S.label[level];
+    size_t idx = (size_t)blockIdx.x * GEO_BLOCK + threadIdx.x;
+    bool hit = idx < g.count() && g.d[idx] == L_ACTIVE;
+    unsigned m = __ballot_sync(0xffffffffu, hit);
+    __shared__ int s[GEO_BLOCK / 32];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = __popc(m);
+    __syncthreads();
+    if (!hit) return;
+    int before = __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += s[w];
+    long long o = base + blockOffset[blockIdx.x] + before;
+    I3 c = mk3((int)(idx % g.n[0]), (int)((idx / g.n[0]) % g.n[1]), (int)(idx / ((size_t)g.n[0] * g.n[1])));
+    double p[3];
+    S.centerPos(c, level, p);      // SIM_RawField::indexToPos of a centre-sampled grid, stored as UT_Vector3 (fp32)
+    pos[3 * o + 0] = (float)p[0];
+    pos[3 * o + 1] = (float)p[1];
+    pos[3 * o + 2] = (float)p[2];
+    pscale[o] = (float)S.levelDx(level);
+    lvl[o] = level;
+}
+
+// Writes the points to the device buffers of the context (geoPos / geoScale / geoLevel) and returns the count.
+int avs_octree_points(AvsContext *c, int64_t *countOut) {
+    DeviceScene &S = c->S;
+    int64_t total = 0;
+    std::vector<int64_t> perLevel(S.levels, 0);
+    std::vector<size_t> blocks(S.levels, 0);
+    size_t maxBlocks = 1, sumBlocks = 0;
+    for (int l = 0; l < S.levels; ++l) {
+        blocks[l] = (S.label[l].count() + GEO_BLOCK - 1) / GEO_BLOCK;
+        maxBlocks = std::max(maxBlocks, blocks[l]);
+        sumBlocks += blocks[l];
+    }
+    if (c->geoCount.reserve(std::max<size_t>(sumBlocks, 1) * sizeof(int32_t))) return AVS_ERR_ALLOC;
+    if (c->geoOffset.reserve(std::max<size_t>(sumBlocks, 1) * sizeof(long long))) return AVS_ERR_ALLOC;
+    // pass 1: counts and per-level offsets
+    size_t bo = 0;
+    for (int l = 0; l < S.levels; ++l) {
+        k_geo_count<<<(unsigned)blocks[l], GEO_BLOCK, 0, c->stream>>>(S.label[l], c->geoCount.as<int32_t>() + bo);
+        ++c->launches;
+        int rc = avs_exclusive_scan_i32_to_i64(c, c->geoCount.as<int32_t>() + bo, c->geoOffset.as<int64_t>() + bo, (int64_t)blocks[l],
+                                               &perLevel[l]);
+        if (rc) return rc;
+        total += perLevel[l];
+        bo += blocks[l];
+    }
+    if (c->geoPos.reserve((size_t)std::max<int64_t>(total, 1) * 3 * sizeof(float))) return AVS_ERR_ALLOC;
+    if (c->geoScale.reserve((size_t)std::max<int64_t>(total, 1) * sizeof(float))) return AVS_ERR_ALLOC;
+    if (c->geoLevel.reserve((size_t)std::max<int64_t>(total, 1) * sizeof(int32_t))) return AVS_ERR_ALLOC;
+    // pass 2: ordered fill
+    bo = 0;
+    long long base = 0;
+    for (int l = 0; l < S.levels; ++l) {
+        if (perLevel[l] > 0) {
+            k_geo_fill<<<(unsigned)blocks[l], GEO_BLOCK, 0, c->stream>>>(S, l, c->geoOffset.as<long long>() + bo, base, c->geoPos.as<float>(),
+                                                                          c->geoScale.as<float>(), c->geoLevel.as<int32_t>());
+            ++c->launches;
+        }
+        base += perLevel[l];
+        bo += blocks[l];
+    }
+    AVS_CUDA_CHECK(cudaGetLastError());
+    *countOut = total;
+    return AVS_OK;
+}

@@ -224,6 +224,28 @@ class Solver:
         self._check(self._L.avs_assemble(self._h, C.byref(f), C.byref(p), C.byref(r)), "avs_assemble")
         return SolveInfo.from_c(r)
 
+    def build_octree(self, scene: Scene, params: Params) -> SolveInfo:
+        """avs_build_octree: stages 1-3 only (the reference's ``onlyPrintOctree`` early return, AV.cpp:292-293)."""
+        keep: list = []
+        f = fields_to_c(scene, keep)
+        p = params.to_c()
+        r = _new_result()
+        self._check(self._L.avs_build_octree(self._h, C.byref(f), C.byref(p), C.byref(r)), "avs_build_octree")
+        return SolveInfo.from_c(r)
+
+    def octree_points(self):
+        """The octree geometry dump (HDK_OctreeGrid::outputOctreeGeometry, OG.cpp:245-308): ``(P, pscale, octreeLevel)``
+        with one point per ACTIVE cell -- positions (n, 3) float32, pscale (n,) float32, octreeLevel (n,) int32."""
+        n = C.c_int64()
+        self._check(self._L.avs_get_octree_points(self._h, C.byref(n), None, None, None), "avs_get_octree_points")
+        pos = np.empty((n.value, 3), np.float32)
+        pscale = np.empty(n.value, np.float32)
+        level = np.empty(n.value, np.int32)
+        if n.value:
+            self._check(self._L.avs_get_octree_points(self._h, C.byref(n), pos.ctypes.data, pscale.ctypes.data, level.ctypes.data),
+                        "avs_get_octree_points")
+        return pos, pscale, level
+
     def solve_resident(self, params: Params) -> SolveInfo:
         p = params.to_c()
         r = _new_result()
@@ -359,6 +381,7 @@ class SIM_Object:
 
     def __init__(self, scalar_fields: Dict[str, Scene] = None, **fields):
         self.fields = dict(fields)
+        self.geometry: Dict[str, tuple] = {}     # getOrCreateGeometry(obj, "octreeGeometry") (AV.cpp:285)
 
     @staticmethod
     def from_scene(scene: Scene) -> "SIM_Object":
@@ -454,8 +477,13 @@ class HDK_AdaptiveViscosity:
         if self._solver is None:
             self._solver = Solver(device=self._device)
         if self.doPrintOctree and self.onlyPrintOctree:
-            # AV.cpp:283-294: only the octree is requested; the geometry dump itself is Houdini-only (out of scope)
-            self.info = self._solver.assemble(scene, self._params(timestep))
+            # AV.cpp:283-294: dump the octree geometry ("octreeGeometry" SIM_GeometryCopy: P, pscale, octreeLevel) and return
+            try:
+                self.info = self._solver.build_octree(scene, self._params(timestep))
+                obj.geometry["octreeGeometry"] = self._solver.octree_points()
+            except AvsError as e:
+                self.addError(obj, str(e))
+                return False
             return True
         out = [v.data for v in vel]
         try:
@@ -463,6 +491,8 @@ class HDK_AdaptiveViscosity:
         except AvsError as e:
             self.addError(obj, str(e))
             return False
+        if self.doPrintOctree:
+            obj.geometry["octreeGeometry"] = self._solver.octree_points()
         i = self.info
         # event.setExtraInfo (AV.cpp:645-652)
         self.extra_info = "iterations=%d, error=%.6f, octree DOFS=%d, regular DOFs=%d" % (

@@ -180,6 +180,16 @@ int avs_solve_resident(AvsContext *ctx, const AvsParams *p, AvsResult *res);
 /* Stage 11 on the resident solution: node pyramid + interpSPGrid + write-back to the regular grid. */
 int avs_apply(AvsContext *ctx, AvsVelocityOut *out, AvsResult *res);
 
+/* The octree geometry dump of the DOP's `doPrintOctree` / `onlyPrintOctree` toggles (AV.cpp:283-294;
+ * HDK_OctreeGrid::outputOctreeGeometry, HDK_OctreeGrid.cpp:245-308).
+ * avs_build_octree runs stages 1-3 only (weights, refinement mask, label pyramid) -- the `onlyPrintOctree` early return.
+ * avs_get_octree_points is valid after avs_build_octree / avs_assemble / avs_solve: one point per ACTIVE cell of every
+ * built level -- pos[3*i..] = cell centre (fp32, like UT_Vector3), pscale[i] = voxel size of the cell's level,
+ * level[i] = "octreeLevel".  HOST buffers; NULL arrays are skipped, so a first call with NULLs returns the count.
+ * Point order is level-major then x-fastest; the reference's order follows its tile iterator and is not a contract. */
+int avs_build_octree(AvsContext *ctx, const AvsFields *in, const AvsParams *p, AvsResult *res);
+int avs_get_octree_points(AvsContext *ctx, int64_t *count, float *pos, float *pscale, int32_t *level);
+
 /* Read-back of the resident state, all to HOST buffers (NULL pointers are skipped).
  * keys: n x 5 int32 (level, axis, i, j, k) -- DOF numbering is NOT part of the parity contract,
  * results are compared by geometric key. */

@@ -1591,6 +1591,31 @@ int64_t orc_get_node_grid(void *h, int kind, int level, float *out, int *res) {
 }
 int64_t orc_interpolated_faces(void *h) { return ((Oracle *)h)->interpolatedFaces; }
 
+// HDK_OctreeGrid::outputOctreeGeometry (OG.cpp:245-308, called from AV.cpp:283-294 under doPrintOctree): one point per
+// ACTIVE cell of every built level: P = indexToPos(cell) stored as UT_Vector3 (fp32), pscale = the level's voxel size,
+// octreeLevel = level.  The reference appends in tile order; here level-major, x-fastest (the point SET is the contract).
+int64_t orc_get_octree_points(void *h, float *pos, float *pscale, int32_t *level) {
+    Oracle *o = (Oracle *)h;
+    int64_t n = 0;
+    for (int l = 0; l < o->levels; ++l) {
+        const Arr3<uint8_t> &g = o->labels[l];
+        for (int z = 0; z < g.n[2]; ++z)
+            for (int y = 0; y < g.n[1]; ++y)
+                for (int x = 0; x < g.n[0]; ++x) {
+                    if (g.d[g.lin(x, y, z)] != ACTIVE) continue;   // OG.cpp:286
+                    if (pos) {
+                        double p[3];
+                        o->centerPos(mk(x, y, z), l, p);           // OG.cpp:289-292
+                        for (int a = 0; a < 3; ++a) pos[3 * n + a] = (float)p[a];
+                        pscale[n] = (float)o->levelDx(l);          // OG.cpp:273, 295
+                        level[n] = l;                              // OG.cpp:296
+                    }
+                    ++n;
+                }
+    }
+    return n;
+}
+
 void orc_get_csr(void *h, int64_t *rowPtr, int32_t *col, double *val) {
     Oracle *o = (Oracle *)h;
     std::memcpy(rowPtr, o->rowPtr.data(), o->rowPtr.size() * sizeof(int64_t));

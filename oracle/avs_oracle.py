@@ -89,6 +89,8 @@ def lib():
         L.orc_get_node_grid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
         L.orc_interpolated_faces.restype = C.c_int64
         L.orc_interpolated_faces.argtypes = [C.c_void_p]
+        L.orc_get_octree_points.restype = C.c_int64
+        L.orc_get_octree_points.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_stencil.argtypes = [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p, C.POINTER(C.c_int),
                                                                 C.c_void_p, C.POINTER(C.c_double)]
         L.orc_spmv_f64.argtypes = [C.c_int64] + [C.c_void_p] * 5
@@ -293,6 +295,16 @@ class OracleRun:
     @property
     def interpolated_faces(self):
         return self._L.orc_interpolated_faces(self._h)
+
+    def octree_points(self):
+        """HDK_OctreeGrid::outputOctreeGeometry (OG.cpp:245-308): (P (n,3) f32, pscale (n,) f32, octreeLevel (n,) i32)."""
+        n = self._L.orc_get_octree_points(self._h, None, None, None)
+        pos = np.empty((n, 3), np.float32)
+        pscale = np.empty(n, np.float32)
+        level = np.empty(n, np.int32)
+        if n:
+            self._L.orc_get_octree_points(self._h, pos.ctypes.data, pscale.ctypes.data, level.ctypes.data)
+        return pos, pscale, level
 
     def csr(self):
         n, nnz = self.n_face, self.nnz

@@ -22,6 +22,11 @@ CASES = {
     "solid_ground": dict(scene=dict(n=32, radius_cells=9, center=(0.5, 0.34, 0.5), ground_height=0.125,
                                     ground_velocity=(0.1, 0.0, -0.2)), levels=3),
     "no_enhanced_gradients": dict(scene=dict(n=32, radius_cells=11), levels=4, enhanced=False),
+    # the "theta" solid weights (AV.cpp:772-790) -- dead in a stock scene because of the option-name
+    # mismatch (AV.h:37), reachable through the ABI
+    "solid_weights": dict(scene=dict(n=32, radius_cells=9, center=(0.5, 0.34, 0.5), ground_height=0.12,
+                                     ground_velocity=(0.0, 0.05, 0.0)), levels=3, params=dict(do_apply_solid_weights=True)),
+    "wide_fine_band": dict(scene=dict(n=64, radius_cells=24), levels=4, params=dict(fine_bandwidth=5, number_super_samples=2)),
 }
 
 
@@ -35,6 +40,7 @@ def solver():
 
 def _params(case, tol=1e-10, **kw):
     from adaptiveviscositysolver_b200.solver import Params
+    kw = dict(case.get("params", {}), **kw)
     return (Params(octree_levels=case["levels"], tolerance=tol, use_enhanced_gradients=case.get("enhanced", True), **kw),
             orc.OracleParams(octree_levels=case["levels"], tolerance=tol,
                              use_enhanced_gradients=case.get("enhanced", True), **kw))
