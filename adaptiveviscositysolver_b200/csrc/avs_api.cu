@@ -116,7 +116,7 @@ void avs_destroy(AvsContext *c) {
     avs_dist_destroy(c);
     DevBuf *bufs[] = {&c->fullSolution, &c->inSurface, &c->inVisc, &c->inDens, &c->inColl, &c->centerW, &c->tiles, &c->brickCount, &c->brickOffset,
                       &c->scanTmp, &c->counters, &c->rowKeys, &c->x0, &c->rhs, &c->solution, &c->rowCount, &c->rowOffset,
-                      &c->csrPtr, &c->csrCol, &c->csrVal, &c->A.sliceOff, &c->A.val, &c->A.col, &c->A.invDiag, &c->A.meta,
+                      &c->csrPtr, &c->csrCol, &c->csrVal, &c->A.sliceOff, &c->A.val, &c->A.col, &c->A.invDiag, &c->A.meta, &c->cg.pcgState,
                       &c->cg.x, &c->cg.r, &c->cg.p, &c->cg.t, &c->cg.partials, &c->cg.scalars, &c->cgRhs,
                       &c->stageCol, &c->stageVal, &c->diag, &c->slicePairs, &c->edgeTiles, &c->solidW, &c->signA, &c->signB, &c->bandList, &c->brickCost, &c->brickCostPrefix,
                       &c->geoCount, &c->geoOffset, &c->geoPos, &c->geoScale, &c->geoLevel};
@@ -303,7 +303,12 @@ static int runSolve(AvsContext *c, const AvsParams *p, AvsResult *res) {
     // Launches after convergence are no-ops (device-side `done` flag): only the launches that did work count.
     // Event pair 0 is the residual SpMV (r = b - A x0), pairs 1..iters+1 are the CG iterations incl. the one that broke out.
     const int64_t realCg = std::min<int64_t>((int64_t)res->iterations + 1, std::max<int64_t>(p->max_iterations, 0));
-    if (c->timeSpmv) {
+    if (c->pcgUsed) {   // persistent kernel: phase times come from its own %globaltimer stamps
+        res->spmv_ms = c->pcgSpmvMs;
+        res->spmv_launches = c->pcgPhases;
+        res->cg_update_xr_ms = c->pcgXrMs;
+        res->cg_update_p_ms = c->pcgPMs;
+    } else if (c->timeSpmv) {
         const size_t pairs = std::min<size_t>(c->spmvEventsUsed / 2, (size_t)(realCg + 1));
         float total = 0;
         for (size_t i = 0; i < pairs; ++i) {

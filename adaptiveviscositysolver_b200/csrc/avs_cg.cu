@@ -23,6 +23,7 @@
 #include <cstring>
 
 #include "avs_context.h"
+#include "avs_p2p.cuh"
 
 #define CG_THREADS 256
 #define CG_CTAS_PER_SM 8
@@ -261,21 +262,39 @@ struct CgScalars {
 };
 
 // ---- SpMV: y = A x, fused partial dot x.y -------------------------------------------------------
-template <class T, class T2, bool DOT, int SPMV_U>
-__global__ void __launch_bounds__(CG_THREADS) k_spmv_sjds(long long nrows, long long nslices, const long long *__restrict__ sliceOff,
-                                                          const int32_t *__restrict__ meta, const T2 *__restrict__ val2,
-                                                          const int2 *__restrict__ col2, const T *__restrict__ x, T *__restrict__ y,
-                                                          double *__restrict__ parts, const CgScalars *sc) {
-    if (sc && sc->done) return;
-    __shared__ double sh[CG_THREADS / 32 + 1];
-    const int lane = threadIdx.x & 31;
-    const long long warpsTotal = ((long long)gridDim.x * CG_THREADS) >> 5;
+// The slice loop shared by the stand-alone SpMV kernel and the persistent CG kernel.  NC = true gathers x through the
+// read-only path (ld.global.nc): only legal when x is not written during the kernel's lifetime, i.e. NOT inside the
+// persistent kernel, where p is rewritten every iteration by other CTAs (and by peers over NVLink).
+// The matrix as the SpMV kernels see it (passed by value).
+template <class T, class T2>
+struct SjdsView {
+    long long nrows, nslices;
+    const long long *sliceOff;   // in pairs
+    const int32_t *meta;
+    const T2 *val2;
+    const int2 *col2;
+};
+template <class T, class T2>
+static SjdsView<T, T2> sjdsView(const SellMatrix &A) {
+    SjdsView<T, T2> v;
+    v.nrows = A.n; v.nslices = A.nslices;
+    v.sliceOff = A.sliceOff.as<long long>(); v.meta = A.meta.as<int32_t>();
+    v.val2 = A.val.as<T2>(); v.col2 = A.col.as<int2>();
+    return v;
+}
+
+// One slice = 32 rows = one warp.  Returns the lane's contribution to x.y (row r of the slice, 0 when !DOT).
+// NC = true gathers x through the read-only path (ld.global.nc): only legal when x is not written during the kernel's
+// lifetime, i.e. NOT inside the persistent CG kernel, where p is rewritten every iteration by other CTAs (and by peers
+// over NVLink).
+template <class T, class T2, bool DOT, int SPMV_U, bool NC>
+__device__ __forceinline__ double spmvOneSlice(long long s, int lane, const SjdsView<T, T2> &A, const T *x, T *y) {
     double dot = 0;
-    for (long long s = ((long long)blockIdx.x * CG_THREADS + threadIdx.x) >> 5; s < nslices; s += warpsTotal) {
-        const int m = meta[s * 32 + lane];
+    {
+        const int m = A.meta[s * 32 + lane];
         const int np = m & 0xff;
         const long long r = s * 32 + (m >> 8);
-        const long long base = sliceOff[s] + lane;
+        const long long base = A.sliceOff[s] + lane;
         const int maxnp = __shfl_sync(0xffffffffu, np, 0);
         T acc = 0;
         long long off = 0;
@@ -296,13 +315,16 @@ __global__ void __launch_bounds__(CG_THREADS) k_spmv_sjds(long long nrows, long 
             for (int u = 0; u < SPMV_U; ++u) {
                 v[u].x = 0; v[u].y = 0;
                 cc[u].x = 0; cc[u].y = 0;
-                if (act[u]) { v[u] = val2[o[u]]; cc[u] = col2[o[u]]; }
+                if (act[u]) { v[u] = A.val2[o[u]]; cc[u] = A.col2[o[u]]; }
             }
             T xa[SPMV_U], xb[SPMV_U];
 #pragma unroll
             for (int u = 0; u < SPMV_U; ++u) {
                 xa[u] = 0; xb[u] = 0;
-                if (act[u]) { xa[u] = __ldg(x + cc[u].x); xb[u] = __ldg(x + cc[u].y); }
+                if (act[u]) {
+                    if (NC) { xa[u] = __ldg(x + cc[u].x); xb[u] = __ldg(x + cc[u].y); }
+                    else { xa[u] = x[cc[u].x]; xb[u] = x[cc[u].y]; }
+                }
             }
 #pragma unroll
             for (int u = 0; u < SPMV_U; ++u) {
@@ -310,11 +332,47 @@ __global__ void __launch_bounds__(CG_THREADS) k_spmv_sjds(long long nrows, long 
                 acc += v[u].y * xb[u];
             }
         }
-        if (r < nrows) {
+        if (r < A.nrows) {
             y[r] = acc;
-            if (DOT) dot += (double)__ldg(x + r) * (double)acc;
+            if (DOT) dot += (double)(NC ? __ldg(x + r) : x[r]) * (double)acc;
         }
     }
+    return dot;
+}
+// static schedule: warp w of the grid takes slices w, w + W, w + 2W, ...
+template <class T, class T2, bool DOT, int SPMV_U, bool NC>
+__device__ __forceinline__ double spmvSlices(const SjdsView<T, T2> &A, const T *x, T *y) {
+    const int lane = threadIdx.x & 31;
+    const long long warpsTotal = ((long long)gridDim.x * CG_THREADS) >> 5;
+    double dot = 0;
+    for (long long s = ((long long)blockIdx.x * CG_THREADS + threadIdx.x) >> 5; s < A.nslices; s += warpsTotal)
+        dot += spmvOneSlice<T, T2, DOT, SPMV_U, NC>(s, lane, A, x, y);
+    return dot;
+}
+// dynamic schedule: warps grab chunks of PCG_CHUNK consecutive slices from a global counter
+#define PCG_CHUNK 4
+template <class T, class T2, bool DOT, int SPMV_U, bool NC>
+__device__ __forceinline__ double spmvSlicesDynamic(const SjdsView<T, T2> &A, const T *x, T *y, unsigned long long *counter) {
+    const int lane = threadIdx.x & 31;
+    double dot = 0;
+    while (true) {
+        unsigned long long c = 0;
+        if (lane == 0) c = atomicAdd(counter, (unsigned long long)PCG_CHUNK);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if ((long long)c >= A.nslices) break;
+        const long long e = min((long long)c + PCG_CHUNK, A.nslices);
+        for (long long s = (long long)c; s < e; ++s)
+            dot += spmvOneSlice<T, T2, DOT, SPMV_U, NC>(s, lane, A, x, y);
+    }
+    return dot;
+}
+
+template <class T, class T2, bool DOT, int SPMV_U>
+__global__ void __launch_bounds__(CG_THREADS) k_spmv_sjds(const __grid_constant__ SjdsView<T, T2> A, const T *__restrict__ x, T *__restrict__ y,
+                                                          double *__restrict__ parts, const CgScalars *sc) {
+    if (sc && sc->done) return;
+    __shared__ double sh[CG_THREADS / 32 + 1];
+    double dot = spmvSlices<T, T2, DOT, SPMV_U, true>(A, x, y);
     if (DOT) {
         double t = blockSum(dot, sh);
         if (threadIdx.x == 0) parts[blockIdx.x] = t;
@@ -398,11 +456,14 @@ __device__ __forceinline__ T sliceRowSum(const T2 *__restrict__ v, const int2 *_
 }
 
 template <class T, class T2, bool DOT>
-__global__ void __launch_bounds__(TMA_THREADS, 1) k_spmv_tma(long long nrows, long long nslices, const long long *__restrict__ sliceOff,
-                                                             const int32_t *__restrict__ meta, const T2 *__restrict__ val2,
-                                                             const int2 *__restrict__ col2, const T *__restrict__ x, T *__restrict__ y,
+__global__ void __launch_bounds__(TMA_THREADS, 1) k_spmv_tma(const __grid_constant__ SjdsView<T, T2> A, const T *__restrict__ x, T *__restrict__ y,
                                                              double *__restrict__ parts, const CgScalars *sc) {
     if (sc && sc->done) return;
+    const long long nrows = A.nrows, nslices = A.nslices;
+    const long long *__restrict__ sliceOff = A.sliceOff;
+    const int32_t *__restrict__ meta = A.meta;
+    const T2 *__restrict__ val2 = A.val2;
+    const int2 *__restrict__ col2 = A.col2;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bar = (uint64_t *)smem;
     const size_t stageBytes = (size_t)TMA_CAP_PAIRS * (sizeof(T2) + sizeof(int2));
@@ -585,6 +646,273 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_update_p(long long n, const T
         p[i] = invDiag[i] * r[i] + b * p[i];
 }
 
+// ---- persistent CG kernel --------------------------------------------------------------------------
+// One cooperative launch runs the whole iteration loop: SpMV (+ p.Ap) | grid barrier | x,r update (+ r.r, r.z) | grid
+// barrier | convergence test, p update | grid barrier.  No kernel boundaries, no host polling, no iterations launched past
+// convergence: at ~1 M rows the three launches + gaps of the per-launch path cost as much as the SpMV itself, and at the
+// 1/8-of-C3 partitions of the 8-GPU run they are the floor (SURVEY.md section 7 "CG latency floor").  Every CTA finishes
+// the per-CTA partial sums itself, in the same fixed order, so all CTAs (and, multi-GPU, all ranks) hold bit-identical
+// scalars and take the same branches -- the Eigen loop of the header comment, unchanged.
+// Multi-GPU (peer-memory mode): the two scalar all-reduces and the halo exchange happen INSIDE this kernel over NVLink --
+// CTA 0 stores this rank's sums into every peer's mailbox and every CTA spins on its own mailbox; after the p update the
+// CTAs push the rows their peers need straight into the peers' halo slots, the last CTA to finish raises the peers' flags,
+// and the next SpMV waits for the flags of the ranks it receives from.
+// Memory visibility between phases comes from the barrier (release fence + atomic, acquire spin + fence: the pattern of
+// cooperative_groups' grid sync); p is gathered with ordinary loads, never ld.global.nc.
+struct PcgState {                 // device-resident, copied back by the host after every launch
+    unsigned long long seqPush, seqReduce;
+    unsigned long long phaseNs[3];    // accumulated %globaltimer time of the SpMV / x,r / p phases (CTA 0, barrier to barrier)
+    unsigned long long spmvPhases;    // SpMV phases executed
+    unsigned int barrier;             // grid barrier arrival counter (zeroed before every launch)
+    unsigned int pushArrivals;        // halo push arrival counter (zeroed before every launch)
+    unsigned long long work[2];       // dynamic SpMV schedule: next slice, double buffered by iteration parity (zeroed likewise)
+    int abort;                        // a spin loop timed out (peer died / co-residency broken): everybody leaves
+    int pad;
+};
+#define PCG_TIMEOUT_NS 8000000000ull
+
+__device__ __forceinline__ unsigned long long globalTimerNs() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned ldAcquireGpu(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ldVolatileU64(const unsigned long long *p) { return *(const volatile unsigned long long *)p; }
+
+// All CTAs of the (co-resident) grid.  Returns false when the launch is being aborted.
+__device__ __forceinline__ bool gridBarrier(PcgState *st, unsigned &target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(&st->barrier, 1u);
+        unsigned long long t0 = 0;
+        unsigned spins = 0;
+        while (ldAcquireGpu(&st->barrier) < target) {
+            if ((++spins & 0x3ff) == 0) {
+                if (*(volatile int *)&st->abort) break;
+                unsigned long long now = globalTimerNs();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > PCG_TIMEOUT_NS) { *(volatile int *)&st->abort = 1; break; }
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    return *(volatile int *)&st->abort == 0;
+}
+
+// v[0..COUNT) holds this rank's sums (the same bits in every CTA); on return it holds the sum over ranks, in rank order.
+template <int COUNT>
+__device__ __forceinline__ bool rankSum(double (&v)[COUNT], const PcgDist &D, unsigned long long seq, PcgState *st) {
+    const int par = (int)(seq & 1ull);
+    P2PHeader *mine = (P2PHeader *)D.peerRegion[D.myRank];
+    if (blockIdx.x == 0 && threadIdx.x < D.P) {
+        P2PHeader *peer = (P2PHeader *)D.peerRegion[threadIdx.x];
+#pragma unroll
+        for (int q = 0; q < COUNT; ++q) *(volatile double *)&peer->mail[par][D.myRank][q] = v[q];
+        __threadfence_system();
+        *(volatile unsigned long long *)&peer->flag[par][D.myRank] = seq;
+    }
+    if (threadIdx.x < D.P) {
+        unsigned long long t0 = 0;
+        unsigned spins = 0;
+        while (ldVolatileU64(&mine->flag[par][threadIdx.x]) != seq) {
+            if ((++spins & 0x3ff) == 0) {
+                if (*(volatile int *)&st->abort) break;
+                unsigned long long now = globalTimerNs();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > PCG_TIMEOUT_NS) { *(volatile int *)&st->abort = 1; break; }
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (*(volatile int *)&st->abort) return false;
+#pragma unroll
+    for (int q = 0; q < COUNT; ++q) {
+        double t = 0;
+        for (int r = 0; r < D.P; ++r) t += *(const volatile double *)&mine->mail[par][r][q];
+        v[q] = t;
+    }
+    return true;
+}
+
+// After the p update (and the barrier behind it): store the rows my peers need into their halo slots; the last CTA to
+// finish raises pushFlag[myRank] = seq in every peer I send to.
+template <class T>
+__device__ __forceinline__ void pushHalo(const T *p, const PcgDist &D, unsigned long long seq, PcgState *st, unsigned &pushTarget) {
+    for (long long i = (long long)blockIdx.x * CG_THREADS + threadIdx.x; i < D.nSend; i += (long long)gridDim.x * CG_THREADS) {
+        const int2 dst = D.sendDst[i];
+        T *peerP = (T *)((char *)D.peerRegion[dst.x] + P2P_HEADER_BYTES);
+        *(volatile T *)(peerP + dst.y) = p[D.sendIdx[i] - D.rowBegin];
+    }
+    __threadfence_system();
+    __syncthreads();
+    pushTarget += gridDim.x;
+    if (threadIdx.x == 0) {
+        unsigned prev = atomicAdd(&st->pushArrivals, 1u);
+        if (prev + 1 == pushTarget) {   // every CTA's stores are ordered before this point (fence + atomic chain)
+            __threadfence_system();
+            for (int q = 0; q < D.P; ++q)
+                if ((D.sendMask >> q) & 1u) {
+                    P2PHeader *peer = (P2PHeader *)D.peerRegion[q];
+                    *(volatile unsigned long long *)&peer->pushFlag[D.myRank] = seq;
+                }
+        }
+    }
+}
+__device__ __forceinline__ bool waitHalo(const PcgDist &D, unsigned long long seq, PcgState *st) {
+    if (threadIdx.x < D.P && ((D.recvMask >> threadIdx.x) & 1u)) {
+        const P2PHeader *mine = (const P2PHeader *)D.peerRegion[D.myRank];
+        unsigned long long t0 = 0;
+        unsigned spins = 0;
+        while (ldVolatileU64(&mine->pushFlag[threadIdx.x]) < seq) {
+            if ((++spins & 0x3ff) == 0) {
+                if (*(volatile int *)&st->abort) break;
+                unsigned long long now = globalTimerNs();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > PCG_TIMEOUT_NS) { *(volatile int *)&st->abort = 1; break; }
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    return *(volatile int *)&st->abort == 0;
+}
+
+template <class T, class T2>
+struct PcgArgs {
+    long long n;
+    SjdsView<T, T2> M;
+    const T *invDiag;
+    T *x, *r, *p, *t;
+    double *parts;       // 3 * gridDim.x: p.Ap | r.r | r.z
+    CgScalars *sc;
+    PcgState *st;
+    int itLimit;         // stop once sc->iters reaches this
+    int pushFirst;       // 1: the p vector of this launch's first SpMV has not been pushed to the peers yet
+    int dynamic;         // 1: warps take slices from a global counter instead of a fixed stride
+    PcgDist D;
+};
+
+template <class T, class T2, int SPMV_U, int MINB>
+__global__ void __launch_bounds__(CG_THREADS, MINB) k_cg_persistent(const __grid_constant__ PcgArgs<T, T2> A) {
+    __shared__ double sh[CG_THREADS / 32 + 1];
+    __shared__ unsigned long long tm[4];   // thread 0 of CTA 0: phase start stamp + 3 accumulators
+    __shared__ double rrLast;
+    CgScalars *sc = A.sc;
+    PcgState *st = A.st;
+    if (sc->done) return;       // uniform: written before the launch
+    const bool dist = A.D.P > 1;
+    const bool timer = blockIdx.x == 0 && threadIdx.x == 0;
+    const int G = gridDim.x;
+    double rho = sc->rho[0];
+    int iters = sc->iters;
+    int k = 0;                  // iterations started in this launch: sequence numbers derive from it
+    unsigned barTarget = 0, pushTarget = 0;
+    bool stop = false, breakdown = false;
+    if (timer) { tm[1] = tm[2] = tm[3] = 0; rrLast = sc->residualNorm2; }
+    // sequence numbers: reduce #(2k+1), #(2k+2) in iteration k; push #(pushFirst + k) feeds iteration k's SpMV
+    const unsigned long long seqPush0 = A.D.seqPush + (unsigned long long)A.pushFirst;
+
+    if (dist && A.pushFirst) pushHalo<T>(A.p, A.D, seqPush0, st, pushTarget);
+    while (iters < A.itLimit) {
+        if (timer) tm[0] = globalTimerNs();
+        // ---- t = A p, partial p.t
+        if (dist && !waitHalo(A.D, seqPush0 + k, st)) break;
+        {
+            double dot = A.dynamic
+                ? spmvSlicesDynamic<T, T2, true, SPMV_U, false>(A.M, A.p, A.t, &st->work[k & 1])
+                : spmvSlices<T, T2, true, SPMV_U, false>(A.M, A.p, A.t);
+            double s0 = blockSum(dot, sh);
+            if (threadIdx.x == 0) A.parts[blockIdx.x] = s0;
+        }
+        if (!gridBarrier(st, barTarget)) break;
+        if (timer) { unsigned long long now = globalTimerNs(); tm[1] += now - tm[0]; tm[0] = now; st->work[(k + 1) & 1] = 0; }
+        double pt[1] = {reduceParts(A.parts, G, sh)};
+        if (dist && !rankSum<1>(pt, A.D, A.D.seqReduce + 2ull * k + 1, st)) break;
+        const double alphaD = rho / pt[0];
+        breakdown = !isfinite(alphaD);
+        const T alpha = breakdown ? (T)0 : (T)alphaD;
+        // ---- x += alpha p, r -= alpha t, partial r.r and r.z
+        {
+            // two elements per thread and trip (one 128-bit access per vector for fp64): more bytes in flight per thread
+            double rr = 0, rz = 0;
+            const long long gid = (long long)blockIdx.x * CG_THREADS + threadIdx.x, gstride = (long long)G * CG_THREADS;
+            const long long n2 = A.n >> 1;
+            for (long long j = gid; j < n2; j += gstride) {
+                const T2 pv = ((const T2 *)A.p)[j], tv = ((const T2 *)A.t)[j], dv = ((const T2 *)A.invDiag)[j];
+                T2 rv = ((T2 *)A.r)[j], xv = ((T2 *)A.x)[j];
+                rv.x -= alpha * tv.x; rv.y -= alpha * tv.y;
+                xv.x += alpha * pv.x; xv.y += alpha * pv.y;
+                ((T2 *)A.x)[j] = xv;
+                ((T2 *)A.r)[j] = rv;
+                rr += (double)rv.x * (double)rv.x + (double)rv.y * (double)rv.y;
+                rz += (double)rv.x * (double)(T)(dv.x * rv.x) + (double)rv.y * (double)(T)(dv.y * rv.y);
+            }
+            if ((A.n & 1) && gid == 0) {
+                const long long i = A.n - 1;
+                T ri = A.r[i] - alpha * A.t[i];
+                A.x[i] += alpha * A.p[i];
+                A.r[i] = ri;
+                rr += (double)ri * (double)ri;
+                rz += (double)ri * (double)(T)(A.invDiag[i] * ri);
+            }
+            double s0 = blockSum(rr, sh), s1 = blockSum(rz, sh);
+            if (threadIdx.x == 0) { A.parts[G + blockIdx.x] = s0; A.parts[2 * G + blockIdx.x] = s1; }
+        }
+        if (!gridBarrier(st, barTarget)) break;
+        if (timer) { unsigned long long now = globalTimerNs(); tm[2] += now - tm[0]; tm[0] = now; }
+        double rs[2];
+        rs[0] = reduceParts(A.parts + G, G, sh);
+        rs[1] = reduceParts(A.parts + 2 * G, G, sh);
+        if (dist && !rankSum<2>(rs, A.D, A.D.seqReduce + 2ull * k + 2, st)) break;
+        ++k;
+        if (timer) rrLast = rs[0];
+        stop = (rs[0] < sc->threshold) || breakdown;
+        if (stop) break;                       // Eigen: break before ++i
+        // ---- p = z + beta p
+        const T beta = (T)(rs[1] / rho);
+        rho = rs[1];
+        ++iters;
+        {
+            const long long gid = (long long)blockIdx.x * CG_THREADS + threadIdx.x, gstride = (long long)G * CG_THREADS;
+            const long long n2 = A.n >> 1;
+            for (long long j = gid; j < n2; j += gstride) {
+                const T2 dv = ((const T2 *)A.invDiag)[j], rv = ((const T2 *)A.r)[j];
+                T2 pv = ((T2 *)A.p)[j];
+                pv.x = dv.x * rv.x + beta * pv.x;
+                pv.y = dv.y * rv.y + beta * pv.y;
+                ((T2 *)A.p)[j] = pv;
+            }
+            if ((A.n & 1) && gid == 0) { const long long i = A.n - 1; A.p[i] = A.invDiag[i] * A.r[i] + beta * A.p[i]; }
+        }
+        if (!gridBarrier(st, barTarget)) break;
+        if (dist) pushHalo<T>(A.p, A.D, seqPush0 + k, st, pushTarget);
+        if (timer) tm[3] += globalTimerNs() - tm[0];
+    }
+    if (timer) {
+        sc->rho[0] = rho;
+        sc->rho[1] = rho;
+        sc->iters = iters;
+        sc->residualNorm2 = rrLast;
+        if (breakdown) sc->breakdown = 1;
+        if (stop) sc->done = 1;
+        // k counts completed (SpMV, x/r) phase pairs; a stopped iteration did both reduces but no p update / push
+        st->seqReduce = A.D.seqReduce + 2ull * k;
+        st->seqPush = seqPush0 + (stop ? k - 1 : k);
+        st->phaseNs[0] += tm[1];
+        st->phaseNs[1] += tm[2];
+        st->phaseNs[2] += tm[3];
+        st->spmvPhases += k;
+    }
+}
+
 template <class T>
 __global__ void k_convert_in(long long n, const double *in, T *out) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -604,6 +932,28 @@ static int spmvU() {
         if (u != 2 && u != 4 && u != 8) u = 4;
     }
     return u;
+}
+// AVS_CG_MODE=launch selects the three-launches-per-iteration loop (kept for A/B measurements and for the NCCL fallback);
+// the default is the persistent cooperative kernel.
+static bool cgUsePersistent() {
+    static int t = -1;
+    if (t < 0) {
+        const char *e = getenv("AVS_CG_MODE");
+        t = (e && strcmp(e, "launch") == 0) ? 0 : 1;
+    }
+    return t == 1;
+}
+// AVS_PCG_MINB=5 selects the variant whose register allocation aims at 5 resident CTAs per SM (measured at C3: spills,
+// no faster than the default 4); AVS_PCG_DYN=1 the dynamic slice schedule (measured slower: 0.51 vs 0.46 ms per SpMV).
+template <class T, class T2>
+static const void *pcgKernel() {
+    static int minb = -1;
+    if (minb < 0) {
+        const char *e = getenv("AVS_PCG_MINB");
+        minb = e ? atoi(e) : 4;
+    }
+    if (minb == 5) return (const void *)k_cg_persistent<T, T2, 4, 5>;
+    return (const void *)k_cg_persistent<T, T2, 4, 4>;
 }
 static bool spmvUseTma() {
     static int t = -1;
@@ -631,12 +981,9 @@ static void launchSpmv(AvsContext *c, SellMatrix &A, const T *x, T *y, double *p
             cudaFuncSetAttribute(k_spmv_tma<T, T2, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             attrSet[DOT] = true;
         }
-        k_spmv_tma<T, T2, DOT><<<grid, TMA_THREADS, smem, c->stream>>>(A.n, A.nslices, A.sliceOff.as<long long>(), A.meta.as<int32_t>(),
-                                                                       A.val.as<T2>(), A.col.as<int2>(), x, y, parts, sc);
+        k_spmv_tma<T, T2, DOT><<<grid, TMA_THREADS, smem, c->stream>>>(sjdsView<T, T2>(A), x, y, parts, sc);
     } else {
-#define SPMV_LAUNCH(U)                                                                                                            \
-    k_spmv_sjds<T, T2, DOT, U><<<grid, CG_THREADS, 0, c->stream>>>(A.n, A.nslices, A.sliceOff.as<long long>(), A.meta.as<int32_t>(), \
-                                                                    A.val.as<T2>(), A.col.as<int2>(), x, y, parts, sc)
+#define SPMV_LAUNCH(U) k_spmv_sjds<T, T2, DOT, U><<<grid, CG_THREADS, 0, c->stream>>>(sjdsView<T, T2>(A), x, y, parts, sc)
         switch (spmvU()) {
             case 2: SPMV_LAUNCH(2); break;
             case 8: SPMV_LAUNCH(8); break;
@@ -688,13 +1035,25 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
     const int grid = cgGrid(c, n);
     const int sgrid = spmvGrid<T, T2>(c, A.nslices);
     const bool dist = c->dist != nullptr;
+    c->pcgUsed = false;
+    int pgrid = 0;   // persistent CG kernel: all CTAs co-resident (cooperative launch)
+    {
+        int perSM = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, pcgKernel<T, T2>(), CG_THREADS, 0);
+        if (e != cudaSuccess || perSM < 1) { cudaGetLastError(); perSM = 1; }
+        const char *env = getenv("AVS_PCG_CTAS_PER_SM");
+        if (env && atoi(env) >= 1) perSM = std::min(perSM, atoi(env));
+        long long want = std::max<long long>((A.nslices * 32 + CG_THREADS - 1) / CG_THREADS, 1);
+        pgrid = (int)std::min<long long>(want, (long long)c->numSMs * perSM);
+        if (dist) pgrid = (int)((long long)c->numSMs * perSM);   // every rank runs the flag logic even with few rows
+    }
     const long long nHalo = dist ? c->nHalo : 0;
     const size_t vb = (size_t)std::max<long long>(n, 1) * sizeof(T);
     if (w.x.reserve(vb) || w.r.reserve(vb) || w.t.reserve(vb)) return AVS_ERR_ALLOC;
     if (w.p.reserve((size_t)std::max<long long>(n + nHalo, 1) * sizeof(T))) return AVS_ERR_ALLOC;  // owned rows + halo slots
     DevBuf &bbuf = c->cgRhs;
     if (bbuf.reserve(vb)) return AVS_ERR_ALLOC;
-    if (w.partials.reserve(((size_t)grid * 3 + (size_t)sgrid + 16) * sizeof(double))) return AVS_ERR_ALLOC;
+    if (w.partials.reserve(((size_t)std::max(grid, pgrid) * 3 + (size_t)sgrid + 16) * sizeof(double))) return AVS_ERR_ALLOC;
     if (w.scalars.reserve(sizeof(CgScalars))) return AVS_ERR_ALLOC;
     T *x = w.x.as<T>(), *r = w.r.as<T>(), *pp = w.p.as<T>(), *t = w.t.as<T>(), *b = bbuf.as<T>();
     if (dist) {  // peer-memory mode: p lives in the region the peers have mapped
@@ -734,94 +1093,146 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
         k_cg_init_scalars<<<1, CG_THREADS, 0, c->stream>>>(parts, grid, p->tolerance, tiny, sc);
     c->launches += 2;
 
-    const int *doneFlag = (const int *)((const char *)sc + offsetof(CgScalars, done));
-    // (opt-in, AVS_L2_PERSIST=1: measured -1% on the SpMV but +19% on the x,r update at C3, net loss)
-    // Keep the SpMV's gathered vector resident in L2 while the matrix streams through: p is re-read ~17x per launch
-    // (once per non-zero), the matrix exactly once.  Persisting window on p, streaming everything else.
-    bool l2window = false;
-    {
-        const char *env = getenv("AVS_L2_PERSIST");
-        int maxPersist = 0, maxWindow = 0;
-        cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
-        cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
-        size_t bytes = (size_t)(n + nHalo) * sizeof(T);
-        if ((env && env[0] == '1') && maxPersist > 0 && maxWindow > 0 && bytes > 0) {
-            size_t setAside = std::min<size_t>((size_t)maxPersist, bytes);
-            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setAside);
+    const int maxIters = p->max_iterations;
+    CgScalars *hs = (CgScalars *)c->hostScalars;  // pinned
+    PcgDist pd;
+    const bool persistent = cgUsePersistent() && (!dist || avs_dist_pcg_args(c, &pd));
+    if (persistent) {
+        // ---- one cooperative launch per `check_every` iterations (default: all of them) -------------------------------
+        if (w.pcgState.reserve(sizeof(PcgState))) return AVS_ERR_ALLOC;
+        PcgState *st = w.pcgState.as<PcgState>();
+        PcgState *hst = (PcgState *)((char *)c->hostScalars + 256);
+        AVS_CUDA_CHECK(cudaMemsetAsync(st, 0, sizeof(PcgState), c->stream));
+        PcgArgs<T, T2> ka;
+        ka.n = n;
+        ka.M = sjdsView<T, T2>(A);
+        ka.invDiag = A.invDiag.as<T>();
+        ka.x = x; ka.r = r; ka.p = pp; ka.t = t;
+        ka.parts = parts; ka.sc = sc; ka.st = st;
+        ka.D = dist ? pd : PcgDist();
+        ka.pushFirst = 1;
+        { const char *env = getenv("AVS_PCG_DYN"); ka.dynamic = (env && env[0] == '1') ? 1 : 0; }
+        const int chunk = p->check_every > 0 ? p->check_every : (p->cancel ? 256 : maxIters);
+        int itersKnown = 0;
+        while (true) {
+            ka.itLimit = std::min(maxIters, itersKnown + std::max(chunk, 1));
+            void *kargs[] = {(void *)&ka};
+            AVS_CUDA_CHECK(cudaLaunchCooperativeKernel(pcgKernel<T, T2>(), dim3(pgrid), dim3(CG_THREADS), kargs, 0, c->stream));
+            ++c->launches;
+            AVS_CUDA_CHECK(cudaMemcpyAsync(&hs[0], sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, c->stream));
+            AVS_CUDA_CHECK(cudaMemcpyAsync(hst, st, sizeof(PcgState), cudaMemcpyDeviceToHost, c->stream));
+            AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            if (hst->abort) {
+                c->lastError = "persistent CG kernel timed out waiting for a grid barrier or a peer";
+                avs_set_last_error("k_cg_persistent (spin-wait timeout)", cudaErrorLaunchTimeout, __FILE__, __LINE__);
+                return AVS_ERR_CUDA;
+            }
+            itersKnown = hs[0].iters;
+            ka.pushFirst = 0;
+            ka.D.seqPush = hst->seqPush;
+            ka.D.seqReduce = hst->seqReduce;
+            if (hs[0].done || itersKnown >= maxIters) break;
+            if (p->cancel && *p->cancel) {
+                if (dist) avs_dist_pcg_commit(c, hst->seqPush, hst->seqReduce);
+                return AVS_ERR_CANCELLED;
+            }
+            // counters restart with every launch
+            AVS_CUDA_CHECK(cudaMemsetAsync((char *)st + offsetof(PcgState, barrier), 0, 2 * sizeof(unsigned int) + 2 * sizeof(unsigned long long), c->stream));
+        }
+        if (dist) avs_dist_pcg_commit(c, hst->seqPush, hst->seqReduce);
+        c->pcgSpmvMs = (float)(hst->phaseNs[0] * 1e-6);
+        c->pcgXrMs = (float)(hst->phaseNs[1] * 1e-6);
+        c->pcgPMs = (float)(hst->phaseNs[2] * 1e-6);
+        c->pcgPhases = (int64_t)hst->spmvPhases;
+        c->pcgUsed = true;
+    } else {
+        const int *doneFlag = (const int *)((const char *)sc + offsetof(CgScalars, done));
+        // (opt-in, AVS_L2_PERSIST=1: measured -1% on the SpMV but +19% on the x,r update at C3, net loss)
+        // Keep the SpMV's gathered vector resident in L2 while the matrix streams through: p is re-read ~17x per launch
+        // (once per non-zero), the matrix exactly once.  Persisting window on p, streaming everything else.
+        bool l2window = false;
+        {
+            const char *env = getenv("AVS_L2_PERSIST");
+            int maxPersist = 0, maxWindow = 0;
+            cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
+            cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+            size_t bytes = (size_t)(n + nHalo) * sizeof(T);
+            if ((env && env[0] == '1') && maxPersist > 0 && maxWindow > 0 && bytes > 0) {
+                size_t setAside = std::min<size_t>((size_t)maxPersist, bytes);
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setAside);
+                cudaStreamAttrValue attr;
+                memset(&attr, 0, sizeof(attr));
+                attr.accessPolicyWindow.base_ptr = (void *)pp;
+                attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)maxWindow);
+                attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)setAside / (double)attr.accessPolicyWindow.num_bytes);
+                attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                l2window = cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+                if (!l2window) cudaGetLastError();
+            }
+        }
+        int checkEvery = p->check_every > 0 ? p->check_every : 32;
+        int launched = 0;
+        bool done = false;
+        // the flag copy of batch k is awaited only after batch k+1 has been enqueued, so the GPU never idles
+        cudaEvent_t evPrev = nullptr;
+        int slot = 0;
+        while (!done) {
+            int batch = std::min(checkEvery, maxIters - launched);
+            for (int it = 0; it < batch; ++it) {
+                const int parity = (launched + it) & 1;
+                if (dist && (rcd = avs_dist_halo_exchange(c, pp, A.precision, doneFlag))) return rcd;
+                launchSpmv<T, T2, true>(c, A, pp, t, ptParts, sc, sgrid);
+                const double *ptSrc = ptParts, *rrSrc = parts;
+                int ptN = sgrid, rrN = grid;
+                if (dist) {
+                    if ((rcd = avs_dist_allreduce_parts(c, ptParts, sgrid, 1, red, doneFlag))) return rcd;
+                    ptSrc = red;
+                    ptN = 1;
+                }
+                cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+                if (c->timeSpmv && c->auxEventsUsed + 3 <= c->auxEvents.size()) {
+                    e0 = c->auxEvents[c->auxEventsUsed++]; e1 = c->auxEvents[c->auxEventsUsed++]; e2 = c->auxEvents[c->auxEventsUsed++];
+                    cudaEventRecord(e0, c->stream);
+                }
+                k_cg_update_xr<T><<<grid, CG_THREADS, 0, c->stream>>>(n, pp, t, A.invDiag.as<T>(), x, r, ptSrc, ptN, parts, grid, sc, parity);
+                if (e1) cudaEventRecord(e1, c->stream);
+                if (dist) {
+                    if ((rcd = avs_dist_allreduce_parts(c, parts, grid, 2, red + 1, doneFlag))) return rcd;
+                    rrSrc = red + 1;
+                    rrN = 1;
+                }
+                k_cg_update_p<T><<<grid, CG_THREADS, 0, c->stream>>>(n, r, A.invDiag.as<T>(), pp, rrSrc, rrN, sc, parity);
+                if (e2) cudaEventRecord(e2, c->stream);
+                c->launches += 3;
+            }
+            launched += batch;
+            AVS_CUDA_CHECK(cudaMemcpyAsync(&hs[slot], sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, c->stream));
+            AVS_CUDA_CHECK(cudaEventRecord(c->evPoll[slot], c->stream));
+            if (evPrev) {
+                AVS_CUDA_CHECK(cudaEventSynchronize(evPrev));
+                if (hs[slot ^ 1].done) done = true;
+            }
+            evPrev = c->evPoll[slot];
+            slot ^= 1;
+            if (launched >= maxIters || batch == 0) {
+                AVS_CUDA_CHECK(cudaEventSynchronize(evPrev));
+                break;
+            }
+            if (p->cancel && *p->cancel) {
+                AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+                return AVS_ERR_CANCELLED;
+            }
+        }
+        AVS_CUDA_CHECK(cudaMemcpyAsync(&hs[0], sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, c->stream));
+        AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (l2window) {
             cudaStreamAttrValue attr;
             memset(&attr, 0, sizeof(attr));
-            attr.accessPolicyWindow.base_ptr = (void *)pp;
-            attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)maxWindow);
-            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)setAside / (double)attr.accessPolicyWindow.num_bytes);
-            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            l2window = cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
-            if (!l2window) cudaGetLastError();
+            attr.accessPolicyWindow.num_bytes = 0;
+            cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+            cudaCtxResetPersistingL2Cache();
         }
-    }
-    const int maxIters = p->max_iterations;
-    int checkEvery = p->check_every > 0 ? p->check_every : 32;
-    CgScalars *hs = (CgScalars *)c->hostScalars;  // pinned
-    int launched = 0;
-    bool done = false;
-    // the flag copy of batch k is awaited only after batch k+1 has been enqueued, so the GPU never idles
-    cudaEvent_t evPrev = nullptr;
-    int slot = 0;
-    while (!done) {
-        int batch = std::min(checkEvery, maxIters - launched);
-        for (int it = 0; it < batch; ++it) {
-            const int parity = (launched + it) & 1;
-            if (dist && (rcd = avs_dist_halo_exchange(c, pp, A.precision, doneFlag))) return rcd;
-            launchSpmv<T, T2, true>(c, A, pp, t, ptParts, sc, sgrid);
-            const double *ptSrc = ptParts, *rrSrc = parts;
-            int ptN = sgrid, rrN = grid;
-            if (dist) {
-                if ((rcd = avs_dist_allreduce_parts(c, ptParts, sgrid, 1, red, doneFlag))) return rcd;
-                ptSrc = red;
-                ptN = 1;
-            }
-            cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
-            if (c->timeSpmv && c->auxEventsUsed + 3 <= c->auxEvents.size()) {
-                e0 = c->auxEvents[c->auxEventsUsed++]; e1 = c->auxEvents[c->auxEventsUsed++]; e2 = c->auxEvents[c->auxEventsUsed++];
-                cudaEventRecord(e0, c->stream);
-            }
-            k_cg_update_xr<T><<<grid, CG_THREADS, 0, c->stream>>>(n, pp, t, A.invDiag.as<T>(), x, r, ptSrc, ptN, parts, grid, sc, parity);
-            if (e1) cudaEventRecord(e1, c->stream);
-            if (dist) {
-                if ((rcd = avs_dist_allreduce_parts(c, parts, grid, 2, red + 1, doneFlag))) return rcd;
-                rrSrc = red + 1;
-                rrN = 1;
-            }
-            k_cg_update_p<T><<<grid, CG_THREADS, 0, c->stream>>>(n, r, A.invDiag.as<T>(), pp, rrSrc, rrN, sc, parity);
-            if (e2) cudaEventRecord(e2, c->stream);
-            c->launches += 3;
-        }
-        launched += batch;
-        AVS_CUDA_CHECK(cudaMemcpyAsync(&hs[slot], sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, c->stream));
-        AVS_CUDA_CHECK(cudaEventRecord(c->evPoll[slot], c->stream));
-        if (evPrev) {
-            AVS_CUDA_CHECK(cudaEventSynchronize(evPrev));
-            if (hs[slot ^ 1].done) done = true;
-        }
-        evPrev = c->evPoll[slot];
-        slot ^= 1;
-        if (launched >= maxIters || batch == 0) {
-            AVS_CUDA_CHECK(cudaEventSynchronize(evPrev));
-            break;
-        }
-        if (p->cancel && *p->cancel) {
-            AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-            return AVS_ERR_CANCELLED;
-        }
-    }
-    AVS_CUDA_CHECK(cudaMemcpyAsync(&hs[0], sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, c->stream));
-    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    if (l2window) {
-        cudaStreamAttrValue attr;
-        memset(&attr, 0, sizeof(attr));
-        attr.accessPolicyWindow.num_bytes = 0;
-        cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
-        cudaCtxResetPersistingL2Cache();
     }
     CgScalars fin = hs[0];
     if (fin.zeroRhs) {

@@ -54,6 +54,7 @@ struct CgWork {
     DevBuf x, r, p, t;      // CG vectors
     DevBuf partials;        // per-CTA partial sums
     DevBuf scalars;         // device-resident CG scalars
+    DevBuf pcgState;        // PcgState of the persistent CG kernel
 };
 
 struct AvsContext {
@@ -96,6 +97,7 @@ struct AvsContext {
     int levelsAllocated = 0;
     int64_t nRows = 0, nnz = 0, nEdge = 0, nCenter = 0, nRegular = 0;
     int64_t rowBegin = 0, rowEnd = 0;  // rows owned by this rank
+    std::vector<int> slabZ;            // [nranks+1] z-plane cuts of the regular grid (stage 4 labels + stage 11 are slab-sharded)
     std::vector<long long> rowStarts;  // [nranks+1] first row of every rank's block (brick-granular, cost-balanced, identical on all ranks)
 
     SellMatrix A;
@@ -109,6 +111,10 @@ struct AvsContext {
     size_t auxEventsUsed = 0;
 
     int64_t launches = 0, spmvLaunches = 0;
+    // persistent CG kernel: phase times measured in-kernel (%globaltimer, barrier to barrier)
+    bool pcgUsed = false;
+    float pcgSpmvMs = 0.f, pcgXrMs = 0.f, pcgPMs = 0.f;
+    int64_t pcgPhases = 0;
     float spmvMs = 0.f;
     cudaEvent_t ev[AVS_STAGE_COUNT + 2] = {};
 };
@@ -119,6 +125,8 @@ int avs_stage_weights(AvsContext *c, const AvsParams *p);
 int avs_stage_octree(AvsContext *c, const AvsParams *p);
 int avs_stage_regular_labels(AvsContext *c);
 int avs_octree_points(AvsContext *c, int64_t *countOut);
+int avs_slab_cuts(AvsContext *c);
+void avs_slab_range(const AvsContext *c, int axis, int q, int *z0, int *z1);
 int avs_stage_octree_labels(AvsContext *c);
 int avs_stage_restriction(AvsContext *c);
 int avs_stage_system(AvsContext *c, const AvsParams *p);
@@ -139,8 +147,13 @@ int avs_dist_build_halo(AvsContext *c);
 int avs_dist_halo_exchange(AvsContext *c, void *p, int precision, const int *done);
 void *avs_dist_prepare_p(AvsContext *c, int *rcOut);
 int avs_dist_mode(AvsContext *c);
+struct PcgDist;
+bool avs_dist_pcg_args(AvsContext *c, PcgDist *out);
+void avs_dist_pcg_commit(AvsContext *c, unsigned long long seqPush, unsigned long long seqReduce);
 int avs_dist_allreduce_parts(AvsContext *c, const double *parts, int nparts, int count, double *out, const int *done);
 int avs_dist_allgather_solution(AvsContext *c, const double *local, double *full);
+int avs_dist_allreduce_u64(AvsContext *c, unsigned long long *d, int count);   // in-place sum over ranks (setup paths only)
+int avs_dist_allgather_slabs(AvsContext *c, float *dOut[3]);                  // every rank's z-slab of the regular output -> all ranks
 int avs_spmv_time(AvsContext *c, SellMatrix &A, int repeats, float *msPerLaunch);
 int avs_spmv_once(AvsContext *c, SellMatrix &A, const double *dX, double *dY);
 

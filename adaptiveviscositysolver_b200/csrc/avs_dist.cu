@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "avs_context.h"
+#include "avs_p2p.cuh"
 
 struct NcclApi {
     void *handle = nullptr;
@@ -79,16 +80,6 @@ static bool loadNccl() {
 // and maps the regions of all peers.  The hot loop then needs no NCCL call: halo values are LOADED from the owners'
 // p vectors over NVLink by k_p2p_halo_pull, and the scalar all-reduce is P remote STORES into the peers' mailboxes
 // followed by a local spin (k_p2p_allreduce) -- both inside our own kernels.
-#define P2P_MAX_RANKS 16
-#define P2P_HEADER_BYTES 8192
-struct P2PHeader {
-    unsigned long long ready;                               // sequence number of the p vector that is complete
-    unsigned long long pad[15];
-    unsigned long long flag[2][P2P_MAX_RANKS];              // mailbox sequence flags, written by the peers
-    double mail[2][P2P_MAX_RANKS][4];                       // mailbox payload (<= 3 doubles used)
-};
-static_assert(sizeof(P2PHeader) <= P2P_HEADER_BYTES, "header too large");
-
 struct DistState {
     ncclComm_t comm = nullptr;
     // peer-memory mode
@@ -98,7 +89,9 @@ struct DistState {
     void *peerRegion[P2P_MAX_RANKS] = {};  // mapped regions (peerRegion[rank] == region)
     DevBuf peerTable;                      // device copy of peerRegion[]
     DevBuf haloSrc;                        // int2 per halo slot: (owner rank, index in the owner's p)
-    unsigned long long seqReady = 0, seqReduce = 0;
+    unsigned long long seqReady = 0, seqReduce = 0, seqPush = 0;
+    DevBuf sendDst;                        // int2 per send entry: (peer, element index in the peer's p) -- push mode
+    std::vector<int32_t> allCounts;        // P x P: allCounts[q*P + o] = halo values rank q needs from owner o
     DevBuf flag, index, haloCols, sendIdx, sendBuf, counts, scal;
     std::vector<int> recvCnt, recvOff, sendCnt, sendOff;
     long long nHalo = 0, nSend = 0;
@@ -142,7 +135,7 @@ void avs_dist_destroy(AvsContext *c) {
     if (d->region) cudaFree(d->region);
     d->peerTable.release();
     d->haloSrc.release();
-    DevBuf *bufs[] = {&d->flag, &d->index, &d->haloCols, &d->sendIdx, &d->sendBuf, &d->counts, &d->scal};
+    DevBuf *bufs[] = {&d->flag, &d->index, &d->haloCols, &d->sendIdx, &d->sendBuf, &d->counts, &d->scal, &d->sendDst};
     for (DevBuf *b : bufs) b->release();
     delete d;
     c->dist = nullptr;
@@ -230,7 +223,8 @@ int avs_dist_build_halo(AvsContext *c) {
     int32_t *dMine = d->counts.as<int32_t>() + (size_t)P * P;
     AVS_CUDA_CHECK(cudaMemcpyAsync(dMine, d->recvCnt.data(), (size_t)P * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     NCCL_CHECK(c, g_nccl.AllGather(dMine, d->counts.p, (size_t)P, ncclInt32, d->comm, c->stream));
-    std::vector<int32_t> all((size_t)P * P);
+    std::vector<int32_t> &all = d->allCounts;
+    all.assign((size_t)P * P, 0);
     AVS_CUDA_CHECK(cudaMemcpyAsync(all.data(), d->counts.p, (size_t)P * P * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     long long nSend = 0;
@@ -358,6 +352,7 @@ static int p2pEnsureRegion(AvsContext *c, size_t elems) {
     AVS_CUDA_CHECK(cudaMemsetAsync(d->region, 0, P2P_HEADER_BYTES, c->stream));
     d->seqReady = 0;
     d->seqReduce = 0;
+    d->seqPush = 0;
     // exchange IPC handles
     cudaIpcMemHandle_t mine;
     AVS_CUDA_CHECK(cudaIpcGetMemHandle(&mine, d->region));
@@ -392,6 +387,15 @@ static int p2pEnsureRegion(AvsContext *c, size_t elems) {
     return AVS_OK;
 }
 
+struct SendTable { int off[P2P_MAX_RANKS + 1]; long long base[P2P_MAX_RANKS]; };
+__global__ void k_send_dst(long long nSend, const __grid_constant__ SendTable st, int P, int2 *dst) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nSend) return;
+    int q = 0;
+    while (q + 1 < P && st.off[q + 1] <= i) ++q;
+    dst[i] = make_int2(q, (int)(st.base[q] + (i - st.off[q])));
+}
+
 // Called once per solve after the halo is known.  Returns the p vector the CG must use (inside the exported region)
 // or nullptr when the NCCL path is active.
 void *avs_dist_prepare_p(AvsContext *c, int *rcOut) {
@@ -410,7 +414,52 @@ void *avs_dist_prepare_p(AvsContext *c, int *rcOut) {
                                                                                  d->haloSrc.as<int2>());
         ++c->launches;
     }
+    // push mode (persistent CG kernel): where every value of my send list lands in its consumer's p vector.
+    // Rank q keeps its halo slots sorted by global column, i.e. grouped by owner; my block starts at slot
+    // sum_{o < me} allCounts[q*P + o] and holds my send list for q in the same order (avs_dist_build_halo).
+    if (d->sendDst.reserve((size_t)std::max<long long>(d->nSend, 1) * sizeof(int2))) { *rcOut = AVS_ERR_ALLOC; return nullptr; }
+    if (d->nSend > 0) {
+        SendTable st;
+        for (int q = 0; q < c->nranks; ++q) {
+            long long slot0 = 0;
+            for (int o = 0; o < c->rank; ++o) slot0 += d->allCounts[(size_t)q * c->nranks + o];
+            st.off[q] = d->sendOff[q];
+            st.base[q] = (c->rowStarts[q + 1] - c->rowStarts[q]) + slot0;
+        }
+        st.off[c->nranks] = d->sendOff[c->nranks];
+        k_send_dst<<<(unsigned)((d->nSend + 255) / 256), 256, 0, c->stream>>>(d->nSend, st, c->nranks, d->sendDst.as<int2>());
+        ++c->launches;
+    }
     return (char *)d->region + P2P_HEADER_BYTES;
+}
+
+// Everything the persistent CG kernel needs for its in-kernel exchanges; false when the peer-memory mode is off.
+bool avs_dist_pcg_args(AvsContext *c, PcgDist *out) {
+    DistState *d = (DistState *)c->dist;
+    if (!d || !d->p2p || !d->region) return false;
+    PcgDist a;
+    a.P = c->nranks;
+    a.myRank = c->rank;
+    a.peerRegion = d->peerTable.as<void *>();
+    a.sendIdx = d->sendIdx.as<int32_t>();
+    a.sendDst = d->sendDst.as<int2>();
+    a.nSend = d->nSend;
+    a.rowBegin = c->rowBegin;
+    for (int q = 0; q < c->nranks; ++q) {
+        if (q == c->rank) continue;
+        if (d->recvCnt[q] > 0) a.recvMask |= 1u << q;
+        if (d->sendCnt[q] > 0) a.sendMask |= 1u << q;
+    }
+    a.seqPush = d->seqPush;
+    a.seqReduce = d->seqReduce;
+    *out = a;
+    return true;
+}
+void avs_dist_pcg_commit(AvsContext *c, unsigned long long seqPush, unsigned long long seqReduce) {
+    DistState *d = (DistState *)c->dist;
+    if (!d) return;
+    d->seqPush = seqPush;
+    d->seqReduce = seqReduce;
 }
 
 // p[nLocal + slot] <- owner's p for every halo slot
@@ -481,6 +530,34 @@ int avs_dist_allgather_solution(AvsContext *c, const double *local, double *full
     for (int q = 0; q < P; ++q) {
         long long b = c->rowStarts[q], e = c->rowStarts[q + 1];
         if (e > b) NCCL_CHECK(c, g_nccl.Broadcast(full + b, full + b, (size_t)(e - b), ncclFloat64, q, d->comm, c->stream));
+    }
+    NCCL_CHECK(c, g_nccl.GroupEnd());
+    return AVS_OK;
+}
+
+int avs_dist_allreduce_u64(AvsContext *c, unsigned long long *d, int count) {
+    DistState *ds = (DistState *)c->dist;
+    if (!ds) return AVS_OK;
+    NCCL_CHECK(c, g_nccl.AllReduce(d, d, (size_t)count, ncclUint64, ncclSum, ds->comm, c->stream));
+    return AVS_OK;
+}
+
+// Stage 11 is sharded by z-slabs of the regular grid (avs_slab_cuts): rank q has filled planes [z0_q, z1_q) of every axis.
+// In-place broadcasts from the owners, grouped: after this every rank holds the whole velocity field (solveGasSubclass
+// updates `vel` in place, AV.cpp:698 -- a caller on any rank sees the complete result).
+int avs_dist_allgather_slabs(AvsContext *c, float *dOut[3]) {
+    DistState *ds = (DistState *)c->dist;
+    if (!ds) return AVS_OK;
+    NCCL_CHECK(c, g_nccl.GroupStart());
+    for (int a = 0; a < 3; ++a) {
+        const size_t plane = (size_t)c->S.regular[a].n[0] * c->S.regular[a].n[1];
+        for (int q = 0; q < c->nranks; ++q) {
+            int z0, z1;
+            avs_slab_range(c, a, q, &z0, &z1);
+            if (z1 <= z0) continue;
+            float *ptr = dOut[a] + plane * (size_t)z0;
+            NCCL_CHECK(c, g_nccl.Broadcast(ptr, ptr, plane * (size_t)(z1 - z0), ncclFloat32, q, ds->comm, c->stream));
+        }
     }
     NCCL_CHECK(c, g_nccl.GroupEnd());
     return AVS_OK;

@@ -49,6 +49,14 @@ __device__ __forceinline__ void forCells(const int n[3], F f) {
     }
 }
 
+// z-window variant: blockIdx.z counts planes from zOff (multi-GPU z-slabs of the regular grid)
+template <class F>
+__device__ __forceinline__ void forCellsZ(const int n[3], int zOff, F f) {
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z + zOff;
+    if (z >= n[2]) return;
+    f(x, y, z, (size_t)x + (size_t)n[0] * ((size_t)y + (size_t)n[1] * (size_t)z), x < n[0]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Stage 1: computeSDFWeightsSampled restated: fraction of the n^3 sub-samples at
 // offsets ((k+1/2)/n - 1/2) dx whose interpolated sdf (minus dilate) is negative.
@@ -498,9 +506,9 @@ __device__ __forceinline__ bool faceHasWeight(const DeviceScene &S, const I3 &fa
 }
 
 // classifyRegularVelocityFaces (AV.cpp:1087-1165)
-__global__ void k_classify_regular(const __grid_constant__ DeviceScene S, int axis, Grid3<uint8_t> tiles) {
+__global__ void k_classify_regular(const __grid_constant__ DeviceScene S, int axis, Grid3<uint8_t> tiles, int zOff) {
     const Grid3<int8_t> g = S.regular[axis];
-    forCells(g.n, [&](int x, int y, int z, size_t idx, bool ok) {
+    forCellsZ(g.n, zOff, [&](int x, int y, int z, size_t idx, bool ok) {
     const bool in = ok;
     int8_t out = F_UNASSIGNED;
     if (in) {
@@ -642,11 +650,76 @@ int avs_stage_regular_labels(AvsContext *c) {
     unsigned long long *cnt = c->counters.as<unsigned long long>();
     AVS_CUDA_CHECK(cudaMemsetAsync(cnt + 16, 0, 3 * sizeof(unsigned long long), c->stream));
     LAUNCH_3D(c, k_mark_surface_tiles, S.N, S, t[0], t[1], t[2]);
-    for (int a = 0; a < 3; ++a) LAUNCH_3D(c, k_classify_regular, S.regular[a].n, S, a, t[a]);
-    // regular DOF count (most of the liquid volume: a fused per-warp atomic would serialise on one address)
-    for (int a = 0; a < 3; ++a)
-        LAUNCH_1D(c, k_count_equal<int8_t>, S.regular[a].count(), S.regular[a].d, S.regular[a].count(), (int8_t)F_FLUID, cnt + 16);
+    // Multi-GPU: the regular grid is only read by stage 11 (which regular faces are written back, AV.cpp:2843-2890) and by
+    // the regular DOF count, both per-face work with no coupling -- so every rank classifies, and later fills, only its own
+    // slab of z-planes (avs_slab_cuts); the count is summed over ranks, the output slabs are all-gathered after stage 11.
+    int rc2 = avs_slab_cuts(c);
+    if (rc2) return rc2;
+    for (int a = 0; a < 3; ++a) {
+        int z0, z1;
+        avs_slab_range(c, a, c->rank, &z0, &z1);
+        if (z1 <= z0) continue;
+        dim3 g((unsigned)((S.regular[a].n[0] + 127) / 128), (unsigned)S.regular[a].n[1], (unsigned)(z1 - z0));
+        k_classify_regular<<<g, 128, 0, c->stream>>>(S, a, t[a], z0);
+        ++c->launches;
+        // regular DOF count (most of the liquid volume: a fused per-warp atomic would serialise on one address)
+        const size_t plane = (size_t)S.regular[a].n[0] * S.regular[a].n[1];
+        const size_t cntCells = plane * (size_t)(z1 - z0);
+        LAUNCH_1D(c, k_count_equal<int8_t>, cntCells, S.regular[a].d + plane * (size_t)z0, cntCells, (int8_t)F_FLUID, cnt + 16);
+    }
+    if (c->nranks > 1 && (rc2 = avs_dist_allreduce_u64(c, cnt + 16, 1))) return rc2;
     return AVS_OK;
+}
+
+// ---- z-slabs of the regular grid (multi-GPU) ---------------------------------------------------------------------
+// Liquid cells per z-plane of the surface field: the weight of a plane in stage 11 (faces inside the liquid are the ones
+// that get copied or interpolated).
+__global__ void k_plane_liquid(DField surface, unsigned long long *planeCount) {
+    const int z = (int)blockIdx.x;
+    int cnt = 0;
+    const size_t base = (size_t)surface.n[0] * surface.n[1] * (size_t)z;
+    const size_t plane = (size_t)surface.n[0] * surface.n[1];
+    for (size_t i = (size_t)blockIdx.y * blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.y * blockDim.x)
+        cnt += surface.d[base + i] < 0.f;
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(planeCount + z, (unsigned long long)cnt);
+}
+
+// slabZ[q] .. slabZ[q+1] = cell planes of rank q.  Identical on every rank (integer counts of identical inputs).
+int avs_slab_cuts(AvsContext *c) {
+    const int P = c->nranks, nz = c->S.N[2];
+    c->slabZ.assign(P + 1, 0);
+    c->slabZ[P] = nz;
+    if (P == 1) return AVS_OK;
+    std::vector<unsigned long long> h(nz, 0);
+    if (c->S.surface.d) {
+        if (c->scanTmp.reserve((size_t)nz * sizeof(unsigned long long))) return AVS_ERR_ALLOC;
+        unsigned long long *d = c->scanTmp.as<unsigned long long>();
+        AVS_CUDA_CHECK(cudaMemsetAsync(d, 0, (size_t)nz * sizeof(unsigned long long), c->stream));
+        k_plane_liquid<<<dim3((unsigned)nz, 16), 256, 0, c->stream>>>(c->S.surface, d);
+        ++c->launches;
+        AVS_CUDA_CHECK(cudaMemcpyAsync(h.data(), d, (size_t)nz * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+    // every plane also costs one streaming pass over its labels: a floor of 2 % of a full plane keeps empty regions cheap but not free
+    const unsigned long long floorW = std::max<unsigned long long>(1, (unsigned long long)c->S.N[0] * c->S.N[1] / 50);
+    unsigned long long total = 0;
+    for (int z = 0; z < nz; ++z) { h[z] += floorW; total += h[z]; }
+    unsigned long long run = 0;
+    int q = 1;
+    for (int z = 0; z < nz && q < P; ++z) {
+        run += h[z];
+        while (q < P && run * (unsigned long long)P >= total * (unsigned long long)q) c->slabZ[q++] = z + 1;
+    }
+    for (; q < P; ++q) c->slabZ[q] = nz;
+    return AVS_OK;
+}
+// planes [z0, z1) of the axis-`axis` face grid that rank q owns (the z-face grid has one more plane: the last rank takes it)
+void avs_slab_range(const AvsContext *c, int axis, int q, int *z0, int *z1) {
+    const int P = c->nranks;
+    if (P == 1 || c->slabZ.size() != (size_t)P + 1) { *z0 = 0; *z1 = c->S.regular[axis].n[2]; return; }
+    *z0 = c->slabZ[q];
+    *z1 = (q == P - 1) ? c->S.regular[axis].n[2] : c->slabZ[q + 1];
 }
 
 // ---- DOF numbering: count -> scan -> assign over 8^3-cell bricks in Morton order -----------------

@@ -274,9 +274,9 @@ __device__ double interpSPGrid(const DeviceScene &S, const NodeScene &NS, const 
 
 // applyVelocitiesToRegularGrid (AV.cpp:2815-2894)
 __global__ void k_apply_regular(const __grid_constant__ DeviceScene S, const NodeScene *NS, int axis, const double *sol, float *out,
-                                unsigned long long *interpolated) {
+                                unsigned long long *interpolated, int zOff) {
     const Grid3<int8_t> g = S.regular[axis];
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z + zOff;
     bool interp = false;
     if (x < g.n[0]) {
         const size_t idx = g.lin(x, y, z);
@@ -362,9 +362,18 @@ int avs_apply_regular(AvsContext *c, float *dOut[3], unsigned long long *hostInt
     AVS_CUDA_CHECK(cudaMemcpyAsync(c->nodeScene.p, &NS, sizeof(NS), cudaMemcpyHostToDevice, c->stream));
     unsigned long long *cnt = c->counters.as<unsigned long long>() + 26;
     AVS_CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
-    for (int a = 0; a < 3; ++a) {
-        k_apply_regular<<<grid3(S.regular[a].n), 128, 0, c->stream>>>(S, c->nodeScene.as<NodeScene>(), a, sol, dOut[a], cnt);
+    for (int a = 0; a < 3; ++a) {   // multi-GPU: only this rank's z-slab (the caller all-gathers the slabs)
+        int z0, z1;
+        avs_slab_range(c, a, c->rank, &z0, &z1);
+        if (z1 <= z0) continue;
+        dim3 g((unsigned)((S.regular[a].n[0] + 127) / 128), (unsigned)S.regular[a].n[1], (unsigned)(z1 - z0));
+        k_apply_regular<<<g, 128, 0, c->stream>>>(S, c->nodeScene.as<NodeScene>(), a, sol, dOut[a], cnt, z0);
         ++c->launches;
+    }
+    if (c->nranks > 1) {
+        int rcd = avs_dist_allreduce_u64(c, cnt, 1);
+        if (rcd) return rcd;
+        if ((rcd = avs_dist_allgather_slabs(c, dOut))) return rcd;
     }
     AVS_CUDA_CHECK(cudaMemcpyAsync(hostInterpolated, cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));  // also keeps the stack copy of NS alive until the H2D copy is done

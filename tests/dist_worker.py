@@ -29,7 +29,11 @@ def main():
         sc = sphere_drop(n, R, noise=0.01)
         tol = 1e-10
         out = [v.data.copy() for v in sc.vel]
+        # chunked relaunches of the persistent CG kernel (check_every iterations per cooperative launch) must not change a bit
+        s.solve(sc, Params(octree_levels=L, tolerance=tol, check_every=5))
+        x_chunked = s.solution()
         info = s.solve(sc, Params(octree_levels=L, tolerance=tol), out)
+        assert np.array_equal(x_chunked, s.solution()), "chunked and single-launch CG differ"
         rb, re = s.local_range()
         starts = s.row_starts(world)
         assert (rb, re) == (starts[rank], starts[rank + 1]) and starts[0] == 0 and starts[-1] == info.octree_dofs

@@ -14,13 +14,23 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
+@pytest.mark.parametrize("mode", ["persistent", "launch", "nccl"])
 @pytest.mark.parametrize("world", [2])
-def test_multi_gpu_solve_matches_oracle(world):
+def test_multi_gpu_solve_matches_oracle(world, mode):
+    """persistent: in-kernel halo push + scalar all-reduce over peer memory (default); launch: one kernel per step with
+    the peer-memory exchange kernels (AVS_CG_MODE=launch); nccl: grouped send/recv + ncclAllReduce (AVS_DIST_MODE=nccl)."""
+    import os
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), str(ROOT / "tests" / "dist_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(ROOT))
+    env = dict(os.environ)
+    env.pop("AVS_CG_MODE", None); env.pop("AVS_DIST_MODE", None)
+    if mode == "launch":
+        env["AVS_CG_MODE"] = "launch"
+    if mode == "nccl":
+        env["AVS_DIST_MODE"] = "nccl"
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(ROOT), env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "[dist_worker]" in r.stdout
