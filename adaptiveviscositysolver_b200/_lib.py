@@ -57,7 +57,7 @@ class AvsResult(C.Structure):
                 ("stage_ms", C.c_float * AVS_STAGE_COUNT), ("spmv_ms", C.c_float),
                 ("cg_update_xr_ms", C.c_float), ("cg_update_p_ms", C.c_float),
                 ("dist_mode", C.c_int32), ("reserved0", C.c_int32), ("halo_columns", C.c_int64),
-                ("interpolated_faces", C.c_int64)]
+                ("interpolated_faces", C.c_int64), ("cg_kernel_ms", C.c_float), ("cg_kernel_launches", C.c_int32)]
 
 
 class AvsDeviceConfig(C.Structure):

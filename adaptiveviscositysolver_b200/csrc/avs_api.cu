@@ -88,6 +88,8 @@ int avs_create(const AvsDeviceConfig *cfg, AvsContext **out) {
     cudaEventCreateWithFlags(&c->evUploadDone, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->evPoll[0], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->evPoll[1], cudaEventDisableTiming);
+    cudaEventCreate(&c->evPcg[0]);
+    cudaEventCreate(&c->evPcg[1]);
     if (cudaHostAlloc(&c->hostScalars, 512, cudaHostAllocDefault) != cudaSuccess) { delete c; return AVS_ERR_ALLOC; }
     if (c->timeSpmv) {
         c->spmvEvents.resize(2 * 4096);
@@ -132,6 +134,7 @@ void avs_destroy(AvsContext *c) {
     }
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->evPoll) if (e) cudaEventDestroy(e);
+    for (auto &e : c->evPcg) if (e) cudaEventDestroy(e);
     for (auto &e : c->spmvEvents) if (e) cudaEventDestroy(e);
     for (auto &e : c->auxEvents) if (e) cudaEventDestroy(e);
     if (c->evCopyGate) cudaEventDestroy(c->evCopyGate);
@@ -294,6 +297,8 @@ static int runSolve(AvsContext *c, const AvsParams *p, AvsResult *res) {
     if (c->solution.reserve((size_t)std::max<long long>(n, 1) * sizeof(double))) return AVS_ERR_ALLOC;
     c->spmvEventsUsed = 0;
     c->auxEventsUsed = 0;
+    res->cg_kernel_ms = 0.f;
+    res->cg_kernel_launches = 0;
     c->spmvMs = 0;
     const int64_t spmv0 = c->spmvLaunches;
     cudaEventRecord(c->ev[AVS_STAGE_SOLVE], c->stream);
@@ -308,6 +313,8 @@ static int runSolve(AvsContext *c, const AvsParams *p, AvsResult *res) {
         res->spmv_launches = c->pcgPhases;
         res->cg_update_xr_ms = c->pcgXrMs;
         res->cg_update_p_ms = c->pcgPMs;
+        res->cg_kernel_ms = c->pcgKernelMs;
+        res->cg_kernel_launches = c->pcgLaunches;
     } else if (c->timeSpmv) {
         const size_t pairs = std::min<size_t>(c->spmvEventsUsed / 2, (size_t)(realCg + 1));
         float total = 0;

@@ -1036,6 +1036,8 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
     const int sgrid = spmvGrid<T, T2>(c, A.nslices);
     const bool dist = c->dist != nullptr;
     c->pcgUsed = false;
+    c->pcgKernelMs = 0.f;
+    c->pcgLaunches = 0;
     int pgrid = 0;   // persistent CG kernel: all CTAs co-resident (cooperative launch)
     {
         int perSM = 0;
@@ -1117,11 +1119,18 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
         while (true) {
             ka.itLimit = std::min(maxIters, itersKnown + std::max(chunk, 1));
             void *kargs[] = {(void *)&ka};
+            AVS_CUDA_CHECK(cudaEventRecord(c->evPcg[0], c->stream));
             AVS_CUDA_CHECK(cudaLaunchCooperativeKernel(pcgKernel<T, T2>(), dim3(pgrid), dim3(CG_THREADS), kargs, 0, c->stream));
+            AVS_CUDA_CHECK(cudaEventRecord(c->evPcg[1], c->stream));
             ++c->launches;
+            ++c->pcgLaunches;
             AVS_CUDA_CHECK(cudaMemcpyAsync(&hs[0], sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, c->stream));
             AVS_CUDA_CHECK(cudaMemcpyAsync(hst, st, sizeof(PcgState), cudaMemcpyDeviceToHost, c->stream));
             AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            {
+                float ms = 0;
+                if (cudaEventElapsedTime(&ms, c->evPcg[0], c->evPcg[1]) == cudaSuccess) c->pcgKernelMs += ms;
+            }
             if (hst->abort) {
                 c->lastError = "persistent CG kernel timed out waiting for a grid barrier or a peer";
                 avs_set_last_error("k_cg_persistent (spin-wait timeout)", cudaErrorLaunchTimeout, __FILE__, __LINE__);

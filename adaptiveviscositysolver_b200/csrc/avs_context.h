@@ -114,6 +114,9 @@ struct AvsContext {
     // persistent CG kernel: phase times measured in-kernel (%globaltimer, barrier to barrier)
     bool pcgUsed = false;
     float pcgSpmvMs = 0.f, pcgXrMs = 0.f, pcgPMs = 0.f;
+    float pcgKernelMs = 0.f;          // CUDA events around the cooperative launches
+    int pcgLaunches = 0;
+    cudaEvent_t evPcg[2] = {};
     int64_t pcgPhases = 0;
     float spmvMs = 0.f;
     cudaEvent_t ev[AVS_STAGE_COUNT + 2] = {};

@@ -78,6 +78,8 @@ class SolveInfo:
     cg_update_p_ms: float = 0.0
     dist_mode: int = 0
     halo_columns: int = 0
+    cg_kernel_ms: float = 0.0       # persistent CG kernel: CUDA events around its cooperative launch(es)
+    cg_kernel_launches: int = 0
 
     @staticmethod
     def from_c(r: AvsResult) -> "SolveInfo":
@@ -85,7 +87,7 @@ class SolveInfo:
                          r.center_dofs, r.nnz, r.local_rows, r.spmv_launches, r.kernel_launches,
                          {STAGE_NAMES[i]: float(r.stage_ms[i]) for i in range(11)}, float(r.spmv_ms),
                          r.interpolated_faces, float(r.cg_update_xr_ms), float(r.cg_update_p_ms), r.dist_mode,
-                         r.halo_columns)
+                         r.halo_columns, float(r.cg_kernel_ms), int(r.cg_kernel_launches))
 
 
 def _new_result() -> AvsResult:

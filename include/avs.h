@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AVS_ABI_VERSION 1
+#define AVS_ABI_VERSION 2
 
 typedef enum AvsStatus {
     AVS_OK = 0,
@@ -135,14 +135,18 @@ typedef struct AvsResult {
     int64_t spmv_launches;    /* SpMV launches that did work (residual + CG iterations; launches after convergence are no-ops) */
     int64_t kernel_launches;  /* all kernels this call launched          */
     float stage_ms[AVS_STAGE_COUNT];
-    float spmv_ms;            /* accumulated device time of the SpMV launches (only with AvsDeviceConfig.time_spmv) */
-    float cg_update_xr_ms;    /* accumulated device time of the x,r update kernel (time_spmv only) */
-    float cg_update_p_ms;     /* accumulated device time of the p update kernel (time_spmv only)   */
+    float spmv_ms;            /* accumulated device time of the SpMV phases: persistent CG kernel -- measured inside the kernel
+                                 (%globaltimer of CTA 0, grid barrier to grid barrier); per-launch CG (AVS_CG_MODE=launch) --
+                                 CUDA events around every SpMV launch, only with AvsDeviceConfig.time_spmv */
+    float cg_update_xr_ms;    /* same for the x,r update phase (incl. its scalar all-reduce wait when nranks > 1) */
+    float cg_update_p_ms;     /* same for the p update phase (incl. the halo push when nranks > 1)              */
     int32_t dist_mode;        /* 0 single GPU, 1 NCCL hot loop, 2 peer-memory (NVLink loads/stores in our kernels) */
     int32_t reserved0;
     int64_t halo_columns;     /* off-rank columns this rank's rows reference */
     int64_t interpolated_faces; /* regular faces inside coarse cells, filled by the octree interpolator (interpSPGrid,
                                   HDK_OctreeVectorFieldInterpolator.cpp:660-845); 0 when depth == 1 */
+    float cg_kernel_ms;       /* device time of the persistent CG kernel, CUDA events around its cooperative launch(es) */
+    int32_t cg_kernel_launches; /* cooperative launches of that kernel (1 unless check_every / cancel chunking is on)     */
 } AvsResult;
 
 typedef struct AvsDeviceConfig {

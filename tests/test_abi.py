@@ -26,7 +26,7 @@ def test_every_declared_symbol_is_exported(built):
     for name in declared:
         assert hasattr(L, name), name
     assert declared == set(built.EXPORTS)
-    assert L.avs_abi_version() == 1
+    assert L.avs_abi_version() == 2
 
 
 def test_struct_layout_matches_header(built, tmp_path):
