@@ -86,6 +86,8 @@ int avs_create(const AvsDeviceConfig *cfg, AvsContext **out) {
     cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&c->evCopyGate, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->evUploadDone, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->evDownloadDone, cudaEventDisableTiming);
+    for (auto &e : c->evAxis) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->evPoll[0], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->evPoll[1], cudaEventDisableTiming);
     cudaEventCreate(&c->evPcg[0]);
@@ -139,6 +141,8 @@ void avs_destroy(AvsContext *c) {
     for (auto &e : c->auxEvents) if (e) cudaEventDestroy(e);
     if (c->evCopyGate) cudaEventDestroy(c->evCopyGate);
     if (c->evUploadDone) cudaEventDestroy(c->evUploadDone);
+    if (c->evDownloadDone) cudaEventDestroy(c->evDownloadDone);
+    for (auto &e : c->evAxis) if (e) cudaEventDestroy(e);
     if (c->copyStream) cudaStreamDestroy(c->copyStream);
     if (c->hostScalars) cudaFreeHost(c->hostScalars);
     if (c->ownStream) cudaStreamDestroy(c->stream);
@@ -370,13 +374,16 @@ static int runApply(AvsContext *c, AvsVelocityOut *out, AvsResult *res) {
         if (rcg) return rcg;
     }
     unsigned long long pending = 0;
-    int rc = avs_apply_regular(c, dOut, &pending);
+    const bool streamed = !out->on_device && c->nranks == 1;   // per-axis downloads overlap the remaining apply kernels
+    int rc = avs_apply_regular(c, dOut, &pending, streamed ? out->vel : nullptr);
     if (rc) return rc;
     cudaEventRecord(c->ev[AVS_STAGE_DOWNLOAD], c->stream);
-    if (!out->on_device)
+    if (streamed) AVS_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->evDownloadDone, 0));
+    else if (!out->on_device)
         for (int a = 0; a < 3; ++a)
             AVS_CUDA_CHECK(cudaMemcpyAsync(out->vel[a], dOut[a], c->S.regular[a].count() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     cudaEventRecord(c->ev[AVS_STAGE_DOWNLOAD + 1], c->stream);
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));   // the caller's host arrays are complete on return
     collectStageTimes(c, res, AVS_STAGE_APPLY, AVS_STAGE_DOWNLOAD);
     for (int a = 0; a < 3; ++a) tmp[a].release();
     res->kernel_launches = c->launches;

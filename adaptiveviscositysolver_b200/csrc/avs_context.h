@@ -67,6 +67,7 @@ struct AvsContext {
     bool ownStream = false;
     cudaStream_t copyStream = nullptr;   // host->device copies that overlap the labelling stages
     cudaEvent_t evCopyGate = nullptr, evUploadDone = nullptr;
+    cudaEvent_t evAxis[3] = {}, evDownloadDone = nullptr;   // per-axis device -> host copies of the output under stage 11
     bool timeSpmv = false;
     int numSMs = 148;
     std::string lastError;
@@ -134,7 +135,7 @@ int avs_stage_octree_labels(AvsContext *c);
 int avs_stage_restriction(AvsContext *c);
 int avs_stage_system(AvsContext *c, const AvsParams *p);
 int avs_stage_solve(AvsContext *c, const AvsParams *p, AvsResult *res);
-int avs_apply_regular(AvsContext *c, float *dOut[3], unsigned long long *hostPending);
+int avs_apply_regular(AvsContext *c, float *dOut[3], unsigned long long *hostPending, float *const *hostOut);
 
 int avs_sell_from_csr(AvsContext *c, SellMatrix &A, int64_t n, const int64_t *dPtr, const int32_t *dCol,
                       const double *dVal, int precision);

@@ -305,7 +305,7 @@ __global__ void k_apply_regular(const __grid_constant__ DeviceScene S, const Nod
 
 static dim3 grid3(const int n[3]) { return dim3((unsigned)((n[0] + 127) / 128), (unsigned)n[1], (unsigned)n[2]); }
 
-int avs_apply_regular(AvsContext *c, float *dOut[3], unsigned long long *hostInterpolated) {
+int avs_apply_regular(AvsContext *c, float *dOut[3], unsigned long long *hostInterpolated, float *const *hostOut) {
     const DeviceScene &S = c->S;
     const int L = S.levels;
     const double *sol = c->nranks > 1 ? c->fullSolution.as<double>() : c->solution.as<double>();
@@ -369,7 +369,14 @@ int avs_apply_regular(AvsContext *c, float *dOut[3], unsigned long long *hostInt
         dim3 g((unsigned)((S.regular[a].n[0] + 127) / 128), (unsigned)S.regular[a].n[1], (unsigned)(z1 - z0));
         k_apply_regular<<<g, 128, 0, c->stream>>>(S, c->nodeScene.as<NodeScene>(), a, sol, dOut[a], cnt, z0);
         ++c->launches;
+        if (hostOut && c->nranks == 1) {
+            // host caller: the device -> host copy of this axis runs on the copy stream underneath the next axis' kernel
+            AVS_CUDA_CHECK(cudaEventRecord(c->evAxis[a], c->stream));
+            AVS_CUDA_CHECK(cudaStreamWaitEvent(c->copyStream, c->evAxis[a], 0));
+            AVS_CUDA_CHECK(cudaMemcpyAsync(hostOut[a], dOut[a], S.regular[a].count() * sizeof(float), cudaMemcpyDeviceToHost, c->copyStream));
+        }
     }
+    if (hostOut && c->nranks == 1) AVS_CUDA_CHECK(cudaEventRecord(c->evDownloadDone, c->copyStream));
     if (c->nranks > 1) {
         int rcd = avs_dist_allreduce_u64(c, cnt, 1);
         if (rcd) return rcd;

@@ -10,6 +10,7 @@
 // re-evaluates the <= ~12 stencils that touch it, merges duplicates in registers/local memory and
 // writes its CSR segment directly (count pass -> scan -> fill pass).
 #include <algorithm>
+#include <cstdlib>
 #include <cstdio>
 
 #include "avs_context.h"
@@ -428,7 +429,8 @@ __device__ void buildRow(const DeviceScene &S, int32_t vi, const RowKey &k, doub
 // (entry j of local row r at j*stride + r, so a warp's writes are coalesced), its entry count, its
 // rhs and its diagonal.  The CG's SJDS matrix is filled straight from the staging area; a canonical
 // CSR (sorted columns) is only built when a caller asks to read the system back.
-__global__ void __launch_bounds__(128) k_assemble(const __grid_constant__ DeviceScene S, const RowKey *keys, const double *x0,
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_assemble(const __grid_constant__ DeviceScene S, const RowKey *keys, const double *x0,
                                                   long long rowBegin, long long nLocal, long long stride, int32_t *rowCount,
                                                   int32_t *stageCol, double *stageVal, double *rhs, double *diagOut,
                                                   int *overflowFlag) {
@@ -491,9 +493,20 @@ int avs_stage_system(AvsContext *c, const AvsParams *p) {
     c->nnz = 0;
     if (nLocal > 0) {
         unsigned blocks = (unsigned)((nLocal + 127) / 128);
-        k_assemble<<<blocks, 128, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->x0.as<double>(), c->rowBegin, nLocal, stride,
-                                                  c->rowCount.as<int32_t>(), c->stageCol.as<int32_t>(), c->stageVal.as<double>(),
-                                                  c->rhs.as<double>(), c->diag.as<double>(), flag);
+        // AVS_ASM_MINB: resident CTAs per SM the register allocation aims at.  Measured at C3 (stage 'system'): 4 (128 registers,
+        // no spills) 36.5 ms, 5: 32.9, 6: 32.2, 8 (64 registers, 788 B spills) 30.8 ms -- the kernel is latency-bound (ncu: 19 % warps
+        // active, long-scoreboard stalls), so occupancy beats spills.
+        static int minb = -1;
+        if (minb < 0) { const char *e = getenv("AVS_ASM_MINB"); minb = e ? atoi(e) : 8; }
+#define ASM_LAUNCH(M)                                                                                                              \
+    k_assemble<M><<<blocks, 128, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->x0.as<double>(), c->rowBegin, nLocal, stride,       \
+                                                 c->rowCount.as<int32_t>(), c->stageCol.as<int32_t>(), c->stageVal.as<double>(),      \
+                                                 c->rhs.as<double>(), c->diag.as<double>(), flag)
+        if (minb >= 8) ASM_LAUNCH(8);
+        else if (minb >= 6) ASM_LAUNCH(6);
+        else if (minb == 5) ASM_LAUNCH(5);
+        else ASM_LAUNCH(4);
+#undef ASM_LAUNCH
         ++c->launches;
         int64_t nnz = 0;
         int rc = avs_exclusive_scan_i32_to_i64(c, c->rowCount.as<int32_t>(), c->csrPtr.as<int64_t>(), nLocal, &nnz);
