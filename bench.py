@@ -158,6 +158,8 @@ def run_reference(args, w):
     if rank != 0:
         return
     from oracle import avs_oracle as orc
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the reference arm runs on rank 0 alone and takes all host cores
+    orc.set_num_threads(os.cpu_count() or 1)
     cores = orc.num_threads()
     t0 = time.time()
     scene = make_scene(w)
