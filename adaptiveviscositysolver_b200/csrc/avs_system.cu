@@ -474,7 +474,6 @@ __global__ void k_csr_from_stage(long long nLocal, long long stride, const int32
 
 int avs_stage_system(AvsContext *c, const AvsParams *p) {
     (void)p;
-    const long long n = c->nRows;
     // row partition: computed with the numbering (avs_stage_octree_labels)
     c->rowBegin = c->rowStarts[c->rank];
     c->rowEnd = c->rowStarts[c->rank + 1];

@@ -161,10 +161,10 @@ def run_reference(args, w):
     # torchrun exports OMP_NUM_THREADS=1 to every rank: the reference arm runs on rank 0 alone and takes all host cores
     orc.set_num_threads(os.cpu_count() or 1)
     cores = orc.num_threads()
-    t0 = time.time()
     scene = make_scene(w)
+    t0 = time.time()
     run = orc.OracleRun(scene, orc.OracleParams(octree_levels=w["L"], tolerance=w["tol"], dt=w.get("dt", 1.0 / 24.0)), stop_after_stage=9)
-    t_asm = time.time() - t0
+    t_asm = time.time() - t0          # stages 1-9 of the restated reference path (weights ... linear system)
     ptr, col, val = run.csr()
     b, x0 = run.rhs(), run.x0()
     n = run.n_face
@@ -178,12 +178,20 @@ def run_reference(args, w):
         orc.cg(ptr, col, val, b, x0, 0.0, m)
     dt = (time.time() - t) / args.steps
     value = n * m / dt
+    # Outside the timed steps, for transparency: ONE whole solve of the reference path -- assembly (above) + the CG run to
+    # the workload's tolerance -- when that fits the time budget.  `value` (the driver's denominator) stays the CG-only
+    # sample, i.e. it EXCLUDES the reference's assembly time while this repo's arm includes all stages in its step.
+    whole = None
+    if per_it * 400 < 90.0:
+        t = time.time(); _, it_full, err_full = orc.cg(ptr, col, val, b, x0, w["tol"], 2500); t_cg = time.time() - t
+        whole = {"assembly_s": round(t_asm, 2), "cg_s": round(t_cg, 2), "iterations": int(it_full), "rel_error": float(err_full),
+                 "dof_iters_per_s": n * it_full / (t_asm + t_cg) if it_full > 0 else 0.0}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": w["desc"], "N": int(n), "nnz": int(run.nnz), "levels": int(run.levels), "tolerance": w["tol"],
-                   "oracle_assembly_s": round(t_asm, 2)},
+                   "oracle_assembly_s": round(t_asm, 2), "whole_solve": whole},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{m} Jacobi-PCG iterations per step on the oracle-assembled system (N={n}), OpenMP {cores} threads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
