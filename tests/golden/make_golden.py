@@ -38,7 +38,7 @@ HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent.parent
 sys.path.insert(0, str(ROOT))
 
-from adaptiveviscositysolver_b200.scenes import sphere_drop  # noqa: E402
+from adaptiveviscositysolver_b200.scenes import buckling_sheet, sphere_drop  # noqa: E402
 
 # name -> scene kwargs, octree levels, extra params
 CASES = {
@@ -52,6 +52,8 @@ CASES = {
     # solid ground plane with a moving solid (SOLIDBOUNDARY faces, boundary stencil terms)
     "solid_ground32_l3": dict(scene=dict(n=32, radius_cells=9, center=(0.5, 0.34, 0.5), ground_height=0.125,
                                          ground_velocity=(0.1, 0.0, -0.2)), levels=3),
+    # BASELINE.json configs[4] at reduced resolution: folded buckling-sheet frame, variable viscosity, ground plane, dt = 1/120
+    "buckling_f6_dx2mm": dict(maker="buckling_sheet", scene=dict(frame=6, dx=0.002), levels=4, dt=1.0 / 120.0),
 }
 TOL = 1e-10
 MAX_OUT = 200_000
@@ -89,10 +91,14 @@ def golden_vector(n: int) -> np.ndarray:
     return np.random.default_rng(20261017).standard_normal(n)
 
 
+def make_scene(case: dict):
+    return buckling_sheet(**case["scene"]) if case.get("maker") == "buckling_sheet" else sphere_drop(**case["scene"])
+
+
 def build(name: str, case: dict) -> dict:
     from oracle import avs_oracle as orc
-    sc = sphere_drop(**case["scene"])
-    ref = orc.OracleRun(sc, orc.OracleParams(octree_levels=case["levels"], tolerance=TOL))
+    sc = make_scene(case)
+    ref = orc.OracleRun(sc, orc.OracleParams(octree_levels=case["levels"], tolerance=TOL, dt=case.get("dt", 1.0 / 24.0)))
     keys = ref.face_keys()
     order = key_order(keys)
     inv = np.empty_like(order)

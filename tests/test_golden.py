@@ -12,8 +12,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from adaptiveviscositysolver_b200.scenes import sphere_drop
-from tests.golden.make_golden import CASES, classes, golden_vector, input_hashes, key_order, sha
+from tests.golden.make_golden import CASES, classes, golden_vector, input_hashes, key_order, make_scene, sha
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
 
@@ -29,7 +28,7 @@ def test_fixture_matches_scene_generator(name):
     """The committed vectors belong to the scenes the generator produces today."""
     z, meta = load(name)
     assert meta["case"] == json.loads(json.dumps(CASES[name]))
-    sc = sphere_drop(**CASES[name]["scene"])
+    sc = make_scene(CASES[name])
     assert input_hashes(sc) == meta["input_sha256"]
     keys = z["keys"]
     assert keys.shape == (meta["octree_dofs"], 5)
@@ -42,8 +41,8 @@ def test_oracle_reproduces_golden(name):
     from oracle import avs_oracle as orc
     z, meta = load(name)
     case = CASES[name]
-    sc = sphere_drop(**case["scene"])
-    ref = orc.OracleRun(sc, orc.OracleParams(octree_levels=case["levels"], tolerance=meta["tolerance"]))
+    sc = make_scene(case)
+    ref = orc.OracleRun(sc, orc.OracleParams(octree_levels=case["levels"], tolerance=meta["tolerance"], dt=case.get("dt", 1.0 / 24.0)))
     assert (ref.levels, ref.n_face, ref.n_edge, ref.n_center, ref.regular_dofs, ref.nnz, ref.interpolated_faces) == \
         (meta["levels"], meta["octree_dofs"], meta["edge_dofs"], meta["center_dofs"], meta["regular_dofs"], meta["nnz"],
          meta["interpolated_faces"])
@@ -92,9 +91,9 @@ def test_gpu_reproduces_golden(solver, name):
     from adaptiveviscositysolver_b200.solver import Params
     z, meta = load(name)
     case = CASES[name]
-    sc = sphere_drop(**case["scene"])
+    sc = make_scene(case)
     out = [v.data.copy() for v in sc.vel]
-    info = solver.solve(sc, Params(octree_levels=case["levels"], tolerance=meta["tolerance"]), out)
+    info = solver.solve(sc, Params(octree_levels=case["levels"], tolerance=meta["tolerance"], dt=case.get("dt", 1.0 / 24.0)), out)
     assert (info.levels, info.octree_dofs, info.edge_dofs, info.center_dofs, info.regular_dofs, info.nnz,
             info.interpolated_faces) == \
         (meta["levels"], meta["octree_dofs"], meta["edge_dofs"], meta["center_dofs"], meta["regular_dofs"], meta["nnz"],
@@ -128,7 +127,7 @@ def test_gpu_reproduces_golden(solver, name):
     assert np.abs(rhs[order] - z["rhs"]).max() <= 1e-12 * np.abs(z["rhs"]).max()
     assert np.abs(x0[order] - z["x0"]).max() <= 1e-12 * max(np.abs(z["x0"]).max(), 1e-300)
     # solve: velocity L-inf < 1e-6 (north star); both sides converged to 1e-10
-    assert abs(info.iterations - meta["iterations"]) <= 2
+    assert abs(info.iterations - meta["iterations"]) <= max(2, meta["iterations"] // 50)   # stiff buckling frame: +-2 %
     assert np.abs(solver.solution()[order] - z["x"]).max() < 1e-6
     # regular-grid output
     for a in range(3):
