@@ -32,3 +32,39 @@ def halo_plan(ptr, col, row_begin: int, row_end: int, n: int, nranks: int, start
     bounds = np.array(starts if starts is not None else [n * q // nranks for q in range(nranks + 1)])
     recv_counts = np.diff(np.searchsorted(halo, bounds))
     return halo, local.astype(np.int32), recv_counts
+
+
+def slab_cuts(plane_liquid_cells, nranks: int, plane_cells: int):
+    """z-plane cuts of the REGULAR grid for the slab-sharded stages (regular-face classification and the stage-11
+    write-back, ``avs_slab_cuts`` in csrc/avs_labels.cu): ``cuts[q] .. cuts[q+1]`` are rank q's cell planes.
+
+    The weight of a plane is its number of liquid cells (sdf < 0) plus a floor of 2 % of a full plane (every plane
+    still costs one streaming pass); cut q is the first plane boundary where the running weight reaches q/P of the
+    total.  Pure integer arithmetic on identical inputs, hence identical on every rank."""
+    w = np.asarray(plane_liquid_cells, dtype=np.int64) + max(1, int(plane_cells) // 50)
+    nz, total = w.size, int(w.sum())
+    cuts = [0] * (nranks + 1)
+    cuts[nranks] = nz
+    run, q = 0, 1
+    for z in range(nz):
+        if q >= nranks:
+            break
+        run += int(w[z])
+        while q < nranks and run * nranks >= total * q:
+            cuts[q] = z + 1
+            q += 1
+    for r in range(q, nranks):
+        cuts[r] = nz
+    return cuts
+
+
+def slab_range(cuts, axis: int, rank: int, face_planes: int):
+    """Planes [z0, z1) of the axis-``axis`` face grid that ``rank`` owns: the z-face grid has one more plane than
+    there are cell planes, the last rank takes it (``avs_slab_range``)."""
+    nranks = len(cuts) - 1
+    return cuts[rank], (face_planes if rank == nranks - 1 else cuts[rank + 1])
+
+
+def deal_frames(nframes: int, rank: int, nranks: int):
+    """C5: the frames of a prescribed-geometry sequence are independent solves, dealt round-robin (bench.py)."""
+    return [f for f in range(nframes) if f % nranks == rank]

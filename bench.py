@@ -218,7 +218,8 @@ def run_frames(args, w):
         dist.init_process_group("nccl", device_id=dev)
     peak, peak_src = peaks()
     params = Params(octree_levels=w["L"], tolerance=w["tol"], dt=w["dt"], single_precision=args.fp32)
-    mine = [f for f in range(w["frames"]) if f % world == rank]
+    from adaptiveviscositysolver_b200.dist_plan import deal_frames
+    mine = deal_frames(w["frames"], rank, world)
     scenes = [make_scene(w, f) for f in mine]
     dscenes = [to_device_scene(sc, torch, dev) for sc in scenes]
     douts = [[v.data.clone() for v in ds.vel] for ds in dscenes]
