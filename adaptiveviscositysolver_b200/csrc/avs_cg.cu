@@ -913,6 +913,245 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) k_cg_persistent(const __grid
     }
 }
 
+// ---- experimental variant of the persistent kernel (AVS_PCG_KERNEL=x; NOT the default, see profiles/r1_experiments.md) ---------
+// Three changes against k_cg_persistent, kept in a kernel of their own so that the default kernel's code generation is untouched:
+//  (1) the SpMV slice loop pins its load schedule: every gather index gets `+ z`, z = (all four column words of the trip OR-ed) >> 31
+//      -- always 0 (local column indices are < 2^31) but not foldable by ptxas -- so no gather can be issued before ALL column loads
+//      of the trip (the slow builds issued gather 0 before column loads 1-3: three dependent latencies per trip instead of two);
+//  (2) flag-in-data scalar all-reduce (the idea of NCCL's LL protocol): no fence between payload and flag;
+//  (3) interior-first SpMV: slices that read no halo slot run before the wait for the peers' halo push.
+// (2) and (3) were parity-green on 2 GPUs and cut 25 us per iteration off the exchange; they were not merged because the build that
+// carried them had the slow SpMV schedule that (1) is meant to rule out.  To be measured in round 2.
+template <class T, class T2, int SPMV_U>
+__device__ __forceinline__ double spmvOneSliceOrdered(long long s, int lane, const SjdsView<T, T2> &A, const T *x, T *y) {
+    const int m = A.meta[s * 32 + lane];
+    const int np = m & 0xff;
+    const long long r = s * 32 + (m >> 8);
+    const long long base = A.sliceOff[s] + lane;
+    const int maxnp = __shfl_sync(0xffffffffu, np, 0);
+    T acc = 0;
+    long long off = 0;
+    for (int j0 = 0; j0 < maxnp; j0 += SPMV_U) {
+        long long o[SPMV_U];
+        bool act[SPMV_U];
+#pragma unroll
+        for (int u = 0; u < SPMV_U; ++u) {
+            act[u] = (j0 + u) < np;
+            o[u] = base + off;
+            off += __popc(__ballot_sync(0xffffffffu, act[u]));
+        }
+        T2 v[SPMV_U];
+        int2 cc[SPMV_U];
+        int all = 0;
+#pragma unroll
+        for (int u = 0; u < SPMV_U; ++u) {
+            v[u].x = 0; v[u].y = 0;
+            cc[u].x = 0; cc[u].y = 0;
+            if (act[u]) { cc[u] = A.col2[o[u]]; v[u] = A.val2[o[u]]; }
+            all |= cc[u].x | cc[u].y;
+        }
+        const int z = all >> 31;   // 0: column indices are non-negative; ties every gather below to all column loads above
+        T xa[SPMV_U], xb[SPMV_U];
+#pragma unroll
+        for (int u = 0; u < SPMV_U; ++u) {
+            xa[u] = 0; xb[u] = 0;
+            if (act[u]) { xa[u] = x[cc[u].x + z]; xb[u] = x[cc[u].y + z]; }
+        }
+#pragma unroll
+        for (int u = 0; u < SPMV_U; ++u) {
+            acc += v[u].x * xa[u];
+            acc += v[u].y * xb[u];
+        }
+    }
+    double dot = 0;
+    if (r < A.nrows) {
+        y[r] = acc;
+        dot = (double)x[r] * (double)acc;
+    }
+    return dot;
+}
+
+// flag[s] = 1 when slice s gathers from a halo slot (local column >= nLocal)
+__global__ void k_slice_needs_halo(long long nslices, const long long *__restrict__ sliceOff, const int2 *__restrict__ col2, int nLocal,
+                                   uint8_t *flag) {
+    const long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (s >= nslices) return;
+    bool hit = false;
+    for (long long i = sliceOff[s] + lane; i < sliceOff[s + 1]; i += 32) {
+        const int2 c = col2[i];
+        hit = hit || c.x >= nLocal || c.y >= nLocal;
+    }
+    const unsigned any = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) flag[s] = any ? 1 : 0;
+}
+
+// v[0..COUNT): this rank's sums (same bits in every CTA) -> sum over ranks in rank order.  `shw`: P * COUNT * 2 32-bit words.
+template <int COUNT>
+__device__ __forceinline__ bool rankSumLL(double (&v)[COUNT], const PcgDist &D, unsigned long long seq, PcgState *st, unsigned *shw) {
+    const int par = (int)(seq & 1ull);
+    const unsigned long long tag = (seq & 0xffffffffull) << 32;
+    P2PHeader *mine = (P2PHeader *)D.peerRegion[D.myRank];
+    if (blockIdx.x == 0 && threadIdx.x < D.P * COUNT * 2) {
+        const int peerRank = threadIdx.x / (COUNT * 2), q = (threadIdx.x / 2) % COUNT, half = threadIdx.x & 1;
+        P2PHeader *peer = (P2PHeader *)D.peerRegion[peerRank];
+        unsigned long long bits = 0;
+#pragma unroll
+        for (int i = 0; i < COUNT; ++i)
+            if (i == q) bits = (unsigned long long)__double_as_longlong(v[i]);
+        const unsigned long long word = (half ? (bits >> 32) : (bits & 0xffffffffull)) | tag;
+        *(volatile unsigned long long *)&peer->ll[par][D.myRank][q][half] = word;
+    }
+    __syncthreads();
+    if (threadIdx.x < D.P * COUNT * 2) {
+        const int sender = threadIdx.x / (COUNT * 2), q = (threadIdx.x / 2) % COUNT, half = threadIdx.x & 1;
+        const unsigned long long *slot = &mine->ll[par][sender][q][half];
+        unsigned long long w = ldVolatileU64(slot), t0 = 0;
+        unsigned spins = 0;
+        while ((w & 0xffffffff00000000ull) != tag) {
+            if ((++spins & 0x3ff) == 0) {
+                if (*(volatile int *)&st->abort) break;
+                unsigned long long now = globalTimerNs();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > PCG_TIMEOUT_NS) { *(volatile int *)&st->abort = 1; break; }
+            }
+            w = ldVolatileU64(slot);
+        }
+        shw[threadIdx.x] = (unsigned)(w & 0xffffffffull);
+    }
+    __syncthreads();
+    if (*(volatile int *)&st->abort) return false;
+#pragma unroll
+    for (int q = 0; q < COUNT; ++q) {
+        double t = 0;
+        for (int r = 0; r < D.P; ++r) {
+            const unsigned lo = shw[(r * COUNT + q) * 2], hi = shw[(r * COUNT + q) * 2 + 1];
+            t += __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+        }
+        v[q] = t;
+    }
+    __syncthreads();
+    return true;
+}
+
+template <class T, class T2, int SPMV_U>
+__global__ void __launch_bounds__(CG_THREADS, 4) k_cg_persistent_x(const __grid_constant__ PcgArgs<T, T2> A, const uint8_t *__restrict__ sliceHalo) {
+    __shared__ double sh[CG_THREADS / 32 + 1];
+    __shared__ unsigned shw[P2P_MAX_RANKS * 4];
+    __shared__ unsigned long long tm[4];
+    __shared__ double rrLast;
+    CgScalars *sc = A.sc;
+    PcgState *st = A.st;
+    if (sc->done) return;
+    const bool dist = A.D.P > 1;
+    const bool timer = blockIdx.x == 0 && threadIdx.x == 0;
+    const int G = gridDim.x;
+    double rho = sc->rho[0];
+    int iters = sc->iters;
+    int k = 0;
+    unsigned barTarget = 0, pushTarget = 0;
+    bool stop = false, breakdown = false;
+    if (timer) { tm[1] = tm[2] = tm[3] = 0; rrLast = sc->residualNorm2; }
+    const unsigned long long seqPush0 = A.D.seqPush + (unsigned long long)A.pushFirst;
+    const bool twoPass = dist && sliceHalo != nullptr;
+    const int lane = threadIdx.x & 31;
+    const long long warpsTotal = ((long long)G * CG_THREADS) >> 5;
+
+    if (dist && A.pushFirst) pushHalo<T>(A.p, A.D, seqPush0, st, pushTarget);
+    while (iters < A.itLimit) {
+        if (timer) tm[0] = globalTimerNs();
+        // ---- t = A p, partial p.t: interior slices first, the slices on the partition boundary after the halo has landed
+        {
+            double dot = 0;
+            bool okHalo = true;
+            for (int pass = 0; pass < (twoPass ? 2 : 1); ++pass) {
+                if (dist && pass == (twoPass ? 1 : 0) && !(okHalo = waitHalo(A.D, seqPush0 + k, st))) break;
+                for (long long s = ((long long)blockIdx.x * CG_THREADS + threadIdx.x) >> 5; s < A.M.nslices; s += warpsTotal) {
+                    if (twoPass && sliceHalo[s] != pass) continue;
+                    dot += spmvOneSliceOrdered<T, T2, SPMV_U>(s, lane, A.M, A.p, A.t);
+                }
+            }
+            if (!okHalo) break;
+            double s0 = blockSum(dot, sh);
+            if (threadIdx.x == 0) A.parts[blockIdx.x] = s0;
+        }
+        if (!gridBarrier(st, barTarget)) break;
+        if (timer) { unsigned long long now = globalTimerNs(); tm[1] += now - tm[0]; tm[0] = now; }
+        double pt[1] = {reduceParts(A.parts, G, sh)};
+        if (dist && !rankSumLL<1>(pt, A.D, A.D.seqReduce + 2ull * k + 1, st, shw)) break;
+        const double alphaD = rho / pt[0];
+        breakdown = !isfinite(alphaD);
+        const T alpha = breakdown ? (T)0 : (T)alphaD;
+        {
+            double rr = 0, rz = 0;
+            const long long gid = (long long)blockIdx.x * CG_THREADS + threadIdx.x, gstride = (long long)G * CG_THREADS;
+            const long long n2 = A.n >> 1;
+            for (long long j = gid; j < n2; j += gstride) {
+                const T2 pv = ((const T2 *)A.p)[j], tv = ((const T2 *)A.t)[j], dv = ((const T2 *)A.invDiag)[j];
+                T2 rv = ((T2 *)A.r)[j], xv = ((T2 *)A.x)[j];
+                rv.x -= alpha * tv.x; rv.y -= alpha * tv.y;
+                xv.x += alpha * pv.x; xv.y += alpha * pv.y;
+                ((T2 *)A.x)[j] = xv;
+                ((T2 *)A.r)[j] = rv;
+                rr += (double)rv.x * (double)rv.x + (double)rv.y * (double)rv.y;
+                rz += (double)rv.x * (double)(T)(dv.x * rv.x) + (double)rv.y * (double)(T)(dv.y * rv.y);
+            }
+            if ((A.n & 1) && gid == 0) {
+                const long long i = A.n - 1;
+                T ri = A.r[i] - alpha * A.t[i];
+                A.x[i] += alpha * A.p[i];
+                A.r[i] = ri;
+                rr += (double)ri * (double)ri;
+                rz += (double)ri * (double)(T)(A.invDiag[i] * ri);
+            }
+            double s0 = blockSum(rr, sh), s1 = blockSum(rz, sh);
+            if (threadIdx.x == 0) { A.parts[G + blockIdx.x] = s0; A.parts[2 * G + blockIdx.x] = s1; }
+        }
+        if (!gridBarrier(st, barTarget)) break;
+        if (timer) { unsigned long long now = globalTimerNs(); tm[2] += now - tm[0]; tm[0] = now; }
+        double rs[2];
+        rs[0] = reduceParts(A.parts + G, G, sh);
+        rs[1] = reduceParts(A.parts + 2 * G, G, sh);
+        if (dist && !rankSumLL<2>(rs, A.D, A.D.seqReduce + 2ull * k + 2, st, shw)) break;
+        ++k;
+        if (timer) rrLast = rs[0];
+        stop = (rs[0] < sc->threshold) || breakdown;
+        if (stop) break;
+        const T beta = (T)(rs[1] / rho);
+        rho = rs[1];
+        ++iters;
+        {
+            const long long gid = (long long)blockIdx.x * CG_THREADS + threadIdx.x, gstride = (long long)G * CG_THREADS;
+            const long long n2 = A.n >> 1;
+            for (long long j = gid; j < n2; j += gstride) {
+                const T2 dv = ((const T2 *)A.invDiag)[j], rv = ((const T2 *)A.r)[j];
+                T2 pv = ((T2 *)A.p)[j];
+                pv.x = dv.x * rv.x + beta * pv.x;
+                pv.y = dv.y * rv.y + beta * pv.y;
+                ((T2 *)A.p)[j] = pv;
+            }
+            if ((A.n & 1) && gid == 0) { const long long i = A.n - 1; A.p[i] = A.invDiag[i] * A.r[i] + beta * A.p[i]; }
+        }
+        if (!gridBarrier(st, barTarget)) break;
+        if (dist) pushHalo<T>(A.p, A.D, seqPush0 + k, st, pushTarget);
+        if (timer) tm[3] += globalTimerNs() - tm[0];
+    }
+    if (timer) {
+        sc->rho[0] = rho;
+        sc->rho[1] = rho;
+        sc->iters = iters;
+        sc->residualNorm2 = rrLast;
+        if (breakdown) sc->breakdown = 1;
+        if (stop) sc->done = 1;
+        st->seqReduce = A.D.seqReduce + 2ull * k;
+        st->seqPush = seqPush0 + (stop ? k - 1 : k);
+        st->phaseNs[0] += tm[1];
+        st->phaseNs[1] += tm[2];
+        st->phaseNs[2] += tm[3];
+        st->spmvPhases += k;
+    }
+}
+
 template <class T>
 __global__ void k_convert_in(long long n, const double *in, T *out) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -945,6 +1184,16 @@ static bool cgUsePersistent() {
 }
 // AVS_PCG_MINB=5 selects the variant whose register allocation aims at 5 resident CTAs per SM (measured at C3: spills,
 // no faster than the default 4); AVS_PCG_DYN=1 the dynamic slice schedule (measured slower: 0.51 vs 0.46 ms per SpMV).
+// AVS_PCG_KERNEL=x selects the experimental kernel k_cg_persistent_x (pinned load schedule, flag-in-data all-reduce,
+// interior-first SpMV) -- parity-tested pieces, not yet measured as a whole; off by default.
+static bool pcgExperimental() {
+    static int x = -1;
+    if (x < 0) {
+        const char *e = getenv("AVS_PCG_KERNEL");
+        x = (e && e[0] == 'x') ? 1 : 0;
+    }
+    return x == 1;
+}
 template <class T, class T2>
 static const void *pcgKernel() {
     static int minb = -1;
@@ -952,6 +1201,7 @@ static const void *pcgKernel() {
         const char *e = getenv("AVS_PCG_MINB");
         minb = e ? atoi(e) : 4;
     }
+    if (pcgExperimental()) return (const void *)k_cg_persistent_x<T, T2, 4>;
     if (minb == 5) return (const void *)k_cg_persistent<T, T2, 4, 5>;
     return (const void *)k_cg_persistent<T, T2, 4, 4>;
 }
@@ -1114,11 +1364,19 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
         ka.D = dist ? pd : PcgDist();
         ka.pushFirst = 1;
         { const char *env = getenv("AVS_PCG_DYN"); ka.dynamic = (env && env[0] == '1') ? 1 : 0; }
+        const uint8_t *sliceHalo = nullptr;
+        if (pcgExperimental() && dist && A.nslices > 0) {
+            if (w.sliceHalo.reserve((size_t)A.nslices)) return AVS_ERR_ALLOC;
+            k_slice_needs_halo<<<(unsigned)((A.nslices * 32 + 255) / 256), 256, 0, c->stream>>>(A.nslices, A.sliceOff.as<long long>(), A.col.as<int2>(),
+                                                                                      (int)n, w.sliceHalo.as<uint8_t>());
+            ++c->launches;
+            sliceHalo = w.sliceHalo.as<uint8_t>();
+        }
         const int chunk = p->check_every > 0 ? p->check_every : (p->cancel ? 256 : maxIters);
         int itersKnown = 0;
         while (true) {
             ka.itLimit = std::min(maxIters, itersKnown + std::max(chunk, 1));
-            void *kargs[] = {(void *)&ka};
+            void *kargs[] = {(void *)&ka, (void *)&sliceHalo};   // the default kernel takes one parameter, the experimental one two
             AVS_CUDA_CHECK(cudaEventRecord(c->evPcg[0], c->stream));
             AVS_CUDA_CHECK(cudaLaunchCooperativeKernel(pcgKernel<T, T2>(), dim3(pgrid), dim3(CG_THREADS), kargs, 0, c->stream));
             AVS_CUDA_CHECK(cudaEventRecord(c->evPcg[1], c->stream));

@@ -55,6 +55,7 @@ struct CgWork {
     DevBuf partials;        // per-CTA partial sums
     DevBuf scalars;         // device-resident CG scalars
     DevBuf pcgState;        // PcgState of the persistent CG kernel
+    DevBuf sliceHalo;       // experimental kernel: uint8 per slice, 1 = reads a halo slot
 };
 
 struct AvsContext {

@@ -14,6 +14,9 @@ struct P2PHeader {
     unsigned long long flag[2][P2P_MAX_RANKS];              // mailbox sequence flags, written by the peers
     double mail[2][P2P_MAX_RANKS][4];                       // mailbox payload (<= 3 doubles used)
     unsigned long long pushFlag[P2P_MAX_RANKS];             // push mode: sender q's halo values of sequence n have landed
+    // experimental kernel (AVS_PCG_KERNEL=x): flag-in-data mailboxes -- one 8-byte store carries 32 payload bits and the
+    // 32-bit sequence number, so no fence separates data and flag: ll[parity][sender][value][half]
+    unsigned long long ll[2][P2P_MAX_RANKS][3][2];
 };
 static_assert(sizeof(P2PHeader) <= P2P_HEADER_BYTES, "header too large");
 
