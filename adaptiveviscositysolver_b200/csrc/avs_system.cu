@@ -14,8 +14,8 @@
 #include <cstdio>
 
 #include "avs_context.h"
+#include "avs_rowacc.cuh"
 
-#define MAX_ROW 64
 #define MAX_STENCIL 40
 
 struct Stencil {
@@ -312,22 +312,11 @@ int avs_stage_restriction(AvsContext *c) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Stage 9: one matrix row.
-struct RowAcc {
-    int n;
-    int overflow;
-    int32_t col[MAX_ROW];
-    double val[MAX_ROW];
-    __device__ __forceinline__ void add(int32_t c, double v) {
-        for (int i = 0; i < n; ++i)
-            if (col[i] == c) { val[i] += v; return; }  // setFromTriplets sums duplicates (AV.cpp:614)
-        if (n < MAX_ROW) { col[n] = c; val[n] = v; ++n; }
-        else overflow = 1;
-    }
-};
+// Stage 9: one matrix row (accumulators: avs_rowacc.cuh).
 
 // applyToMatrix (AV.cpp:2404-2457)
-__device__ __noinline__ void applyToMatrix(RowAcc &row, double &rhsI, double &diag, double coefficient, int32_t vi, const Stencil &st) {
+template <class Row>
+__device__ __noinline__ void applyToMatrix(Row &row, double &rhsI, double &diag, double coefficient, int32_t vi, const Stencil &st) {
     for (int i = 0; i < st.n; ++i)
         if (st.idx[i] == vi) { coefficient *= st.coef[i]; break; }
     for (int i = 0; i < st.n; ++i) {
@@ -339,7 +328,8 @@ __device__ __noinline__ void applyToMatrix(RowAcc &row, double &rhsI, double &di
 }
 
 // buildOctreeSystemFromStencilsPartial (AV.cpp:2459-2777) for row vi
-__device__ void buildRow(const DeviceScene &S, int32_t vi, const RowKey &k, double x0i, RowAcc &row, double &rhsI) {
+template <class Row>
+__device__ void buildRow(const DeviceScene &S, int32_t vi, const RowKey &k, double x0i, Row &row, double &rhsI) {
     const int level = k.level, axis = k.axis;
     const I3 face = mk3(k.i, k.j, k.k);
     const Grid3<uint8_t> &lab = S.label[level];
@@ -429,7 +419,7 @@ __device__ void buildRow(const DeviceScene &S, int32_t vi, const RowKey &k, doub
 // (entry j of local row r at j*stride + r, so a warp's writes are coalesced), its entry count, its
 // rhs and its diagonal.  The CG's SJDS matrix is filled straight from the staging area; a canonical
 // CSR (sorted columns) is only built when a caller asks to read the system back.
-template <int MINB>
+template <int MINB, class Row>
 __global__ void __launch_bounds__(128, MINB) k_assemble(const __grid_constant__ DeviceScene S, const RowKey *keys, const double *x0,
                                                   long long rowBegin, long long nLocal, long long stride, int32_t *rowCount,
                                                   int32_t *stageCol, double *stageVal, double *rhs, double *diagOut,
@@ -437,9 +427,8 @@ __global__ void __launch_bounds__(128, MINB) k_assemble(const __grid_constant__ 
     long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nLocal) return;
     const long long gi = rowBegin + r;
-    RowAcc row;
-    row.n = 0;
-    row.overflow = 0;
+    Row row;
+    row.init();
     double rhsI = 0;
     buildRow(S, (int32_t)gi, keys[gi], x0[gi], row, rhsI);
     if (row.overflow) *overflowFlag = 1;
@@ -497,10 +486,19 @@ int avs_stage_system(AvsContext *c, const AvsParams *p) {
         // active, long-scoreboard stalls), so occupancy beats spills.
         static int minb = -1;
         if (minb < 0) { const char *e = getenv("AVS_ASM_MINB"); minb = e ? atoi(e) : 8; }
+        static int hashRow = -1;   // AVS_ASM_ROW=hash: experimental hashed row accumulator (avs_rowacc.cuh), not yet measured
+        if (hashRow < 0) { const char *e = getenv("AVS_ASM_ROW"); hashRow = (e && e[0] == 'h') ? 1 : 0; }
 #define ASM_LAUNCH(M)                                                                                                              \
-    k_assemble<M><<<blocks, 128, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->x0.as<double>(), c->rowBegin, nLocal, stride,       \
+    do {                                                                                                                           \
+    if (hashRow)                                                                                                                   \
+        k_assemble<M, RowAccHash><<<blocks, 128, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->x0.as<double>(), c->rowBegin, nLocal, stride, \
                                                  c->rowCount.as<int32_t>(), c->stageCol.as<int32_t>(), c->stageVal.as<double>(),      \
-                                                 c->rhs.as<double>(), c->diag.as<double>(), flag)
+                                                 c->rhs.as<double>(), c->diag.as<double>(), flag);                                    \
+    else                                                                                                                           \
+    k_assemble<M, RowAcc><<<blocks, 128, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->x0.as<double>(), c->rowBegin, nLocal, stride,       \
+                                                 c->rowCount.as<int32_t>(), c->stageCol.as<int32_t>(), c->stageVal.as<double>(),      \
+                                                 c->rhs.as<double>(), c->diag.as<double>(), flag);                                    \
+    } while (0)
         if (minb >= 8) ASM_LAUNCH(8);
         else if (minb >= 6) ASM_LAUNCH(6);
         else if (minb == 5) ASM_LAUNCH(5);

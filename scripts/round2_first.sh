@@ -6,6 +6,8 @@ for w in c3 c2; do
   python bench.py --workload $w --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r2_bench_${w}_default.json 2> gpurun_out/r2_bench_${w}_default.err
   AVS_PCG_KERNEL=x python bench.py --workload $w --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r2_bench_${w}_x.json 2> gpurun_out/r2_bench_${w}_x.err
 done
+AVS_ASM_ROW=hash python -m pytest tests -m gpu -q --tb=short 2>&1 | tail -3 > gpurun_out/r2_pytest_gpu_hash.log; tail -2 gpurun_out/r2_pytest_gpu_hash.log
+AVS_ASM_ROW=hash python bench.py --workload c3 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r2_bench_c3_hashrow.json 2> gpurun_out/r2_bench_c3_hashrow.err
 python bench.py --workload c4 --steps 2 --warmup 2 > gpurun_out/r2_bench_c4.json 2> gpurun_out/r2_bench_c4.err
 # memcheck + racecheck of one small solve through the C-ABI (sanitizers in CI on the small config)
 cat > /tmp/avs_small.py <<'PY'
