@@ -20,16 +20,16 @@ class GAS_API HDK_AdaptiveViscosity : public GAS_SubSolver
 public:
     // the options the reference reads (HDK_AdaptiveViscosity.h:28-41) -- including the two it reads under names no
     // parameter defines ("fineBandwidth", "doApplySolidWeights"), so behaviour matches bit for bit
-    GET_DATA_FUNC_F(SIM_NAME_TOLERANCE, SolverTolerance);
-    GET_DATA_FUNC_I("maxIterations", MaxIterations);
-    GET_DATA_FUNC_I("numberSuperSamples", NumberSuperSamples);
-    GET_DATA_FUNC_I("octreeLevels", OctreeLevels);
-    GET_DATA_FUNC_I("fineBandwidth", FineBandwidth);
-    GET_DATA_FUNC_B("useEnhancedGradients", UseEnhancedGradients);
-    GET_DATA_FUNC_B("doApplySolidWeights", DoApplySolidWeights);
-    GET_DATA_FUNC_B("doPrintOctree", DoPrintOctree);
-    GET_DATA_FUNC_B("onlyPrintOctree", OnlyPrintOctree);
-    GET_DATA_FUNC_F("extrapolation", Extrapolation);
+    GET_DATA_FUNC_F(SIM_NAME_TOLERANCE, SolverTolerance);            // AV.h:28  -> AvsParams.tolerance
+    GET_DATA_FUNC_I("maxIterations", MaxIterations);                 // AV.h:29  -> max_iterations
+    GET_DATA_FUNC_I("numberSuperSamples", NumberSuperSamples);       // AV.h:30  -> number_super_samples
+    GET_DATA_FUNC_I("octreeLevels", OctreeLevels);                   // AV.h:31  -> octree_levels
+    GET_DATA_FUNC_I("fineBandwidth", FineBandwidth);                 // AV.h:33  -> fine_bandwidth (no parameter of that name: stays 0)
+    GET_DATA_FUNC_B("useEnhancedGradients", UseEnhancedGradients);   // AV.h:35  -> use_enhanced_gradients
+    GET_DATA_FUNC_B("doApplySolidWeights", DoApplySolidWeights);     // AV.h:37  -> do_apply_solid_weights (likewise unset)
+    GET_DATA_FUNC_B("doPrintOctree", DoPrintOctree);                 // AV.h:39  -> avs_get_octree_points
+    GET_DATA_FUNC_B("onlyPrintOctree", OnlyPrintOctree);             // AV.h:40  -> avs_build_octree
+    GET_DATA_FUNC_F("extrapolation", Extrapolation);                 // AV.h:41  -> extrapolation
     // additions of this build
     GET_DATA_FUNC_I("cudaDevice", CudaDevice);
     GET_DATA_FUNC_B("singlePrecision", SinglePrecision);
