@@ -261,3 +261,26 @@ def test_prolongation_linear_exact_over_one_transition():
         out, reg = r3.out_velocity(a), r3.regular_index(a)
         m = reg >= 0
         assert np.abs(out[m] - sc.vel[a].data[m]).max() < 2.5 * sc.dx     # bounded by O(dx * gradient)
+
+
+def test_cg_agrees_with_independent_solvers():
+    """The restated Eigen loop against two independent implementations on the oracle's own system: SciPy's sparse direct solve
+    (the solution) and SciPy's preconditioned CG with the same Jacobi preconditioner, initial guess and relative tolerance (the
+    iteration count -- the textbook PCG recurrence Eigen implements; SciPy tests ||r|| <= rtol ||b|| like Eigen's
+    ||r||^2 < tol^2 ||b||^2)."""
+    import scipy.sparse as sp
+    from adaptiveviscositysolver_b200.scenes import sphere_drop
+    sc = sphere_drop(32, 11, noise=0.01)
+    tight = orc.OracleRun(sc, orc.OracleParams(octree_levels=4, tolerance=1e-12))
+    A = tight.scipy_matrix().tocsc()
+    b, x0 = tight.rhs(), tight.x0()
+    x_direct = spla.spsolve(A, b)
+    assert np.abs(tight.solution() - x_direct).max() < 1e-9 * max(1.0, np.abs(x_direct).max())
+    for tol in (1e-3, 1e-6):
+        run = orc.OracleRun(sc, orc.OracleParams(octree_levels=4, tolerance=tol))
+        count = [0]
+        M = sp.diags(1.0 / A.diagonal())
+        x_sp, info = spla.cg(A, b, x0=x0, rtol=tol, atol=0.0, M=M, maxiter=2500, callback=lambda xk: count.__setitem__(0, count[0] + 1))
+        assert info == 0
+        assert abs(count[0] - run.iterations) <= max(2, run.iterations // 20), (tol, count[0], run.iterations)
+        assert np.abs(x_sp - run.solution()).max() < 50 * tol * np.abs(x_direct).max()
