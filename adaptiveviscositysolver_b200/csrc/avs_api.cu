@@ -120,7 +120,7 @@ void avs_destroy(AvsContext *c) {
     avs_dist_destroy(c);
     DevBuf *bufs[] = {&c->fullSolution, &c->inSurface, &c->inVisc, &c->inDens, &c->inColl, &c->centerW, &c->tiles, &c->brickCount, &c->brickOffset,
                       &c->scanTmp, &c->counters, &c->rowKeys, &c->x0, &c->rhs, &c->solution, &c->rowCount, &c->rowOffset,
-                      &c->csrPtr, &c->csrCol, &c->csrVal, &c->A.sliceOff, &c->A.val, &c->A.col, &c->A.invDiag, &c->A.meta, &c->cg.pcgState, &c->cg.sliceHalo,
+                      &c->csrPtr, &c->csrCol, &c->csrVal, &c->A.sliceOff, &c->A.val, &c->A.col, &c->A.invDiag, &c->A.meta, &c->cg.pcgState, &c->cg.sliceHalo, &c->cg.sliceFlag, &c->cg.sliceIndex, &c->cg.boundaryList, &c->cg.pcgLocal,
                       &c->cg.x, &c->cg.r, &c->cg.p, &c->cg.t, &c->cg.partials, &c->cg.scalars, &c->cgRhs,
                       &c->stageCol, &c->stageVal, &c->diag, &c->slicePairs, &c->edgeTiles, &c->solidW, &c->signA, &c->signB, &c->bandList, &c->brickCost, &c->brickCostPrefix,
                       &c->geoCount, &c->geoOffset, &c->geoPos, &c->geoScale, &c->geoLevel};

@@ -349,6 +349,189 @@ __device__ __forceinline__ double spmvSlices(const SjdsView<T, T2> &A, const T *
         dot += spmvOneSlice<T, T2, DOT, SPMV_U, NC>(s, lane, A, x, y);
     return dot;
 }
+// ---- SpMV slice loop, variant "prefetch" -----------------------------------------------------------
+// Same arithmetic as spmvOneSlice.  Every trip additionally asks L2 for the lines of the slice's value / column stream
+// that the NEXT trip will read (prefetch.global.L2, no destination register), so the dependent chain of a trip is
+// L2 latency (columns) + gather latency instead of DRAM latency + gather latency.
+__device__ __forceinline__ void prefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <class T, class T2, bool DOT, int SPMV_U, bool NC>
+__device__ __forceinline__ double spmvOneSlicePf(long long s, int lane, const SjdsView<T, T2> &A, const T *x, T *y) {
+    double dot = 0;
+    const int m = A.meta[s * 32 + lane];
+    const int np = m & 0xff;
+    const long long r = s * 32 + (m >> 8);
+    const long long base = A.sliceOff[s] + lane;
+    const int maxnp = __shfl_sync(0xffffffffu, np, 0);
+    T acc = 0;
+    long long off = 0;
+    for (int j0 = 0; j0 < maxnp; j0 += SPMV_U) {
+        long long o[SPMV_U];
+        bool act[SPMV_U];
+#pragma unroll
+        for (int u = 0; u < SPMV_U; ++u) {
+            act[u] = (j0 + u) < np;
+            o[u] = base + off;
+            off += __popc(__ballot_sync(0xffffffffu, act[u]));
+        }
+        if (j0 + SPMV_U < maxnp) {   // the next trip's entries start at base - lane + off; <= 32 * SPMV_U of them
+            const long long nx = base - lane + off;
+            if (lane < 4 * SPMV_U) prefetchL2((const char *)(A.val2 + nx) + lane * 128);
+            else if (lane < 6 * SPMV_U) prefetchL2((const char *)(A.col2 + nx) + (lane - 4 * SPMV_U) * 128);
+        }
+        T2 v[SPMV_U];
+        int2 cc[SPMV_U];
+#pragma unroll
+        for (int u = 0; u < SPMV_U; ++u) {
+            v[u].x = 0; v[u].y = 0;
+            cc[u].x = 0; cc[u].y = 0;
+            if (act[u]) { v[u] = A.val2[o[u]]; cc[u] = A.col2[o[u]]; }
+        }
+        T xa[SPMV_U], xb[SPMV_U];
+#pragma unroll
+        for (int u = 0; u < SPMV_U; ++u) {
+            xa[u] = 0; xb[u] = 0;
+            if (act[u]) {
+                if (NC) { xa[u] = __ldg(x + cc[u].x); xb[u] = __ldg(x + cc[u].y); }
+                else { xa[u] = x[cc[u].x]; xb[u] = x[cc[u].y]; }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SPMV_U; ++u) {
+            acc += v[u].x * xa[u];
+            acc += v[u].y * xb[u];
+        }
+    }
+    if (r < A.nrows) {
+        y[r] = acc;
+        if (DOT) dot += (double)(NC ? __ldg(x + r) : x[r]) * (double)acc;
+    }
+    return dot;
+}
+
+// ---- SpMV slice loop, variant "ring" ---------------------------------------------------------------
+// The matrix stream (value pairs + column pairs) of a slice is staged through shared memory by the warp that owns the slice:
+// every lane copies ITS entry of a pair-step with cp.async (LDGSTS, 16 B values / 8 B columns) into a per-warp ring of
+// SPMV_RING pair-steps and later reads back only what it copied itself -- no CTA barrier, no cross-lane hand-over, the
+// warps stay independent.  The ring runs SPMV_RING pair-steps ahead of the gathers, so a trip waits for ONE latency (the
+// gathers of x) instead of two dependent ones (columns, then gathers), and the in-flight matrix bytes need no registers.
+__device__ __forceinline__ uint32_t smemAddr32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cpAsync16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smemAddr32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cpAsync8(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smemAddr32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+template <class T2>
+__device__ __forceinline__ void cpAsyncPair(T2 *dst, const T2 *src) {
+    if (sizeof(T2) == 16) cpAsync16(dst, src); else cpAsync8(dst, src);
+}
+template <class T2, int SPMV_RING>
+__host__ __device__ constexpr size_t spmvRingBytesPerWarp() { return (size_t)SPMV_RING * 32 * (sizeof(T2) + sizeof(int2)); }
+
+// ring: this warp's SPMV_RING * 32 value pairs followed by SPMV_RING * 32 column pairs.  (m, sliceBase) = meta word of this
+// lane and sliceOff[s], loaded by the caller one slice ahead.
+template <class T, class T2, bool DOT, int SPMV_U, bool NC, int SPMV_RING>
+__device__ __forceinline__ double spmvOneSliceRing(long long s, int lane, int m, long long sliceBase, const SjdsView<T, T2> &A, const T *x, T *y,
+                                                   T2 *ringVal, int2 *ringCol) {
+    static_assert(SPMV_RING % SPMV_U == 0, "ring must hold whole trips");
+    constexpr int GROUPS = SPMV_RING / SPMV_U;   // cp.async groups in flight
+    const int np = m & 0xff;
+    const long long r = s * 32 + (m >> 8);
+    const int maxnp = __shfl_sync(0xffffffffu, np, 0);
+    const T2 *gval = A.val2 + sliceBase + lane;
+    const int2 *gcol = A.col2 + sliceBase + lane;
+    int offF = 0, jf = 0;   // fetch side: entries of the slice before pair-step jf
+    auto fetchGroup = [&]() {
+#pragma unroll
+        for (int u = 0; u < SPMV_U; ++u) {
+            const int j = jf + u;
+            const bool a = j < np;
+            if (a) {
+                const int slot = (j & (SPMV_RING - 1)) * 32 + lane;
+                cpAsyncPair<T2>(ringVal + slot, gval + offF);
+                cpAsync8(ringCol + slot, gcol + offF);
+            }
+            offF += __popc(__ballot_sync(0xffffffffu, a));
+        }
+        cpAsyncCommit();
+        jf += SPMV_U;
+    };
+#pragma unroll
+    for (int g = 0; g < GROUPS; ++g) fetchGroup();
+    T acc = 0;
+    for (int jc = 0; jc < maxnp; jc += SPMV_U) {
+        cpAsyncWait<GROUPS - 1>();
+        int2 cc[SPMV_U];
+        bool act[SPMV_U];
+#pragma unroll
+        for (int u = 0; u < SPMV_U; ++u) {
+            act[u] = (jc + u) < np;
+            cc[u].x = 0; cc[u].y = 0;
+            if (act[u]) cc[u] = ringCol[((jc + u) & (SPMV_RING - 1)) * 32 + lane];
+        }
+        T xa[SPMV_U], xb[SPMV_U];
+#pragma unroll
+        for (int u = 0; u < SPMV_U; ++u) {
+            xa[u] = 0; xb[u] = 0;
+            if (act[u]) {
+                if (NC) { xa[u] = __ldg(x + cc[u].x); xb[u] = __ldg(x + cc[u].y); }
+                else { xa[u] = x[cc[u].x]; xb[u] = x[cc[u].y]; }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SPMV_U; ++u) {
+            if (act[u]) {
+                const T2 v = ringVal[((jc + u) & (SPMV_RING - 1)) * 32 + lane];
+                acc += v.x * xa[u];
+                acc += v.y * xb[u];
+            }
+        }
+        fetchGroup();   // refills the slots just read (empty group once the slice is exhausted: keeps the group count uniform)
+    }
+    double dot = 0;
+    if (r < A.nrows) {
+        y[r] = acc;
+        if (DOT) dot = (double)(NC ? __ldg(x + r) : x[r]) * (double)acc;
+    }
+    return dot;
+}
+// static schedule like spmvSlices; meta word and slice offset of the next slice are loaded while the current one runs
+template <class T, class T2, bool DOT, int SPMV_U, bool NC, int SPMV_RING>
+__device__ __forceinline__ double spmvSlicesRing(const SjdsView<T, T2> &A, const T *x, T *y, unsigned char *smemRing) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T2 *ringVal = (T2 *)(smemRing + (size_t)warp * spmvRingBytesPerWarp<T2, SPMV_RING>());
+    int2 *ringCol = (int2 *)(ringVal + SPMV_RING * 32);
+    const long long warpsTotal = ((long long)gridDim.x * CG_THREADS) >> 5;
+    double dot = 0;
+    long long s = ((long long)blockIdx.x * CG_THREADS + threadIdx.x) >> 5;
+    if (s >= A.nslices) return 0;
+    int m = A.meta[s * 32 + lane];
+    long long sb = A.sliceOff[s];
+    while (true) {
+        const long long sn = s + warpsTotal;
+        int mn = 0;
+        long long sbn = 0;
+        if (sn < A.nslices) { mn = A.meta[sn * 32 + lane]; sbn = A.sliceOff[sn]; }
+        dot += spmvOneSliceRing<T, T2, DOT, SPMV_U, NC, SPMV_RING>(s, lane, m, sb, A, x, y, ringVal, ringCol);
+        if (sn >= A.nslices) break;
+        s = sn; m = mn; sb = sbn;
+    }
+    return dot;
+}
+template <class T, class T2, bool DOT, int SPMV_U, bool NC>
+__device__ __forceinline__ double spmvSlicesPf(const SjdsView<T, T2> &A, const T *x, T *y) {
+    const int lane = threadIdx.x & 31;
+    const long long warpsTotal = ((long long)gridDim.x * CG_THREADS) >> 5;
+    double dot = 0;
+    for (long long s = ((long long)blockIdx.x * CG_THREADS + threadIdx.x) >> 5; s < A.nslices; s += warpsTotal)
+        dot += spmvOneSlicePf<T, T2, DOT, SPMV_U, NC>(s, lane, A, x, y);
+    return dot;
+}
+
 // dynamic schedule: warps grab chunks of PCG_CHUNK consecutive slices from a global counter
 #define PCG_CHUNK 4
 template <class T, class T2, bool DOT, int SPMV_U, bool NC>
@@ -373,6 +556,30 @@ __global__ void __launch_bounds__(CG_THREADS) k_spmv_sjds(const __grid_constant_
     if (sc && sc->done) return;
     __shared__ double sh[CG_THREADS / 32 + 1];
     double dot = spmvSlices<T, T2, DOT, SPMV_U, true>(A, x, y);
+    if (DOT) {
+        double t = blockSum(dot, sh);
+        if (threadIdx.x == 0) parts[blockIdx.x] = t;
+    }
+}
+
+template <class T, class T2, bool DOT, int SPMV_U>
+__global__ void __launch_bounds__(CG_THREADS) k_spmv_sjds_pf(const __grid_constant__ SjdsView<T, T2> A, const T *__restrict__ x, T *__restrict__ y,
+                                                             double *__restrict__ parts, const CgScalars *sc) {
+    if (sc && sc->done) return;
+    __shared__ double sh[CG_THREADS / 32 + 1];
+    double dot = spmvSlicesPf<T, T2, DOT, SPMV_U, true>(A, x, y);
+    if (DOT) {
+        double t = blockSum(dot, sh);
+        if (threadIdx.x == 0) parts[blockIdx.x] = t;
+    }
+}
+template <class T, class T2, bool DOT, int SPMV_U, int SPMV_RING>
+__global__ void __launch_bounds__(CG_THREADS) k_spmv_sjds_ring(const __grid_constant__ SjdsView<T, T2> A, const T *__restrict__ x, T *__restrict__ y,
+                                                               double *__restrict__ parts, const CgScalars *sc) {
+    if (sc && sc->done) return;
+    extern __shared__ __align__(128) unsigned char dynSmem[];
+    __shared__ double sh[CG_THREADS / 32 + 1];
+    double dot = spmvSlicesRing<T, T2, DOT, SPMV_U, true, SPMV_RING>(A, x, y, dynSmem);
     if (DOT) {
         double t = blockSum(dot, sh);
         if (threadIdx.x == 0) parts[blockIdx.x] = t;
@@ -807,9 +1014,12 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) k_cg_persistent(const __grid
     __shared__ double rrLast;
     CgScalars *sc = A.sc;
     PcgState *st = A.st;
-    if (sc->done) return;       // uniform: written before the launch
-    const bool dist = A.D.P > 1;
     const bool timer = blockIdx.x == 0 && threadIdx.x == 0;
+    if (sc->done) {             // uniform: written before the launch.  Nothing was exchanged: hand the counters back unchanged
+        if (timer) { st->seqPush = A.D.seqPush; st->seqReduce = A.D.seqReduce; }
+        return;
+    }
+    const bool dist = A.D.P > 1;
     const int G = gridDim.x;
     double rho = sc->rho[0];
     int iters = sc->iters;
@@ -913,111 +1123,105 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) k_cg_persistent(const __grid
     }
 }
 
-// ---- experimental variant of the persistent kernel (AVS_PCG_KERNEL=x; NOT the default, see profiles/r1_experiments.md) ---------
-// Three changes against k_cg_persistent, kept in a kernel of their own so that the default kernel's code generation is untouched:
-//  (1) the SpMV slice loop pins its load schedule: every gather index gets `+ z`, z = (all four column words of the trip OR-ed) >> 31
-//      -- always 0 (local column indices are < 2^31) but not foldable by ptxas -- so no gather can be issued before ALL column loads
-//      of the trip (the slow builds issued gather 0 before column loads 1-3: three dependent latencies per trip instead of two);
-//  (2) flag-in-data scalar all-reduce (the idea of NCCL's LL protocol): no fence between payload and flag;
-//  (3) interior-first SpMV: slices that read no halo slot run before the wait for the peers' halo push.
-// (2) and (3) were parity-green on 2 GPUs and cut 25 us per iteration off the exchange; they were not merged because the build that
-// carried them had the slow SpMV schedule that (1) is meant to rule out.  To be measured in round 2.
-template <class T, class T2, int SPMV_U>
-__device__ __forceinline__ double spmvOneSliceOrdered(long long s, int lane, const SjdsView<T, T2> &A, const T *x, T *y) {
-    const int m = A.meta[s * 32 + lane];
-    const int np = m & 0xff;
-    const long long r = s * 32 + (m >> 8);
-    const long long base = A.sliceOff[s] + lane;
-    const int maxnp = __shfl_sync(0xffffffffu, np, 0);
-    T acc = 0;
-    long long off = 0;
-    for (int j0 = 0; j0 < maxnp; j0 += SPMV_U) {
-        long long o[SPMV_U];
-        bool act[SPMV_U];
-#pragma unroll
-        for (int u = 0; u < SPMV_U; ++u) {
-            act[u] = (j0 + u) < np;
-            o[u] = base + off;
-            off += __popc(__ballot_sync(0xffffffffu, act[u]));
-        }
-        T2 v[SPMV_U];
-        int2 cc[SPMV_U];
-        int all = 0;
-#pragma unroll
-        for (int u = 0; u < SPMV_U; ++u) {
-            v[u].x = 0; v[u].y = 0;
-            cc[u].x = 0; cc[u].y = 0;
-            if (act[u]) { cc[u] = A.col2[o[u]]; v[u] = A.val2[o[u]]; }
-            all |= cc[u].x | cc[u].y;
-        }
-        const int z = all >> 31;   // 0: column indices are non-negative; ties every gather below to all column loads above
-        T xa[SPMV_U], xb[SPMV_U];
-#pragma unroll
-        for (int u = 0; u < SPMV_U; ++u) {
-            xa[u] = 0; xb[u] = 0;
-            if (act[u]) { xa[u] = x[cc[u].x + z]; xb[u] = x[cc[u].y + z]; }
-        }
-#pragma unroll
-        for (int u = 0; u < SPMV_U; ++u) {
-            acc += v[u].x * xa[u];
-            acc += v[u].y * xb[u];
-        }
-    }
-    double dot = 0;
-    if (r < A.nrows) {
-        y[r] = acc;
-        dot = (double)x[r] * (double)acc;
-    }
-    return dot;
-}
+// ---- persistent CG kernel, version 2 (default) ---------------------------------------------------------------------------------
+// Same Eigen loop, same three phases per iteration, but every synchronisation point is ONE wait instead of a chain:
+//  * syncs A and B (after the SpMV: p.Ap; after the x,r update: r.r, r.z) merge the grid barrier, the reduction of the per-CTA
+//    partial sums and the scalar all-reduce over the ranks.  Every CTA stores its partials and bumps an arrival counter; the LAST CTA
+//    to arrive adds the partials in a fixed order and stores the rank's sums straight into the mailbox of every rank (its own
+//    included) as flag-in-data words (32 payload bits + 32-bit sequence number per 8-byte store: no fence between data and flag, the
+//    idea of NCCL's LL protocol).  All CTAs of all ranks then spin on their own rank's mailbox until the P contributions of this
+//    sequence number are there and add them in rank order: bit-identical scalars everywhere, and the arrival of the rank's own
+//    contribution doubles as the grid barrier.  v1 paid barrier + 592 redundant reductions + fence.sys + flag + spin in sequence.
+//  * p is double buffered (p_{k+1} = z + beta p_k is written to the other buffer), so the rows a peer needs are RECOMPUTED from r,
+//    invdiag and p_k by whichever thread gets there first and stored into the peer's halo slots over NVLink before the owner's own
+//    sweep -- no barrier between "p updated" and "halo pushed".  Sync C (last arriver raises localReady and the peers' pushFlag)
+//    is not waited for at all: the next SpMV waits for localReady, runs the slices that read no halo slot, and only then waits for
+//    the peers' pushFlag and runs the boundary slices (about 1 % of the slices), so the NVLink latency hides under the interior SpMV.
+// Single GPU: the same kernel with P = 1 (mailbox and flags in a local header, no remote store).
+struct Pcg2State {                // device-resident, copied back by the host after every launch
+    unsigned long long seqPush, seqReduce;
+    unsigned long long phaseNs[3];    // accumulated %globaltimer time of the SpMV / x,r / p phases (thread 0 of CTA 0)
+    unsigned long long spmvPhases;
+    unsigned int arrive[4];           // arrival counters of syncs A, B, C (zeroed before every launch)
+    int abort;
+    int pad;
+};
 
-// flag[s] = 1 when slice s gathers from a halo slot (local column >= nLocal)
-__global__ void k_slice_needs_halo(long long nslices, const long long *__restrict__ sliceOff, const int2 *__restrict__ col2, int nLocal,
-                                   uint8_t *flag) {
-    const long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (s >= nslices) return;
-    bool hit = false;
-    for (long long i = sliceOff[s] + lane; i < sliceOff[s + 1]; i += 32) {
-        const int2 c = col2[i];
-        hit = hit || c.x >= nLocal || c.y >= nLocal;
-    }
-    const unsigned any = __ballot_sync(0xffffffffu, hit);
-    if (lane == 0) flag[s] = any ? 1 : 0;
-}
-
-// v[0..COUNT): this rank's sums (same bits in every CTA) -> sum over ranks in rank order.  `shw`: P * COUNT * 2 32-bit words.
-template <int COUNT>
-__device__ __forceinline__ bool rankSumLL(double (&v)[COUNT], const PcgDist &D, unsigned long long seq, PcgState *st, unsigned *shw) {
-    const int par = (int)(seq & 1ull);
-    const unsigned long long tag = (seq & 0xffffffffull) << 32;
-    P2PHeader *mine = (P2PHeader *)D.peerRegion[D.myRank];
-    if (blockIdx.x == 0 && threadIdx.x < D.P * COUNT * 2) {
-        const int peerRank = threadIdx.x / (COUNT * 2), q = (threadIdx.x / 2) % COUNT, half = threadIdx.x & 1;
-        P2PHeader *peer = (P2PHeader *)D.peerRegion[peerRank];
-        unsigned long long bits = 0;
-#pragma unroll
-        for (int i = 0; i < COUNT; ++i)
-            if (i == q) bits = (unsigned long long)__double_as_longlong(v[i]);
-        const unsigned long long word = (half ? (bits >> 32) : (bits & 0xffffffffull)) | tag;
-        *(volatile unsigned long long *)&peer->ll[par][D.myRank][q][half] = word;
+__device__ __forceinline__ double reducePartsCg(const double *parts, int n, double *sh /* [CG_THREADS/32 + 1] */) {
+    double v = 0;
+    for (int i = threadIdx.x; i < n; i += CG_THREADS) v += __ldcg(parts + i);
+    v = warpSum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int i = 0; i < CG_THREADS / 32; ++i) t += sh[i];
+        sh[CG_THREADS / 32] = t;
     }
     __syncthreads();
-    if (threadIdx.x < D.P * COUNT * 2) {
-        const int sender = threadIdx.x / (COUNT * 2), q = (threadIdx.x / 2) % COUNT, half = threadIdx.x & 1;
+    return sh[CG_THREADS / 32];
+}
+template <class ST>
+__device__ __forceinline__ bool spinTimedOut(unsigned &spins, unsigned long long &t0, ST *st) {
+    if ((++spins & 0x3ff) != 0) return false;
+    if (*(volatile int *)&st->abort) return true;
+    const unsigned long long now = globalTimerNs();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > PCG_TIMEOUT_NS) { *(volatile int *)&st->abort = 1; return true; }
+    return false;
+}
+
+// v[0..COUNT): this CTA's partial sums (valid in thread 0).  On return: the sums over all CTAs of all ranks, the same bits in every
+// thread of every CTA of every rank.  Doubles as the grid barrier (see above).  shw: 4 * P2P_MAX_RANKS words, shLast: 1 int.
+template <int COUNT>
+__device__ __forceinline__ bool syncSum(double (&v)[COUNT], double *parts, unsigned *counter, unsigned &target, const PcgDist &D, P2PHeader *mine,
+                                        unsigned long long seq, Pcg2State *st, double *sh, unsigned *shw, int *shLast) {
+    const int G = gridDim.x;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < COUNT; ++q) parts[q * G + blockIdx.x] = v[q];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += (unsigned)G;
+        __threadfence();
+        const unsigned prev = atomicAdd(counter, 1u);
+        const int last = (prev + 1u == target) ? 1 : 0;
+        if (last) __threadfence();
+        *shLast = last;
+    }
+    __syncthreads();
+    const int par = (int)(seq & 1ull);
+    const unsigned long long tag = (seq & 0xffffffffull) << 32;
+    const int words = D.P * COUNT * 2;
+    if (*shLast) {   // CTA-uniform
+        double tot[COUNT];
+#pragma unroll
+        for (int q = 0; q < COUNT; ++q) tot[q] = reducePartsCg(parts + q * G, G, sh);
+        if (threadIdx.x < words) {
+            const int peerRank = threadIdx.x / (COUNT * 2), q = (threadIdx.x >> 1) % COUNT, half = threadIdx.x & 1;
+            P2PHeader *peer = (P2PHeader *)D.peerRegion[peerRank];
+            unsigned long long bits = 0;
+#pragma unroll
+            for (int i = 0; i < COUNT; ++i)
+                if (i == q) bits = (unsigned long long)__double_as_longlong(tot[i]);
+            const unsigned long long word = (half ? (bits >> 32) : (bits & 0xffffffffull)) | tag;
+            __threadfence();   // release: everything this rank's CTAs wrote before they arrived is visible before the rank's word
+            *(volatile unsigned long long *)&peer->ll[par][D.myRank][q][half] = word;
+        }
+    }
+    if (threadIdx.x < words) {
+        const int sender = threadIdx.x / (COUNT * 2), q = (threadIdx.x >> 1) % COUNT, half = threadIdx.x & 1;
         const unsigned long long *slot = &mine->ll[par][sender][q][half];
         unsigned long long w = ldVolatileU64(slot), t0 = 0;
         unsigned spins = 0;
         while ((w & 0xffffffff00000000ull) != tag) {
-            if ((++spins & 0x3ff) == 0) {
-                if (*(volatile int *)&st->abort) break;
-                unsigned long long now = globalTimerNs();
-                if (t0 == 0) t0 = now;
-                else if (now - t0 > PCG_TIMEOUT_NS) { *(volatile int *)&st->abort = 1; break; }
-            }
+            if (spinTimedOut(spins, t0, st)) break;
             w = ldVolatileU64(slot);
         }
         shw[threadIdx.x] = (unsigned)(w & 0xffffffffull);
+        __threadfence();       // acquire
     }
     __syncthreads();
     if (*(volatile int *)&st->abort) return false;
@@ -1030,64 +1234,161 @@ __device__ __forceinline__ bool rankSumLL(double (&v)[COUNT], const PcgDist &D, 
         }
         v[q] = t;
     }
-    __syncthreads();
+    __syncthreads();   // shw / shLast are reused by the next sync
     return true;
 }
 
-template <class T, class T2, int SPMV_U>
-__global__ void __launch_bounds__(CG_THREADS, 4) k_cg_persistent_x(const __grid_constant__ PcgArgs<T, T2> A, const uint8_t *__restrict__ sliceHalo) {
+// the one expression for p_{k+1}: the owner's sweep and the halo push must produce the same bits
+__device__ __forceinline__ double pNext(double d, double r, double beta, double p) { return __fma_rn(beta, p, __dmul_rn(d, r)); }
+__device__ __forceinline__ float pNext(float d, float r, float beta, float p) { return __fmaf_rn(beta, p, __fmul_rn(d, r)); }
+
+template <class T, class T2>
+struct Pcg2Args {
+    long long n;
+    SjdsView<T, T2> M;
+    const T *invDiag;
+    T *x, *r, *t;
+    T *p[2];             // the two p buffers (owned rows, then halo slots); iteration k of a launch reads p[(parity0 + k) & 1]
+    double *parts;       // 3 * gridDim.x
+    CgScalars *sc;
+    Pcg2State *st;
+    P2PHeader *mine;     // this rank's header (inside the peer-mapped region when P > 1)
+    int itLimit;
+    int pushFirst;       // 1: first launch of a solve -- p_0 (from k_cg_init, buffer 0) has not been pushed / flagged yet
+    int parity0;         // buffer that holds the current p at kernel entry
+    PcgDist D;
+};
+
+template <class T>
+__device__ __forceinline__ T *peerP(const PcgDist &D, int rank, int buf) {
+    return (T *)((char *)D.peerRegion[rank] + P2P_HEADER_BYTES + (size_t)buf * D.pStrideBytes);
+}
+
+// Sync C: every CTA has written its rows of the new p (and its share of the halo pushes).  Nobody waits here.
+__device__ __forceinline__ void arrivePush(unsigned *counter, unsigned &target, const PcgDist &D, P2PHeader *mine, unsigned long long seq, bool pushedRemote) {
+    if (pushedRemote) __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        if (pushedRemote) __threadfence_system(); else __threadfence();
+        const unsigned prev = atomicAdd(counter, 1u);
+        if (prev + 1u == target) {
+            if (D.P > 1) __threadfence_system(); else __threadfence();
+            *(volatile unsigned long long *)&mine->localReady = seq;
+            for (int q = 0; q < D.P; ++q)
+                if ((D.sendMask >> q) & 1u) *(volatile unsigned long long *)&((P2PHeader *)D.peerRegion[q])->pushFlag[D.myRank] = seq;
+        }
+    }
+}
+__device__ __forceinline__ bool waitLocalReady(P2PHeader *mine, unsigned long long seq, Pcg2State *st) {
+    if (threadIdx.x == 0) {
+        unsigned long long t0 = 0;
+        unsigned spins = 0;
+        while (ldVolatileU64(&mine->localReady) < seq)
+            if (spinTimedOut(spins, t0, st)) break;
+        __threadfence();
+    }
+    __syncthreads();
+    return *(volatile int *)&st->abort == 0;
+}
+__device__ __forceinline__ bool waitHaloReady(const PcgDist &D, P2PHeader *mine, unsigned long long seq, Pcg2State *st) {
+    if (threadIdx.x < D.P && ((D.recvMask >> threadIdx.x) & 1u)) {
+        unsigned long long t0 = 0;
+        unsigned spins = 0;
+        while (ldVolatileU64(&mine->pushFlag[threadIdx.x]) < seq)
+            if (spinTimedOut(spins, t0, st)) break;
+        __threadfence_system();
+    }
+    __syncthreads();
+    return *(volatile int *)&st->abort == 0;
+}
+
+// SPMV_MODE: 0 register-staged slice loop, 1 + L2 prefetch, 2 per-warp cp.async ring (8 pair-steps, trips of 4)
+template <class T, class T2, int SPMV_MODE>
+__device__ __forceinline__ double pcgSlice(long long s, int lane, const SjdsView<T, T2> &M, const T *p, T *t, unsigned char *ring) {
+    if (SPMV_MODE == 2) {
+        const int warp = threadIdx.x >> 5;
+        T2 *ringVal = (T2 *)(ring + (size_t)warp * spmvRingBytesPerWarp<T2, 8>());
+        int2 *ringCol = (int2 *)(ringVal + 8 * 32);
+        return spmvOneSliceRing<T, T2, true, 4, false, 8>(s, lane, M.meta[s * 32 + lane], M.sliceOff[s], M, p, t, ringVal, ringCol);
+    }
+    if (SPMV_MODE == 1) return spmvOneSlicePf<T, T2, true, 4, false>(s, lane, M, p, t);
+    return spmvOneSlice<T, T2, true, 4, false>(s, lane, M, p, t);
+}
+
+template <class T, class T2, int SPMV_MODE, int MINB>
+__global__ void __launch_bounds__(CG_THREADS, MINB) k_cg_persistent2(const __grid_constant__ Pcg2Args<T, T2> A) {
+    extern __shared__ __align__(128) unsigned char dynSmem[];
     __shared__ double sh[CG_THREADS / 32 + 1];
     __shared__ unsigned shw[P2P_MAX_RANKS * 4];
-    __shared__ unsigned long long tm[4];
+    __shared__ int shLast;
+    __shared__ unsigned long long tm[4];   // thread 0 of CTA 0: phase start stamp + 3 accumulators
     __shared__ double rrLast;
     CgScalars *sc = A.sc;
-    PcgState *st = A.st;
-    if (sc->done) return;
-    const bool dist = A.D.P > 1;
+    Pcg2State *st = A.st;
     const bool timer = blockIdx.x == 0 && threadIdx.x == 0;
+    // sequence numbers: reduce #(2k+1), #(2k+2) in iteration k of this launch; push #(seqPush0 + k) feeds iteration k's SpMV
+    const unsigned long long seqPush0 = A.D.seqPush + (unsigned long long)A.pushFirst;
+    if (sc->done) {             // uniform: written before the launch.  Report the counters unchanged (nothing was exchanged).
+        if (timer) { st->seqPush = A.D.seqPush; st->seqReduce = A.D.seqReduce; }
+        return;
+    }
+    const bool dist = A.D.P > 1;
     const int G = gridDim.x;
+    const int lane = threadIdx.x & 31;
+    const long long gwarp = ((long long)blockIdx.x * CG_THREADS + threadIdx.x) >> 5, warpsTotal = ((long long)G * CG_THREADS) >> 5;
+    const long long gid = (long long)blockIdx.x * CG_THREADS + threadIdx.x, gstride = (long long)G * CG_THREADS;
+    const long long n2 = A.n >> 1;
+    const bool pushes = dist && (long long)blockIdx.x * CG_THREADS < A.D.nSend;   // this CTA stores into peer memory
     double rho = sc->rho[0];
     int iters = sc->iters;
     int k = 0;
-    unsigned barTarget = 0, pushTarget = 0;
+    unsigned tgtA = 0, tgtB = 0, tgtC = 0;
     bool stop = false, breakdown = false;
     if (timer) { tm[1] = tm[2] = tm[3] = 0; rrLast = sc->residualNorm2; }
-    const unsigned long long seqPush0 = A.D.seqPush + (unsigned long long)A.pushFirst;
-    const bool twoPass = dist && sliceHalo != nullptr;
-    const int lane = threadIdx.x & 31;
-    const long long warpsTotal = ((long long)G * CG_THREADS) >> 5;
 
-    if (dist && A.pushFirst) pushHalo<T>(A.p, A.D, seqPush0, st, pushTarget);
-    while (iters < A.itLimit) {
-        if (timer) tm[0] = globalTimerNs();
-        // ---- t = A p, partial p.t: interior slices first, the slices on the partition boundary after the halo has landed
-        {
-            double dot = 0;
-            bool okHalo = true;
-            for (int pass = 0; pass < (twoPass ? 2 : 1); ++pass) {
-                if (dist && pass == (twoPass ? 1 : 0) && !(okHalo = waitHalo(A.D, seqPush0 + k, st))) break;
-                for (long long s = ((long long)blockIdx.x * CG_THREADS + threadIdx.x) >> 5; s < A.M.nslices; s += warpsTotal) {
-                    if (twoPass && sliceHalo[s] != pass) continue;
-                    dot += spmvOneSliceOrdered<T, T2, SPMV_U>(s, lane, A.M, A.p, A.t);
-                }
+    if (A.pushFirst) {   // p_0 sits in buffer parity0 (written by k_cg_init): copy the rows the peers need, then flag
+        const T *pc = A.p[A.parity0];
+        if (dist)
+            for (long long i = gid; i < A.D.nSend; i += gstride) {
+                const int2 dst = A.D.sendDst[i];
+                *(volatile T *)(peerP<T>(A.D, dst.x, A.parity0) + dst.y) = pc[A.D.sendIdx[i] - A.D.rowBegin];
             }
-            if (!okHalo) break;
-            double s0 = blockSum(dot, sh);
-            if (threadIdx.x == 0) A.parts[blockIdx.x] = s0;
+        arrivePush(&st->arrive[2], tgtC, A.D, A.mine, seqPush0, pushes);
+    }
+    while (iters < A.itLimit) {
+        const int cur = (A.parity0 + k) & 1;
+        T *pc = A.p[cur], *pn = A.p[cur ^ 1];
+        if (timer) tm[0] = globalTimerNs();
+        // ---- t = A p, partial p.t: slices that read no halo slot first, the boundary slices after the peers' values have landed
+        double pt[1];
+        {
+            if (!waitLocalReady(A.mine, seqPush0 + k, st)) break;
+            double dot = 0;
+            if (!dist) {
+                if (SPMV_MODE == 2) dot = spmvSlicesRing<T, T2, true, 4, false, 8>(A.M, pc, A.t, dynSmem);
+                else
+                    for (long long s = gwarp; s < A.M.nslices; s += warpsTotal) dot += pcgSlice<T, T2, SPMV_MODE>(s, lane, A.M, pc, A.t, dynSmem);
+            } else {
+                for (long long s = gwarp; s < A.M.nslices; s += warpsTotal)
+                    if (!A.D.sliceHalo[s]) dot += pcgSlice<T, T2, SPMV_MODE>(s, lane, A.M, pc, A.t, dynSmem);
+                if (!waitHaloReady(A.D, A.mine, seqPush0 + k, st)) break;
+                for (long long i = gwarp; i < A.D.nBoundary; i += warpsTotal)
+                    dot += pcgSlice<T, T2, SPMV_MODE>((long long)A.D.boundarySlices[i], lane, A.M, pc, A.t, dynSmem);
+            }
+            pt[0] = blockSum(dot, sh);
         }
-        if (!gridBarrier(st, barTarget)) break;
-        if (timer) { unsigned long long now = globalTimerNs(); tm[1] += now - tm[0]; tm[0] = now; }
-        double pt[1] = {reduceParts(A.parts, G, sh)};
-        if (dist && !rankSumLL<1>(pt, A.D, A.D.seqReduce + 2ull * k + 1, st, shw)) break;
+        if (!syncSum<1>(pt, A.parts, &st->arrive[0], tgtA, A.D, A.mine, A.D.seqReduce + 2ull * k + 1, st, sh, shw, &shLast)) break;
+        if (timer) { const unsigned long long now = globalTimerNs(); tm[1] += now - tm[0]; tm[0] = now; }
         const double alphaD = rho / pt[0];
         breakdown = !isfinite(alphaD);
         const T alpha = breakdown ? (T)0 : (T)alphaD;
+        // ---- x += alpha p, r -= alpha t, partial r.r and r.z (two elements per thread and trip: 128-bit accesses for fp64)
+        double rs[2];
         {
             double rr = 0, rz = 0;
-            const long long gid = (long long)blockIdx.x * CG_THREADS + threadIdx.x, gstride = (long long)G * CG_THREADS;
-            const long long n2 = A.n >> 1;
             for (long long j = gid; j < n2; j += gstride) {
-                const T2 pv = ((const T2 *)A.p)[j], tv = ((const T2 *)A.t)[j], dv = ((const T2 *)A.invDiag)[j];
+                const T2 pv = ((const T2 *)pc)[j], tv = ((const T2 *)A.t)[j], dv = ((const T2 *)A.invDiag)[j];
                 T2 rv = ((T2 *)A.r)[j], xv = ((T2 *)A.x)[j];
                 rv.x -= alpha * tv.x; rv.y -= alpha * tv.y;
                 xv.x += alpha * pv.x; xv.y += alpha * pv.y;
@@ -1099,41 +1400,39 @@ __global__ void __launch_bounds__(CG_THREADS, 4) k_cg_persistent_x(const __grid_
             if ((A.n & 1) && gid == 0) {
                 const long long i = A.n - 1;
                 T ri = A.r[i] - alpha * A.t[i];
-                A.x[i] += alpha * A.p[i];
+                A.x[i] += alpha * pc[i];
                 A.r[i] = ri;
                 rr += (double)ri * (double)ri;
                 rz += (double)ri * (double)(T)(A.invDiag[i] * ri);
             }
-            double s0 = blockSum(rr, sh), s1 = blockSum(rz, sh);
-            if (threadIdx.x == 0) { A.parts[G + blockIdx.x] = s0; A.parts[2 * G + blockIdx.x] = s1; }
+            rs[0] = blockSum(rr, sh);
+            rs[1] = blockSum(rz, sh);
         }
-        if (!gridBarrier(st, barTarget)) break;
-        if (timer) { unsigned long long now = globalTimerNs(); tm[2] += now - tm[0]; tm[0] = now; }
-        double rs[2];
-        rs[0] = reduceParts(A.parts + G, G, sh);
-        rs[1] = reduceParts(A.parts + 2 * G, G, sh);
-        if (dist && !rankSumLL<2>(rs, A.D, A.D.seqReduce + 2ull * k + 2, st, shw)) break;
+        if (!syncSum<2>(rs, A.parts + G, &st->arrive[1], tgtB, A.D, A.mine, A.D.seqReduce + 2ull * k + 2, st, sh, shw, &shLast)) break;
+        if (timer) { const unsigned long long now = globalTimerNs(); tm[2] += now - tm[0]; tm[0] = now; }
         ++k;
         if (timer) rrLast = rs[0];
         stop = (rs[0] < sc->threshold) || breakdown;
-        if (stop) break;
+        if (stop) break;                       // Eigen: break before ++i
+        // ---- p_{k+1} = z + beta p_k into the other buffer; the rows the peers need go out first
         const T beta = (T)(rs[1] / rho);
         rho = rs[1];
         ++iters;
-        {
-            const long long gid = (long long)blockIdx.x * CG_THREADS + threadIdx.x, gstride = (long long)G * CG_THREADS;
-            const long long n2 = A.n >> 1;
-            for (long long j = gid; j < n2; j += gstride) {
-                const T2 dv = ((const T2 *)A.invDiag)[j], rv = ((const T2 *)A.r)[j];
-                T2 pv = ((T2 *)A.p)[j];
-                pv.x = dv.x * rv.x + beta * pv.x;
-                pv.y = dv.y * rv.y + beta * pv.y;
-                ((T2 *)A.p)[j] = pv;
+        if (dist)
+            for (long long i = gid; i < A.D.nSend; i += gstride) {
+                const long long row = A.D.sendIdx[i] - A.D.rowBegin;
+                const int2 dst = A.D.sendDst[i];
+                *(volatile T *)(peerP<T>(A.D, dst.x, cur ^ 1) + dst.y) = pNext(A.invDiag[row], __ldcg(A.r + row), beta, pc[row]);
             }
-            if ((A.n & 1) && gid == 0) { const long long i = A.n - 1; A.p[i] = A.invDiag[i] * A.r[i] + beta * A.p[i]; }
+        for (long long j = gid; j < n2; j += gstride) {
+            const T2 dv = ((const T2 *)A.invDiag)[j], rv = ((const T2 *)A.r)[j], pv = ((const T2 *)pc)[j];
+            T2 o;
+            o.x = pNext(dv.x, rv.x, beta, pv.x);
+            o.y = pNext(dv.y, rv.y, beta, pv.y);
+            ((T2 *)pn)[j] = o;
         }
-        if (!gridBarrier(st, barTarget)) break;
-        if (dist) pushHalo<T>(A.p, A.D, seqPush0 + k, st, pushTarget);
+        if ((A.n & 1) && gid == 0) { const long long i = A.n - 1; pn[i] = pNext(A.invDiag[i], A.r[i], beta, pc[i]); }
+        arrivePush(&st->arrive[2], tgtC, A.D, A.mine, seqPush0 + k, pushes);
         if (timer) tm[3] += globalTimerNs() - tm[0];
     }
     if (timer) {
@@ -1143,6 +1442,7 @@ __global__ void __launch_bounds__(CG_THREADS, 4) k_cg_persistent_x(const __grid_
         sc->residualNorm2 = rrLast;
         if (breakdown) sc->breakdown = 1;
         if (stop) sc->done = 1;
+        // k counts completed (SpMV, x/r) phase pairs; a stopped iteration did both reduces but no p update / push
         st->seqReduce = A.D.seqReduce + 2ull * k;
         st->seqPush = seqPush0 + (stop ? k - 1 : k);
         st->phaseNs[0] += tm[1];
@@ -1150,6 +1450,25 @@ __global__ void __launch_bounds__(CG_THREADS, 4) k_cg_persistent_x(const __grid_
         st->phaseNs[2] += tm[3];
         st->spmvPhases += k;
     }
+}
+
+// flag[s] = 1 when slice s gathers from a halo slot (local column >= nLocal)
+__global__ void k_slice_needs_halo(long long nslices, const long long *__restrict__ sliceOff, const int2 *__restrict__ col2, int nLocal,
+                                   uint8_t *flag, int32_t *flag32) {
+    const long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (s >= nslices) return;
+    bool hit = false;
+    for (long long i = sliceOff[s] + lane; i < sliceOff[s + 1]; i += 32) {
+        const int2 c = col2[i];
+        hit = hit || c.x >= nLocal || c.y >= nLocal;
+    }
+    const unsigned any = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) { flag[s] = any ? 1 : 0; flag32[s] = any ? 1 : 0; }
+}
+__global__ void k_compact_slices(long long nslices, const uint8_t *flag, const long long *index, int32_t *list) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < nslices && flag[s]) list[index[s]] = (int32_t)s;
 }
 
 template <class T>
@@ -1182,17 +1501,15 @@ static bool cgUsePersistent() {
     }
     return t == 1;
 }
-// AVS_PCG_MINB=5 selects the variant whose register allocation aims at 5 resident CTAs per SM (measured at C3: spills,
-// no faster than the default 4); AVS_PCG_DYN=1 the dynamic slice schedule (measured slower: 0.51 vs 0.46 ms per SpMV).
-// AVS_PCG_KERNEL=x selects the experimental kernel k_cg_persistent_x (pinned load schedule, flag-in-data all-reduce,
-// interior-first SpMV) -- parity-tested pieces, not yet measured as a whole; off by default.
-static bool pcgExperimental() {
-    static int x = -1;
-    if (x < 0) {
+// AVS_PCG_KERNEL=v1 selects round 1's persistent kernel (three grid barriers + separate all-reduce and halo push per iteration;
+// kept for A/B measurements); the default is k_cg_persistent2.  AVS_PCG_MINB=5 (v1 only): register allocation for 5 CTAs per SM.
+static int pcgVersion() {
+    static int v = -1;
+    if (v < 0) {
         const char *e = getenv("AVS_PCG_KERNEL");
-        x = (e && e[0] == 'x') ? 1 : 0;
+        v = (e && strcmp(e, "v1") == 0) ? 1 : 2;
     }
-    return x == 1;
+    return v;
 }
 template <class T, class T2>
 static const void *pcgKernel() {
@@ -1201,9 +1518,35 @@ static const void *pcgKernel() {
         const char *e = getenv("AVS_PCG_MINB");
         minb = e ? atoi(e) : 4;
     }
-    if (pcgExperimental()) return (const void *)k_cg_persistent_x<T, T2, 4>;
     if (minb == 5) return (const void *)k_cg_persistent<T, T2, 4, 5>;
     return (const void *)k_cg_persistent<T, T2, 4, 4>;
+}
+// AVS_SPMV_MODE selects the slice loop of the stand-alone SpMV kernel and of the persistent CG kernel:
+//   base (default) register-staged | pf = + L2 prefetch of the next trip | ring = matrix stream staged through a per-warp cp.async ring
+static int spmvMode() {
+    static int m = -1;
+    if (m < 0) {
+        const char *e = getenv("AVS_SPMV_MODE");
+        m = 0;
+        if (e && strcmp(e, "pf") == 0) m = 1;
+        if (e && strcmp(e, "ring") == 0) m = 2;
+        if (e && strcmp(e, "ring4") == 0) m = 3;
+    }
+    return m;
+}
+template <class T, class T2>
+static const void *pcg2Kernel(size_t *smemOut) {
+    const void *k;
+    size_t smem = 0;
+    switch (spmvMode()) {
+        case 1: k = (const void *)k_cg_persistent2<T, T2, 1, 4>; break;
+        case 2:
+        case 3: k = (const void *)k_cg_persistent2<T, T2, 2, 4>; smem = (CG_THREADS / 32) * spmvRingBytesPerWarp<T2, 8>(); break;
+        default: k = (const void *)k_cg_persistent2<T, T2, 0, 4>; break;
+    }
+    if (smem) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    *smemOut = smem;
+    return k;
 }
 static bool spmvUseTma() {
     static int t = -1;
@@ -1232,6 +1575,21 @@ static void launchSpmv(AvsContext *c, SellMatrix &A, const T *x, T *y, double *p
             attrSet[DOT] = true;
         }
         k_spmv_tma<T, T2, DOT><<<grid, TMA_THREADS, smem, c->stream>>>(sjdsView<T, T2>(A), x, y, parts, sc);
+    } else if (spmvMode() >= 2) {   // per-warp cp.async ring: 8 pair-steps in trips of 4 (mode 2) or 4 pair-steps in trips of 2 (mode 3)
+#define RING_LAUNCH(U, R)                                                                                                        \
+    {                                                                                                                            \
+        static bool attrSet = false;                                                                                             \
+        const size_t smem = (CG_THREADS / 32) * spmvRingBytesPerWarp<T2, R>();                                                   \
+        if (!attrSet) {                                                                                                          \
+            cudaFuncSetAttribute(k_spmv_sjds_ring<T, T2, DOT, U, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+            attrSet = true;                                                                                                      \
+        }                                                                                                                        \
+        k_spmv_sjds_ring<T, T2, DOT, U, R><<<grid, CG_THREADS, smem, c->stream>>>(sjdsView<T, T2>(A), x, y, parts, sc);          \
+    }
+        if (spmvMode() == 2) RING_LAUNCH(4, 8) else RING_LAUNCH(2, 4)
+#undef RING_LAUNCH
+    } else if (spmvMode() == 1) {   // L2 prefetch of the next trip
+        k_spmv_sjds_pf<T, T2, DOT, 4><<<grid, CG_THREADS, 0, c->stream>>>(sjdsView<T, T2>(A), x, y, parts, sc);
     } else {
 #define SPMV_LAUNCH(U) k_spmv_sjds<T, T2, DOT, U><<<grid, CG_THREADS, 0, c->stream>>>(sjdsView<T, T2>(A), x, y, parts, sc)
         switch (spmvU()) {
@@ -1255,6 +1613,17 @@ static int spmvGrid(AvsContext *c, long long nslices) {
     }
     int perSM = 0;
     cudaError_t e;
+    if (spmvMode() == 2) {
+        const size_t smem = (CG_THREADS / 32) * spmvRingBytesPerWarp<T2, 8>();
+        cudaFuncSetAttribute(k_spmv_sjds_ring<T, T2, true, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_spmv_sjds_ring<T, T2, true, 4, 8>, CG_THREADS, smem);
+    } else if (spmvMode() == 3) {
+        const size_t smem = (CG_THREADS / 32) * spmvRingBytesPerWarp<T2, 4>();
+        cudaFuncSetAttribute(k_spmv_sjds_ring<T, T2, true, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_spmv_sjds_ring<T, T2, true, 2, 4>, CG_THREADS, smem);
+    } else if (spmvMode() == 1)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_spmv_sjds_pf<T, T2, true, 4>, CG_THREADS, 0);
+    else
     switch (spmvU()) {
         case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_spmv_sjds<T, T2, true, 2>, CG_THREADS, 0); break;
         case 8: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_spmv_sjds<T, T2, true, 8>, CG_THREADS, 0); break;
@@ -1291,7 +1660,10 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
     int pgrid = 0;   // persistent CG kernel: all CTAs co-resident (cooperative launch)
     {
         int perSM = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, pcgKernel<T, T2>(), CG_THREADS, 0);
+        size_t smem2 = 0;
+        const void *k2 = pcg2Kernel<T, T2>(&smem2);
+        cudaError_t e = pcgVersion() == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k2, CG_THREADS, smem2)
+                                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, pcgKernel<T, T2>(), CG_THREADS, 0);
         if (e != cudaSuccess || perSM < 1) { cudaGetLastError(); perSM = 1; }
         const char *env = getenv("AVS_PCG_CTAS_PER_SM");
         if (env && atoi(env) >= 1) perSM = std::min(perSM, atoi(env));
@@ -1302,7 +1674,8 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
     const long long nHalo = dist ? c->nHalo : 0;
     const size_t vb = (size_t)std::max<long long>(n, 1) * sizeof(T);
     if (w.x.reserve(vb) || w.r.reserve(vb) || w.t.reserve(vb)) return AVS_ERR_ALLOC;
-    if (w.p.reserve((size_t)std::max<long long>(n + nHalo, 1) * sizeof(T))) return AVS_ERR_ALLOC;  // owned rows + halo slots
+    const long long pPad = (n + nHalo + 63) & ~63ll;   // single GPU: the persistent kernel's second p buffer starts here
+    if (w.p.reserve((size_t)std::max<long long>(2 * pPad, 1) * sizeof(T))) return AVS_ERR_ALLOC;  // owned rows + halo slots, double buffered
     DevBuf &bbuf = c->cgRhs;
     if (bbuf.reserve(vb)) return AVS_ERR_ALLOC;
     if (w.partials.reserve(((size_t)std::max(grid, pgrid) * 3 + (size_t)sgrid + 16) * sizeof(double))) return AVS_ERR_ALLOC;
@@ -1349,8 +1722,104 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
     CgScalars *hs = (CgScalars *)c->hostScalars;  // pinned
     PcgDist pd;
     const bool persistent = cgUsePersistent() && (!dist || avs_dist_pcg_args(c, &pd));
-    if (persistent) {
-        // ---- one cooperative launch per `check_every` iterations (default: all of them) -------------------------------
+    if (persistent && pcgVersion() == 2) {
+        // ---- k_cg_persistent2: one cooperative launch per `check_every` iterations (default: all of them) ----------------
+        if (w.pcgState.reserve(sizeof(Pcg2State) + 64)) return AVS_ERR_ALLOC;
+        Pcg2State *st = w.pcgState.as<Pcg2State>();
+        Pcg2State *hst = (Pcg2State *)((char *)c->hostScalars + 256);
+        AVS_CUDA_CHECK(cudaMemsetAsync(st, 0, sizeof(Pcg2State), c->stream));
+        Pcg2Args<T, T2> ka;
+        ka.n = n;
+        ka.M = sjdsView<T, T2>(A);
+        ka.invDiag = A.invDiag.as<T>();
+        ka.x = x; ka.r = r; ka.t = t;
+        ka.parts = parts; ka.sc = sc; ka.st = st;
+        ka.pushFirst = 1;
+        ka.parity0 = 0;
+        if (dist) {
+            ka.D = pd;
+            ka.p[0] = pp;
+            ka.p[1] = (T *)((char *)pp + pd.pStrideBytes);
+            ka.mine = (P2PHeader *)((char *)pp - P2P_HEADER_BYTES);
+            // slices that gather from a halo slot run after the peers' values have landed: flag them, list them in ascending order
+            if (w.sliceHalo.reserve((size_t)std::max<long long>(A.nslices, 1)) || w.sliceFlag.reserve((size_t)std::max<long long>(A.nslices, 1) * 4) ||
+                w.sliceIndex.reserve((size_t)(std::max<long long>(A.nslices, 1) + 1) * 8))
+                return AVS_ERR_ALLOC;
+            int64_t nBoundary = 0;
+            if (A.nslices > 0) {
+                k_slice_needs_halo<<<(unsigned)((A.nslices * 32 + 255) / 256), 256, 0, c->stream>>>(A.nslices, A.sliceOff.as<long long>(), A.col.as<int2>(), (int)n,
+                                                                                          w.sliceHalo.as<uint8_t>(), w.sliceFlag.as<int32_t>());
+                ++c->launches;
+                int rcs = avs_exclusive_scan_i32_to_i64(c, w.sliceFlag.as<int32_t>(), w.sliceIndex.as<int64_t>(), A.nslices, &nBoundary);
+                if (rcs) return rcs;
+            }
+            if (w.boundaryList.reserve((size_t)std::max<int64_t>(nBoundary, 1) * 4)) return AVS_ERR_ALLOC;
+            if (nBoundary > 0) {
+                k_compact_slices<<<(unsigned)((A.nslices + 255) / 256), 256, 0, c->stream>>>(A.nslices, w.sliceHalo.as<uint8_t>(), w.sliceIndex.as<long long>(),
+                                                                                   w.boundaryList.as<int32_t>());
+                ++c->launches;
+            }
+            ka.D.sliceHalo = w.sliceHalo.as<uint8_t>();
+            ka.D.boundarySlices = w.boundaryList.as<int32_t>();
+            ka.D.nBoundary = nBoundary;
+            c->pcgBoundarySlices = nBoundary;
+        } else {
+            // single GPU: mailbox + flags in a local header, "peer table" with one entry
+            if (w.pcgLocal.reserve(P2P_HEADER_BYTES + P2P_MAX_RANKS * sizeof(void *))) return AVS_ERR_ALLOC;
+            AVS_CUDA_CHECK(cudaMemsetAsync(w.pcgLocal.p, 0, P2P_HEADER_BYTES, c->stream));
+            void *self = w.pcgLocal.p;
+            AVS_CUDA_CHECK(cudaMemcpyAsync((char *)w.pcgLocal.p + P2P_HEADER_BYTES, &self, sizeof(void *), cudaMemcpyHostToDevice, c->stream));
+            ka.D = PcgDist();
+            ka.D.peerRegion = (void *const *)((char *)w.pcgLocal.p + P2P_HEADER_BYTES);
+            ka.p[0] = pp;
+            ka.p[1] = pp + pPad;
+            ka.mine = (P2PHeader *)w.pcgLocal.p;
+        }
+        size_t smem2 = 0;
+        const void *kern = pcg2Kernel<T, T2>(&smem2);
+        const int chunk = p->check_every > 0 ? p->check_every : (p->cancel ? 256 : maxIters);
+        int itersKnown = 0;
+        while (true) {
+            ka.itLimit = std::min(maxIters, itersKnown + std::max(chunk, 1));
+            void *kargs[] = {(void *)&ka};
+            AVS_CUDA_CHECK(cudaEventRecord(c->evPcg[0], c->stream));
+            AVS_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(pgrid), dim3(CG_THREADS), kargs, smem2, c->stream));
+            AVS_CUDA_CHECK(cudaEventRecord(c->evPcg[1], c->stream));
+            ++c->launches;
+            ++c->pcgLaunches;
+            AVS_CUDA_CHECK(cudaMemcpyAsync(&hs[0], sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, c->stream));
+            AVS_CUDA_CHECK(cudaMemcpyAsync(hst, st, sizeof(Pcg2State), cudaMemcpyDeviceToHost, c->stream));
+            AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            {
+                float ms = 0;
+                if (cudaEventElapsedTime(&ms, c->evPcg[0], c->evPcg[1]) == cudaSuccess) c->pcgKernelMs += ms;
+            }
+            if (hst->abort) {
+                c->lastError = "persistent CG kernel timed out waiting for its own CTAs or a peer";
+                avs_set_last_error("k_cg_persistent2 (spin-wait timeout)", cudaErrorLaunchTimeout, __FILE__, __LINE__);
+                return AVS_ERR_CUDA;
+            }
+            ka.parity0 = (ka.parity0 + (hs[0].iters - itersKnown)) & 1;   // one buffer flip per completed p update
+            itersKnown = hs[0].iters;
+            ka.pushFirst = 0;
+            ka.D.seqPush = hst->seqPush;
+            ka.D.seqReduce = hst->seqReduce;
+            if (hs[0].done || itersKnown >= maxIters) break;
+            if (p->cancel && *p->cancel) {
+                if (dist) avs_dist_pcg_commit(c, hst->seqPush, hst->seqReduce);
+                return AVS_ERR_CANCELLED;
+            }
+            // arrival counters restart with every launch
+            AVS_CUDA_CHECK(cudaMemsetAsync((char *)st + offsetof(Pcg2State, arrive), 0, 4 * sizeof(unsigned int), c->stream));
+        }
+        if (dist) avs_dist_pcg_commit(c, hst->seqPush, hst->seqReduce);
+        c->pcgSpmvMs = (float)(hst->phaseNs[0] * 1e-6);
+        c->pcgXrMs = (float)(hst->phaseNs[1] * 1e-6);
+        c->pcgPMs = (float)(hst->phaseNs[2] * 1e-6);
+        c->pcgPhases = (int64_t)hst->spmvPhases;
+        c->pcgUsed = true;
+    } else if (persistent) {
+        // ---- round 1's kernel (AVS_PCG_KERNEL=v1) -----------------------------------------------------------------------
         if (w.pcgState.reserve(sizeof(PcgState))) return AVS_ERR_ALLOC;
         PcgState *st = w.pcgState.as<PcgState>();
         PcgState *hst = (PcgState *)((char *)c->hostScalars + 256);
@@ -1364,19 +1833,11 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
         ka.D = dist ? pd : PcgDist();
         ka.pushFirst = 1;
         { const char *env = getenv("AVS_PCG_DYN"); ka.dynamic = (env && env[0] == '1') ? 1 : 0; }
-        const uint8_t *sliceHalo = nullptr;
-        if (pcgExperimental() && dist && A.nslices > 0) {
-            if (w.sliceHalo.reserve((size_t)A.nslices)) return AVS_ERR_ALLOC;
-            k_slice_needs_halo<<<(unsigned)((A.nslices * 32 + 255) / 256), 256, 0, c->stream>>>(A.nslices, A.sliceOff.as<long long>(), A.col.as<int2>(),
-                                                                                      (int)n, w.sliceHalo.as<uint8_t>());
-            ++c->launches;
-            sliceHalo = w.sliceHalo.as<uint8_t>();
-        }
         const int chunk = p->check_every > 0 ? p->check_every : (p->cancel ? 256 : maxIters);
         int itersKnown = 0;
         while (true) {
             ka.itLimit = std::min(maxIters, itersKnown + std::max(chunk, 1));
-            void *kargs[] = {(void *)&ka, (void *)&sliceHalo};   // the default kernel takes one parameter, the experimental one two
+            void *kargs[] = {(void *)&ka};
             AVS_CUDA_CHECK(cudaEventRecord(c->evPcg[0], c->stream));
             AVS_CUDA_CHECK(cudaLaunchCooperativeKernel(pcgKernel<T, T2>(), dim3(pgrid), dim3(CG_THREADS), kargs, 0, c->stream));
             AVS_CUDA_CHECK(cudaEventRecord(c->evPcg[1], c->stream));

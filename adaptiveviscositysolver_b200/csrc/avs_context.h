@@ -55,7 +55,8 @@ struct CgWork {
     DevBuf partials;        // per-CTA partial sums
     DevBuf scalars;         // device-resident CG scalars
     DevBuf pcgState;        // PcgState of the persistent CG kernel
-    DevBuf sliceHalo;       // experimental kernel: uint8 per slice, 1 = reads a halo slot
+    DevBuf sliceHalo, sliceFlag, sliceIndex, boundaryList;  // multi-GPU: slices that read a halo slot (flag u8 / i32, scan, ascending list)
+    DevBuf pcgLocal;        // single GPU: the persistent kernel's mailbox header + one-entry peer table
 };
 
 struct AvsContext {
@@ -120,6 +121,7 @@ struct AvsContext {
     int pcgLaunches = 0;
     cudaEvent_t evPcg[2] = {};
     int64_t pcgPhases = 0;
+    int64_t pcgBoundarySlices = 0;
     float spmvMs = 0.f;
     cudaEvent_t ev[AVS_STAGE_COUNT + 2] = {};
 };

@@ -403,7 +403,7 @@ void *avs_dist_prepare_p(AvsContext *c, int *rcOut) {
     *rcOut = AVS_OK;
     if (!d || !d->p2p) return nullptr;
     const long long nLocal = c->rowEnd - c->rowBegin;
-    int rc = p2pEnsureRegion(c, (size_t)(nLocal + d->nHalo + 64));
+    int rc = p2pEnsureRegion(c, 2 * (size_t)(nLocal + d->nHalo + 64) + 64);   // two p buffers (the persistent kernel double-buffers p)
     if (rc) { *rcOut = rc; return nullptr; }
     if (!d->p2p) return nullptr;
     if (d->haloSrc.reserve((size_t)std::max<long long>(d->nHalo, 1) * sizeof(int2))) { *rcOut = AVS_ERR_ALLOC; return nullptr; }
@@ -452,6 +452,8 @@ bool avs_dist_pcg_args(AvsContext *c, PcgDist *out) {
     }
     a.seqPush = d->seqPush;
     a.seqReduce = d->seqReduce;
+    // regionBytes is the same on every rank (p2pEnsureRegion agrees on the maximum), hence so is the buffer distance
+    a.pStrideBytes = ((unsigned long long)(d->regionBytes - P2P_HEADER_BYTES) / 2) & ~255ull;
     *out = a;
     return true;
 }

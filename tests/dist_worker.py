@@ -25,6 +25,13 @@ def main():
     dist.broadcast_object_list(uid, src=0)
     s = Solver(device=local, rank=rank, nranks=world, nccl_unique_id=uid[0])
     ok = True
+    # A solve that converges before its first iteration (zero rhs: fluid at rest) must leave the in-kernel exchange's sequence
+    # counters where the peers' flags are -- the solves below run on the same context right after it.
+    rest = sphere_drop(32, 11)
+    for v in rest.vel:
+        v.data[...] = 0
+    info0 = s.solve(rest, Params(octree_levels=4, tolerance=1e-8))
+    assert info0.iterations == 0 and info0.error == 0, (info0.iterations, info0.error)
     for n, R, L in ((32, 11, 4), (64, 26, 6)):
         sc = sphere_drop(n, R, noise=0.01)
         tol = 1e-10

@@ -14,10 +14,11 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-@pytest.mark.parametrize("mode", ["persistent", "launch", "nccl"])
+@pytest.mark.parametrize("mode", ["persistent", "persistent_ring", "persistent_v1", "launch", "nccl"])
 @pytest.mark.parametrize("world", [2])
 def test_multi_gpu_solve_matches_oracle(world, mode):
-    """persistent: in-kernel halo push + scalar all-reduce over peer memory (default); launch: one kernel per step with
+    """persistent: k_cg_persistent2, in-kernel halo push + scalar all-reduce over peer memory (default; _ring = with the cp.async
+    slice loop, _v1 = round 1's kernel); launch: one kernel per step with
     the peer-memory exchange kernels (AVS_CG_MODE=launch); nccl: grouped send/recv + ncclAllReduce (AVS_DIST_MODE=nccl)."""
     import os
     import torch
@@ -26,7 +27,12 @@ def test_multi_gpu_solve_matches_oracle(world, mode):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), str(ROOT / "tests" / "dist_worker.py")]
     env = dict(os.environ)
-    env.pop("AVS_CG_MODE", None); env.pop("AVS_DIST_MODE", None)
+    for k in ("AVS_CG_MODE", "AVS_DIST_MODE", "AVS_PCG_KERNEL", "AVS_SPMV_MODE"):
+        env.pop(k, None)
+    if mode == "persistent_v1":
+        env["AVS_PCG_KERNEL"] = "v1"
+    if mode == "persistent_ring":
+        env["AVS_SPMV_MODE"] = "ring"
     if mode == "launch":
         env["AVS_CG_MODE"] = "launch"
     if mode == "nccl":
