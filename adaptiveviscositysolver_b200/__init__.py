@@ -9,7 +9,7 @@ from .scenes import SampledField, Scene, sphere_drop  # noqa: F401
 
 
 def __getattr__(name):  # lazy: importing the package must work on a box without the built library
-    if name in ("Solver", "Params", "HDK_AdaptiveViscosity", "SIM_Object", "SolveInfo"):
+    if name in ("Solver", "MultiSolver", "Params", "HDK_AdaptiveViscosity", "SIM_Object", "SolveInfo"):
         from . import solver
         return getattr(solver, name)
     raise AttributeError(name)

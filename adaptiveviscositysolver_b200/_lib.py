@@ -22,6 +22,7 @@ EXPORTS = [
     "avs_solve", "avs_assemble", "avs_solve_resident", "avs_apply", "avs_get_sizes", "avs_get_keys",
     "avs_get_system_csr", "avs_get_solution", "avs_get_grid", "avs_cg_csr", "avs_spmv_csr", "avs_time_spmv_resident",
     "avs_build_octree", "avs_get_octree_points",
+    "avs_create_multi", "avs_destroy_multi", "avs_multi_size", "avs_multi_context", "avs_solve_multi",
 ]
 
 
@@ -110,6 +111,13 @@ def load():
     L.avs_time_spmv_resident.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double)]
     L.avs_build_octree.argtypes = [vp, C.POINTER(AvsFields), C.POINTER(AvsParams), C.POINTER(AvsResult)]
     L.avs_get_octree_points.argtypes = [vp, C.POINTER(C.c_int64), vp, vp, vp]
+    L.avs_create_multi.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.avs_destroy_multi.argtypes = [vp]
+    L.avs_destroy_multi.restype = None
+    L.avs_multi_size.argtypes = [vp]
+    L.avs_multi_context.argtypes = [vp, C.c_int]
+    L.avs_multi_context.restype = vp
+    L.avs_solve_multi.argtypes = [vp, C.POINTER(AvsFields), C.POINTER(AvsParams), C.POINTER(AvsVelocityOut), C.POINTER(AvsResult)]
     for name in EXPORTS:
         getattr(L, name)  # every symbol of include/avs.h must be exported
     _lib = L

@@ -5,6 +5,9 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "avs_context.h"
 
@@ -56,7 +59,10 @@ void avs_default_params(AvsParams *p) {
     p->cancel = nullptr;
 }
 
-int avs_create(const AvsDeviceConfig *cfg, AvsContext **out) {
+static int createImpl(const AvsDeviceConfig *cfg, void *localGroup, int deviceShare, AvsContext **out);
+int avs_create(const AvsDeviceConfig *cfg, AvsContext **out) { return createImpl(cfg, nullptr, 1, out); }
+
+static int createImpl(const AvsDeviceConfig *cfg, void *localGroup, int deviceShare, AvsContext **out) {
     if (!out) return AVS_ERR_INVALID_ARGUMENT;
     *out = nullptr;
     int ndev = 0;
@@ -75,6 +81,8 @@ int avs_create(const AvsDeviceConfig *cfg, AvsContext **out) {
         c->timeSpmv = cfg->time_spmv != 0;
         c->stream = (cudaStream_t)cfg->stream;
     }
+    c->localGroup = localGroup;
+    c->deviceShare = std::max(1, deviceShare);
     if (c->device < 0 || c->device >= ndev || c->rank < 0 || c->rank >= c->nranks) { delete c; return AVS_ERR_INVALID_ARGUMENT; }
     if (cudaSetDevice(c->device) != cudaSuccess) { delete c; return AVS_ERR_CUDA; }
     if (!c->stream) {
@@ -374,12 +382,23 @@ static int runApply(AvsContext *c, AvsVelocityOut *out, AvsResult *res) {
         if (rcg) return rcg;
     }
     unsigned long long pending = 0;
+    c->outputIsHost = !out->on_device;
     const bool streamed = !out->on_device && c->nranks == 1;   // per-axis downloads overlap the remaining apply kernels
     int rc = avs_apply_regular(c, dOut, &pending, streamed ? out->vel : nullptr);
     if (rc) return rc;
     cudaEventRecord(c->ev[AVS_STAGE_DOWNLOAD], c->stream);
     if (streamed) AVS_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->evDownloadDone, 0));
-    else if (!out->on_device)
+    else if (!out->on_device && c->slabOutputOnly && c->nranks > 1) {
+        // in-process group: the ranks share the caller's host arrays, every rank fills the z-slab it computed
+        for (int a = 0; a < 3; ++a) {
+            int z0, z1;
+            avs_slab_range(c, a, c->rank, &z0, &z1);
+            if (z1 <= z0) continue;
+            const size_t plane = (size_t)c->S.regular[a].n[0] * c->S.regular[a].n[1];
+            AVS_CUDA_CHECK(cudaMemcpyAsync(out->vel[a] + plane * (size_t)z0, dOut[a] + plane * (size_t)z0, plane * (size_t)(z1 - z0) * sizeof(float),
+                                           cudaMemcpyDeviceToHost, c->stream));
+        }
+    } else if (!out->on_device)
         for (int a = 0; a < 3; ++a)
             AVS_CUDA_CHECK(cudaMemcpyAsync(out->vel[a], dOut[a], c->S.regular[a].count() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     cudaEventRecord(c->ev[AVS_STAGE_DOWNLOAD + 1], c->stream);
@@ -635,6 +654,105 @@ int avs_time_spmv_resident(AvsContext *c, int precision, int repeats, float *msP
     const double s = c->A.precision == AVS_PRECISION_F32 ? 4.0 : 8.0;
     if (algorithmicBytes) *algorithmicBytes = (double)c->A.nnz * (s + 4.0) + (double)(c->A.n + 1) * 4.0 + 2.0 * (double)c->A.n * s;
     return avs_spmv_time(c, c->A, repeats, msPerLaunch);
+}
+
+// ---- one process, several GPUs ----------------------------------------------------------------------------------------------
+// The DOP surface is single-threaded (solveGasSubclass is called on one cook thread, HDK_AdaptiveViscosity.cpp:126-128).
+// avs_create_multi builds one rank context per listed device; avs_solve_multi runs the row-partitioned solve on all of them --
+// one short-lived host thread per rank (the per-rank pipeline has host-side waits, so the ranks must be driven concurrently;
+// the calling thread blocks until all have returned) -- reading the caller's host fields and writing the caller's host
+// velocity arrays (every rank downloads the z-slab it computed).  No NCCL, no CUDA IPC: peer access + plain pointers.
+struct AvsMulti {
+    int n = 0;
+    void *group = nullptr;
+    std::vector<AvsContext *> ctx;
+    std::vector<int> status;
+    std::vector<AvsResult> res;
+};
+
+int avs_create_multi(const int32_t *devices, int32_t n, int32_t time_spmv, AvsMulti **out) {
+    if (!out || !devices || n < 1 || n > 16) return AVS_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    AvsMulti *m = new (std::nothrow) AvsMulti();
+    if (!m) return AVS_ERR_ALLOC;
+    m->n = n;
+    std::vector<int> devs(devices, devices + n);
+    m->group = n > 1 ? avs_local_group_create(n, devs.data()) : nullptr;
+    m->ctx.assign(n, nullptr);
+    m->status.assign(n, AVS_OK);
+    m->res.resize(n);
+    // peer access is enabled per rank inside avs_dist_init; creation itself has no collective, so it can run sequentially
+    for (int r = 0; r < n; ++r) {
+        AvsDeviceConfig cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.size = sizeof(cfg);
+        cfg.device = devs[r];
+        cfg.rank = r;
+        cfg.nranks = n;
+        cfg.time_spmv = time_spmv;
+        int share = 0;
+        for (int q = 0; q < n; ++q) share += devs[q] == devs[r];
+        int rc = createImpl(&cfg, m->group, share, &m->ctx[r]);
+        if (rc != AVS_OK) {
+            for (int q = 0; q < r; ++q) avs_destroy(m->ctx[q]);
+            if (m->group) avs_local_group_destroy(m->group);
+            delete m;
+            return rc;
+        }
+        m->ctx[r]->slabOutputOnly = n > 1;
+    }
+    *out = m;
+    return AVS_OK;
+}
+
+void avs_destroy_multi(AvsMulti *m) {
+    if (!m) return;
+    for (AvsContext *c : m->ctx) avs_destroy(c);
+    if (m->group) avs_local_group_destroy(m->group);
+    delete m;
+}
+
+int avs_multi_size(AvsMulti *m) { return m ? m->n : 0; }
+AvsContext *avs_multi_context(AvsMulti *m, int rank) { return (m && rank >= 0 && rank < m->n) ? m->ctx[rank] : nullptr; }
+
+int avs_solve_multi(AvsMulti *m, const AvsFields *in, const AvsParams *p, AvsVelocityOut *out, AvsResult *res) {
+    if (!m || !in || !p || !res || res->size != sizeof(AvsResult)) return AVS_ERR_INVALID_ARGUMENT;
+    if (m->n > 1) {
+        // the ranks read the same host arrays: device pointers belong to one GPU and cannot be shared this way
+        const AvsField *all[] = {&in->surface, &in->viscosity, &in->density, &in->collision, &in->vel[0], &in->vel[1], &in->vel[2],
+                                 &in->face_weights[0], &in->face_weights[1], &in->face_weights[2], &in->collision_vel[0], &in->collision_vel[1],
+                                 &in->collision_vel[2]};
+        for (const AvsField *f : all)
+            if (f->data && f->on_device) return AVS_ERR_UNSUPPORTED;
+        if (out && out->on_device) return AVS_ERR_UNSUPPORTED;
+        if (p->cancel) return AVS_ERR_UNSUPPORTED;   // a cancelled rank would leave its peers waiting
+    }
+    avs_local_group_reset(m->group);
+    std::vector<std::thread> pool;
+    std::vector<std::string> errors(m->n);
+    for (int r = 0; r < m->n; ++r) {
+        m->res[r] = *res;
+        pool.emplace_back([m, r, in, p, out, &errors]() {
+            m->status[r] = avs_solve(m->ctx[r], in, p, out, &m->res[r]);
+            if (m->status[r] != AVS_OK) {
+                errors[r] = std::string(avs_last_error()) + " " + m->ctx[r]->lastError;
+                avs_local_group_fail(m->group);   // wake the peers out of their barriers
+            }
+        });
+    }
+    for (auto &t : pool) t.join();
+    *res = m->res[0];
+    int rc = AVS_OK;
+    for (int r = 0; r < m->n; ++r)
+        if (m->status[r] != AVS_OK && rc == AVS_OK) {
+            rc = m->status[r];
+            snprintf(g_lastError, sizeof(g_lastError), "rank %d: %s", r, errors[r].c_str());
+        }
+    // stage times: the slowest rank of every stage (the ranks run side by side)
+    for (int r = 1; r < m->n; ++r)
+        for (int i = 0; i < AVS_STAGE_COUNT; ++i) res->stage_ms[i] = std::max(res->stage_ms[i], m->res[r].stage_ms[i]);
+    res->status = rc;
+    return rc;
 }
 
 }  // extern "C"

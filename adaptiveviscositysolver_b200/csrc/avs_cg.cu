@@ -26,6 +26,7 @@
 #include "avs_p2p.cuh"
 
 #define CG_THREADS 256
+#define SJDS_HALO_BIT 0x40000000   // meta word: this slice gathers from a halo slot (multi-GPU; set per solve by k_slice_needs_halo)
 #define CG_CTAS_PER_SM 8
 
 // ---- SJDS build ---------------------------------------------------------------------------------
@@ -60,7 +61,7 @@ __global__ void k_sjds_fill_stage(long long n, const int32_t *rowLen, const int3
     int lane = threadIdx.x & 31;
     if (s >= nslices) return;
     int m = meta[s * 32 + lane];
-    int np = m & 0xff, orig = m >> 8;
+    int np = m & 0xff, orig = (m >> 8) & 31;
     long long r = s * 32 + orig;
     int len = (r < n) ? rowLen[r] : 0;
     long long base = sliceOff[s];
@@ -99,7 +100,7 @@ __global__ void k_sjds_fill(long long n, const long long *ptr, const int32_t *co
     int lane = threadIdx.x & 31;
     if (s >= nslices) return;
     int m = meta[s * 32 + lane];
-    int np = m & 0xff, orig = m >> 8;
+    int np = m & 0xff, orig = (m >> 8) & 31;
     long long r = s * 32 + orig;
     long long p0 = (r < n) ? ptr[r] : 0;
     int len = (r < n) ? (int)(ptr[r + 1] - p0) : 0;
@@ -293,7 +294,7 @@ __device__ __forceinline__ double spmvOneSlice(long long s, int lane, const Sjds
     {
         const int m = A.meta[s * 32 + lane];
         const int np = m & 0xff;
-        const long long r = s * 32 + (m >> 8);
+        const long long r = s * 32 + ((m >> 8) & 31);
         const long long base = A.sliceOff[s] + lane;
         const int maxnp = __shfl_sync(0xffffffffu, np, 0);
         T acc = 0;
@@ -360,7 +361,7 @@ __device__ __forceinline__ double spmvOneSlicePf(long long s, int lane, const Sj
     double dot = 0;
     const int m = A.meta[s * 32 + lane];
     const int np = m & 0xff;
-    const long long r = s * 32 + (m >> 8);
+    const long long r = s * 32 + ((m >> 8) & 31);
     const long long base = A.sliceOff[s] + lane;
     const int maxnp = __shfl_sync(0xffffffffu, np, 0);
     T acc = 0;
@@ -440,7 +441,7 @@ __device__ __forceinline__ double spmvOneSliceRing(long long s, int lane, int m,
     static_assert(SPMV_RING % SPMV_U == 0, "ring must hold whole trips");
     constexpr int GROUPS = SPMV_RING / SPMV_U;   // cp.async groups in flight
     const int np = m & 0xff;
-    const long long r = s * 32 + (m >> 8);
+    const long long r = s * 32 + ((m >> 8) & 31);
     const int maxnp = __shfl_sync(0xffffffffu, np, 0);
     const T2 *gval = A.val2 + sliceBase + lane;
     const int2 *gcol = A.col2 + sliceBase + lane;
@@ -725,7 +726,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) k_spmv_tma(const __grid_consta
         if (s < s1) {
             const int m = meta[s * 32 + lane];
             const int npl = m & 0xff;
-            const long long r = s * 32 + (m >> 8);
+            const long long r = s * 32 + ((m >> 8) & 31);
             const int maxnp = __shfl_sync(0xffffffffu, npl, 0);
             const long long rel = sliceOff[s] - p0;
             T acc;
@@ -889,6 +890,7 @@ __device__ __forceinline__ unsigned ldAcquireGpu(const unsigned *p) {
     return v;
 }
 __device__ __forceinline__ unsigned long long ldVolatileU64(const unsigned long long *p) { return *(const volatile unsigned long long *)p; }
+__device__ __forceinline__ unsigned ldVolatileU32(const unsigned *p) { return *(const volatile unsigned *)p; }
 
 // All CTAs of the (co-resident) grid.  Returns false when the launch is being aborted.
 __device__ __forceinline__ bool gridBarrier(PcgState *st, unsigned &target) {
@@ -1123,6 +1125,10 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) k_cg_persistent(const __grid
     }
 }
 
+// acquire-release fences (the v2 kernel's synchronisation is release/acquire, it never needs sequential consistency)
+__device__ __forceinline__ void fenceGpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void fenceSys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+
 // ---- persistent CG kernel, version 2 (default) ---------------------------------------------------------------------------------
 // Same Eigen loop, same three phases per iteration, but every synchronisation point is ONE wait instead of a chain:
 //  * syncs A and B (after the SpMV: p.Ap; after the x,r update: r.r, r.z) merge the grid barrier, the reduction of the per-CTA
@@ -1147,20 +1153,14 @@ struct Pcg2State {                // device-resident, copied back by the host af
     int pad;
 };
 
-__device__ __forceinline__ double reducePartsCg(const double *parts, int n, double *sh /* [CG_THREADS/32 + 1] */) {
+// The canonical reduction of the per-CTA partial sums: ONE warp, lane-strided loads straight from L2, shuffle tree.  Every CTA of
+// every rank uses this order (and so does the CTA that posts the rank's sum to the peers), hence bit-identical scalars everywhere.
+__device__ __forceinline__ double warpReduceParts(const double *parts, int n, int lane) {
     double v = 0;
-    for (int i = threadIdx.x; i < n; i += CG_THREADS) v += __ldcg(parts + i);
-    v = warpSum(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0;
-        for (int i = 0; i < CG_THREADS / 32; ++i) t += sh[i];
-        sh[CG_THREADS / 32] = t;
-    }
-    __syncthreads();
-    return sh[CG_THREADS / 32];
+    for (int i = lane; i < n; i += 32) v += __ldcg(parts + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
 }
 template <class ST>
 __device__ __forceinline__ bool spinTimedOut(unsigned &spins, unsigned long long &t0, ST *st) {
@@ -1173,68 +1173,109 @@ __device__ __forceinline__ bool spinTimedOut(unsigned &spins, unsigned long long
 }
 
 // v[0..COUNT): this CTA's partial sums (valid in thread 0).  On return: the sums over all CTAs of all ranks, the same bits in every
-// thread of every CTA of every rank.  Doubles as the grid barrier (see above).  shw: 4 * P2P_MAX_RANKS words, shLast: 1 int.
+// thread of every CTA of every rank.  Also the grid barrier between two phases.  Warp 0 does the work:
+//   lane 0 publishes the CTA's partials and bumps the arrival counter; the LAST CTA to arrive reduces the rank's partials and stores
+//   the sums into the mailboxes of the PEERS (flag-in-data words); every CTA waits for the counter (local barrier), reduces the
+//   partials itself (same canonical order), then -- P > 1 -- waits for the peers' words and adds the P contributions in rank order.
 template <int COUNT>
 __device__ __forceinline__ bool syncSum(double (&v)[COUNT], double *parts, unsigned *counter, unsigned &target, const PcgDist &D, P2PHeader *mine,
-                                        unsigned long long seq, Pcg2State *st, double *sh, unsigned *shw, int *shLast) {
+                                        unsigned long long seq, Pcg2State *st, double *shOut /* [COUNT] */) {
     const int G = gridDim.x;
+    const int lane = threadIdx.x & 31;
+    target += (unsigned)G;
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int q = 0; q < COUNT; ++q) parts[q * G + blockIdx.x] = v[q];
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        target += (unsigned)G;
-        __threadfence();
-        const unsigned prev = atomicAdd(counter, 1u);
-        const int last = (prev + 1u == target) ? 1 : 0;
-        if (last) __threadfence();
-        *shLast = last;
-    }
-    __syncthreads();
-    const int par = (int)(seq & 1ull);
-    const unsigned long long tag = (seq & 0xffffffffull) << 32;
-    const int words = D.P * COUNT * 2;
-    if (*shLast) {   // CTA-uniform
+    __syncthreads();   // every thread's writes of this phase precede lane 0's release below
+    if (threadIdx.x < 32) {
+        const int par = (int)(seq & 1ull);
+        const unsigned long long tag = (seq & 0xffffffffull) << 32;
+        int last = 0;
+        if (lane == 0) {
+            fenceGpu();
+            const unsigned prev = atomicAdd(counter, 1u);
+            last = (prev + 1u == target) ? 1 : 0;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
         double tot[COUNT];
+        bool have = false;
+        if (last) {   // warp-uniform: the partials of all CTAs of this rank are in L2
+            if (lane == 0) fenceGpu();
+            __syncwarp();
 #pragma unroll
-        for (int q = 0; q < COUNT; ++q) tot[q] = reducePartsCg(parts + q * G, G, sh);
-        if (threadIdx.x < words) {
-            const int peerRank = threadIdx.x / (COUNT * 2), q = (threadIdx.x >> 1) % COUNT, half = threadIdx.x & 1;
-            P2PHeader *peer = (P2PHeader *)D.peerRegion[peerRank];
-            unsigned long long bits = 0;
+            for (int q = 0; q < COUNT; ++q) tot[q] = warpReduceParts(parts + q * G, G, lane);
+            have = true;
+            // one lane per (peer, value, half): sender-side slot index = myRank
+            const int words = (D.P - 1) * COUNT * 2;
+            if (lane < words) {
+                int peerRank = lane / (COUNT * 2);
+                if (peerRank >= D.myRank) ++peerRank;
+                const int q = (lane >> 1) % COUNT, half = lane & 1;
+                unsigned long long bits = 0;
 #pragma unroll
-            for (int i = 0; i < COUNT; ++i)
-                if (i == q) bits = (unsigned long long)__double_as_longlong(tot[i]);
-            const unsigned long long word = (half ? (bits >> 32) : (bits & 0xffffffffull)) | tag;
-            __threadfence();   // release: everything this rank's CTAs wrote before they arrived is visible before the rank's word
-            *(volatile unsigned long long *)&peer->ll[par][D.myRank][q][half] = word;
+                for (int i = 0; i < COUNT; ++i)
+                    if (i == q) bits = (unsigned long long)__double_as_longlong(tot[i]);
+                const unsigned long long word = (half ? (bits >> 32) : (bits & 0xffffffffull)) | tag;
+                *(volatile unsigned long long *)&((P2PHeader *)D.peerRegion[peerRank])->ll[par][D.myRank][q][half] = word;
+            }
+        } else {
+            if (lane == 0) {   // local barrier
+                unsigned long long t0 = 0;
+                unsigned spins = 0;
+                while (ldVolatileU32(counter) < target)
+                    if (spinTimedOut(spins, t0, st)) break;
+                fenceGpu();
+            }
+            __syncwarp();
         }
-    }
-    if (threadIdx.x < words) {
-        const int sender = threadIdx.x / (COUNT * 2), q = (threadIdx.x >> 1) % COUNT, half = threadIdx.x & 1;
-        const unsigned long long *slot = &mine->ll[par][sender][q][half];
-        unsigned long long w = ldVolatileU64(slot), t0 = 0;
-        unsigned spins = 0;
-        while ((w & 0xffffffff00000000ull) != tag) {
-            if (spinTimedOut(spins, t0, st)) break;
-            w = ldVolatileU64(slot);
+        if (!have) {
+#pragma unroll
+            for (int q = 0; q < COUNT; ++q) tot[q] = warpReduceParts(parts + q * G, G, lane);
         }
-        shw[threadIdx.x] = (unsigned)(w & 0xffffffffull);
-        __threadfence();       // acquire
+        if (D.P > 1) {
+            // the peers' words: lane = (sender slot, value, half); senders in rank order, my own contribution from `tot`
+            const int words = (D.P - 1) * COUNT * 2;
+            unsigned lo32 = 0;
+            if (lane < words) {
+                int sender = lane / (COUNT * 2);
+                if (sender >= D.myRank) ++sender;
+                const int q = (lane >> 1) % COUNT, half = lane & 1;
+                const unsigned long long *slot = &mine->ll[par][sender][q][half];
+                unsigned long long w = ldVolatileU64(slot), t0 = 0;
+                unsigned spins = 0;
+                while ((w & 0xffffffff00000000ull) != tag) {
+                    if (spinTimedOut(spins, t0, st)) break;
+                    w = ldVolatileU64(slot);
+                }
+                lo32 = (unsigned)(w & 0xffffffffull);
+            }
+#pragma unroll
+            for (int q = 0; q < COUNT; ++q) {
+                double t = 0;
+                int slotLane = 0;   // lane that holds (sender r, value q, half 0)
+                for (int r = 0; r < D.P; ++r) {
+                    double c;
+                    if (r == D.myRank) c = tot[q];
+                    else {
+                        slotLane = ((r > D.myRank ? r - 1 : r) * COUNT + q) * 2;
+                        const unsigned lo = __shfl_sync(0xffffffffu, lo32, slotLane), hi = __shfl_sync(0xffffffffu, lo32, slotLane + 1);
+                        c = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+                    }
+                    t += c;
+                }
+                tot[q] = t;
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < COUNT; ++q) shOut[q] = tot[q];
+        }
     }
     __syncthreads();
     if (*(volatile int *)&st->abort) return false;
 #pragma unroll
-    for (int q = 0; q < COUNT; ++q) {
-        double t = 0;
-        for (int r = 0; r < D.P; ++r) {
-            const unsigned lo = shw[(r * COUNT + q) * 2], hi = shw[(r * COUNT + q) * 2 + 1];
-            t += __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
-        }
-        v[q] = t;
-    }
-    __syncthreads();   // shw / shLast are reused by the next sync
+    for (int q = 0; q < COUNT; ++q) v[q] = shOut[q];
     return true;
 }
 
@@ -1264,29 +1305,29 @@ __device__ __forceinline__ T *peerP(const PcgDist &D, int rank, int buf) {
     return (T *)((char *)D.peerRegion[rank] + P2P_HEADER_BYTES + (size_t)buf * D.pStrideBytes);
 }
 
-// Sync C: every CTA has written its rows of the new p (and its share of the halo pushes).  Nobody waits here.
-__device__ __forceinline__ void arrivePush(unsigned *counter, unsigned &target, const PcgDist &D, P2PHeader *mine, unsigned long long seq, bool pushedRemote) {
-    if (pushedRemote) __threadfence_system();
+// Sync C: every CTA has written its rows of the new p (and its share of the halo pushes).  Nobody waits here: the next SpMV waits
+// for the arrival counter (local part) and for the peers' pushFlag (halo part).
+__device__ __forceinline__ void arrivePush(unsigned *counter, unsigned &target, const PcgDist &D, unsigned long long seq, bool pushedRemote) {
+    if (pushedRemote) fenceSys();
     __syncthreads();
+    target += gridDim.x;
     if (threadIdx.x == 0) {
-        target += gridDim.x;
-        if (pushedRemote) __threadfence_system(); else __threadfence();
+        if (pushedRemote) fenceSys(); else fenceGpu();
         const unsigned prev = atomicAdd(counter, 1u);
-        if (prev + 1u == target) {
-            if (D.P > 1) __threadfence_system(); else __threadfence();
-            *(volatile unsigned long long *)&mine->localReady = seq;
+        if (D.P > 1 && prev + 1u == target) {   // every CTA's pushes are ordered before this point (fence + atomic chain)
+            fenceSys();
             for (int q = 0; q < D.P; ++q)
                 if ((D.sendMask >> q) & 1u) *(volatile unsigned long long *)&((P2PHeader *)D.peerRegion[q])->pushFlag[D.myRank] = seq;
         }
     }
 }
-__device__ __forceinline__ bool waitLocalReady(P2PHeader *mine, unsigned long long seq, Pcg2State *st) {
+__device__ __forceinline__ bool waitLocalReady(const unsigned *counter, unsigned target, Pcg2State *st) {
     if (threadIdx.x == 0) {
         unsigned long long t0 = 0;
         unsigned spins = 0;
-        while (ldVolatileU64(&mine->localReady) < seq)
+        while (ldVolatileU32(counter) < target)
             if (spinTimedOut(spins, t0, st)) break;
-        __threadfence();
+        fenceGpu();
     }
     __syncthreads();
     return *(volatile int *)&st->abort == 0;
@@ -1297,7 +1338,7 @@ __device__ __forceinline__ bool waitHaloReady(const PcgDist &D, P2PHeader *mine,
         unsigned spins = 0;
         while (ldVolatileU64(&mine->pushFlag[threadIdx.x]) < seq)
             if (spinTimedOut(spins, t0, st)) break;
-        __threadfence_system();
+        fenceSys();
     }
     __syncthreads();
     return *(volatile int *)&st->abort == 0;
@@ -1320,8 +1361,7 @@ template <class T, class T2, int SPMV_MODE, int MINB>
 __global__ void __launch_bounds__(CG_THREADS, MINB) k_cg_persistent2(const __grid_constant__ Pcg2Args<T, T2> A) {
     extern __shared__ __align__(128) unsigned char dynSmem[];
     __shared__ double sh[CG_THREADS / 32 + 1];
-    __shared__ unsigned shw[P2P_MAX_RANKS * 4];
-    __shared__ int shLast;
+    __shared__ double shSum[2];
     __shared__ unsigned long long tm[4];   // thread 0 of CTA 0: phase start stamp + 3 accumulators
     __shared__ double rrLast;
     CgScalars *sc = A.sc;
@@ -1354,7 +1394,7 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) k_cg_persistent2(const __gri
                 const int2 dst = A.D.sendDst[i];
                 *(volatile T *)(peerP<T>(A.D, dst.x, A.parity0) + dst.y) = pc[A.D.sendIdx[i] - A.D.rowBegin];
             }
-        arrivePush(&st->arrive[2], tgtC, A.D, A.mine, seqPush0, pushes);
+        arrivePush(&st->arrive[2], tgtC, A.D, seqPush0, pushes);
     }
     while (iters < A.itLimit) {
         const int cur = (A.parity0 + k) & 1;
@@ -1363,7 +1403,7 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) k_cg_persistent2(const __gri
         // ---- t = A p, partial p.t: slices that read no halo slot first, the boundary slices after the peers' values have landed
         double pt[1];
         {
-            if (!waitLocalReady(A.mine, seqPush0 + k, st)) break;
+            if (!waitLocalReady(&st->arrive[2], tgtC, st)) break;
             double dot = 0;
             if (!dist) {
                 if (SPMV_MODE == 2) dot = spmvSlicesRing<T, T2, true, 4, false, 8>(A.M, pc, A.t, dynSmem);
@@ -1371,14 +1411,14 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) k_cg_persistent2(const __gri
                     for (long long s = gwarp; s < A.M.nslices; s += warpsTotal) dot += pcgSlice<T, T2, SPMV_MODE>(s, lane, A.M, pc, A.t, dynSmem);
             } else {
                 for (long long s = gwarp; s < A.M.nslices; s += warpsTotal)
-                    if (!A.D.sliceHalo[s]) dot += pcgSlice<T, T2, SPMV_MODE>(s, lane, A.M, pc, A.t, dynSmem);
+                    if (!(A.M.meta[s * 32] & SJDS_HALO_BIT)) dot += pcgSlice<T, T2, SPMV_MODE>(s, lane, A.M, pc, A.t, dynSmem);
                 if (!waitHaloReady(A.D, A.mine, seqPush0 + k, st)) break;
                 for (long long i = gwarp; i < A.D.nBoundary; i += warpsTotal)
                     dot += pcgSlice<T, T2, SPMV_MODE>((long long)A.D.boundarySlices[i], lane, A.M, pc, A.t, dynSmem);
             }
             pt[0] = blockSum(dot, sh);
         }
-        if (!syncSum<1>(pt, A.parts, &st->arrive[0], tgtA, A.D, A.mine, A.D.seqReduce + 2ull * k + 1, st, sh, shw, &shLast)) break;
+        if (!syncSum<1>(pt, A.parts, &st->arrive[0], tgtA, A.D, A.mine, A.D.seqReduce + 2ull * k + 1, st, shSum)) break;
         if (timer) { const unsigned long long now = globalTimerNs(); tm[1] += now - tm[0]; tm[0] = now; }
         const double alphaD = rho / pt[0];
         breakdown = !isfinite(alphaD);
@@ -1408,7 +1448,7 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) k_cg_persistent2(const __gri
             rs[0] = blockSum(rr, sh);
             rs[1] = blockSum(rz, sh);
         }
-        if (!syncSum<2>(rs, A.parts + G, &st->arrive[1], tgtB, A.D, A.mine, A.D.seqReduce + 2ull * k + 2, st, sh, shw, &shLast)) break;
+        if (!syncSum<2>(rs, A.parts + G, &st->arrive[1], tgtB, A.D, A.mine, A.D.seqReduce + 2ull * k + 2, st, shSum)) break;
         if (timer) { const unsigned long long now = globalTimerNs(); tm[2] += now - tm[0]; tm[0] = now; }
         ++k;
         if (timer) rrLast = rs[0];
@@ -1432,7 +1472,7 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) k_cg_persistent2(const __gri
             ((T2 *)pn)[j] = o;
         }
         if ((A.n & 1) && gid == 0) { const long long i = A.n - 1; pn[i] = pNext(A.invDiag[i], A.r[i], beta, pc[i]); }
-        arrivePush(&st->arrive[2], tgtC, A.D, A.mine, seqPush0 + k, pushes);
+        arrivePush(&st->arrive[2], tgtC, A.D, seqPush0 + k, pushes);
         if (timer) tm[3] += globalTimerNs() - tm[0];
     }
     if (timer) {
@@ -1454,7 +1494,7 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) k_cg_persistent2(const __gri
 
 // flag[s] = 1 when slice s gathers from a halo slot (local column >= nLocal)
 __global__ void k_slice_needs_halo(long long nslices, const long long *__restrict__ sliceOff, const int2 *__restrict__ col2, int nLocal,
-                                   uint8_t *flag, int32_t *flag32) {
+                                   uint8_t *flag, int32_t *flag32, int32_t *meta) {
     const long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (s >= nslices) return;
@@ -1465,6 +1505,7 @@ __global__ void k_slice_needs_halo(long long nslices, const long long *__restric
     }
     const unsigned any = __ballot_sync(0xffffffffu, hit);
     if (lane == 0) { flag[s] = any ? 1 : 0; flag32[s] = any ? 1 : 0; }
+    if (any) meta[s * 32 + lane] |= SJDS_HALO_BIT;   // the SpMV's interior pass skips the slice without touching another array
 }
 __global__ void k_compact_slices(long long nslices, const uint8_t *flag, const long long *index, int32_t *list) {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1669,7 +1710,10 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
         if (env && atoi(env) >= 1) perSM = std::min(perSM, atoi(env));
         long long want = std::max<long long>((A.nslices * 32 + CG_THREADS - 1) / CG_THREADS, 1);
         pgrid = (int)std::min<long long>(want, (long long)c->numSMs * perSM);
+        // ranks that share one device (in-process group, tests) must be co-resident TOGETHER: they spin on each other's flags
+        if (c->deviceShare > 1) perSM = std::max(1, perSM / c->deviceShare);
         if (dist) pgrid = (int)((long long)c->numSMs * perSM);   // every rank runs the flag logic even with few rows
+        else pgrid = (int)std::min<long long>(pgrid, (long long)c->numSMs * perSM);
     }
     const long long nHalo = dist ? c->nHalo : 0;
     const size_t vb = (size_t)std::max<long long>(n, 1) * sizeof(T);
@@ -1722,7 +1766,7 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
     CgScalars *hs = (CgScalars *)c->hostScalars;  // pinned
     PcgDist pd;
     const bool persistent = cgUsePersistent() && (!dist || avs_dist_pcg_args(c, &pd));
-    if (persistent && pcgVersion() == 2) {
+    if (persistent && pcgVersion() == 2 && c->nranks <= 8) {   // the mailbox exchange of syncSum fits the peers' words into one warp
         // ---- k_cg_persistent2: one cooperative launch per `check_every` iterations (default: all of them) ----------------
         if (w.pcgState.reserve(sizeof(Pcg2State) + 64)) return AVS_ERR_ALLOC;
         Pcg2State *st = w.pcgState.as<Pcg2State>();
@@ -1748,7 +1792,7 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
             int64_t nBoundary = 0;
             if (A.nslices > 0) {
                 k_slice_needs_halo<<<(unsigned)((A.nslices * 32 + 255) / 256), 256, 0, c->stream>>>(A.nslices, A.sliceOff.as<long long>(), A.col.as<int2>(), (int)n,
-                                                                                          w.sliceHalo.as<uint8_t>(), w.sliceFlag.as<int32_t>());
+                                                                                          w.sliceHalo.as<uint8_t>(), w.sliceFlag.as<int32_t>(), A.meta.as<int32_t>());
                 ++c->launches;
                 int rcs = avs_exclusive_scan_i32_to_i64(c, w.sliceFlag.as<int32_t>(), w.sliceIndex.as<int64_t>(), A.nslices, &nBoundary);
                 if (rcs) return rcs;

@@ -63,6 +63,10 @@ struct AvsContext {
     int device = 0;
     int rank = 0, nranks = 1;
     void *dist = nullptr;            // DistState (avs_dist.cu) when nranks > 1
+    void *localGroup = nullptr;      // LocalGroup (avs_dist.cu) when the ranks live in one process (avs_create_multi)
+    int deviceShare = 1;             // ranks of the group that run on this rank's device (cooperative grids must co-reside)
+    bool slabOutputOnly = false;     // multi-GPU host output: every rank downloads only its z-slab into the caller's arrays
+    bool outputIsHost = false;       // set by runApply: the velocity of this call goes to host memory
     long long nHalo = 0;              // off-rank columns referenced by the local rows
     const long long *haloIndex = nullptr;  // device: global column -> halo slot (valid where flagged)
     cudaStream_t stream = nullptr;
@@ -149,6 +153,10 @@ int avs_sell_from_stage(AvsContext *c, SellMatrix &A, int64_t n, int64_t nnz, co
                         long long rowBegin, long long rowEnd, const long long *haloIndex);
 int avs_build_csr(AvsContext *c);
 int avs_dist_init(AvsContext *c, const void *uniqueId128);
+void *avs_local_group_create(int P, const int *devices);
+void avs_local_group_destroy(void *g);
+void avs_local_group_fail(void *g);
+void avs_local_group_reset(void *g);
 void avs_dist_destroy(AvsContext *c);
 int avs_dist_build_halo(AvsContext *c);
 int avs_dist_halo_exchange(AvsContext *c, void *p, int precision, const int *done);

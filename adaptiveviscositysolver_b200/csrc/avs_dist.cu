@@ -9,13 +9,23 @@
 // NCCL is loaded at run time (dlopen "libnccl.so.2": inside a torch process this resolves to the NCCL torch
 // already loaded), so the single-GPU library has no NCCL dependency.  The communicator is created by the
 // library from a unique id the host broadcasts (avs_nccl_unique_id on rank 0 -> AvsDeviceConfig).
+//
+// Second way in: ONE process drives all GPUs (avs_create_multi, the shape of a Houdini DOP: solveGasSubclass is called on
+// one cook thread, HDK_AdaptiveViscosity.cpp:126-128).  The rank contexts then share a LocalGroup: the set-up collectives
+// (counts, halo lists, solution / slab gathers) are a host barrier plus plain device-to-device copies between the ranks'
+// buffers -- same address space, so a published pointer is enough -- and the peer regions of the CG are mapped with
+// cudaDeviceEnablePeerAccess instead of CUDA IPC.  No NCCL at all; several ranks may even share one device (tests).
 #include <dlfcn.h>
 #include <nccl.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "avs_context.h"
@@ -80,8 +90,54 @@ static bool loadNccl() {
 // and maps the regions of all peers.  The hot loop then needs no NCCL call: halo values are LOADED from the owners'
 // p vectors over NVLink by k_p2p_halo_pull, and the scalar all-reduce is P remote STORES into the peers' mailboxes
 // followed by a local spin (k_p2p_allreduce) -- both inside our own kernels.
+// Shared by the rank contexts of one process (avs_create_multi).  Every collective below is called by all rank threads.
+struct LocalGroup {
+    int P = 0;
+    int device[P2P_MAX_RANKS] = {};
+    std::mutex mu;
+    std::condition_variable cv;
+    int waiting = 0;
+    unsigned long long generation = 0;
+    std::atomic<int> failed{0};
+    const void *ptr[P2P_MAX_RANKS][4] = {};
+    unsigned long long u64[P2P_MAX_RANKS][8] = {};
+    const int *hostInts[P2P_MAX_RANKS] = {};
+    // returns false when a rank has failed (or nobody showed up for 120 s): callers give up instead of hanging
+    bool barrier() {
+        std::unique_lock<std::mutex> lk(mu);
+        const unsigned long long gen = generation;
+        if (++waiting == P) {
+            waiting = 0;
+            ++generation;
+            cv.notify_all();
+            return failed.load() == 0;
+        }
+        const auto deadline = std::chrono::steady_clock::now() + std::chrono::seconds(120);
+        while (generation == gen) {
+            if (cv.wait_for(lk, std::chrono::milliseconds(50)) == std::cv_status::timeout) {
+                if (failed.load() || std::chrono::steady_clock::now() > deadline) {
+                    failed.store(1);
+                    --waiting;
+                    return false;
+                }
+            }
+        }
+        return failed.load() == 0;
+    }
+};
+void *avs_local_group_create(int P, const int *devices) {
+    LocalGroup *g = new LocalGroup();
+    g->P = P;
+    for (int q = 0; q < P; ++q) g->device[q] = devices[q];
+    return g;
+}
+void avs_local_group_destroy(void *g) { delete (LocalGroup *)g; }
+void avs_local_group_fail(void *g) { if (g) { ((LocalGroup *)g)->failed.store(1); ((LocalGroup *)g)->cv.notify_all(); } }
+void avs_local_group_reset(void *g) { if (g) ((LocalGroup *)g)->failed.store(0); }
+
 struct DistState {
     ncclComm_t comm = nullptr;
+    LocalGroup *local = nullptr;           // single-process mode (avs_create_multi): no NCCL
     // peer-memory mode
     bool p2p = false;
     void *region = nullptr;                // my exported region
@@ -107,8 +163,101 @@ extern "C" int avs_nccl_unique_id(void *out128) {
     return AVS_OK;
 }
 
+#define LOCAL_BARRIER(c, d)                                                                      \
+    do {                                                                                         \
+        if (!(d)->local->barrier()) {                                                            \
+            (c)->lastError = "a rank of the in-process group failed or timed out";               \
+            return AVS_ERR_NCCL;                                                                 \
+        }                                                                                        \
+    } while (0)
+
+// ---- the set-up collectives, NCCL or in-process ---------------------------------------------------------------------------
+// recv[q * bytes ..] = rank q's send buffer (device pointers)
+static int commAllGather(AvsContext *c, DistState *d, const void *dSend, void *dRecv, size_t bytes) {
+    if (!d->local) {
+        NCCL_CHECK(c, g_nccl.AllGather(dSend, dRecv, bytes, ncclUint8, d->comm, c->stream));
+        return AVS_OK;
+    }
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    d->local->ptr[c->rank][0] = dSend;
+    LOCAL_BARRIER(c, d);
+    for (int q = 0; q < c->nranks; ++q)
+        AVS_CUDA_CHECK(cudaMemcpyPeerAsync((char *)dRecv + (size_t)q * bytes, c->device, d->local->ptr[q][0], d->local->device[q], bytes, c->stream));
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    LOCAL_BARRIER(c, d);
+    return AVS_OK;
+}
+// in place on the device; op: 0 sum, 1 max, 2 min
+static int commAllReduceU64(AvsContext *c, DistState *d, unsigned long long *dv, int count, int op) {
+    if (!d->local) {
+        const ncclRedOp_t o = op == 0 ? ncclSum : op == 1 ? ncclMax : ncclMin;
+        NCCL_CHECK(c, g_nccl.AllReduce(dv, dv, (size_t)count, ncclUint64, o, d->comm, c->stream));
+        return AVS_OK;
+    }
+    if (count > 8) return AVS_ERR_INVALID_ARGUMENT;
+    AVS_CUDA_CHECK(cudaMemcpyAsync(d->local->u64[c->rank], dv, (size_t)count * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    LOCAL_BARRIER(c, d);
+    unsigned long long r[8];
+    for (int i = 0; i < count; ++i) {
+        unsigned long long v = d->local->u64[0][i];
+        for (int q = 1; q < c->nranks; ++q) {
+            const unsigned long long w = d->local->u64[q][i];
+            v = op == 0 ? v + w : op == 1 ? std::max(v, w) : std::min(v, w);
+        }
+        r[i] = v;
+    }
+    LOCAL_BARRIER(c, d);   // everybody has read before anybody publishes again
+    AVS_CUDA_CHECK(cudaMemcpyAsync(dv, r, (size_t)count * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return AVS_OK;
+}
+// every rank's buffer `base` (same layout on all ranks) receives, for each q, bytes [off[q], off[q] + len[q]) from rank q's buffer
+static int commGatherSegments(AvsContext *c, DistState *d, void *base, const size_t *off, const size_t *len, ncclDataType_t dt, size_t elem) {
+    const int P = c->nranks;
+    if (!d->local) {
+        NCCL_CHECK(c, g_nccl.GroupStart());
+        for (int q = 0; q < P; ++q)
+            if (len[q] > 0) NCCL_CHECK(c, g_nccl.Broadcast((char *)base + off[q], (char *)base + off[q], len[q] / elem, dt, q, d->comm, c->stream));
+        NCCL_CHECK(c, g_nccl.GroupEnd());
+        return AVS_OK;
+    }
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    d->local->ptr[c->rank][1] = base;
+    LOCAL_BARRIER(c, d);
+    for (int q = 0; q < P; ++q)
+        if (q != c->rank && len[q] > 0)
+            AVS_CUDA_CHECK(cudaMemcpyPeerAsync((char *)base + off[q], c->device, (const char *)d->local->ptr[q][1] + off[q], d->local->device[q], len[q], c->stream));
+    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    LOCAL_BARRIER(c, d);
+    return AVS_OK;
+}
+
 int avs_dist_init(AvsContext *c, const void *uniqueId128) {
     if (c->nranks <= 1) return AVS_OK;
+    if (c->localGroup) {   // single-process mode: the group object replaces the communicator
+        if (c->nranks > P2P_MAX_RANKS) return AVS_ERR_UNSUPPORTED;
+        DistState *d = new DistState();
+        c->dist = d;
+        d->local = (LocalGroup *)c->localGroup;
+        d->recvCnt.assign(c->nranks, 0);
+        d->recvOff.assign(c->nranks + 1, 0);
+        d->sendCnt.assign(c->nranks, 0);
+        d->sendOff.assign(c->nranks + 1, 0);
+        if (d->scal.reserve(64 * sizeof(double))) return AVS_ERR_ALLOC;
+        d->p2p = true;
+        for (int q = 0; q < c->nranks; ++q) {   // direct loads / stores into the peers' regions
+            const int dev = d->local->device[q];
+            if (dev == c->device) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, c->device, dev);
+            if (!can) { c->lastError = "GPUs of the in-process group cannot access each other's memory"; return AVS_ERR_UNSUPPORTED; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(dev, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { c->lastError = "cudaDeviceEnablePeerAccess failed"; cudaGetLastError(); return AVS_ERR_CUDA; }
+            cudaGetLastError();
+        }
+        return AVS_OK;
+    }
     if (!uniqueId128) return AVS_ERR_INVALID_ARGUMENT;
     if (!loadNccl()) { c->lastError = "cannot load libnccl.so.2"; return AVS_ERR_NCCL; }
     DistState *d = new DistState();
@@ -129,8 +278,9 @@ int avs_dist_init(AvsContext *c, const void *uniqueId128) {
 void avs_dist_destroy(AvsContext *c) {
     DistState *d = (DistState *)c->dist;
     if (!d) return;
-    for (int q = 0; q < c->nranks && q < P2P_MAX_RANKS; ++q)
-        if (q != c->rank && d->peerRegion[q]) cudaIpcCloseMemHandle(d->peerRegion[q]);
+    if (!d->local)
+        for (int q = 0; q < c->nranks && q < P2P_MAX_RANKS; ++q)
+            if (q != c->rank && d->peerRegion[q]) cudaIpcCloseMemHandle(d->peerRegion[q]);
     if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);   // also orders "close" before the peers' "free"
     if (d->region) cudaFree(d->region);
     d->peerTable.release();
@@ -222,7 +372,10 @@ int avs_dist_build_halo(AvsContext *c) {
     if (d->counts.reserve((size_t)P * P * sizeof(int32_t) + (size_t)P * sizeof(int32_t))) return AVS_ERR_ALLOC;
     int32_t *dMine = d->counts.as<int32_t>() + (size_t)P * P;
     AVS_CUDA_CHECK(cudaMemcpyAsync(dMine, d->recvCnt.data(), (size_t)P * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-    NCCL_CHECK(c, g_nccl.AllGather(dMine, d->counts.p, (size_t)P, ncclInt32, d->comm, c->stream));
+    {
+        int rcg = commAllGather(c, d, dMine, d->counts.p, (size_t)P * sizeof(int32_t));
+        if (rcg) return rcg;
+    }
     std::vector<int32_t> &all = d->allCounts;
     all.assign((size_t)P * P, 0);
     AVS_CUDA_CHECK(cudaMemcpyAsync(all.data(), d->counts.p, (size_t)P * P * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -237,14 +390,30 @@ int avs_dist_build_halo(AvsContext *c) {
     d->nSend = nSend;
     if (d->sendIdx.reserve((size_t)std::max<long long>(nSend, 1) * sizeof(int32_t))) return AVS_ERR_ALLOC;
     if (d->sendBuf.reserve((size_t)std::max<long long>(nSend, 1) * sizeof(double))) return AVS_ERR_ALLOC;
-    NCCL_CHECK(c, g_nccl.GroupStart());
-    for (int q = 0; q < P; ++q) {
-        if (q == c->rank) continue;
-        if (d->recvCnt[q] > 0) NCCL_CHECK(c, g_nccl.Send(d->haloCols.as<int32_t>() + d->recvOff[q], (size_t)d->recvCnt[q], ncclInt32, q, d->comm, c->stream));
-        if (d->sendCnt[q] > 0) NCCL_CHECK(c, g_nccl.Recv(d->sendIdx.as<int32_t>() + d->sendOff[q], (size_t)d->sendCnt[q], ncclInt32, q, d->comm, c->stream));
+    if (d->local) {
+        // my send list for rank q = the block of q's (sorted, owner-grouped) halo column list that I own: pull it out of q's buffer
+        AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        d->local->ptr[c->rank][2] = d->haloCols.p;
+        LOCAL_BARRIER(c, d);
+        for (int q = 0; q < P; ++q) {
+            if (q == c->rank || d->sendCnt[q] == 0) continue;
+            long long off = 0;
+            for (int o = 0; o < c->rank; ++o) off += all[(size_t)q * P + o];
+            AVS_CUDA_CHECK(cudaMemcpyPeerAsync(d->sendIdx.as<int32_t>() + d->sendOff[q], c->device, (const int32_t *)d->local->ptr[q][2] + off,
+                                               d->local->device[q], (size_t)d->sendCnt[q] * sizeof(int32_t), c->stream));
+        }
+        AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        LOCAL_BARRIER(c, d);
+    } else {
+        NCCL_CHECK(c, g_nccl.GroupStart());
+        for (int q = 0; q < P; ++q) {
+            if (q == c->rank) continue;
+            if (d->recvCnt[q] > 0) NCCL_CHECK(c, g_nccl.Send(d->haloCols.as<int32_t>() + d->recvOff[q], (size_t)d->recvCnt[q], ncclInt32, q, d->comm, c->stream));
+            if (d->sendCnt[q] > 0) NCCL_CHECK(c, g_nccl.Recv(d->sendIdx.as<int32_t>() + d->sendOff[q], (size_t)d->sendCnt[q], ncclInt32, q, d->comm, c->stream));
+        }
+        NCCL_CHECK(c, g_nccl.GroupEnd());
+        AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     }
-    NCCL_CHECK(c, g_nccl.GroupEnd());
-    AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     c->nHalo = d->nHalo;
     c->haloIndex = d->index.as<long long>();
     return AVS_OK;
@@ -334,15 +503,16 @@ static int p2pEnsureRegion(AvsContext *c, size_t elems) {
     // agree on the capacity: max over ranks
     unsigned long long need = (unsigned long long)(P2P_HEADER_BYTES + elems * 8 + 256);
     unsigned long long *dNeed = (unsigned long long *)d->scal.as<double>() + 32;
+    int rcc;
     AVS_CUDA_CHECK(cudaMemcpyAsync(dNeed, &need, sizeof(need), cudaMemcpyHostToDevice, c->stream));
-    NCCL_CHECK(c, g_nccl.AllReduce(dNeed, dNeed, 1, ncclUint64, ncclMax, d->comm, c->stream));
+    if ((rcc = commAllReduceU64(c, d, dNeed, 1, 1))) return rcc;
     AVS_CUDA_CHECK(cudaMemcpyAsync(&need, dNeed, sizeof(need), cudaMemcpyDeviceToHost, c->stream));
     AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     if (d->region && need <= d->regionBytes) return AVS_OK;
     // tear down the old mappings (everyone closes before anyone frees: the all-reduce above/below orders it)
     for (int q = 0; q < P; ++q)
-        if (q != c->rank && d->peerRegion[q]) { cudaIpcCloseMemHandle(d->peerRegion[q]); d->peerRegion[q] = nullptr; }
-    NCCL_CHECK(c, g_nccl.AllReduce(dNeed, dNeed, 1, ncclUint64, ncclMax, d->comm, c->stream));
+        if (q != c->rank && d->peerRegion[q]) { if (!d->local) cudaIpcCloseMemHandle(d->peerRegion[q]); d->peerRegion[q] = nullptr; }
+    if ((rcc = commAllReduceU64(c, d, dNeed, 1, 1))) return rcc;
     AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     if (d->region) cudaFree(d->region);
     d->region = nullptr;
@@ -353,6 +523,17 @@ static int p2pEnsureRegion(AvsContext *c, size_t elems) {
     d->seqReady = 0;
     d->seqReduce = 0;
     d->seqPush = 0;
+    if (d->local) {   // one address space: the pointer itself is the handle (peer access was enabled in avs_dist_init)
+        AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        d->local->ptr[c->rank][3] = d->region;
+        LOCAL_BARRIER(c, d);
+        for (int q = 0; q < P; ++q) d->peerRegion[q] = const_cast<void *>(d->local->ptr[q][3]);
+        LOCAL_BARRIER(c, d);
+        if (d->peerTable.reserve(P2P_MAX_RANKS * sizeof(void *))) return AVS_ERR_ALLOC;
+        AVS_CUDA_CHECK(cudaMemcpyAsync(d->peerTable.p, d->peerRegion, P2P_MAX_RANKS * sizeof(void *), cudaMemcpyHostToDevice, c->stream));
+        AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        return AVS_OK;
+    }
     // exchange IPC handles
     cudaIpcMemHandle_t mine;
     AVS_CUDA_CHECK(cudaIpcGetMemHandle(&mine, d->region));
@@ -504,6 +685,7 @@ int avs_dist_halo_exchange(AvsContext *c, void *p, int precision, const int *don
         (void)p;
         return AVS_OK;
     }
+    if (d->local) { c->lastError = "the in-process group has no NCCL hot loop"; return AVS_ERR_UNSUPPORTED; }
     return precision == AVS_PRECISION_F32 ? avs_dist_halo_exchange_t<float>(c, (float *)p) : avs_dist_halo_exchange_t<double>(c, (double *)p);
 }
 
@@ -518,50 +700,50 @@ int avs_dist_allreduce_parts(AvsContext *c, const double *parts, int nparts, int
     }
     k_reduce_parts<<<1, 256, 0, c->stream>>>(parts, nparts, count, out);
     ++c->launches;
+    if (d && d->local) { c->lastError = "the in-process group has no NCCL hot loop"; return AVS_ERR_UNSUPPORTED; }
     if (d) NCCL_CHECK(c, g_nccl.AllReduce(out, out, (size_t)count, ncclFloat64, ncclSum, d->comm, c->stream));
     return AVS_OK;
 }
 
-// every rank ends up with the full solution vector (rank q's block at offset N q/P)
+// every rank ends up with the full solution vector (rank q's block at its row offset)
 int avs_dist_allgather_solution(AvsContext *c, const double *local, double *full) {
     DistState *d = (DistState *)c->dist;
     const int P = c->nranks;
     if (!d) return AVS_OK;
     AVS_CUDA_CHECK(cudaMemcpyAsync(full + c->rowBegin, local, (size_t)(c->rowEnd - c->rowBegin) * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-    NCCL_CHECK(c, g_nccl.GroupStart());
-    for (int q = 0; q < P; ++q) {
-        long long b = c->rowStarts[q], e = c->rowStarts[q + 1];
-        if (e > b) NCCL_CHECK(c, g_nccl.Broadcast(full + b, full + b, (size_t)(e - b), ncclFloat64, q, d->comm, c->stream));
+    size_t off[P2P_MAX_RANKS] = {}, len[P2P_MAX_RANKS] = {};
+    for (int q = 0; q < P && q < P2P_MAX_RANKS; ++q) {
+        off[q] = (size_t)c->rowStarts[q] * sizeof(double);
+        len[q] = (size_t)(c->rowStarts[q + 1] - c->rowStarts[q]) * sizeof(double);
     }
-    NCCL_CHECK(c, g_nccl.GroupEnd());
-    return AVS_OK;
+    return commGatherSegments(c, d, full, off, len, ncclFloat64, sizeof(double));
 }
 
 int avs_dist_allreduce_u64(AvsContext *c, unsigned long long *d, int count) {
     DistState *ds = (DistState *)c->dist;
     if (!ds) return AVS_OK;
-    NCCL_CHECK(c, g_nccl.AllReduce(d, d, (size_t)count, ncclUint64, ncclSum, ds->comm, c->stream));
-    return AVS_OK;
+    return commAllReduceU64(c, ds, d, count, 0);
 }
 
 // Stage 11 is sharded by z-slabs of the regular grid (avs_slab_cuts): rank q has filled planes [z0_q, z1_q) of every axis.
-// In-place broadcasts from the owners, grouped: after this every rank holds the whole velocity field (solveGasSubclass
+// In-place gathers from the owners: after this every rank holds the whole velocity field (solveGasSubclass
 // updates `vel` in place, AV.cpp:698 -- a caller on any rank sees the complete result).
 int avs_dist_allgather_slabs(AvsContext *c, float *dOut[3]) {
     DistState *ds = (DistState *)c->dist;
     if (!ds) return AVS_OK;
-    NCCL_CHECK(c, g_nccl.GroupStart());
     for (int a = 0; a < 3; ++a) {
         const size_t plane = (size_t)c->S.regular[a].n[0] * c->S.regular[a].n[1];
-        for (int q = 0; q < c->nranks; ++q) {
+        size_t off[P2P_MAX_RANKS] = {}, len[P2P_MAX_RANKS] = {};
+        for (int q = 0; q < c->nranks && q < P2P_MAX_RANKS; ++q) {
             int z0, z1;
             avs_slab_range(c, a, q, &z0, &z1);
             if (z1 <= z0) continue;
-            float *ptr = dOut[a] + plane * (size_t)z0;
-            NCCL_CHECK(c, g_nccl.Broadcast(ptr, ptr, plane * (size_t)(z1 - z0), ncclFloat32, q, ds->comm, c->stream));
+            off[q] = plane * (size_t)z0 * sizeof(float);
+            len[q] = plane * (size_t)(z1 - z0) * sizeof(float);
         }
+        int rc = commGatherSegments(c, ds, dOut[a], off, len, ncclFloat32, sizeof(float));
+        if (rc) return rc;
     }
-    NCCL_CHECK(c, g_nccl.GroupEnd());
     return AVS_OK;
 }
 

@@ -380,7 +380,8 @@ int avs_apply_regular(AvsContext *c, float *dOut[3], unsigned long long *hostInt
     if (c->nranks > 1) {
         int rcd = avs_dist_allreduce_u64(c, cnt, 1);
         if (rcd) return rcd;
-        if ((rcd = avs_dist_allgather_slabs(c, dOut))) return rcd;
+        // in-process group with host output: every rank downloads its own slab into the caller's arrays instead (avs_api.cu)
+        if (!(c->slabOutputOnly && c->outputIsHost) && (rcd = avs_dist_allgather_slabs(c, dOut))) return rcd;
     }
     AVS_CUDA_CHECK(cudaMemcpyAsync(hostInterpolated, cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));  // also keeps the stack copy of NS alive until the H2D copy is done

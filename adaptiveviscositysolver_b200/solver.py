@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
@@ -179,9 +179,12 @@ class Solver:
             raise AvsError(rc, "avs_create", _lib.last_error())
         self._h = h
 
+    _owned = True
+
     def close(self):
         if getattr(self, "_h", None):
-            self._L.avs_destroy(self._h)
+            if self._owned:
+                self._L.avs_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -391,6 +394,67 @@ class SIM_Object:
                        surfaceweights=scene.face_weights, viscosity=scene.viscosity, massdensity=scene.density)
         o.res, o.origin, o.dx = scene.res, scene.origin, scene.dx
         return o
+
+
+class MultiSolver:
+    """``AvsMulti``: ONE host thread drives the row-partitioned solve on several GPUs (``avs_create_multi`` /
+    ``avs_solve_multi``, include/avs.h) -- the shape of the DOP, whose ``solveGasSubclass`` runs on Houdini's cook thread
+    (HDK_AdaptiveViscosity.cpp:126-128).  ``devices`` may repeat an ordinal: the ranks then share that GPU (how the multi-rank
+    path is exercised on a one-GPU box).  Fields and ``out`` must be host (numpy) arrays."""
+
+    def __init__(self, devices: Sequence[int], time_spmv: bool = False):
+        self._L = _lib.load()
+        n = len(devices)
+        arr = (C.c_int32 * n)(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = self._L.avs_create_multi(arr, n, int(time_spmv), C.byref(h))
+        if rc != AVS_OK:
+            raise AvsError(rc, "avs_create_multi", _lib.last_error())
+        self._h = h
+        self.nranks = n
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.avs_destroy_multi(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def rank(self, r: int) -> "Solver":
+        """Read-back view of rank ``r``'s context (keys, local system, local solution, label grids)."""
+        v = Solver.__new__(Solver)
+        v._L = self._L
+        v._h = C.c_void_p(self._L.avs_multi_context(self._h, int(r)))
+        v._owned = False
+        return v
+
+    def solve(self, scene: Scene, params: Params, out: Optional[List] = None) -> SolveInfo:
+        keep: list = []
+        f = fields_to_c(scene, keep)
+        p = params.to_c()
+        r = _new_result()
+        o = None
+        if out is not None:
+            o = AvsVelocityOut()
+            for a in range(3):
+                assert isinstance(out[a], np.ndarray) and out[a].dtype == np.float32 and out[a].flags.c_contiguous
+                o.vel[a] = out[a].ctypes.data
+            o.on_device = 0
+        rc = self._L.avs_solve_multi(self._h, C.byref(f), C.byref(p), C.byref(o) if o is not None else None, C.byref(r))
+        if rc != AVS_OK:
+            raise AvsError(rc, "avs_solve_multi", _lib.last_error())
+        return SolveInfo.from_c(r)
+
+    def solution(self) -> np.ndarray:
+        """The full solution vector, concatenated over the ranks' row blocks."""
+        return np.concatenate([self.rank(r).solution() for r in range(self.nranks)])
+
+    def keys(self) -> np.ndarray:
+        return self.rank(0).keys()
 
 
 class HDK_AdaptiveViscosity:

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AVS_ABI_VERSION 2
+#define AVS_ABI_VERSION 3
 
 typedef enum AvsStatus {
     AVS_OK = 0,
@@ -173,6 +173,22 @@ void avs_default_params(AvsParams *p);
 
 /* The drop-in call: replaces HDK_AdaptiveViscosity.cpp:233-707 in one shot. */
 int avs_solve(AvsContext *ctx, const AvsFields *in, const AvsParams *p, AvsVelocityOut *out, AvsResult *res);
+
+/* ---- one process, several GPUs ------------------------------------------------------------------
+ * The same drop-in call for a host that owns all GPUs from ONE thread -- the shape of the DOP: solveGasSubclass is called
+ * on Houdini's cook thread, one object at a time (HDK_AdaptiveViscosity.cpp:126-128, HDK_AdaptiveViscosity.h:57-58).
+ * avs_create_multi makes one rank context per entry of `devices` (an ordinal may repeat: ranks then share that GPU, which is
+ * how the multi-rank path is tested on a one-GPU box); avs_solve_multi row-partitions the solve over them and returns when
+ * every rank is done.  Fields and the output velocity must be HOST arrays (every rank reads the same inputs and writes the
+ * z-slab of `out` it computed); `cancel` is not supported.  No NCCL and no CUDA IPC are involved: the GPUs must be able to
+ * access each other's memory (cudaDeviceCanAccessPeer).  `res` receives rank 0's result with per-stage times maximised over
+ * the ranks; avs_multi_context(m, r) exposes rank r's context to the read-back functions below. */
+typedef struct AvsMulti AvsMulti;
+int avs_create_multi(const int32_t *devices, int32_t n, int32_t time_spmv, AvsMulti **out);
+void avs_destroy_multi(AvsMulti *m);
+int avs_multi_size(AvsMulti *m);
+AvsContext *avs_multi_context(AvsMulti *m, int rank);
+int avs_solve_multi(AvsMulti *m, const AvsFields *in, const AvsParams *p, AvsVelocityOut *out, AvsResult *res);
 
 /* ---- staged entry points (tests, benchmarks, multi-step hosts) --------------------------------- */
 

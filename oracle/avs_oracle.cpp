@@ -41,6 +41,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -1358,7 +1359,10 @@ static T dot(exint n, const T *a, const T *b) {
 template <class T>
 static void eigenCG(exint n, const exint *ptr, const int32_t *col, const T *val, const T *b, T *x,
                     double tol_in, int maxIters, int *itersOut, double *errOut) {
-    std::vector<T> invdiag((size_t)n), r((size_t)n), p((size_t)n), z((size_t)n), tmp((size_t)n);
+    // work vectors: NOT value-initialised (five serial 80 MB memsets per call at 10 M rows); every entry is written before it is
+    // read, first touched by the thread that owns it
+    std::unique_ptr<T[]> work(new T[5 * (size_t)std::max<exint>(n, 1)]);
+    T *invdiag = work.get(), *r = invdiag + n, *p = r + n, *z = p + n, *tmp = z + n;
     // DiagonalPreconditioner::factorize
 #pragma omp parallel for schedule(static)
     for (exint i = 0; i < n; ++i) {
@@ -1366,12 +1370,12 @@ static void eigenCG(exint n, const exint *ptr, const int32_t *col, const T *val,
         bool found = false;
         for (exint k = ptr[i]; k < ptr[i + 1]; ++k)
             if (col[k] == i) { d = val[k]; found = true; break; }
-        invdiag[(size_t)i] = (found && d != T(0)) ? T(1) / d : T(1);
+        invdiag[i] = (found && d != T(0)) ? T(1) / d : T(1);
     }
     const T tol = (T)tol_in;
-    spmv(n, ptr, col, val, x, tmp.data());
+    spmv(n, ptr, col, val, x, tmp);
 #pragma omp parallel for schedule(static)
-    for (exint i = 0; i < n; ++i) r[(size_t)i] = b[i] - tmp[(size_t)i];
+    for (exint i = 0; i < n; ++i) r[i] = b[i] - tmp[i];
     T rhsNorm2 = dot(n, b, b);
     if (rhsNorm2 == 0) {
         for (exint i = 0; i < n; ++i) x[i] = 0;
@@ -1381,33 +1385,33 @@ static void eigenCG(exint n, const exint *ptr, const int32_t *col, const T *val,
     }
     const T considerAsZero = (std::numeric_limits<T>::min)();
     T threshold = std::max(T(tol * tol * rhsNorm2), considerAsZero);
-    T residualNorm2 = dot(n, r.data(), r.data());
+    T residualNorm2 = dot(n, r, r);
     if (residualNorm2 < threshold) {
         *itersOut = 0;
         *errOut = std::sqrt((double)(residualNorm2 / rhsNorm2));
         return;
     }
 #pragma omp parallel for schedule(static)
-    for (exint i = 0; i < n; ++i) p[(size_t)i] = invdiag[(size_t)i] * r[(size_t)i];
-    T absNew = dot(n, r.data(), p.data());
+    for (exint i = 0; i < n; ++i) p[i] = invdiag[i] * r[i];
+    T absNew = dot(n, r, p);
     int i = 0;
     while (i < maxIters) {
-        spmv(n, ptr, col, val, p.data(), tmp.data());
-        T alpha = absNew / dot(n, p.data(), tmp.data());
+        spmv(n, ptr, col, val, p, tmp);
+        T alpha = absNew / dot(n, p, tmp);
 #pragma omp parallel for schedule(static)
         for (exint j = 0; j < n; ++j) {
-            x[j] += alpha * p[(size_t)j];
-            r[(size_t)j] -= alpha * tmp[(size_t)j];
+            x[j] += alpha * p[j];
+            r[j] -= alpha * tmp[j];
         }
-        residualNorm2 = dot(n, r.data(), r.data());
+        residualNorm2 = dot(n, r, r);
         if (residualNorm2 < threshold) break;
 #pragma omp parallel for schedule(static)
-        for (exint j = 0; j < n; ++j) z[(size_t)j] = invdiag[(size_t)j] * r[(size_t)j];
+        for (exint j = 0; j < n; ++j) z[j] = invdiag[j] * r[j];
         T absOld = absNew;
-        absNew = dot(n, r.data(), z.data());
+        absNew = dot(n, r, z);
         T beta = absNew / absOld;
 #pragma omp parallel for schedule(static)
-        for (exint j = 0; j < n; ++j) p[(size_t)j] = z[(size_t)j] + beta * p[(size_t)j];
+        for (exint j = 0; j < n; ++j) p[j] = z[j] + beta * p[j];
         ++i;
     }
     *errOut = std::sqrt((double)(residualNorm2 / rhsNorm2));

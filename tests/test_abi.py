@@ -20,13 +20,13 @@ def built():
 
 def test_every_declared_symbol_is_exported(built):
     header = (ROOT / "include" / "avs.h").read_text()
-    declared = set(re.findall(r"^(?:int|void|const char \*)\s*\*?\s*(avs_\w+)\s*\(", header, re.M))
+    declared = set(re.findall(r"^(?:int|void|const char \*|AvsContext \*)\s*\*?\s*(avs_\w+)\s*\(", header, re.M))
     assert len(declared) >= 18
     L = built.load()
     for name in declared:
         assert hasattr(L, name), name
     assert declared == set(built.EXPORTS)
-    assert L.avs_abi_version() == 2
+    assert L.avs_abi_version() == 3
 
 
 def test_struct_layout_matches_header(built, tmp_path):
