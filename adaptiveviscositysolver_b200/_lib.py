@@ -18,7 +18,7 @@ STAGE_NAMES = ["upload", "surface_weights", "octree", "regular_labels", "octree_
                "system", "solve", "apply", "download", "total", "_"]
 
 EXPORTS = [
-    "avs_abi_version", "avs_nccl_unique_id", "avs_get_local_range", "avs_get_row_starts", "avs_create", "avs_destroy", "avs_status_string", "avs_last_error", "avs_default_params",
+    "avs_abi_version", "avs_device_count", "avs_nccl_unique_id", "avs_get_local_range", "avs_get_row_starts", "avs_create", "avs_destroy", "avs_status_string", "avs_last_error", "avs_default_params",
     "avs_solve", "avs_assemble", "avs_solve_resident", "avs_apply", "avs_get_sizes", "avs_get_keys",
     "avs_get_system_csr", "avs_get_solution", "avs_get_grid", "avs_cg_csr", "avs_spmv_csr", "avs_time_spmv_resident",
     "avs_build_octree", "avs_get_octree_points",

@@ -9,9 +9,25 @@
 #include <thread>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges are no-ops unless a profiler (nsys, ncu --nvtx) is attached
+
 #include "avs_context.h"
 
+// NVTX range per pipeline stage, named after the reference's UT_PerfMonAutoSolveEvent labels (HDK_AdaptiveViscosity.cpp:306, 360,
+// 441, 473, 516, 554, 603, 662, 759, 776, 813, 874): a timeline of this library reads like Houdini's performance monitor.
+struct NvtxRange {
+    explicit NvtxRange(const char *label) { nvtxRangePushA(label); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 static thread_local char g_lastError[512] = "";
+bool g_avsAsyncAlloc = false;
+thread_local cudaStream_t g_avsTlsStream = nullptr;
+// every entry point: bind the calling thread to the context's device and stream
+static inline void enterContext(AvsContext *c) {
+    cudaSetDevice(c->device);
+    g_avsTlsStream = c->stream;
+}
 
 void avs_set_last_error(const char *what, cudaError_t e, const char *file, int line) {
     snprintf(g_lastError, sizeof(g_lastError), "%s failed: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
@@ -21,6 +37,12 @@ void avs_set_last_error(const char *what, cudaError_t e, const char *file, int l
 extern "C" {
 
 int avs_abi_version(void) { return AVS_ABI_VERSION; }
+
+int avs_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
 
 const char *avs_last_error(void) { return g_lastError; }
 
@@ -89,6 +111,7 @@ static int createImpl(const AvsDeviceConfig *cfg, void *localGroup, int deviceSh
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return AVS_ERR_CUDA; }
         c->ownStream = true;
     }
+    g_avsTlsStream = c->stream;
     cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, c->device);
     for (auto &e : c->ev) cudaEventCreate(&e);
     cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking);
@@ -100,14 +123,14 @@ static int createImpl(const AvsDeviceConfig *cfg, void *localGroup, int deviceSh
     cudaEventCreateWithFlags(&c->evPoll[1], cudaEventDisableTiming);
     cudaEventCreate(&c->evPcg[0]);
     cudaEventCreate(&c->evPcg[1]);
-    if (cudaHostAlloc(&c->hostScalars, 512, cudaHostAllocDefault) != cudaSuccess) { delete c; return AVS_ERR_ALLOC; }
+    if (cudaHostAlloc(&c->hostScalars, 512, cudaHostAllocDefault) != cudaSuccess) { c->hostScalars = nullptr; avs_destroy(c); return AVS_ERR_ALLOC; }
     if (c->timeSpmv) {
         c->spmvEvents.resize(2 * 4096);
         for (auto &e : c->spmvEvents) cudaEventCreate(&e);
         c->auxEvents.resize(3 * 4096);
         for (auto &e : c->auxEvents) cudaEventCreate(&e);
     }
-    if (c->counters.reserve(64 * sizeof(unsigned long long))) { delete c; return AVS_ERR_ALLOC; }
+    if (c->counters.reserve(64 * sizeof(unsigned long long))) { avs_destroy(c); return AVS_ERR_ALLOC; }
     memset(&c->S, 0, sizeof(c->S));
     if (c->nranks > 1) {
         int rc = avs_dist_init(c, cfg ? cfg->nccl_unique_id : nullptr);
@@ -123,7 +146,7 @@ static int createImpl(const AvsDeviceConfig *cfg, void *localGroup, int deviceSh
 
 void avs_destroy(AvsContext *c) {
     if (!c) return;
-    cudaSetDevice(c->device);
+    enterContext(c);
     cudaStreamSynchronize(c->stream);
     avs_dist_destroy(c);
     DevBuf *bufs[] = {&c->fullSolution, &c->inSurface, &c->inVisc, &c->inDens, &c->inColl, &c->centerW, &c->tiles, &c->brickCount, &c->brickOffset,
@@ -270,11 +293,11 @@ static int runAssemble(AvsContext *c, const AvsFields *in, const AvsParams *p, A
     int rc;
     c->haveSystem = c->haveSolution = c->haveOctree = false;
     cudaEventRecord(c->ev[AVS_STAGE_UPLOAD], c->stream);
-    if ((rc = avs_stage_upload(c, in, p))) return rc;
+    { NvtxRange nv("Upload Fields (host -> device)"); AVS_TRACE("avs_stage_upload"); if ((rc = avs_stage_upload(c, in, p))) return rc; }
     cudaEventRecord(c->ev[AVS_STAGE_SURFACE_WEIGHTS], c->stream);
-    if ((rc = avs_stage_weights(c, p))) return rc;
+    { NvtxRange nv("Compute Surface Weights"); AVS_TRACE("avs_stage_weights"); if ((rc = avs_stage_weights(c, p))) return rc; }   // + "Compute Collision Weights"
     cudaEventRecord(c->ev[AVS_STAGE_OCTREE], c->stream);
-    if ((rc = avs_stage_octree(c, p))) return rc;
+    { NvtxRange nv("Build Mask for Octree + Build Octree"); AVS_TRACE("avs_stage_octree"); if ((rc = avs_stage_octree(c, p))) return rc; }
     c->haveOctree = true;
     cudaEventRecord(c->ev[AVS_STAGE_REGULAR_LABELS], c->stream);
     if (octreeOnly) {   // onlyPrintOctree (AV.cpp:292-293): the reference returns right after the geometry dump
@@ -282,17 +305,19 @@ static int runAssemble(AvsContext *c, const AvsFields *in, const AvsParams *p, A
         res->levels = c->S.levels;
         return AVS_OK;
     }
-    if ((rc = avs_stage_regular_labels(c))) return rc;
+    { NvtxRange nv("Build Regular Grid Velocity Labels"); AVS_TRACE("avs_stage_regular_labels"); if ((rc = avs_stage_regular_labels(c))) return rc; }
     cudaEventRecord(c->ev[AVS_STAGE_OCTREE_LABELS], c->stream);
-    if ((rc = avs_stage_octree_labels(c))) return rc;
+    { NvtxRange nv("Build Octree Velocity and Stress Labels"); AVS_TRACE("avs_stage_octree_labels"); if ((rc = avs_stage_octree_labels(c))) return rc; }
     cudaStreamWaitEvent(c->stream, c->evUploadDone, 0);  // velocity + face weights have landed
     cudaEventRecord(c->ev[AVS_STAGE_RESTRICTION], c->stream);
-    if ((rc = avs_stage_restriction(c))) return rc;
+    { NvtxRange nv("Interpolate Regular Grid Velocities at Octree Velocity Faces"); AVS_TRACE("avs_stage_restriction"); if ((rc = avs_stage_restriction(c))) return rc; }
     cudaEventRecord(c->ev[AVS_STAGE_SYSTEM], c->stream);
-    if ((rc = avs_stage_system(c, p))) return rc;
+    NvtxRange nvSystem("Build Edge/Cell Stress Stencils + Build Octree Linear System");
+    AVS_TRACE("avs_stage_system"); if ((rc = avs_stage_system(c, p))) return rc;
     // the CG's matrix format is part of "Build Octree Linear System" (the reference's setFromTriplets, AV.cpp:614)
     c->nHalo = 0;
     c->haloIndex = nullptr;
+    AVS_TRACE("sjds build");
     if (c->nranks > 1 && (rc = avs_dist_build_halo(c))) return rc;
     if ((rc = avs_sell_from_stage(c, c->A, c->rowEnd - c->rowBegin, c->nnz, c->rowCount.as<int32_t>(), c->stageCol.as<int32_t>(),
                                   c->stageVal.as<double>(), c->stageStride, c->diag.as<double>(), p->precision,
@@ -314,6 +339,8 @@ static int runSolve(AvsContext *c, const AvsParams *p, AvsResult *res) {
     c->spmvMs = 0;
     const int64_t spmv0 = c->spmvLaunches;
     cudaEventRecord(c->ev[AVS_STAGE_SOLVE], c->stream);
+    AVS_TRACE("avs_cg_run");
+    NvtxRange nvSolve("Solve Linear System");
     int rc = avs_cg_run(c, c->A, c->rhs.as<double>(), c->x0.as<double>() + c->rowBegin, c->solution.as<double>(), p, res);
     cudaEventRecord(c->ev[AVS_STAGE_SOLVE + 1], c->stream);
     collectStageTimes(c, res, AVS_STAGE_SOLVE, AVS_STAGE_SOLVE);
@@ -359,9 +386,15 @@ static int runSolve(AvsContext *c, const AvsParams *p, AvsResult *res) {
 
 static int runApply(AvsContext *c, AvsVelocityOut *out, AvsResult *res) {
     if (!c->haveSolution || !out) return AVS_ERR_INVALID_ARGUMENT;
+    AVS_TRACE("apply");
+    NvtxRange nvApply("Apply Octree Solution to Regular Grid");
     cudaEventRecord(c->ev[AVS_STAGE_APPLY], c->stream);
     float *dOut[3];
-    DevBuf tmp[3];
+    struct TmpBufs {   // released on every exit path
+        DevBuf b[3];
+        ~TmpBufs() { for (DevBuf &x : b) x.release(); }
+        DevBuf &operator[](int a) { return b[a]; }
+    } tmp;
     for (int a = 0; a < 3; ++a) {
         if (!out->vel[a]) return AVS_ERR_INVALID_ARGUMENT;
         size_t bytes = c->S.regular[a].count() * sizeof(float);
@@ -404,7 +437,6 @@ static int runApply(AvsContext *c, AvsVelocityOut *out, AvsResult *res) {
     cudaEventRecord(c->ev[AVS_STAGE_DOWNLOAD + 1], c->stream);
     AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));   // the caller's host arrays are complete on return
     collectStageTimes(c, res, AVS_STAGE_APPLY, AVS_STAGE_DOWNLOAD);
-    for (int a = 0; a < 3; ++a) tmp[a].release();
     res->kernel_launches = c->launches;
     res->interpolated_faces = (int64_t)pending;
     return AVS_OK;
@@ -414,7 +446,7 @@ extern "C" {
 
 int avs_assemble(AvsContext *c, const AvsFields *in, const AvsParams *p, AvsResult *res) {
     if (!c || !res || res->size != sizeof(AvsResult)) return AVS_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(c->device);
+    enterContext(c);
     memset(res->stage_ms, 0, sizeof(res->stage_ms));
     c->launches = 0;
     c->spmvLaunches = 0;
@@ -425,7 +457,7 @@ int avs_assemble(AvsContext *c, const AvsFields *in, const AvsParams *p, AvsResu
 
 int avs_build_octree(AvsContext *c, const AvsFields *in, const AvsParams *p, AvsResult *res) {
     if (!c || !res || res->size != sizeof(AvsResult)) return AVS_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(c->device);
+    enterContext(c);
     memset(res->stage_ms, 0, sizeof(res->stage_ms));
     c->launches = 0;
     c->spmvLaunches = 0;
@@ -438,7 +470,7 @@ int avs_build_octree(AvsContext *c, const AvsFields *in, const AvsParams *p, Avs
 int avs_get_octree_points(AvsContext *c, int64_t *count, float *pos, float *pscale, int32_t *level) {
     if (!c || !count) return AVS_ERR_INVALID_ARGUMENT;
     if (!c->haveOctree) return AVS_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(c->device);
+    enterContext(c);
     int64_t n = 0;
     int rc = avs_octree_points(c, &n);
     if (rc) return rc;
@@ -454,7 +486,7 @@ int avs_get_octree_points(AvsContext *c, int64_t *count, float *pos, float *psca
 
 int avs_solve_resident(AvsContext *c, const AvsParams *p, AvsResult *res) {
     if (!c || !p || p->size != sizeof(AvsParams) || !res || res->size != sizeof(AvsResult)) return AVS_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(c->device);
+    enterContext(c);
     fillCounts(c, res);
     int rc = runSolve(c, p, res);
     res->status = rc;
@@ -463,7 +495,7 @@ int avs_solve_resident(AvsContext *c, const AvsParams *p, AvsResult *res) {
 
 int avs_apply(AvsContext *c, AvsVelocityOut *out, AvsResult *res) {
     if (!c || !res || res->size != sizeof(AvsResult)) return AVS_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(c->device);
+    enterContext(c);
     int rc = runApply(c, out, res);
     res->status = rc;
     return rc;
@@ -471,7 +503,7 @@ int avs_apply(AvsContext *c, AvsVelocityOut *out, AvsResult *res) {
 
 int avs_solve(AvsContext *c, const AvsFields *in, const AvsParams *p, AvsVelocityOut *out, AvsResult *res) {
     if (!c || !res || res->size != sizeof(AvsResult)) return AVS_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(c->device);
+    enterContext(c);
     memset(res->stage_ms, 0, sizeof(res->stage_ms));
     c->launches = 0;
     c->spmvLaunches = 0;
@@ -513,8 +545,8 @@ int avs_get_row_starts(AvsContext *c, int64_t *starts) {
 }
 
 int avs_get_keys(AvsContext *c, int32_t *keys) {
-    if (!c || !keys) return AVS_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(c->device);
+    if (!c || !keys || !c->haveSystem) return AVS_ERR_INVALID_ARGUMENT;   // keys exist only behind a geometric system (not avs_cg_csr)
+    enterContext(c);
     AVS_CUDA_CHECK(cudaMemcpyAsync(keys, c->rowKeys.p, (size_t)c->nRows * sizeof(RowKey), cudaMemcpyDeviceToHost, c->stream));
     AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     return AVS_OK;
@@ -522,7 +554,7 @@ int avs_get_keys(AvsContext *c, int32_t *keys) {
 
 int avs_get_system_csr(AvsContext *c, int64_t *rowPtr, int32_t *col, double *val, double *rhs, double *x0) {
     if (!c || !c->haveSystem) return AVS_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(c->device);
+    enterContext(c);
     const long long n = c->rowEnd - c->rowBegin;
     if (col || val) {
         int rc = avs_build_csr(c);
@@ -539,7 +571,7 @@ int avs_get_system_csr(AvsContext *c, int64_t *rowPtr, int32_t *col, double *val
 
 int avs_get_solution(AvsContext *c, double *x) {
     if (!c || !c->haveSolution || !x) return AVS_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(c->device);
+    enterContext(c);
     AVS_CUDA_CHECK(cudaMemcpyAsync(x, c->solution.p, (size_t)(c->rowEnd - c->rowBegin) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     return AVS_OK;
@@ -548,7 +580,8 @@ int avs_get_solution(AvsContext *c, double *x) {
 int avs_get_grid(AvsContext *c, int kind, int level, int axis, void *out, int32_t *res, int64_t *nbytes) {
     if (!c || axis < 0 || axis > 2) return AVS_ERR_INVALID_ARGUMENT;
     if (kind >= 0 && kind <= 3 && (level < 0 || level >= c->S.levels)) return AVS_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(c->device);
+    if (kind == 0 ? !c->haveOctree : !c->haveSystem) return AVS_ERR_INVALID_ARGUMENT;   // nothing resident yet (or a caller CSR only)
+    enterContext(c);
     const DeviceScene &S = c->S;
     const void *src = nullptr;
     const int *n = nullptr;
@@ -603,7 +636,7 @@ int avs_cg_csr(AvsContext *c, int64_t n, const int64_t *rowPtr, const int32_t *c
                const AvsParams *p, AvsResult *res) {
     if (!c || !p || p->size != sizeof(AvsParams) || !res || res->size != sizeof(AvsResult) || !rhs || !x) return AVS_ERR_INVALID_ARGUMENT;
     if (c->nranks > 1) return AVS_ERR_UNSUPPORTED;  // caller matrices are single-GPU only
-    cudaSetDevice(c->device);
+    enterContext(c);
     memset(res->stage_ms, 0, sizeof(res->stage_ms));
     c->launches = 0;
     c->spmvLaunches = 0;
@@ -633,7 +666,7 @@ int avs_spmv_csr(AvsContext *c, int64_t n, const int64_t *rowPtr, const int32_t 
                  int precision, int repeats, float *msPerLaunch) {
     if (!c || !x || !y) return AVS_ERR_INVALID_ARGUMENT;
     if (c->nranks > 1) return AVS_ERR_UNSUPPORTED;
-    cudaSetDevice(c->device);
+    enterContext(c);
     int rc = uploadCsr(c, n, rowPtr, col, val, precision);
     if (rc) return rc;
     const size_t vb = (size_t)std::max<int64_t>(n, 1) * sizeof(double);
@@ -650,7 +683,7 @@ int avs_spmv_csr(AvsContext *c, int64_t n, const int64_t *rowPtr, const int32_t 
 int avs_time_spmv_resident(AvsContext *c, int precision, int repeats, float *msPerLaunch, double *algorithmicBytes) {
     if (!c || !msPerLaunch || c->A.n == 0) return AVS_ERR_INVALID_ARGUMENT;
     (void)precision;
-    cudaSetDevice(c->device);
+    enterContext(c);
     const double s = c->A.precision == AVS_PRECISION_F32 ? 4.0 : 8.0;
     if (algorithmicBytes) *algorithmicBytes = (double)c->A.nnz * (s + 4.0) + (double)(c->A.n + 1) * 4.0 + 2.0 * (double)c->A.n * s;
     return avs_spmv_time(c, c->A, repeats, msPerLaunch);
@@ -678,6 +711,9 @@ int avs_create_multi(const int32_t *devices, int32_t n, int32_t time_spmv, AvsMu
     m->n = n;
     std::vector<int> devs(devices, devices + n);
     m->group = n > 1 ? avs_local_group_create(n, devs.data()) : nullptr;
+    for (int r = 0; r < n; ++r)
+        for (int q = 0; q < r; ++q)
+            if (devs[q] == devs[r]) g_avsAsyncAlloc = true;   // ranks share a device: no device-synchronising allocator calls from now on
     m->ctx.assign(n, nullptr);
     m->status.assign(n, AVS_OK);
     m->res.resize(n);

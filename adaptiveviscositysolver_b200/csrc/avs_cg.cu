@@ -1153,14 +1153,22 @@ struct Pcg2State {                // device-resident, copied back by the host af
     int pad;
 };
 
-// The canonical reduction of the per-CTA partial sums: ONE warp, lane-strided loads straight from L2, shuffle tree.  Every CTA of
-// every rank uses this order (and so does the CTA that posts the rank's sum to the peers), hence bit-identical scalars everywhere.
-__device__ __forceinline__ double warpReduceParts(const double *parts, int n, int lane) {
+// The canonical reduction of the per-CTA partial sums (every CTA of every rank uses this one order, and so does the CTA that posts
+// the rank's sum to the peers: bit-identical scalars everywhere).  Loads go straight to L2 (other CTAs wrote the partials).
+__device__ __forceinline__ double reducePartsCg(const double *parts, int n, double *sh /* [CG_THREADS/32 + 1] */) {
     double v = 0;
-    for (int i = lane; i < n; i += 32) v += __ldcg(parts + i);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+    for (int i = threadIdx.x; i < n; i += CG_THREADS) v += __ldcg(parts + i);
+    v = warpSum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int i = 0; i < CG_THREADS / 32; ++i) t += sh[i];
+        sh[CG_THREADS / 32] = t;
+    }
+    __syncthreads();
+    return sh[CG_THREADS / 32];
 }
 template <class ST>
 __device__ __forceinline__ bool spinTimedOut(unsigned &spins, unsigned long long &t0, ST *st) {
@@ -1173,45 +1181,41 @@ __device__ __forceinline__ bool spinTimedOut(unsigned &spins, unsigned long long
 }
 
 // v[0..COUNT): this CTA's partial sums (valid in thread 0).  On return: the sums over all CTAs of all ranks, the same bits in every
-// thread of every CTA of every rank.  Also the grid barrier between two phases.  Warp 0 does the work:
-//   lane 0 publishes the CTA's partials and bumps the arrival counter; the LAST CTA to arrive reduces the rank's partials and stores
-//   the sums into the mailboxes of the PEERS (flag-in-data words); every CTA waits for the counter (local barrier), reduces the
-//   partials itself (same canonical order), then -- P > 1 -- waits for the peers' words and adds the P contributions in rank order.
+// thread of every CTA of every rank.  Also the grid barrier between two phases.
+//   every CTA publishes its partials and bumps the arrival counter, waits for the counter (the local barrier: one release fence, one
+//   acquire fence per CTA, like a plain grid barrier) and reduces the partials itself;
+//   P > 1: the LAST CTA to arrive reduces first and stores the rank's sums into the mailboxes of the PEERS as flag-in-data words, so
+//   the NVLink trip overlaps the other CTAs' own reduction; everybody then waits for the peers' words and adds the P contributions in
+//   rank order.  shw: 4 * P2P_MAX_RANKS words.
 template <int COUNT>
 __device__ __forceinline__ bool syncSum(double (&v)[COUNT], double *parts, unsigned *counter, unsigned &target, const PcgDist &D, P2PHeader *mine,
-                                        unsigned long long seq, Pcg2State *st, double *shOut /* [COUNT] */) {
+                                        unsigned long long seq, Pcg2State *st, double *sh, unsigned *shw, int *shLast) {
     const int G = gridDim.x;
-    const int lane = threadIdx.x & 31;
+    const int par = (int)(seq & 1ull);
+    const unsigned long long tag = (seq & 0xffffffffull) << 32;
+    const int words = (D.P - 1) * COUNT * 2;
     target += (unsigned)G;
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int q = 0; q < COUNT; ++q) parts[q * G + blockIdx.x] = v[q];
     }
-    __syncthreads();   // every thread's writes of this phase precede lane 0's release below
-    if (threadIdx.x < 32) {
-        const int par = (int)(seq & 1ull);
-        const unsigned long long tag = (seq & 0xffffffffull) << 32;
-        int last = 0;
-        if (lane == 0) {
-            fenceGpu();
-            const unsigned prev = atomicAdd(counter, 1u);
-            last = (prev + 1u == target) ? 1 : 0;
-        }
-        last = __shfl_sync(0xffffffffu, last, 0);
-        double tot[COUNT];
-        bool have = false;
-        if (last) {   // warp-uniform: the partials of all CTAs of this rank are in L2
-            if (lane == 0) fenceGpu();
-            __syncwarp();
+    __syncthreads();   // every thread's writes of this phase precede thread 0's release below
+    if (threadIdx.x == 0) {
+        fenceGpu();
+        const unsigned prev = atomicAdd(counter, 1u);
+        if (D.P > 1) *shLast = (prev + 1u == target) ? 1 : 0;
+    }
+    double tot[COUNT];
+    if (D.P > 1) {
+        __syncthreads();
+        if (*shLast) {   // CTA-uniform: every CTA of this rank has arrived, its partials are in L2
+            if (threadIdx.x == 0) fenceGpu();
 #pragma unroll
-            for (int q = 0; q < COUNT; ++q) tot[q] = warpReduceParts(parts + q * G, G, lane);
-            have = true;
-            // one lane per (peer, value, half): sender-side slot index = myRank
-            const int words = (D.P - 1) * COUNT * 2;
-            if (lane < words) {
-                int peerRank = lane / (COUNT * 2);
+            for (int q = 0; q < COUNT; ++q) tot[q] = reducePartsCg(parts + q * G, G, sh);
+            if (threadIdx.x < words) {   // one thread per (peer, value, half); my slot in the peer's mailbox = my rank
+                int peerRank = threadIdx.x / (COUNT * 2);
                 if (peerRank >= D.myRank) ++peerRank;
-                const int q = (lane >> 1) % COUNT, half = lane & 1;
+                const int q = (threadIdx.x >> 1) % COUNT, half = threadIdx.x & 1;
                 unsigned long long bits = 0;
 #pragma unroll
                 for (int i = 0; i < COUNT; ++i)
@@ -1219,63 +1223,49 @@ __device__ __forceinline__ bool syncSum(double (&v)[COUNT], double *parts, unsig
                 const unsigned long long word = (half ? (bits >> 32) : (bits & 0xffffffffull)) | tag;
                 *(volatile unsigned long long *)&((P2PHeader *)D.peerRegion[peerRank])->ll[par][D.myRank][q][half] = word;
             }
-        } else {
-            if (lane == 0) {   // local barrier
-                unsigned long long t0 = 0;
-                unsigned spins = 0;
-                while (ldVolatileU32(counter) < target)
-                    if (spinTimedOut(spins, t0, st)) break;
-                fenceGpu();
-            }
-            __syncwarp();
-        }
-        if (!have) {
-#pragma unroll
-            for (int q = 0; q < COUNT; ++q) tot[q] = warpReduceParts(parts + q * G, G, lane);
-        }
-        if (D.P > 1) {
-            // the peers' words: lane = (sender slot, value, half); senders in rank order, my own contribution from `tot`
-            const int words = (D.P - 1) * COUNT * 2;
-            unsigned lo32 = 0;
-            if (lane < words) {
-                int sender = lane / (COUNT * 2);
-                if (sender >= D.myRank) ++sender;
-                const int q = (lane >> 1) % COUNT, half = lane & 1;
-                const unsigned long long *slot = &mine->ll[par][sender][q][half];
-                unsigned long long w = ldVolatileU64(slot), t0 = 0;
-                unsigned spins = 0;
-                while ((w & 0xffffffff00000000ull) != tag) {
-                    if (spinTimedOut(spins, t0, st)) break;
-                    w = ldVolatileU64(slot);
-                }
-                lo32 = (unsigned)(w & 0xffffffffull);
-            }
-#pragma unroll
-            for (int q = 0; q < COUNT; ++q) {
-                double t = 0;
-                int slotLane = 0;   // lane that holds (sender r, value q, half 0)
-                for (int r = 0; r < D.P; ++r) {
-                    double c;
-                    if (r == D.myRank) c = tot[q];
-                    else {
-                        slotLane = ((r > D.myRank ? r - 1 : r) * COUNT + q) * 2;
-                        const unsigned lo = __shfl_sync(0xffffffffu, lo32, slotLane), hi = __shfl_sync(0xffffffffu, lo32, slotLane + 1);
-                        c = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
-                    }
-                    t += c;
-                }
-                tot[q] = t;
-            }
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int q = 0; q < COUNT; ++q) shOut[q] = tot[q];
         }
     }
+    if (threadIdx.x == 0) {   // local barrier
+        unsigned long long t0 = 0;
+        unsigned spins = 0;
+        while (ldVolatileU32(counter) < target)
+            if (spinTimedOut(spins, t0, st)) break;
+        fenceGpu();
+    }
     __syncthreads();
+#pragma unroll
+    for (int q = 0; q < COUNT; ++q) tot[q] = reducePartsCg(parts + q * G, G, sh);
+    if (D.P > 1) {
+        if (threadIdx.x < words) {   // thread = (sender slot, value, half), senders in rank order without me
+            int sender = threadIdx.x / (COUNT * 2);
+            if (sender >= D.myRank) ++sender;
+            const int q = (threadIdx.x >> 1) % COUNT, half = threadIdx.x & 1;
+            const unsigned long long *slot = &mine->ll[par][sender][q][half];
+            unsigned long long w = ldVolatileU64(slot), t0 = 0;
+            unsigned spins = 0;
+            while ((w & 0xffffffff00000000ull) != tag) {
+                if (spinTimedOut(spins, t0, st)) break;
+                w = ldVolatileU64(slot);
+            }
+            shw[threadIdx.x] = (unsigned)(w & 0xffffffffull);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < COUNT; ++q) {
+            double t = 0;
+            for (int r = 0; r < D.P; ++r) {
+                if (r == D.myRank) { t += tot[q]; continue; }
+                const int slotIdx = ((r > D.myRank ? r - 1 : r) * COUNT + q) * 2;
+                const unsigned lo = shw[slotIdx], hi = shw[slotIdx + 1];
+                t += __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+            }
+            tot[q] = t;
+        }
+        __syncthreads();   // shw / shLast are reused by the next sync
+    }
     if (*(volatile int *)&st->abort) return false;
 #pragma unroll
-    for (int q = 0; q < COUNT; ++q) v[q] = shOut[q];
+    for (int q = 0; q < COUNT; ++q) v[q] = tot[q];
     return true;
 }
 
@@ -1289,7 +1279,9 @@ struct Pcg2Args {
     SjdsView<T, T2> M;
     const T *invDiag;
     T *x, *r, *t;
-    T *p[2];             // the two p buffers (owned rows, then halo slots); iteration k of a launch reads p[(parity0 + k) & 1]
+    T *p0;               // p buffer 0 (owned rows, then halo slots); buffer 1 = p0 + pDelta bytes.  Iteration k of a launch reads
+    long long pDelta;    // buffer (parity0 + k) & 1.  Two pointers in an ARRAY would be selected with a register-indexed constant-bank
+                         // load that ptxas re-issues inside the SpMV loop in front of every gather (measured: +14 % SpMV time)
     double *parts;       // 3 * gridDim.x
     CgScalars *sc;
     Pcg2State *st;
@@ -1344,6 +1336,17 @@ __device__ __forceinline__ bool waitHaloReady(const PcgDist &D, P2PHeader *mine,
     return *(volatile int *)&st->abort == 0;
 }
 
+// A/B variant (AVS_SPMV_MODE=call): the slice loop as a function of its own, scheduled and register-allocated independently of the
+// synchronisation code around it.  Measured 13 % slower than the inlined loop (0.527 vs 0.464 ms per SpMV phase at C3), so it is not
+// the default; the instability it was meant to cure turned out to be the p-buffer pointer (see Pcg2Args::p0).
+template <class T, class T2>
+__device__ __noinline__ double spmvSliceCall(long long s, int lane, long long nrows, const long long *sliceOff, const int32_t *meta, const T2 *val2,
+                                             const int2 *col2, const T *p, T *t) {
+    SjdsView<T, T2> M;   // rebuilt from scalars: a by-reference struct would be read through local memory on every use
+    M.nrows = nrows; M.nslices = 0; M.sliceOff = sliceOff; M.meta = meta; M.val2 = val2; M.col2 = col2;
+    return spmvOneSlice<T, T2, true, 4, false>(s, lane, M, p, t);
+}
+
 // SPMV_MODE: 0 register-staged slice loop, 1 + L2 prefetch, 2 per-warp cp.async ring (8 pair-steps, trips of 4)
 template <class T, class T2, int SPMV_MODE>
 __device__ __forceinline__ double pcgSlice(long long s, int lane, const SjdsView<T, T2> &M, const T *p, T *t, unsigned char *ring) {
@@ -1354,6 +1357,7 @@ __device__ __forceinline__ double pcgSlice(long long s, int lane, const SjdsView
         return spmvOneSliceRing<T, T2, true, 4, false, 8>(s, lane, M.meta[s * 32 + lane], M.sliceOff[s], M, p, t, ringVal, ringCol);
     }
     if (SPMV_MODE == 1) return spmvOneSlicePf<T, T2, true, 4, false>(s, lane, M, p, t);
+    if (SPMV_MODE == 3) return spmvSliceCall<T, T2>(s, lane, M.nrows, M.sliceOff, M.meta, M.val2, M.col2, p, t);   // A/B: measured 13 % slower
     return spmvOneSlice<T, T2, true, 4, false>(s, lane, M, p, t);
 }
 
@@ -1361,7 +1365,8 @@ template <class T, class T2, int SPMV_MODE, int MINB>
 __global__ void __launch_bounds__(CG_THREADS, MINB) k_cg_persistent2(const __grid_constant__ Pcg2Args<T, T2> A) {
     extern __shared__ __align__(128) unsigned char dynSmem[];
     __shared__ double sh[CG_THREADS / 32 + 1];
-    __shared__ double shSum[2];
+    __shared__ unsigned shw[P2P_MAX_RANKS * 4];
+    __shared__ int shLast;
     __shared__ unsigned long long tm[4];   // thread 0 of CTA 0: phase start stamp + 3 accumulators
     __shared__ double rrLast;
     CgScalars *sc = A.sc;
@@ -1388,7 +1393,7 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) k_cg_persistent2(const __gri
     if (timer) { tm[1] = tm[2] = tm[3] = 0; rrLast = sc->residualNorm2; }
 
     if (A.pushFirst) {   // p_0 sits in buffer parity0 (written by k_cg_init): copy the rows the peers need, then flag
-        const T *pc = A.p[A.parity0];
+        const T *pc = (const T *)((const char *)A.p0 + (A.parity0 ? A.pDelta : 0));
         if (dist)
             for (long long i = gid; i < A.D.nSend; i += gstride) {
                 const int2 dst = A.D.sendDst[i];
@@ -1398,7 +1403,8 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) k_cg_persistent2(const __gri
     }
     while (iters < A.itLimit) {
         const int cur = (A.parity0 + k) & 1;
-        T *pc = A.p[cur], *pn = A.p[cur ^ 1];
+        T *pc = (T *)((char *)A.p0 + (cur ? A.pDelta : 0)), *pn = (T *)((char *)A.p0 + (cur ? 0 : A.pDelta));
+        asm volatile("" : "+l"(pc), "+l"(pn));   // pin both in registers for the whole iteration (no rematerialisation inside the slice loop)
         if (timer) tm[0] = globalTimerNs();
         // ---- t = A p, partial p.t: slices that read no halo slot first, the boundary slices after the peers' values have landed
         double pt[1];
@@ -1418,7 +1424,7 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) k_cg_persistent2(const __gri
             }
             pt[0] = blockSum(dot, sh);
         }
-        if (!syncSum<1>(pt, A.parts, &st->arrive[0], tgtA, A.D, A.mine, A.D.seqReduce + 2ull * k + 1, st, shSum)) break;
+        if (!syncSum<1>(pt, A.parts, &st->arrive[0], tgtA, A.D, A.mine, A.D.seqReduce + 2ull * k + 1, st, sh, shw, &shLast)) break;
         if (timer) { const unsigned long long now = globalTimerNs(); tm[1] += now - tm[0]; tm[0] = now; }
         const double alphaD = rho / pt[0];
         breakdown = !isfinite(alphaD);
@@ -1448,7 +1454,7 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) k_cg_persistent2(const __gri
             rs[0] = blockSum(rr, sh);
             rs[1] = blockSum(rz, sh);
         }
-        if (!syncSum<2>(rs, A.parts + G, &st->arrive[1], tgtB, A.D, A.mine, A.D.seqReduce + 2ull * k + 2, st, shSum)) break;
+        if (!syncSum<2>(rs, A.parts + G, &st->arrive[1], tgtB, A.D, A.mine, A.D.seqReduce + 2ull * k + 2, st, sh, shw, &shLast)) break;
         if (timer) { const unsigned long long now = globalTimerNs(); tm[2] += now - tm[0]; tm[0] = now; }
         ++k;
         if (timer) rrLast = rs[0];
@@ -1572,6 +1578,7 @@ static int spmvMode() {
         if (e && strcmp(e, "pf") == 0) m = 1;
         if (e && strcmp(e, "ring") == 0) m = 2;
         if (e && strcmp(e, "ring4") == 0) m = 3;
+        if (e && strcmp(e, "call") == 0) m = 4;     // persistent kernel calling the slice loop as a separate function (stand-alone SpMV: base)
     }
     return m;
 }
@@ -1581,6 +1588,7 @@ static const void *pcg2Kernel(size_t *smemOut) {
     size_t smem = 0;
     switch (spmvMode()) {
         case 1: k = (const void *)k_cg_persistent2<T, T2, 1, 4>; break;
+        case 4: k = (const void *)k_cg_persistent2<T, T2, 3, 4>; break;
         case 2:
         case 3: k = (const void *)k_cg_persistent2<T, T2, 2, 4>; smem = (CG_THREADS / 32) * spmvRingBytesPerWarp<T2, 8>(); break;
         default: k = (const void *)k_cg_persistent2<T, T2, 0, 4>; break;
@@ -1616,7 +1624,7 @@ static void launchSpmv(AvsContext *c, SellMatrix &A, const T *x, T *y, double *p
             attrSet[DOT] = true;
         }
         k_spmv_tma<T, T2, DOT><<<grid, TMA_THREADS, smem, c->stream>>>(sjdsView<T, T2>(A), x, y, parts, sc);
-    } else if (spmvMode() >= 2) {   // per-warp cp.async ring: 8 pair-steps in trips of 4 (mode 2) or 4 pair-steps in trips of 2 (mode 3)
+    } else if (spmvMode() == 2 || spmvMode() == 3) {   // per-warp cp.async ring: 8 pair-steps in trips of 4 (mode 2) or 4 pair-steps in trips of 2 (mode 3)
 #define RING_LAUNCH(U, R)                                                                                                        \
     {                                                                                                                            \
         static bool attrSet = false;                                                                                             \
@@ -1762,6 +1770,7 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
         k_cg_init_scalars<<<1, CG_THREADS, 0, c->stream>>>(parts, grid, p->tolerance, tiny, sc);
     c->launches += 2;
 
+    AVS_TRACE("cg: init done, entering the loop (pgrid %d, grid %d, sgrid %d)", pgrid, grid, sgrid);
     const int maxIters = p->max_iterations;
     CgScalars *hs = (CgScalars *)c->hostScalars;  // pinned
     PcgDist pd;
@@ -1782,8 +1791,8 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
         ka.parity0 = 0;
         if (dist) {
             ka.D = pd;
-            ka.p[0] = pp;
-            ka.p[1] = (T *)((char *)pp + pd.pStrideBytes);
+            ka.p0 = pp;
+            ka.pDelta = (long long)pd.pStrideBytes;
             ka.mine = (P2PHeader *)((char *)pp - P2P_HEADER_BYTES);
             // slices that gather from a halo slot run after the peers' values have landed: flag them, list them in ascending order
             if (w.sliceHalo.reserve((size_t)std::max<long long>(A.nslices, 1)) || w.sliceFlag.reserve((size_t)std::max<long long>(A.nslices, 1) * 4) ||
@@ -1815,8 +1824,8 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
             AVS_CUDA_CHECK(cudaMemcpyAsync((char *)w.pcgLocal.p + P2P_HEADER_BYTES, &self, sizeof(void *), cudaMemcpyHostToDevice, c->stream));
             ka.D = PcgDist();
             ka.D.peerRegion = (void *const *)((char *)w.pcgLocal.p + P2P_HEADER_BYTES);
-            ka.p[0] = pp;
-            ka.p[1] = pp + pPad;
+            ka.p0 = pp;
+            ka.pDelta = (long long)pPad * (long long)sizeof(T);
             ka.mine = (P2PHeader *)w.pcgLocal.p;
         }
         size_t smem2 = 0;
@@ -1827,6 +1836,7 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
             ka.itLimit = std::min(maxIters, itersKnown + std::max(chunk, 1));
             void *kargs[] = {(void *)&ka};
             AVS_CUDA_CHECK(cudaEventRecord(c->evPcg[0], c->stream));
+            AVS_TRACE("rank %d cg: cooperative launch, grid %d itLimit %d smem %zu seqPush %llu seqReduce %llu", c->rank, pgrid, ka.itLimit, smem2, ka.D.seqPush, ka.D.seqReduce);
             AVS_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(pgrid), dim3(CG_THREADS), kargs, smem2, c->stream));
             AVS_CUDA_CHECK(cudaEventRecord(c->evPcg[1], c->stream));
             ++c->launches;
@@ -1838,6 +1848,7 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
                 float ms = 0;
                 if (cudaEventElapsedTime(&ms, c->evPcg[0], c->evPcg[1]) == cudaSuccess) c->pcgKernelMs += ms;
             }
+            AVS_TRACE("rank %d cg: kernel returned, iters %d done %d abort %d", c->rank, hs[0].iters, hs[0].done, hst->abort);
             if (hst->abort) {
                 c->lastError = "persistent CG kernel timed out waiting for its own CTAs or a peer";
                 avs_set_last_error("k_cg_persistent2 (spin-wait timeout)", cudaErrorLaunchTimeout, __FILE__, __LINE__);
@@ -2005,6 +2016,11 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
             cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
             cudaCtxResetPersistingL2Cache();
         }
+    }
+    if (dist && avs_dist_timed_out(c)) {
+        c->lastError = "a multi-GPU exchange kernel timed out waiting for a peer";
+        avs_set_last_error("halo exchange / all-reduce (spin-wait timeout)", cudaErrorLaunchTimeout, __FILE__, __LINE__);
+        return AVS_ERR_CUDA;
     }
     CgScalars fin = hs[0];
     if (fin.zeroRhs) {

@@ -182,3 +182,13 @@ struct RowKey {
     } while (0)
 
 void avs_set_last_error(const char *what, cudaError_t e, const char *file, int line);
+
+// AVS_TRACE=1 in the environment: one stderr line per pipeline step (debugging aid; a getenv per call site otherwise)
+#include <cstdio>
+#include <cstdlib>
+#define AVS_TRACE(...)                                                          \
+    do {                                                                        \
+        static int _on = -1;                                                    \
+        if (_on < 0) { const char *_e = getenv("AVS_TRACE"); _on = (_e && _e[0] == '1') ? 1 : 0; } \
+        if (_on) { fprintf(stderr, "[avs] " __VA_ARGS__); fputc('\n', stderr); fflush(stderr); }   \
+    } while (0)

@@ -11,15 +11,41 @@
 
 // Growable device buffer: allocations are cached in the context across solves (the reference
 // rebuilds everything per call, HDK_AdaptiveViscosity.cpp:233-707; here only the contents are).
+// Ranks that SHARE one device (avs_create_multi with a repeated ordinal: the one-GPU test configuration) must never make a
+// device-synchronising call while a peer's kernel spins on a flag they are about to raise: cudaFree / cudaMalloc would wait for
+// that kernel -> deadlock.  In that mode buffers come from the stream-ordered allocator on the calling thread's context stream.
+extern bool g_avsAsyncAlloc;                     // set once by avs_create_multi when two ranks share a device
+extern thread_local cudaStream_t g_avsTlsStream; // stream of the context the calling thread is currently working for
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
-    int reserve(size_t bytes) {
-        if (bytes <= cap) return 0;
-        if (p) cudaFree(p);
+    bool async = false;
+    void freeNow() {
+        if (!p) return;
+        if (async) {
+            cudaStreamSynchronize(g_avsTlsStream);   // kernels of this context that still use the buffer
+            cudaFreeAsync(p, g_avsTlsStream);
+        } else cudaFree(p);
         p = nullptr;
         cap = 0;
+    }
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        freeNow();
         size_t want = bytes + bytes / 8 + 256;
+        if (g_avsAsyncAlloc) {
+            if (cudaMallocAsync(&p, want, g_avsTlsStream) != cudaSuccess) {
+                cudaGetLastError();
+                want = bytes;
+                if (cudaMallocAsync(&p, want, g_avsTlsStream) != cudaSuccess) { cudaGetLastError(); p = nullptr; return -1; }
+            }
+            cudaStreamSynchronize(g_avsTlsStream);   // the context's other streams (copy stream) may use the buffer next
+            async = true;
+            cap = want;
+            return 0;
+        }
+        async = false;
         if (cudaMalloc(&p, want) != cudaSuccess) {
             cudaGetLastError();
             if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); p = nullptr; return -1; }
@@ -28,11 +54,7 @@ struct DevBuf {
         cap = want;
         return 0;
     }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
+    void release() { freeNow(); }
     template <class T> T *as() const { return (T *)p; }
 };
 
@@ -162,6 +184,7 @@ int avs_dist_build_halo(AvsContext *c);
 int avs_dist_halo_exchange(AvsContext *c, void *p, int precision, const int *done);
 void *avs_dist_prepare_p(AvsContext *c, int *rcOut);
 int avs_dist_mode(AvsContext *c);
+bool avs_dist_timed_out(AvsContext *c);
 struct PcgDist;
 bool avs_dist_pcg_args(AvsContext *c, PcgDist *out);
 void avs_dist_pcg_commit(AvsContext *c, unsigned long long seqPush, unsigned long long seqReduce);

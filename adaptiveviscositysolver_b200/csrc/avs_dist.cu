@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstddef>
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
@@ -421,6 +422,13 @@ int avs_dist_build_halo(AvsContext *c) {
 
 // ---- peer-memory mode ------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long ldVolatile(const unsigned long long *p) { return *(const volatile unsigned long long *)p; }
+// 8 s on %globaltimer since the first call (t0 == 0)
+__device__ __forceinline__ bool spinExpired(unsigned long long &t0) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (t0 == 0) { t0 = now; return false; }
+    return now - t0 > 8000000000ull;
+}
 
 struct RowStarts { long long v[P2P_MAX_RANKS + 1]; };
 __global__ void k_halo_sources(long long nHalo, const int32_t *haloCols, const __grid_constant__ RowStarts starts, int P, int2 *src) {
@@ -445,7 +453,11 @@ __global__ void k_p2p_halo_pull(long long nHalo, const int2 *src, void *const *p
     }
     if (threadIdx.x < P && ((neighbourMask >> threadIdx.x) & 1u)) {
         const P2PHeader *peer = (const P2PHeader *)peerRegion[threadIdx.x];
-        while (ldVolatile(&peer->ready) < seq) __nanosleep(200);
+        unsigned long long t0 = 0;
+        while (ldVolatile(&peer->ready) < seq) {
+            __nanosleep(200);
+            if (spinExpired(t0)) { *(volatile unsigned long long *)&mine->timedOut = 1; break; }   // a lost peer must not hang the GPU
+        }
     }
     __syncthreads();
     __threadfence_system();
@@ -485,7 +497,11 @@ __global__ void k_p2p_allreduce(const double *parts, int nparts, int count, void
     }
     P2PHeader *mine = (P2PHeader *)peerRegion[myRank];
     if (threadIdx.x < P) {
-        while (ldVolatile(&mine->flag[par][threadIdx.x]) != seq) __nanosleep(100);
+        unsigned long long t0 = 0;
+        while (ldVolatile(&mine->flag[par][threadIdx.x]) != seq) {
+            __nanosleep(100);
+            if (spinExpired(t0)) { *(volatile unsigned long long *)&mine->timedOut = 1; break; }
+        }
     }
     __syncthreads();
     __threadfence_system();
@@ -499,6 +515,7 @@ __global__ void k_p2p_allreduce(const double *parts, int nparts, int count, void
 // (Re)creates the exported region so that it can hold `elems` vector elements of 8 bytes; collective.
 static int p2pEnsureRegion(AvsContext *c, size_t elems) {
     DistState *d = (DistState *)c->dist;
+    AVS_TRACE("rank %d: ensure region for %zu elements (have %zu bytes)", c->rank, elems, d->regionBytes);
     const int P = c->nranks;
     // agree on the capacity: max over ranks
     unsigned long long need = (unsigned long long)(P2P_HEADER_BYTES + elems * 8 + 256);
@@ -674,6 +691,7 @@ int avs_dist_halo_exchange(AvsContext *c, void *p, int precision, const int *don
         for (int q = 0; q < c->nranks; ++q)
             if (q != c->rank && d->recvCnt[q] > 0) mask |= 1u << q;
         ++d->seqReady;
+        AVS_TRACE("rank %d: halo pull seq %llu (nHalo %lld, mask %x)", c->rank, d->seqReady, d->nHalo, mask);
         unsigned blocks = (unsigned)std::max<long long>(1, (d->nHalo + 255) / 256);
         if (precision == AVS_PRECISION_F32)
             k_p2p_halo_pull<float><<<blocks, 256, 0, c->stream>>>(d->nHalo, d->haloSrc.as<int2>(), d->peerTable.as<void *>(), c->rank, c->nranks,
@@ -694,6 +712,7 @@ int avs_dist_allreduce_parts(AvsContext *c, const double *parts, int nparts, int
     DistState *d = (DistState *)c->dist;
     if (d && d->p2p) {
         ++d->seqReduce;
+        AVS_TRACE("rank %d: p2p allreduce seq %llu (count %d)", c->rank, d->seqReduce, count);
         k_p2p_allreduce<<<1, 256, 0, c->stream>>>(parts, nparts, count, d->peerTable.as<void *>(), c->rank, c->nranks, d->seqReduce, out, done);
         ++c->launches;
         return AVS_OK;
@@ -745,6 +764,17 @@ int avs_dist_allgather_slabs(AvsContext *c, float *dOut[3]) {
         if (rc) return rc;
     }
     return AVS_OK;
+}
+
+// true when one of the per-launch exchange kernels gave up waiting for a peer (the solve's result is then garbage)
+bool avs_dist_timed_out(AvsContext *c) {
+    DistState *d = (DistState *)c->dist;
+    if (!d || !d->p2p || !d->region) return false;
+    unsigned long long v = 0;
+    if (cudaMemcpyAsync(&v, (char *)d->region + offsetof(P2PHeader, timedOut), sizeof(v), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return false;
+    cudaStreamSynchronize(c->stream);
+    if (v) cudaMemsetAsync((char *)d->region + offsetof(P2PHeader, timedOut), 0, sizeof(v), c->stream);
+    return v != 0;
 }
 
 // 0 = single GPU, 1 = NCCL hot loop, 2 = peer-memory hot loop

@@ -25,23 +25,37 @@
         }                                                                                      \
     } while (0)
 
+// grid-stride counting kernels: 16 elements per thread and trip, at most 8 CTAs per SM
+#define LAUNCH_COUNT(ctx, kernel, count, ...)                                                  \
+    do {                                                                                       \
+        size_t _n = (size_t)(count);                                                           \
+        if (_n > 0) {                                                                          \
+            unsigned _b = (unsigned)std::min<size_t>((_n / 16 + 255) / 256 + 1, (size_t)(ctx)->numSMs * 8); \
+            kernel<<<_b, 256, 0, (ctx)->stream>>>(__VA_ARGS__);                                \
+            ++(ctx)->launches;                                                                 \
+        }                                                                                      \
+    } while (0)
+
 static_assert(sizeof(DeviceScene) <= 4000, "DeviceScene must fit the kernel parameter space");
 
-// Grid kernels are launched as (ceil(nx/128), ny, nz) x 128 threads: x from the thread index, y/z from the block
-// index -- no 64-bit div/mod per thread (that cost more than the memory traffic of these streaming passes).
+// Grid kernels are launched as (ceil(nx/128), ceil(ny/CELL_YB), nz) x (128, CELL_YB) threads: x and y from the thread index,
+// z from the block index -- no 64-bit div/mod per thread (that cost more than the memory traffic of these streaming passes).
+// One 128-thread CTA per grid row made a 512^3 sweep one million CTAs: every such kernel sat on the same 0.54 ms floor (the
+// CTA launch rate, ~150 cycles per CTA and SM) whatever it read or wrote; four rows per CTA lift the floor.
+#define CELL_YB 4
 #define LAUNCH_3D(ctx, kernel, n3, ...)                                                        \
     do {                                                                                       \
         if ((n3)[0] > 0 && (n3)[1] > 0 && (n3)[2] > 0) {                                        \
-            dim3 _g((unsigned)(((n3)[0] + 127) / 128), (unsigned)(n3)[1], (unsigned)(((n3)[2] + ZREP - 1) / ZREP));    \
-            kernel<<<_g, 128, 0, (ctx)->stream>>>(__VA_ARGS__);                                \
+            dim3 _g((unsigned)(((n3)[0] + 127) / 128), (unsigned)(((n3)[1] + CELL_YB - 1) / CELL_YB), (unsigned)(((n3)[2] + ZREP - 1) / ZREP));    \
+            kernel<<<_g, dim3(128, CELL_YB), 0, (ctx)->stream>>>(__VA_ARGS__);                  \
             ++(ctx)->launches;                                                                 \
         }                                                                                      \
     } while (0)
 #define ZREP 1   // grid cells per thread along z (8 was measured slower: serialises the per-cell loads of a thread)
 template <class F>
 __device__ __forceinline__ void forCells(const int n[3], F f) {
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y;
-    const bool inx = x < n[0];
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y);
+    const bool inx = x < n[0] && y < n[1];
     for (int r = 0; r < ZREP; ++r) {
         const int z = (int)blockIdx.z * ZREP + r;
         if (z >= n[2]) return;  // uniform over the CTA
@@ -52,9 +66,9 @@ __device__ __forceinline__ void forCells(const int n[3], F f) {
 // z-window variant: blockIdx.z counts planes from zOff (multi-GPU z-slabs of the regular grid)
 template <class F>
 __device__ __forceinline__ void forCellsZ(const int n[3], int zOff, F f) {
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z + zOff;
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y), z = (int)blockIdx.z + zOff;
     if (z >= n[2]) return;
-    f(x, y, z, (size_t)x + (size_t)n[0] * ((size_t)y + (size_t)n[1] * (size_t)z), x < n[0]);
+    f(x, y, z, (size_t)x + (size_t)n[0] * ((size_t)y + (size_t)n[1] * (size_t)z), x < n[0] && y < n[1]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -159,10 +173,10 @@ __device__ void sdfWeightSample(Grid3<float> w, const DField &sdf, double off0, 
 // the register-heavy sampler below ran the trivial 98 % of the samples at 12 % occupancy).
 __global__ void k_weights_classify(Grid3<float> w, int sn0, int sn1, int sn2, const uint8_t *signClass, uint32_t *list,
                                    unsigned long long *listCount) {
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y), z = (int)blockIdx.z;
     bool band = false;
     size_t idx = 0;
-    if (x < w.n[0]) {
+    if (x < w.n[0] && y < w.n[1]) {
         idx = w.lin(x, y, z);
         int cx = min(x, sn0 - 1), cy = min(y, sn1 - 1), cz = min(z, sn2 - 1);
         uint8_t cls = signClass[(size_t)cx + (size_t)sn0 * ((size_t)cy + (size_t)sn1 * cz)];
@@ -238,8 +252,8 @@ static int weightsFor(AvsContext *c, DevBuf &buf, Grid3<float> &g, const DField 
         if (c->bandList.reserve(g.count() * sizeof(uint32_t))) return AVS_ERR_ALLOC;
         unsigned long long *cnt = c->counters.as<unsigned long long>() + 30;
         AVS_CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
-        dim3 grid((unsigned)((g.n[0] + 127) / 128), (unsigned)g.n[1], (unsigned)g.n[2]);
-        k_weights_classify<<<grid, 128, 0, c->stream>>>(g, sdf.n[0], sdf.n[1], sdf.n[2], signClass, c->bandList.as<uint32_t>(), cnt);
+        dim3 grid((unsigned)((g.n[0] + 127) / 128), (unsigned)((g.n[1] + CELL_YB - 1) / CELL_YB), (unsigned)g.n[2]);
+        k_weights_classify<<<grid, dim3(128, CELL_YB), 0, c->stream>>>(g, sdf.n[0], sdf.n[1], sdf.n[2], signClass, c->bandList.as<uint32_t>(), cnt);
         ++c->launches;
         unsigned long long h = 0;
         AVS_CUDA_CHECK(cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
@@ -382,13 +396,30 @@ __global__ void k_octree_top(Grid3<uint8_t> g) {
     if (idx < g.count() && g.d[idx] == L_UP) g.d[idx] = L_ACTIVE;
 }
 
+// one-byte element types only: 16 elements per thread and trip (128-bit loads), grid-stride, one atomic per CTA
 template <class T>
 __global__ void k_count_equal(const T *d, size_t n, T value, unsigned long long *counter) {
-    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool hit = idx < n && d[idx] == value;
-    unsigned m = __ballot_sync(0xffffffffu, hit);
+    static_assert(sizeof(T) == 1, "byte grids");
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (size_t)gridDim.x * blockDim.x;
+    const unsigned char key = (unsigned char)value;
+    const size_t head = min(n, (size_t)((16 - ((uintptr_t)d & 15)) & 15));   // elements before the first 16-byte boundary
+    int cnt = 0;
+    for (size_t i = tid; i < head; i += nthreads) cnt += ((const unsigned char *)d)[i] == key;
+    const uint4 *v = (const uint4 *)((const unsigned char *)d + head);
+    const size_t nvec = (n - head) / 16;
+    for (size_t i = tid; i < nvec; i += nthreads) {
+        const uint4 q = v[i];
+        const unsigned w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) cnt += ((w[j] >> (8 * b)) & 0xffu) == key;
+    }
+    for (size_t i = head + nvec * 16 + tid; i < n; i += nthreads) cnt += ((const unsigned char *)d)[i] == key;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     __shared__ int s[8];
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = __popc(m);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = cnt;
     __syncthreads();
     if (threadIdx.x == 0) {
         int t = 0;
@@ -452,7 +483,7 @@ int avs_stage_octree(AvsContext *c, const AvsParams *p) {
     unsigned long long *cnt = c->counters.as<unsigned long long>();
     AVS_CUDA_CHECK(cudaMemsetAsync(cnt, 0, 64 * sizeof(unsigned long long), c->stream));
     for (int l = 0; l < L; ++l)
-        LAUNCH_1D(c, k_count_equal<uint8_t>, S.label[l].count(), S.label[l].d, S.label[l].count(), (uint8_t)L_ACTIVE, cnt + l);
+        LAUNCH_COUNT(c, k_count_equal<uint8_t>, S.label[l].count(), S.label[l].d, S.label[l].count(), (uint8_t)L_ACTIVE, cnt + l);
     unsigned long long h[AVS_MAX_LEVELS];
     AVS_CUDA_CHECK(cudaMemcpyAsync(h, cnt, L * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -659,13 +690,13 @@ int avs_stage_regular_labels(AvsContext *c) {
         int z0, z1;
         avs_slab_range(c, a, c->rank, &z0, &z1);
         if (z1 <= z0) continue;
-        dim3 g((unsigned)((S.regular[a].n[0] + 127) / 128), (unsigned)S.regular[a].n[1], (unsigned)(z1 - z0));
-        k_classify_regular<<<g, 128, 0, c->stream>>>(S, a, t[a], z0);
+        dim3 g((unsigned)((S.regular[a].n[0] + 127) / 128), (unsigned)((S.regular[a].n[1] + CELL_YB - 1) / CELL_YB), (unsigned)(z1 - z0));
+        k_classify_regular<<<g, dim3(128, CELL_YB), 0, c->stream>>>(S, a, t[a], z0);
         ++c->launches;
         // regular DOF count (most of the liquid volume: a fused per-warp atomic would serialise on one address)
         const size_t plane = (size_t)S.regular[a].n[0] * S.regular[a].n[1];
         const size_t cntCells = plane * (size_t)(z1 - z0);
-        LAUNCH_1D(c, k_count_equal<int8_t>, cntCells, S.regular[a].d + plane * (size_t)z0, cntCells, (int8_t)F_FLUID, cnt + 16);
+        LAUNCH_COUNT(c, k_count_equal<int8_t>, cntCells, S.regular[a].d + plane * (size_t)z0, cntCells, (int8_t)F_FLUID, cnt + 16);
     }
     if (c->nranks > 1 && (rc2 = avs_dist_allreduce_u64(c, cnt + 16, 1))) return rc2;
     return AVS_OK;

@@ -19,7 +19,8 @@ struct P2PHeader {
     // persistent CG kernel: flag-in-data mailboxes (the idea of NCCL's LL protocol) -- one 8-byte store carries 32 payload
     // bits and the 32-bit sequence number, so no fence separates data and flag: ll[parity][sender][value][half]
     unsigned long long ll[2][P2P_MAX_RANKS][3][2];
-    unsigned long long localReady;                          // sequence number of the p vector whose OWNED rows are complete
+    unsigned long long localReady;                          // (unused since the arrival counter doubles as the local barrier)
+    unsigned long long timedOut;                            // set by an exchange kernel that gave up waiting for a peer
 };
 static_assert(sizeof(P2PHeader) <= P2P_HEADER_BYTES, "header too large");
 

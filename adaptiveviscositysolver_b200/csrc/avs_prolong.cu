@@ -48,8 +48,8 @@ __device__ __forceinline__ float octVel(const DeviceScene &S, const double *sol,
 
 // setActiveNodes (VFI.cpp:118-188) + sampleActiveNodes (VFI.cpp:190-286)
 __global__ void k_node_sample(const __grid_constant__ DeviceScene S, NodeLevel nl, const double *sol, int level) {
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
-    if (x >= nl.label.n[0]) return;
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y), z = (int)blockIdx.z;
+    if (x >= nl.label.n[0] || y >= nl.label.n[1]) return;
     const size_t idx = nl.label.lin(x, y, z);
     const I3 node = mk3(x, y, z);
     // cheap reject: a node with an active face is a corner of an ACTIVE cell
@@ -104,8 +104,8 @@ __global__ void k_node_sample(const __grid_constant__ DeviceScene S, NodeLevel n
 
 // bubbleActiveNodeValues (VFI.cpp:288-355): one thread per PARENT node (its co-located child is unique)
 __global__ void k_node_bubble(NodeLevel child, NodeLevel par) {
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
-    if (x >= par.label.n[0]) return;
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y), z = (int)blockIdx.z;
+    if (x >= par.label.n[0] || y >= par.label.n[1]) return;
     const int cx = 2 * x, cy = 2 * y, cz = 2 * z;
     if (cx >= child.label.n[0] || cy >= child.label.n[1] || cz >= child.label.n[2]) return;
     const size_t pi = par.label.lin(x, y, z), ci = child.label.lin(cx, cy, cz);
@@ -120,8 +120,8 @@ __global__ void k_node_bubble(NodeLevel child, NodeLevel par) {
 
 // finishIncompleteNodes (VFI.cpp:357-567)
 __global__ void k_node_finish(const __grid_constant__ DeviceScene S, NodeLevel nl, const double *sol, int level) {
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
-    if (x >= nl.label.n[0]) return;
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y), z = (int)blockIdx.z;
+    if (x >= nl.label.n[0] || y >= nl.label.n[1]) return;
     const size_t idx = nl.label.lin(x, y, z);
     if (nl.label.d[idx] != N_ACTIVE) return;
     unsigned flag = nl.flag.d[idx];
@@ -175,8 +175,8 @@ __global__ void k_node_finish(const __grid_constant__ DeviceScene S, NodeLevel n
 
 // normalizeActiveNodes (VFI.cpp:569-613)
 __global__ void k_node_normalize(NodeLevel nl) {
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
-    if (x >= nl.label.n[0]) return;
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y), z = (int)blockIdx.z;
+    if (x >= nl.label.n[0] || y >= nl.label.n[1]) return;
     const size_t idx = nl.label.lin(x, y, z);
     if (nl.label.d[idx] != N_ACTIVE) return;
     for (int a = 0; a < 3; ++a) nl.val[a].d[idx] = (float)((double)nl.val[a].d[idx] / (double)nl.w[a].d[idx]);
@@ -184,8 +184,8 @@ __global__ void k_node_normalize(NodeLevel nl) {
 
 // distributeNodeValuesDown (VFI.cpp:615-658)
 __global__ void k_node_distribute(NodeLevel child, NodeLevel par) {
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
-    if (x >= child.label.n[0]) return;
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y), z = (int)blockIdx.z;
+    if (x >= child.label.n[0] || y >= child.label.n[1]) return;
     const size_t idx = child.label.lin(x, y, z);
     if (child.label.d[idx] != N_DEPENDENT) return;
     const I3 pn = mk3(x >> 1, y >> 1, z >> 1);
@@ -303,7 +303,8 @@ __global__ void k_apply_regular(const __grid_constant__ DeviceScene S, const Nod
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(interpolated, (unsigned long long)__popc(m));
 }
 
-static dim3 grid3(const int n[3]) { return dim3((unsigned)((n[0] + 127) / 128), (unsigned)n[1], (unsigned)n[2]); }
+#define NODE_YB 4   // grid rows per CTA (128 x 4 threads): one row per CTA is bound by the CTA launch rate on 512^3 grids
+static dim3 grid3(const int n[3]) { return dim3((unsigned)((n[0] + 127) / 128), (unsigned)((n[1] + NODE_YB - 1) / NODE_YB), (unsigned)n[2]); }
 
 int avs_apply_regular(AvsContext *c, float *dOut[3], unsigned long long *hostInterpolated, float *const *hostOut) {
     const DeviceScene &S = c->S;
@@ -319,7 +320,7 @@ int avs_apply_regular(AvsContext *c, float *dOut[3], unsigned long long *hostInt
             for (int a = 0; a < 3; ++a) n[a] = S.label[l].n[a] + 1;
             const size_t cnt = (size_t)n[0] * n[1] * n[2];
             // one allocation per level: label | flag | 3 val | 3 w
-            const size_t bytes = cnt * (1 + 2 + 24) + 1024;
+            const size_t bytes = cnt * (1 + 2 + 24) + 8 * 256;   // take() rounds each of the 8 sub-arrays up to 256 B
             if (c->nodes[l].reserve(bytes)) return AVS_ERR_ALLOC;
             char *base = c->nodes[l].as<char>();
             size_t off = 0;
@@ -338,23 +339,23 @@ int avs_apply_regular(AvsContext *c, float *dOut[3], unsigned long long *hostInt
             for (int k = 0; k < 3; ++k) { nl.flag.n[k] = n[k]; nl.label.n[k] = n[k]; }
         }
         for (int l = 0; l < L; ++l) {
-            k_node_sample<<<grid3(NS.lv[l].label.n), 128, 0, c->stream>>>(S, NS.lv[l], sol, l);
+            k_node_sample<<<grid3(NS.lv[l].label.n), dim3(128, NODE_YB), 0, c->stream>>>(S, NS.lv[l], sol, l);
             ++c->launches;
         }
         for (int l = 0; l < L - 1; ++l) {
-            k_node_bubble<<<grid3(NS.lv[l + 1].label.n), 128, 0, c->stream>>>(NS.lv[l], NS.lv[l + 1]);
+            k_node_bubble<<<grid3(NS.lv[l + 1].label.n), dim3(128, NODE_YB), 0, c->stream>>>(NS.lv[l], NS.lv[l + 1]);
             ++c->launches;
         }
         for (int l = 0; l < L - 1; ++l) {
-            k_node_finish<<<grid3(NS.lv[l].label.n), 128, 0, c->stream>>>(S, NS.lv[l], sol, l);
+            k_node_finish<<<grid3(NS.lv[l].label.n), dim3(128, NODE_YB), 0, c->stream>>>(S, NS.lv[l], sol, l);
             ++c->launches;
         }
         for (int l = 0; l < L; ++l) {
-            k_node_normalize<<<grid3(NS.lv[l].label.n), 128, 0, c->stream>>>(NS.lv[l]);
+            k_node_normalize<<<grid3(NS.lv[l].label.n), dim3(128, NODE_YB), 0, c->stream>>>(NS.lv[l]);
             ++c->launches;
         }
         for (int l = L - 2; l >= 0; --l) {
-            k_node_distribute<<<grid3(NS.lv[l].label.n), 128, 0, c->stream>>>(NS.lv[l], NS.lv[l + 1]);
+            k_node_distribute<<<grid3(NS.lv[l].label.n), dim3(128, NODE_YB), 0, c->stream>>>(NS.lv[l], NS.lv[l + 1]);
             ++c->launches;
         }
     }

@@ -11,6 +11,7 @@
 // writes its CSR segment directly (count pass -> scan -> fill pass).
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <cstdio>
 
 #include "avs_context.h"
@@ -441,6 +442,168 @@ __global__ void __launch_bounds__(128, MINB) k_assemble(const __grid_constant__ 
     diagOut[r] = row.val[row.n - 1];  // buildRow adds the diagonal last and it is unique (AV.cpp:2768)
 }
 
+// ---- warp-cooperative assembly (default) ----------------------------------------------------------------------------------------
+// One WARP owns one matrix row.  A row is touched by at most 26 stresses, in the fixed order buildRow visits them: per side of the face
+// the cell-centred stress and up to 8 T-junction ghost edges (9 x 2 slots), then per transverse edge position the sibling (or first
+// child) edge and the edge itself (or second child) (2 x 4 slots).  Lane l decides whether slot l exists and evaluates ITS stencil --
+// so the ~10 stencil evaluations a row needs run side by side instead of one after the other in a single thread -- then the warp
+// merges the slots in slot order: the owner lane broadcasts (column, value) pairs, the row lives in registers (entry e in lane e & 31),
+// a duplicate column is found with one compare + ballot instead of a linear search through local memory.  Same insertion order and the
+// same order of additions per entry as the one-thread-per-row kernel: bit-identical rows.
+struct SlotRef {
+    int kind;   // 0 none, 1 cell-centred stress, 2 edge stress
+    I3 idx;
+    int axis, level;
+};
+__device__ __forceinline__ int otherAxis(int axis, int which) { return which == 0 ? (axis == 0 ? 1 : 0) : (axis == 2 ? 1 : 2); }
+
+__device__ SlotRef rowSlot(const DeviceScene &S, const RowKey &k, int slot) {
+    const int level = k.level, axis = k.axis;
+    const I3 face = mk3(k.i, k.j, k.k);
+    SlotRef r;
+    r.kind = 0; r.idx = face; r.axis = 0; r.level = 0;
+    if (slot < 18) {   // AV.cpp:2547-2649
+        const int dir = slot / 9, sub = slot % 9;
+        const Grid3<uint8_t> &lab = S.label[level];
+        const I3 cell = faceToCell(face, axis, dir);
+        if (cell[axis] < 0 || cell[axis] >= lab.n[axis]) return r;
+        I3 sc;
+        int sl;
+        if (lab.get(cell) == L_ACTIVE) { sc = cell; sl = level; }
+        else { sc = parentOf(cell); sl = level + 1; }
+        if (sl >= S.levels) return r;
+        if (sub == 0) {
+            if (S.center[sl].get(sc) >= 0) { r.kind = 1; r.idx = sc; r.axis = axis; r.level = sl; }
+            return r;
+        }
+        const int t = sub - 1, fa = otherAxis(axis, t >> 2), fd = (t >> 1) & 1, ins = t & 1;
+        const I3 af = cellToFace(sc, fa, fd);
+        if (sl > 0 && S.face[sl][fa].get(af) == F_UNASSIGNED) {
+            const int ea = 3 - fa - axis;
+            const I3 e = childEdgeInFace(af, fa, ea, ins);
+            if (S.edge[sl - 1][ea].get(e) >= 0) { r.kind = 2; r.idx = e; r.axis = ea; r.level = sl - 1; }
+        }
+        return r;
+    }
+    if (slot >= 26) return r;
+    // AV.cpp:2652-2742
+    const int t = slot - 18, ea = otherAxis(axis, t >> 2), dir = (t >> 1) & 1, second = t & 1;
+    const Grid3<int8_t> &eg = S.edge[level][ea];
+    const I3 e = faceToEdge(face, axis, ea, dir);
+    const int8_t ei = eg.get(e);
+    if (ei >= 0) {
+        if (second) { r.kind = 2; r.idx = e; r.axis = ea; r.level = level; }
+        else if (S.enhanced) {   // sibling edge across a transition (AV.cpp:2664-2697)
+            const Grid3<int32_t> &fgrid = S.face[level][axis];
+            const int ta = 3 - ea - axis;
+            I3 af = face;
+            af[ta] += (dir == 0) ? -1 : 1;
+            if (af[ta] >= 0 && af[ta] < fgrid.n[ta] && fgrid.get(af) == F_UNASSIGNED) {
+                I3 se = e;
+                se[ea] += (e[ea] % 2 == 0) ? 1 : -1;
+                if (eg.get(se) >= 0) { r.kind = 2; r.idx = se; r.axis = ea; r.level = level; }
+            }
+        }
+    } else if (ei == F_UNASSIGNED && level > 0) {   // AV.cpp:2714-2742
+        const I3 ce = childEdge(e, ea, second);
+        if (S.edge[level - 1][ea].get(ce) >= 0) { r.kind = 2; r.idx = ce; r.axis = ea; r.level = level - 1; }
+    }
+    return r;
+}
+
+__device__ __forceinline__ double shflD(double v, int src) {
+    return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src), __shfl_sync(0xffffffffu, __double2loint(v), src));
+}
+
+#define ASM_WARPS 4
+__global__ void __launch_bounds__(ASM_WARPS * 32) k_assemble_warp(const __grid_constant__ DeviceScene S, const RowKey *keys, const double *x0,
+                                                                  long long rowBegin, long long nLocal, long long stride, int32_t *rowCount,
+                                                                  int32_t *stageCol, double *stageVal, double *rhs, double *diagOut, int *overflowFlag) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    Stencil st;
+    for (long long r = warp; r < nLocal; r += nWarps) {
+        const long long gi = rowBegin + r;
+        const int32_t vi = (int32_t)gi;
+        const RowKey k = keys[gi];
+        // ---- every lane: does my slot exist? then my stencil, my weight, my row coefficient
+        const SlotRef ref = rowSlot(S, k, lane);
+        double coefficient = 0;
+        st.n = st.nb = 0;
+        if (ref.kind == 1) {
+            centerStressFaces(S, st, ref.idx, ref.axis, ref.level);
+            coefficient = centerStressWeight(S, ref.idx, ref.level);
+        } else if (ref.kind == 2) {
+            edgeStressFaces(S, st, ref.idx, ref.axis, ref.level);
+            coefficient = edgeStressWeight(S, ref.idx, ref.axis, ref.level);
+        }
+        if (ref.kind) {   // applyToMatrix (AV.cpp:2423-2435): scale by the coefficient of this row's own face
+            for (int i = 0; i < st.n; ++i)
+                if (st.idx[i] == vi) { coefficient *= st.coef[i]; break; }
+        }
+        // ---- merge in slot order
+        int n = 0, overflow = 0;
+        int32_t col0 = -1, col1 = -1;
+        double val0 = 0, val1 = 0, diag = 0, rhsI = 0;
+        unsigned todo = __ballot_sync(0xffffffffu, ref.kind != 0);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int ns = __shfl_sync(0xffffffffu, st.n, src), nbs = __shfl_sync(0xffffffffu, st.nb, src);
+            for (int i = 0; i < ns; ++i) {
+                const int32_t c = __shfl_sync(0xffffffffu, st.idx[i], src);
+                const double el = shflD(coefficient * st.coef[i], src);
+                if (c == vi) { diag += el; continue; }
+                const bool m0 = lane < n && col0 == c;
+                const unsigned b0 = __ballot_sync(0xffffffffu, m0);
+                if (b0) { if (m0) val0 += el; continue; }
+                if (n > 32) {
+                    const bool m1 = 32 + lane < n && col1 == c;
+                    const unsigned b1 = __ballot_sync(0xffffffffu, m1);
+                    if (b1) { if (m1) val1 += el; continue; }
+                }
+                if (n < MAX_ROW - 1) {   // the last slot is kept for the diagonal
+                    if ((n & 31) == lane) {
+                        if (n < 32) { col0 = c; val0 = el; }
+                        else { col1 = c; val1 = el; }
+                    }
+                    ++n;
+                } else overflow = 1;
+            }
+            for (int i = 0; i < nbs; ++i) rhsI -= shflD(coefficient * st.bnd[i], src);
+        }
+        // ---- velocity control volume (AV.cpp:2748-2772); the diagonal goes last and is unique
+        const int level = k.level, axis = k.axis;
+        const I3 face = mk3(k.i, k.j, k.k);
+        double fw;
+        if (level == 0) {
+            fw = (double)S.faceW[axis].raw(face[0], face[1], face[2]);
+            if (fw == 1.) fw = faceOctreeVolume(S, face, axis, level);
+        } else fw = faceOctreeVolume(S, face, axis, level);
+        if (!S.density.d) fw *= (double)S.density.constant;
+        else {
+            double p[3];
+            S.facePos(face, axis, level, p);
+            fw *= S.density.value(p);
+        }
+        const double dval = fw + diag;
+        if ((n & 31) == lane) {
+            if (n < 32) { col0 = vi; val0 = dval; }
+            else { col1 = vi; val1 = dval; }
+        }
+        ++n;
+        rhsI += fw * x0[gi];
+        if (lane < n) { stageCol[(long long)lane * stride + r] = col0; stageVal[(long long)lane * stride + r] = val0; }
+        if (32 + lane < n) { stageCol[(long long)(32 + lane) * stride + r] = col1; stageVal[(long long)(32 + lane) * stride + r] = val1; }
+        if (lane == 0) {
+            rowCount[r] = n;
+            rhs[r] = rhsI;
+            diagOut[r] = dval;
+            if (overflow) *overflowFlag = 1;
+        }
+    }
+}
+
 // canonical CSR from the staging area (lazy: only for read-back)
 __global__ void k_csr_from_stage(long long nLocal, long long stride, const int32_t *rowCount, const long long *ptr,
                                  const int32_t *stageCol, const double *stageVal, int32_t *col, double *val) {
@@ -488,6 +651,15 @@ int avs_stage_system(AvsContext *c, const AvsParams *p) {
         if (minb < 0) { const char *e = getenv("AVS_ASM_MINB"); minb = e ? atoi(e) : 8; }
         static int hashRow = -1;   // AVS_ASM_ROW=hash: experimental hashed row accumulator (avs_rowacc.cuh), not yet measured
         if (hashRow < 0) { const char *e = getenv("AVS_ASM_ROW"); hashRow = (e && e[0] == 'h') ? 1 : 0; }
+        static int warpAsm = -1;   // AVS_ASM=thread selects the one-thread-per-row kernel (A/B measurements)
+        if (warpAsm < 0) { const char *e = getenv("AVS_ASM"); warpAsm = (e && strcmp(e, "thread") == 0) ? 0 : 1; }
+        if (warpAsm && !hashRow) {
+            const long long wantBlocks = (nLocal + ASM_WARPS - 1) / ASM_WARPS;
+            const unsigned wblocks = (unsigned)std::min<long long>(wantBlocks, (long long)c->numSMs * 64);
+            k_assemble_warp<<<wblocks, ASM_WARPS * 32, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->x0.as<double>(), c->rowBegin, nLocal, stride,
+                                                                     c->rowCount.as<int32_t>(), c->stageCol.as<int32_t>(), c->stageVal.as<double>(),
+                                                                     c->rhs.as<double>(), c->diag.as<double>(), flag);
+        } else {
 #define ASM_LAUNCH(M)                                                                                                              \
     do {                                                                                                                           \
     if (hashRow)                                                                                                                   \
@@ -504,6 +676,7 @@ int avs_stage_system(AvsContext *c, const AvsParams *p) {
         else if (minb == 5) ASM_LAUNCH(5);
         else ASM_LAUNCH(4);
 #undef ASM_LAUNCH
+        }
         ++c->launches;
         int64_t nnz = 0;
         int rc = avs_exclusive_scan_i32_to_i64(c, c->rowCount.as<int32_t>(), c->csrPtr.as<int64_t>(), nLocal, &nnz);

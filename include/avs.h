@@ -164,6 +164,7 @@ typedef struct AvsContext AvsContext;
 
 /* life cycle */
 int avs_abi_version(void);
+int avs_device_count(void);            /* CUDA devices visible to the process (0 = none: every avs_create fails) */
 int avs_nccl_unique_id(void *out128);  /* rank 0: fill 128 bytes; the host broadcasts them to every rank */
 int avs_create(const AvsDeviceConfig *cfg, AvsContext **out);
 void avs_destroy(AvsContext *ctx);
@@ -220,10 +221,15 @@ int avs_get_keys(AvsContext *ctx, int32_t *keys);
 /* row_ptr/col/val/rhs cover the rows this rank owns (global column ids); x0 is the full restricted u^n [n_rows] */
 int avs_get_system_csr(AvsContext *ctx, int64_t *row_ptr, int32_t *col, double *val, double *rhs, double *x0);
 int avs_get_solution(AvsContext *ctx, double *x);   /* the rows this rank owns: [N*rank/nranks, N*(rank+1)/nranks) */
-/* kind: 0 cell labels (uint8 INACTIVE/ACTIVE/UP/DOWN), 1 face labels, 2 edge labels, 3 centre labels,
- * 4 regular-grid face labels (int32: >=0 DOF, -1 UNASSIGNED, -2 SOLIDBOUNDARY, -3 OUTSIDE; for kinds 2,3
- * active entries read 0), 5 centre weights (float32), 6 edge weights (float32).
- * Writes the grid resolution to res[3]; copies when `out` != NULL; returns bytes via *nbytes. */
+/* One grid of the resident state; valid after avs_build_octree (kind 0) / avs_assemble / avs_solve, else AVS_ERR_INVALID_ARGUMENT.
+ *   kind 0  cell labels of `level`                 uint8   INACTIVE 0 / ACTIVE 1 / UP 2 / DOWN 3
+ *   kind 1  octree face labels of (level, axis)    int32   >= 0 DOF row, -1 UNASSIGNED, -2 SOLIDBOUNDARY, -3 OUTSIDE
+ *   kind 2  edge-stress labels of (level, axis)    int8    0 active, -1 / -2 / -3 as above
+ *   kind 3  centre-stress labels of `level`        int8    0 active, -1 otherwise
+ *   kind 4  regular-grid face labels of `axis`     int8    0 solved face, -1 / -2 / -3 as above (level ignored)
+ *   kind 5  centre integration weights             float32 (level, axis ignored)
+ *   kind 6  edge integration weights of `axis`     float32 (level ignored)
+ * Writes the grid resolution to res[3] (x-fastest); copies to the HOST buffer `out` when non-NULL; returns bytes via *nbytes. */
 int avs_get_grid(AvsContext *ctx, int kind, int level, int axis, void *out, int32_t *res, int64_t *nbytes);
 
 /* Stand-alone linear algebra on a caller-supplied CSR matrix (host pointers, int64 row_ptr, int32 col):

@@ -26,7 +26,11 @@
 void initializeSIM(void *) { IMPLEMENT_DATAFACTORY(HDK_AdaptiveViscosity); }
 
 HDK_AdaptiveViscosity::HDK_AdaptiveViscosity(const SIM_DataFactory *factory) : BaseClass(factory) {}
-HDK_AdaptiveViscosity::~HDK_AdaptiveViscosity() { if (myContext) avs_destroy(myContext); }
+HDK_AdaptiveViscosity::~HDK_AdaptiveViscosity()
+{
+    if (myMulti) avs_destroy_multi(myMulti);      // owns its rank contexts
+    else if (myContext) avs_destroy(myContext);
+}
 
 // The parameter surface of the reference (HDK_AdaptiveViscosity.cpp:36-116): names, labels and defaults are kept so existing
 // scenes bind; "cudaDevice" and "singlePrecision" are new (the reference selects precision at compile time, USESINGLEPRECISION).
@@ -65,6 +69,7 @@ const SIM_DopDescription *HDK_AdaptiveViscosity::getDopDescription()
     static PRM_Name octreeGeometryName("octreeGeometry", "Octree Geometry");
     static PRM_Default octreeGeometryDefault(0, "OctreeGeometry");
     static PRM_Name cudaDeviceName("cudaDevice", "CUDA Device");
+    static PRM_Name cudaDeviceCountName("cudaDeviceCount", "CUDA Device Count");
     static PRM_Name singlePrecisionName("singlePrecision", "Single Precision Solve");
 
     static PRM_Template templates[] = {
@@ -87,6 +92,7 @@ const SIM_DopDescription *HDK_AdaptiveViscosity::getDopDescription()
         PRM_Template(PRM_TOGGLE, 1, &onlyPrintOctreeName, PRMzeroDefaults),
         PRM_Template(PRM_STRING, 1, &octreeGeometryName, &octreeGeometryDefault),
         PRM_Template(PRM_INT, 1, &cudaDeviceName, PRMzeroDefaults),
+        PRM_Template(PRM_INT, 1, &cudaDeviceCountName, PRMoneDefaults),
         PRM_Template(PRM_TOGGLE, 1, &singlePrecisionName, PRMzeroDefaults),
         PRM_Template()};
 
@@ -98,18 +104,33 @@ const SIM_DopDescription *HDK_AdaptiveViscosity::getDopDescription()
 AvsContext *HDK_AdaptiveViscosity::context(SIM_Object *obj)
 {
     const int device = getCudaDevice();
-    if (myContext && myContextDevice == device) return myContext;
+    const int count = getCudaDeviceCount() > 1 ? getCudaDeviceCount() : 1;
+    if (myContext && myContextDevice == device && myContextCount == count) return myContext;
+    if (myMulti) { avs_destroy_multi(myMulti); myMulti = nullptr; myContext = nullptr; }
     if (myContext) { avs_destroy(myContext); myContext = nullptr; }
-    AvsDeviceConfig cfg{};
-    cfg.size = sizeof cfg;
-    cfg.device = device;
-    cfg.nranks = 1;
-    if (avs_create(&cfg, &myContext) != AVS_OK) {
+    int rc;
+    if (count > 1) {
+        // the cook thread owns all GPUs: one rank context per device, no NCCL, no second process (include/avs.h)
+        std::vector<int32_t> devices(count);
+        const int visible = avs_device_count();   // ordinals wrap when fewer GPUs are visible: ranks then share a GPU (tests)
+        for (int i = 0; i < count; ++i) devices[i] = visible > 0 ? (device + i) % visible : device + i;
+        rc = avs_create_multi(devices.data(), count, 0, &myMulti);
+        if (rc == AVS_OK) myContext = avs_multi_context(myMulti, 0);   // read-back (octree geometry) goes through rank 0
+    } else {
+        AvsDeviceConfig cfg{};
+        cfg.size = sizeof cfg;
+        cfg.device = device;
+        cfg.nranks = 1;
+        rc = avs_create(&cfg, &myContext);
+    }
+    if (rc != AVS_OK) {
         addError(obj, SIM_MESSAGE, avs_last_error(), UT_ERROR_ABORT);   // no GPU: fail loudly, there is no CPU path
         myContext = nullptr;
+        myMulti = nullptr;
         return nullptr;
     }
     myContextDevice = device;
+    myContextCount = count;
     return myContext;
 }
 
@@ -201,10 +222,11 @@ bool HDK_AdaptiveViscosity::solveGasSubclass(SIM_Engine &engine, SIM_Object *obj
     p.do_apply_solid_weights = getDoApplySolidWeights();
     p.extrapolation = getExtrapolation();
     p.precision = getSinglePrecision() ? AVS_PRECISION_F32 : AVS_PRECISION_F64;
-    static_assert(sizeof(int) == sizeof(int32_t), "UT_Interrupt flag is polled as int32");
+    // AvsParams.cancel stays NULL: UT_Interrupt has no asynchronous callback this shim could set a flag from, and a non-NULL
+    // pointer that nothing sets would only chunk the persistent CG kernel (256 iterations per launch) for no benefit.  A host
+    // that owns a watcher thread polling opInterrupt() can pass its flag here; AVS_ERR_CANCELLED then maps to a quiet return.
     UT_Interrupt *boss = UTgetInterrupt();
-    volatile int32_t cancel = 0;
-    p.cancel = &cancel;            // set from opInterrupt() by a UT_Interrupt callback in a full build; polled per CG chunk
+    p.cancel = nullptr;
 
     AvsResult r{};
     r.size = sizeof r;
@@ -223,7 +245,8 @@ bool HDK_AdaptiveViscosity::solveGasSubclass(SIM_Engine &engine, SIM_Object *obj
             out.vel[a] = outv[a].data();
         }
         UT_PerfMonAutoSolveEvent event(this, "Solve Linear System");
-        int rc = avs_solve(ctx, &in, &p, &out, &r);
+        int rc = myMulti ? avs_solve_multi(myMulti, &in, &p, &out, &r) : avs_solve(ctx, &in, &p, &out, &r);
+        if (rc == AVS_ERR_CANCELLED) return true;                                                        // user interrupt: quiet
         if (rc != AVS_OK) return fail(rc == AVS_ERR_CUDA ? avs_last_error() : avs_status_string(rc));   // AV.cpp:621-622
         for (int a = 0; a < 3; ++a)              // applyVelocitiesToRegularGrid (AV.cpp:696-706)
             velocityField->getField(a)->fieldNC()->extractFromFlattened(outv[a].data(), in.vel[a].res[0],

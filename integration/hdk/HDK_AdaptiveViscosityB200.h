@@ -14,6 +14,7 @@
 #include <GAS/GAS_Utils.h>
 
 struct AvsContext;
+struct AvsMulti;
 
 class GAS_API HDK_AdaptiveViscosity : public GAS_SubSolver
 {
@@ -31,7 +32,8 @@ public:
     GET_DATA_FUNC_B("onlyPrintOctree", OnlyPrintOctree);             // AV.h:40  -> avs_build_octree
     GET_DATA_FUNC_F("extrapolation", Extrapolation);                 // AV.h:41  -> extrapolation
     // additions of this build
-    GET_DATA_FUNC_I("cudaDevice", CudaDevice);
+    GET_DATA_FUNC_I("cudaDevice", CudaDevice);                       // first CUDA device ordinal
+    GET_DATA_FUNC_I("cudaDeviceCount", CudaDeviceCount);             // > 1: row-partition the solve over that many consecutive GPUs
     GET_DATA_FUNC_B("singlePrecision", SinglePrecision);
 
 protected:
@@ -45,7 +47,8 @@ private:
     AvsContext *context(SIM_Object *obj);
 
     AvsContext *myContext = nullptr;   // device buffers are cached across cooks (the reference reallocates per call)
-    int myContextDevice = -1;
+    AvsMulti *myMulti = nullptr;       // cudaDeviceCount > 1: one rank context per GPU, all driven from this cook thread
+    int myContextDevice = -1, myContextCount = 0;
 
     DECLARE_STANDARD_GETCASTTOTYPE();
     DECLARE_DATAFACTORY(HDK_AdaptiveViscosity, GAS_SubSolver, "HDK Adaptive Viscosity", getDopDescription());

@@ -40,7 +40,34 @@ def build(force: bool = False) -> Path | None:
     return _LIB_PATH
 
 
+_SHIM_PATH = _HERE / "_ref" / "libavs_shim.so"
+
+
+def build_shim(force: bool = False) -> Path:
+    """oracle/_ref/libavs_shim.so: THIS repository's Houdini-side shim (integration/hdk/HDK_AdaptiveViscosityB200.cpp) compiled
+    against the same stand-ins and linked to libavs_b200.so -- needs no reference source, only g++ and the built CUDA library."""
+    if _SHIM_PATH.exists() and not force:
+        return _SHIM_PATH
+    r = subprocess.run(["make", "-C", str(_HERE), "shim"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle/_ref shim build failed:\n" + r.stdout[-3000:] + r.stderr[-3000:])
+    return _SHIM_PATH
+
+
 _lib = None
+_shim = None
+
+
+def _bind(L):
+    _bind_signatures(L)
+    return L
+
+
+def shim_lib():
+    global _shim
+    if _shim is None:
+        _shim = _bind(C.CDLL(str(build_shim())))
+    return _shim
 
 
 def lib():
@@ -48,38 +75,40 @@ def lib():
     if _lib is None:
         if build() is None:
             raise RuntimeError("oracle/_ref/libavs_ref.so is missing and /root/reference is not available to build it")
-        L = C.CDLL(str(_LIB_PATH))
-        L.ref_create.restype = C.c_void_p
-        L.ref_create.argtypes = [C.POINTER(_Scene), C.POINTER(_Params)]
-        L.ref_destroy.argtypes = [C.c_void_p]
-        L.ref_run.argtypes = [C.c_void_p]
-        L.ref_set_threads.argtypes = [C.c_int]
-        L.ref_set_weight_shortcut.argtypes = [C.c_int]
-        L.ref_error_count.argtypes = [C.c_void_p]
-        L.ref_error_text.restype = C.c_char_p
-        L.ref_error_text.argtypes = [C.c_void_p, C.c_int]
-        L.ref_extra_info.restype = C.c_char_p
-        L.ref_extra_info.argtypes = [C.c_void_p]
-        L.ref_levels.argtypes = [C.c_void_p]
-        L.ref_count.restype = C.c_int64
-        L.ref_count.argtypes = [C.c_void_p, C.c_int]
-        L.ref_error.restype = C.c_double
-        L.ref_error.argtypes = [C.c_void_p]
-        L.ref_get_float.restype = C.c_int64
-        L.ref_get_float.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
-        L.ref_get_labels.restype = C.c_int64
-        L.ref_get_labels.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
-        L.ref_get_index_grid.restype = C.c_int64
-        L.ref_get_index_grid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
-        L.ref_get_face_keys.argtypes = [C.c_void_p, C.c_void_p]
-        L.ref_get_vector.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
-        L.ref_get_csr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-        L.ref_get_out_velocity.restype = C.c_int64
-        L.ref_get_out_velocity.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
-        L.ref_get_octree_points.restype = C.c_int64
-        L.ref_get_octree_points.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-        _lib = L
+        _lib = _bind(C.CDLL(str(_LIB_PATH)))
     return _lib
+
+
+def _bind_signatures(L):
+    L.ref_create.restype = C.c_void_p
+    L.ref_create.argtypes = [C.POINTER(_Scene), C.POINTER(_Params)]
+    L.ref_destroy.argtypes = [C.c_void_p]
+    L.ref_run.argtypes = [C.c_void_p]
+    L.ref_set_threads.argtypes = [C.c_int]
+    L.ref_set_weight_shortcut.argtypes = [C.c_int]
+    L.ref_error_count.argtypes = [C.c_void_p]
+    L.ref_error_text.restype = C.c_char_p
+    L.ref_error_text.argtypes = [C.c_void_p, C.c_int]
+    L.ref_extra_info.restype = C.c_char_p
+    L.ref_extra_info.argtypes = [C.c_void_p]
+    L.ref_levels.argtypes = [C.c_void_p]
+    L.ref_count.restype = C.c_int64
+    L.ref_count.argtypes = [C.c_void_p, C.c_int]
+    L.ref_error.restype = C.c_double
+    L.ref_error.argtypes = [C.c_void_p]
+    L.ref_get_float.restype = C.c_int64
+    L.ref_get_float.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    L.ref_get_labels.restype = C.c_int64
+    L.ref_get_labels.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    L.ref_get_index_grid.restype = C.c_int64
+    L.ref_get_index_grid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    L.ref_get_face_keys.argtypes = [C.c_void_p, C.c_void_p]
+    L.ref_get_vector.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.ref_get_csr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ref_get_out_velocity.restype = C.c_int64
+    L.ref_get_out_velocity.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    L.ref_get_octree_points.restype = C.c_int64
+    L.ref_get_octree_points.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 
 
 def set_threads(n: int) -> None:
@@ -91,16 +120,22 @@ class RefRun:
     """One call of the reference's HDK_AdaptiveViscosity::solveGasSubclass (HDK_AdaptiveViscosity.cpp:126-707) on the stand-in
     fields; exposes what the reference computed on the way."""
 
+    def _library(self):
+        return lib()
+
+    _precision_word = 0
+
     def __init__(self, scene, params: OracleParams | None = None, octree_only: bool = False, weight_shortcut: bool = True):
         params = params or OracleParams()
-        if params.single_precision:
+        if params.single_precision and self._precision_word == 0:
             raise ValueError("libavs_ref.so is built without USESINGLEPRECISION")
-        self._L = lib()
+        self._L = self._library()
         keep = []
         sc = _scene_struct(scene, keep)
         p = _Params(params.dt, params.tolerance, params.extrapolation, params.max_iterations,
                     params.number_super_samples, params.octree_levels, params.fine_bandwidth,
-                    int(params.use_enhanced_gradients), int(params.do_apply_solid_weights), 0, 3 if octree_only else 0)
+                    int(params.use_enhanced_gradients), int(params.do_apply_solid_weights),
+                    self._precision_word | int(params.single_precision), 3 if octree_only else 0)
         self._L.ref_set_weight_shortcut(int(weight_shortcut))
         self._h = self._L.ref_create(C.byref(sc), C.byref(p))
         del keep
@@ -208,3 +243,26 @@ class RefRun:
         import scipy.sparse as sp
         ptr, col, val = self.csr()
         return sp.csr_matrix((val, col, ptr), shape=(self.n_face, self.n_face))
+
+
+class ShimRun(RefRun):
+    """The same harness around THIS repository's Houdini-side shim (integration/hdk/HDK_AdaptiveViscosityB200.cpp): the stand-in
+    "Houdini" calls the shim's solveGasSubclass, the shim flattens the fields and calls avs_solve / avs_solve_multi in
+    libavs_b200.so, and writes the velocity back -- the drop-in boundary end to end.  Needs a GPU.  Only what the DOP itself
+    exposes is available afterwards: ``out_velocity``, ``octree_points``, ``errors``, ``extra_info`` (the PerfMon string)."""
+
+    def __init__(self, scene, params: OracleParams | None = None, octree_only: bool = False, gpus: int = 1):
+        self._precision_word = (int(gpus) if gpus > 1 else 0) << 8
+        super().__init__(scene, params, octree_only)
+
+    def _library(self):
+        return shim_lib()
+
+    def info(self) -> dict:
+        """iterations / error / DOF counts parsed from the PerfMon extra-info string (AV.cpp:645-652)."""
+        out = {}
+        for part in self.extra_info.split(","):
+            if "=" in part:
+                k, v = part.strip().split("=")
+                out[k.strip()] = float(v)
+        return out

@@ -434,6 +434,18 @@ public:
         return true;
     }
     void collapseAllTiles() { for (auto &t : myTiles) t.tryCompress(); }
+    // flat copies: element (x, y, z) at x * xstride + y * ystride + z * zstride
+    void flatten(T *flat, exint xstride, exint ystride, exint zstride) const {
+        for (int z = 0; z < myRes[2]; ++z)
+            for (int y = 0; y < myRes[1]; ++y)
+                for (int x = 0; x < myRes[0]; ++x) flat[x * xstride + y * ystride + z * zstride] = getValue(x, y, z);
+    }
+    void extractFromFlattened(const T *flat, exint ystride, exint zstride) {
+        for (int z = 0; z < myRes[2]; ++z)
+            for (int y = 0; y < myRes[1]; ++y)
+                for (int x = 0; x < myRes[0]; ++x) setValue(x, y, z, flat[x + y * ystride + z * zstride]);
+        collapseAllTiles();
+    }
 };
 
 template <class T>
@@ -814,6 +826,8 @@ public:
         return true;
     }
     UT_Vector3 getVoxelSize() const { return myFields[0].getVoxelSize(); }
+    int myModifications = 0;
+    void pubHandleModification() { ++myModifications; }
 };
 
 // ---- GU / GA -------------------------------------------------------------------------------------
@@ -821,6 +835,7 @@ typedef exint GA_Offset;
 enum GA_AttributeOwner { GA_ATTRIB_VERTEX, GA_ATTRIB_POINT, GA_ATTRIB_PRIMITIVE, GA_ATTRIB_GLOBAL };
 struct GA_Defaults { double v; explicit GA_Defaults(double x) : v(x) {} };
 class GU_Detail;
+struct GA_Attribute { GU_Detail *detail; std::string name; };
 struct GA_AttributeSet { void bumpAllDataIds(GA_AttributeOwner) {} };
 class GU_Detail {
 public:
@@ -829,13 +844,24 @@ public:
     std::map<std::string, std::vector<exint>> myInt;
     GA_AttributeSet myAttribs;
     void clear() { myPos.clear(); myFloat.clear(); myInt.clear(); }
-    void addFloatTuple(GA_AttributeOwner, const char *name, int, const GA_Defaults &) { myFloat[name]; }
-    void addIntTuple(GA_AttributeOwner, const char *name, int, const GA_Defaults &) { myInt[name]; }
-    GA_Offset appendPoint() {
-        myPos.emplace_back();
-        for (auto &kv : myFloat) kv.second.push_back(0);
-        for (auto &kv : myInt) kv.second.push_back(-1);
-        return (GA_Offset)myPos.size() - 1;
+    std::vector<std::unique_ptr<GA_Attribute>> myAttribObjects;
+    GA_Attribute *addFloatTuple(GA_AttributeOwner, const char *name, int, const GA_Defaults &) {
+        myFloat[name].resize(myPos.size(), 0);
+        myAttribObjects.emplace_back(new GA_Attribute{this, name});
+        return myAttribObjects.back().get();
+    }
+    GA_Attribute *addIntTuple(GA_AttributeOwner, const char *name, int, const GA_Defaults &) {
+        myInt[name].resize(myPos.size(), -1);
+        myAttribObjects.emplace_back(new GA_Attribute{this, name});
+        return myAttribObjects.back().get();
+    }
+    GA_Offset appendPoint() { return appendPointBlock(1); }
+    GA_Offset appendPointBlock(exint n) {
+        const GA_Offset first = (GA_Offset)myPos.size();
+        myPos.resize(myPos.size() + (size_t)n);
+        for (auto &kv : myFloat) kv.second.resize(myPos.size(), 0);
+        for (auto &kv : myInt) kv.second.resize(myPos.size(), -1);
+        return first;
     }
     void setPos3(GA_Offset o, const UT_Vector3 &p) { myPos[(size_t)o] = p; }
     GA_AttributeSet &getAttributes() { return myAttribs; }
@@ -847,6 +873,7 @@ class GA_RWHandleF {
 public:
     GA_RWHandleF() {}
     GA_RWHandleF(GU_Detail *gd, GA_AttributeOwner, const char *n) : g(gd), name(n) {}
+    GA_RWHandleF(GA_Attribute *a) : g(a ? a->detail : nullptr), name(a ? a->name : "") {}
     bool isValid() const { return g && g->myFloat.count(name); }
     void bumpDataId() {}
     void set(GA_Offset o, double v) { g->myFloat[name][(size_t)o] = v; }
@@ -858,6 +885,7 @@ class GA_RWHandleI {
 public:
     GA_RWHandleI() {}
     GA_RWHandleI(GU_Detail *gd, GA_AttributeOwner, const char *n) : g(gd), name(n) {}
+    GA_RWHandleI(GA_Attribute *a) : g(a ? a->detail : nullptr), name(a ? a->name : "") {}
     bool isValid() const { return g && g->myInt.count(name); }
     void bumpDataId() {}
     void set(GA_Offset o, exint v) { g->myInt[name][(size_t)o] = v; }
@@ -885,7 +913,7 @@ public:
     std::vector<std::string> errors;
 };
 enum { SIM_MESSAGE = 0 };
-enum { UT_ERROR_WARNING = 1 };
+enum { UT_ERROR_WARNING = 1, UT_ERROR_ABORT = 2 };
 #define SIM_NAME_TOLERANCE "tolerance"
 #define GAS_NAME_SURFACE "surface"
 #define GAS_NAME_VELOCITY "velocity"

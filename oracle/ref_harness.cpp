@@ -19,7 +19,14 @@
 #include <string>
 #include <vector>
 
+// With -DAVS_SHIM_HARNESS the same harness drives integration/hdk/HDK_AdaptiveViscosityB200.cpp instead -- the Houdini-side shim
+// of THIS repository (same class name, same DOP surface), which hands the solve to libavs_b200.so: the drop-in, run end to end
+// on the stand-in fields (oracle/_ref/libavs_shim.so; needs a GPU at run time).
+#ifdef AVS_SHIM_HARNESS
+#include "HDK_AdaptiveViscosityB200.h"
+#else
 #include "HDK_AdaptiveViscosity.h"
+#endif
 
 namespace {
 
@@ -156,6 +163,9 @@ void *ref_create(const OrcScene *s, const OrcParams *p) {
     r->options["doApplySolidWeights"] = p->doApplySolidWeights;
     r->options["extrapolation"] = p->extrapolation;
     r->options["doPrintOctree"] = 1;
+    r->options["cudaDevice"] = 0;
+    r->options["cudaDeviceCount"] = p->singlePrecision >> 8;        // shim harness: bits 8.. of the precision word = GPU count
+    r->options["singlePrecision"] = p->singlePrecision & 1;
     r->options["onlyPrintOctree"] = (p->stopAfterStage > 0 && p->stopAfterStage <= 3) ? 1 : 0;
     r->dt = p->dt;
     return r;
@@ -229,6 +239,7 @@ int ref_run(void *h) {
         if (std::strcmp(label, "Build Octree Velocity and Stress Labels") == 0) snapshotFields(r);
     };
     mock_hdk::hooks().extraInfo = [r](const char *info) { r->extraInfo = info; };
+#ifndef AVS_SHIM_HARNESS
     mock_eigen::hooks().beforeSolve = [r](const Eigen::SparseMatrix<double> &A, const Eigen::VectorXd &b, const Eigen::VectorXd &g) {
         r->rowPtr = A.ptr; r->colIdx = A.col; r->val = A.val;
         r->rhs.assign(b.data(), b.data() + b.size());
@@ -239,6 +250,7 @@ int ref_run(void *h) {
         r->iterations = it;
         r->error = err;
     };
+#endif
     HDK_AdaptiveViscosity *solver = HDK_AdaptiveViscosity::mockCreate();
     solver->myOptions = r->options;
     GAS_SubSolver *base = solver;
@@ -246,7 +258,9 @@ int ref_run(void *h) {
     r->ok = base->solveGasSubclass(engine, &r->obj, 0.0, r->dt);
     delete base;   // through the (public, virtual) base destructor
     mock_hdk::hooks() = mock_hdk::Hooks();
+#ifndef AVS_SHIM_HARNESS
     mock_eigen::hooks() = mock_eigen::Hooks();
+#endif
     for (int a = 0; a < 3; ++a) copyGrid(r->vel.myFields[a], r->outVel[a], false);
     auto it = r->obj.geometry.find("octreeGeometry");
     if (it != r->obj.geometry.end()) {

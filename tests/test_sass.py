@@ -1,0 +1,57 @@
+"""Build-time checks on the generated code (cuobjdump -sass of libavs_b200.so; no GPU needed).
+
+The SpMV phase of the persistent CG kernel once ran 14 % slower after an unrelated edit: the two p-buffer pointers were kernel
+parameters in an ARRAY selected by the iteration parity, and ptxas re-issued the register-indexed constant-bank load that picks the
+pointer (``LDC c[0x0][R..]``) inside the slice loop, in front of every gather of p.  The pointer is now computed arithmetically and
+pinned in a register; this test keeps that class of regression out of the hot kernels."""
+import re
+import shutil
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+LIB = ROOT / "adaptiveviscositysolver_b200" / "libavs_b200.so"
+CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+
+
+@pytest.fixture(scope="module")
+def sass():
+    import __graft_entry__ as g
+    g.build()
+    if not Path(CUOBJDUMP).exists():
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([CUOBJDUMP, "-sass", str(LIB)], capture_output=True, text=True, check=True).stdout
+    funcs, name = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            funcs[name] = []
+        elif name:
+            funcs[name].append(line)
+    return funcs
+
+
+def test_hot_kernels_have_no_register_indexed_constant_loads(sass):
+    hot = [n for n in sass if "k_cg_persistent" in n or "k_spmv_sjds" in n]
+    assert len(hot) >= 8
+    for n in hot:
+        bad = [l for l in sass[n] if re.search(r"c\[0x0\]\[R", l)]
+        assert not bad, (n, bad[:3])
+
+
+def test_hot_kernels_do_not_spill_in_the_default_configuration(sass):
+    """fp64 and fp32 instantiations of the default persistent kernel (slice loop mode 0, 4 CTAs per SM) and of the stand-alone SpMV."""
+    for n, body in sass.items():
+        if ("k_cg_persistent2I" in n and "Li0ELi4E" in n) or ("k_spmv_sjdsI" in n and "ELi4EE" in n):
+            spills = [l for l in body if re.search(r"\b(LDL|STL)\b", l)]
+            assert len(spills) <= 4, (n, len(spills))
+
+
+def test_ring_variant_uses_async_copies_and_tma_variant_bulk_copies(sass):
+    ring = [n for n in sass if "k_spmv_sjds_ring" in n]
+    assert ring and all(any("LDGSTS" in l for l in sass[n]) for n in ring)
+    tma = [n for n in sass if "k_spmv_tma" in n]
+    assert tma and all(any("UBLKCP" in l for l in sass[n]) for n in tma)
