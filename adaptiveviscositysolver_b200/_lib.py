@@ -18,7 +18,7 @@ STAGE_NAMES = ["upload", "surface_weights", "octree", "regular_labels", "octree_
                "system", "solve", "apply", "download", "total", "_"]
 
 EXPORTS = [
-    "avs_abi_version", "avs_device_count", "avs_nccl_unique_id", "avs_get_local_range", "avs_get_row_starts", "avs_create", "avs_destroy", "avs_status_string", "avs_last_error", "avs_default_params",
+    "avs_abi_version", "avs_device_count", "avs_nccl_unique_id", "avs_get_local_range", "avs_get_row_starts", "avs_get_output_slab", "avs_create", "avs_destroy", "avs_status_string", "avs_last_error", "avs_default_params",
     "avs_solve", "avs_assemble", "avs_solve_resident", "avs_apply", "avs_get_sizes", "avs_get_keys",
     "avs_get_system_csr", "avs_get_solution", "avs_get_grid", "avs_cg_csr", "avs_spmv_csr", "avs_time_spmv_resident",
     "avs_build_octree", "avs_get_octree_points",
@@ -63,7 +63,7 @@ class AvsResult(C.Structure):
 
 class AvsDeviceConfig(C.Structure):
     _fields_ = [("size", C.c_uint32), ("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32),
-                ("nccl_unique_id", C.c_void_p), ("stream", C.c_void_p), ("time_spmv", C.c_int32)]
+                ("nccl_unique_id", C.c_void_p), ("stream", C.c_void_p), ("time_spmv", C.c_int32), ("distributed_output", C.c_int32)]
 
 
 class AvsError(RuntimeError):
@@ -103,6 +103,7 @@ def load():
     L.avs_get_local_range.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.avs_nccl_unique_id.argtypes = [vp]
     L.avs_get_row_starts.argtypes = [vp, vp]
+    L.avs_get_output_slab.argtypes = [vp, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.avs_get_system_csr.argtypes = [vp, vp, vp, vp, vp, vp]
     L.avs_get_solution.argtypes = [vp, vp]
     L.avs_get_grid.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]

@@ -101,6 +101,7 @@ static int createImpl(const AvsDeviceConfig *cfg, void *localGroup, int deviceSh
         c->rank = cfg->rank;
         c->nranks = std::max(1, cfg->nranks);
         c->timeSpmv = cfg->time_spmv != 0;
+        c->slabOutputOnly = cfg->distributed_output != 0 && cfg->nranks > 1;
         c->stream = (cudaStream_t)cfg->stream;
     }
     c->localGroup = localGroup;
@@ -535,6 +536,15 @@ int avs_get_local_range(AvsContext *c, int64_t *b, int64_t *e) {
     if (!c) return AVS_ERR_INVALID_ARGUMENT;
     if (b) *b = c->rowBegin;
     if (e) *e = c->rowEnd;
+    return AVS_OK;
+}
+
+int avs_get_output_slab(AvsContext *c, int axis, int32_t *z0, int32_t *z1) {
+    if (!c || axis < 0 || axis > 2 || !z0 || !z1 || !c->haveSystem) return AVS_ERR_INVALID_ARGUMENT;
+    int a = 0, b = 0;
+    avs_slab_range(c, axis, c->rank, &a, &b);
+    *z0 = a;
+    *z1 = b;
     return AVS_OK;
 }
 

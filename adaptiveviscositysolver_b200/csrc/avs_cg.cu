@@ -1281,7 +1281,9 @@ struct Pcg2Args {
     T *x, *r, *t;
     T *p0;               // p buffer 0 (owned rows, then halo slots); buffer 1 = p0 + pDelta bytes.  Iteration k of a launch reads
     long long pDelta;    // buffer (parity0 + k) & 1.  Two pointers in an ARRAY would be selected with a register-indexed constant-bank
-                         // load that ptxas re-issues inside the SpMV loop in front of every gather (measured: +14 % SpMV time)
+                         // load that ptxas re-issues inside the SpMV loop in front of every gather (measured: +14 % SpMV time).
+                         // Nor may the pointer be laundered through inline asm: the gathers then become GENERIC loads (LD.E instead
+                         // of LDG.E), the same 14 %.  tests/test_sass.py checks both.
     double *parts;       // 3 * gridDim.x
     CgScalars *sc;
     Pcg2State *st;
@@ -1404,7 +1406,6 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) k_cg_persistent2(const __gri
     while (iters < A.itLimit) {
         const int cur = (A.parity0 + k) & 1;
         T *pc = (T *)((char *)A.p0 + (cur ? A.pDelta : 0)), *pn = (T *)((char *)A.p0 + (cur ? 0 : A.pDelta));
-        asm volatile("" : "+l"(pc), "+l"(pn));   // pin both in registers for the whole iteration (no rematerialisation inside the slice loop)
         if (timer) tm[0] = globalTimerNs();
         // ---- t = A p, partial p.t: slices that read no halo slot first, the boundary slices after the peers' values have landed
         double pt[1];
@@ -1550,13 +1551,16 @@ static bool cgUsePersistent() {
 }
 // AVS_PCG_KERNEL=v1 selects round 1's persistent kernel (three grid barriers + separate all-reduce and halo push per iteration;
 // kept for A/B measurements); the default is k_cg_persistent2.  AVS_PCG_MINB=5 (v1 only): register allocation for 5 CTAs per SM.
-static int pcgVersion() {
-    static int v = -1;
-    if (v < 0) {
+// Default: k_cg_persistent2 when the solve is row-partitioned over several ranks (its merged synchronisation points are what
+// multi-GPU needs), round 1's k_cg_persistent on a single GPU (same speed at 10 M rows, 5-9 % faster on 0.2-1 M rows where the
+// per-iteration synchronisation dominates: C2 18.8 vs 20.6 ms, C5 264 vs 278 ms).  AVS_PCG_KERNEL=v1 / v2 forces one.
+static int pcgVersion(bool dist) {
+    static int forced = -1;
+    if (forced < 0) {
         const char *e = getenv("AVS_PCG_KERNEL");
-        v = (e && strcmp(e, "v1") == 0) ? 1 : 2;
+        forced = (e && strcmp(e, "v1") == 0) ? 1 : (e && strcmp(e, "v2") == 0) ? 2 : 0;
     }
-    return v;
+    return forced ? forced : (dist ? 2 : 1);
 }
 template <class T, class T2>
 static const void *pcgKernel() {
@@ -1711,7 +1715,7 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
         int perSM = 0;
         size_t smem2 = 0;
         const void *k2 = pcg2Kernel<T, T2>(&smem2);
-        cudaError_t e = pcgVersion() == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k2, CG_THREADS, smem2)
+        cudaError_t e = pcgVersion(dist) == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k2, CG_THREADS, smem2)
                                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, pcgKernel<T, T2>(), CG_THREADS, 0);
         if (e != cudaSuccess || perSM < 1) { cudaGetLastError(); perSM = 1; }
         const char *env = getenv("AVS_PCG_CTAS_PER_SM");
@@ -1775,7 +1779,7 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
     CgScalars *hs = (CgScalars *)c->hostScalars;  // pinned
     PcgDist pd;
     const bool persistent = cgUsePersistent() && (!dist || avs_dist_pcg_args(c, &pd));
-    if (persistent && pcgVersion() == 2 && c->nranks <= 8) {   // the mailbox exchange of syncSum fits the peers' words into one warp
+    if (persistent && pcgVersion(dist) == 2 && c->nranks <= 8) {   // the mailbox exchange of syncSum fits the peers' words into one warp
         // ---- k_cg_persistent2: one cooperative launch per `check_every` iterations (default: all of them) ----------------
         if (w.pcgState.reserve(sizeof(Pcg2State) + 64)) return AVS_ERR_ALLOC;
         Pcg2State *st = w.pcgState.as<Pcg2State>();

@@ -40,9 +40,10 @@ static_assert(sizeof(DeviceScene) <= 4000, "DeviceScene must fit the kernel para
 
 // Grid kernels are launched as (ceil(nx/128), ceil(ny/CELL_YB), nz) x (128, CELL_YB) threads: x and y from the thread index,
 // z from the block index -- no 64-bit div/mod per thread (that cost more than the memory traffic of these streaming passes).
-// One 128-thread CTA per grid row made a 512^3 sweep one million CTAs: every such kernel sat on the same 0.54 ms floor (the
-// CTA launch rate, ~150 cycles per CTA and SM) whatever it read or wrote; four rows per CTA lift the floor.
-#define CELL_YB 4
+// CELL_YB = grid rows per CTA.  Measured at C3 (512^3) with 4 rows per CTA (128 x 4 threads): the trivial streaming passes gain
+// ~10 % (weights 5.70 -> 5.15 ms, octree 2.56 -> 2.19), but the gather-heavy classification passes lose more (octree labels
+// 9.07 -> 10.79 ms): one row per CTA stays.
+#define CELL_YB 1
 #define LAUNCH_3D(ctx, kernel, n3, ...)                                                        \
     do {                                                                                       \
         if ((n3)[0] > 0 && (n3)[1] > 0 && (n3)[2] > 0) {                                        \

@@ -303,7 +303,7 @@ __global__ void k_apply_regular(const __grid_constant__ DeviceScene S, const Nod
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(interpolated, (unsigned long long)__popc(m));
 }
 
-#define NODE_YB 4   // grid rows per CTA (128 x 4 threads): one row per CTA is bound by the CTA launch rate on 512^3 grids
+#define NODE_YB 1   // grid rows per CTA; 4 (128 x 4 threads) measured slower for the node pyramid at C3 (apply 22.3 -> 24.4 ms)
 static dim3 grid3(const int n[3]) { return dim3((unsigned)((n[0] + 127) / 128), (unsigned)((n[1] + NODE_YB - 1) / NODE_YB), (unsigned)n[2]); }
 
 int avs_apply_regular(AvsContext *c, float *dOut[3], unsigned long long *hostInterpolated, float *const *hostOut) {
@@ -381,8 +381,9 @@ int avs_apply_regular(AvsContext *c, float *dOut[3], unsigned long long *hostInt
     if (c->nranks > 1) {
         int rcd = avs_dist_allreduce_u64(c, cnt, 1);
         if (rcd) return rcd;
-        // in-process group with host output: every rank downloads its own slab into the caller's arrays instead (avs_api.cu)
-        if (!(c->slabOutputOnly && c->outputIsHost) && (rcd = avs_dist_allgather_slabs(c, dOut))) return rcd;
+        // distributed output (AvsDeviceConfig.distributed_output, always on for avs_create_multi): every rank keeps / downloads
+        // the slab it computed; otherwise the slabs are all-gathered so that every rank holds the whole field
+        if (!c->slabOutputOnly && (rcd = avs_dist_allgather_slabs(c, dOut))) return rcd;
     }
     AVS_CUDA_CHECK(cudaMemcpyAsync(hostInterpolated, cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));  // also keeps the stack copy of NS alive until the H2D copy is done

@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(128, MINB) k_assemble(const __grid_constant__ 
     diagOut[r] = row.val[row.n - 1];  // buildRow adds the diagonal last and it is unique (AV.cpp:2768)
 }
 
-// ---- warp-cooperative assembly (default) ----------------------------------------------------------------------------------------
+// ---- warp-cooperative assembly (experiment, AVS_ASM=warp; NOT the default: see avs_stage_system) ----------------------------------------------------------------------------------------
 // One WARP owns one matrix row.  A row is touched by at most 26 stresses, in the fixed order buildRow visits them: per side of the face
 // the cell-centred stress and up to 8 T-junction ghost edges (9 x 2 slots), then per transverse edge position the sibling (or first
 // child) edge and the edge itself (or second child) (2 x 4 slots).  Lane l decides whether slot l exists and evaluates ITS stencil --
@@ -651,8 +651,9 @@ int avs_stage_system(AvsContext *c, const AvsParams *p) {
         if (minb < 0) { const char *e = getenv("AVS_ASM_MINB"); minb = e ? atoi(e) : 8; }
         static int hashRow = -1;   // AVS_ASM_ROW=hash: experimental hashed row accumulator (avs_rowacc.cuh), not yet measured
         if (hashRow < 0) { const char *e = getenv("AVS_ASM_ROW"); hashRow = (e && e[0] == 'h') ? 1 : 0; }
-        static int warpAsm = -1;   // AVS_ASM=thread selects the one-thread-per-row kernel (A/B measurements)
-        if (warpAsm < 0) { const char *e = getenv("AVS_ASM"); warpAsm = (e && strcmp(e, "thread") == 0) ? 0 : 1; }
+        static int warpAsm = -1;   // AVS_ASM=warp selects the warp-per-row kernel (measured 4.6x SLOWER at C3: 140.7 vs 30.5 ms -- one row in
+                                   // flight per warp instead of 32, and its stencils still sit in local memory; kept for the record)
+        if (warpAsm < 0) { const char *e = getenv("AVS_ASM"); warpAsm = (e && strcmp(e, "warp") == 0) ? 1 : 0; }
         if (warpAsm && !hashRow) {
             const long long wantBlocks = (nLocal + ASM_WARPS - 1) / ASM_WARPS;
             const unsigned wblocks = (unsigned)std::min<long long>(wantBlocks, (long long)c->numSMs * 64);

@@ -158,7 +158,7 @@ class Solver:
     """One ``AvsContext``: a single-threaded solver bound to one GPU (include/avs.h)."""
 
     def __init__(self, device: int = 0, rank: int = 0, nranks: int = 1, time_spmv: bool = False, stream: int = 0,
-                 nccl_unique_id: Optional[bytes] = None):
+                 nccl_unique_id: Optional[bytes] = None, distributed_output: bool = False):
         self._L = _lib.load()
         cfg = AvsDeviceConfig()
         cfg.size = C.sizeof(AvsDeviceConfig)
@@ -173,6 +173,7 @@ class Solver:
             cfg.nccl_unique_id = None
         cfg.stream = stream or None
         cfg.time_spmv = int(time_spmv)
+        cfg.distributed_output = int(distributed_output)
         h = C.c_void_p()
         rc = self._L.avs_create(C.byref(cfg), C.byref(h))
         if rc != AVS_OK:
@@ -306,6 +307,12 @@ class Solver:
         self._check(self._L.avs_get_system_csr(self._h, ptr.ctypes.data, col.ctypes.data, val.ctypes.data,
                                                rhs.ctypes.data, x0.ctypes.data), "avs_get_system_csr")
         return ptr, col, val, rhs, x0
+
+    def output_slab(self, axis: int):
+        """z-planes [z0, z1) of velocity component ``axis`` this rank computes (and, with distributed output, fills)."""
+        z0, z1 = C.c_int32(), C.c_int32()
+        self._check(self._L.avs_get_output_slab(self._h, int(axis), C.byref(z0), C.byref(z1)), "avs_get_output_slab")
+        return z0.value, z1.value
 
     def solution(self) -> np.ndarray:
         b, e = self.local_range()

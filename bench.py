@@ -342,6 +342,7 @@ def main():
     ap.add_argument("--fp32", action="store_true", help="USESINGLEPRECISION solve (C3's ncu capture config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather-output", action="store_true", help="N > 1: all-gather the output z-slabs so that every rank holds the whole velocity field")
     ap.add_argument("--no-spmv-events", action="store_true", help="do not bracket SpMV launches with CUDA events (roofline from back-to-back timing)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
@@ -380,7 +381,10 @@ def main():
         box = [nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         uid = box[0]
-    solver = Solver(device=local, rank=rank, nranks=world, time_spmv=not args.no_spmv_events, nccl_unique_id=uid)
+    # N > 1: every rank keeps (device-resident steps) / downloads (e2e steps) the z-slab of the output it computed -- the row-partitioned
+    # solve leaves a slab-partitioned velocity field; --gather-output restores "whole field on every rank" (NVLink all-gather of 1.6 GB)
+    solver = Solver(device=local, rank=rank, nranks=world, time_spmv=not args.no_spmv_events, nccl_unique_id=uid,
+                    distributed_output=(world > 1 and not args.gather_output))
     if device_gen:
         from adaptiveviscositysolver_b200.scenes_torch import sphere_drop_device
         dscene = sphere_drop_device(w["n"], w["R"], dev)
@@ -449,8 +453,8 @@ def main():
     persistent = cg_launches > 0
     # DRAM traffic of one launch of the dominant kernel from the committed ncu --set full capture (same matrix only)
     traffic = None
-    tp = ROOT / "profiles" / ("r1_cg_persistent_traffic.json" if persistent else "r1_spmv_traffic.json")
-    if tp.exists() and world == 1 and not args.fp32:
+    tp = ROOT / "profiles" / (("r2_cg_persistent_fp32_traffic.json" if args.fp32 else "r1_cg_persistent_traffic.json") if persistent else "r1_spmv_traffic.json")
+    if tp.exists() and world == 1 and (persistent or not args.fp32):
         tj = json.loads(tp.read_text())
         if tj.get("N") == int(N) and tj.get("nnz") == int(nnz):
             traffic = tj["traffic_bytes_per_launch"]
@@ -502,6 +506,13 @@ def main():
             te = torch.tensor([e_ms], device=dev)
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
             e_ms = float(te.item())
+        if world > 1 and not args.gather_output:   # every rank downloads only the z-slab it computed: count what this rank moved
+            plane = [int(np.prod(v.data.shape[1:])) for v in scene.vel]
+            d2h = sum(plane[a] * max(0, solver.output_slab(a)[1] - solver.output_slab(a)[0]) * 4 for a in range(3))
+        if world > 1:   # whole-job bytes (every rank uploads the full fields: labelling is replicated)
+            tb = torch.tensor([float(h2d), float(d2h)], device=dev, dtype=torch.float64)
+            dist.all_reduce(tb)
+            h2d, d2h = (float(v) for v in tb.tolist())
         e2e = {"value": N * einfo.iterations / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": e_ms,
                "stage_ms": {k2: round(v, 3) for k2, v in einfo.stage_ms.items()}}
@@ -528,7 +539,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32" if args.fp32 else "f64", "data": "synthetic",
-            "config": {"workload": w["desc"], "N": int(N), "nnz": int(nnz_total), "rows_per_rank": int(n_local), "dist_mode": {0: "single", 1: "nccl", 2: "peer-memory"}[info.dist_mode], "halo_columns": int(info.halo_columns), "levels": int(info.levels), "iterations": int(iters),
+            "config": {"workload": w["desc"], "N": int(N), "nnz": int(nnz_total), "rows_per_rank": int(n_local), "dist_mode": {0: "single", 1: "nccl", 2: "peer-memory"}[info.dist_mode], "output": ("z-slab per rank" if (world > 1 and not args.gather_output) else "whole field"), "halo_columns": int(info.halo_columns), "levels": int(info.levels), "iterations": int(iters),
                        "rel_error": info.error, "tolerance": w["tol"], "regular_dofs": int(info.regular_dofs),
                        # `value` is the whole step (labelling + assembly + CG + write-back); the CG stage alone, for comparison
                        # with the reference arm's `config.cg_only` and this arm's `cpu_baseline` (both CG only):

@@ -158,6 +158,10 @@ typedef struct AvsDeviceConfig {
                                  NULL when nranks==1. The library creates its own communicator from it. */
     void *stream;             /* cudaStream_t to run on; NULL = the library creates its own */
     int32_t time_spmv;        /* 1: bracket every SpMV launch with CUDA events (bench only) */
+    int32_t distributed_output; /* nranks > 1 only.  0 (default): on return EVERY rank's output arrays hold the whole velocity field
+                                 (the z-slabs are all-gathered over NVLink).  1: a rank fills -- and, for host arrays, downloads --
+                                 only the z-slab of the regular grid it computed; the other planes keep what the caller put there.
+                                 The slabs of all ranks tile the grid (avs_get_output_slab). */
 } AvsDeviceConfig;
 
 typedef struct AvsContext AvsContext;
@@ -217,6 +221,8 @@ int avs_get_octree_points(AvsContext *ctx, int64_t *count, float *pos, float *ps
 int avs_get_sizes(AvsContext *ctx, int64_t *n_rows, int64_t *nnz, int32_t *levels);
 int avs_get_local_range(AvsContext *ctx, int64_t *row_begin, int64_t *row_end);  /* rows owned by this rank */
 int avs_get_row_starts(AvsContext *ctx, int64_t *starts /* [nranks+1] */);  /* first row of every rank's block */
+/* z-planes [z0, z1) of velocity component `axis` that this rank computes in stage 11 (the whole grid when nranks == 1) */
+int avs_get_output_slab(AvsContext *ctx, int axis, int32_t *z0, int32_t *z1);
 int avs_get_keys(AvsContext *ctx, int32_t *keys);
 /* row_ptr/col/val/rhs cover the rows this rank owns (global column ids); x0 is the full restricted u^n [n_rows] */
 int avs_get_system_csr(AvsContext *ctx, int64_t *row_ptr, int32_t *col, double *val, double *rhs, double *x0);

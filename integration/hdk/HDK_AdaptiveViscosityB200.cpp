@@ -137,11 +137,11 @@ AvsContext *HDK_AdaptiveViscosity::context(SIM_Object *obj)
 namespace {
 
 // SIM_RawField -> flat x-fastest float32 buffer + sample descriptor (include/avs.h: AvsField)
-AvsField flatten(const SIM_RawField &f, std::vector<float> &store)
+AvsField flatten(const SIM_RawField &f, std::vector<float> &store, bool allowConstant = true)
 {
     AvsField d{};
     fpreal32 c = 0;
-    if (f.field()->isConstant(&c)) {             // the reference's isConstant fast paths (AV.cpp:2090, 2248, 2501)
+    if (allowConstant && f.field()->isConstant(&c)) {   // the reference's isConstant fast paths (AV.cpp:2090, 2248, 2501)
         d.data = nullptr;
         d.constant = c;
         return d;
@@ -202,13 +202,12 @@ bool HDK_AdaptiveViscosity::solveGasSubclass(SIM_Engine &engine, SIM_Object *obj
     in.density = flatten(*densityField->getField(), store[2]);
     in.collision = flatten(*solidField->getField(), store[3]);
     for (int a = 0; a < 3; ++a) {
-        in.vel[a] = flatten(*velocityField->getField(a), store[4 + a]);
-        in.face_weights[a] = flatten(*faceWeightsField->getField(a), store[7 + a]);
+        // velocity and face weights always travel dense: Houdini may hold a component as constant tiles (a w = 0 drop), but the
+        // solver reads them per face and writes the velocity back in place
+        in.vel[a] = flatten(*velocityField->getField(a), store[4 + a], false);
+        in.face_weights[a] = flatten(*faceWeightsField->getField(a), store[7 + a], false);
         in.collision_vel[a] = flatten(*solidVelocityField->getField(a), store[10 + a]);
     }
-    // a constant velocity / weight component is still a dense field for the solver (it writes the velocity back)
-    for (int a = 0; a < 3; ++a)
-        if (!in.vel[a].data || !in.face_weights[a].data) return fail("Liquid velocity and face weights must be uncompressed fields");
 
     AvsParams p;
     avs_default_params(&p);

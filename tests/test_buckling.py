@@ -59,6 +59,38 @@ def test_folded_frame_system_properties():
         assert v @ (A @ v) > 0
 
 
+def test_ground_plane_on_a_grid_plane_is_sensitive_to_fp32_voxel_size():
+    """The DOP boundary (integration/hdk) carries the voxel size as fp32.  At dx = 0.002 -- not an fp32 number -- the
+    ground plane y = 0 of this scene lies exactly on a grid plane, the fp32 dx moves those faces 8e-10 off it, and the centre
+    sub-sample of their solid weights changes side: same DOFs, a different (equally valid) system.  At dx = 2^-9 fp32 and fp64
+    describe the same grid; tests/test_gpu_hdk_shim.py therefore runs the buckling frame at 2^-9."""
+    import copy
+    p = orc.OracleParams(octree_levels=4, tolerance=1e-10, dt=DT)
+
+    def as_fp32_grid(sc):
+        out = copy.deepcopy(sc)
+        dxf = float(np.float32(sc.dx))
+        out.dx = dxf
+        centre = [o + 0.5 * dxf for o in sc.origin]     # the stand-in's UT_Vector3 keeps the origin exact; dx is fp32
+        for f in (out.surface, out.viscosity, out.collision):
+            if f.data is not None:
+                f.dx, f.org = dxf, tuple(centre)
+        for a in range(3):
+            org = list(centre)
+            org[a] = sc.origin[a]
+            for f in (out.vel[a], out.face_weights[a]):
+                f.dx, f.org = dxf, tuple(org)
+        return out
+
+    sc = buckling_sheet(6, dx=0.002)
+    exact, f32 = orc.OracleRun(sc, p), orc.OracleRun(as_fp32_grid(sc), p)
+    assert exact.n_face == f32.n_face and exact.regular_dofs == f32.regular_dofs
+    assert abs(exact.iterations - f32.iterations) > exact.iterations // 10       # 1332 vs 925
+    sc = buckling_sheet(6, dx=2.0 ** -9)
+    exact, f32 = orc.OracleRun(sc, p), orc.OracleRun(as_fp32_grid(sc), p)
+    assert exact.iterations == f32.iterations and np.array_equal(exact.solution(), f32.solution())
+
+
 @pytest.fixture(scope="module")
 def solver():
     from adaptiveviscositysolver_b200.solver import Solver

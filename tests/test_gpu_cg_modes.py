@@ -95,17 +95,19 @@ def test_per_launch_cg_mode(tma):
     assert r.stdout.strip().startswith("ok")
 
 
-@pytest.mark.parametrize("variant", ["pf", "ring", "ring4", "v1"])
+@pytest.mark.parametrize("variant", ["v2", "v2_pf", "v2_ring", "v2_ring4", "v2_call", "v1"])
 def test_persistent_kernel_variants(variant):
-    """The slice loops selectable with AVS_SPMV_MODE (L2 prefetch; matrix stream staged through a per-warp cp.async ring) inside
-    the persistent CG kernel and in the stand-alone SpMV, and round 1's persistent kernel (AVS_PCG_KERNEL=v1)."""
+    """Both persistent CG kernels on one GPU (the default there is round 1's k_cg_persistent; k_cg_persistent2 is the multi-GPU
+    default and is forced here with AVS_PCG_KERNEL=v2), and the slice loops selectable with AVS_SPMV_MODE inside k_cg_persistent2
+    and in the stand-alone SpMV: L2 prefetch, matrix stream staged through a per-warp cp.async ring (two depths), slice loop as a
+    separate function."""
     env = dict(os.environ)
     env.pop("AVS_CG_MODE", None)
     env.pop("AVS_SPMV_TMA", None)
-    if variant == "v1":
-        env["AVS_PCG_KERNEL"] = "v1"
-    else:
-        env["AVS_SPMV_MODE"] = variant
+    env.pop("AVS_SPMV_MODE", None)
+    env["AVS_PCG_KERNEL"] = "v1" if variant == "v1" else "v2"
+    if "_" in variant:
+        env["AVS_SPMV_MODE"] = variant.split("_", 1)[1]
     r = subprocess.run([sys.executable, "-c", _WORKER % (str(ROOT), False)], capture_output=True, text=True, timeout=600, cwd=str(ROOT), env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.strip().startswith("ok")

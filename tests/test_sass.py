@@ -42,6 +42,17 @@ def test_hot_kernels_have_no_register_indexed_constant_loads(sass):
         assert not bad, (n, bad[:3])
 
 
+def test_persistent_cg_kernel_gathers_p_with_global_loads(sass):
+    """A pointer laundered through inline asm (or otherwise stripped of its address space) turns the gathers of p into generic
+    loads (LD.E): measured 0.518 instead of 0.464 ms per SpMV phase at C3."""
+    names = [n for n in sass if "k_cg_persistent2I" in n]
+    assert len(names) >= 6
+    for n in names:
+        generic = [l for l in sass[n] if re.search(r"\bLD\.E", l)]
+        assert not generic, (n, generic[:3])
+        assert any(re.search(r"\bLDG\.E\.(64|128)", l) for l in sass[n])
+
+
 def test_hot_kernels_do_not_spill_in_the_default_configuration(sass):
     """fp64 and fp32 instantiations of the default persistent kernel (slice loop mode 0, 4 CTAs per SM) and of the stand-alone SpMV."""
     for n, body in sass.items():
