@@ -151,7 +151,7 @@ void avs_destroy(AvsContext *c) {
     cudaStreamSynchronize(c->stream);
     avs_dist_destroy(c);
     DevBuf *bufs[] = {&c->fullSolution, &c->inSurface, &c->inVisc, &c->inDens, &c->inColl, &c->centerW, &c->tiles, &c->brickCount, &c->brickOffset,
-                      &c->scanTmp, &c->counters, &c->rowKeys, &c->x0, &c->rhs, &c->solution, &c->rowCount, &c->rowOffset,
+                      &c->scanTmp, &c->counters, &c->rowKeys, &c->coarseRows, &c->asmRowList, &c->faceWRow, &c->x0, &c->rhs, &c->solution, &c->rowCount, &c->rowOffset,
                       &c->csrPtr, &c->csrCol, &c->csrVal, &c->A.sliceOff, &c->A.val, &c->A.col, &c->A.invDiag, &c->A.meta, &c->cg.pcgState, &c->cg.sliceHalo, &c->cg.sliceFlag, &c->cg.sliceIndex, &c->cg.boundaryList, &c->cg.pcgLocal,
                       &c->cg.x, &c->cg.r, &c->cg.p, &c->cg.t, &c->cg.partials, &c->cg.scalars, &c->cgRhs,
                       &c->stageCol, &c->stageVal, &c->diag, &c->slicePairs, &c->edgeTiles, &c->solidW, &c->signA, &c->signB, &c->bandList, &c->brickCost, &c->brickCostPrefix,
@@ -255,9 +255,31 @@ int avs_stage_upload(AvsContext *c, const AvsFields *in, const AvsParams *p) {
     // the copy stream must not overwrite buffers a previous solve on the compute stream may still be reading
     AVS_CUDA_CHECK(cudaEventRecord(c->evCopyGate, c->stream));
     AVS_CUDA_CHECK(cudaStreamWaitEvent(c->copyStream, c->evCopyGate, 0));
-    for (int a = 0; a < 3; ++a) {
+    for (int a = 0; a < 3; ++a)
         if ((rc = uploadField(c, c->inVel[a], S.vel[a], in->vel[a], c->copyStream))) return rc;
-        if ((rc = uploadField(c, c->inFaceW[a], S.faceW[a], in->face_weights[a], c->copyStream))) return rc;
+    // Face weights are read once per LEVEL-0 ROW (k_gather_face_weights, avs_system.cu) -- a band around the surface, ~2 % of the
+    // three dense arrays.  Pinned (page-locked / registered) host arrays are therefore not copied at all: the gather kernel reads
+    // the values it needs through the mapped host pointer.  Pageable arrays cannot be mapped and are uploaded whole as before;
+    // AVS_FACEW_UPLOAD=bulk forces that path (A/B measurements).
+    static int bulk = -1;
+    if (bulk < 0) { const char *e = getenv("AVS_FACEW_UPLOAD"); bulk = (e && strcmp(e, "bulk") == 0) ? 1 : 0; }
+    c->faceWMappedBytes = 0;
+    for (int a = 0; a < 3; ++a) {
+        const AvsField &f = in->face_weights[a];
+        const void *mapped = nullptr;
+        if (!bulk && f.data && !f.on_device) {
+            cudaPointerAttributes attr;
+            if (cudaPointerGetAttributes(&attr, f.data) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+                mapped = attr.devicePointer;
+            else cudaGetLastError();
+        }
+        if (mapped) {
+            AvsField g = f;
+            g.data = (const float *)mapped;
+            g.on_device = 1;   // device-addressable: read in place
+            if ((rc = uploadField(c, c->inFaceW[a], S.faceW[a], g, c->copyStream))) return rc;
+            c->faceWMappedBytes = 1;
+        } else if ((rc = uploadField(c, c->inFaceW[a], S.faceW[a], f, c->copyStream))) return rc;
     }
     AVS_CUDA_CHECK(cudaEventRecord(c->evUploadDone, c->copyStream));
     return AVS_OK;
@@ -574,7 +596,13 @@ int avs_get_system_csr(AvsContext *c, int64_t *rowPtr, int32_t *col, double *val
     if (col) AVS_CUDA_CHECK(cudaMemcpyAsync(col, c->csrCol.p, (size_t)c->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     if (val) AVS_CUDA_CHECK(cudaMemcpyAsync(val, c->csrVal.p, (size_t)c->nnz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (rhs) AVS_CUDA_CHECK(cudaMemcpyAsync(rhs, c->rhs.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (x0) AVS_CUDA_CHECK(cudaMemcpyAsync(x0, c->x0.p, (size_t)c->nRows * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (x0) {
+        if (!c->x0AllRows) {   // multi-GPU solves restrict only the rows they own: complete the vector for the read-back
+            int rc = avs_stage_restriction(c, true);
+            if (rc) return rc;
+        }
+        AVS_CUDA_CHECK(cudaMemcpyAsync(x0, c->x0.p, (size_t)c->nRows * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
     AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     return AVS_OK;
 }

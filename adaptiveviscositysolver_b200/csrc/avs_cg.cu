@@ -1554,13 +1554,13 @@ static bool cgUsePersistent() {
 // Default: k_cg_persistent2 when the solve is row-partitioned over several ranks (its merged synchronisation points are what
 // multi-GPU needs), round 1's k_cg_persistent on a single GPU (same speed at 10 M rows, 5-9 % faster on 0.2-1 M rows where the
 // per-iteration synchronisation dominates: C2 18.8 vs 20.6 ms, C5 264 vs 278 ms).  AVS_PCG_KERNEL=v1 / v2 forces one.
-static int pcgVersion(bool dist) {
+static int pcgVersion(bool dist, bool fp32) {
     static int forced = -1;
     if (forced < 0) {
         const char *e = getenv("AVS_PCG_KERNEL");
         forced = (e && strcmp(e, "v1") == 0) ? 1 : (e && strcmp(e, "v2") == 0) ? 2 : 0;
     }
-    return forced ? forced : (dist ? 2 : 1);
+    return forced ? forced : ((dist || fp32) ? 2 : 1);   // fp32: the prefetching slice loop (spmvMode) exists in k_cg_persistent2 only
 }
 template <class T, class T2>
 static const void *pcgKernel() {
@@ -1574,23 +1574,27 @@ static const void *pcgKernel() {
 }
 // AVS_SPMV_MODE selects the slice loop of the stand-alone SpMV kernel and of the persistent CG kernel:
 //   base (default) register-staged | pf = + L2 prefetch of the next trip | ring = matrix stream staged through a per-warp cp.async ring
-static int spmvMode() {
-    static int m = -1;
-    if (m < 0) {
+// Default: base for fp64; pf for fp32 -- measured at C3 (N = 10.0 M): fp32 SpMV phase 0.342 ms with the prefetch against 0.366-0.371
+// without (solve 127 vs 135 ms), fp64 0.477-0.482 with against 0.462-0.464 without.
+static int spmvMode(bool fp32) {
+    static int m = -2;
+    if (m == -2) {
         const char *e = getenv("AVS_SPMV_MODE");
-        m = 0;
+        m = -1;
+        if (e && strcmp(e, "base") == 0) m = 0;
         if (e && strcmp(e, "pf") == 0) m = 1;
         if (e && strcmp(e, "ring") == 0) m = 2;
         if (e && strcmp(e, "ring4") == 0) m = 3;
         if (e && strcmp(e, "call") == 0) m = 4;     // persistent kernel calling the slice loop as a separate function (stand-alone SpMV: base)
     }
-    return m;
+    return m >= 0 ? m : (fp32 ? 1 : 0);
 }
+#define SPMV_MODE_T spmvMode(sizeof(T) == 4)
 template <class T, class T2>
 static const void *pcg2Kernel(size_t *smemOut) {
     const void *k;
     size_t smem = 0;
-    switch (spmvMode()) {
+    switch (SPMV_MODE_T) {
         case 1: k = (const void *)k_cg_persistent2<T, T2, 1, 4>; break;
         case 4: k = (const void *)k_cg_persistent2<T, T2, 3, 4>; break;
         case 2:
@@ -1628,7 +1632,7 @@ static void launchSpmv(AvsContext *c, SellMatrix &A, const T *x, T *y, double *p
             attrSet[DOT] = true;
         }
         k_spmv_tma<T, T2, DOT><<<grid, TMA_THREADS, smem, c->stream>>>(sjdsView<T, T2>(A), x, y, parts, sc);
-    } else if (spmvMode() == 2 || spmvMode() == 3) {   // per-warp cp.async ring: 8 pair-steps in trips of 4 (mode 2) or 4 pair-steps in trips of 2 (mode 3)
+    } else if (SPMV_MODE_T == 2 || SPMV_MODE_T == 3) {   // per-warp cp.async ring: 8 pair-steps in trips of 4 (mode 2) or 4 pair-steps in trips of 2 (mode 3)
 #define RING_LAUNCH(U, R)                                                                                                        \
     {                                                                                                                            \
         static bool attrSet = false;                                                                                             \
@@ -1639,9 +1643,9 @@ static void launchSpmv(AvsContext *c, SellMatrix &A, const T *x, T *y, double *p
         }                                                                                                                        \
         k_spmv_sjds_ring<T, T2, DOT, U, R><<<grid, CG_THREADS, smem, c->stream>>>(sjdsView<T, T2>(A), x, y, parts, sc);          \
     }
-        if (spmvMode() == 2) RING_LAUNCH(4, 8) else RING_LAUNCH(2, 4)
+        if (SPMV_MODE_T == 2) RING_LAUNCH(4, 8) else RING_LAUNCH(2, 4)
 #undef RING_LAUNCH
-    } else if (spmvMode() == 1) {   // L2 prefetch of the next trip
+    } else if (SPMV_MODE_T == 1) {   // L2 prefetch of the next trip
         k_spmv_sjds_pf<T, T2, DOT, 4><<<grid, CG_THREADS, 0, c->stream>>>(sjdsView<T, T2>(A), x, y, parts, sc);
     } else {
 #define SPMV_LAUNCH(U) k_spmv_sjds<T, T2, DOT, U><<<grid, CG_THREADS, 0, c->stream>>>(sjdsView<T, T2>(A), x, y, parts, sc)
@@ -1666,15 +1670,15 @@ static int spmvGrid(AvsContext *c, long long nslices) {
     }
     int perSM = 0;
     cudaError_t e;
-    if (spmvMode() == 2) {
+    if (SPMV_MODE_T == 2) {
         const size_t smem = (CG_THREADS / 32) * spmvRingBytesPerWarp<T2, 8>();
         cudaFuncSetAttribute(k_spmv_sjds_ring<T, T2, true, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_spmv_sjds_ring<T, T2, true, 4, 8>, CG_THREADS, smem);
-    } else if (spmvMode() == 3) {
+    } else if (SPMV_MODE_T == 3) {
         const size_t smem = (CG_THREADS / 32) * spmvRingBytesPerWarp<T2, 4>();
         cudaFuncSetAttribute(k_spmv_sjds_ring<T, T2, true, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_spmv_sjds_ring<T, T2, true, 2, 4>, CG_THREADS, smem);
-    } else if (spmvMode() == 1)
+    } else if (SPMV_MODE_T == 1)
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_spmv_sjds_pf<T, T2, true, 4>, CG_THREADS, 0);
     else
     switch (spmvU()) {
@@ -1715,7 +1719,7 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
         int perSM = 0;
         size_t smem2 = 0;
         const void *k2 = pcg2Kernel<T, T2>(&smem2);
-        cudaError_t e = pcgVersion(dist) == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k2, CG_THREADS, smem2)
+        cudaError_t e = pcgVersion(dist, sizeof(T) == 4) == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k2, CG_THREADS, smem2)
                                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, pcgKernel<T, T2>(), CG_THREADS, 0);
         if (e != cudaSuccess || perSM < 1) { cudaGetLastError(); perSM = 1; }
         const char *env = getenv("AVS_PCG_CTAS_PER_SM");
@@ -1779,7 +1783,7 @@ static int cgRunT(AvsContext *c, SellMatrix &A, const double *dRhs, const double
     CgScalars *hs = (CgScalars *)c->hostScalars;  // pinned
     PcgDist pd;
     const bool persistent = cgUsePersistent() && (!dist || avs_dist_pcg_args(c, &pd));
-    if (persistent && pcgVersion(dist) == 2 && c->nranks <= 8) {   // the mailbox exchange of syncSum fits the peers' words into one warp
+    if (persistent && pcgVersion(dist, sizeof(T) == 4) == 2 && c->nranks <= 8) {   // the mailbox exchange of syncSum fits the peers' words into one warp
         // ---- k_cg_persistent2: one cooperative launch per `check_every` iterations (default: all of them) ----------------
         if (w.pcgState.reserve(sizeof(Pcg2State) + 64)) return AVS_ERR_ALLOC;
         Pcg2State *st = w.pcgState.as<Pcg2State>();

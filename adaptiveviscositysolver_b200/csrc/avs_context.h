@@ -111,6 +111,9 @@ struct AvsContext {
     DevBuf signA, signB;    // sign classes of the surface SDF neighbourhoods (weights shortcut)
     DevBuf brickCount, brickCost, brickCostPrefix, brickOffset, scanTmp, counters;
     DevBuf rowKeys;         // RowKey[n]
+    DevBuf faceWRow;                        // fp32 [N]: the face weight of every level-0 row (k_gather_face_weights)
+    DevBuf asmRowList;                      // split assembly: local ids of the rows left for the generic kernel
+    DevBuf coarseRows;                      // ids of the rows of level >= 3 (restriction: one CTA per such row)
     DevBuf x0, rhs, solution, fullSolution;  // fp64: x0 [N], rhs/solution [local rows], fullSolution [N] (multi-GPU apply)
     DevBuf rowCount, rowOffset; // assembly scratch (int32 / int64)
     DevBuf csrPtr, csrCol, csrVal;  // canonical CSR of the local rows (int64 / int32 / fp64); col/val built lazily
@@ -126,6 +129,9 @@ struct AvsContext {
     int levelsAllocated = 0;
     int64_t nRows = 0, nnz = 0, nEdge = 0, nCenter = 0, nRegular = 0;
     int64_t rowBegin = 0, rowEnd = 0;  // rows owned by this rank
+    long long asmGenericRows = 0;      // rows of the last assembly that went through the generic kernel (split assembly: the non-simple ones)
+    int faceWMappedBytes = 0;          // 1: the face weights of this solve are read through mapped host pointers (no bulk upload)
+    bool x0AllRows = true;             // x0 holds the restricted velocity of every row (false: only of [rowBegin, rowEnd))
     std::vector<int> slabZ;            // [nranks+1] z-plane cuts of the regular grid (stage 4 labels + stage 11 are slab-sharded)
     std::vector<long long> rowStarts;  // [nranks+1] first row of every rank's block (brick-granular, cost-balanced, identical on all ranks)
 
@@ -161,7 +167,7 @@ int avs_octree_points(AvsContext *c, int64_t *countOut);
 int avs_slab_cuts(AvsContext *c);
 void avs_slab_range(const AvsContext *c, int axis, int q, int *z0, int *z1);
 int avs_stage_octree_labels(AvsContext *c);
-int avs_stage_restriction(AvsContext *c);
+int avs_stage_restriction(AvsContext *c, bool allRows = false);   // nranks > 1: only the rows this rank owns unless allRows
 int avs_stage_system(AvsContext *c, const AvsParams *p);
 int avs_stage_solve(AvsContext *c, const AvsParams *p, AvsResult *res);
 int avs_apply_regular(AvsContext *c, float *dOut[3], unsigned long long *hostPending, float *const *hostOut);

@@ -42,7 +42,9 @@ static_assert(sizeof(DeviceScene) <= 4000, "DeviceScene must fit the kernel para
 // z from the block index -- no 64-bit div/mod per thread (that cost more than the memory traffic of these streaming passes).
 // CELL_YB = grid rows per CTA.  Measured at C3 (512^3) with 4 rows per CTA (128 x 4 threads): the trivial streaming passes gain
 // ~10 % (weights 5.70 -> 5.15 ms, octree 2.56 -> 2.19), but the gather-heavy classification passes lose more (octree labels
-// 9.07 -> 10.79 ms): one row per CTA stays.
+// 9.07 -> 10.79 ms): one row per CTA stays.  Four samples per THREAD with the loads hoisted in front of the decisions (round 2, same
+// decisions, bit-identical output) lost as well: octree labels 9.24 -> 11.04 ms, regular labels 3.95 -> 3.79 ms at C3 -- these
+// kernels are bound by their integer index arithmetic (~270 instructions per face), not by load latency; not kept.
 #define CELL_YB 1
 #define LAUNCH_3D(ctx, kernel, n3, ...)                                                        \
     do {                                                                                       \
@@ -238,6 +240,90 @@ __global__ void k_sign_axis(const uint8_t *in, int nx, int ny, int nz, int axis,
     });
 }
 
+// ---- the same three passes, four cells per thread (rows whose length is a multiple of 4: every row then starts 4-byte / 16-byte
+// aligned).  One cell per thread keeps a single 1- or 4-byte load in flight per thread and the passes end up latency-bound at
+// ~1 TB/s; with 4 cells per thread the loads of a thread are independent, 4x wider and issued together.
+__device__ __forceinline__ unsigned combine3x4(unsigned a, unsigned b, unsigned c) {   // combine3 on four packed class bytes
+    unsigned r = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const unsigned x = (a >> (8 * k)) & 0xffu, y = (b >> (8 * k)) & 0xffu, z = (c >> (8 * k)) & 0xffu;
+        r |= ((x == y && y == z) ? x : 2u) << (8 * k);
+    }
+    return r;
+}
+__global__ void k_sign_x4(const float *__restrict__ sdf, int nx, int ny, int nz, uint8_t *__restrict__ out) {
+    const int x4 = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
+    const int x = 4 * x4;
+    if (x >= nx) return;
+    const size_t row = (size_t)nx * ((size_t)y + (size_t)ny * (size_t)z);
+    const float4 v = *(const float4 *)(sdf + row + x);
+    const float l = sdf[row + max(x - 1, 0)], r = sdf[row + min(x + 4, nx - 1)];
+    const unsigned s[6] = {l < 0.f ? 0u : 1u, v.x < 0.f ? 0u : 1u, v.y < 0.f ? 0u : 1u, v.z < 0.f ? 0u : 1u, v.w < 0.f ? 0u : 1u, r < 0.f ? 0u : 1u};
+    unsigned o = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o |= ((s[k] == s[k + 1] && s[k + 1] == s[k + 2]) ? s[k + 1] : 2u) << (8 * k);
+    *(unsigned *)(out + row + x) = o;
+}
+__global__ void k_sign_axis4(const uint8_t *__restrict__ in, int nx, int ny, int nz, int axis, uint8_t *__restrict__ out) {
+    const int x4 = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
+    const int x = 4 * x4;
+    if (x >= nx) return;
+    const size_t idx = (size_t)x + (size_t)nx * ((size_t)y + (size_t)ny * (size_t)z);
+    const size_t stride = axis == 1 ? (size_t)nx : (size_t)nx * ny;
+    const int pos = axis == 1 ? y : z, top = axis == 1 ? ny - 1 : nz - 1;
+    const unsigned a = *(const unsigned *)(in + (pos > 0 ? idx - stride : idx)), b = *(const unsigned *)(in + idx),
+                   c = *(const unsigned *)(in + (pos < top ? idx + stride : idx));
+    *(unsigned *)(out + idx) = combine3x4(a, b, c);
+}
+
+// Light pass for ALL FOUR weight grids at once (centre + the three edge grids; aligned sdf grid only): one thread per index
+// (x, y, z) of the (N+1)^3 corner lattice, four x positions per thread (x, x+128, x+256, x+384: every load / store instruction of a
+// warp stays one contiguous segment).  The sign class of the clamped cell is read ONCE and decides the weight of the centre sample
+// and of the three edge samples that carry this index: 1 (all voxels under the sample negative), 0 (all non-negative), or the
+// sample goes on its grid's band list for k_sdf_weights.  Replaces four dense passes that each re-read the class array.
+struct WeightGrids {
+    Grid3<float> g[4];          // centre, edge x, edge y, edge z
+    uint32_t *list[4];
+    unsigned long long cap[4];  // entries a list can hold; counts beyond it are detected on the host (dense fallback)
+};
+__global__ void k_weights_classify4(const __grid_constant__ WeightGrids W, int sn0, int sn1, int sn2, const uint8_t *__restrict__ signClass,
+                                    unsigned long long *listCount) {
+    const int y = (int)blockIdx.y, z = (int)blockIdx.z;
+    const int cy = min(y, sn1 - 1), cz = min(z, sn2 - 1);
+    const size_t crow = (size_t)sn0 * ((size_t)cy + (size_t)sn1 * (size_t)cz);
+    const int xb = (int)blockIdx.x * 512 + (int)threadIdx.x;
+    uint8_t cls[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int x = xb + 128 * j;
+        cls[j] = (x <= sn0) ? signClass[crow + min(x, sn0 - 1)] : (uint8_t)0;
+    }
+#pragma unroll
+    for (int gi = 0; gi < 4; ++gi) {
+        const Grid3<float> &g = W.g[gi];
+        const bool rowOk = y < g.n[1] && z < g.n[2];   // uniform over the CTA
+        if (!rowOk) continue;
+        const size_t row = (size_t)g.n[0] * ((size_t)y + (size_t)g.n[1] * (size_t)z);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int x = xb + 128 * j;
+            const bool in = x < g.n[0];
+            const bool band = in && cls[j] == 2;
+            if (in && cls[j] != 2) g.d[row + x] = cls[j] == 0 ? 1.f : 0.f;
+            const unsigned m = __ballot_sync(0xffffffffu, band);   // warp-aggregated append
+            if (m) {
+                const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+                unsigned long long base = 0;
+                if (lane == leader) base = atomicAdd(listCount + gi, (unsigned long long)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                const unsigned long long slot = base + __popc(m & ((1u << lane) - 1));
+                if (band && slot < W.cap[gi]) W.list[gi][slot] = (uint32_t)(row + x);
+            }
+        }
+    }
+}
+
 // setScaleDivideThreshold(1, nullptr, &b, 0): a /= b where b > 0 (AV.cpp:781-789)
 __global__ void k_divide_where_positive(float *a, const float *b, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -279,24 +365,70 @@ int avs_stage_weights(AvsContext *c, const AvsParams *p) {
     // sign classes of the surface SDF (only valid as a shortcut when the field sits on the scene grid with dilate = 0,
     // which avs_stage_upload has validated for `surface`)
     const uint8_t *cls = nullptr;
+    const size_t cells = (size_t)S.N[0] * S.N[1] * S.N[2];
     if (S.surface.d && n >= 1) {
-        const size_t cells = (size_t)S.N[0] * S.N[1] * S.N[2];
         if (c->signA.reserve(cells) || c->signB.reserve(cells)) return AVS_ERR_ALLOC;
-        LAUNCH_3D(c, k_sign_x, S.N, S.surface.d, S.N[0], S.N[1], S.N[2], c->signA.as<uint8_t>());
-        LAUNCH_3D(c, k_sign_axis, S.N, c->signA.as<uint8_t>(), S.N[0], S.N[1], S.N[2], 1, c->signB.as<uint8_t>());
-        LAUNCH_3D(c, k_sign_axis, S.N, c->signB.as<uint8_t>(), S.N[0], S.N[1], S.N[2], 2, c->signA.as<uint8_t>());
+        if (S.N[0] % 4 == 0) {   // rows start 16-byte aligned (cudaMalloc base, row length a multiple of 4 floats): 4 cells per thread
+            const dim3 g4((unsigned)((S.N[0] / 4 + 127) / 128), (unsigned)S.N[1], (unsigned)S.N[2]);
+            k_sign_x4<<<g4, 128, 0, c->stream>>>(S.surface.d, S.N[0], S.N[1], S.N[2], c->signA.as<uint8_t>());
+            k_sign_axis4<<<g4, 128, 0, c->stream>>>(c->signA.as<uint8_t>(), S.N[0], S.N[1], S.N[2], 1, c->signB.as<uint8_t>());
+            k_sign_axis4<<<g4, 128, 0, c->stream>>>(c->signB.as<uint8_t>(), S.N[0], S.N[1], S.N[2], 2, c->signA.as<uint8_t>());
+            c->launches += 3;
+        } else {
+            LAUNCH_3D(c, k_sign_x, S.N, S.surface.d, S.N[0], S.N[1], S.N[2], c->signA.as<uint8_t>());
+            LAUNCH_3D(c, k_sign_axis, S.N, c->signA.as<uint8_t>(), S.N[0], S.N[1], S.N[2], 1, c->signB.as<uint8_t>());
+            LAUNCH_3D(c, k_sign_axis, S.N, c->signB.as<uint8_t>(), S.N[0], S.N[1], S.N[2], 2, c->signA.as<uint8_t>());
+        }
         cls = c->signA.as<uint8_t>();
     }
-    int rc = weightsFor(c, c->centerW, S.centerW, S.surface, offC, S.N, n, 0.0, cls);
-    if (rc) return rc;
-    for (int a = 0; a < 3; ++a) {
-        double off[3] = {0, 0, 0};
-        off[a] = 0.5;  // an a-directed edge is centred along a only (HDK_Utilities.h:13-15)
-        int res[3] = {S.N[0] + 1, S.N[1] + 1, S.N[2] + 1};
-        res[a] -= 1;
-        rc = weightsFor(c, c->edgeW[a], S.edgeW[a], S.surface, off, res, n, 0.0, cls);
-        if (rc) return rc;
+    // the four grids: centre samples, and per axis a the a-directed edges (centred along a only, HDK_Utilities.h:13-15)
+    Grid3<float> *grids[4] = {&S.centerW, &S.edgeW[0], &S.edgeW[1], &S.edgeW[2]};
+    DevBuf *bufs[4] = {&c->centerW, &c->edgeW[0], &c->edgeW[1], &c->edgeW[2]};
+    double offs[4][3] = {{0.5, 0.5, 0.5}, {0.5, 0, 0}, {0, 0.5, 0}, {0, 0, 0.5}};
+    for (int gi = 0; gi < 4; ++gi) {
+        Grid3<float> &g = *grids[gi];
+        for (int k = 0; k < 3; ++k) g.n[k] = S.N[k] + ((gi == 0 || k == gi - 1) ? 0 : 1);
+        if (bufs[gi]->reserve(g.count() * sizeof(float))) return AVS_ERR_ALLOC;
+        g.d = bufs[gi]->as<float>();
     }
+    const size_t lattice = (size_t)(S.N[0] + 1) * (S.N[1] + 1) * (S.N[2] + 1);
+    if (cls && lattice < 0xffffffffull) {
+        // one fused light pass over the corner lattice writes the 0 / 1 weights of all four grids and lists their band samples
+        WeightGrids W;
+        const size_t cap = lattice / 4 + 4096;   // a band is a thin shell: a list that overflows falls back to the dense sampler
+        if (c->bandList.reserve(4 * cap * sizeof(uint32_t))) return AVS_ERR_ALLOC;
+        for (int gi = 0; gi < 4; ++gi) {
+            W.g[gi] = *grids[gi];
+            W.list[gi] = c->bandList.as<uint32_t>() + (size_t)gi * cap;
+            W.cap[gi] = cap;
+        }
+        unsigned long long *cnt = c->counters.as<unsigned long long>() + 28;   // slots 28..31
+        AVS_CUDA_CHECK(cudaMemsetAsync(cnt, 0, 4 * sizeof(unsigned long long), c->stream));
+        const dim3 grid((unsigned)((S.N[0] + 1 + 511) / 512), (unsigned)(S.N[1] + 1), (unsigned)(S.N[2] + 1));
+        k_weights_classify4<<<grid, 128, 0, c->stream>>>(W, S.N[0], S.N[1], S.N[2], cls, cnt);
+        ++c->launches;
+        unsigned long long h[4] = {0, 0, 0, 0};
+        AVS_CUDA_CHECK(cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        for (int gi = 0; gi < 4; ++gi) {
+            Grid3<float> &g = *grids[gi];
+            if (h[gi] > cap) {   // not a thin band (noise field): every sample decides for itself, class shortcut included
+                LAUNCH_3D(c, k_sdf_weights, g.n, g, S.surface, offs[gi][0], offs[gi][1], offs[gi][2], S.origin[0], S.origin[1], S.origin[2], S.dx0, n,
+                          0.0, cls, nullptr, nullptr);
+            } else if (h[gi] > 0) {
+                k_sdf_weights<<<(unsigned)((h[gi] + 127) / 128), 128, 0, c->stream>>>(g, S.surface, offs[gi][0], offs[gi][1], offs[gi][2], S.origin[0],
+                                                                                  S.origin[1], S.origin[2], S.dx0, n, 0.0, nullptr, W.list[gi], cnt + gi);
+                ++c->launches;
+            }
+        }
+    } else {
+        for (int gi = 0; gi < 4; ++gi) {
+            Grid3<float> &g = *grids[gi];
+            LAUNCH_3D(c, k_sdf_weights, g.n, g, S.surface, offs[gi][0], offs[gi][1], offs[gi][2], S.origin[0], S.origin[1], S.origin[2], S.dx0, n, 0.0,
+                      cls, nullptr, nullptr);
+        }
+    }
+    int rc = AVS_OK;
     if (p->do_apply_solid_weights) {  // AV.cpp:772-790
         DevBuf &tmp = c->solidW;
         Grid3<float> g;

@@ -47,8 +47,8 @@ __device__ __forceinline__ float octVel(const DeviceScene &S, const double *sol,
 }
 
 // setActiveNodes (VFI.cpp:118-188) + sampleActiveNodes (VFI.cpp:190-286)
-__global__ void k_node_sample(const __grid_constant__ DeviceScene S, NodeLevel nl, const double *sol, int level) {
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y), z = (int)blockIdx.z;
+__global__ void k_node_sample(const __grid_constant__ DeviceScene S, NodeLevel nl, const double *sol, int level, int zLo) {
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y), z = (int)blockIdx.z + zLo;
     if (x >= nl.label.n[0] || y >= nl.label.n[1]) return;
     const size_t idx = nl.label.lin(x, y, z);
     const I3 node = mk3(x, y, z);
@@ -103,8 +103,8 @@ __global__ void k_node_sample(const __grid_constant__ DeviceScene S, NodeLevel n
 }
 
 // bubbleActiveNodeValues (VFI.cpp:288-355): one thread per PARENT node (its co-located child is unique)
-__global__ void k_node_bubble(NodeLevel child, NodeLevel par) {
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y), z = (int)blockIdx.z;
+__global__ void k_node_bubble(NodeLevel child, NodeLevel par, int zLo) {
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y), z = (int)blockIdx.z + zLo;
     if (x >= par.label.n[0] || y >= par.label.n[1]) return;
     const int cx = 2 * x, cy = 2 * y, cz = 2 * z;
     if (cx >= child.label.n[0] || cy >= child.label.n[1] || cz >= child.label.n[2]) return;
@@ -119,8 +119,8 @@ __global__ void k_node_bubble(NodeLevel child, NodeLevel par) {
 }
 
 // finishIncompleteNodes (VFI.cpp:357-567)
-__global__ void k_node_finish(const __grid_constant__ DeviceScene S, NodeLevel nl, const double *sol, int level) {
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y), z = (int)blockIdx.z;
+__global__ void k_node_finish(const __grid_constant__ DeviceScene S, NodeLevel nl, const double *sol, int level, int zLo) {
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y), z = (int)blockIdx.z + zLo;
     if (x >= nl.label.n[0] || y >= nl.label.n[1]) return;
     const size_t idx = nl.label.lin(x, y, z);
     if (nl.label.d[idx] != N_ACTIVE) return;
@@ -143,9 +143,20 @@ __global__ void k_node_finish(const __grid_constant__ DeviceScene S, NodeLevel n
         }
         if (!found) {
             I3 cell = f;  // HDKfaceToCell(face, faceAxis, 1)
-            int sl = level;
-            while (sl < L && S.label[sl].get(cell) != L_ACTIVE) { cell = parentOf(cell); ++sl; }
+            int sl = L;   // first level >= `level` whose ancestor of the cell is ACTIVE; all labels fetched at once (no dependent chain)
+            {
+                uint8_t labs[AVS_MAX_LEVELS];
+#pragma unroll
+                for (int l = 0; l < AVS_MAX_LEVELS; ++l) {
+                    const int sh = max(l - level, 0);
+                    labs[l] = (l >= level && l < L) ? S.label[l].get(mk3(f[0] >> sh, f[1] >> sh, f[2] >> sh)) : (uint8_t)L_INACTIVE;
+                }
+#pragma unroll
+                for (int l = AVS_MAX_LEVELS - 1; l >= 0; --l)
+                    if (labs[l] == L_ACTIVE) sl = l;
+            }
             if (sl >= L) { flag += 1u << bit; continue; }  // asserted impossible in the reference (VFI.cpp:490)
+            { const int sh = sl - level; cell = mk3(f[0] >> sh, f[1] >> sh, f[2] >> sh); }
             double fp[3];
             S.facePos(f, fa, level, fp);
             const double idxNode = (fp[fa] - S.origin[fa]) / S.levelDx(sl);
@@ -174,8 +185,8 @@ __global__ void k_node_finish(const __grid_constant__ DeviceScene S, NodeLevel n
 }
 
 // normalizeActiveNodes (VFI.cpp:569-613)
-__global__ void k_node_normalize(NodeLevel nl) {
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y), z = (int)blockIdx.z;
+__global__ void k_node_normalize(NodeLevel nl, int zLo) {
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y), z = (int)blockIdx.z + zLo;
     if (x >= nl.label.n[0] || y >= nl.label.n[1]) return;
     const size_t idx = nl.label.lin(x, y, z);
     if (nl.label.d[idx] != N_ACTIVE) return;
@@ -183,8 +194,8 @@ __global__ void k_node_normalize(NodeLevel nl) {
 }
 
 // distributeNodeValuesDown (VFI.cpp:615-658)
-__global__ void k_node_distribute(NodeLevel child, NodeLevel par) {
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y), z = (int)blockIdx.z;
+__global__ void k_node_distribute(NodeLevel child, NodeLevel par, int zLo) {
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y), z = (int)blockIdx.z + zLo;
     if (x >= child.label.n[0] || y >= child.label.n[1]) return;
     const size_t idx = child.label.lin(x, y, z);
     if (child.label.d[idx] != N_DEPENDENT) return;
@@ -199,8 +210,22 @@ __device__ double interpSPGrid(const DeviceScene &S, const NodeScene &NS, const 
     I3 cell;
     for (int a = 0; a < 3; ++a) cell[a] = (int)floor((pos[a] - S.origin[a]) / S.levelDx(0));
     const int a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
-    for (int level = 0; level < L; ++level) {
-        if (S.label[level].get(cell) == L_ACTIVE) {
+    // The reference climbs from level 0 until the cell is ACTIVE (VFI.cpp:676-690): a chain of up to L dependent loads.  The
+    // ancestors' indices are known up front, so all L labels are fetched at once and the first ACTIVE one is picked.
+    int hit = L;
+    {
+        uint8_t labs[AVS_MAX_LEVELS];
+#pragma unroll
+        for (int l = 0; l < AVS_MAX_LEVELS; ++l)
+            labs[l] = (l < L) ? S.label[l].get(mk3(cell[0] >> l, cell[1] >> l, cell[2] >> l)) : (uint8_t)L_INACTIVE;
+#pragma unroll
+        for (int l = AVS_MAX_LEVELS - 1; l >= 0; --l)
+            if (labs[l] == L_ACTIVE) hit = l;
+    }
+    if (hit < L) {
+        const int level = hit;
+        cell = mk3(cell[0] >> level, cell[1] >> level, cell[2] >> level);
+        {
             const double h = S.levelDx(level);
             double ifp[3];
             I3 face;
@@ -267,7 +292,6 @@ __device__ double interpSPGrid(const DeviceScene &S, const NodeScene &NS, const 
             }
             return (1. - ciw) * fiv[0] + ciw * fiv[1];
         }
-        cell = parentOf(cell);
     }
     return 0.;
 }
@@ -304,7 +328,8 @@ __global__ void k_apply_regular(const __grid_constant__ DeviceScene S, const Nod
 }
 
 #define NODE_YB 1   // grid rows per CTA; 4 (128 x 4 threads) measured slower for the node pyramid at C3 (apply 22.3 -> 24.4 ms)
-static dim3 grid3(const int n[3]) { return dim3((unsigned)((n[0] + 127) / 128), (unsigned)((n[1] + NODE_YB - 1) / NODE_YB), (unsigned)n[2]); }
+// node planes [zLo, zLo + nz) of a level
+static dim3 grid3(const int n[3], int nz) { return dim3((unsigned)((n[0] + 127) / 128), (unsigned)((n[1] + NODE_YB - 1) / NODE_YB), (unsigned)nz); }
 
 int avs_apply_regular(AvsContext *c, float *dOut[3], unsigned long long *hostInterpolated, float *const *hostOut) {
     const DeviceScene &S = c->S;
@@ -338,24 +363,50 @@ int avs_apply_regular(AvsContext *c, float *dOut[3], unsigned long long *hostInt
             nl.label.d = lb;
             for (int k = 0; k < 3; ++k) { nl.flag.n[k] = n[k]; nl.label.n[k] = n[k]; }
         }
+        // Multi-GPU: this rank writes back only its z-slab of the regular grid, and interpSPGrid reads node values only on the
+        // faces of the ACTIVE cell that contains the sample.  Every node kernel is either local or couples CO-LOCATED nodes of
+        // adjacent levels (bubble up / distribute down), so the pyramid is needed -- and built -- only between the fine planes
+        // zA and zB: the slab widened to the top-level cells it touches (any ACTIVE cell overlapping the slab nests in those).
+        int zA = 0, zB = S.Pad[2];
+        if (c->nranks > 1) {
+            int s0 = S.Pad[2], s1 = 0;
+            for (int a = 0; a < 3; ++a) {
+                int z0, z1;
+                avs_slab_range(c, a, c->rank, &z0, &z1);
+                if (z1 > z0) { s0 = std::min(s0, z0); s1 = std::max(s1, z1); }
+            }
+            const int top = 1 << (L - 1);
+            zA = s1 > s0 ? (s0 / top) * top : 0;
+            zB = s1 > s0 ? std::min(S.Pad[2], ((s1 + top - 1) / top) * top) : -1;   // empty slab: no node is read
+        }
+        int zLo[AVS_MAX_LEVELS], nzW[AVS_MAX_LEVELS];
         for (int l = 0; l < L; ++l) {
-            k_node_sample<<<grid3(NS.lv[l].label.n), dim3(128, NODE_YB), 0, c->stream>>>(S, NS.lv[l], sol, l);
+            zLo[l] = zA >> l;
+            nzW[l] = zB < zA ? 0 : std::min((zB >> l), NS.lv[l].label.n[2] - 1) - zLo[l] + 1;
+        }
+        for (int l = 0; l < L; ++l) {
+            if (nzW[l] <= 0) continue;
+            k_node_sample<<<grid3(NS.lv[l].label.n, nzW[l]), dim3(128, NODE_YB), 0, c->stream>>>(S, NS.lv[l], sol, l, zLo[l]);
             ++c->launches;
         }
         for (int l = 0; l < L - 1; ++l) {
-            k_node_bubble<<<grid3(NS.lv[l + 1].label.n), dim3(128, NODE_YB), 0, c->stream>>>(NS.lv[l], NS.lv[l + 1]);
+            if (nzW[l + 1] <= 0) continue;
+            k_node_bubble<<<grid3(NS.lv[l + 1].label.n, nzW[l + 1]), dim3(128, NODE_YB), 0, c->stream>>>(NS.lv[l], NS.lv[l + 1], zLo[l + 1]);
             ++c->launches;
         }
         for (int l = 0; l < L - 1; ++l) {
-            k_node_finish<<<grid3(NS.lv[l].label.n), dim3(128, NODE_YB), 0, c->stream>>>(S, NS.lv[l], sol, l);
+            if (nzW[l] <= 0) continue;
+            k_node_finish<<<grid3(NS.lv[l].label.n, nzW[l]), dim3(128, NODE_YB), 0, c->stream>>>(S, NS.lv[l], sol, l, zLo[l]);
             ++c->launches;
         }
         for (int l = 0; l < L; ++l) {
-            k_node_normalize<<<grid3(NS.lv[l].label.n), dim3(128, NODE_YB), 0, c->stream>>>(NS.lv[l]);
+            if (nzW[l] <= 0) continue;
+            k_node_normalize<<<grid3(NS.lv[l].label.n, nzW[l]), dim3(128, NODE_YB), 0, c->stream>>>(NS.lv[l], zLo[l]);
             ++c->launches;
         }
         for (int l = L - 2; l >= 0; --l) {
-            k_node_distribute<<<grid3(NS.lv[l].label.n), dim3(128, NODE_YB), 0, c->stream>>>(NS.lv[l], NS.lv[l + 1]);
+            if (nzW[l] <= 0) continue;
+            k_node_distribute<<<grid3(NS.lv[l].label.n, nzW[l]), dim3(128, NODE_YB), 0, c->stream>>>(NS.lv[l], NS.lv[l + 1], zLo[l]);
             ++c->launches;
         }
     }

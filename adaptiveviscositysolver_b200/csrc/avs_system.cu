@@ -236,9 +236,10 @@ __device__ __forceinline__ double restrictHatTerm(const DeviceScene &S, int axis
 }
 
 // levels 0 and 1: leaves added in the reference's order (bit-identical to the oracle); level 2: hat form
-__global__ void k_restrict_fine(const __grid_constant__ DeviceScene S, const RowKey *keys, long long n, double *x0) {
+__global__ void k_restrict_fine(const __grid_constant__ DeviceScene S, const RowKey *keys, long long base, long long n, double *x0) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    i += base;
     RowKey k = keys[i];
     if (k.level > 2) return;
     I3 face = mk3(k.i, k.j, k.k);
@@ -277,34 +278,42 @@ __global__ void k_restrict_coarse(const __grid_constant__ DeviceScene S, const R
     }
     if (threadIdx.x == 0) x0[i] = sh[0] / (double)(side * side * side * side);  // 16^-l, exact power of two
 }
-__global__ void k_collect_coarse_rows(const RowKey *keys, long long n, int32_t *rows, unsigned long long *counter) {
+__global__ void k_collect_coarse_rows(const RowKey *keys, long long base, long long n, int32_t *rows, unsigned long long *counter) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    i += base;
     if (keys[i].level >= 3) {
         unsigned long long slot = atomicAdd(counter, 1ull);
         rows[slot] = (int32_t)i;  // order is irrelevant: every row is written exactly once
     }
 }
 
-int avs_stage_restriction(AvsContext *c) {
-    const long long n = c->nRows;
-    if (c->x0.reserve((size_t)std::max<long long>(n, 1) * sizeof(double))) return AVS_ERR_ALLOC;
-    if (n == 0) return AVS_OK;
+// Multi-GPU: a rank restricts only the rows it owns -- the assembly reads x0 of its own rows (rhs += M u^n) and the CG stages its
+// local x0 in p's buffer and fetches the halo entries from the peers (avs_cg.cu) -- unless `allRows` (read-back of the whole x0).
+int avs_stage_restriction(AvsContext *c, bool allRows) {
+    const long long nAll = c->nRows;
+    if (c->x0.reserve((size_t)std::max<long long>(nAll, 1) * sizeof(double))) return AVS_ERR_ALLOC;
+    // (rowBegin / rowEnd are assigned by avs_stage_system, after this stage: take the block from the numbering's row partition)
+    const bool all = allRows || c->nranks == 1 || c->rowStarts.size() != (size_t)c->nranks + 1;
+    const long long base = all ? 0 : c->rowStarts[c->rank];
+    const long long n = all ? nAll : c->rowStarts[c->rank + 1] - c->rowStarts[c->rank];
+    c->x0AllRows = all;
+    if (n <= 0) return AVS_OK;
     unsigned blocks = (unsigned)((n + 255) / 256);
-    k_restrict_fine<<<blocks, 256, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), n, c->x0.as<double>());
+    k_restrict_fine<<<blocks, 256, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), base, n, c->x0.as<double>());
     ++c->launches;
     if (c->S.levels > 3) {
         // rows of level >= 3 are few (a few percent): compact their ids, then one CTA per row
-        if (c->rowCount.reserve((size_t)n * sizeof(int32_t))) return AVS_ERR_ALLOC;
+        if (c->coarseRows.reserve((size_t)n * sizeof(int32_t))) return AVS_ERR_ALLOC;   // own buffer: rowCount holds the assembled rows' lengths
         unsigned long long *cnt = c->counters.as<unsigned long long>() + 24;
         AVS_CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
-        k_collect_coarse_rows<<<blocks, 256, 0, c->stream>>>(c->rowKeys.as<RowKey>(), n, c->rowCount.as<int32_t>(), cnt);
+        k_collect_coarse_rows<<<blocks, 256, 0, c->stream>>>(c->rowKeys.as<RowKey>(), base, n, c->coarseRows.as<int32_t>(), cnt);
         ++c->launches;
         unsigned long long h = 0;
         AVS_CUDA_CHECK(cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
         AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
         if (h > 0) {
-            k_restrict_coarse<<<(unsigned)h, 256, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->rowCount.as<int32_t>(), c->x0.as<double>());
+            k_restrict_coarse<<<(unsigned)h, 256, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->coarseRows.as<int32_t>(), c->x0.as<double>());
             ++c->launches;
         }
     }
@@ -330,7 +339,7 @@ __device__ __noinline__ void applyToMatrix(Row &row, double &rhsI, double &diag,
 
 // buildOctreeSystemFromStencilsPartial (AV.cpp:2459-2777) for row vi
 template <class Row>
-__device__ void buildRow(const DeviceScene &S, int32_t vi, const RowKey &k, double x0i, Row &row, double &rhsI) {
+__device__ void buildRow(const DeviceScene &S, int32_t vi, const RowKey &k, double x0i, float faceWeight, Row &row, double &rhsI) {
     const int level = k.level, axis = k.axis;
     const I3 face = mk3(k.i, k.j, k.k);
     const Grid3<uint8_t> &lab = S.label[level];
@@ -403,7 +412,7 @@ __device__ void buildRow(const DeviceScene &S, int32_t vi, const RowKey &k, doub
     // velocity control volume (AV.cpp:2748-2772)
     double fw;
     if (level == 0) {
-        fw = (double)S.faceW[axis].raw(face[0], face[1], face[2]);
+        fw = (double)faceWeight;   // S.faceW[axis] at the face, fetched by k_gather_face_weights
         if (fw == 1.) fw = faceOctreeVolume(S, face, axis, level);
     } else fw = faceOctreeVolume(S, face, axis, level);
     if (!S.density.d) fw *= (double)S.density.constant;
@@ -416,22 +425,39 @@ __device__ void buildRow(const DeviceScene &S, int32_t vi, const RowKey &k, doub
     rhsI += fw * x0i;
 }
 
+// The face-weight field ("surfaceweights", AV.cpp:144) is read at ONE place of the whole path: the control volume of a LEVEL-0
+// row (AV.cpp:2748-2760).  So the three dense arrays (1.6 GB at 512^3) need not be resident: this kernel fetches the one value each
+// level-0 row of this rank needs into a per-row array.  S.faceW[a].d is either a device copy / the caller's device array, or --
+// when the caller's host arrays are pinned -- the mapped HOST pointer, and the reads then go over PCIe: ~N_level0 x 32-byte
+// sectors instead of the bulk upload (avs_stage_upload).
+__global__ void k_gather_face_weights(const __grid_constant__ DeviceScene S, const RowKey *keys, long long base, long long n, float *fwRow) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    i += base;
+    const RowKey k = keys[i];
+    fwRow[i] = (k.level == 0) ? S.faceW[k.axis].raw(k.i, k.j, k.k) : 1.f;
+}
+
 // One pass: every row thread writes its merged entries into a column-major staging area
 // (entry j of local row r at j*stride + r, so a warp's writes are coalesced), its entry count, its
 // rhs and its diagonal.  The CG's SJDS matrix is filled straight from the staging area; a canonical
 // CSR (sorted columns) is only built when a caller asks to read the system back.
 template <int MINB, class Row>
-__global__ void __launch_bounds__(128, MINB) k_assemble(const __grid_constant__ DeviceScene S, const RowKey *keys, const double *x0,
+__global__ void __launch_bounds__(128, MINB) k_assemble(const __grid_constant__ DeviceScene S, const RowKey *keys, const double *x0, const float *fwRow,
                                                   long long rowBegin, long long nLocal, long long stride, int32_t *rowCount,
                                                   int32_t *stageCol, double *stageVal, double *rhs, double *diagOut,
-                                                  int *overflowFlag) {
+                                                  int *overflowFlag, const int32_t *rowList, const unsigned long long *rowListCount) {
     long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (rowList) {   // second pass of the split assembly: only the rows k_assemble_simple passed on
+        if ((unsigned long long)r >= *rowListCount) return;
+        r = rowList[r];
+    }
     if (r >= nLocal) return;
     const long long gi = rowBegin + r;
     Row row;
     row.init();
     double rhsI = 0;
-    buildRow(S, (int32_t)gi, keys[gi], x0[gi], row, rhsI);
+    buildRow(S, (int32_t)gi, keys[gi], x0[gi], fwRow[gi], row, rhsI);
     if (row.overflow) *overflowFlag = 1;
     rowCount[r] = row.n;
     for (int i = 0; i < row.n; ++i) {
@@ -442,165 +468,219 @@ __global__ void __launch_bounds__(128, MINB) k_assemble(const __grid_constant__ 
     diagOut[r] = row.val[row.n - 1];  // buildRow adds the diagonal last and it is unique (AV.cpp:2768)
 }
 
-// ---- warp-cooperative assembly (experiment, AVS_ASM=warp; NOT the default: see avs_stage_system) ----------------------------------------------------------------------------------------
-// One WARP owns one matrix row.  A row is touched by at most 26 stresses, in the fixed order buildRow visits them: per side of the face
-// the cell-centred stress and up to 8 T-junction ghost edges (9 x 2 slots), then per transverse edge position the sibling (or first
-// child) edge and the edge itself (or second child) (2 x 4 slots).  Lane l decides whether slot l exists and evaluates ITS stencil --
-// so the ~10 stencil evaluations a row needs run side by side instead of one after the other in a single thread -- then the warp
-// merges the slots in slot order: the owner lane broadcasts (column, value) pairs, the row lives in registers (entry e in lane e & 31),
-// a duplicate column is found with one compare + ballot instead of a linear search through local memory.  Same insertion order and the
-// same order of additions per entry as the one-thread-per-row kernel: bit-identical rows.
-struct SlotRef {
-    int kind;   // 0 none, 1 cell-centred stress, 2 edge stress
-    I3 idx;
-    int axis, level;
+// ---- split assembly, first pass (default): the level-0 rows without T-junctions, solids or coarse neighbours -------------------
+// buildRow's control flow (which stencils exist, what each one touches) is what makes k_assemble slow: ncu showed 10.8 of 32
+// lanes active per instruction and the stencils in local memory.  For a level-0 face whose two cells are ACTIVE (or outside the
+// grid) and whose stencil faces are all DOFs or OUTSIDE -- no UNASSIGNED (coarser) face, no SOLID face -- every branch of
+// edgeStressFaces / centerStressFaces / applyToMatrix is decided by a handful of labels:
+//   * the two centre stresses contribute (self, self -/+ 1 along the axis) with coefficients -/+ 1/dx;
+//   * the four edge stresses (two transverse axes x two sides) contribute the own-axis neighbour across the edge and the two
+//     transverse faces that meet at the edge, all with +/- 0.5/G, G = float(float(0 + dx/2) + dx/2) (no transition: AV.cpp:1755-1782);
+//   * control volumes are 1 (faceOctreeVolume / edgeOctreeVolume of an all-level-0 neighbourhood).
+// This kernel fetches all labels, indices and weights of a row up front (one memory round trip after the key), evaluates exactly
+// those expressions in buildRow's order -- the entries, their order and every rounding are bit-identical to k_assemble's
+// (tests/test_gpu_kernel_variants.py) -- and hands every other row to k_assemble through `rowList`.
+struct SimpleRowOut {   // entries go straight to the column-major staging area (the decision "simple" is taken before the first add)
+    int n;
+    int32_t *col;
+    double *val, last;
+    long long stride;
+    __device__ __forceinline__ void add(int32_t c, double v) {
+        col[(long long)n * stride] = c;
+        val[(long long)n * stride] = v;
+        last = v;
+        ++n;
+    }
 };
-__device__ __forceinline__ int otherAxis(int axis, int which) { return which == 0 ? (axis == 0 ? 1 : 0) : (axis == 2 ? 1 : 2); }
-
-__device__ SlotRef rowSlot(const DeviceScene &S, const RowKey &k, int slot) {
-    const int level = k.level, axis = k.axis;
-    const I3 face = mk3(k.i, k.j, k.k);
-    SlotRef r;
-    r.kind = 0; r.idx = face; r.axis = 0; r.level = 0;
-    if (slot < 18) {   // AV.cpp:2547-2649
-        const int dir = slot / 9, sub = slot % 9;
-        const Grid3<uint8_t> &lab = S.label[level];
-        const I3 cell = faceToCell(face, axis, dir);
-        if (cell[axis] < 0 || cell[axis] >= lab.n[axis]) return r;
-        I3 sc;
-        int sl;
-        if (lab.get(cell) == L_ACTIVE) { sc = cell; sl = level; }
-        else { sc = parentOf(cell); sl = level + 1; }
-        if (sl >= S.levels) return r;
-        if (sub == 0) {
-            if (S.center[sl].get(sc) >= 0) { r.kind = 1; r.idx = sc; r.axis = axis; r.level = sl; }
-            return r;
-        }
-        const int t = sub - 1, fa = otherAxis(axis, t >> 2), fd = (t >> 1) & 1, ins = t & 1;
-        const I3 af = cellToFace(sc, fa, fd);
-        if (sl > 0 && S.face[sl][fa].get(af) == F_UNASSIGNED) {
-            const int ea = 3 - fa - axis;
-            const I3 e = childEdgeInFace(af, fa, ea, ins);
-            if (S.edge[sl - 1][ea].get(e) >= 0) { r.kind = 2; r.idx = e; r.axis = ea; r.level = sl - 1; }
-        }
-        return r;
+template <int AXIS>
+__device__ __forceinline__ bool buildSimpleRow(const DeviceScene &S, int32_t vi, const I3 &face, double x0i, float fwRaw, SimpleRowOut &row, double &rhsI) {
+    const Grid3<uint8_t> &lab = S.label[0];
+    const Grid3<int32_t> &fg = S.face[0][AXIS];
+    constexpr int T1 = (AXIS + 1) % 3, T2 = (AXIS + 2) % 3;           // the two transverse axes
+    constexpr int EA0 = T1 < T2 ? T1 : T2, EA1 = T1 < T2 ? T2 : T1;   // buildRow visits the edge axes in ascending order
+    // ---- everything a decision may need, fetched unconditionally with clamped indices ---------------------------------------
+    const I3 cell[2] = {faceToCell(face, AXIS, 0), face};
+    bool cellIn[2];
+    uint8_t cl[2];
+    int8_t cen[2];
+    float cw[2];
+    int32_t along[2];   // face -/+ 1 along the axis
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+        cellIn[d] = cell[d][AXIS] >= 0 && cell[d][AXIS] < lab.n[AXIS];
+        cl[d] = lab.get(cell[d]);
+        cen[d] = S.center[0].get(cell[d]);
+        cw[d] = S.centerW.get(cell[d]);
+        I3 f = face;
+        f[AXIS] += d ? 1 : -1;
+        along[d] = fg.get(f);
     }
-    if (slot >= 26) return r;
-    // AV.cpp:2652-2742
-    const int t = slot - 18, ea = otherAxis(axis, t >> 2), dir = (t >> 1) & 1, second = t & 1;
-    const Grid3<int8_t> &eg = S.edge[level][ea];
-    const I3 e = faceToEdge(face, axis, ea, dir);
-    const int8_t ei = eg.get(e);
-    if (ei >= 0) {
-        if (second) { r.kind = 2; r.idx = e; r.axis = ea; r.level = level; }
-        else if (S.enhanced) {   // sibling edge across a transition (AV.cpp:2664-2697)
-            const Grid3<int32_t> &fgrid = S.face[level][axis];
-            const int ta = 3 - ea - axis;
-            I3 af = face;
-            af[ta] += (dir == 0) ? -1 : 1;
-            if (af[ta] >= 0 && af[ta] < fgrid.n[ta] && fgrid.get(af) == F_UNASSIGNED) {
-                I3 se = e;
-                se[ea] += (e[ea] % 2 == 0) ? 1 : -1;
-                if (eg.get(se) >= 0) { r.kind = 2; r.idx = se; r.axis = ea; r.level = level; }
+    int8_t ei[2][2];
+    float ew[2][2];
+    int32_t own[2][2], cross[2][2][2];
+    bool ownIn[2][2], crossIn[2][2][2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int ea = q ? EA1 : EA0, ta = 3 - AXIS - ea;
+#pragma unroll
+        for (int dir = 0; dir < 2; ++dir) {
+            const I3 e = faceToEdge(face, AXIS, ea, dir);
+            ei[q][dir] = S.edge[0][ea].get(e);
+            ew[q][dir] = S.edgeW[ea].get(e);
+            // own-axis face across the edge: edgeToFace(e, ea, AXIS, dir) = face -/+ 1 along ta
+            I3 of = face;
+            of[ta] += dir ? 1 : -1;
+            ownIn[q][dir] = of[ta] >= 0 && of[ta] < fg.n[ta];
+            own[q][dir] = fg.get(of);
+            // the two ta-faces that meet at the edge: edgeToFace(e, ea, ta, d2) = e - (d2 == 0) along AXIS
+            const Grid3<int32_t> &tg = S.face[0][ta];
+#pragma unroll
+            for (int d2 = 0; d2 < 2; ++d2) {
+                I3 cf = e;
+                if (d2 == 0) --cf[AXIS];
+                crossIn[q][dir][d2] = cf[AXIS] >= 0 && cf[AXIS] < tg.n[AXIS];
+                cross[q][dir][d2] = tg.get(cf);
             }
         }
-    } else if (ei == F_UNASSIGNED && level > 0) {   // AV.cpp:2714-2742
-        const I3 ce = childEdge(e, ea, second);
-        if (S.edge[level - 1][ea].get(ce) >= 0) { r.kind = 2; r.idx = ce; r.axis = ea; r.level = level - 1; }
     }
-    return r;
-}
-
-__device__ __forceinline__ double shflD(double v, int src) {
-    return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src), __shfl_sync(0xffffffffu, __double2loint(v), src));
-}
-
-#define ASM_WARPS 4
-__global__ void __launch_bounds__(ASM_WARPS * 32) k_assemble_warp(const __grid_constant__ DeviceScene S, const RowKey *keys, const double *x0,
-                                                                  long long rowBegin, long long nLocal, long long stride, int32_t *rowCount,
-                                                                  int32_t *stageCol, double *stageVal, double *rhs, double *diagOut, int *overflowFlag) {
-    const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    Stencil st;
-    for (long long r = warp; r < nLocal; r += nWarps) {
-        const long long gi = rowBegin + r;
-        const int32_t vi = (int32_t)gi;
-        const RowKey k = keys[gi];
-        // ---- every lane: does my slot exist? then my stencil, my weight, my row coefficient
-        const SlotRef ref = rowSlot(S, k, lane);
-        double coefficient = 0;
-        st.n = st.nb = 0;
-        if (ref.kind == 1) {
-            centerStressFaces(S, st, ref.idx, ref.axis, ref.level);
-            coefficient = centerStressWeight(S, ref.idx, ref.level);
-        } else if (ref.kind == 2) {
-            edgeStressFaces(S, st, ref.idx, ref.axis, ref.level);
-            coefficient = edgeStressWeight(S, ref.idx, ref.axis, ref.level);
+    // ---- is it a simple row? ------------------------------------------------------------------------------------------------
+    bool simple = true;
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+        if (cellIn[d] && cl[d] != L_ACTIVE) simple = false;                        // the stress cell is the parent (AV.cpp:2562-2572)
+        if (cellIn[d] && cen[d] >= 0 && along[d] == F_SOLID) simple = false;       // boundary term
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int dir = 0; dir < 2; ++dir) {
+            if (ei[q][dir] < 0) continue;
+            if (ownIn[q][dir] && (own[q][dir] == F_UNASSIGNED || own[q][dir] == F_SOLID)) simple = false;
+#pragma unroll
+            for (int d2 = 0; d2 < 2; ++d2)
+                if (crossIn[q][dir][d2] && (cross[q][dir][d2] == F_UNASSIGNED || cross[q][dir][d2] == F_SOLID)) simple = false;
         }
-        if (ref.kind) {   // applyToMatrix (AV.cpp:2423-2435): scale by the coefficient of this row's own face
-            for (int i = 0; i < st.n; ++i)
-                if (st.idx[i] == vi) { coefficient *= st.coef[i]; break; }
-        }
-        // ---- merge in slot order
-        int n = 0, overflow = 0;
-        int32_t col0 = -1, col1 = -1;
-        double val0 = 0, val1 = 0, diag = 0, rhsI = 0;
-        unsigned todo = __ballot_sync(0xffffffffu, ref.kind != 0);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int ns = __shfl_sync(0xffffffffu, st.n, src), nbs = __shfl_sync(0xffffffffu, st.nb, src);
-            for (int i = 0; i < ns; ++i) {
-                const int32_t c = __shfl_sync(0xffffffffu, st.idx[i], src);
-                const double el = shflD(coefficient * st.coef[i], src);
-                if (c == vi) { diag += el; continue; }
-                const bool m0 = lane < n && col0 == c;
-                const unsigned b0 = __ballot_sync(0xffffffffu, m0);
-                if (b0) { if (m0) val0 += el; continue; }
-                if (n > 32) {
-                    const bool m1 = 32 + lane < n && col1 == c;
-                    const unsigned b1 = __ballot_sync(0xffffffffu, m1);
-                    if (b1) { if (m1) val1 += el; continue; }
-                }
-                if (n < MAX_ROW - 1) {   // the last slot is kept for the diagonal
-                    if ((n & 31) == lane) {
-                        if (n < 32) { col0 = c; val0 = el; }
-                        else { col1 = c; val1 = el; }
-                    }
-                    ++n;
-                } else overflow = 1;
-            }
-            for (int i = 0; i < nbs; ++i) rhsI -= shflD(coefficient * st.bnd[i], src);
-        }
-        // ---- velocity control volume (AV.cpp:2748-2772); the diagonal goes last and is unique
-        const int level = k.level, axis = k.axis;
-        const I3 face = mk3(k.i, k.j, k.k);
-        double fw;
-        if (level == 0) {
-            fw = (double)S.faceW[axis].raw(face[0], face[1], face[2]);
-            if (fw == 1.) fw = faceOctreeVolume(S, face, axis, level);
-        } else fw = faceOctreeVolume(S, face, axis, level);
-        if (!S.density.d) fw *= (double)S.density.constant;
+    if (!simple) return false;
+    // ---- the row, in buildRow's order ---------------------------------------------------------------------------------------
+    const double dx = S.levelDx(0);
+    const double G = (double)(float)((double)(float)(0.0 + .5 * dx) + .5 * dx);   // gradientDx of an edge without transition
+    double diag = 0;
+    row.n = 0;
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+        if (!cellIn[d] || cen[d] < 0) continue;
+        double w = (double)cw[d];                                                  // centerStressWeight, level 0
+        if (!S.viscosity.d) w *= (double)S.viscosity.constant;
         else {
             double p[3];
-            S.facePos(face, axis, level, p);
-            fw *= S.density.value(p);
+            S.centerPos(cell[d], 0, p);
+            w *= S.viscosity.value(p);
         }
-        const double dval = fw + diag;
-        if ((n & 31) == lane) {
-            if (n < 32) { col0 = vi; val0 = dval; }
-            else { col1 = vi; val1 = dval; }
+        double coefficient = 2. * S.dt * w;
+        const double cLo = -1. / dx, cHi = 1. / dx;                                // sign / dx
+        // stencil order: low face, high face.  d == 0: (face - 1, self); d == 1: (self, face + 1)
+        coefficient *= d == 0 ? cHi : cLo;
+        if (d == 0) {
+            if (along[0] >= 0) row.add(along[0], coefficient * cLo);
+            diag += coefficient * cHi;
+        } else {
+            diag += coefficient * cLo;
+            if (along[1] >= 0) row.add(along[1], coefficient * cHi);
         }
-        ++n;
-        rhsI += fw * x0[gi];
-        if (lane < n) { stageCol[(long long)lane * stride + r] = col0; stageVal[(long long)lane * stride + r] = val0; }
-        if (32 + lane < n) { stageCol[(long long)(32 + lane) * stride + r] = col1; stageVal[(long long)(32 + lane) * stride + r] = val1; }
-        if (lane == 0) {
-            rowCount[r] = n;
-            rhs[r] = rhsI;
-            diagOut[r] = dval;
-            if (overflow) *overflowFlag = 1;
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int ea = q ? EA1 : EA0, ta = 3 - AXIS - ea;
+#pragma unroll
+        for (int dir = 0; dir < 2; ++dir) {
+            if (ei[q][dir] < 0) continue;
+            double w = (double)ew[q][dir];                                         // edgeStressWeight, level 0; edgeOctreeVolume == 1 here
+            if (!S.viscosity.d) w *= (double)S.viscosity.constant;
+            else {
+                double p[3];
+                S.edgePos(faceToEdge(face, AXIS, ea, dir), ea, 0, p);
+                w *= S.viscosity.value(p);
+            }
+            double coefficient = 4. * S.dt * w;
+            const double cNeg = .5 * -1. / G, cPos = .5 * 1. / G;
+            // own face is edgeToFace(e, ea, AXIS, d2) with d2 = 1 - dir: its coefficient is cPos for dir == 0, cNeg for dir == 1
+            coefficient *= dir == 0 ? cPos : cNeg;
+            // stencil order: face axes ascending (skipping ea), d2 = 0, 1
+            if (AXIS < ta) {
+                if (dir == 0) {   // d2 = 0: the neighbour (face - 1 along ta), d2 = 1: self
+                    if (ownIn[q][dir] && own[q][dir] >= 0) row.add(own[q][dir], coefficient * cNeg);
+                    diag += coefficient * cPos;
+                } else {          // d2 = 0: self, d2 = 1: the neighbour (face + 1 along ta)
+                    diag += coefficient * cNeg;
+                    if (ownIn[q][dir] && own[q][dir] >= 0) row.add(own[q][dir], coefficient * cPos);
+                }
+            }
+#pragma unroll
+            for (int d2 = 0; d2 < 2; ++d2)
+                if (crossIn[q][dir][d2] && cross[q][dir][d2] >= 0) row.add(cross[q][dir][d2], coefficient * (d2 == 0 ? cNeg : cPos));
+            if (!(AXIS < ta)) {
+                if (dir == 0) {
+                    if (ownIn[q][dir] && own[q][dir] >= 0) row.add(own[q][dir], coefficient * cNeg);
+                    diag += coefficient * cPos;
+                } else {
+                    diag += coefficient * cNeg;
+                    if (ownIn[q][dir] && own[q][dir] >= 0) row.add(own[q][dir], coefficient * cPos);
+                }
+            }
         }
+    }
+    double fw = (double)fwRaw;                                                     // velocity control volume; faceOctreeVolume == 1 here
+    if (!S.density.d) fw *= (double)S.density.constant;
+    else {
+        double p[3];
+        S.facePos(face, AXIS, 0, p);
+        fw *= S.density.value(p);
+    }
+    row.add(vi, fw + diag);
+    rhsI = 0;
+    rhsI += fw * x0i;
+    return true;
+}
+
+__global__ void __launch_bounds__(128) k_assemble_simple(const __grid_constant__ DeviceScene S, const RowKey *keys, const double *x0, const float *fwRow,
+                                                         long long rowBegin, long long nLocal, long long stride, int32_t *rowCount,
+                                                         int32_t *stageCol, double *stageVal, double *rhs, double *diagOut,
+                                                         int32_t *rowList, unsigned long long *rowListCount) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool pass = false;
+    if (r < nLocal) {
+        const long long gi = rowBegin + r;
+        const RowKey k = keys[gi];
+        pass = true;
+        if (k.level == 0) {
+            const I3 face = mk3(k.i, k.j, k.k);
+            const double x0i = x0[gi];
+            const float fwi = fwRow[gi];
+            SimpleRowOut row;
+            row.col = stageCol + r;
+            row.val = stageVal + r;
+            row.stride = stride;
+            row.last = 0;
+            double rhsI = 0;
+            bool ok;
+            if (k.axis == 0) ok = buildSimpleRow<0>(S, (int32_t)gi, face, x0i, fwi, row, rhsI);
+            else if (k.axis == 1) ok = buildSimpleRow<1>(S, (int32_t)gi, face, x0i, fwi, row, rhsI);
+            else ok = buildSimpleRow<2>(S, (int32_t)gi, face, x0i, fwi, row, rhsI);
+            if (ok) {
+                pass = false;
+                rowCount[r] = row.n;
+                rhs[r] = rhsI;
+                diagOut[r] = row.last;   // the diagonal is added last (AV.cpp:2768)
+            }
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, pass);   // warp-aggregated append of the rows left for k_assemble
+    if (m) {
+        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(rowListCount, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (pass) rowList[base + __popc(m & ((1u << lane) - 1))] = (int32_t)r;
     }
 }
 
@@ -642,55 +722,69 @@ int avs_stage_system(AvsContext *c, const AvsParams *p) {
     int *flag = (int *)(c->counters.as<unsigned long long>() + 25);
     AVS_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(unsigned long long), c->stream));
     c->nnz = 0;
+    if (c->faceWRow.reserve((size_t)std::max<long long>(c->nRows, 1) * sizeof(float))) return AVS_ERR_ALLOC;
     if (nLocal > 0) {
         unsigned blocks = (unsigned)((nLocal + 127) / 128);
+        k_gather_face_weights<<<(unsigned)((nLocal + 255) / 256), 256, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->rowBegin, nLocal,
+                                                                                     c->faceWRow.as<float>());
+        ++c->launches;
         // AVS_ASM_MINB: resident CTAs per SM the register allocation aims at.  Measured at C3 (stage 'system'): 4 (128 registers,
         // no spills) 36.5 ms, 5: 32.9, 6: 32.2, 8 (64 registers, 788 B spills) 30.8 ms -- the kernel is latency-bound (ncu: 19 % warps
         // active, long-scoreboard stalls), so occupancy beats spills.
         static int minb = -1;
         if (minb < 0) { const char *e = getenv("AVS_ASM_MINB"); minb = e ? atoi(e) : 8; }
-        static int hashRow = -1;   // AVS_ASM_ROW=hash: experimental hashed row accumulator (avs_rowacc.cuh), not yet measured
-        if (hashRow < 0) { const char *e = getenv("AVS_ASM_ROW"); hashRow = (e && e[0] == 'h') ? 1 : 0; }
-        static int warpAsm = -1;   // AVS_ASM=warp selects the warp-per-row kernel (measured 4.6x SLOWER at C3: 140.7 vs 30.5 ms -- one row in
-                                   // flight per warp instead of 32, and its stencils still sit in local memory; kept for the record)
-        if (warpAsm < 0) { const char *e = getenv("AVS_ASM"); warpAsm = (e && strcmp(e, "warp") == 0) ? 1 : 0; }
-        if (warpAsm && !hashRow) {
-            const long long wantBlocks = (nLocal + ASM_WARPS - 1) / ASM_WARPS;
-            const unsigned wblocks = (unsigned)std::min<long long>(wantBlocks, (long long)c->numSMs * 64);
-            k_assemble_warp<<<wblocks, ASM_WARPS * 32, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->x0.as<double>(), c->rowBegin, nLocal, stride,
-                                                                     c->rowCount.as<int32_t>(), c->stageCol.as<int32_t>(), c->stageVal.as<double>(),
-                                                                     c->rhs.as<double>(), c->diag.as<double>(), flag);
-        } else {
+        // Row accumulator of k_assemble (avs_rowacc.cuh): hashed lookup by default, AVS_ASM_ROW=linear for the linear search.  Same
+        // entries in the same order either way.  Measured at C3, stage "system": single-pass assembly 28.9 (hash) vs 30.7 ms (linear);
+        // second pass of the split assembly -- the rows it is left with are the long ones (T-junctions, 26-46 entries) -- 24.1 vs 25.7 ms.
+        static int hashRow = -1;
+        if (hashRow < 0) { const char *e = getenv("AVS_ASM_ROW"); hashRow = (e && e[0] == 'l') ? 0 : 1; }
+        // AVS_ASM=generic: every row through k_assemble (the single-pass assembly of round 1; A/B measurements and the bit-equality test)
+        static int split = -1;
+        if (split < 0) { const char *e = getenv("AVS_ASM"); split = (e && strcmp(e, "generic") == 0) ? 0 : 1; }
+        const int32_t *rowList = nullptr;
+        const unsigned long long *rowListCount = nullptr;
+        if (split) {
+            if (c->asmRowList.reserve((size_t)nLocal * sizeof(int32_t))) return AVS_ERR_ALLOC;
+            unsigned long long *lc = c->counters.as<unsigned long long>() + 27;
+            AVS_CUDA_CHECK(cudaMemsetAsync(lc, 0, sizeof(unsigned long long), c->stream));
+            k_assemble_simple<<<blocks, 128, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->x0.as<double>(), c->faceWRow.as<float>(), c->rowBegin, nLocal, stride,
+                                                           c->rowCount.as<int32_t>(), c->stageCol.as<int32_t>(), c->stageVal.as<double>(),
+                                                           c->rhs.as<double>(), c->diag.as<double>(), c->asmRowList.as<int32_t>(), lc);
+            ++c->launches;
+            rowList = c->asmRowList.as<int32_t>();
+            rowListCount = lc;
+        }
 #define ASM_LAUNCH(M)                                                                                                              \
     do {                                                                                                                           \
     if (hashRow)                                                                                                                   \
-        k_assemble<M, RowAccHash><<<blocks, 128, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->x0.as<double>(), c->rowBegin, nLocal, stride, \
+        k_assemble<M, RowAccHash><<<blocks, 128, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->x0.as<double>(), c->faceWRow.as<float>(), c->rowBegin, nLocal, stride, \
                                                  c->rowCount.as<int32_t>(), c->stageCol.as<int32_t>(), c->stageVal.as<double>(),      \
-                                                 c->rhs.as<double>(), c->diag.as<double>(), flag);                                    \
+                                                 c->rhs.as<double>(), c->diag.as<double>(), flag, rowList, rowListCount);                                    \
     else                                                                                                                           \
-    k_assemble<M, RowAcc><<<blocks, 128, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->x0.as<double>(), c->rowBegin, nLocal, stride,       \
+    k_assemble<M, RowAcc><<<blocks, 128, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->x0.as<double>(), c->faceWRow.as<float>(), c->rowBegin, nLocal, stride,       \
                                                  c->rowCount.as<int32_t>(), c->stageCol.as<int32_t>(), c->stageVal.as<double>(),      \
-                                                 c->rhs.as<double>(), c->diag.as<double>(), flag);                                    \
+                                                 c->rhs.as<double>(), c->diag.as<double>(), flag, rowList, rowListCount);                                    \
     } while (0)
         if (minb >= 8) ASM_LAUNCH(8);
         else if (minb >= 6) ASM_LAUNCH(6);
         else if (minb == 5) ASM_LAUNCH(5);
         else ASM_LAUNCH(4);
 #undef ASM_LAUNCH
-        }
         ++c->launches;
         int64_t nnz = 0;
         int rc = avs_exclusive_scan_i32_to_i64(c, c->rowCount.as<int32_t>(), c->csrPtr.as<int64_t>(), nLocal, &nnz);
         if (rc) return rc;
         c->nnz = nnz;
         AVS_CUDA_CHECK(cudaMemcpyAsync(c->csrPtr.as<long long>() + nLocal, &c->nnz, sizeof(long long), cudaMemcpyHostToDevice, c->stream));
-        int h = 0;
-        AVS_CUDA_CHECK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        unsigned long long hc[3] = {0, 0, 0};   // counters 25 (overflow flag, low word), 26 (stage 11), 27 (rows left for k_assemble)
+        AVS_CUDA_CHECK(cudaMemcpyAsync(hc, c->counters.as<unsigned long long>() + 25, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
         AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        if (h) {
+        if ((int)(hc[0] & 0xffffffffull)) {
             c->lastError = "a matrix row exceeded MAX_ROW entries";
             return AVS_ERR_UNSUPPORTED;
         }
+        c->asmGenericRows = rowListCount ? (long long)hc[2] : nLocal;
+        AVS_TRACE("assembly: %lld of %lld rows through k_assemble", c->asmGenericRows, nLocal);
     } else {
         long long z = 0;
         AVS_CUDA_CHECK(cudaMemcpyAsync(c->csrPtr.p, &z, sizeof(z), cudaMemcpyHostToDevice, c->stream));

@@ -278,7 +278,13 @@ def run_frames(args, w):
     einfos = one_pass(pscenes, pouts)
     torch.cuda.synchronize()
     e_ms = (time.perf_counter() - t0) * 1e3
-    h2d = sum(dense_bytes(sc) for sc in scenes)
+    # face weights are pinned here and read in place, one value per level-0 row, unless AVS_FACEW_UPLOAD=bulk (see main()); rows of
+    # level 0 are not read back per frame here, so the gather is counted at its upper bound of one 32-byte sector per ROW
+    if os.environ.get("AVS_FACEW_UPLOAD") == "bulk":
+        h2d = sum(dense_bytes(sc) for sc in scenes)
+    else:
+        h2d = sum(dense_bytes(sc) - sum(int(np.prod(f.data.shape)) * 4 for f in sc.face_weights if f.data is not None) for sc in scenes)
+        h2d += sum(32 * int(i.octree_dofs) for i in einfos)
     d2h = sum(sum(int(np.prod(v.data.shape)) * 4 for v in sc.vel) for sc in scenes)
 
     tot = torch.tensor([float(work), float(h2d), float(d2h), float(launches)], device=dev, dtype=torch.float64)
@@ -492,7 +498,15 @@ def main():
     elif not args.no_e2e:
         pscene = to_pinned_scene(scene, torch)
         pout = [torch.from_numpy(v.data.copy()).pin_memory() for v in scene.vel]
-        h2d = dense_bytes(scene)   # the 7 dense fields; the output starts from the library's device copy of the input velocity
+        # Host -> device traffic of one step: every dense field is copied whole EXCEPT the three face-weight arrays -- they are
+        # pinned here, so the library reads them through mapped host pointers, one value per level-0 row of the rank
+        # (k_gather_face_weights): counted as one 32-byte PCIe sector per such row, an upper bound (neighbouring rows share sectors).
+        # AVS_FACEW_UPLOAD=bulk restores the whole-array upload (then all 7 dense fields are counted).
+        bulk_facew = os.environ.get("AVS_FACEW_UPLOAD") == "bulk"
+        facew_bytes = sum(int(np.prod(f.data.shape)) * 4 for f in scene.face_weights if f.data is not None)
+        level0_rows = int((solver.keys()[:, 0] == 0).sum()) if not bulk_facew else 0
+        h2d = dense_bytes(scene) if bulk_facew else dense_bytes(scene) - facew_bytes
+        h2d_gather = 0 if bulk_facew else 32 * level0_rows   # whole job (each rank gathers only its own rows)
         d2h = sum(int(np.prod(v.data.shape)) * 4 for v in scene.vel)
         solver.solve(pscene, params, pout)
         barrier()
@@ -509,12 +523,15 @@ def main():
         if world > 1 and not args.gather_output:   # every rank downloads only the z-slab it computed: count what this rank moved
             plane = [int(np.prod(v.data.shape[1:])) for v in scene.vel]
             d2h = sum(plane[a] * max(0, solver.output_slab(a)[1] - solver.output_slab(a)[0]) * 4 for a in range(3))
-        if world > 1:   # whole-job bytes (every rank uploads the full fields: labelling is replicated)
+        if world > 1:   # whole-job bytes (every rank uploads the full surface / velocity fields: labelling is replicated)
             tb = torch.tensor([float(h2d), float(d2h)], device=dev, dtype=torch.float64)
             dist.all_reduce(tb)
             h2d, d2h = (float(v) for v in tb.tolist())
+        h2d += h2d_gather
         e2e = {"value": N * einfo.iterations / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": e_ms,
+               "face_weights": ("whole arrays uploaded" if bulk_facew else
+                                f"read in place from pinned host memory: one value per level-0 row ({level0_rows} rows, counted at 32 B each)"),
                "stage_ms": {k2: round(v, 3) for k2, v in einfo.stage_ms.items()}}
         del pscene, pout
 

@@ -2,8 +2,9 @@
 
 TEST INFRASTRUCTURE ONLY: imported by ``tests/``, ``__graft_entry__.smoke()`` and
 ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs.  The product package never
-imports this module.  Parity status of the oracle itself: "parity unpinned" (the reference
-needs Houdini + Eigen, ships no tests or fixtures) -- see the header of avs_oracle.cpp.
+imports this module.  Parity status of the oracle itself: pinned bit for bit to the reference's own
+sources compiled against the stand-ins of oracle/mock_hdk (oracle/_ref, tests/test_reference_pin.py);
+Houdini's and Eigen's behaviour is assumed -- see the header of avs_oracle.cpp.
 
 Scenes are duck-typed: any object with the attributes used in ``_scene_struct`` works
 (``adaptiveviscositysolver_b200.scenes.Scene`` is what the tests pass).  Arrays are numpy

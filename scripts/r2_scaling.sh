@@ -18,7 +18,7 @@ if [ "$N" = "2" ]; then
 timeout 600 python -m pytest tests/test_gpu_multi.py tests/test_gpu_inprocess_multi.py tests/test_gpu_hdk_shim.py -q --tb=short 2>&1 | tail -12 > gpurun_out/r2s_pytest_multi_g2.log; tail -4 gpurun_out/r2s_pytest_multi_g2.log
 fi
 run c3 --workload c3 --steps 3 --warmup 3 --no-cpu-baseline
-AVS_PCG_KERNEL=v1 run c3_v1 --workload c3 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e
+if [ "$N" = "2" ]; then AVS_PCG_KERNEL=v1 run c3_v1 --workload c3 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e; fi
 run c4 --workload c4 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e
 if [ "$N" = "2" ]; then AVS_PCG_KERNEL=v1 run c4_v1 --workload c4 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e; fi
 if [ "$N" = "8" ]; then run c5 --workload c5 --steps 3 --warmup 3 --no-cpu-baseline; run c3_gather --workload c3 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --gather-output; fi
