@@ -151,10 +151,10 @@ void avs_destroy(AvsContext *c) {
     cudaStreamSynchronize(c->stream);
     avs_dist_destroy(c);
     DevBuf *bufs[] = {&c->fullSolution, &c->inSurface, &c->inVisc, &c->inDens, &c->inColl, &c->centerW, &c->tiles, &c->brickCount, &c->brickOffset,
-                      &c->scanTmp, &c->counters, &c->rowKeys, &c->coarseRows, &c->asmRowList, &c->faceWRow, &c->x0, &c->rhs, &c->solution, &c->rowCount, &c->rowOffset,
+                      &c->scanTmp, &c->counters, &c->rowKeys, &c->coarseRows, &c->asmRowList, &c->faceWRow, &c->rowMass, &c->x0, &c->rhs, &c->solution, &c->rowCount, &c->rowOffset,
                       &c->csrPtr, &c->csrCol, &c->csrVal, &c->A.sliceOff, &c->A.val, &c->A.col, &c->A.invDiag, &c->A.meta, &c->cg.pcgState, &c->cg.sliceHalo, &c->cg.sliceFlag, &c->cg.sliceIndex, &c->cg.boundaryList, &c->cg.pcgLocal,
                       &c->cg.x, &c->cg.r, &c->cg.p, &c->cg.t, &c->cg.partials, &c->cg.scalars, &c->cgRhs,
-                      &c->stageCol, &c->stageVal, &c->diag, &c->slicePairs, &c->edgeTiles, &c->solidW, &c->signA, &c->signB, &c->bandList, &c->brickCost, &c->brickCostPrefix,
+                      &c->stageCol, &c->stageVal, &c->diag, &c->slicePairs, &c->edgeTiles, &c->tileFlags, &c->tileLists, &c->nodeTileList, &c->solidW, &c->signA, &c->signB, &c->bandList, &c->brickCost, &c->brickCostPrefix,
                       &c->geoCount, &c->geoOffset, &c->geoPos, &c->geoScale, &c->geoLevel};
     for (DevBuf *b : bufs) b->release();
     for (int a = 0; a < 3; ++a) {
@@ -331,22 +331,41 @@ static int runAssemble(AvsContext *c, const AvsFields *in, const AvsParams *p, A
     { NvtxRange nv("Build Regular Grid Velocity Labels"); AVS_TRACE("avs_stage_regular_labels"); if ((rc = avs_stage_regular_labels(c))) return rc; }
     cudaEventRecord(c->ev[AVS_STAGE_OCTREE_LABELS], c->stream);
     { NvtxRange nv("Build Octree Velocity and Stress Labels"); AVS_TRACE("avs_stage_octree_labels"); if ((rc = avs_stage_octree_labels(c))) return rc; }
-    cudaStreamWaitEvent(c->stream, c->evUploadDone, 0);  // velocity + face weights have landed
-    cudaEventRecord(c->ev[AVS_STAGE_RESTRICTION], c->stream);
-    { NvtxRange nv("Interpolate Regular Grid Velocities at Octree Velocity Faces"); AVS_TRACE("avs_stage_restriction"); if ((rc = avs_stage_restriction(c))) return rc; }
+    // The assembly needs everything but the velocity (u^n only enters the right-hand side, through its mass term), so it runs BEFORE
+    // the restriction: the velocity's host -> device copy has labelling + assembly to hide under (avs_stage_upload).
     cudaEventRecord(c->ev[AVS_STAGE_SYSTEM], c->stream);
-    NvtxRange nvSystem("Build Edge/Cell Stress Stencils + Build Octree Linear System");
-    AVS_TRACE("avs_stage_system"); if ((rc = avs_stage_system(c, p))) return rc;
-    // the CG's matrix format is part of "Build Octree Linear System" (the reference's setFromTriplets, AV.cpp:614)
-    c->nHalo = 0;
-    c->haloIndex = nullptr;
-    AVS_TRACE("sjds build");
-    if (c->nranks > 1 && (rc = avs_dist_build_halo(c))) return rc;
-    if ((rc = avs_sell_from_stage(c, c->A, c->rowEnd - c->rowBegin, c->nnz, c->rowCount.as<int32_t>(), c->stageCol.as<int32_t>(),
-                                  c->stageVal.as<double>(), c->stageStride, c->diag.as<double>(), p->precision,
-                                  c->rowBegin, c->rowEnd, c->haloIndex))) return rc;
+    {
+        NvtxRange nvSystem("Build Edge/Cell Stress Stencils + Build Octree Linear System");
+        AVS_TRACE("avs_stage_system"); if ((rc = avs_stage_system(c, p))) return rc;
+        // the CG's matrix format is part of "Build Octree Linear System" (the reference's setFromTriplets, AV.cpp:614)
+        c->nHalo = 0;
+        c->haloIndex = nullptr;
+        AVS_TRACE("sjds build");
+        if (c->nranks > 1 && (rc = avs_dist_build_halo(c))) return rc;
+        if ((rc = avs_sell_from_stage(c, c->A, c->rowEnd - c->rowBegin, c->nnz, c->rowCount.as<int32_t>(), c->stageCol.as<int32_t>(),
+                                      c->stageVal.as<double>(), c->stageStride, c->diag.as<double>(), p->precision,
+                                      c->rowBegin, c->rowEnd, c->haloIndex))) return rc;
+    }
+    cudaStreamWaitEvent(c->stream, c->evUploadDone, 0);  // the velocity has landed
+    cudaEventRecord(c->ev[AVS_STAGE_RESTRICTION], c->stream);
+    {
+        NvtxRange nv("Interpolate Regular Grid Velocities at Octree Velocity Faces");
+        AVS_TRACE("avs_stage_restriction");
+        if ((rc = avs_stage_restriction(c))) return rc;
+        if ((rc = avs_finish_rhs(c))) return rc;
+    }
     cudaEventRecord(c->ev[AVS_STAGE_SOLVE], c->stream);
-    collectStageTimes(c, res, AVS_STAGE_UPLOAD, AVS_STAGE_SYSTEM);
+    collectStageTimes(c, res, AVS_STAGE_UPLOAD, AVS_STAGE_REGULAR_LABELS);
+    {   // octree labels -> system -> restriction -> (solve): events in time order
+        const int order[4] = {AVS_STAGE_OCTREE_LABELS, AVS_STAGE_SYSTEM, AVS_STAGE_RESTRICTION, AVS_STAGE_SOLVE};
+        cudaEventSynchronize(c->ev[AVS_STAGE_SOLVE]);
+        for (int k = 0; k < 3; ++k) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->ev[order[k]], c->ev[order[k + 1]]);
+            res->stage_ms[order[k]] = ms;
+            res->stage_ms[AVS_STAGE_TOTAL] += ms;
+        }
+    }
     fillCounts(c, res);
     return AVS_OK;
 }
@@ -751,7 +770,18 @@ int avs_create_multi(const int32_t *devices, int32_t n, int32_t time_spmv, AvsMu
     m->group = n > 1 ? avs_local_group_create(n, devs.data()) : nullptr;
     for (int r = 0; r < n; ++r)
         for (int q = 0; q < r; ++q)
-            if (devs[q] == devs[r]) g_avsAsyncAlloc = true;   // ranks share a device: no device-synchronising allocator calls from now on
+            if (devs[q] == devs[r]) {
+                g_avsAsyncAlloc = true;   // ranks share a device: no device-synchronising allocator calls from now on
+                // ... and no lazily loaded kernels: the first launch of a kernel may synchronise the context, which cannot complete
+                // while the peer rank's kernel on the SAME device spins waiting for this rank (tests/conftest.py sets the variable)
+                const char *ml = getenv("CUDA_MODULE_LOADING");
+                static bool warned = false;
+                if (!warned && !(ml && strcmp(ml, "EAGER") == 0)) {
+                    fprintf(stderr, "[avs] avs_create_multi: ranks share a GPU; set CUDA_MODULE_LOADING=EAGER before CUDA initialises "
+                                    "(lazy kernel loading can stall a rank until its peer's spin-wait times out)\n");
+                    warned = true;
+                }
+            }
     m->ctx.assign(n, nullptr);
     m->status.assign(n, AVS_OK);
     m->res.resize(n);
@@ -816,12 +846,16 @@ int avs_solve_multi(AvsMulti *m, const AvsFields *in, const AvsParams *p, AvsVel
     }
     for (auto &t : pool) t.join();
     *res = m->res[0];
-    int rc = AVS_OK;
+    // the rank that failed FIRST is the one to report: its peers only see their barriers give up afterwards
+    int rc = AVS_OK, primary = -1;
     for (int r = 0; r < m->n; ++r)
-        if (m->status[r] != AVS_OK && rc == AVS_OK) {
-            rc = m->status[r];
-            snprintf(g_lastError, sizeof(g_lastError), "rank %d: %s", r, errors[r].c_str());
-        }
+        if (m->status[r] != AVS_OK && (primary < 0 || (errors[primary].find("in-process group") != std::string::npos &&
+                                                        errors[r].find("in-process group") == std::string::npos)))
+            primary = r;
+    if (primary >= 0) {
+        rc = m->status[primary];
+        snprintf(g_lastError, sizeof(g_lastError), "rank %d: %s (%s)", primary, avs_status_string(rc), errors[primary].c_str());
+    }
     // stage times: the slowest rank of every stage (the ranks run side by side)
     for (int r = 1; r < m->n; ++r)
         for (int i = 0; i < AVS_STAGE_COUNT; ++i) res->stage_ms[i] = std::max(res->stage_ms[i], m->res[r].stage_ms[i]);

@@ -111,6 +111,7 @@ struct AvsContext {
     DevBuf signA, signB;    // sign classes of the surface SDF neighbourhoods (weights shortcut)
     DevBuf brickCount, brickCost, brickCostPrefix, brickOffset, scanTmp, counters;
     DevBuf rowKeys;         // RowKey[n]
+    DevBuf rowMass;                         // fp64 [local rows]: M_u = rho V_face of every row (rhs += M_u u^n, k_finish_rhs)
     DevBuf faceWRow;                        // fp32 [N]: the face weight of every level-0 row (k_gather_face_weights)
     DevBuf asmRowList;                      // split assembly: local ids of the rows left for the generic kernel
     DevBuf coarseRows;                      // ids of the rows of level >= 3 (restriction: one CTA per such row)
@@ -118,6 +119,9 @@ struct AvsContext {
     DevBuf rowCount, rowOffset; // assembly scratch (int32 / int64)
     DevBuf csrPtr, csrCol, csrVal;  // canonical CSR of the local rows (int64 / int32 / fp64); col/val built lazily
     DevBuf stageCol, stageVal, diag; // assembly staging area (column-major, MAX_ROW deep) and the diagonal
+    Grid3<uint8_t> tileFlagsGrid = {nullptr, {0, 0, 0}};   // view of tileFlags for the current solve (d == nullptr: dense labelling ran)
+    DevBuf nodeTileList;                 // level-0 node tiles of the interpolator's pyramid (avs_prolong.cu)
+    DevBuf tileFlags, tileLists;         // level-0 labelling: per-16^3-tile flags (ACTIVE / non-UP present) and the compacted tile lists
     DevBuf slicePairs, edgeTiles, solidW; // per-solve scratch kept across calls (no cudaMalloc/cudaFree in steady state)
     DevBuf geoCount, geoOffset, geoPos, geoScale, geoLevel;  // octree geometry dump (OG.cpp:245-308), built on request
     bool haveOctree = false;
@@ -167,6 +171,7 @@ int avs_octree_points(AvsContext *c, int64_t *countOut);
 int avs_slab_cuts(AvsContext *c);
 void avs_slab_range(const AvsContext *c, int axis, int q, int *z0, int *z1);
 int avs_stage_octree_labels(AvsContext *c);
+int avs_finish_rhs(AvsContext *c);   // rhs += M_u u^n once the restriction has run (after the assembly)
 int avs_stage_restriction(AvsContext *c, bool allRows = false);   // nranks > 1: only the rows this rank owns unless allRows
 int avs_stage_system(AvsContext *c, const AvsParams *p);
 int avs_stage_solve(AvsContext *c, const AvsParams *p, AvsResult *res);

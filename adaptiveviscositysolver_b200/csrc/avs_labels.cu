@@ -689,11 +689,8 @@ __global__ void k_classify_regular(const __grid_constant__ DeviceScene S, int ax
     });
 }
 
-// classifyOctreeVelocityFaces (AV.cpp:1167-1323)
-__global__ void k_classify_faces(const __grid_constant__ DeviceScene S, int level, int axis, Grid3<uint8_t> tiles) {
-    const Grid3<int32_t> g = S.face[level][axis];
-    forCells(g.n, [&](int x, int y, int z, size_t idx, bool ok) {
-        if (!ok) return;
+// classifyOctreeVelocityFaces (AV.cpp:1167-1323): label of one face
+__device__ __forceinline__ int32_t classifyFace(const DeviceScene &S, int level, int axis, const Grid3<uint8_t> &tiles, int x, int y, int z) {
     int32_t out = F_UNASSIGNED;
     I3 face = mk3(x, y, z);
     const Grid3<uint8_t> &lab = S.label[level];
@@ -717,7 +714,13 @@ __global__ void k_classify_faces(const __grid_constant__ DeviceScene S, int leve
                 out = F_FLUID;
         }
     }
-    g.d[idx] = out;
+    return out;
+}
+__global__ void k_classify_faces(const __grid_constant__ DeviceScene S, int level, int axis, Grid3<uint8_t> tiles) {
+    const Grid3<int32_t> g = S.face[level][axis];
+    forCells(g.n, [&](int x, int y, int z, size_t idx, bool ok) {
+        if (!ok) return;
+        g.d[idx] = classifyFace(S, level, axis, tiles, x, y, z);
     });
 }
 
@@ -736,13 +739,10 @@ __global__ void k_mark_edge_tiles(Grid3<uint8_t> lab, Grid3<uint8_t> t0, Grid3<u
     });
 }
 
-// classifyEdgeStresses (AV.cpp:1325-1405)
-__global__ void k_classify_edges(const __grid_constant__ DeviceScene S, int level, int axis, Grid3<uint8_t> tiles, unsigned long long *counter) {
-    const Grid3<int8_t> g = S.edge[level][axis];
-    forCells(g.n, [&](int x, int y, int z, size_t idx, bool ok) {
-    const bool in = ok;
+// classifyEdgeStresses (AV.cpp:1325-1405): label of one edge
+__device__ __forceinline__ int8_t classifyEdge(const DeviceScene &S, int level, int axis, const Grid3<uint8_t> &tiles, int x, int y, int z) {
     int8_t out = F_UNASSIGNED;
-    if (in && tileOccupied(tiles, x, y, z)) {
+    if (tileOccupied(tiles, x, y, z)) {
         const Grid3<uint8_t> &lab = S.label[level];
         I3 edge = mk3(x, y, z);
         int vr[3];
@@ -765,23 +765,144 @@ __global__ void k_classify_edges(const __grid_constant__ DeviceScene S, int leve
             else out = F_FLUID;
         }
     }
-    if (in) g.d[idx] = out;
-    countWarp(in && out == F_FLUID, counter);
+    return out;
+}
+__global__ void k_classify_edges(const __grid_constant__ DeviceScene S, int level, int axis, Grid3<uint8_t> tiles, unsigned long long *counter) {
+    const Grid3<int8_t> g = S.edge[level][axis];
+    forCells(g.n, [&](int x, int y, int z, size_t idx, bool ok) {
+        int8_t out = F_UNASSIGNED;
+        if (ok) {
+            out = classifyEdge(S, level, axis, tiles, x, y, z);
+            g.d[idx] = out;
+        }
+        countWarp(ok && out == F_FLUID, counter);
     });
 }
 
-// classifyCenterStresses (AV.cpp:1407-1443)
-__global__ void k_classify_centers(const __grid_constant__ DeviceScene S, int level, unsigned long long *counter) {
-    const Grid3<int8_t> g = S.center[level];
-    forCells(g.n, [&](int x, int y, int z, size_t idx, bool ok) {
-    const bool in = ok;
+// classifyCenterStresses (AV.cpp:1407-1443): label of one cell centre
+__device__ __forceinline__ int8_t classifyCenter(const DeviceScene &S, int level, int x, int y, int z, size_t idx) {
     int8_t out = F_UNASSIGNED;
-    if (in && S.label[level].d[idx] == L_ACTIVE) {
+    if (S.label[level].d[idx] == L_ACTIVE) {
         if (level != 0) out = F_FLUID;
         else if (S.centerW.get(mk3(x, y, z)) > 0.f) out = F_FLUID;
     }
-    if (in) g.d[idx] = out;
-    countWarp(in && out == F_FLUID, counter);
+    return out;
+}
+__global__ void k_classify_centers(const __grid_constant__ DeviceScene S, int level, unsigned long long *counter) {
+    const Grid3<int8_t> g = S.center[level];
+    forCells(g.n, [&](int x, int y, int z, size_t idx, bool ok) {
+        int8_t out = F_UNASSIGNED;
+        if (ok) {
+            out = classifyCenter(S, level, x, y, z, idx);
+            g.d[idx] = out;
+        }
+        countWarp(ok && out == F_FLUID, counter);
+    });
+}
+
+// ---- level 0 on the tiles that can hold anything but the default label ----------------------------------------------------------
+// Level 0 is 87 % of all cells, but only a band around the surface is refined down to it: deep inside the liquid every cell is UP
+// and every face / edge / centre label is UNASSIGNED, outside the reference never looks (unoccupied tiles keep UNASSIGNED,
+// AV.cpp:886-1085).  So the level-0 label grids are memset to UNASSIGNED and the classification runs only on the 16^3 tiles where
+// another label is possible -- decided per tile from two flags of the cell tile (any ACTIVE cell / any cell that is not UP) and the
+// reference's own occupancy maps.  Same per-sample functions as the dense kernels above, hence the same labels.
+enum : uint8_t { TILE_HAS_ACTIVE = 1, TILE_HAS_NON_UP = 2 };
+
+// One CTA per cell tile: the two flags, and findOccupiedEdgeStressTiles (the 4 a-edges of every ACTIVE cell, a = 0,1,2) on the way.
+__global__ void k_tile_flags(Grid3<uint8_t> lab, Grid3<uint8_t> flags, Grid3<uint8_t> t0, Grid3<uint8_t> t1, Grid3<uint8_t> t2) {
+    const int tx = (int)blockIdx.x, ty = (int)blockIdx.y, tz = (int)blockIdx.z;
+    const int y = ty * AVS_TILE + (int)(threadIdx.x & 15), z = tz * AVS_TILE + (int)(threadIdx.x >> 4);
+    int mine = 0;
+    if (y < lab.n[1] && z < lab.n[2]) {
+        const int x0 = tx * AVS_TILE, x1 = min(x0 + AVS_TILE, lab.n[0]);
+        const size_t row = (size_t)lab.n[0] * ((size_t)y + (size_t)lab.n[1] * (size_t)z);
+        for (int x = x0; x < x1; ++x) {
+            const uint8_t l = lab.d[row + x];
+            if (l != L_UP) mine |= TILE_HAS_NON_UP;
+            if (l == L_ACTIVE) {
+                mine |= TILE_HAS_ACTIVE;
+                const I3 c = mk3(x, y, z);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    markTile(t0, cellToEdge(c, 0, e));
+                    markTile(t1, cellToEdge(c, 1, e));
+                    markTile(t2, cellToEdge(c, 2, e));
+                }
+            }
+        }
+    }
+    // __syncthreads_or returns "any thread's predicate is non-zero", not the bitwise OR: one vote per flag
+    const int anyActive = __syncthreads_or(mine & TILE_HAS_ACTIVE), anyNonUp = __syncthreads_or(mine & TILE_HAS_NON_UP);
+    if (threadIdx.x == 0) flags.d[flags.lin(tx, ty, tz)] = (uint8_t)((anyActive ? TILE_HAS_ACTIVE : 0) | (anyNonUp ? TILE_HAS_NON_UP : 0));
+}
+
+// Compacts the tiles of one grid that need classification into `list` (packed 10-bit coordinates; order irrelevant).
+//   kind 0: face tiles of `axis` -- occupied (AV.cpp:886-943) and an adjacent cell may be other than UP, or the tile touches the
+//           low / high end of the grid on `axis` (domain-boundary faces are OUTSIDE, AV.cpp:1210-1215)
+//   kind 1: edge tiles -- occupied (AV.cpp:1002-1057)          kind 2: cell tiles with an ACTIVE cell
+__global__ void k_tile_list(Grid3<uint8_t> occ, Grid3<uint8_t> flags, int kind, int axis, uint32_t *list, unsigned int *count) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= occ.count()) return;
+    const int tx = (int)(i % occ.n[0]), ty = (int)((i / occ.n[0]) % occ.n[1]), tz = (int)(i / ((size_t)occ.n[0] * occ.n[1]));
+    bool take;
+    if (kind == 2) take = (flags.d[i] & TILE_HAS_ACTIVE) != 0;   // occ == flags grid
+    else if (kind == 1) take = occ.d[i] != 0;
+    else {
+        take = false;
+        if (occ.d[i]) {
+            int t[3] = {tx, ty, tz};
+            const bool inGrid = tx < flags.n[0] && ty < flags.n[1] && tz < flags.n[2];
+            take = !inGrid || t[axis] == 0 || (flags.d[flags.lin(tx, ty, tz)] & TILE_HAS_NON_UP);
+            if (!take) {
+                --t[axis];
+                take = (flags.d[flags.lin(t[0], t[1], t[2])] & TILE_HAS_NON_UP) != 0;
+            }
+        }
+    }
+    if (take) list[atomicAdd(count, 1u)] = (uint32_t)tx | ((uint32_t)ty << 10) | ((uint32_t)tz << 20);
+}
+
+// one CTA (256 threads = 16 x 16) per listed tile, 16 planes each; launched with an upper bound of CTAs
+template <class F>
+__device__ __forceinline__ void forTileSamples(const uint32_t *list, const unsigned int *count, const int n[3], F f) {
+    if (blockIdx.x >= *count) return;
+    const uint32_t t = list[blockIdx.x];
+    const int x = (int)(t & 1023u) * AVS_TILE + (int)(threadIdx.x & 15), y = (int)((t >> 10) & 1023u) * AVS_TILE + (int)(threadIdx.x >> 4);
+    const int z0 = (int)(t >> 20) * AVS_TILE;
+    const bool inxy = x < n[0] && y < n[1];
+    for (int dz = 0; dz < AVS_TILE; ++dz) {
+        const int z = z0 + dz;
+        if (z >= n[2]) return;   // uniform over the CTA
+        f(x, y, z, (size_t)x + (size_t)n[0] * ((size_t)y + (size_t)n[1] * (size_t)z), inxy);
+    }
+}
+__global__ void k_classify_faces_tiles(const __grid_constant__ DeviceScene S, int axis, Grid3<uint8_t> tiles, const uint32_t *list, const unsigned int *count) {
+    const Grid3<int32_t> g = S.face[0][axis];
+    forTileSamples(list, count, g.n, [&](int x, int y, int z, size_t idx, bool ok) {
+        if (ok) g.d[idx] = classifyFace(S, 0, axis, tiles, x, y, z);
+    });
+}
+__global__ void k_classify_edges_tiles(const __grid_constant__ DeviceScene S, int axis, Grid3<uint8_t> tiles, const uint32_t *list, const unsigned int *count,
+                                       unsigned long long *counter) {
+    const Grid3<int8_t> g = S.edge[0][axis];
+    forTileSamples(list, count, g.n, [&](int x, int y, int z, size_t idx, bool ok) {
+        int8_t out = F_UNASSIGNED;
+        if (ok) {
+            out = classifyEdge(S, 0, axis, tiles, x, y, z);
+            g.d[idx] = out;
+        }
+        countWarp(ok && out == F_FLUID, counter);
+    });
+}
+__global__ void k_classify_centers_tiles(const __grid_constant__ DeviceScene S, const uint32_t *list, const unsigned int *count, unsigned long long *counter) {
+    const Grid3<int8_t> g = S.center[0];
+    forTileSamples(list, count, g.n, [&](int x, int y, int z, size_t idx, bool ok) {
+        int8_t out = F_UNASSIGNED;
+        if (ok) {
+            out = classifyCenter(S, 0, x, y, z, idx);
+            g.d[idx] = out;
+        }
+        countWarp(ok && out == F_FLUID, counter);
     });
 }
 
@@ -949,10 +1070,31 @@ __device__ __forceinline__ void brickThreadCount(const DeviceScene &S, int level
     }
 }
 
+// `tileFlags` (level 0 only, may be null): flags of the 16^3 cell tiles (k_tile_flags).  A level-0 face is a DOF only next to an ACTIVE
+// cell, so a brick whose tile and whose three lower neighbour tiles hold no ACTIVE cell has no rows: it is not read at all.
 __global__ void k_brick_count(const __grid_constant__ DeviceScene S, const __grid_constant__ BrickLayout bl, int level, int32_t *brickCount,
-                              int32_t *brickCost) {
+                              int32_t *brickCost, Grid3<uint8_t> tileFlags) {
     int b[3];
     brickCoord(bl, level, blockIdx.x, b);
+    if (tileFlags.d) {
+        const int t[3] = {b[0] * BRICK / AVS_TILE, b[1] * BRICK / AVS_TILE, b[2] * BRICK / AVS_TILE};
+        bool any = (tileFlags.d[tileFlags.lin(t[0], t[1], t[2])] & TILE_HAS_ACTIVE) != 0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (any || t[a] == 0 || (b[a] * BRICK) % AVS_TILE != 0) continue;   // only the brick at the low end of a tile sees the tile below
+            int q[3] = {t[0], t[1], t[2]};
+            --q[a];
+            any = (tileFlags.d[tileFlags.lin(q[0], q[1], q[2])] & TILE_HAS_ACTIVE) != 0;
+        }
+        if (!any) {   // uniform over the CTA
+            if (threadIdx.x == 0) {
+                const long long pos = brickPos(bl, level, b);
+                brickCount[pos] = 0;
+                brickCost[pos] = 0;
+            }
+            return;
+        }
+    }
     int32_t vals[6];
     int na[3];
     brickThreadCount(S, level, b, threadIdx.x, vals, na);
@@ -1114,6 +1256,7 @@ __global__ void k_find_cuts(const long long *costPrefix, const long long *rowOff
 int avs_stage_octree_labels(AvsContext *c) {
     DeviceScene &S = c->S;
     const int L = S.levels;
+    c->tileFlagsGrid.d = nullptr;
     if (L == 0) {  // no ACTIVE cell at all (the reference asserts this away, OG.cpp:206): an empty system
         c->nRows = 0;
         c->nEdge = c->nCenter = 0;
@@ -1154,18 +1297,56 @@ int avs_stage_octree_labels(AvsContext *c) {
         if (c->center[l].reserve(ce.count())) return AVS_ERR_ALLOC;
         ce.d = c->center[l].as<int8_t>();
     }
+    // AVS_LABELS=dense: level 0 through the dense sweeps as well (round 1; A/B measurements and the bit-equality test)
+    static int dense0 = -1;
+    if (dense0 < 0) { const char *e = getenv("AVS_LABELS"); dense0 = (e && strcmp(e, "dense") == 0) ? 1 : 0; }
+    Grid3<uint8_t> tileFlags;
+    tileFlags.d = nullptr;
+    tileFlags.n[0] = tileFlags.n[1] = tileFlags.n[2] = 0;
     for (int l = 0; l < L; ++l) {
-        for (int a = 0; a < 3; ++a) LAUNCH_3D(c, k_classify_faces, S.face[l][a].n, S, l, a, t0[a]);
         Grid3<uint8_t> te[3];
         int res[3][3];
         for (int a = 0; a < 3; ++a)
             for (int k = 0; k < 3; ++k) res[a][k] = S.edge[l][a].n[k];
         int rc = tileGrid(c, edgeTiles, te, res);
         if (rc) return rc;
+        if (l == 0 && !dense0) {
+            // ---- level 0, tile-culled (see k_tile_flags) ----
+            for (int k = 0; k < 3; ++k) tileFlags.n[k] = (S.label[0].n[k] + AVS_TILE - 1) / AVS_TILE;
+            size_t listCap = tileFlags.count();
+            for (int a = 0; a < 3; ++a) listCap = std::max(listCap, std::max(t0[a].count(), te[a].count()));
+            if (tileFlags.n[0] > 1023 || tileFlags.n[1] > 1023 || tileFlags.n[2] > 1023) return AVS_ERR_UNSUPPORTED;   // packed tile coordinates
+            if (c->tileFlags.reserve(tileFlags.count()) || c->tileLists.reserve(7 * listCap * sizeof(uint32_t))) return AVS_ERR_ALLOC;
+            tileFlags.d = c->tileFlags.as<uint8_t>();
+            unsigned int *lcnt = (unsigned int *)(cnt + 32);   // 7 list lengths in counter slots 32..35
+            AVS_CUDA_CHECK(cudaMemsetAsync(lcnt, 0, 8 * sizeof(unsigned int), c->stream));
+            k_tile_flags<<<dim3((unsigned)tileFlags.n[0], (unsigned)tileFlags.n[1], (unsigned)tileFlags.n[2]), 256, 0, c->stream>>>(S.label[0], tileFlags, te[0],
+                                                                                                                        te[1], te[2]);
+            ++c->launches;
+            uint32_t *lists = c->tileLists.as<uint32_t>();
+            for (int a = 0; a < 3; ++a) {
+                AVS_CUDA_CHECK(cudaMemsetAsync(S.face[0][a].d, 0xFF, S.face[0][a].count() * sizeof(int32_t), c->stream));   // F_UNASSIGNED
+                AVS_CUDA_CHECK(cudaMemsetAsync(S.edge[0][a].d, 0xFF, S.edge[0][a].count(), c->stream));
+            }
+            AVS_CUDA_CHECK(cudaMemsetAsync(S.center[0].d, 0xFF, S.center[0].count(), c->stream));
+            for (int a = 0; a < 3; ++a) {
+                k_tile_list<<<(unsigned)((t0[a].count() + 255) / 256), 256, 0, c->stream>>>(t0[a], tileFlags, 0, a, lists + (size_t)a * listCap, lcnt + a);
+                k_classify_faces_tiles<<<(unsigned)t0[a].count(), 256, 0, c->stream>>>(S, a, t0[a], lists + (size_t)a * listCap, lcnt + a);
+                k_tile_list<<<(unsigned)((te[a].count() + 255) / 256), 256, 0, c->stream>>>(te[a], tileFlags, 1, a, lists + (size_t)(3 + a) * listCap, lcnt + 3 + a);
+                k_classify_edges_tiles<<<(unsigned)te[a].count(), 256, 0, c->stream>>>(S, a, te[a], lists + (size_t)(3 + a) * listCap, lcnt + 3 + a, cnt + 17);
+                c->launches += 4;
+            }
+            k_tile_list<<<(unsigned)((tileFlags.count() + 255) / 256), 256, 0, c->stream>>>(tileFlags, tileFlags, 2, 0, lists + 6 * listCap, lcnt + 6);
+            k_classify_centers_tiles<<<(unsigned)tileFlags.count(), 256, 0, c->stream>>>(S, lists + 6 * listCap, lcnt + 6, cnt + 18);
+            c->launches += 2;
+            continue;
+        }
+        for (int a = 0; a < 3; ++a) LAUNCH_3D(c, k_classify_faces, S.face[l][a].n, S, l, a, t0[a]);
         LAUNCH_3D(c, k_mark_edge_tiles, S.label[l].n, S.label[l], te[0], te[1], te[2]);
         for (int a = 0; a < 3; ++a) LAUNCH_3D(c, k_classify_edges, S.edge[l][a].n, S, l, a, te[a], cnt + 17);
         LAUNCH_3D(c, k_classify_centers, S.center[l].n, S, l, cnt + 18);
     }
+    c->tileFlagsGrid = tileFlags;
     // (stress DOF counts -- the reference numbers them, AV.cpp:1632-1715 -- were accumulated by the classify kernels)
     // numbering
     BrickLayout bl;
@@ -1184,7 +1365,9 @@ int avs_stage_octree_labels(AvsContext *c) {
     if (c->brickOffset.reserve((size_t)total * sizeof(long long))) return AVS_ERR_ALLOC;
     for (int l = 0; l < L; ++l) {
         unsigned nb = (unsigned)((long long)bl.nb[l][0] * bl.nb[l][1] * bl.nb[l][2]);
-        k_brick_count<<<nb, 256, 0, c->stream>>>(S, bl, l, c->brickCount.as<int32_t>(), c->brickCost.as<int32_t>());
+        Grid3<uint8_t> cull = tileFlags;
+        if (l > 0) cull.d = nullptr;
+        k_brick_count<<<nb, 256, 0, c->stream>>>(S, bl, l, c->brickCount.as<int32_t>(), c->brickCost.as<int32_t>(), cull);
         ++c->launches;
     }
     int64_t nRows = 0;

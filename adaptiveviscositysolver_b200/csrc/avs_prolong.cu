@@ -47,9 +47,7 @@ __device__ __forceinline__ float octVel(const DeviceScene &S, const double *sol,
 }
 
 // setActiveNodes (VFI.cpp:118-188) + sampleActiveNodes (VFI.cpp:190-286)
-__global__ void k_node_sample(const __grid_constant__ DeviceScene S, NodeLevel nl, const double *sol, int level, int zLo) {
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y), z = (int)blockIdx.z + zLo;
-    if (x >= nl.label.n[0] || y >= nl.label.n[1]) return;
+__device__ __forceinline__ void nodeSample(const DeviceScene &S, const NodeLevel &nl, const double *sol, int level, int x, int y, int z) {
     const size_t idx = nl.label.lin(x, y, z);
     const I3 node = mk3(x, y, z);
     // cheap reject: a node with an active face is a corner of an ACTIVE cell
@@ -119,9 +117,7 @@ __global__ void k_node_bubble(NodeLevel child, NodeLevel par, int zLo) {
 }
 
 // finishIncompleteNodes (VFI.cpp:357-567)
-__global__ void k_node_finish(const __grid_constant__ DeviceScene S, NodeLevel nl, const double *sol, int level, int zLo) {
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y), z = (int)blockIdx.z + zLo;
-    if (x >= nl.label.n[0] || y >= nl.label.n[1]) return;
+__device__ __forceinline__ void nodeFinish(const DeviceScene &S, const NodeLevel &nl, const double *sol, int level, int x, int y, int z) {
     const size_t idx = nl.label.lin(x, y, z);
     if (nl.label.d[idx] != N_ACTIVE) return;
     unsigned flag = nl.flag.d[idx];
@@ -185,23 +181,79 @@ __global__ void k_node_finish(const __grid_constant__ DeviceScene S, NodeLevel n
 }
 
 // normalizeActiveNodes (VFI.cpp:569-613)
-__global__ void k_node_normalize(NodeLevel nl, int zLo) {
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y), z = (int)blockIdx.z + zLo;
-    if (x >= nl.label.n[0] || y >= nl.label.n[1]) return;
+__device__ __forceinline__ void nodeNormalize(const NodeLevel &nl, int x, int y, int z) {
     const size_t idx = nl.label.lin(x, y, z);
     if (nl.label.d[idx] != N_ACTIVE) return;
     for (int a = 0; a < 3; ++a) nl.val[a].d[idx] = (float)((double)nl.val[a].d[idx] / (double)nl.w[a].d[idx]);
 }
 
 // distributeNodeValuesDown (VFI.cpp:615-658)
-__global__ void k_node_distribute(NodeLevel child, NodeLevel par, int zLo) {
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y), z = (int)blockIdx.z + zLo;
-    if (x >= child.label.n[0] || y >= child.label.n[1]) return;
+__device__ __forceinline__ void nodeDistribute(const NodeLevel &child, const NodeLevel &par, int x, int y, int z) {
     const size_t idx = child.label.lin(x, y, z);
     if (child.label.d[idx] != N_DEPENDENT) return;
     const I3 pn = mk3(x >> 1, y >> 1, z >> 1);
     for (int a = 0; a < 3; ++a) child.val[a].d[idx] = par.val[a].get(pn);
     child.label.d[idx] = N_ACTIVE;
+}
+
+// ---- launch shapes of the four per-node passes ------------------------------------------------------------------------------
+// dense: one thread per node of planes [zLo, zLo + gridDim.z).  tiles (level 0, where 87 % of the nodes live but only those around
+// the refined band are ever ACTIVE): the node labels are memset to INACTIVE and the pass runs on the 16^3 node tiles that touch a
+// cell tile with an ACTIVE cell (flags of k_tile_flags, avs_labels.cu) -- a node is ACTIVE only as a corner of an ACTIVE cell.
+#define NODE_DENSE_XYZ(nl)                                                                                                              \
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y), z = (int)blockIdx.z + zLo; \
+    if (x >= (nl).label.n[0] || y >= (nl).label.n[1]) return;
+template <class F>
+__device__ __forceinline__ void forNodeTiles(const uint32_t *list, const unsigned int *count, const int n[3], int zLo, int zHi, F f) {
+    if (blockIdx.x >= *count) return;
+    const uint32_t t = list[blockIdx.x];
+    const int x = (int)(t & 1023u) * AVS_TILE + (int)(threadIdx.x & 15), y = (int)((t >> 10) & 1023u) * AVS_TILE + (int)(threadIdx.x >> 4);
+    if (x >= n[0] || y >= n[1]) return;
+    const int z0 = max((int)(t >> 20) * AVS_TILE, zLo), z1 = min(min((int)(t >> 20) * AVS_TILE + AVS_TILE, n[2]), zHi + 1);
+    for (int z = z0; z < z1; ++z) f(x, y, z);
+}
+__global__ void k_node_sample(const __grid_constant__ DeviceScene S, NodeLevel nl, const double *sol, int level, int zLo) {
+    NODE_DENSE_XYZ(nl)
+    nodeSample(S, nl, sol, level, x, y, z);
+}
+__global__ void k_node_finish(const __grid_constant__ DeviceScene S, NodeLevel nl, const double *sol, int level, int zLo) {
+    NODE_DENSE_XYZ(nl)
+    nodeFinish(S, nl, sol, level, x, y, z);
+}
+__global__ void k_node_normalize(NodeLevel nl, int zLo) {
+    NODE_DENSE_XYZ(nl)
+    nodeNormalize(nl, x, y, z);
+}
+__global__ void k_node_distribute(NodeLevel child, NodeLevel par, int zLo) {
+    NODE_DENSE_XYZ(child)
+    nodeDistribute(child, par, x, y, z);
+}
+__global__ void k_node_sample_tiles(const __grid_constant__ DeviceScene S, NodeLevel nl, const double *sol, int level, int zLo, int zHi,
+                                    const uint32_t *list, const unsigned int *count) {
+    forNodeTiles(list, count, nl.label.n, zLo, zHi, [&](int x, int y, int z) { nodeSample(S, nl, sol, level, x, y, z); });
+}
+__global__ void k_node_finish_tiles(const __grid_constant__ DeviceScene S, NodeLevel nl, const double *sol, int level, int zLo, int zHi,
+                                    const uint32_t *list, const unsigned int *count) {
+    forNodeTiles(list, count, nl.label.n, zLo, zHi, [&](int x, int y, int z) { nodeFinish(S, nl, sol, level, x, y, z); });
+}
+__global__ void k_node_normalize_tiles(NodeLevel nl, int zLo, int zHi, const uint32_t *list, const unsigned int *count) {
+    forNodeTiles(list, count, nl.label.n, zLo, zHi, [&](int x, int y, int z) { nodeNormalize(nl, x, y, z); });
+}
+__global__ void k_node_distribute_tiles(NodeLevel child, NodeLevel par, int zLo, int zHi, const uint32_t *list, const unsigned int *count) {
+    forNodeTiles(list, count, child.label.n, zLo, zHi, [&](int x, int y, int z) { nodeDistribute(child, par, x, y, z); });
+}
+// node tiles (of the (n+1)^3 node grid) that touch a cell tile holding an ACTIVE cell; node tile t touches cell tiles t - {0,1}^3
+__global__ void k_node_tile_list(int n0, int n1, int n2, Grid3<uint8_t> flags, uint32_t *list, unsigned int *count) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n0 * n1 * n2) return;
+    const int tx = (int)(i % n0), ty = (int)((i / n0) % n1), tz = (int)(i / ((size_t)n0 * n1));
+    bool take = false;
+    for (int q = 0; q < 8 && !take; ++q) {
+        const int cx = tx - (q & 1), cy = ty - ((q >> 1) & 1), cz = tz - (q >> 2);
+        if (cx < 0 || cy < 0 || cz < 0 || cx >= flags.n[0] || cy >= flags.n[1] || cz >= flags.n[2]) continue;
+        take = (flags.d[flags.lin(cx, cy, cz)] & 1) != 0;   // TILE_HAS_ACTIVE
+    }
+    if (take) list[atomicAdd(count, 1u)] = (uint32_t)tx | ((uint32_t)ty << 10) | ((uint32_t)tz << 20);
 }
 
 // interpSPGrid (VFI.cpp:660-845)
@@ -384,9 +436,28 @@ int avs_apply_regular(AvsContext *c, float *dOut[3], unsigned long long *hostInt
             zLo[l] = zA >> l;
             nzW[l] = zB < zA ? 0 : std::min((zB >> l), NS.lv[l].label.n[2] - 1) - zLo[l] + 1;
         }
+        // level 0 on node tiles when the labelling stage left its tile flags (default); the other levels are 1/8, 1/64, ... of it
+        const uint32_t *tl = nullptr;
+        unsigned int *tc = nullptr;
+        unsigned tcap = 0;
+        if (c->tileFlagsGrid.d && nzW[0] > 0) {
+            const int *nn = NS.lv[0].label.n;
+            const int t0 = (nn[0] + AVS_TILE - 1) / AVS_TILE, t1 = (nn[1] + AVS_TILE - 1) / AVS_TILE, t2 = (nn[2] + AVS_TILE - 1) / AVS_TILE;
+            tcap = (unsigned)((size_t)t0 * t1 * t2);
+            if (c->nodeTileList.reserve((size_t)tcap * sizeof(uint32_t))) return AVS_ERR_ALLOC;
+            tc = (unsigned int *)(c->counters.as<unsigned long long>() + 36);
+            AVS_CUDA_CHECK(cudaMemsetAsync(tc, 0, sizeof(unsigned int), c->stream));
+            // nodes of tiles that are not listed keep N_INACTIVE (k_node_sample would have written exactly that)
+            AVS_CUDA_CHECK(cudaMemsetAsync(NS.lv[0].label.d + (size_t)nn[0] * nn[1] * (size_t)zLo[0], N_INACTIVE, (size_t)nn[0] * nn[1] * (size_t)nzW[0], c->stream));
+            k_node_tile_list<<<(tcap + 255) / 256, 256, 0, c->stream>>>(t0, t1, t2, c->tileFlagsGrid, c->nodeTileList.as<uint32_t>(), tc);
+            ++c->launches;
+            tl = c->nodeTileList.as<uint32_t>();
+        }
+        const int zHi0 = zLo[0] + nzW[0] - 1;
         for (int l = 0; l < L; ++l) {
             if (nzW[l] <= 0) continue;
-            k_node_sample<<<grid3(NS.lv[l].label.n, nzW[l]), dim3(128, NODE_YB), 0, c->stream>>>(S, NS.lv[l], sol, l, zLo[l]);
+            if (l == 0 && tl) k_node_sample_tiles<<<tcap, 256, 0, c->stream>>>(S, NS.lv[0], sol, 0, zLo[0], zHi0, tl, tc);
+            else k_node_sample<<<grid3(NS.lv[l].label.n, nzW[l]), dim3(128, NODE_YB), 0, c->stream>>>(S, NS.lv[l], sol, l, zLo[l]);
             ++c->launches;
         }
         for (int l = 0; l < L - 1; ++l) {
@@ -396,17 +467,20 @@ int avs_apply_regular(AvsContext *c, float *dOut[3], unsigned long long *hostInt
         }
         for (int l = 0; l < L - 1; ++l) {
             if (nzW[l] <= 0) continue;
-            k_node_finish<<<grid3(NS.lv[l].label.n, nzW[l]), dim3(128, NODE_YB), 0, c->stream>>>(S, NS.lv[l], sol, l, zLo[l]);
+            if (l == 0 && tl) k_node_finish_tiles<<<tcap, 256, 0, c->stream>>>(S, NS.lv[0], sol, 0, zLo[0], zHi0, tl, tc);
+            else k_node_finish<<<grid3(NS.lv[l].label.n, nzW[l]), dim3(128, NODE_YB), 0, c->stream>>>(S, NS.lv[l], sol, l, zLo[l]);
             ++c->launches;
         }
         for (int l = 0; l < L; ++l) {
             if (nzW[l] <= 0) continue;
-            k_node_normalize<<<grid3(NS.lv[l].label.n, nzW[l]), dim3(128, NODE_YB), 0, c->stream>>>(NS.lv[l], zLo[l]);
+            if (l == 0 && tl) k_node_normalize_tiles<<<tcap, 256, 0, c->stream>>>(NS.lv[0], zLo[0], zHi0, tl, tc);
+            else k_node_normalize<<<grid3(NS.lv[l].label.n, nzW[l]), dim3(128, NODE_YB), 0, c->stream>>>(NS.lv[l], zLo[l]);
             ++c->launches;
         }
         for (int l = L - 2; l >= 0; --l) {
             if (nzW[l] <= 0) continue;
-            k_node_distribute<<<grid3(NS.lv[l].label.n, nzW[l]), dim3(128, NODE_YB), 0, c->stream>>>(NS.lv[l], NS.lv[l + 1], zLo[l]);
+            if (l == 0 && tl) k_node_distribute_tiles<<<tcap, 256, 0, c->stream>>>(NS.lv[0], NS.lv[1], zLo[0], zHi0, tl, tc);
+            else k_node_distribute<<<grid3(NS.lv[l].label.n, nzW[l]), dim3(128, NODE_YB), 0, c->stream>>>(NS.lv[l], NS.lv[l + 1], zLo[l]);
             ++c->launches;
         }
     }

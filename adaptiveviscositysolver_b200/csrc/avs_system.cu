@@ -339,7 +339,7 @@ __device__ __noinline__ void applyToMatrix(Row &row, double &rhsI, double &diag,
 
 // buildOctreeSystemFromStencilsPartial (AV.cpp:2459-2777) for row vi
 template <class Row>
-__device__ void buildRow(const DeviceScene &S, int32_t vi, const RowKey &k, double x0i, float faceWeight, Row &row, double &rhsI) {
+__device__ void buildRow(const DeviceScene &S, int32_t vi, const RowKey &k, float faceWeight, Row &row, double &rhsI, double &massOut) {
     const int level = k.level, axis = k.axis;
     const I3 face = mk3(k.i, k.j, k.k);
     const Grid3<uint8_t> &lab = S.label[level];
@@ -422,7 +422,7 @@ __device__ void buildRow(const DeviceScene &S, int32_t vi, const RowKey &k, doub
         fw *= S.density.value(p);
     }
     row.add(vi, fw + diag);
-    rhsI += fw * x0i;
+    massOut = fw;   // rhs_i += M_u u^n_i (AV.cpp:2767-2772) is added by k_finish_rhs once the restricted velocity exists
 }
 
 // The face-weight field ("surfaceweights", AV.cpp:144) is read at ONE place of the whole path: the control volume of a LEVEL-0
@@ -443,7 +443,7 @@ __global__ void k_gather_face_weights(const __grid_constant__ DeviceScene S, con
 // rhs and its diagonal.  The CG's SJDS matrix is filled straight from the staging area; a canonical
 // CSR (sorted columns) is only built when a caller asks to read the system back.
 template <int MINB, class Row>
-__global__ void __launch_bounds__(128, MINB) k_assemble(const __grid_constant__ DeviceScene S, const RowKey *keys, const double *x0, const float *fwRow,
+__global__ void __launch_bounds__(128, MINB) k_assemble(const __grid_constant__ DeviceScene S, const RowKey *keys, double *rowMass, const float *fwRow,
                                                   long long rowBegin, long long nLocal, long long stride, int32_t *rowCount,
                                                   int32_t *stageCol, double *stageVal, double *rhs, double *diagOut,
                                                   int *overflowFlag, const int32_t *rowList, const unsigned long long *rowListCount) {
@@ -456,8 +456,9 @@ __global__ void __launch_bounds__(128, MINB) k_assemble(const __grid_constant__ 
     const long long gi = rowBegin + r;
     Row row;
     row.init();
-    double rhsI = 0;
-    buildRow(S, (int32_t)gi, keys[gi], x0[gi], fwRow[gi], row, rhsI);
+    double rhsI = 0, mass = 0;
+    buildRow(S, (int32_t)gi, keys[gi], fwRow[gi], row, rhsI, mass);
+    rowMass[r] = mass;
     if (row.overflow) *overflowFlag = 1;
     rowCount[r] = row.n;
     for (int i = 0; i < row.n; ++i) {
@@ -493,7 +494,7 @@ struct SimpleRowOut {   // entries go straight to the column-major staging area 
     }
 };
 template <int AXIS>
-__device__ __forceinline__ bool buildSimpleRow(const DeviceScene &S, int32_t vi, const I3 &face, double x0i, float fwRaw, SimpleRowOut &row, double &rhsI) {
+__device__ __forceinline__ bool buildSimpleRow(const DeviceScene &S, int32_t vi, const I3 &face, float fwRaw, SimpleRowOut &row, double &massOut) {
     const Grid3<uint8_t> &lab = S.label[0];
     const Grid3<int32_t> &fg = S.face[0][AXIS];
     constexpr int T1 = (AXIS + 1) % 3, T2 = (AXIS + 2) % 3;           // the two transverse axes
@@ -637,12 +638,11 @@ __device__ __forceinline__ bool buildSimpleRow(const DeviceScene &S, int32_t vi,
         fw *= S.density.value(p);
     }
     row.add(vi, fw + diag);
-    rhsI = 0;
-    rhsI += fw * x0i;
+    massOut = fw;   // no boundary terms in a simple row: rhs_i = 0 + M_u u^n_i (k_finish_rhs)
     return true;
 }
 
-__global__ void __launch_bounds__(128) k_assemble_simple(const __grid_constant__ DeviceScene S, const RowKey *keys, const double *x0, const float *fwRow,
+__global__ void __launch_bounds__(128) k_assemble_simple(const __grid_constant__ DeviceScene S, const RowKey *keys, double *rowMass, const float *fwRow,
                                                          long long rowBegin, long long nLocal, long long stride, int32_t *rowCount,
                                                          int32_t *stageCol, double *stageVal, double *rhs, double *diagOut,
                                                          int32_t *rowList, unsigned long long *rowListCount) {
@@ -654,22 +654,22 @@ __global__ void __launch_bounds__(128) k_assemble_simple(const __grid_constant__
         pass = true;
         if (k.level == 0) {
             const I3 face = mk3(k.i, k.j, k.k);
-            const double x0i = x0[gi];
             const float fwi = fwRow[gi];
             SimpleRowOut row;
             row.col = stageCol + r;
             row.val = stageVal + r;
             row.stride = stride;
             row.last = 0;
-            double rhsI = 0;
+            double mass = 0;
             bool ok;
-            if (k.axis == 0) ok = buildSimpleRow<0>(S, (int32_t)gi, face, x0i, fwi, row, rhsI);
-            else if (k.axis == 1) ok = buildSimpleRow<1>(S, (int32_t)gi, face, x0i, fwi, row, rhsI);
-            else ok = buildSimpleRow<2>(S, (int32_t)gi, face, x0i, fwi, row, rhsI);
+            if (k.axis == 0) ok = buildSimpleRow<0>(S, (int32_t)gi, face, fwi, row, mass);
+            else if (k.axis == 1) ok = buildSimpleRow<1>(S, (int32_t)gi, face, fwi, row, mass);
+            else ok = buildSimpleRow<2>(S, (int32_t)gi, face, fwi, row, mass);
             if (ok) {
                 pass = false;
                 rowCount[r] = row.n;
-                rhs[r] = rhsI;
+                rhs[r] = 0;
+                rowMass[r] = mass;
                 diagOut[r] = row.last;   // the diagonal is added last (AV.cpp:2768)
             }
         }
@@ -723,6 +723,9 @@ int avs_stage_system(AvsContext *c, const AvsParams *p) {
     AVS_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(unsigned long long), c->stream));
     c->nnz = 0;
     if (c->faceWRow.reserve((size_t)std::max<long long>(c->nRows, 1) * sizeof(float))) return AVS_ERR_ALLOC;
+    if (c->rowMass.reserve((size_t)std::max<long long>(nLocal, 1) * sizeof(double))) return AVS_ERR_ALLOC;
+    // face weights that were uploaded whole (pageable host arrays) must have landed; mapped ones are read in place
+    if (!c->faceWMappedBytes) cudaStreamWaitEvent(c->stream, c->evUploadDone, 0);
     if (nLocal > 0) {
         unsigned blocks = (unsigned)((nLocal + 127) / 128);
         k_gather_face_weights<<<(unsigned)((nLocal + 255) / 256), 256, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->rowBegin, nLocal,
@@ -747,7 +750,7 @@ int avs_stage_system(AvsContext *c, const AvsParams *p) {
             if (c->asmRowList.reserve((size_t)nLocal * sizeof(int32_t))) return AVS_ERR_ALLOC;
             unsigned long long *lc = c->counters.as<unsigned long long>() + 27;
             AVS_CUDA_CHECK(cudaMemsetAsync(lc, 0, sizeof(unsigned long long), c->stream));
-            k_assemble_simple<<<blocks, 128, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->x0.as<double>(), c->faceWRow.as<float>(), c->rowBegin, nLocal, stride,
+            k_assemble_simple<<<blocks, 128, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->rowMass.as<double>(), c->faceWRow.as<float>(), c->rowBegin, nLocal, stride,
                                                            c->rowCount.as<int32_t>(), c->stageCol.as<int32_t>(), c->stageVal.as<double>(),
                                                            c->rhs.as<double>(), c->diag.as<double>(), c->asmRowList.as<int32_t>(), lc);
             ++c->launches;
@@ -757,11 +760,11 @@ int avs_stage_system(AvsContext *c, const AvsParams *p) {
 #define ASM_LAUNCH(M)                                                                                                              \
     do {                                                                                                                           \
     if (hashRow)                                                                                                                   \
-        k_assemble<M, RowAccHash><<<blocks, 128, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->x0.as<double>(), c->faceWRow.as<float>(), c->rowBegin, nLocal, stride, \
+        k_assemble<M, RowAccHash><<<blocks, 128, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->rowMass.as<double>(), c->faceWRow.as<float>(), c->rowBegin, nLocal, stride, \
                                                  c->rowCount.as<int32_t>(), c->stageCol.as<int32_t>(), c->stageVal.as<double>(),      \
                                                  c->rhs.as<double>(), c->diag.as<double>(), flag, rowList, rowListCount);                                    \
     else                                                                                                                           \
-    k_assemble<M, RowAcc><<<blocks, 128, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->x0.as<double>(), c->faceWRow.as<float>(), c->rowBegin, nLocal, stride,       \
+    k_assemble<M, RowAcc><<<blocks, 128, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->rowMass.as<double>(), c->faceWRow.as<float>(), c->rowBegin, nLocal, stride,       \
                                                  c->rowCount.as<int32_t>(), c->stageCol.as<int32_t>(), c->stageVal.as<double>(),      \
                                                  c->rhs.as<double>(), c->diag.as<double>(), flag, rowList, rowListCount);                                    \
     } while (0)
@@ -792,6 +795,24 @@ int avs_stage_system(AvsContext *c, const AvsParams *p) {
     AVS_CUDA_CHECK(cudaGetLastError());
     c->haveSystem = true;
     c->haveSolution = false;
+    return AVS_OK;
+}
+
+// rhs_i += M_u u^n_i (AV.cpp:2767-2772).  The assembly leaves rhs_i = -(boundary terms) and the row's mass M_u = rho V_face;
+// the restricted velocity is the LAST input the system needs, so the restriction stage runs after the assembly (the velocity's
+// host -> device copy then hides under labelling + assembly) and this kernel completes the right-hand side.  The same two operands
+// are added as in buildOctreeSystemFromStencilsPartial's last statement: bit-identical.
+__global__ void k_finish_rhs(long long n, long long base, const double *x0, const double *rowMass, double *rhs) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) rhs[r] += rowMass[r] * x0[base + r];
+}
+int avs_finish_rhs(AvsContext *c) {
+    const long long n = c->rowEnd - c->rowBegin;
+    if (n > 0) {
+        k_finish_rhs<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->rowBegin, c->x0.as<double>(), c->rowMass.as<double>(), c->rhs.as<double>());
+        ++c->launches;
+    }
+    AVS_CUDA_CHECK(cudaGetLastError());
     return AVS_OK;
 }
 

@@ -183,7 +183,8 @@ int avs_solve(AvsContext *ctx, const AvsFields *in, const AvsParams *p, AvsVeloc
  * The same drop-in call for a host that owns all GPUs from ONE thread -- the shape of the DOP: solveGasSubclass is called
  * on Houdini's cook thread, one object at a time (HDK_AdaptiveViscosity.cpp:126-128, HDK_AdaptiveViscosity.h:57-58).
  * avs_create_multi makes one rank context per entry of `devices` (an ordinal may repeat: ranks then share that GPU, which is
- * how the multi-rank path is tested on a one-GPU box); avs_solve_multi row-partitions the solve over them and returns when
+ * how the multi-rank path is tested on a one-GPU box -- that configuration needs CUDA_MODULE_LOADING=EAGER in the environment
+ * before CUDA initialises, because the ranks' kernels wait for each other and a lazily loaded kernel cannot start meanwhile); avs_solve_multi row-partitions the solve over them and returns when
  * every rank is done.  Fields and the output velocity must be HOST arrays (every rank reads the same inputs and writes the
  * z-slab of `out` it computed); `cancel` is not supported.  No NCCL and no CUDA IPC are involved: the GPUs must be able to
  * access each other's memory (cudaDeviceCanAccessPeer).  `res` receives rank 0's result with per-stage times maximised over

@@ -2,6 +2,12 @@ import os
 import sys
 from pathlib import Path
 
+# Two rank contexts that SHARE one GPU (how the multi-rank paths are tested on a one-GPU box) spin on each other from inside
+# their kernels.  With CUDA's default lazy module loading the first launch of a kernel may need a context-wide synchronisation,
+# which never completes while the peer's kernel spins (CUDA programming guide, "Lazy Loading -- Concurrent Execution"): observed
+# as an occasional 8 s spin-wait time-out in the first multi-rank test of a process.  Must be set before CUDA initialises.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 import pytest
 
 ROOT = Path(__file__).resolve().parent.parent

@@ -1,10 +1,14 @@
-"""The split assembly of round 2 (k_assemble_simple for the level-0 rows without T-junctions / solids, k_assemble for the rest)
-against the single-pass assembly it replaces (AVS_ASM=generic), BIT FOR BIT on one GPU: same rows, same entry order, same
-roundings -- hence the same CG iterates, iteration counts and output velocities.  Scenes cover variable viscosity / density,
-solids (boundary terms), doApplySolidWeights, enhanced gradients off, a ragged non-power-of-two grid and BASELINE configs[1].
+"""Round-2 kernel rewrites against the kernels they replace, BIT FOR BIT on one GPU:
 
-The variant is chosen once per process (environment), so each configuration runs in its own subprocess and prints the sha256 of
-everything the pipeline produced; the digests must be identical."""
+* the split assembly (k_assemble_simple for the level-0 rows without T-junctions / solids, k_assemble with the hashed row
+  accumulator for the rest) against the single-pass assembly with the linear-search accumulator (AVS_ASM=generic,
+  AVS_ASM_ROW=linear): same rows, same entry order, same roundings -- hence the same CG iterates and output velocities;
+* the tile-culled level-0 labelling and node pyramid (memset + classification only on the 16^3 tiles that can hold anything but
+  the default label) against the dense sweeps (AVS_LABELS=dense): same labels, same numbering, same interpolated velocities.
+
+Scenes cover variable viscosity / density, solids (boundary terms), doApplySolidWeights, enhanced gradients off, a ragged
+non-power-of-two grid, a uniform grid and BASELINE configs[1].  A variant is chosen once per process (environment), so each
+configuration runs in its own subprocess and prints the sha256 of everything the pipeline produced; the digests must be identical."""
 import json
 import os
 import subprocess
@@ -65,7 +69,7 @@ print("DIGESTS " + json.dumps(out))
 
 def _run(extra_env):
     env = dict(os.environ)
-    for k in ("AVS_ASM", "AVS_ASM_ROW", "AVS_CG_MODE", "AVS_PCG_KERNEL", "AVS_SPMV_MODE"):
+    for k in ("AVS_ASM", "AVS_LABELS", "AVS_ASM_ROW", "AVS_CG_MODE", "AVS_PCG_KERNEL", "AVS_SPMV_MODE"):
         env.pop(k, None)
     env.update(extra_env)
     r = subprocess.run([sys.executable, "-c", _WORKER % str(ROOT)], capture_output=True, text=True, timeout=900, cwd=str(ROOT), env=env)
@@ -79,8 +83,10 @@ def default_digests():
     return _run({})
 
 
-def test_split_assembly_is_bit_identical_to_the_single_pass_assembly(default_digests):
-    other = _run({"AVS_ASM": "generic"})
+@pytest.mark.parametrize("variant", [{"AVS_ASM": "generic", "AVS_ASM_ROW": "linear"}, {"AVS_LABELS": "dense"}],
+                         ids=["single_pass_assembly", "dense_level0_labelling"])
+def test_rewritten_kernels_are_bit_identical_to_the_ones_they_replace(default_digests, variant):
+    other = _run(variant)
     assert other.keys() == default_digests.keys()
     for name in default_digests:
         assert other[name] == default_digests[name], (name, {k: (other[name][k], default_digests[name][k]) for k in other[name]
