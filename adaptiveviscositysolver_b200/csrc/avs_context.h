@@ -114,7 +114,7 @@ struct AvsContext {
     DevBuf rowMass;                         // fp64 [local rows]: M_u = rho V_face of every row (rhs += M_u u^n, k_finish_rhs)
     DevBuf faceWRow;                        // fp32 [N]: the face weight of every level-0 row (k_gather_face_weights)
     DevBuf asmRowList;                      // split assembly: local ids of the rows left for the generic kernel
-    DevBuf coarseRows;                      // ids of the rows of level >= 3 (restriction: one CTA per such row)
+    DevBuf coarseRows;                      // restriction of the rows of level >= 3: row ids | work-item bases | work items | partial sums
     DevBuf x0, rhs, solution, fullSolution;  // fp64: x0 [N], rhs/solution [local rows], fullSolution [N] (multi-GPU apply)
     DevBuf rowCount, rowOffset; // assembly scratch (int32 / int64)
     DevBuf csrPtr, csrCol, csrVal;  // canonical CSR of the local rows (int64 / int32 / fp64); col/val built lazily
@@ -133,6 +133,7 @@ struct AvsContext {
     int levelsAllocated = 0;
     int64_t nRows = 0, nnz = 0, nEdge = 0, nCenter = 0, nRegular = 0;
     int64_t rowBegin = 0, rowEnd = 0;  // rows owned by this rank
+    bool surfaceTilesMarked = false;   // the weights stage has already filled the level-0 face tile maps (c->tiles) for this solve
     long long asmGenericRows = 0;      // rows of the last assembly that went through the generic kernel (split assembly: the non-simple ones)
     int faceWMappedBytes = 0;          // 1: the face weights of this solve are read through mapped host pointers (no bulk upload)
     bool x0AllRows = true;             // x0 holds the restricted velocity of every row (false: only of [rowBegin, rowEnd))

@@ -252,12 +252,25 @@ __device__ __forceinline__ unsigned combine3x4(unsigned a, unsigned b, unsigned 
     }
     return r;
 }
-__global__ void k_sign_x4(const float *__restrict__ sdf, int nx, int ny, int nz, uint8_t *__restrict__ out) {
+// Also findOccupiedRegularVelocityTiles (AV.cpp:886-943; k_mark_surface_tiles below is the stand-alone form): this pass reads the
+// whole surface field anyway, so it marks the face tiles of every cell with sdf < 2 dx on the way (t0.d == nullptr: no marking).
+__global__ void k_sign_x4(const float *__restrict__ sdf, int nx, int ny, int nz, uint8_t *__restrict__ out, double twoDx, Grid3<uint8_t> t0,
+                          Grid3<uint8_t> t1, Grid3<uint8_t> t2) {
     const int x4 = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
     const int x = 4 * x4;
     if (x >= nx) return;
     const size_t row = (size_t)nx * ((size_t)y + (size_t)ny * (size_t)z);
     const float4 v = *(const float4 *)(sdf + row + x);
+    if (t0.d) {
+        const bool h3 = (double)v.w < twoDx;
+        if (h3 || (double)v.x < twoDx || (double)v.y < twoDx || (double)v.z < twoDx) {
+            const int tx = x / AVS_TILE, ty = y / AVS_TILE, tz = z / AVS_TILE;   // x .. x+3 lie in one tile, and so do their +1 faces but the last
+            t0.d[t0.lin(tx, ty, tz)] = 1;
+            t1.d[t1.lin(tx, ty, tz)] = 1; t1.d[t1.lin(tx, (y + 1) / AVS_TILE, tz)] = 1;
+            t2.d[t2.lin(tx, ty, tz)] = 1; t2.d[t2.lin(tx, ty, (z + 1) / AVS_TILE)] = 1;
+            if (h3) t0.d[t0.lin((x + 4) / AVS_TILE, ty, tz)] = 1;
+        }
+    }
     const float l = sdf[row + max(x - 1, 0)], r = sdf[row + min(x + 4, nx - 1)];
     const unsigned s[6] = {l < 0.f ? 0u : 1u, v.x < 0.f ? 0u : 1u, v.y < 0.f ? 0u : 1u, v.z < 0.f ? 0u : 1u, v.w < 0.f ? 0u : 1u, r < 0.f ? 0u : 1u};
     unsigned o = 0;
@@ -358,8 +371,10 @@ static int weightsFor(AvsContext *c, DevBuf &buf, Grid3<float> &g, const DField 
     return AVS_OK;
 }
 
+static int avs_face_tile_maps(AvsContext *c, Grid3<uint8_t> t[3]);
 int avs_stage_weights(AvsContext *c, const AvsParams *p) {
     DeviceScene &S = c->S;
+    c->surfaceTilesMarked = false;
     const int n = p->number_super_samples;
     const double offC[3] = {0.5, 0.5, 0.5};
     // sign classes of the surface SDF (only valid as a shortcut when the field sits on the scene grid with dilate = 0,
@@ -370,7 +385,12 @@ int avs_stage_weights(AvsContext *c, const AvsParams *p) {
         if (c->signA.reserve(cells) || c->signB.reserve(cells)) return AVS_ERR_ALLOC;
         if (S.N[0] % 4 == 0) {   // rows start 16-byte aligned (cudaMalloc base, row length a multiple of 4 floats): 4 cells per thread
             const dim3 g4((unsigned)((S.N[0] / 4 + 127) / 128), (unsigned)S.N[1], (unsigned)S.N[2]);
-            k_sign_x4<<<g4, 128, 0, c->stream>>>(S.surface.d, S.N[0], S.N[1], S.N[2], c->signA.as<uint8_t>());
+            // the regular-grid face tile maps of stage 4 are filled here, by the pass that reads the surface anyway
+            Grid3<uint8_t> ft[3];
+            int rct = avs_face_tile_maps(c, ft);
+            if (rct) return rct;
+            c->surfaceTilesMarked = true;
+            k_sign_x4<<<g4, 128, 0, c->stream>>>(S.surface.d, S.N[0], S.N[1], S.N[2], c->signA.as<uint8_t>(), 2.0 * S.dx0, ft[0], ft[1], ft[2]);
             k_sign_axis4<<<g4, 128, 0, c->stream>>>(c->signA.as<uint8_t>(), S.N[0], S.N[1], S.N[2], 1, c->signB.as<uint8_t>());
             k_sign_axis4<<<g4, 128, 0, c->stream>>>(c->signB.as<uint8_t>(), S.N[0], S.N[1], S.N[2], 2, c->signA.as<uint8_t>());
             c->launches += 3;
@@ -523,6 +543,72 @@ __global__ void k_octree_pass3(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
     if (par.d[pi] == L_INACTIVE) par.d[pi] = L_UP;
     });
 }
+// ---- the same passes with 16 cells per thread (rows whose length is a multiple of 16: one 128-bit load per thread) ------------
+// One byte per thread keeps these sweeps at ~0.25 TB/s.  Only a band of cells is ACTIVE and the UP cells of one 16-cell run share
+// 8 parents, so a thread that loads 16 labels at once usually has nothing (pass 2) or eight byte-checks (pass 3) left to do.
+__global__ void k_octree_pass2_active16(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
+    const int x0 = 16 * (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
+    if (x0 >= cur.n[0]) return;
+    const size_t row = (size_t)cur.n[0] * ((size_t)y + (size_t)cur.n[1] * (size_t)z);
+    __align__(16) uint8_t v[16];
+    *(uint4 *)v = *(const uint4 *)(cur.d + row + x0);
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) any = any || v[k] == L_ACTIVE;
+    if (!any) return;
+    for (int k = 0; k < 16; ++k) {
+        if (v[k] != L_ACTIVE) continue;
+        const I3 c = mk3(x0 + k, y, z);
+#pragma unroll
+        for (int axis = 0; axis < 3; ++axis)
+#pragma unroll
+            for (int dir = 0; dir < 2; ++dir) {
+                I3 a = cellToCell(c, axis, dir);
+                if (a[axis] < 0 || a[axis] >= cur.n[axis]) continue;
+                if (cur.at(a) == L_UP) par.d[par.lin(a[0] >> 1, a[1] >> 1, a[2] >> 1)] = L_ACTIVE;
+            }
+    }
+}
+__global__ void k_octree_pass3_16(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
+    const int x0 = 16 * (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
+    if (x0 >= cur.n[0]) return;
+    const size_t row = (size_t)cur.n[0] * ((size_t)y + (size_t)cur.n[1] * (size_t)z);
+    __align__(16) uint8_t v[16];
+    *(uint4 *)v = *(const uint4 *)(cur.d + row + x0);
+    const size_t prow = par.lin(x0 >> 1, y >> 1, z >> 1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (v[2 * k] == L_UP || v[2 * k + 1] == L_UP) {
+            if (par.d[prow + k] == L_INACTIVE) par.d[prow + k] = L_UP;
+        }
+}
+// k_base_labels with 4 cells per thread (padded rows are a multiple of 4): one 32-bit store per thread
+__global__ void k_base_labels4(const __grid_constant__ DeviceScene S, double inner, double outer) {
+    const Grid3<uint8_t> lab = S.label[0];
+    const int x0 = 4 * (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
+    if (x0 >= lab.n[0]) return;
+    unsigned packed = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int x = x0 + k;
+        uint8_t out = L_INACTIVE;
+        if (x < S.N[0] && y < S.N[1] && z < S.N[2]) {
+            double sdf = (double)S.surface.raw(x, y, z);
+            if (sdf > 0 && sdf < outer) out = L_ACTIVE;
+            else if (sdf <= 0.) {
+                if (sdf > -inner) out = L_ACTIVE;
+                else {
+                    double p[3];
+                    S.centerPos(mk3(x, y, z), 0, p);
+                    out = (S.collision.value(p) > (-inner - S.extrap)) ? L_ACTIVE : L_UP;
+                }
+            }
+        }
+        packed |= (unsigned)out << (8 * k);
+    }
+    *(unsigned *)(lab.d + lab.lin(x0, y, z)) = packed;
+}
+
 // setTopLevel (OG.cpp:843-875)
 __global__ void k_octree_top(Grid3<uint8_t> g) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -602,13 +688,24 @@ int avs_stage_octree(AvsContext *c, const AvsParams *p) {
     }
     const double fineVoxelWidth = std::max(2.0, (double)p->fine_bandwidth);  // AV.cpp:259
     const double inner = S.dx0 * fineVoxelWidth, outer = 3.0 * S.dx0;         // AV.cpp:261-262
-    LAUNCH_3D(c, k_base_labels, S.label[0].n, S, inner, outer);
+    if (S.label[0].n[0] % 4 == 0) {
+        const dim3 g((unsigned)((S.label[0].n[0] / 4 + 127) / 128), (unsigned)S.label[0].n[1], (unsigned)S.label[0].n[2]);
+        k_base_labels4<<<g, 128, 0, c->stream>>>(S, inner, outer);
+        ++c->launches;
+    } else LAUNCH_3D(c, k_base_labels, S.label[0].n, S, inner, outer);
     for (int l = 0; l < L - 1; ++l) {
         Grid3<uint8_t> cur = S.label[l], par = S.label[l + 1];
         LAUNCH_3D(c, k_octree_pass1, par.n, cur, par);
         if (l > 0) LAUNCH_3D(c, k_octree_pass2_down, cur.n, cur, par);
-        LAUNCH_3D(c, k_octree_pass2_active, cur.n, cur, par);
-        LAUNCH_3D(c, k_octree_pass3, cur.n, cur, par);
+        if (cur.n[0] % 16 == 0) {   // 16 cells per thread
+            const dim3 g((unsigned)((cur.n[0] / 16 + 63) / 64), (unsigned)cur.n[1], (unsigned)cur.n[2]);
+            k_octree_pass2_active16<<<g, 64, 0, c->stream>>>(cur, par);
+            k_octree_pass3_16<<<g, 64, 0, c->stream>>>(cur, par);
+            c->launches += 2;
+        } else {
+            LAUNCH_3D(c, k_octree_pass2_active, cur.n, cur, par);
+            LAUNCH_3D(c, k_octree_pass3, cur.n, cur, par);
+        }
     }
     LAUNCH_1D(c, k_octree_top, S.label[L - 1].count(), S.label[L - 1]);
     // level capping (OG.cpp:198-211): first level without an ACTIVE cell
@@ -642,7 +739,9 @@ __device__ __forceinline__ bool tileOccupied(const Grid3<uint8_t> &t, int x, int
     return t.d[t.lin(x / AVS_TILE, y / AVS_TILE, z / AVS_TILE)] != 0;
 }
 
-// findOccupiedRegularVelocityTiles (AV.cpp:886-943): both faces of every cell with sdf < 2 dx
+// findOccupiedRegularVelocityTiles (AV.cpp:886-943): both faces of every cell with sdf < 2 dx.  (The six byte stores of a warp's
+// lanes hit two or three tile bytes per map and are merged by the hardware: electing one lane per 16-cell segment to do them
+// measured no faster -- regular labels 3.99 -> 4.33 ms at C3.)
 __global__ void k_mark_surface_tiles(const __grid_constant__ DeviceScene S, Grid3<uint8_t> t0, Grid3<uint8_t> t1,
                                      Grid3<uint8_t> t2) {
     forCells(S.N, [&](int x, int y, int z, size_t idx, bool ok) {
@@ -816,8 +915,12 @@ __global__ void k_tile_flags(Grid3<uint8_t> lab, Grid3<uint8_t> flags, Grid3<uin
     if (y < lab.n[1] && z < lab.n[2]) {
         const int x0 = tx * AVS_TILE, x1 = min(x0 + AVS_TILE, lab.n[0]);
         const size_t row = (size_t)lab.n[0] * ((size_t)y + (size_t)lab.n[1] * (size_t)z);
+        __align__(16) uint8_t cells[AVS_TILE];
+        if (x1 - x0 == AVS_TILE && lab.n[0] % AVS_TILE == 0) *(uint4 *)cells = *(const uint4 *)(lab.d + row + x0);   // rows start 16-byte aligned
+        else
+            for (int x = x0; x < x1; ++x) cells[x - x0] = lab.d[row + x];
         for (int x = x0; x < x1; ++x) {
-            const uint8_t l = lab.d[row + x];
+            const uint8_t l = cells[x - x0];
             if (l != L_UP) mine |= TILE_HAS_NON_UP;
             if (l == L_ACTIVE) {
                 mine |= TILE_HAS_ACTIVE;
@@ -919,6 +1022,31 @@ static int tileGrid(AvsContext *c, DevBuf &buf, Grid3<uint8_t> t[3], const int r
     return AVS_OK;
 }
 
+// the three level-0 face tile maps (c->tiles): dimensions from the PADDED face grids, which avs_stage_octree fixes later -- the
+// padding is a pure function of the resolution, so it is computed here as well
+static void faceTileRes(const AvsContext *c, int res[3][3]) {
+    for (int k = 0; k < 3; ++k) {
+        int pad = 1;
+        while (pad < c->S.N[k]) pad <<= 1;   // OG.cpp:18-24
+        for (int a = 0; a < 3; ++a) res[a][k] = pad + 1;
+    }
+}
+static void avs_face_tile_views(AvsContext *c, Grid3<uint8_t> t[3]) {
+    int res[3][3];
+    faceTileRes(c, res);
+    size_t total = 0;
+    for (int a = 0; a < 3; ++a) {
+        for (int k = 0; k < 3; ++k) t[a].n[k] = (res[a][k] + AVS_TILE - 1) / AVS_TILE;
+        t[a].d = c->tiles.as<uint8_t>() + total;
+        total += (t[a].count() + 255) / 256 * 256;
+    }
+}
+static int avs_face_tile_maps(AvsContext *c, Grid3<uint8_t> t[3]) {   // allocates and zeroes
+    int res[3][3];
+    faceTileRes(c, res);
+    return tileGrid(c, c->tiles, t, res);
+}
+
 int avs_stage_regular_labels(AvsContext *c) {
     DeviceScene &S = c->S;
     int res[3][3];
@@ -930,11 +1058,15 @@ int avs_stage_regular_labels(AvsContext *c) {
     // One tile map per axis, dimensioned for the padded face grids; tile coordinates (idx/16) are the
     // same for the regular grid and for octree level 0, so stage 5 reuses these maps.
     Grid3<uint8_t> t[3];
-    int rc = tileGrid(c, c->tiles, t, res);
-    if (rc) return rc;
+    int rc = AVS_OK;
+    if (c->surfaceTilesMarked) avs_face_tile_views(c, t);   // filled by the weights stage (k_sign_x4)
+    else {
+        rc = avs_face_tile_maps(c, t);
+        if (rc) return rc;
+        LAUNCH_3D(c, k_mark_surface_tiles, S.N, S, t[0], t[1], t[2]);
+    }
     unsigned long long *cnt = c->counters.as<unsigned long long>();
     AVS_CUDA_CHECK(cudaMemsetAsync(cnt + 16, 0, 3 * sizeof(unsigned long long), c->stream));
-    LAUNCH_3D(c, k_mark_surface_tiles, S.N, S, t[0], t[1], t[2]);
     // Multi-GPU: the regular grid is only read by stage 11 (which regular faces are written back, AV.cpp:2843-2890) and by
     // the regular DOF count, both per-face work with no coupling -- so every rank classifies, and later fills, only its own
     // slab of z-planes (avs_slab_cuts); the count is summed over ranks, the output slabs are all-gathered after stage 11.

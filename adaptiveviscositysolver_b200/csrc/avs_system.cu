@@ -260,15 +260,43 @@ __global__ void k_restrict_fine(const __grid_constant__ DeviceScene S, const Row
     for (int q = 0; q < 7 * 16; ++q) acc += restrictHatTerm(S, k.axis, 2, face, q);
     x0[i] = acc * (1.0 / 256.0);  // 16^-l
 }
-// levels >= 3: one CTA per row, terms strided over the threads, fixed-order tree reduction
-__global__ void k_restrict_coarse(const __grid_constant__ DeviceScene S, const RowKey *keys, const int32_t *rows, double *x0) {
-    long long i = rows[blockIdx.x];
-    RowKey k = keys[i];
-    I3 face = mk3(k.i, k.j, k.k);
+// levels >= 3: a row's (2^(l+1) - 1) 4^l terms are split into restrictSplit(l) work items of <= ~16 K terms, one CTA each -- one
+// CTA per ROW left the few top-level rows (4.2 M terms each at level 7) as a serial tail longer than all other rows together.
+// k_collect_coarse_rows (two passes: count, then fill) lists the rows and their work items; every CTA reduces its strided share in
+// a fixed order into partial[item]; k_restrict_coarse_finish adds a row's parts in ascending order: deterministic, the same on
+// every rank count.
+#define RESTRICT_MAX_SPLIT 256
+__host__ __device__ __forceinline__ int restrictSplit(int level) {
+    const long long side = 1ll << level, terms = (2 * side - 1) * side * side;
+    const long long s = (terms + 16383) / 16384;
+    return (int)(s < 1 ? 1 : (s > RESTRICT_MAX_SPLIT ? RESTRICT_MAX_SPLIT : s));
+}
+// counters[0] = coarse rows, counters[1] = work items.  fill == 0: count only.
+__global__ void k_collect_coarse_rows(const RowKey *keys, long long base, long long n, int fill, int32_t *rows, long long *rowItemBase, int2 *items,
+                                      unsigned long long *counters) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    i += base;
+    const int level = keys[i].level;
+    if (level < 3) return;
+    const int split = restrictSplit(level);
+    const unsigned long long slot = atomicAdd(&counters[0], 1ull);           // order is irrelevant: every row is written exactly once
+    const unsigned long long first = atomicAdd(&counters[1], (unsigned long long)split);
+    if (!fill) return;
+    rows[slot] = (int32_t)i;
+    rowItemBase[slot] = (long long)first;
+    for (int p = 0; p < split; ++p) items[first + p] = make_int2((int)slot, p);
+}
+__global__ void k_restrict_coarse(const __grid_constant__ DeviceScene S, const RowKey *keys, const int32_t *rows, const int2 *items, double *partial) {
+    const int2 item = items[blockIdx.x];
+    const long long i = rows[item.x];
+    const RowKey k = keys[i];
+    const int split = restrictSplit(k.level), part = item.y;
+    const I3 face = mk3(k.i, k.j, k.k);
     const long long side = 1ll << k.level;
     const long long terms = (2 * side - 1) * side * side;
     double acc = 0;
-    for (long long q = threadIdx.x; q < terms; q += blockDim.x) acc += restrictHatTerm(S, k.axis, k.level, face, q);
+    for (long long q = (long long)part * blockDim.x + threadIdx.x; q < terms; q += (long long)blockDim.x * split) acc += restrictHatTerm(S, k.axis, k.level, face, q);
     __shared__ double sh[256];
     sh[threadIdx.x] = acc;
     __syncthreads();
@@ -276,16 +304,19 @@ __global__ void k_restrict_coarse(const __grid_constant__ DeviceScene S, const R
         if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) x0[i] = sh[0] / (double)(side * side * side * side);  // 16^-l, exact power of two
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
-__global__ void k_collect_coarse_rows(const RowKey *keys, long long base, long long n, int32_t *rows, unsigned long long *counter) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    i += base;
-    if (keys[i].level >= 3) {
-        unsigned long long slot = atomicAdd(counter, 1ull);
-        rows[slot] = (int32_t)i;  // order is irrelevant: every row is written exactly once
-    }
+__global__ void k_restrict_coarse_finish(const RowKey *keys, const int32_t *rows, const long long *rowItemBase, unsigned long long nCoarse, const double *partial,
+                                         double *x0) {
+    const unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nCoarse) return;
+    const long long i = rows[r];
+    const int level = keys[i].level, split = restrictSplit(level);
+    const double *part = partial + rowItemBase[r];
+    double acc = 0;
+    for (int p = 0; p < split; ++p) acc += part[p];
+    const long long side = 1ll << level;
+    x0[i] = acc / (double)(side * side * side * side);  // 16^-l, exact power of two
 }
 
 // Multi-GPU: a rank restricts only the rows it owns -- the assembly reads x0 of its own rows (rhs += M u^n) and the CG stages its
@@ -303,18 +334,28 @@ int avs_stage_restriction(AvsContext *c, bool allRows) {
     k_restrict_fine<<<blocks, 256, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), base, n, c->x0.as<double>());
     ++c->launches;
     if (c->S.levels > 3) {
-        // rows of level >= 3 are few (a few percent): compact their ids, then one CTA per row
-        if (c->coarseRows.reserve((size_t)n * sizeof(int32_t))) return AVS_ERR_ALLOC;   // own buffer: rowCount holds the assembled rows' lengths
-        unsigned long long *cnt = c->counters.as<unsigned long long>() + 24;
-        AVS_CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
-        k_collect_coarse_rows<<<blocks, 256, 0, c->stream>>>(c->rowKeys.as<RowKey>(), base, n, c->coarseRows.as<int32_t>(), cnt);
+        // rows of level >= 3 are few (a few percent): count them and their work items, then list them, then one CTA per item
+        unsigned long long *cnt = c->counters.as<unsigned long long>() + 40;   // slots 40, 41
+        unsigned long long h[2] = {0, 0};
+        AVS_CUDA_CHECK(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), c->stream));
+        k_collect_coarse_rows<<<blocks, 256, 0, c->stream>>>(c->rowKeys.as<RowKey>(), base, n, 0, nullptr, nullptr, nullptr, cnt);
         ++c->launches;
-        unsigned long long h = 0;
-        AVS_CUDA_CHECK(cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        AVS_CUDA_CHECK(cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
         AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        if (h > 0) {
-            k_restrict_coarse<<<(unsigned)h, 256, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), c->coarseRows.as<int32_t>(), c->x0.as<double>());
-            ++c->launches;
+        if (h[0] > 0) {
+            // one buffer: rows int32[h0] | item base int64[h0] | items int2[h1] | partial double[h1]
+            const size_t oBase = (h[0] * 4 + 255) / 256 * 256, oItems = oBase + (h[0] * 8 + 255) / 256 * 256, oPart = oItems + (h[1] * 8 + 255) / 256 * 256;
+            if (c->coarseRows.reserve(oPart + h[1] * 8)) return AVS_ERR_ALLOC;
+            char *buf = c->coarseRows.as<char>();
+            int32_t *rows = (int32_t *)buf;
+            long long *rowBase = (long long *)(buf + oBase);
+            int2 *items = (int2 *)(buf + oItems);
+            double *partial = (double *)(buf + oPart);
+            AVS_CUDA_CHECK(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), c->stream));
+            k_collect_coarse_rows<<<blocks, 256, 0, c->stream>>>(c->rowKeys.as<RowKey>(), base, n, 1, rows, rowBase, items, cnt);
+            k_restrict_coarse<<<(unsigned)h[1], 256, 0, c->stream>>>(c->S, c->rowKeys.as<RowKey>(), rows, items, partial);
+            k_restrict_coarse_finish<<<(unsigned)((h[0] + 255) / 256), 256, 0, c->stream>>>(c->rowKeys.as<RowKey>(), rows, rowBase, h[0], partial, c->x0.as<double>());
+            c->launches += 3;
         }
     }
     AVS_CUDA_CHECK(cudaGetLastError());
