@@ -307,23 +307,28 @@ __global__ void k_weights_classify4(const __grid_constant__ WeightGrids W, int s
     const size_t crow = (size_t)sn0 * ((size_t)cy + (size_t)sn1 * (size_t)cz);
     const int xb = (int)blockIdx.x * 512 + (int)threadIdx.x;
     uint8_t cls[4];
+    bool band4 = false;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int x = xb + 128 * j;
         cls[j] = (x <= sn0) ? signClass[crow + min(x, sn0 - 1)] : (uint8_t)0;
+        band4 = band4 || cls[j] == 2;
     }
+    // 98 % of the warps see no band sample at all: they only store (no ballots, no list logic)
+    const bool warpHasBand = __any_sync(0xffffffffu, band4);
 #pragma unroll
     for (int gi = 0; gi < 4; ++gi) {
         const Grid3<float> &g = W.g[gi];
-        const bool rowOk = y < g.n[1] && z < g.n[2];   // uniform over the CTA
-        if (!rowOk) continue;
-        const size_t row = (size_t)g.n[0] * ((size_t)y + (size_t)g.n[1] * (size_t)z);
+        if (!(y < g.n[1] && z < g.n[2])) continue;   // uniform over the CTA
+        float *rowp = g.d + (size_t)g.n[0] * ((size_t)y + (size_t)g.n[1] * (size_t)z);
+        const unsigned rowIdx = (unsigned)((size_t)g.n[0] * ((size_t)y + (size_t)g.n[1] * (size_t)z));   // lattice < 2^32 (checked on the host)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int x = xb + 128 * j;
             const bool in = x < g.n[0];
+            if (in && cls[j] != 2) rowp[x] = cls[j] == 0 ? 1.f : 0.f;
+            if (!warpHasBand) continue;
             const bool band = in && cls[j] == 2;
-            if (in && cls[j] != 2) g.d[row + x] = cls[j] == 0 ? 1.f : 0.f;
             const unsigned m = __ballot_sync(0xffffffffu, band);   // warp-aggregated append
             if (m) {
                 const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
@@ -331,7 +336,7 @@ __global__ void k_weights_classify4(const __grid_constant__ WeightGrids W, int s
                 if (lane == leader) base = atomicAdd(listCount + gi, (unsigned long long)__popc(m));
                 base = __shfl_sync(0xffffffffu, base, leader);
                 const unsigned long long slot = base + __popc(m & ((1u << lane) - 1));
-                if (band && slot < W.cap[gi]) W.list[gi][slot] = (uint32_t)(row + x);
+                if (band && slot < W.cap[gi]) W.list[gi][slot] = rowIdx + (unsigned)x;
             }
         }
     }
@@ -943,6 +948,9 @@ __global__ void k_tile_flags(Grid3<uint8_t> lab, Grid3<uint8_t> flags, Grid3<uin
 //   kind 0: face tiles of `axis` -- occupied (AV.cpp:886-943) and an adjacent cell may be other than UP, or the tile touches the
 //           low / high end of the grid on `axis` (domain-boundary faces are OUTSIDE, AV.cpp:1210-1215)
 //   kind 1: edge tiles -- occupied (AV.cpp:1002-1057)          kind 2: cell tiles with an ACTIVE cell
+//   kind 3: face tiles of `axis` ABOVE level 0 (occ.d unused, only its dimensions): the reference classifies every face there, but a
+//           face is FLUID only next to an ACTIVE cell (AV.cpp:1304-1318) and UNASSIGNED otherwise -- the tile or its lower neighbour
+//           on `axis` must hold an ACTIVE cell
 __global__ void k_tile_list(Grid3<uint8_t> occ, Grid3<uint8_t> flags, int kind, int axis, uint32_t *list, unsigned int *count) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= occ.count()) return;
@@ -950,7 +958,17 @@ __global__ void k_tile_list(Grid3<uint8_t> occ, Grid3<uint8_t> flags, int kind, 
     bool take;
     if (kind == 2) take = (flags.d[i] & TILE_HAS_ACTIVE) != 0;   // occ == flags grid
     else if (kind == 1) take = occ.d[i] != 0;
-    else {
+    else if (kind == 3) {
+        int t[3] = {tx, ty, tz};
+        take = false;
+        if (t[(axis + 1) % 3] < flags.n[(axis + 1) % 3] && t[(axis + 2) % 3] < flags.n[(axis + 2) % 3]) {
+            if (t[axis] < flags.n[axis]) take = (flags.d[flags.lin(t[0], t[1], t[2])] & TILE_HAS_ACTIVE) != 0;
+            if (!take && t[axis] > 0) {
+                --t[axis];
+                take = (flags.d[flags.lin(t[0], t[1], t[2])] & TILE_HAS_ACTIVE) != 0;
+            }
+        }
+    } else {
         take = false;
         if (occ.d[i]) {
             int t[3] = {tx, ty, tz};
@@ -979,30 +997,32 @@ __device__ __forceinline__ void forTileSamples(const uint32_t *list, const unsig
         f(x, y, z, (size_t)x + (size_t)n[0] * ((size_t)y + (size_t)n[1] * (size_t)z), inxy);
     }
 }
-__global__ void k_classify_faces_tiles(const __grid_constant__ DeviceScene S, int axis, Grid3<uint8_t> tiles, const uint32_t *list, const unsigned int *count) {
-    const Grid3<int32_t> g = S.face[0][axis];
+__global__ void k_classify_faces_tiles(const __grid_constant__ DeviceScene S, int level, int axis, Grid3<uint8_t> tiles, const uint32_t *list,
+                                       const unsigned int *count) {
+    const Grid3<int32_t> g = S.face[level][axis];
     forTileSamples(list, count, g.n, [&](int x, int y, int z, size_t idx, bool ok) {
-        if (ok) g.d[idx] = classifyFace(S, 0, axis, tiles, x, y, z);
+        if (ok) g.d[idx] = classifyFace(S, level, axis, tiles, x, y, z);
     });
 }
-__global__ void k_classify_edges_tiles(const __grid_constant__ DeviceScene S, int axis, Grid3<uint8_t> tiles, const uint32_t *list, const unsigned int *count,
-                                       unsigned long long *counter) {
-    const Grid3<int8_t> g = S.edge[0][axis];
+__global__ void k_classify_edges_tiles(const __grid_constant__ DeviceScene S, int level, int axis, Grid3<uint8_t> tiles, const uint32_t *list,
+                                       const unsigned int *count, unsigned long long *counter) {
+    const Grid3<int8_t> g = S.edge[level][axis];
     forTileSamples(list, count, g.n, [&](int x, int y, int z, size_t idx, bool ok) {
         int8_t out = F_UNASSIGNED;
         if (ok) {
-            out = classifyEdge(S, 0, axis, tiles, x, y, z);
+            out = classifyEdge(S, level, axis, tiles, x, y, z);
             g.d[idx] = out;
         }
         countWarp(ok && out == F_FLUID, counter);
     });
 }
-__global__ void k_classify_centers_tiles(const __grid_constant__ DeviceScene S, const uint32_t *list, const unsigned int *count, unsigned long long *counter) {
-    const Grid3<int8_t> g = S.center[0];
+__global__ void k_classify_centers_tiles(const __grid_constant__ DeviceScene S, int level, const uint32_t *list, const unsigned int *count,
+                                         unsigned long long *counter) {
+    const Grid3<int8_t> g = S.center[level];
     forTileSamples(list, count, g.n, [&](int x, int y, int z, size_t idx, bool ok) {
         int8_t out = F_UNASSIGNED;
         if (ok) {
-            out = classifyCenter(S, 0, x, y, z, idx);
+            out = classifyCenter(S, level, x, y, z, idx);
             g.d[idx] = out;
         }
         countWarp(ok && out == F_FLUID, counter);
@@ -1202,7 +1222,7 @@ __device__ __forceinline__ void brickThreadCount(const DeviceScene &S, int level
     }
 }
 
-// `tileFlags` (level 0 only, may be null): flags of the 16^3 cell tiles (k_tile_flags).  A level-0 face is a DOF only next to an ACTIVE
+// `tileFlags` (d may be null): flags of the level's 16^3 cell tiles (k_tile_flags).  A face is a DOF only next to an ACTIVE
 // cell, so a brick whose tile and whose three lower neighbour tiles hold no ACTIVE cell has no rows: it is not read at all.
 __global__ void k_brick_count(const __grid_constant__ DeviceScene S, const __grid_constant__ BrickLayout bl, int level, int32_t *brickCount,
                               int32_t *brickCost, Grid3<uint8_t> tileFlags) {
@@ -1432,9 +1452,22 @@ int avs_stage_octree_labels(AvsContext *c) {
     // AVS_LABELS=dense: level 0 through the dense sweeps as well (round 1; A/B measurements and the bit-equality test)
     static int dense0 = -1;
     if (dense0 < 0) { const char *e = getenv("AVS_LABELS"); dense0 = (e && strcmp(e, "dense") == 0) ? 1 : 0; }
-    Grid3<uint8_t> tileFlags;
-    tileFlags.d = nullptr;
-    tileFlags.n[0] = tileFlags.n[1] = tileFlags.n[2] = 0;
+    // tile flags of every level that is classified tile by tile: levels with at least 4 tiles on every axis (the others are tiny)
+    Grid3<uint8_t> flagsL[AVS_MAX_LEVELS];
+    size_t flagBytes = 0, flagOff[AVS_MAX_LEVELS];
+    for (int l = 0; l < L; ++l) {
+        flagsL[l].d = nullptr;
+        for (int k = 0; k < 3; ++k) flagsL[l].n[k] = (S.label[l].n[k] + AVS_TILE - 1) / AVS_TILE;
+        flagOff[l] = flagBytes;
+        const bool tiled = !dense0 && (l == 0 || (flagsL[l].n[0] >= 4 && flagsL[l].n[1] >= 4 && flagsL[l].n[2] >= 4));
+        if (tiled) flagBytes += (flagsL[l].count() + 255) / 256 * 256;
+        else flagsL[l].n[0] = 0;   // marks "dense"
+    }
+    if (flagBytes && c->tileFlags.reserve(flagBytes)) return AVS_ERR_ALLOC;
+    for (int l = 0; l < L; ++l)
+        if (flagsL[l].n[0] > 0) flagsL[l].d = c->tileFlags.as<uint8_t>() + flagOff[l];
+    Grid3<uint8_t> tileFlags = flagsL[0];   // level 0: also used by the interpolator (avs_prolong.cu)
+    if (!tileFlags.d) tileFlags.n[0] = tileFlags.n[1] = tileFlags.n[2] = 0;
     for (int l = 0; l < L; ++l) {
         Grid3<uint8_t> te[3];
         int res[3][3];
@@ -1442,34 +1475,40 @@ int avs_stage_octree_labels(AvsContext *c) {
             for (int k = 0; k < 3; ++k) res[a][k] = S.edge[l][a].n[k];
         int rc = tileGrid(c, edgeTiles, te, res);
         if (rc) return rc;
-        if (l == 0 && !dense0) {
-            // ---- level 0, tile-culled (see k_tile_flags) ----
-            for (int k = 0; k < 3; ++k) tileFlags.n[k] = (S.label[0].n[k] + AVS_TILE - 1) / AVS_TILE;
-            size_t listCap = tileFlags.count();
-            for (int a = 0; a < 3; ++a) listCap = std::max(listCap, std::max(t0[a].count(), te[a].count()));
-            if (tileFlags.n[0] > 1023 || tileFlags.n[1] > 1023 || tileFlags.n[2] > 1023) return AVS_ERR_UNSUPPORTED;   // packed tile coordinates
-            if (c->tileFlags.reserve(tileFlags.count()) || c->tileLists.reserve(7 * listCap * sizeof(uint32_t))) return AVS_ERR_ALLOC;
-            tileFlags.d = c->tileFlags.as<uint8_t>();
+        if (flagsL[l].d) {
+            // ---- tile-culled (see k_tile_flags) ----
+            const Grid3<uint8_t> fl = flagsL[l];
+            Grid3<uint8_t> ft[3];   // face tile grids: the occupancy maps at level 0, dimensions only above
+            for (int a = 0; a < 3; ++a) {
+                ft[a] = t0[a];
+                if (l > 0) {
+                    ft[a].d = nullptr;
+                    for (int k = 0; k < 3; ++k) ft[a].n[k] = (S.label[l].n[k] + 1 + AVS_TILE - 1) / AVS_TILE;
+                }
+            }
+            size_t listCap = fl.count();
+            for (int a = 0; a < 3; ++a) listCap = std::max(listCap, std::max(ft[a].count(), te[a].count()));
+            if (ft[0].n[0] > 1023 || ft[0].n[1] > 1023 || ft[0].n[2] > 1023) return AVS_ERR_UNSUPPORTED;   // packed tile coordinates
+            if (c->tileLists.reserve(7 * listCap * sizeof(uint32_t))) return AVS_ERR_ALLOC;
             unsigned int *lcnt = (unsigned int *)(cnt + 32);   // 7 list lengths in counter slots 32..35
             AVS_CUDA_CHECK(cudaMemsetAsync(lcnt, 0, 8 * sizeof(unsigned int), c->stream));
-            k_tile_flags<<<dim3((unsigned)tileFlags.n[0], (unsigned)tileFlags.n[1], (unsigned)tileFlags.n[2]), 256, 0, c->stream>>>(S.label[0], tileFlags, te[0],
-                                                                                                                        te[1], te[2]);
+            k_tile_flags<<<dim3((unsigned)fl.n[0], (unsigned)fl.n[1], (unsigned)fl.n[2]), 256, 0, c->stream>>>(S.label[l], fl, te[0], te[1], te[2]);
             ++c->launches;
             uint32_t *lists = c->tileLists.as<uint32_t>();
             for (int a = 0; a < 3; ++a) {
-                AVS_CUDA_CHECK(cudaMemsetAsync(S.face[0][a].d, 0xFF, S.face[0][a].count() * sizeof(int32_t), c->stream));   // F_UNASSIGNED
-                AVS_CUDA_CHECK(cudaMemsetAsync(S.edge[0][a].d, 0xFF, S.edge[0][a].count(), c->stream));
+                AVS_CUDA_CHECK(cudaMemsetAsync(S.face[l][a].d, 0xFF, S.face[l][a].count() * sizeof(int32_t), c->stream));   // F_UNASSIGNED
+                AVS_CUDA_CHECK(cudaMemsetAsync(S.edge[l][a].d, 0xFF, S.edge[l][a].count(), c->stream));
             }
-            AVS_CUDA_CHECK(cudaMemsetAsync(S.center[0].d, 0xFF, S.center[0].count(), c->stream));
+            AVS_CUDA_CHECK(cudaMemsetAsync(S.center[l].d, 0xFF, S.center[l].count(), c->stream));
             for (int a = 0; a < 3; ++a) {
-                k_tile_list<<<(unsigned)((t0[a].count() + 255) / 256), 256, 0, c->stream>>>(t0[a], tileFlags, 0, a, lists + (size_t)a * listCap, lcnt + a);
-                k_classify_faces_tiles<<<(unsigned)t0[a].count(), 256, 0, c->stream>>>(S, a, t0[a], lists + (size_t)a * listCap, lcnt + a);
-                k_tile_list<<<(unsigned)((te[a].count() + 255) / 256), 256, 0, c->stream>>>(te[a], tileFlags, 1, a, lists + (size_t)(3 + a) * listCap, lcnt + 3 + a);
-                k_classify_edges_tiles<<<(unsigned)te[a].count(), 256, 0, c->stream>>>(S, a, te[a], lists + (size_t)(3 + a) * listCap, lcnt + 3 + a, cnt + 17);
+                k_tile_list<<<(unsigned)((ft[a].count() + 255) / 256), 256, 0, c->stream>>>(ft[a], fl, l == 0 ? 0 : 3, a, lists + (size_t)a * listCap, lcnt + a);
+                k_classify_faces_tiles<<<(unsigned)ft[a].count(), 256, 0, c->stream>>>(S, l, a, t0[a], lists + (size_t)a * listCap, lcnt + a);
+                k_tile_list<<<(unsigned)((te[a].count() + 255) / 256), 256, 0, c->stream>>>(te[a], fl, 1, a, lists + (size_t)(3 + a) * listCap, lcnt + 3 + a);
+                k_classify_edges_tiles<<<(unsigned)te[a].count(), 256, 0, c->stream>>>(S, l, a, te[a], lists + (size_t)(3 + a) * listCap, lcnt + 3 + a, cnt + 17);
                 c->launches += 4;
             }
-            k_tile_list<<<(unsigned)((tileFlags.count() + 255) / 256), 256, 0, c->stream>>>(tileFlags, tileFlags, 2, 0, lists + 6 * listCap, lcnt + 6);
-            k_classify_centers_tiles<<<(unsigned)tileFlags.count(), 256, 0, c->stream>>>(S, lists + 6 * listCap, lcnt + 6, cnt + 18);
+            k_tile_list<<<(unsigned)((fl.count() + 255) / 256), 256, 0, c->stream>>>(fl, fl, 2, 0, lists + 6 * listCap, lcnt + 6);
+            k_classify_centers_tiles<<<(unsigned)fl.count(), 256, 0, c->stream>>>(S, l, lists + 6 * listCap, lcnt + 6, cnt + 18);
             c->launches += 2;
             continue;
         }
@@ -1497,9 +1536,7 @@ int avs_stage_octree_labels(AvsContext *c) {
     if (c->brickOffset.reserve((size_t)total * sizeof(long long))) return AVS_ERR_ALLOC;
     for (int l = 0; l < L; ++l) {
         unsigned nb = (unsigned)((long long)bl.nb[l][0] * bl.nb[l][1] * bl.nb[l][2]);
-        Grid3<uint8_t> cull = tileFlags;
-        if (l > 0) cull.d = nullptr;
-        k_brick_count<<<nb, 256, 0, c->stream>>>(S, bl, l, c->brickCount.as<int32_t>(), c->brickCost.as<int32_t>(), cull);
+        k_brick_count<<<nb, 256, 0, c->stream>>>(S, bl, l, c->brickCount.as<int32_t>(), c->brickCost.as<int32_t>(), flagsL[l]);
         ++c->launches;
     }
     int64_t nRows = 0;

@@ -1,4 +1,4 @@
-# Round 2, call U (1 GPU): surface tile marking fused into the sign pass -- full suite + C3 + C4.
+# Round 2, call U (1 GPU): validation of the latest labelling changes -- full suite + C3 + C4.
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q --tb=short 2>&1 | tail -30 > gpurun_out/r2u_pytest_gpu.log; tail -6 gpurun_out/r2u_pytest_gpu.log
 run() { name=$1; shift; "$@" > gpurun_out/r2u_$name.json 2> gpurun_out/r2u_$name.err; python - <<PY
