@@ -46,8 +46,8 @@ WORKLOADS = {
     "c2lit": dict(n=128, R=56, L=5, tol=1e-6, desc="C2 (literal) 128^3 R=56 octree depth 5, ~0.5 M DOF"),
     "c3": dict(n=512, R=246, L=7, tol=1e-6, desc="C3 512^3 R=246 octree depth 7, ~10 M DOF"),
     "c3lit": dict(n=256, R=120, L=7, tol=1e-6, desc="C3 (literal) 256^3 R=120 octree depth 7, ~2.4 M DOF"),
-    # BASELINE.json configs[3] (~40 M DOF): fields generated on the device (scenes_torch), never resident in host memory.
-    # Not yet run on a GPU (added after the round's GPU budget was spent); needs ~120 GB of HBM on one GPU.
+    # BASELINE.json configs[3] (~40 M DOF, the config of the >= 6x multi-GPU target): fields generated on the device (scenes_torch),
+    # never resident in host memory; fits one B200 (N = 40,270,056, 462 iterations; profiles/r2_scaling.md has 1 / 2 / 4 / 8 GPUs).
     "c4": dict(n=1024, R=492, L=8, tol=1e-6, device_gen=True, desc="C4 1024^3 R=492 octree depth 8, ~40 M DOF (device-generated fields)"),
     # BASELINE.json configs[4]: 10 prescribed-geometry frames of the buckling sheet (scenes.buckling_sheet); frames are
     # independent solves, so they are dealt round-robin to the ranks with no data-path collective

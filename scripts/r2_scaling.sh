@@ -21,5 +21,4 @@ run c3 --workload c3 --steps 3 --warmup 3 --no-cpu-baseline
 if [ "$N" = "2" ]; then AVS_PCG_KERNEL=v1 run c3_v1 --workload c3 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e; fi
 run c4 --workload c4 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e
 if [ "$N" = "2" ]; then AVS_PCG_KERNEL=v1 run c4_v1 --workload c4 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e; fi
-if [ "$N" != "2" ]; then AVS_PCG_CTAS_PER_SM=2 run c3_cta2 --workload c3 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e; fi
 if [ "$N" = "8" ]; then run c5 --workload c5 --steps 3 --warmup 3 --no-cpu-baseline; run c3_gather --workload c3 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --gather-output; fi
