@@ -171,33 +171,6 @@ __device__ void sdfWeightSample(Grid3<float> w, const DField &sdf, double off0, 
     w.d[idx] = (float)((double)count / total);
 }
 
-// Light pass (aligned sdf grid only): weight = 1 / 0 from the precomputed sign class of the sample's voxel
-// neighbourhood; samples in the mixed band are appended to `list` for k_sdf_weights (few registers, full occupancy:
-// the register-heavy sampler below ran the trivial 98 % of the samples at 12 % occupancy).
-__global__ void k_weights_classify(Grid3<float> w, int sn0, int sn1, int sn2, const uint8_t *signClass, uint32_t *list,
-                                   unsigned long long *listCount) {
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y), z = (int)blockIdx.z;
-    bool band = false;
-    size_t idx = 0;
-    if (x < w.n[0] && y < w.n[1]) {
-        idx = w.lin(x, y, z);
-        int cx = min(x, sn0 - 1), cy = min(y, sn1 - 1), cz = min(z, sn2 - 1);
-        uint8_t cls = signClass[(size_t)cx + (size_t)sn0 * ((size_t)cy + (size_t)sn1 * cz)];
-        if (cls == 0) w.d[idx] = 1.f;
-        else if (cls == 1) w.d[idx] = 0.f;
-        else band = true;
-    }
-    // warp-aggregated append
-    unsigned m = __ballot_sync(0xffffffffu, band);
-    if (m) {
-        int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-        unsigned long long base = 0;
-        if (lane == leader) base = atomicAdd(listCount, (unsigned long long)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (band) list[base + __popc(m & ((1u << lane) - 1))] = (uint32_t)idx;
-    }
-}
-
 __global__ void k_sdf_weights(Grid3<float> w, DField sdf, double off0, double off1, double off2, double o0,
                               double o1, double o2, double dx0, int n, double dilate, const uint8_t *signClass,
                               const uint32_t *list, const unsigned long long *listCount) {
@@ -348,31 +321,14 @@ __global__ void k_divide_where_positive(float *a, const float *b, size_t n) {
     if (i < n && b[i] > 0.f) a[i] = a[i] / b[i];
 }
 
+// dense supersampling of one weight grid (the collision weights of doApplySolidWeights: any grid, dilated, no sign classes)
 static int weightsFor(AvsContext *c, DevBuf &buf, Grid3<float> &g, const DField &sdf, const double off[3],
-                      const int res[3], int n, double dilate, const uint8_t *signClass) {
+                      const int res[3], int n, double dilate) {
     g.n[0] = res[0]; g.n[1] = res[1]; g.n[2] = res[2];
     if (buf.reserve(g.count() * sizeof(float))) return AVS_ERR_ALLOC;
     g.d = buf.as<float>();
-    if (signClass && g.count() < 0xffffffffull) {
-        if (c->bandList.reserve(g.count() * sizeof(uint32_t))) return AVS_ERR_ALLOC;
-        unsigned long long *cnt = c->counters.as<unsigned long long>() + 30;
-        AVS_CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
-        dim3 grid((unsigned)((g.n[0] + 127) / 128), (unsigned)((g.n[1] + CELL_YB - 1) / CELL_YB), (unsigned)g.n[2]);
-        k_weights_classify<<<grid, dim3(128, CELL_YB), 0, c->stream>>>(g, sdf.n[0], sdf.n[1], sdf.n[2], signClass, c->bandList.as<uint32_t>(), cnt);
-        ++c->launches;
-        unsigned long long h = 0;
-        AVS_CUDA_CHECK(cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-        AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        if (h > 0) {
-            k_sdf_weights<<<(unsigned)((h + 127) / 128), 128, 0, c->stream>>>(g, sdf, off[0], off[1], off[2], c->S.origin[0], c->S.origin[1],
-                                                                            c->S.origin[2], c->S.dx0, n, dilate, nullptr,
-                                                                            c->bandList.as<uint32_t>(), cnt);
-            ++c->launches;
-        }
-        return AVS_OK;
-    }
     LAUNCH_3D(c, k_sdf_weights, g.n, g, sdf, off[0], off[1], off[2], c->S.origin[0], c->S.origin[1],
-              c->S.origin[2], c->S.dx0, n, dilate, signClass, nullptr, nullptr);
+              c->S.origin[2], c->S.dx0, n, dilate, nullptr, nullptr, nullptr);
     return AVS_OK;
 }
 
@@ -457,13 +413,13 @@ int avs_stage_weights(AvsContext *c, const AvsParams *p) {
     if (p->do_apply_solid_weights) {  // AV.cpp:772-790
         DevBuf &tmp = c->solidW;
         Grid3<float> g;
-        rc = weightsFor(c, tmp, g, S.collision, offC, S.N, n, -S.extrap, nullptr);
+        rc = weightsFor(c, tmp, g, S.collision, offC, S.N, n, -S.extrap);
         if (rc) return rc;
         LAUNCH_1D(c, k_divide_where_positive, g.count(), S.centerW.d, g.d, g.count());
         for (int a = 0; a < 3; ++a) {
             double off[3] = {0, 0, 0};
             off[a] = 0.5;
-            rc = weightsFor(c, tmp, g, S.collision, off, S.edgeW[a].n, n, -S.extrap, nullptr);
+            rc = weightsFor(c, tmp, g, S.collision, off, S.edgeW[a].n, n, -S.extrap);
             if (rc) return rc;
             LAUNCH_1D(c, k_divide_where_positive, g.count(), S.edgeW[a].d, g.d, g.count());
         }
