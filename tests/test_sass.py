@@ -66,3 +66,23 @@ def test_ring_variant_uses_async_copies_and_tma_variant_bulk_copies(sass):
     assert ring and all(any("LDGSTS" in l for l in sass[n]) for n in ring)
     tma = [n for n in sass if "k_spmv_tma" in n]
     assert tma and all(any("UBLKCP" in l for l in sass[n]) for n in tma)
+
+
+def test_closed_form_assembly_kernel_uses_no_local_memory(sass):
+    """k_assemble_simple exists because the generic assembly pass is bound by per-thread local memory (stencil + row accumulator +
+    spills, profiles/r2_assembly_ncu_summary.md): the closed-form kernel must keep everything in registers and write its entries
+    straight to the staging area -- no LDL / STL at all."""
+    names = [n for n in sass if "k_assemble_simple" in n]
+    assert len(names) == 1
+    local = [l for l in sass[names[0]] if re.search(r"\b(LDL|STL)\b", l)]
+    assert not local, local[:3]
+
+
+def test_fp32_persistent_kernel_prefetches_the_next_trip(sass):
+    """The fp32 default (k_cg_persistent2<float, float2, 1, 4>) differs from the base slice loop by the L2 prefetch of the next trip's
+    matrix stream (profiles/r2_fp32_c3_ncu_summary.md: -8 % SpMV time); it must still be in the generated code."""
+    names = [n for n in sass if "k_cg_persistent2If6float2Li1ELi4E" in n]
+    assert len(names) == 1
+    assert any(re.search(r"\bCCTL\.E\.PF2\b", l) for l in sass[names[0]]), "no L2 prefetch (CCTL.E.PF2) in the fp32 default kernel"
+    base = [n for n in sass if "k_cg_persistent2If6float2Li0ELi4E" in n]
+    assert len(base) == 1 and not any(re.search(r"\bCCTL\.E\.PF2\b", l) for l in sass[base[0]])   # the base slice loop has none
