@@ -29,6 +29,13 @@ static inline void enterContext(AvsContext *c) {
     g_avsTlsStream = c->stream;
 }
 
+// leaving an entry point: a context-level message (c->lastError, e.g. why a scene is AVS_ERR_UNSUPPORTED) becomes the text
+// avs_last_error() returns on this thread; AVS_ERR_CUDA keeps the text of the failed CUDA call (avs_set_last_error)
+static inline int leaveContext(AvsContext *c, int rc) {
+    if (rc != AVS_OK && rc != AVS_ERR_CUDA && !c->lastError.empty()) snprintf(g_lastError, sizeof(g_lastError), "%s", c->lastError.c_str());
+    return rc;
+}
+
 void avs_set_last_error(const char *what, cudaError_t e, const char *file, int line) {
     snprintf(g_lastError, sizeof(g_lastError), "%s failed: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
     cudaGetLastError();
@@ -492,9 +499,10 @@ int avs_assemble(AvsContext *c, const AvsFields *in, const AvsParams *p, AvsResu
     memset(res->stage_ms, 0, sizeof(res->stage_ms));
     c->launches = 0;
     c->spmvLaunches = 0;
+    c->lastError.clear();
     int rc = runAssemble(c, in, p, res);
     res->status = rc;
-    return rc;
+    return leaveContext(c, rc);
 }
 
 int avs_build_octree(AvsContext *c, const AvsFields *in, const AvsParams *p, AvsResult *res) {
@@ -550,6 +558,7 @@ int avs_solve(AvsContext *c, const AvsFields *in, const AvsParams *p, AvsVelocit
     c->launches = 0;
     c->spmvLaunches = 0;
     cudaEventRecord(c->ev[AVS_STAGE_COUNT], c->stream);
+    c->lastError.clear();
     int rc = runAssemble(c, in, p, res);
     if (rc == AVS_OK) rc = runSolve(c, p, res);
     if (rc == AVS_OK && out) rc = runApply(c, out, res);
@@ -561,7 +570,7 @@ int avs_solve(AvsContext *c, const AvsFields *in, const AvsParams *p, AvsVelocit
         res->stage_ms[AVS_STAGE_TOTAL] = ms;
     }
     res->status = rc;
-    return rc;
+    return leaveContext(c, rc);
 }
 
 // ---- read-back ------------------------------------------------------------------------------

@@ -11,9 +11,14 @@
 #endif
 #endif
 
-#define MAX_ROW 64
+// Longest row: a coarse face whose whole neighbourhood is one level finer couples to 64 fine faces + itself = 65 entries (32 fine
+// faces of its own axis, 16 of each transverse axis).  Sphere drops never produce one (their rows end at 46 entries); a droplet a
+// few cells across, or liquid folded over a solid, does: 18 of the first 300 scenes of scripts/fuzz_reference_pin.py hold a 65-entry
+// row, none a longer one.  Only the entries a row really has are ever touched in local memory, so the capacity costs nothing there;
+// the staging area of the assembly is MAX_ROW deep (avs_stage_system).
+#define MAX_ROW 80
 
-// Default: linear search over the entries collected so far (rows have 2..46 entries).
+// Linear search over the entries collected so far (rows have 2..65 entries, 16.7 on average).
 struct RowAcc {
     int n;
     int overflow;
@@ -28,8 +33,9 @@ struct RowAcc {
     }
 };
 
-// Experimental (AVS_ASM_ROW=hash): same entries in the same insertion order -- hence bit-identical rows -- but the search goes
-// through a 128-slot open-addressing table of entry indices (load factor <= 0.5): ~1.3 probes per add instead of n/2 compares.
+// Default (AVS_ASM_ROW=linear selects the one above): same entries in the same insertion order -- hence bit-identical rows -- but
+// the search goes through a 128-slot open-addressing table of entry indices (load factor <= 0.625): ~1.3 probes per add instead of
+// n/2 compares.
 // ncu on the default (profiles/r1_experiments.md): 39 % of the assembly kernel's stall samples sit on the compares of the linear
 // search, 1.0e9 of its 8.0e9 warp instructions are those compares, another 1.1e9 their branches.
 struct RowAccHash {
@@ -55,6 +61,6 @@ struct RowAccHash {
             if (col[s] == c) { val[s] += v; return; }
             h = (h + 1) & 127u;
         }
-        overflow = 1;   // table full: cannot happen with MAX_ROW = 64 < 128
+        overflow = 1;   // table full: cannot happen with MAX_ROW = 80 < 128
     }
 };

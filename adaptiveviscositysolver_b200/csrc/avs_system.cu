@@ -725,6 +725,25 @@ __global__ void __launch_bounds__(128) k_assemble_simple(const __grid_constant__
     }
 }
 
+// Column check of the assembled rows.  A scene outside the reference's contract -- liquid that reaches the boundary of the grid: the
+// reference's own debug checks (octreeLabels.unitTest, edgeStressUnitTest, centerStresUnitTest, AV.cpp:411-413, 881) fail on such a
+// scene -- can leave a LABEL (< 0) where a stencil expects a degree of freedom: getEdgeStressFaces appends the parent of an UNASSIGNED
+// face without looking at it (`assert(parentVelocityIndex >= 0)` is compiled out of release builds, AV.cpp:1886-1894), and Eigen's
+// setFromTriplets then writes out of bounds.  Here such a row is detected before any kernel uses its columns as addresses (SJDS fill,
+// halo discovery, the CG's gathers) and the solve ends with AVS_ERR_UNSUPPORTED.  flag[1] = high half of the 64-bit word whose low
+// half is k_assemble's overflow flag.
+__global__ void k_check_columns(long long nLocal, long long stride, const int32_t *rowCount, const int32_t *stageCol, long long nRows, int *flag) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nLocal) return;
+    const int n = rowCount[r];
+    bool bad = false;
+    for (int i = 0; i < n; ++i) {
+        const int32_t col = stageCol[(long long)i * stride + r];
+        bad |= col < 0 || (long long)col >= nRows;
+    }
+    if (bad) flag[1] = 1;
+}
+
 // canonical CSR from the staging area (lazy: only for read-back)
 __global__ void k_csr_from_stage(long long nLocal, long long stride, const int32_t *rowCount, const long long *ptr,
                                  const int32_t *stageCol, const double *stageVal, int32_t *col, double *val) {
@@ -763,6 +782,7 @@ int avs_stage_system(AvsContext *c, const AvsParams *p) {
     int *flag = (int *)(c->counters.as<unsigned long long>() + 25);
     AVS_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(unsigned long long), c->stream));
     c->nnz = 0;
+    bool rowListCountHost = false;   // the split assembly ran (counter 27 holds the rows it left for k_assemble)
     if (c->faceWRow.reserve((size_t)std::max<long long>(c->nRows, 1) * sizeof(float))) return AVS_ERR_ALLOC;
     if (c->rowMass.reserve((size_t)std::max<long long>(nLocal, 1) * sizeof(double))) return AVS_ERR_ALLOC;
     // face weights that were uploaded whole (pageable host arrays) must have landed; mapped ones are read in place
@@ -797,6 +817,7 @@ int avs_stage_system(AvsContext *c, const AvsParams *p) {
             ++c->launches;
             rowList = c->asmRowList.as<int32_t>();
             rowListCount = lc;
+            rowListCountHost = true;
         }
 #define ASM_LAUNCH(M)                                                                                                              \
     do {                                                                                                                           \
@@ -815,23 +836,40 @@ int avs_stage_system(AvsContext *c, const AvsParams *p) {
         else ASM_LAUNCH(4);
 #undef ASM_LAUNCH
         ++c->launches;
+        k_check_columns<<<(unsigned)((nLocal + 255) / 256), 256, 0, c->stream>>>(nLocal, stride, c->rowCount.as<int32_t>(), c->stageCol.as<int32_t>(), c->nRows, flag);
+        ++c->launches;
         int64_t nnz = 0;
         int rc = avs_exclusive_scan_i32_to_i64(c, c->rowCount.as<int32_t>(), c->csrPtr.as<int64_t>(), nLocal, &nnz);
         if (rc) return rc;
         c->nnz = nnz;
         AVS_CUDA_CHECK(cudaMemcpyAsync(c->csrPtr.as<long long>() + nLocal, &c->nnz, sizeof(long long), cudaMemcpyHostToDevice, c->stream));
-        unsigned long long hc[3] = {0, 0, 0};   // counters 25 (overflow flag, low word), 26 (stage 11), 27 (rows left for k_assemble)
+    } else {
+        long long z = 0;
+        AVS_CUDA_CHECK(cudaMemcpyAsync(c->csrPtr.p, &z, sizeof(z), cudaMemcpyHostToDevice, c->stream));
+    }
+    {
+        // the two error flags of the assembly (word 25: overflow in the low half, invalid column in the high half): summed over the
+        // ranks, so that every rank of a row-partitioned solve leaves with the same status instead of waiting for a peer that left
+        if (c->nranks > 1) {
+            int rc = avs_dist_allreduce_u64(c, c->counters.as<unsigned long long>() + 25, 1);
+            if (rc) return rc;
+        }
+        unsigned long long hc[3] = {0, 0, 0};   // counters 25 (error flags), 26 (stage 11), 27 (rows left for k_assemble)
         AVS_CUDA_CHECK(cudaMemcpyAsync(hc, c->counters.as<unsigned long long>() + 25, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
         AVS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
         if ((int)(hc[0] & 0xffffffffull)) {
             c->lastError = "a matrix row exceeded MAX_ROW entries";
             return AVS_ERR_UNSUPPORTED;
         }
-        c->asmGenericRows = rowListCount ? (long long)hc[2] : nLocal;
-        AVS_TRACE("assembly: %lld of %lld rows through k_assemble", c->asmGenericRows, nLocal);
-    } else {
-        long long z = 0;
-        AVS_CUDA_CHECK(cudaMemcpyAsync(c->csrPtr.p, &z, sizeof(z), cudaMemcpyHostToDevice, c->stream));
+        if (hc[0] >> 32) {
+            c->lastError = "a stress stencil references a face that is not a degree of freedom: the liquid reaches the boundary of the grid "
+                           "(the reference asserts on such a scene, HDK_AdaptiveViscosity.cpp:411-413, 881, 1891); pad the fields";
+            return AVS_ERR_UNSUPPORTED;
+        }
+        if (nLocal > 0) {
+            c->asmGenericRows = rowListCountHost ? (long long)hc[2] : nLocal;
+            AVS_TRACE("assembly: %lld of %lld rows through k_assemble", c->asmGenericRows, nLocal);
+        }
     }
     AVS_CUDA_CHECK(cudaGetLastError());
     c->haveSystem = true;

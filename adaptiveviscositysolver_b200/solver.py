@@ -196,7 +196,7 @@ class Solver:
 
     def _check(self, rc, where):
         if rc != AVS_OK:
-            raise AvsError(rc, where, _lib.last_error() if rc == -5 else "")
+            raise AvsError(rc, where, _lib.last_error() if rc in (-5, -10) else "")   # AVS_ERR_CUDA / AVS_ERR_UNSUPPORTED carry a message
 
     # ---- the pipeline
     def solve(self, scene: Scene, params: Params, out: Optional[List] = None) -> SolveInfo:

@@ -173,7 +173,7 @@ int avs_nccl_unique_id(void *out128);  /* rank 0: fill 128 bytes; the host broad
 int avs_create(const AvsDeviceConfig *cfg, AvsContext **out);
 void avs_destroy(AvsContext *ctx);
 const char *avs_status_string(int status);
-const char *avs_last_error(void);   /* detail of the last AVS_ERR_CUDA on this thread */
+const char *avs_last_error(void);   /* detail of the last AVS_ERR_CUDA / AVS_ERR_UNSUPPORTED on this thread */
 void avs_default_params(AvsParams *p);
 
 /* The drop-in call: replaces HDK_AdaptiveViscosity.cpp:233-707 in one shot. */

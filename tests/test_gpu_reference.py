@@ -56,6 +56,11 @@ def test_cuda_path_equals_compiled_reference(solver, name):
         R = ref.RefRun(sc, rp)
     finally:
         ref.set_threads(1)
+    check_cuda_against_reference(solver, sc, gp, R, tol)
+
+
+def check_cuda_against_reference(solver, sc, gp, R, tol):
+    """One avs_solve through the C-ABI against one run of the compiled reference on the same scene and options."""
     assert R.returned_true and not R.errors
     out = [v.data.copy() for v in sc.vel]
     info = solver.solve(sc, gp, out)
@@ -99,6 +104,59 @@ def test_cuda_path_equals_compiled_reference(solver, name):
         assert np.array_equal(out[a][untouched], sc.vel[a].data[untouched])   # AV.cpp:2843-2890
         equal += int((out[a] == ro).sum()); total += ro.size
     assert equal >= 0.98 * total
+
+
+# ---- random scenes --------------------------------------------------------------------------------------------------------------
+# scripts/fuzz_reference_pin.py draws scenes (unions of spheres and boxes on non-cubic grids with arbitrary origin and voxel size,
+# tilted solid planes and solid spheres with their own velocity -- optionally on a collision grid of their own resolution and
+# origin --, variable viscosity / density, velocity noise) and DOP options (octree levels, enhanced gradients, solid weights, band
+# width, super-samples, extrapolation, dt).  On the CPU the restated oracle is held to the compiled reference on those seeds
+# (tests/test_reference_fuzz.py); here the CUDA path is, on seeds that build 1-4 octree levels.  Tolerance 1e-10 and the default
+# iteration limit replace the drawn ones so that the solutions can be compared to 1e-7.
+FUZZ_SEEDS = [4, 15, 25, 34, 43, 48, 57, 61, 70, 77, 135, 192]      # 25, 48 and 135 hold a 65-entry row (the longest there is)
+
+
+def _fuzz():
+    import importlib.util
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("fuzz_reference_pin", Path(__file__).resolve().parent.parent / "scripts" / "fuzz_reference_pin.py")
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.mark.parametrize("seed", FUZZ_SEEDS)
+def test_cuda_path_equals_compiled_reference_on_random_scenes(solver, seed):
+    from adaptiveviscositysolver_b200.solver import Params
+    sc, op, _ = _fuzz().fuzz_case(seed)
+    tol = 1e-10
+    kw = dict(octree_levels=op.octree_levels, tolerance=tol, dt=op.dt, use_enhanced_gradients=op.use_enhanced_gradients,
+              do_apply_solid_weights=op.do_apply_solid_weights, fine_bandwidth=op.fine_bandwidth,
+              number_super_samples=op.number_super_samples, extrapolation=op.extrapolation)
+    R = ref.RefRun(sc, orc.OracleParams(**kw))
+    check_cuda_against_reference(solver, sc, Params(**kw), R, tol)
+
+
+def test_scene_outside_the_reference_contract_is_refused_not_executed(solver):
+    """A liquid that reaches the boundary of the grid violates the reference's own debug checks (edgeStressUnitTest,
+    centerStresUnitTest, octreeLabels.unitTest) and makes its release build emit matrix columns < 0 (AV.cpp:1886-1894; Eigen would
+    write out of bounds).  The library must neither use such a column as an address nor poison its CUDA context: the solve returns
+    AVS_ERR_UNSUPPORTED with a message, and the same context solves a valid scene afterwards."""
+    from adaptiveviscositysolver_b200.solver import AvsError, Params
+    fz = _fuzz()
+    sc, op, _ = fz.fuzz_case(fz.OUT_OF_CONTRACT_SEED)
+    O = orc.OracleRun(sc, op)                      # the restated reference does emit out-of-range columns on this scene
+    assert O.csr()[1].min() < 0
+    out = [v.data.copy() for v in sc.vel]
+    with pytest.raises(AvsError) as e:
+        solver.solve(sc, Params(octree_levels=op.octree_levels, tolerance=op.tolerance, dt=op.dt, use_enhanced_gradients=op.use_enhanced_gradients,
+                                do_apply_solid_weights=op.do_apply_solid_weights, fine_bandwidth=op.fine_bandwidth,
+                                number_super_samples=op.number_super_samples, extrapolation=op.extrapolation), out)
+    assert e.value.status == -10 and "boundary of the grid" in str(e.value)         # AVS_ERR_UNSUPPORTED
+    good = scenes.sphere_drop(32, 10)
+    out = [v.data.copy() for v in good.vel]
+    info = solver.solve(good, Params(octree_levels=4, tolerance=1e-8), out)
+    assert info.status == 0 and info.iterations > 0 and info.error < 1e-8
 
 
 def test_octree_geometry_equals_compiled_reference(solver):

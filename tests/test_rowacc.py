@@ -1,6 +1,5 @@
-"""The experimental hashed row accumulator of the assembly kernel (csrc/avs_rowacc.cuh, AVS_ASM_ROW=hash) against the default
-linear one, compiled for the HOST: same entries, same insertion order, same bits -- for random rows, rows at the MAX_ROW limit,
-overflowing rows and keys that all collide in the table."""
+"""The hashed row accumulator of the assembly kernel (csrc/avs_rowacc.cuh, the default) against the linear one (AVS_ASM_ROW=linear),
+compiled for the HOST: same entries, same insertion order, same bits -- for random rows, rows at the MAX_ROW limit, overflowing rows and keys that all collide in the table."""
 import subprocess
 from pathlib import Path
 
@@ -27,7 +26,7 @@ int main() {
     std::mt19937_64 rng(12345);
     long cases = 0;
     for (int trial = 0; trial < 20000; ++trial) {
-        int distinct = 1 + (int)(rng() % 80);              // up to 80 distinct columns: beyond MAX_ROW = 64 overflows both alike
+        int distinct = 1 + (int)(rng() % 100);             // up to 100 distinct columns: beyond MAX_ROW = 80 overflows both alike
         int adds = 1 + (int)(rng() % 200);
         int32_t base = (int32_t)(rng() % 2000000000u);
         int stride = (trial % 3 == 0) ? 128 : (trial % 3 == 1 ? 1 : (int)(1 + rng() % 5000));   // stride 128 * k: worst-case clustering
@@ -43,8 +42,8 @@ int main() {
     // keys that hash to the same slot: multiples of 2^32 / 128 stepped through the multiplicative hash's period
     {
         std::vector<int32_t> cols; std::vector<double> vals;
-        for (int i = 0; i < 64; ++i) { cols.push_back(i * 128 * 4096); vals.push_back(i + 0.5); }
-        for (int i = 0; i < 64; ++i) { cols.push_back(i * 128 * 4096); vals.push_back(0.25); }
+        for (int i = 0; i < MAX_ROW; ++i) { cols.push_back(i * 128 * 4096); vals.push_back(i + 0.5); }
+        for (int i = 0; i < MAX_ROW; ++i) { cols.push_back(i * 128 * 4096); vals.push_back(0.25); }
         if (compare(cols, vals)) { printf("MISMATCH colliding keys\n"); return 1; }
     }
     printf("ok %ld\n", cases);
