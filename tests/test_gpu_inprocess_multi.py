@@ -62,6 +62,37 @@ def test_single_process_multi_rank_solve(nranks):
         single.close()
 
 
+def test_multi_rank_solve_refuses_a_scene_outside_the_reference_contract():
+    """Liquid at the grid boundary puts the column -3 into the reference's matrix (tests/test_reference_fuzz.py).  Only the rank that
+    owns such a row sees it; the ranks sum their assembly error flags so that ALL of them leave with AVS_ERR_UNSUPPORTED (none waits
+    for a peer that left), and the group solves a valid scene afterwards exactly like a single context."""
+    import importlib.util
+    from pathlib import Path
+    from adaptiveviscositysolver_b200.solver import AvsError, MultiSolver, Params, Solver
+    spec = importlib.util.spec_from_file_location("fuzz_reference_pin", Path(__file__).resolve().parent.parent / "scripts" / "fuzz_reference_pin.py")
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    sc, op, _ = fz.fuzz_case(fz.OUT_OF_CONTRACT_SEED)
+    bad = Params(octree_levels=op.octree_levels, tolerance=op.tolerance, dt=op.dt, use_enhanced_gradients=op.use_enhanced_gradients,
+                 do_apply_solid_weights=op.do_apply_solid_weights, fine_bandwidth=op.fine_bandwidth,
+                 number_super_samples=op.number_super_samples, extrapolation=op.extrapolation)
+    m = MultiSolver(_devices(2))
+    single = Solver(device=0)
+    try:
+        with pytest.raises(AvsError) as e:
+            m.solve(sc, bad, [v.data.copy() for v in sc.vel])
+        assert e.value.status == -10 and "boundary of the grid" in str(e.value)      # AVS_ERR_UNSUPPORTED
+        good, p = sphere_drop(32, 11, noise=0.01), Params(octree_levels=4, tolerance=1e-10)
+        out, out1 = [v.data.copy() for v in good.vel], [v.data.copy() for v in good.vel]
+        info, info1 = m.solve(good, p, out), single.solve(good, p, out1)
+        assert info.octree_dofs == info1.octree_dofs and abs(info.iterations - info1.iterations) <= 1 and info.error < 1e-10
+        for a in range(3):
+            assert np.abs(out[a].astype(np.float64) - out1[a]).max() < 1e-7
+    finally:
+        m.close()
+        single.close()
+
+
 def test_multi_api_rejects_device_pointers_and_bad_arguments():
     import torch
     from adaptiveviscositysolver_b200 import _lib
