@@ -176,7 +176,12 @@ const char *avs_status_string(int status);
 const char *avs_last_error(void);   /* detail of the last AVS_ERR_CUDA / AVS_ERR_UNSUPPORTED on this thread */
 void avs_default_params(AvsParams *p);
 
-/* The drop-in call: replaces HDK_AdaptiveViscosity.cpp:233-707 in one shot. */
+/* The drop-in call: replaces HDK_AdaptiveViscosity.cpp:233-707 in one shot.
+ * Scenes the reference itself does not support -- a liquid that reaches the boundary of the grid makes its debug build assert
+ * (HDK_AdaptiveViscosity.cpp:411-413, 881) and its release build hand Eigen a triplet with column -3 (:1886-1894) -- are refused
+ * with AVS_ERR_UNSUPPORTED (text in avs_last_error()) when a stencil of the assembled system references a face that is not a
+ * degree of freedom; nothing is written to `out`, the context stays usable.  Pad the fields so that the liquid stays a few voxels
+ * inside the grid. */
 int avs_solve(AvsContext *ctx, const AvsFields *in, const AvsParams *p, AvsVelocityOut *out, AvsResult *res);
 
 /* ---- one process, several GPUs ------------------------------------------------------------------

@@ -246,7 +246,7 @@ bool HDK_AdaptiveViscosity::solveGasSubclass(SIM_Engine &engine, SIM_Object *obj
         UT_PerfMonAutoSolveEvent event(this, "Solve Linear System");
         int rc = myMulti ? avs_solve_multi(myMulti, &in, &p, &out, &r) : avs_solve(ctx, &in, &p, &out, &r);
         if (rc == AVS_ERR_CANCELLED) return true;                                                        // user interrupt: quiet
-        if (rc != AVS_OK) return fail((rc == AVS_ERR_CUDA || myMulti) ? avs_last_error() : avs_status_string(rc));   // AV.cpp:621-622
+        if (rc != AVS_OK) return fail((rc == AVS_ERR_CUDA || rc == AVS_ERR_UNSUPPORTED || myMulti) ? avs_last_error() : avs_status_string(rc));   // AV.cpp:621-622
         for (int a = 0; a < 3; ++a)              // applyVelocitiesToRegularGrid (AV.cpp:696-706)
             velocityField->getField(a)->fieldNC()->extractFromFlattened(outv[a].data(), in.vel[a].res[0],
                                                                          exint(in.vel[a].res[0]) * in.vel[a].res[1]);

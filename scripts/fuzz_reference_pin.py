@@ -43,7 +43,8 @@ def _box(c, h):
 def fuzz_case(seed: int):
     """(scene, OracleParams, description) of one seed -- deterministic."""
     rng = np.random.default_rng(100000 + seed)
-    res = tuple(int(v) for v in rng.choice([16, 20, 24, 28, 32, 36, 40, 48], size=3))
+    variant = seed // 1000       # 0: grids of 16-48 cells; 1: 56-96 cells (deeper octrees); 2: as 0 with a distorted, noisy SDF
+    res = tuple(int(v) for v in rng.choice([56, 64, 72, 80, 96] if variant == 1 else [16, 20, 24, 28, 32, 36, 40, 48], size=3))
     if rng.random() < 0.3:
         res = (res[0],) * 3
     dx = float(rng.choice([1.0 / 32, 0.013, 0.1, 0.0625, 0.37]))
@@ -67,11 +68,17 @@ def fuzz_case(seed: int):
     if touch:                    # liquid reaching the grid boundary
         blobs.append(_sphere(lo + ext * np.array([0.5, 0.0, 0.5]), float(0.3 * ext.min())))
 
-    def sdf(x, y, z):
+    def sdf_exact(x, y, z):
         v = blobs[0](x, y, z)
         for b in blobs[1:]:
             v = np.minimum(v, b(x, y, z))
         return v
+
+    sdf = sdf_exact
+    if variant == 2:             # what a simulation hands over is not an exact distance: scaled by a smooth factor in [0.6, 1.4]
+        kd = 2.0 * np.pi / (float(ext.max()) * float(rng.uniform(0.2, 1.0)))
+        pd = rng.uniform(0, 6.28, 3)
+        sdf = lambda x, y, z: sdf_exact(x, y, z) * (1.0 + 0.4 * np.sin(kd * x + pd[0]) * np.cos(kd * y + pd[1]) * np.sin(kd * z + pd[2]))
 
     U = float(rng.uniform(0.1, 2.0))
     k = 2.0 * np.pi / float(ext.max())
@@ -107,6 +114,8 @@ def fuzz_case(seed: int):
     ss = int(rng.choice([1, 2, 3, 4]))
     sc = scenes.analytic_scene(res, origin, dx, sdf, vel, mu=mu, rho=rho, collision_fn=collision_fn, collision_velocity=cvel,
                                supersamples=ss, noise=float(rng.choice([0.0, 0.0, 0.01])), seed=seed)
+    if variant == 2:             # + noise of a few percent of a voxel on the stored samples (zero set moves, band edges get ragged)
+        sc.surface.data += (rng.normal(0.0, 0.03 * dx, sc.surface.data.shape)).astype(np.float32)
     if collision_fn is not None and rng.random() < 0.4:
         # the reference samples the collision field by world position (AV.cpp:141, 853, 1157): give it a grid of its own
         cdx = dx * float(rng.choice([0.75, 1.5, 2.0]))
@@ -120,7 +129,7 @@ def fuzz_case(seed: int):
                          do_apply_solid_weights=bool(collision_fn is not None and rng.random() < 0.4),
                          fine_bandwidth=int(rng.choice([1, 2, 2, 3, 4])), number_super_samples=ss,
                          extrapolation=float(rng.choice([0.5, 0.0, 1.0])), max_iterations=int(rng.choice([2500, 2500, 40])))
-    desc = (f"seed {seed}: res {res} dx {dx:g} origin {tuple(round(o, 4) for o in origin)} blobs {len(blobs)}{' TOUCHING-THE-BOUNDARY' if touch else ''} solid "
+    desc = (f"seed {seed}{['', ' (deep)', ' (distorted sdf)'][min(variant, 2)]}: res {res} dx {dx:g} origin {tuple(round(o, 4) for o in origin)} blobs {len(blobs)}{' TOUCHING-THE-BOUNDARY' if touch else ''} solid "
             f"{'plane' if solid < 0.35 else 'sphere' if solid < 0.55 else 'none'} own-collision-grid {sc.collision.data is not None and sc.collision.dx != dx} "
             f"mu {'var' if callable(mu) else mu0} rho {'var' if callable(rho) else rho0} | levels {p.octree_levels} tol {p.tolerance:g} dt {p.dt:g} "
             f"enh {p.use_enhanced_gradients} solidw {p.do_apply_solid_weights} band {p.fine_bandwidth} ss {ss} extrap {p.extrapolation} maxit {p.max_iterations}")
