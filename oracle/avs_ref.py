@@ -245,6 +245,36 @@ class RefRun:
         return sp.csr_matrix((val, col, ptr), shape=(self.n_face, self.n_face))
 
 
+_LIB32_PATH = _HERE / "_ref" / "libavs_ref_f32.so"
+_lib32 = None
+
+
+def build_f32(force: bool = False) -> Path | None:
+    """oracle/_ref/libavs_ref_f32.so: the reference compiled with USESINGLEPRECISION (needs /root/reference; None without it)."""
+    if _LIB32_PATH.exists() and not force:
+        return _LIB32_PATH
+    if not REFERENCE_SOURCES.exists():
+        return None
+    r = subprocess.run(["make", "-C", str(_HERE), "ref-f32"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle/_ref fp32 build failed:\n" + r.stdout[-3000:] + r.stderr[-3000:])
+    return _LIB32_PATH
+
+
+class RefRun32(RefRun):
+    """The reference's USESINGLEPRECISION build (SolveType = fpreal32: float triplets summed in float by setFromTriplets, float
+    right-hand side, float conjugate gradients, HDK_Utilities.h:25-30).  The harness widens what it snapshots to double."""
+    _precision_word = 1
+
+    def _library(self):
+        global _lib32
+        if _lib32 is None:
+            if build_f32() is None:
+                raise RuntimeError("oracle/_ref/libavs_ref_f32.so is missing and /root/reference is not available to build it")
+            _lib32 = _bind(C.CDLL(str(_LIB32_PATH)))
+        return _lib32
+
+
 class ShimRun(RefRun):
     """The same harness around THIS repository's Houdini-side shim (integration/hdk/HDK_AdaptiveViscosityB200.cpp): the stand-in
     "Houdini" calls the shim's solveGasSubclass, the shim flattens the fields and calls avs_solve / avs_solve_multi in

@@ -148,6 +148,44 @@ def test_reference_debug_build_passes_its_own_unit_tests(tmp_path):
     assert r.returncode == 0 and r.stdout.startswith("ok True"), r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("name", ["sphere32_l4", "solid_ground32_l3", "padded_48x64x40_l5_varmu", "sphere64_l5_tol1e-6"])
+def test_single_precision_oracle_against_the_reference_single_precision_build(name):
+    """USESINGLEPRECISION (SolveType = fpreal32, HDK_Utilities.h:25-30; BASELINE configs[2]): the reference compiled with that define
+    (oracle/Makefile target ref-f32) pushes FLOAT triplets, lets setFromTriplets sum duplicates in float, accumulates the right-hand
+    side in float and runs the float conjugate gradients.  The oracle's fp32 mode -- and the CUDA library's, which follows it --
+    assembles in double and rounds each entry ONCE: same sparsity and numbering, a few percent of the entries differ in the last
+    float bits (more accurate, not bit-identical), iteration counts equal, solutions equal to float accuracy."""
+    if ref.build_f32() is None:
+        pytest.skip("/root/reference not present (the fp32 reference build is made on demand)")
+    if name == "sphere32_l4":
+        sc, kw = scenes.sphere_drop(32, 11, noise=0.01), dict(octree_levels=4, tolerance=1e-4)
+    elif name == "solid_ground32_l3":
+        sc = scenes.sphere_drop(32, 9, center=(0.5, 0.34, 0.5), ground_height=0.125, ground_velocity=(0.1, 0.0, -0.2))
+        kw = dict(octree_levels=3, tolerance=1e-5)
+    elif name == "padded_48x64x40_l5_varmu":
+        sc = scenes.sphere_drop(64, 14, res=(48, 64, 40), center=(0.375, 0.5, 0.3125), variable_viscosity=True, variable_density=True)
+        kw = dict(octree_levels=5, tolerance=1e-4)
+    else:
+        sc, kw = scenes.sphere_drop(64, 26, noise=0.01), dict(octree_levels=5, tolerance=1e-6)
+    p = orc.OracleParams(single_precision=True, **kw)
+    R, O = ref.RefRun32(sc, p), orc.OracleRun(sc, p)
+    assert R.returned_true and not R.errors and R.n_face == O.n_face and R.levels == O.levels
+    assert np.array_equal(R.face_keys(), O.face_keys())
+    (rp, rc, rv), (op, oc, ov) = R.csr(), O.csr()
+    assert np.array_equal(rp, op) and np.array_equal(rc, oc)
+    assert np.array_equal(rv, rv.astype(np.float32).astype(np.float64))                       # the reference's matrix IS float
+    rel = np.abs(rv - ov.astype(np.float32).astype(np.float64)) / np.abs(rv).max()
+    assert rel.max() < 1e-6 and (rel > 0).mean() < 0.10
+    assert np.abs(R.rhs() - O.rhs()).max() <= 1e-6 * np.abs(O.rhs()).max()
+    assert np.abs(R.x0() - O.x0()).max() <= 1e-6 * max(1.0, np.abs(O.x0()).max())             # float vs double restricted velocity
+    assert abs(R.iterations - O.iterations) <= max(1, O.iterations // 50)
+    assert R.error < p.tolerance and O.error < p.tolerance
+    scale = max(1.0, np.abs(O.solution()).max())
+    assert np.abs(R.solution() - O.solution()).max() < 1e-5 * scale
+    for a in range(3):
+        assert np.abs(R.out_velocity(a).astype(np.float64) - O.out_velocity(a)).max() < 1e-5 * scale
+
+
 def test_reference_threaded_fan_out_gives_the_same_system():
     """UT_ThreadedAlgorithm stand-in with 4 jobs per THREADED_METHOD: labels and numbering identical (the reference numbers
     serially), matrix equal up to the order in which setFromTriplets sums a row's duplicates."""
