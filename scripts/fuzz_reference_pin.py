@@ -142,6 +142,9 @@ def compare(sc, p):
     from oracle import avs_ref as ref
     sys.path.insert(0, str(ROOT / "tests"))
     import test_reference_pin as trp
+    # doPrintOctree / onlyPrintOctree (AV.cpp:283-294, OG.cpp:245-308): the same points, pscale and octreeLevel
+    Rg, Og = ref.RefRun(sc, p, octree_only=True), orc.OracleRun(sc, p, stop_after_stage=3)
+    assert sorted(map(tuple, np.column_stack(Rg.octree_points()).tolist())) == sorted(map(tuple, np.column_stack(Og.octree_points()).tolist())), "octree geometry"
     R, O = ref.RefRun(sc, p), orc.OracleRun(sc, p)
     if R.n_face == 0 or O.n_face == 0:
         assert R.n_face == O.n_face
