@@ -13,6 +13,16 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// AVS_DEV marks the device code that tests/test_host_assembly.py ALSO compiles for the host (nvcc -DAVS_HOST_TEST on a test harness
+// that includes avs_system.cu): the row builder of the assembly and everything it calls then exist as __host__ __device__ functions
+// and are run on the CPU against the compiled reference.  In the product build AVS_DEV is plain __device__ (SASS unchanged); the
+// library itself has no CPU path.
+#ifdef AVS_HOST_TEST
+#define AVS_DEV __host__ __device__
+#else
+#define AVS_DEV __device__
+#endif
+
 #define AVS_MAX_LEVELS 10
 #define AVS_TILE 16  // UT_VoxelArray tile edge: the reference classifies only inside "occupied" tiles
 
@@ -79,11 +89,11 @@ struct Grid3 {
         return (size_t)x + (size_t)n[0] * ((size_t)y + (size_t)n[1] * (size_t)z);
     }
     __host__ __device__ __forceinline__ size_t count() const { return (size_t)n[0] * n[1] * n[2]; }
-    __device__ __forceinline__ T get(const I3 &c) const {
+    AVS_DEV __forceinline__ T get(const I3 &c) const {
         int x = min(max(c[0], 0), n[0] - 1), y = min(max(c[1], 0), n[1] - 1), z = min(max(c[2], 0), n[2] - 1);
         return d[lin(x, y, z)];
     }
-    __device__ __forceinline__ T &at(const I3 &c) const { return d[lin(c[0], c[1], c[2])]; }
+    AVS_DEV __forceinline__ T &at(const I3 &c) const { return d[lin(c[0], c[1], c[2])]; }
 };
 
 // One scalar component of an input field, resident on the device (or constant).
@@ -93,14 +103,14 @@ struct DField {
     double org[3];
     double dx;
     float constant;
-    __device__ __forceinline__ float raw(int x, int y, int z) const {
+    AVS_DEV __forceinline__ float raw(int x, int y, int z) const {
         if (!d) return constant;
         x = min(max(x, 0), n[0] - 1); y = min(max(y, 0), n[1] - 1); z = min(max(z, 0), n[2] - 1);
         return d[(size_t)x + (size_t)n[0] * ((size_t)y + (size_t)n[1] * (size_t)z)];
     }
     // SIM_RawField::getValue(pos): trilinear, clamp-to-edge, fp64, a + t*(b-a) without contraction
     // (this translation unit is compiled with -fmad=false so it rounds exactly like the CPU oracle).
-    __device__ double value(const double p[3]) const {
+    AVS_DEV double value(const double p[3]) const {
         if (!d) return (double)constant;
         int i0[3], i1[3];
         double t[3];
@@ -150,17 +160,17 @@ struct DeviceScene {
     Grid3<int8_t> regular[3];  // regular-grid face labels (only >=0 / SOLID / UNASSIGNED matter, AV.cpp:2843-2890)
 
     __host__ __device__ __forceinline__ double levelDx(int level) const { return (double)(float)(dx0 * (double)(1 << level)); }
-    __device__ __forceinline__ void centerPos(const I3 &c, int level, double p[3]) const {
+    AVS_DEV __forceinline__ void centerPos(const I3 &c, int level, double p[3]) const {
         double h = levelDx(level);
 #pragma unroll
         for (int a = 0; a < 3; ++a) p[a] = origin[a] + (c[a] + 0.5) * h;
     }
-    __device__ __forceinline__ void facePos(const I3 &f, int axis, int level, double p[3]) const {
+    AVS_DEV __forceinline__ void facePos(const I3 &f, int axis, int level, double p[3]) const {
         double h = levelDx(level);
 #pragma unroll
         for (int a = 0; a < 3; ++a) p[a] = origin[a] + (f[a] + (a == axis ? 0.0 : 0.5)) * h;
     }
-    __device__ __forceinline__ void edgePos(const I3 &e, int axis, int level, double p[3]) const {
+    AVS_DEV __forceinline__ void edgePos(const I3 &e, int axis, int level, double p[3]) const {
         double h = levelDx(level);
 #pragma unroll
         for (int a = 0; a < 3; ++a) p[a] = origin[a] + (e[a] + (a == axis ? 0.5 : 0.0)) * h;

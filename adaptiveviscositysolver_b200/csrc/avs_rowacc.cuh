@@ -4,7 +4,9 @@
 #include <stdint.h>
 
 #ifndef AVS_HD
-#ifdef __CUDACC__
+#if defined(__CUDACC__) && defined(AVS_HOST_TEST)
+#define AVS_HD __host__ __device__ __forceinline__   // tests/test_host_assembly.py: the row builder compiled for the host as well
+#elif defined(__CUDACC__)
 #define AVS_HD __device__ __forceinline__
 #else
 #define AVS_HD inline

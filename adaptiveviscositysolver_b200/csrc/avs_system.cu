@@ -24,16 +24,16 @@ struct Stencil {
     int32_t idx[MAX_STENCIL];
     double coef[MAX_STENCIL];
     double bnd[8];
-    __device__ __forceinline__ void add(int32_t i, double c) {
+    AVS_DEV __forceinline__ void add(int32_t i, double c) {
         if (n < MAX_STENCIL) { idx[n] = i; coef[n] = c; ++n; }
     }
-    __device__ __forceinline__ void addB(double b) {
+    AVS_DEV __forceinline__ void addB(double b) {
         if (nb < 8) bnd[nb++] = b;
     }
 };
 
 // getEdgeStressFaces (AV.cpp:1717-1908)
-__device__ __noinline__ void edgeStressFaces(const DeviceScene &S, Stencil &st, const I3 &edge, int axis, int level) {
+AVS_DEV __noinline__ void edgeStressFaces(const DeviceScene &S, Stencil &st, const I3 &edge, int axis, int level) {
     st.n = st.nb = 0;
     const double dx = S.levelDx(level);  // AV.cpp:1733
     bool isAtTransition[3] = {false, false, false};
@@ -111,7 +111,7 @@ __device__ __noinline__ void edgeStressFaces(const DeviceScene &S, Stencil &st, 
 }
 
 // getCenterStressFaces (AV.cpp:1910-1963)
-__device__ __noinline__ void centerStressFaces(const DeviceScene &S, Stencil &st, const I3 &cell, int axis, int level) {
+AVS_DEV __noinline__ void centerStressFaces(const DeviceScene &S, Stencil &st, const I3 &cell, int axis, int level) {
     st.n = st.nb = 0;
     const double dx = S.levelDx(level);
     for (int dir = 0; dir < 2; ++dir) {
@@ -131,7 +131,7 @@ __device__ __noinline__ void centerStressFaces(const DeviceScene &S, Stencil &st
 }
 
 // faceOctreeVolumes (AV.cpp:1965-2002)
-__device__ double faceOctreeVolume(const DeviceScene &S, const I3 &face, int axis, int level) {
+AVS_DEV double faceOctreeVolume(const DeviceScene &S, const I3 &face, int axis, int level) {
     const Grid3<uint8_t> &lab = S.label[level];
     const double dx = (double)(1 << level);
     double g = 0;
@@ -147,7 +147,7 @@ __device__ double faceOctreeVolume(const DeviceScene &S, const I3 &face, int axi
 }
 
 // edgeOctreeVolumes (AV.cpp:2004-2057)
-__device__ double edgeOctreeVolume(const DeviceScene &S, const I3 &edge, int axis, int level) {
+AVS_DEV double edgeOctreeVolume(const DeviceScene &S, const I3 &edge, int axis, int level) {
     const double dx = (double)(1 << level);
     float v[3] = {0.f, 0.f, 0.f};
     v[axis] = (float)dx;
@@ -168,7 +168,7 @@ __device__ double edgeOctreeVolume(const DeviceScene &S, const I3 &edge, int axi
 }
 
 // stress weights: AV.cpp:2124-2155 (edges), AV.cpp:2223-2289 (centres)
-__device__ __noinline__ double edgeStressWeight(const DeviceScene &S, const I3 &edge, int axis, int level) {
+AVS_DEV __noinline__ double edgeStressWeight(const DeviceScene &S, const I3 &edge, int axis, int level) {
     double w;
     if (level == 0) {
         w = (double)S.edgeW[axis].get(edge);
@@ -182,7 +182,7 @@ __device__ __noinline__ double edgeStressWeight(const DeviceScene &S, const I3 &
     }
     return 4. * S.dt * w;
 }
-__device__ double centerStressWeight(const DeviceScene &S, const I3 &cell, int level) {
+AVS_DEV double centerStressWeight(const DeviceScene &S, const I3 &cell, int level) {
     double w;
     if (level == 0) w = (double)S.centerW.get(cell);
     else { double dx = (double)(1 << level); w = dx * dx * dx; }
@@ -198,7 +198,7 @@ __device__ double centerStressWeight(const DeviceScene &S, const I3 &cell, int l
 // ------------------------------------------------------------------------------------------------
 // Stage 8: buildVelocityMapping (AV.cpp:2291-2402).  Level 0 copies the regular face value; level l
 // sums 12^l leaves with weights (1/16, 1/8, 1/16) per child and in-axis offset.
-__device__ __forceinline__ double restrictLeaf(const DeviceScene &S, int axis, int level, I3 face, long long q, double &wOut) {
+AVS_DEV __forceinline__ double restrictLeaf(const DeviceScene &S, int axis, int level, I3 face, long long q, double &wOut) {
     // q enumerates the 12^level leaves in depth-first order (base-12 digits, most significant first)
     double w = 1.0;
     long long div = 1;
@@ -221,7 +221,7 @@ __device__ __forceinline__ double restrictLeaf(const DeviceScene &S, int axis, i
 // l-bit integers, so the weight of in-axis offset d is the hat (2^l - |d|) / 4^l; transverse positions are
 // the 2^l x 2^l block, each weighted 4^-l.  (2^(l+1)-1) * 4^l distinct reads instead of 12^l; all weights are
 // dyadic, so only the order of the fp64 additions differs from the reference's flat sum (<= 1e-13 relative).
-__device__ __forceinline__ double restrictHatTerm(const DeviceScene &S, int axis, int level, const I3 &face, long long q) {
+AVS_DEV __forceinline__ double restrictHatTerm(const DeviceScene &S, int axis, int level, const I3 &face, long long q) {
     const int side = 1 << level;
     const int t1 = (int)(q % side);
     const int t2 = (int)((q / side) % side);
@@ -367,7 +367,7 @@ int avs_stage_restriction(AvsContext *c, bool allRows) {
 
 // applyToMatrix (AV.cpp:2404-2457)
 template <class Row>
-__device__ __noinline__ void applyToMatrix(Row &row, double &rhsI, double &diag, double coefficient, int32_t vi, const Stencil &st) {
+AVS_DEV __noinline__ void applyToMatrix(Row &row, double &rhsI, double &diag, double coefficient, int32_t vi, const Stencil &st) {
     for (int i = 0; i < st.n; ++i)
         if (st.idx[i] == vi) { coefficient *= st.coef[i]; break; }
     for (int i = 0; i < st.n; ++i) {
@@ -380,7 +380,7 @@ __device__ __noinline__ void applyToMatrix(Row &row, double &rhsI, double &diag,
 
 // buildOctreeSystemFromStencilsPartial (AV.cpp:2459-2777) for row vi
 template <class Row>
-__device__ void buildRow(const DeviceScene &S, int32_t vi, const RowKey &k, float faceWeight, Row &row, double &rhsI, double &massOut) {
+AVS_DEV void buildRow(const DeviceScene &S, int32_t vi, const RowKey &k, float faceWeight, Row &row, double &rhsI, double &massOut) {
     const int level = k.level, axis = k.axis;
     const I3 face = mk3(k.i, k.j, k.k);
     const Grid3<uint8_t> &lab = S.label[level];
@@ -527,7 +527,7 @@ struct SimpleRowOut {   // entries go straight to the column-major staging area 
     int32_t *col;
     double *val, last;
     long long stride;
-    __device__ __forceinline__ void add(int32_t c, double v) {
+    AVS_DEV __forceinline__ void add(int32_t c, double v) {
         col[(long long)n * stride] = c;
         val[(long long)n * stride] = v;
         last = v;
@@ -535,7 +535,7 @@ struct SimpleRowOut {   // entries go straight to the column-major staging area 
     }
 };
 template <int AXIS>
-__device__ __forceinline__ bool buildSimpleRow(const DeviceScene &S, int32_t vi, const I3 &face, float fwRaw, SimpleRowOut &row, double &massOut) {
+AVS_DEV __forceinline__ bool buildSimpleRow(const DeviceScene &S, int32_t vi, const I3 &face, float fwRaw, SimpleRowOut &row, double &massOut) {
     const Grid3<uint8_t> &lab = S.label[0];
     const Grid3<int32_t> &fg = S.face[0][AXIS];
     constexpr int T1 = (AXIS + 1) % 3, T2 = (AXIS + 2) % 3;           // the two transverse axes

@@ -1,0 +1,155 @@
+// tests/host_assembly.cu -- TEST INFRASTRUCTURE (built and used only by tests/test_host_assembly.py; never part of libavs_b200.so).
+//
+// The row builder of the CUDA library -- buildRow / buildSimpleRow and everything they call in csrc/avs_system.cu and
+// csrc/avs_common.cuh: edgeStressFaces, centerStressFaces, the control volumes, the stress weights, applyToMatrix, the row
+// accumulators -- compiled for the HOST.  The product marks that code AVS_DEV (= __device__); with -DAVS_HOST_TEST it becomes
+// __host__ __device__, and this file, which includes avs_system.cu as a whole, runs it on the CPU over label grids that come from a
+// run of the REFERENCE'S OWN CODE (oracle/_ref/libavs_ref.so).  The rows it returns are then compared with the reference's matrix:
+// the product's assembly source against the reference without a GPU and without the restated oracle in between.
+//
+// What is NOT the product's code here: the loop over the rows (the kernels' one-thread-per-row mapping), the fetch of a row's face
+// weight (k_gather_face_weights, one line) and the staging / SJDS layout -- those only exist on the GPU (tests -m gpu).
+#ifndef AVS_HOST_TEST
+#error "compile with -DAVS_HOST_TEST"
+#endif
+#include "../adaptiveviscositysolver_b200/csrc/avs_system.cu"
+
+struct HostField {          // one scalar component, as AvsField of include/avs.h (host pointer or constant)
+    const float *data;
+    int32_t res[3];
+    double org[3];
+    double dx;
+    float constant;
+};
+struct HostSceneDesc {
+    int32_t N[3];           // liquid surface resolution
+    int32_t levels;         // built octree levels
+    double origin[3], dx, dt, extrapolation;
+    int32_t enhanced;
+    HostField viscosity, density, collisionVel[3], faceW[3];
+    const float *centerW;
+    const float *edgeW[3];
+    const uint8_t *label[AVS_MAX_LEVELS];
+    const int32_t *face[AVS_MAX_LEVELS][3];   // >= 0: DOF (row) index, else UNASSIGNED / SOLIDBOUNDARY / OUTSIDE
+    const int8_t *edge[AVS_MAX_LEVELS][3];    // 0 active, else the negative label
+    const int8_t *center[AVS_MAX_LEVELS];
+};
+
+static DField toField(const HostField &f) {   // csrc/avs_api.cu uploadField: same members, host pointer instead of a device copy
+    DField d;
+    d.d = f.data;
+    for (int a = 0; a < 3; ++a) { d.n[a] = f.res[a]; d.org[a] = f.org[a]; }
+    d.dx = f.dx;
+    d.constant = f.constant;
+    return d;
+}
+
+// the part of DeviceScene the row builder reads, filled like avs_stage_upload / avs_stage_octree / avs_stage_octree_labels do
+static void fillScene(const HostSceneDesc &h, DeviceScene &S) {
+    memset(&S, 0, sizeof(S));
+    for (int a = 0; a < 3; ++a) {
+        S.N[a] = h.N[a];
+        S.origin[a] = h.origin[a];
+        int pad = 1;
+        while (pad < h.N[a]) pad <<= 1;   // OG.cpp:18-24
+        S.Pad[a] = pad;
+    }
+    S.levels = h.levels;
+    S.dx0 = (double)(float)h.dx;          // AV.cpp:242
+    S.dt = h.dt;
+    S.extrap = S.dx0 * h.extrapolation;   // AV.cpp:243
+    S.enhanced = h.enhanced ? 1 : 0;
+    S.viscosity = toField(h.viscosity);
+    S.density = toField(h.density);
+    for (int a = 0; a < 3; ++a) {
+        S.collisionVel[a] = toField(h.collisionVel[a]);
+        S.faceW[a] = toField(h.faceW[a]);
+    }
+    S.centerW.d = (float *)h.centerW;
+    for (int k = 0; k < 3; ++k) S.centerW.n[k] = h.N[k];
+    for (int a = 0; a < 3; ++a) {
+        S.edgeW[a].d = (float *)h.edgeW[a];
+        for (int k = 0; k < 3; ++k) S.edgeW[a].n[k] = h.N[k] + (k != a);
+    }
+    for (int l = 0; l < h.levels; ++l) {
+        Grid3<uint8_t> &lab = S.label[l];
+        lab.d = (uint8_t *)h.label[l];
+        for (int k = 0; k < 3; ++k) lab.n[k] = S.Pad[k] >> l;
+        for (int a = 0; a < 3; ++a) {
+            S.face[l][a].d = (int32_t *)h.face[l][a];
+            S.edge[l][a].d = (int8_t *)h.edge[l][a];
+            for (int k = 0; k < 3; ++k) {
+                S.face[l][a].n[k] = lab.n[k] + (k == a);
+                S.edge[l][a].n[k] = lab.n[k] + (k != a);
+            }
+        }
+        S.center[l].d = (int8_t *)h.center[l];
+        for (int k = 0; k < 3; ++k) S.center[l].n[k] = lab.n[k];
+    }
+}
+
+template <class Row>
+static int genericRow(const DeviceScene &S, int32_t vi, const RowKey &k, float fw, int32_t *col, double *val, double &rhsI, double &mass) {
+    Row row;
+    row.init();
+    rhsI = 0;
+    mass = 0;
+    buildRow(S, vi, k, fw, row, rhsI, mass);
+    if (row.overflow) return -1;
+    for (int i = 0; i < row.n; ++i) { col[i] = row.col[i]; val[i] = row.val[i]; }
+    return row.n;
+}
+
+extern "C" {
+
+int host_max_row(void) { return MAX_ROW; }
+
+// mode 0: every row through buildRow with the hashed accumulator (k_assemble<.., RowAccHash>, the default second pass)
+// mode 1: every row through buildRow with the linear accumulator (AVS_ASM_ROW=linear)
+// mode 2: the split assembly: buildSimpleRow where it accepts the row (k_assemble_simple), buildRow for the rest
+// Entries are returned in the builder's own order, MAX_ROW slots per row: col[r * MAX_ROW + i], val[...]; count[r] = entries,
+// simple[r] = 1 where buildSimpleRow wrote the row.  Returns 0, or -(row + 1) for a row that overflowed.
+long long host_assemble_rows(const HostSceneDesc *h, long long nRows, const int32_t *keys, int mode, int32_t *count, int32_t *col, double *val,
+                             double *rhsI, double *mass, int32_t *simple) {
+    DeviceScene S;
+    fillScene(*h, S);
+    for (long long r = 0; r < nRows; ++r) {
+        RowKey k;
+        k.level = keys[5 * r + 0]; k.axis = keys[5 * r + 1]; k.i = keys[5 * r + 2]; k.j = keys[5 * r + 3]; k.k = keys[5 * r + 4];
+        const float fw = (k.level == 0) ? S.faceW[k.axis].raw(k.i, k.j, k.k) : 1.f;   // k_gather_face_weights
+        int32_t *c = col + r * MAX_ROW;
+        double *v = val + r * MAX_ROW;
+        simple[r] = 0;
+        int n = -1;
+        if (mode == 2 && k.level == 0) {
+            // the staging area of k_assemble_simple is column-major with a stride; here stride = 1 makes it this row's slots
+            SimpleRowOut out;
+            out.col = c;
+            out.val = v;
+            out.stride = 1;
+            out.last = 0;
+            out.n = 0;
+            double m = 0;
+            const I3 face = mk3(k.i, k.j, k.k);
+            bool ok;
+            if (k.axis == 0) ok = buildSimpleRow<0>(S, (int32_t)r, face, fw, out, m);
+            else if (k.axis == 1) ok = buildSimpleRow<1>(S, (int32_t)r, face, fw, out, m);
+            else ok = buildSimpleRow<2>(S, (int32_t)r, face, fw, out, m);
+            if (ok) {
+                n = out.n;
+                rhsI[r] = 0;
+                mass[r] = m;
+                simple[r] = 1;
+            }
+        }
+        if (n < 0) {
+            n = (mode == 1) ? genericRow<RowAcc>(S, (int32_t)r, k, fw, c, v, rhsI[r], mass[r])
+                            : genericRow<RowAccHash>(S, (int32_t)r, k, fw, c, v, rhsI[r], mass[r]);
+            if (n < 0) return -(r + 1);
+        }
+        count[r] = n;
+    }
+    return 0;
+}
+
+}  // extern "C"
