@@ -33,6 +33,7 @@ struct HostSceneDesc {
     const int32_t *face[AVS_MAX_LEVELS][3];   // >= 0: DOF (row) index, else UNASSIGNED / SOLIDBOUNDARY / OUTSIDE
     const int8_t *edge[AVS_MAX_LEVELS][3];    // 0 active, else the negative label
     const int8_t *center[AVS_MAX_LEVELS];
+    HostField vel[3];       // u^n, face sampled (read by the restriction only)
 };
 
 static DField toField(const HostField &f) {   // csrc/avs_api.cu uploadField: same members, host pointer instead of a device copy
@@ -64,6 +65,7 @@ static void fillScene(const HostSceneDesc &h, DeviceScene &S) {
     for (int a = 0; a < 3; ++a) {
         S.collisionVel[a] = toField(h.collisionVel[a]);
         S.faceW[a] = toField(h.faceW[a]);
+        S.vel[a] = toField(h.vel[a]);
     }
     S.centerW.d = (float *)h.centerW;
     for (int k = 0; k < 3; ++k) S.centerW.n[k] = h.N[k];
@@ -150,6 +152,37 @@ long long host_assemble_rows(const HostSceneDesc *h, long long nRows, const int3
         count[r] = n;
     }
     return 0;
+}
+
+// Stage 8, restriction of u^n to the octree faces (AV.cpp:2291-2402) with the library's leaf / hat-weight functions.  The loops
+// are those of k_restrict_fine (levels 0-2, same order of additions) and, for levels >= 3, the plain sum of the terms that
+// k_restrict_coarse / k_restrict_coarse_finish add CTA-wise (same terms, another order: <= 1e-13 relative).
+void host_restrict_rows(const HostSceneDesc *h, long long nRows, const int32_t *keys, double *x0) {
+    DeviceScene S;
+    fillScene(*h, S);
+    for (long long r = 0; r < nRows; ++r) {
+        RowKey k;
+        k.level = keys[5 * r + 0]; k.axis = keys[5 * r + 1]; k.i = keys[5 * r + 2]; k.j = keys[5 * r + 3]; k.k = keys[5 * r + 4];
+        const I3 face = mk3(k.i, k.j, k.k);
+        double acc = 0;
+        if (k.level == 0) {
+            x0[r] = 1.0 * (double)S.vel[k.axis].raw(face[0], face[1], face[2]);
+        } else if (k.level == 1) {
+            for (int q = 0; q < 12; ++q) {
+                double w;
+                double v = restrictLeaf(S, k.axis, 1, face, q, w);
+                acc += w * v;
+            }
+            x0[r] = acc;
+        } else if (k.level == 2) {
+            for (int q = 0; q < 7 * 16; ++q) acc += restrictHatTerm(S, k.axis, 2, face, q);
+            x0[r] = acc * (1.0 / 256.0);
+        } else {
+            const long long side = 1ll << k.level, terms = (2 * side - 1) * side * side;
+            for (long long q = 0; q < terms; ++q) acc += restrictHatTerm(S, k.axis, k.level, face, q);
+            x0[r] = acc / (double)(side * side * side * side);
+        }
+    }
 }
 
 }  // extern "C"

@@ -1,5 +1,6 @@
 """The CUDA library's row builder -- the device code of csrc/avs_system.cu: buildRow, buildSimpleRow, edgeStressFaces,
-centerStressFaces, control volumes, stress weights, applyToMatrix, both row accumulators -- compiled for the HOST
+centerStressFaces, control volumes, stress weights, applyToMatrix, both row accumulators, and the leaf / hat-weight functions of the
+restriction -- compiled for the HOST
 (tests/host_assembly.cu, nvcc -DAVS_HOST_TEST turns the product's AVS_DEV functions into __host__ __device__) and run on label grids
 produced by the REFERENCE'S OWN CODE (oracle/_ref/libavs_ref.so).  Its rows are compared with the reference's matrix and right-hand
 side: the product's assembly SOURCE against the reference, on the CPU, on the golden scenes and on random ones, without the restated
@@ -37,7 +38,7 @@ class HostSceneDesc(C.Structure):
                 ("viscosity", HostField), ("density", HostField), ("collisionVel", HostField * 3), ("faceW", HostField * 3),
                 ("centerW", C.c_void_p), ("edgeW", C.c_void_p * 3),
                 ("label", C.c_void_p * MAX_LEVELS), ("face", (C.c_void_p * 3) * MAX_LEVELS), ("edge", (C.c_void_p * 3) * MAX_LEVELS),
-                ("center", C.c_void_p * MAX_LEVELS)]
+                ("center", C.c_void_p * MAX_LEVELS), ("vel", HostField * 3)]
 
 
 @pytest.fixture(scope="module")
@@ -60,6 +61,8 @@ def harness():
     L = C.CDLL(str(out))
     L.host_assemble_rows.restype = C.c_longlong
     L.host_assemble_rows.argtypes = [C.POINTER(HostSceneDesc), C.c_longlong, C.c_void_p, C.c_int] + [C.c_void_p] * 6
+    L.host_restrict_rows.restype = None
+    L.host_restrict_rows.argtypes = [C.POINTER(HostSceneDesc), C.c_longlong, C.c_void_p, C.c_void_p]
     return L
 
 
@@ -91,6 +94,7 @@ def _describe(sc, p, R, keep):
     for a in range(3):
         d.collisionVel[a] = _field(sc.collision_vel[a], keep)
         d.faceW[a] = _field(sc.face_weights[a], keep)
+        d.vel[a] = _field(sc.vel[a], keep)
     pad = [1 << int(np.ceil(np.log2(n))) if n > 1 else 1 for n in sc.res]
 
     def put(arr, dtype, shape_xyz):
@@ -148,6 +152,13 @@ def check_product_rows_against_reference(L, sc, p):
     assert np.array_equal(sval, rval), "matrix values (bit for bit)"
     # ---- the right-hand side: boundary terms + M_u u^n (the kernel k_finish_rhs adds the second part from the restricted velocity)
     assert np.array_equal(rhs + mass * R.x0(), R.rhs()), "right-hand side (bit for bit)"
+    # ---- the restricted velocity (stage 8): leaves in the reference's order on levels 0 and 1 (bit for bit), closed-form hat weights above
+    x0 = np.zeros(n)
+    k32 = np.ascontiguousarray(keys, np.int32)
+    L.host_restrict_rows(C.byref(d), n, k32.ctypes.data, x0.ctypes.data)
+    fine = keys[:, 0] <= 1
+    assert np.array_equal(x0[fine], R.x0()[fine]), "restriction, levels 0 and 1 (bit for bit)"
+    assert np.abs(x0 - R.x0()).max() <= 1e-13 * max(1.0, np.abs(R.x0()).max()), "restriction, hat form"
     # ---- accumulators and the split assembly: same entries in the same order, bit for bit
     c1 = _assemble(L, d, keys, 1)
     c2 = _assemble(L, d, keys, 2)
