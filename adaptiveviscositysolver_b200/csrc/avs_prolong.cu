@@ -25,29 +25,29 @@ struct NodeScene {
     NodeLevel lv[AVS_MAX_LEVELS];
 };
 
-__device__ __forceinline__ I3 nodeToFace(I3 n, int fa, int fi) {  // UTIL.h:187
+AVS_DEV __forceinline__ I3 nodeToFace(I3 n, int fa, int fi) {  // UTIL.h:187
     if (!(fi & 1)) --n[(fa + 1) % 3];
     if (!(fi & 2)) --n[(fa + 2) % 3];
     return n;
 }
-__device__ __forceinline__ I3 faceToNode(I3 f, int fa, int ni) {  // UTIL.h:133
+AVS_DEV __forceinline__ I3 faceToNode(I3 f, int fa, int ni) {  // UTIL.h:133
     if (ni & 1) ++f[(fa + 1) % 3];
     if (ni & 2) ++f[(fa + 2) % 3];
     return f;
 }
-__device__ __forceinline__ I3 cellToNode(I3 c, int ni) {  // UTIL.h:88
+AVS_DEV __forceinline__ I3 cellToNode(I3 c, int ni) {  // UTIL.h:88
     if (ni & 1) ++c[0];
     if (ni & 2) ++c[1];
     if (ni & 4) ++c[2];
     return c;
 }
-__device__ __forceinline__ float octVel(const DeviceScene &S, const double *sol, int level, int axis, const I3 &f) {
+AVS_DEV __forceinline__ float octVel(const DeviceScene &S, const double *sol, int level, int axis, const I3 &f) {
     int32_t vi = S.face[level][axis].get(f);
     return vi >= 0 ? (float)sol[vi] : 0.f;
 }
 
 // setActiveNodes (VFI.cpp:118-188) + sampleActiveNodes (VFI.cpp:190-286)
-__device__ __forceinline__ void nodeSample(const DeviceScene &S, const NodeLevel &nl, const double *sol, int level, int x, int y, int z) {
+AVS_DEV __forceinline__ void nodeSample(const DeviceScene &S, const NodeLevel &nl, const double *sol, int level, int x, int y, int z) {
     const size_t idx = nl.label.lin(x, y, z);
     const I3 node = mk3(x, y, z);
     // cheap reject: a node with an active face is a corner of an ACTIVE cell
@@ -101,9 +101,7 @@ __device__ __forceinline__ void nodeSample(const DeviceScene &S, const NodeLevel
 }
 
 // bubbleActiveNodeValues (VFI.cpp:288-355): one thread per PARENT node (its co-located child is unique)
-__global__ void k_node_bubble(NodeLevel child, NodeLevel par, int zLo) {
-    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y), z = (int)blockIdx.z + zLo;
-    if (x >= par.label.n[0] || y >= par.label.n[1]) return;
+AVS_DEV __forceinline__ void nodeBubble(const NodeLevel &child, const NodeLevel &par, int x, int y, int z) {
     const int cx = 2 * x, cy = 2 * y, cz = 2 * z;
     if (cx >= child.label.n[0] || cy >= child.label.n[1] || cz >= child.label.n[2]) return;
     const size_t pi = par.label.lin(x, y, z), ci = child.label.lin(cx, cy, cz);
@@ -115,9 +113,14 @@ __global__ void k_node_bubble(NodeLevel child, NodeLevel par, int zLo) {
     }
     child.label.d[ci] = N_DEPENDENT;
 }
+__global__ void k_node_bubble(NodeLevel child, NodeLevel par, int zLo) {
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)(blockIdx.y * blockDim.y + threadIdx.y), z = (int)blockIdx.z + zLo;
+    if (x >= par.label.n[0] || y >= par.label.n[1]) return;
+    nodeBubble(child, par, x, y, z);
+}
 
 // finishIncompleteNodes (VFI.cpp:357-567)
-__device__ __forceinline__ void nodeFinish(const DeviceScene &S, const NodeLevel &nl, const double *sol, int level, int x, int y, int z) {
+AVS_DEV __forceinline__ void nodeFinish(const DeviceScene &S, const NodeLevel &nl, const double *sol, int level, int x, int y, int z) {
     const size_t idx = nl.label.lin(x, y, z);
     if (nl.label.d[idx] != N_ACTIVE) return;
     unsigned flag = nl.flag.d[idx];
@@ -181,14 +184,14 @@ __device__ __forceinline__ void nodeFinish(const DeviceScene &S, const NodeLevel
 }
 
 // normalizeActiveNodes (VFI.cpp:569-613)
-__device__ __forceinline__ void nodeNormalize(const NodeLevel &nl, int x, int y, int z) {
+AVS_DEV __forceinline__ void nodeNormalize(const NodeLevel &nl, int x, int y, int z) {
     const size_t idx = nl.label.lin(x, y, z);
     if (nl.label.d[idx] != N_ACTIVE) return;
     for (int a = 0; a < 3; ++a) nl.val[a].d[idx] = (float)((double)nl.val[a].d[idx] / (double)nl.w[a].d[idx]);
 }
 
 // distributeNodeValuesDown (VFI.cpp:615-658)
-__device__ __forceinline__ void nodeDistribute(const NodeLevel &child, const NodeLevel &par, int x, int y, int z) {
+AVS_DEV __forceinline__ void nodeDistribute(const NodeLevel &child, const NodeLevel &par, int x, int y, int z) {
     const size_t idx = child.label.lin(x, y, z);
     if (child.label.d[idx] != N_DEPENDENT) return;
     const I3 pn = mk3(x >> 1, y >> 1, z >> 1);
@@ -257,7 +260,7 @@ __global__ void k_node_tile_list(int n0, int n1, int n2, Grid3<uint8_t> flags, u
 }
 
 // interpSPGrid (VFI.cpp:660-845)
-__device__ double interpSPGrid(const DeviceScene &S, const NodeScene &NS, const double *sol, const double pos[3], int axis) {
+AVS_DEV double interpSPGrid(const DeviceScene &S, const NodeScene &NS, const double *sol, const double pos[3], int axis) {
     const int L = S.levels;
     I3 cell;
     for (int a = 0; a < 3; ++a) cell[a] = (int)floor((pos[a] - S.origin[a]) / S.levelDx(0));

@@ -1,9 +1,9 @@
 """The CUDA library's row builder -- the device code of csrc/avs_system.cu: buildRow, buildSimpleRow, edgeStressFaces,
 centerStressFaces, control volumes, stress weights, applyToMatrix, both row accumulators, and the leaf / hat-weight functions of the
-restriction -- compiled for the HOST
-(tests/host_assembly.cu, nvcc -DAVS_HOST_TEST turns the product's AVS_DEV functions into __host__ __device__) and run on label grids
+restriction; and of csrc/avs_prolong.cu: the interpolator's node pyramid and interpSPGrid -- compiled for the HOST
+(tests/host_assembly.cu, tests/host_prolong.cu; nvcc -DAVS_HOST_TEST turns the product's AVS_DEV functions into __host__ __device__) and run on label grids
 produced by the REFERENCE'S OWN CODE (oracle/_ref/libavs_ref.so).  Its rows are compared with the reference's matrix and right-hand
-side: the product's assembly SOURCE against the reference, on the CPU, on the golden scenes and on random ones, without the restated
+side, its restricted velocity and its regular-grid output with the reference's: the product's SOURCE against the reference, on the CPU, on the golden scenes and on random ones, without the restated
 oracle in between.  (The GPU tests compare the same code as it runs on the device; this one runs in every CPU round.)
 
 Also checked here: the closed-form pass of the split assembly (buildSimpleRow = k_assemble_simple) writes bit-identical rows, entry
@@ -38,7 +38,7 @@ class HostSceneDesc(C.Structure):
                 ("viscosity", HostField), ("density", HostField), ("collisionVel", HostField * 3), ("faceW", HostField * 3),
                 ("centerW", C.c_void_p), ("edgeW", C.c_void_p * 3),
                 ("label", C.c_void_p * MAX_LEVELS), ("face", (C.c_void_p * 3) * MAX_LEVELS), ("edge", (C.c_void_p * 3) * MAX_LEVELS),
-                ("center", C.c_void_p * MAX_LEVELS), ("vel", HostField * 3)]
+                ("center", C.c_void_p * MAX_LEVELS), ("vel", HostField * 3), ("regular", C.c_void_p * 3)]
 
 
 @pytest.fixture(scope="module")
@@ -48,21 +48,30 @@ def harness():
     if not lib.exists():
         import __graft_entry__
         __graft_entry__.build()
-    out = ROOT / "tests" / "_build" / "libhost_assembly.so"
-    out.parent.mkdir(exist_ok=True)
     csrc = ROOT / "adaptiveviscositysolver_b200" / "csrc"
-    deps = [ROOT / "tests" / "host_assembly.cu", csrc / "avs_system.cu", csrc / "avs_common.cuh", csrc / "avs_rowacc.cuh", csrc / "avs_context.h"]
-    if not out.exists() or out.stat().st_mtime < max(d.stat().st_mtime for d in deps):
-        cmd = [NVCC, "-DAVS_HOST_TEST", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-fmad=false", "-ccbin", "/usr/bin/g++",
-               "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-shared", "-o", str(out), str(deps[0]),
-               "-L", str(lib.parent), "-lavs_b200", "-Xlinker", "-rpath", "-Xlinker", str(lib.parent)]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    L = C.CDLL(str(out))
+    common = [ROOT / "tests" / "host_scene.h", csrc / "avs_common.cuh", csrc / "avs_rowacc.cuh", csrc / "avs_context.h"]
+
+    def build(name, product_source):
+        out = ROOT / "tests" / "_build" / f"lib{name}.so"
+        out.parent.mkdir(exist_ok=True)
+        deps = [ROOT / "tests" / f"{name}.cu", csrc / product_source] + common
+        if not out.exists() or out.stat().st_mtime < max(d.stat().st_mtime for d in deps):
+            cmd = [NVCC, "-DAVS_HOST_TEST", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-fmad=false", "-ccbin", "/usr/bin/g++",
+                   "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-shared", "-o", str(out), str(deps[0]),
+                   "-L", str(lib.parent), "-lavs_b200", "-Xlinker", "-rpath", "-Xlinker", str(lib.parent)]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+        return C.CDLL(str(out))
+
+    L = build("host_assembly", "avs_system.cu")
     L.host_assemble_rows.restype = C.c_longlong
     L.host_assemble_rows.argtypes = [C.POINTER(HostSceneDesc), C.c_longlong, C.c_void_p, C.c_int] + [C.c_void_p] * 6
     L.host_restrict_rows.restype = None
     L.host_restrict_rows.argtypes = [C.POINTER(HostSceneDesc), C.c_longlong, C.c_void_p, C.c_void_p]
+    P = build("host_prolong", "avs_prolong.cu")
+    P.host_apply_regular.restype = C.c_longlong
+    P.host_apply_regular.argtypes = [C.POINTER(HostSceneDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.prolong = P
     return L
 
 
@@ -115,6 +124,8 @@ def _describe(sc, p, R, keep):
             d.face[l][a] = put(fi, np.int32, [cells[k] + (k == a) for k in range(3)])
             d.edge[l][a] = put(np.minimum(R.edge_index(l, a), 0), np.int8, [cells[k] + (k != a) for k in range(3)])
         d.center[l] = put(np.minimum(R.center_index(l), 0), np.int8, cells)
+    for a in range(3):
+        d.regular[a] = put(np.minimum(R.regular_index(a), 0), np.int8, [sc.res[k] + (k == a) for k in range(3)])
     return d
 
 
@@ -159,6 +170,13 @@ def check_product_rows_against_reference(L, sc, p):
     fine = keys[:, 0] <= 1
     assert np.array_equal(x0[fine], R.x0()[fine]), "restriction, levels 0 and 1 (bit for bit)"
     assert np.abs(x0 - R.x0()).max() <= 1e-13 * max(1.0, np.abs(R.x0()).max()), "restriction, hat form"
+    # ---- stage 11: the interpolator's node pyramid + interpSPGrid + the write-back rule, fed with the REFERENCE's solution vector
+    sol = np.ascontiguousarray(R.solution(), np.float64)
+    out = [np.ascontiguousarray(v.data.copy(), np.float32) for v in sc.vel]
+    interpolated = L.prolong.host_apply_regular(C.byref(d), sol.ctypes.data, out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data)
+    for a in range(3):
+        assert np.array_equal(out[a], R.out_velocity(a)), f"regular-grid velocity, axis {a} (bit for bit)"
+    assert interpolated > 0 or R.levels == 1
     # ---- accumulators and the split assembly: same entries in the same order, bit for bit
     c1 = _assemble(L, d, keys, 1)
     c2 = _assemble(L, d, keys, 2)
