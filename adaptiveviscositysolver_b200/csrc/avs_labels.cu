@@ -79,7 +79,7 @@ __device__ __forceinline__ void forCellsZ(const int n[3], int zOff, F f) {
 // offsets ((k+1/2)/n - 1/2) dx whose interpolated sdf (minus dilate) is negative.
 // Early-out: the trilinear interpolant is a convex combination of the voxels it touches, so when
 // every voxel under the sample's box has the same sign the count is n^3 or 0 without sampling.
-__device__ void sdfWeightSample(Grid3<float> w, const DField &sdf, double off0, double off1, double off2, double o0,
+AVS_DEV void sdfWeightSample(Grid3<float> w, const DField &sdf, double off0, double off1, double off2, double o0,
                                 double o1, double o2, double dx0, int n, double dilate, const uint8_t *signClass,
                                 int x, int y, int z, size_t idx) {
     double c[3] = {o0 + (x + off0) * dx0, o1 + (y + off1) * dx0, o2 + (z + off2) * dx0};
@@ -693,10 +693,10 @@ __device__ __forceinline__ void countWarp(bool hit, unsigned long long *counter)
     unsigned m = __ballot_sync(0xffffffffu, hit);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(counter, (unsigned long long)__popc(m));
 }
-__device__ __forceinline__ void markTile(const Grid3<uint8_t> &t, const I3 &c) {
+AVS_DEV __forceinline__ void markTile(const Grid3<uint8_t> &t, const I3 &c) {
     t.d[t.lin(c[0] / AVS_TILE, c[1] / AVS_TILE, c[2] / AVS_TILE)] = 1;
 }
-__device__ __forceinline__ bool tileOccupied(const Grid3<uint8_t> &t, int x, int y, int z) {
+AVS_DEV __forceinline__ bool tileOccupied(const Grid3<uint8_t> &t, int x, int y, int z) {
     return t.d[t.lin(x / AVS_TILE, y / AVS_TILE, z / AVS_TILE)] != 0;
 }
 
@@ -716,7 +716,7 @@ __global__ void k_mark_surface_tiles(const __grid_constant__ DeviceScene S, Grid
 }
 
 // face activity test shared by AV.cpp:1127-1150 and AV.cpp:1235-1258
-__device__ __forceinline__ bool faceHasWeight(const DeviceScene &S, const I3 &face, int axis) {
+AVS_DEV __forceinline__ bool faceHasWeight(const DeviceScene &S, const I3 &face, int axis) {
     I3 b = faceToCell(face, axis, 0), f = faceToCell(face, axis, 1);
     if (S.centerW.get(b) > 0.f || S.centerW.get(f) > 0.f) return true;
 #pragma unroll
@@ -750,7 +750,7 @@ __global__ void k_classify_regular(const __grid_constant__ DeviceScene S, int ax
 }
 
 // classifyOctreeVelocityFaces (AV.cpp:1167-1323): label of one face
-__device__ __forceinline__ int32_t classifyFace(const DeviceScene &S, int level, int axis, const Grid3<uint8_t> &tiles, int x, int y, int z) {
+AVS_DEV __forceinline__ int32_t classifyFace(const DeviceScene &S, int level, int axis, const Grid3<uint8_t> &tiles, int x, int y, int z) {
     int32_t out = F_UNASSIGNED;
     I3 face = mk3(x, y, z);
     const Grid3<uint8_t> &lab = S.label[level];
@@ -800,7 +800,7 @@ __global__ void k_mark_edge_tiles(Grid3<uint8_t> lab, Grid3<uint8_t> t0, Grid3<u
 }
 
 // classifyEdgeStresses (AV.cpp:1325-1405): label of one edge
-__device__ __forceinline__ int8_t classifyEdge(const DeviceScene &S, int level, int axis, const Grid3<uint8_t> &tiles, int x, int y, int z) {
+AVS_DEV __forceinline__ int8_t classifyEdge(const DeviceScene &S, int level, int axis, const Grid3<uint8_t> &tiles, int x, int y, int z) {
     int8_t out = F_UNASSIGNED;
     if (tileOccupied(tiles, x, y, z)) {
         const Grid3<uint8_t> &lab = S.label[level];
@@ -840,7 +840,7 @@ __global__ void k_classify_edges(const __grid_constant__ DeviceScene S, int leve
 }
 
 // classifyCenterStresses (AV.cpp:1407-1443): label of one cell centre
-__device__ __forceinline__ int8_t classifyCenter(const DeviceScene &S, int level, int x, int y, int z, size_t idx) {
+AVS_DEV __forceinline__ int8_t classifyCenter(const DeviceScene &S, int level, int x, int y, int z, size_t idx) {
     int8_t out = F_UNASSIGNED;
     if (S.label[level].d[idx] == L_ACTIVE) {
         if (level != 0) out = F_FLUID;

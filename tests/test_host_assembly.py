@@ -1,7 +1,8 @@
 """The CUDA library's row builder -- the device code of csrc/avs_system.cu: buildRow, buildSimpleRow, edgeStressFaces,
 centerStressFaces, control volumes, stress weights, applyToMatrix, both row accumulators, and the leaf / hat-weight functions of the
-restriction; and of csrc/avs_prolong.cu: the interpolator's node pyramid and interpSPGrid -- compiled for the HOST
-(tests/host_assembly.cu, tests/host_prolong.cu; nvcc -DAVS_HOST_TEST turns the product's AVS_DEV functions into __host__ __device__) and run on label grids
+restriction; of csrc/avs_prolong.cu: the interpolator's node pyramid and interpSPGrid; of csrc/avs_labels.cu: the weight sampler
+and the face / edge / centre classification rules -- compiled for the HOST
+(tests/host_assembly.cu, host_prolong.cu, host_labels.cu; nvcc -DAVS_HOST_TEST turns the product's AVS_DEV functions into __host__ __device__) and run on label grids
 produced by the REFERENCE'S OWN CODE (oracle/_ref/libavs_ref.so).  Its rows are compared with the reference's matrix and right-hand
 side, its restricted velocity and its regular-grid output with the reference's: the product's SOURCE against the reference, on the CPU, on the golden scenes and on random ones, without the restated
 oracle in between.  (The GPU tests compare the same code as it runs on the device; this one runs in every CPU round.)
@@ -41,9 +42,9 @@ class HostSceneDesc(C.Structure):
                 ("center", C.c_void_p * MAX_LEVELS), ("vel", HostField * 3), ("regular", C.c_void_p * 3)]
 
 
-@pytest.fixture(scope="module")
-def harness():
-    """tests/_build/libhost_assembly.so: tests/host_assembly.cu (which #includes the product's avs_system.cu) for host + sm_100a."""
+def build_harness():
+    """tests/_build/libhost_assembly.so, libhost_prolong.so: tests/host_*.cu (which #include the product's avs_system.cu /
+    avs_prolong.cu) compiled by nvcc for host + sm_100a."""
     lib = ROOT / "adaptiveviscositysolver_b200" / "libavs_b200.so"
     if not lib.exists():
         import __graft_entry__
@@ -72,7 +73,18 @@ def harness():
     P.host_apply_regular.restype = C.c_longlong
     P.host_apply_regular.argtypes = [C.POINTER(HostSceneDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.prolong = P
+    B = build("host_labels", "avs_labels.cu")
+    B.host_weights.restype = None
+    B.host_weights.argtypes = [C.POINTER(HostSceneDesc), C.POINTER(HostField), C.POINTER(HostField), C.c_int, C.c_int] + [C.c_void_p] * 4
+    B.host_classify.restype = None
+    B.host_classify.argtypes = [C.POINTER(HostSceneDesc), C.POINTER(HostField), C.POINTER(HostField)] + [C.c_void_p] * 4
+    L.labels = B
     return L
+
+
+@pytest.fixture(scope="module")
+def harness():
+    return build_harness()
 
 
 def _field(f, keep):
@@ -170,6 +182,32 @@ def check_product_rows_against_reference(L, sc, p):
     fine = keys[:, 0] <= 1
     assert np.array_equal(x0[fine], R.x0()[fine]), "restriction, levels 0 and 1 (bit for bit)"
     assert np.abs(x0 - R.x0()).max() <= 1e-13 * max(1.0, np.abs(R.x0()).max()), "restriction, hat form"
+    # ---- stage 1: the super-sampled integration weights (dense sampler; the GPU's sign-class shortcuts are not involved)
+    surf, coll = _field(sc.surface, keep), _field(sc.collision, keep)
+    wres = [list(sc.res)] + [[sc.res[k] + (k != a) for k in range(3)] for a in range(3)]
+    w = [np.zeros(tuple(reversed(r)), np.float32) for r in wres]
+    L.labels.host_weights(C.byref(d), C.byref(surf), C.byref(coll), int(p.number_super_samples), int(p.do_apply_solid_weights),
+                          *[a.ctypes.data for a in w])
+    assert np.array_equal(w[0], R.center_weights()), "centre weights (bit for bit)"
+    for a in range(3):
+        assert np.array_equal(w[1 + a], R.edge_weights(a)), f"edge weights, axis {a} (bit for bit)"
+    # ---- stages 4 and 5: regular-grid, face, edge and centre labels from the reference's cell labels and weights
+    reg = [np.full(tuple(reversed([sc.res[k] + (k == a) for k in range(3)])), 99, np.int8) for a in range(3)]
+    faces, edges, centers = [], [], []
+    for l in range(R.levels):
+        for a in range(3):
+            faces.append(np.full(R.face_index(l, a).shape, 99, np.int8))
+            edges.append(np.full(R.edge_index(l, a).shape, 99, np.int8))
+        centers.append(np.full(R.center_index(l).shape, 99, np.int8))
+    ptrs = lambda arrs: (C.c_void_p * len(arrs))(*[x.ctypes.data for x in arrs])
+    L.labels.host_classify(C.byref(d), C.byref(surf), C.byref(coll), ptrs(reg), ptrs(faces), ptrs(edges), ptrs(centers))
+    for a in range(3):
+        assert np.array_equal(reg[a], np.minimum(R.regular_index(a), 0)), f"regular-grid labels, axis {a}"
+    for l in range(R.levels):
+        for a in range(3):
+            assert np.array_equal(faces[3 * l + a], np.minimum(R.face_index(l, a), 0)), f"face labels, level {l} axis {a}"
+            assert np.array_equal(edges[3 * l + a], np.minimum(R.edge_index(l, a), 0)), f"edge labels, level {l} axis {a}"
+        assert np.array_equal(centers[l], np.minimum(R.center_index(l), 0)), f"centre labels, level {l}"
     # ---- stage 11: the interpolator's node pyramid + interpSPGrid + the write-back rule, fed with the REFERENCE's solution vector
     sol = np.ascontiguousarray(R.solution(), np.float64)
     out = [np.ascontiguousarray(v.data.copy(), np.float32) for v in sc.vel]
