@@ -431,10 +431,7 @@ int avs_stage_weights(AvsContext *c, const AvsParams *p) {
 // ------------------------------------------------------------------------------------------------
 // Stage 2+3a: refinement mask (AV.cpp:839-860) fused with setBaseGridLabels (OG.cpp:310-392):
 // mask 0 -> ACTIVE, < 0 -> UP, > 0 (or outside the un-padded grid) -> INACTIVE.
-__global__ void k_base_labels(const __grid_constant__ DeviceScene S, double inner, double outer) {
-    const Grid3<uint8_t> lab = S.label[0];
-    forCells(lab.n, [&](int x, int y, int z, size_t idx, bool ok) {
-        if (!ok) return;
+AVS_DEV __forceinline__ uint8_t baseLabel(const DeviceScene &S, double inner, double outer, int x, int y, int z) {
     uint8_t out = L_INACTIVE;
     if (x < S.N[0] && y < S.N[1] && z < S.N[2]) {
         double sdf = (double)S.surface.raw(x, y, z);
@@ -448,14 +445,18 @@ __global__ void k_base_labels(const __grid_constant__ DeviceScene S, double inne
             }
         }
     }
-    lab.d[idx] = out;
+    return out;
+}
+__global__ void k_base_labels(const __grid_constant__ DeviceScene S, double inner, double outer) {
+    const Grid3<uint8_t> lab = S.label[0];
+    forCells(lab.n, [&](int x, int y, int z, size_t idx, bool ok) {
+        if (!ok) return;
+        lab.d[idx] = baseLabel(S, inner, outer, x, y, z);
     });
 }
 
 // pass 1, setActiveCellsAndParentList (OG.cpp:394-565): one thread per 2x2x2 sibling block.
-__global__ void k_octree_pass1(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
-    forCells(par.n, [&](int px, int py, int pz, size_t idx, bool ok) {
-        if (!ok) return;
+AVS_DEV __forceinline__ void octreePass1(const Grid3<uint8_t> &cur, const Grid3<uint8_t> &par, int px, int py, int pz, size_t idx) {
     uint8_t v[8];
     bool any = false;
 #pragma unroll
@@ -468,21 +469,21 @@ __global__ void k_octree_pass1(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
     for (int ch = 0; ch < 8; ++ch)
         if (v[ch] == L_UP) cur.d[cur.lin(2 * px + (ch & 1), 2 * py + ((ch >> 1) & 1), 2 * pz + (ch >> 2))] = L_ACTIVE;
     par.d[idx] = L_DOWN;
+}
+__global__ void k_octree_pass1(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
+    forCells(par.n, [&](int px, int py, int pz, size_t idx, bool ok) {
+        if (!ok) return;
+        octreePass1(cur, par, px, py, pz, idx);
     });
 }
 
 // pass 2, setFaceGrading (OG.cpp:656-754). The reference applies its DOWN list before its ACTIVE
 // list (OG.cpp:145, 162); two kernels keep that order.
-__global__ void k_octree_pass2_down(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
-    forCells(cur.n, [&](int x, int y, int z, size_t idx, bool ok) {
-        if (!ok) return;
+AVS_DEV __forceinline__ void octreePass2Down(const Grid3<uint8_t> &cur, const Grid3<uint8_t> &par, int x, int y, int z, size_t idx) {
     if (cur.d[idx] != L_DOWN) return;
     par.d[par.lin(x >> 1, y >> 1, z >> 1)] = L_DOWN;
-    });
 }
-__global__ void k_octree_pass2_active(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
-    forCells(cur.n, [&](int x, int y, int z, size_t idx, bool ok) {
-        if (!ok) return;
+AVS_DEV __forceinline__ void octreePass2Active(const Grid3<uint8_t> &cur, const Grid3<uint8_t> &par, int x, int y, int z, size_t idx) {
     if (cur.d[idx] != L_ACTIVE) return;
     I3 c = mk3(x, y, z);
 #pragma unroll
@@ -493,15 +494,29 @@ __global__ void k_octree_pass2_active(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
             if (a[axis] < 0 || a[axis] >= cur.n[axis]) continue;
             if (cur.at(a) == L_UP) par.d[par.lin(a[0] >> 1, a[1] >> 1, a[2] >> 1)] = L_ACTIVE;
         }
-    });
 }
 // pass 3, setParentsUp (OG.cpp:756-840)
-__global__ void k_octree_pass3(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
-    forCells(cur.n, [&](int x, int y, int z, size_t idx, bool ok) {
-        if (!ok) return;
+AVS_DEV __forceinline__ void octreePass3(const Grid3<uint8_t> &cur, const Grid3<uint8_t> &par, int x, int y, int z, size_t idx) {
     if (cur.d[idx] != L_UP) return;
     size_t pi = par.lin(x >> 1, y >> 1, z >> 1);
     if (par.d[pi] == L_INACTIVE) par.d[pi] = L_UP;
+}
+__global__ void k_octree_pass2_down(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
+    forCells(cur.n, [&](int x, int y, int z, size_t idx, bool ok) {
+        if (!ok) return;
+        octreePass2Down(cur, par, x, y, z, idx);
+    });
+}
+__global__ void k_octree_pass2_active(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
+    forCells(cur.n, [&](int x, int y, int z, size_t idx, bool ok) {
+        if (!ok) return;
+        octreePass2Active(cur, par, x, y, z, idx);
+    });
+}
+__global__ void k_octree_pass3(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
+    forCells(cur.n, [&](int x, int y, int z, size_t idx, bool ok) {
+        if (!ok) return;
+        octreePass3(cur, par, x, y, z, idx);
     });
 }
 // ---- the same passes with 16 cells per thread (rows whose length is a multiple of 16: one 128-bit load per thread) ------------
@@ -550,23 +565,7 @@ __global__ void k_base_labels4(const __grid_constant__ DeviceScene S, double inn
     if (x0 >= lab.n[0]) return;
     unsigned packed = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int x = x0 + k;
-        uint8_t out = L_INACTIVE;
-        if (x < S.N[0] && y < S.N[1] && z < S.N[2]) {
-            double sdf = (double)S.surface.raw(x, y, z);
-            if (sdf > 0 && sdf < outer) out = L_ACTIVE;
-            else if (sdf <= 0.) {
-                if (sdf > -inner) out = L_ACTIVE;
-                else {
-                    double p[3];
-                    S.centerPos(mk3(x, y, z), 0, p);
-                    out = (S.collision.value(p) > (-inner - S.extrap)) ? L_ACTIVE : L_UP;
-                }
-            }
-        }
-        packed |= (unsigned)out << (8 * k);
-    }
+    for (int k = 0; k < 4; ++k) packed |= (unsigned)baseLabel(S, inner, outer, x0 + k, y, z) << (8 * k);
     *(unsigned *)(lab.d + lab.lin(x0, y, z)) = packed;
 }
 

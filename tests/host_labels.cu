@@ -1,7 +1,8 @@
 // tests/host_labels.cu -- TEST INFRASTRUCTURE (built and used only by tests/test_host_assembly.py; never part of libavs_b200.so).
 //
-// Stages 1, 4 and 5 of the CUDA library as far as they live in device FUNCTIONS of csrc/avs_labels.cu: the super-sampling weight
-// sampler (sdfWeightSample = computeSDFWeightsSampled, AV.cpp:712-791) and the per-sample classification rules (faceHasWeight,
+// Stages 1-5 of the CUDA library as far as they live in device FUNCTIONS of csrc/avs_labels.cu: the super-sampling weight sampler
+// (sdfWeightSample = computeSDFWeightsSampled, AV.cpp:712-791), the refinement mask / base labels and the octree passes (baseLabel,
+// octreePass1 / 2Down / 2Active / 3 = AV.cpp:839-860, OG.cpp:310-840) and the per-sample classification rules (faceHasWeight,
 // classifyFace, classifyEdge, classifyCenter = AV.cpp:1087-1443) -- compiled for the HOST (-DAVS_HOST_TEST) and run on the cell
 // labels of a run of the REFERENCE'S OWN CODE; the weights and the face / edge / centre / regular labels they produce are compared
 // with the reference's.  Not the product's code: the loops over samples, the marking of the occupied tiles (the kernels
@@ -48,6 +49,56 @@ void host_weights(const HostSceneDesc *h, const HostField *surface, const HostFi
                 if (s.d[i] > 0.f) g.d[i] = g.d[i] / s.d[i];   // k_divide_where_positive
         }
     }
+}
+
+// Stages 2 + 3 (avs_stage_octree): refinement mask fused with the base labels (baseLabel = AV.cpp:839-860 + OG.cpp:310-392), then per
+// level the passes of HDK_OctreeGrid::init in the order the stage launches them (octreePass1 = setActiveCellsAndParentList,
+// octreePass2Down / octreePass2Active = setFaceGrading, octreePass3 = setParentsUp), setTopLevel and the level cap (OG.cpp:198-211).
+// labelOut[l] must hold (Pad >> l)^3 bytes for l < allocated levels; returns the number of levels built, *allocated = levels allocated.
+int host_octree(const HostSceneDesc *h, const HostField *surface, const HostField *collision, int octreeLevels, int fineBandwidth,
+                uint8_t *const *labelOut, int *allocated) {
+    DeviceScene S;
+    fillScene(*h, S);
+    S.surface = toField(*surface);
+    S.collision = toField(*collision);
+    int L = octreeLevels;  // OG.cpp:32-40
+    for (int a = 0; a < 3; ++a) L = std::min(L, ilog2(S.Pad[a]));
+    if (L < 1) L = 1;
+    if (L > AVS_MAX_LEVELS) L = AVS_MAX_LEVELS;
+    *allocated = L;
+    for (int l = 0; l < L; ++l) {
+        Grid3<uint8_t> &g = S.label[l];
+        for (int a = 0; a < 3; ++a) g.n[a] = S.Pad[a] >> l;
+        g.d = labelOut[l];
+        if (l > 0) memset(g.d, L_INACTIVE, g.count());
+    }
+    const double fineVoxelWidth = std::max(2.0, (double)fineBandwidth);      // AV.cpp:259
+    const double inner = S.dx0 * fineVoxelWidth, outer = 3.0 * S.dx0;         // AV.cpp:261-262
+#define FOR_CELLS(g, body)                           \
+    for (int z = 0; z < (g).n[2]; ++z)               \
+        for (int y = 0; y < (g).n[1]; ++y)           \
+            for (int x = 0; x < (g).n[0]; ++x) { const size_t idx = (g).lin(x, y, z); body; }
+    FOR_CELLS(S.label[0], S.label[0].d[idx] = baseLabel(S, inner, outer, x, y, z))
+    for (int l = 0; l < L - 1; ++l) {
+        Grid3<uint8_t> cur = S.label[l], par = S.label[l + 1];
+        FOR_CELLS(par, octreePass1(cur, par, x, y, z, idx))
+        if (l > 0) FOR_CELLS(cur, octreePass2Down(cur, par, x, y, z, idx))
+        FOR_CELLS(cur, octreePass2Active(cur, par, x, y, z, idx))
+        FOR_CELLS(cur, octreePass3(cur, par, x, y, z, idx))
+    }
+    {
+        Grid3<uint8_t> &top = S.label[L - 1];   // k_octree_top, setTopLevel (OG.cpp:843-875)
+        for (size_t i = 0; i < top.count(); ++i)
+            if (top.d[i] == L_UP) top.d[i] = L_ACTIVE;
+    }
+#undef FOR_CELLS
+    int capped = 0;                              // first level without an ACTIVE cell
+    for (; capped < L; ++capped) {
+        bool any = false;
+        for (size_t i = 0; i < S.label[capped].count() && !any; ++i) any = S.label[capped].d[i] == L_ACTIVE;
+        if (!any) break;
+    }
+    return capped;
 }
 
 // Stages 4 and 5: labels of the regular-grid faces and of the octree faces / edges / centres of every level, from the cell labels
