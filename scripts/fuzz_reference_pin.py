@@ -43,8 +43,10 @@ def _box(c, h):
 def fuzz_case(seed: int):
     """(scene, OracleParams, description) of one seed -- deterministic."""
     rng = np.random.default_rng(100000 + seed)
-    variant = seed // 1000       # 0: grids of 16-48 cells; 1: 56-96 cells (deeper octrees); 2: as 0 with a distorted, noisy SDF
-    res = tuple(int(v) for v in rng.choice([56, 64, 72, 80, 96] if variant == 1 else [16, 20, 24, 28, 32, 36, 40, 48], size=3))
+    variant = seed // 1000       # 0: grids of 16-48 cells; 1: 56-96 cells (deeper octrees); 2: as 0 with a distorted, noisy SDF;
+    #                              3: 96-144 cells, one large blob first (4-5 levels built; tens of seconds per seed)
+    sizes = {1: [56, 64, 72, 80, 96], 3: [96, 112, 128, 144]}.get(variant, [16, 20, 24, 28, 32, 36, 40, 48])
+    res = tuple(int(v) for v in rng.choice(sizes, size=3))
     if rng.random() < 0.3:
         res = (res[0],) * 3
     dx = float(rng.choice([1.0 / 32, 0.013, 0.1, 0.0625, 0.37]))
@@ -58,6 +60,8 @@ def fuzz_case(seed: int):
     touch = rng.random() < 0.1
     margin = 0.0 if touch else 4.5 * dx
     blobs = []
+    if variant == 3:             # a body thick enough for coarse cells: centred sphere filling most of the smallest extent
+        blobs.append(_sphere(lo + 0.5 * ext, float(rng.uniform(0.36, 0.44) * ext.min())))
     for _ in range(int(rng.integers(1, 4))):
         c = lo + ext * rng.uniform(0.25, 0.75, 3)
         room = float(np.min(np.minimum(c - lo, lo + ext - c))) - margin
@@ -124,12 +128,14 @@ def fuzz_case(seed: int):
         xs, ys, zs = [corg[a] + cdx * np.arange(cres[a]) for a in range(3)]
         Z, Y, X = np.meshgrid(zs, ys, xs, indexing="ij", sparse=True)
         sc.collision = scenes.SampledField(np.ascontiguousarray(np.broadcast_to(collision_fn(X, Y, Z), (cres[2], cres[1], cres[0])).astype(np.float32)), corg, cdx)
-    p = orc.OracleParams(octree_levels=int(rng.integers(1, 7)), tolerance=float(rng.choice([1e-3, 1e-6, 1e-10])),
+    p = orc.OracleParams(octree_levels=int(rng.integers(4, 8)) if variant == 3 else int(rng.integers(1, 7)), tolerance=float(rng.choice([1e-3, 1e-6, 1e-10])),
                          dt=float(rng.choice([1.0 / 24, 1.0 / 120, 0.5])), use_enhanced_gradients=bool(rng.random() < 0.75),
                          do_apply_solid_weights=bool(collision_fn is not None and rng.random() < 0.4),
                          fine_bandwidth=int(rng.choice([1, 2, 2, 3, 4])), number_super_samples=ss,
                          extrapolation=float(rng.choice([0.5, 0.0, 1.0])), max_iterations=int(rng.choice([2500, 2500, 40])))
-    desc = (f"seed {seed}{['', ' (deep)', ' (distorted sdf)'][min(variant, 2)]}: res {res} dx {dx:g} origin {tuple(round(o, 4) for o in origin)} blobs {len(blobs)}{' TOUCHING-THE-BOUNDARY' if touch else ''} solid "
+    if variant == 3:
+        p.max_iterations = 40        # half a million rows: the reference's serial CG is not the subject of this variant
+    desc = (f"seed {seed}{['', ' (deep)', ' (distorted sdf)', ' (large)'][min(variant, 3)]}: res {res} dx {dx:g} origin {tuple(round(o, 4) for o in origin)} blobs {len(blobs)}{' TOUCHING-THE-BOUNDARY' if touch else ''} solid "
             f"{'plane' if solid < 0.35 else 'sphere' if solid < 0.55 else 'none'} own-collision-grid {sc.collision.data is not None and sc.collision.dx != dx} "
             f"mu {'var' if callable(mu) else mu0} rho {'var' if callable(rho) else rho0} | levels {p.octree_levels} tol {p.tolerance:g} dt {p.dt:g} "
             f"enh {p.use_enhanced_gradients} solidw {p.do_apply_solid_weights} band {p.fine_bandwidth} ss {ss} extrap {p.extrapolation} maxit {p.max_iterations}")
