@@ -548,7 +548,11 @@ class HDK_AdaptiveViscosity:
 
         scene = Scene(obj.res, obj.origin, obj.dx, surf, vel, fw, visc, dens, coll, cvel)
         if self._solver is None:
-            self._solver = Solver(device=self._device)
+            try:
+                self._solver = Solver(device=self._device)
+            except AvsError as e:      # no GPU / no library: reported like the C++ shim does (addError, UT_ERROR_ABORT) -- no CPU path
+                self.addError(obj, str(e))
+                return False
         if self.doPrintOctree and self.onlyPrintOctree:
             # AV.cpp:283-294: dump the octree geometry ("octreeGeometry" SIM_GeometryCopy: P, pscale, octreeLevel) and return
             try:

@@ -84,6 +84,7 @@ def _bind_signatures(L):
     L.ref_create.argtypes = [C.POINTER(_Scene), C.POINTER(_Params)]
     L.ref_destroy.argtypes = [C.c_void_p]
     L.ref_run.argtypes = [C.c_void_p]
+    L.ref_tamper.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
     L.ref_set_threads.argtypes = [C.c_int]
     L.ref_set_weight_shortcut.argtypes = [C.c_int]
     L.ref_error_count.argtypes = [C.c_void_p]
@@ -125,7 +126,14 @@ class RefRun:
 
     _precision_word = 0
 
-    def __init__(self, scene, params: OracleParams | None = None, octree_only: bool = False, weight_shortcut: bool = True):
+    # names the reference looks its fields up by (GAS_NAME_* of the stand-ins; AV.cpp:138-144, 203, 218)
+    FIELD_NAMES = {"surface": b"surface", "velocity": b"velocity", "collision": b"collision", "collisionvel": b"collisionvel",
+                   "faceWeights": b"faceWeights", "viscosity": b"viscosity", "density": b"density"}
+    _TAMPER_OPS = {"remove": 0, "misalign": 1, "unstagger": 2}
+
+    def __init__(self, scene, params: OracleParams | None = None, octree_only: bool = False, weight_shortcut: bool = True, tamper=()):
+        """``tamper``: (op, field) pairs applied to the object before solveGasSubclass runs -- op "remove", "misalign" or
+        "unstagger", field a key of FIELD_NAMES -- for the validation paths AV.cpp:152-229."""
         params = params or OracleParams()
         if params.single_precision and self._precision_word == 0:
             raise ValueError("libavs_ref.so is built without USESINGLEPRECISION")
@@ -139,6 +147,9 @@ class RefRun:
         self._L.ref_set_weight_shortcut(int(weight_shortcut))
         self._h = self._L.ref_create(C.byref(sc), C.byref(p))
         del keep
+        for op, field in tamper:
+            if self._L.ref_tamper(self._h, self._TAMPER_OPS[op], self.FIELD_NAMES[field]) != 0:
+                raise ValueError(f"cannot {op} field {field}")
         self.returned_true = self._L.ref_run(self._h) == 0
         self.errors = [self._L.ref_error_text(self._h, i).decode() for i in range(self._L.ref_error_count(self._h))]
         self.extra_info = self._L.ref_extra_info(self._h).decode()
@@ -278,12 +289,13 @@ class RefRun32(RefRun):
 class ShimRun(RefRun):
     """The same harness around THIS repository's Houdini-side shim (integration/hdk/HDK_AdaptiveViscosityB200.cpp): the stand-in
     "Houdini" calls the shim's solveGasSubclass, the shim flattens the fields and calls avs_solve / avs_solve_multi in
-    libavs_b200.so, and writes the velocity back -- the drop-in boundary end to end.  Needs a GPU.  Only what the DOP itself
+    libavs_b200.so, and writes the velocity back -- the drop-in boundary end to end.  Needs a GPU (its field validation, which comes
+    first, does not: tests/test_validation_contract.py).  Only what the DOP itself
     exposes is available afterwards: ``out_velocity``, ``octree_points``, ``errors``, ``extra_info`` (the PerfMon string)."""
 
-    def __init__(self, scene, params: OracleParams | None = None, octree_only: bool = False, gpus: int = 1):
+    def __init__(self, scene, params: OracleParams | None = None, octree_only: bool = False, gpus: int = 1, tamper=()):
         self._precision_word = (int(gpus) if gpus > 1 else 0) << 8
-        super().__init__(scene, params, octree_only)
+        super().__init__(scene, params, octree_only, tamper=tamper)
 
     def _library(self):
         return shim_lib()

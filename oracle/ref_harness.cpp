@@ -171,6 +171,27 @@ void *ref_create(const OrcScene *s, const OrcParams *p) {
     return r;
 }
 
+// Validation paths of solveGasSubclass (AV.cpp:152-229): break the object between ref_create and ref_run.
+//   op 0: remove the field `name` from the object;  op 1: shift the field's grid by one voxel along x (no longer aligned);
+//   op 2: give component 0 of the vector field `name` centre sampling (no longer a staggered grid)
+int ref_tamper(void *h, int op, const char *name) {
+    RefRun *r = (RefRun *)h;
+    auto s = r->obj.scalars.find(name);
+    auto v = r->obj.vectors.find(name);
+    if (s == r->obj.scalars.end() && v == r->obj.vectors.end()) return -1;
+    if (op == 0) {
+        if (s != r->obj.scalars.end()) r->obj.scalars.erase(s);
+        else r->obj.vectors.erase(v);
+    } else if (op == 1) {
+        if (s != r->obj.scalars.end()) s->second->myField.myOrigD[0] += s->second->myField.myVoxelSizeD[0];
+        else for (int a = 0; a < 3; ++a) v->second->myFields[a].myOrigD[0] += v->second->myFields[a].myVoxelSizeD[0];
+    } else if (op == 2) {
+        if (v == r->obj.vectors.end()) return -1;
+        v->second->myFields[0].mySample = SIM_SAMPLE_CENTER;
+    } else return -1;
+    return 0;
+}
+
 void ref_destroy(void *h) { delete (RefRun *)h; }
 void ref_set_threads(int n) { mock_hdk::setThreads(n); }
 void ref_set_weight_shortcut(int on) { mock_hdk::weightShortcutRef() = on != 0; }
