@@ -522,9 +522,7 @@ __global__ void k_octree_pass3(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
 // ---- the same passes with 16 cells per thread (rows whose length is a multiple of 16: one 128-bit load per thread) ------------
 // One byte per thread keeps these sweeps at ~0.25 TB/s.  Only a band of cells is ACTIVE and the UP cells of one 16-cell run share
 // 8 parents, so a thread that loads 16 labels at once usually has nothing (pass 2) or eight byte-checks (pass 3) left to do.
-__global__ void k_octree_pass2_active16(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
-    const int x0 = 16 * (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
-    if (x0 >= cur.n[0]) return;
+AVS_DEV __forceinline__ void octreePass2Active16(const Grid3<uint8_t> &cur, const Grid3<uint8_t> &par, int x0, int y, int z) {
     const size_t row = (size_t)cur.n[0] * ((size_t)y + (size_t)cur.n[1] * (size_t)z);
     __align__(16) uint8_t v[16];
     *(uint4 *)v = *(const uint4 *)(cur.d + row + x0);
@@ -545,9 +543,12 @@ __global__ void k_octree_pass2_active16(Grid3<uint8_t> cur, Grid3<uint8_t> par) 
             }
     }
 }
-__global__ void k_octree_pass3_16(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
+__global__ void k_octree_pass2_active16(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
     const int x0 = 16 * (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
     if (x0 >= cur.n[0]) return;
+    octreePass2Active16(cur, par, x0, y, z);
+}
+AVS_DEV __forceinline__ void octreePass3_16(const Grid3<uint8_t> &cur, const Grid3<uint8_t> &par, int x0, int y, int z) {
     const size_t row = (size_t)cur.n[0] * ((size_t)y + (size_t)cur.n[1] * (size_t)z);
     __align__(16) uint8_t v[16];
     *(uint4 *)v = *(const uint4 *)(cur.d + row + x0);
@@ -557,6 +558,11 @@ __global__ void k_octree_pass3_16(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
         if (v[2 * k] == L_UP || v[2 * k + 1] == L_UP) {
             if (par.d[prow + k] == L_INACTIVE) par.d[prow + k] = L_UP;
         }
+}
+__global__ void k_octree_pass3_16(Grid3<uint8_t> cur, Grid3<uint8_t> par) {
+    const int x0 = 16 * (int)(blockIdx.x * blockDim.x + threadIdx.x), y = (int)blockIdx.y, z = (int)blockIdx.z;
+    if (x0 >= cur.n[0]) return;
+    octreePass3_16(cur, par, x0, y, z);
 }
 // k_base_labels with 4 cells per thread (padded rows are a multiple of 4): one 32-bit store per thread
 __global__ void k_base_labels4(const __grid_constant__ DeviceScene S, double inner, double outer) {

@@ -55,8 +55,9 @@ void host_weights(const HostSceneDesc *h, const HostField *surface, const HostFi
 // level the passes of HDK_OctreeGrid::init in the order the stage launches them (octreePass1 = setActiveCellsAndParentList,
 // octreePass2Down / octreePass2Active = setFaceGrading, octreePass3 = setParentsUp), setTopLevel and the level cap (OG.cpp:198-211).
 // labelOut[l] must hold (Pad >> l)^3 bytes for l < allocated levels; returns the number of levels built, *allocated = levels allocated.
+// scalarPasses != 0: the one-cell-per-thread pass functions on every level (what the stage uses where a row is not a multiple of 16).
 int host_octree(const HostSceneDesc *h, const HostField *surface, const HostField *collision, int octreeLevels, int fineBandwidth,
-                uint8_t *const *labelOut, int *allocated) {
+                uint8_t *const *labelOut, int *allocated, int scalarPasses) {
     DeviceScene S;
     fillScene(*h, S);
     S.surface = toField(*surface);
@@ -83,8 +84,17 @@ int host_octree(const HostSceneDesc *h, const HostField *surface, const HostFiel
         Grid3<uint8_t> cur = S.label[l], par = S.label[l + 1];
         FOR_CELLS(par, octreePass1(cur, par, x, y, z, idx))
         if (l > 0) FOR_CELLS(cur, octreePass2Down(cur, par, x, y, z, idx))
-        FOR_CELLS(cur, octreePass2Active(cur, par, x, y, z, idx))
-        FOR_CELLS(cur, octreePass3(cur, par, x, y, z, idx))
+        if (cur.n[0] % 16 == 0 && !scalarPasses) {   // the stage's choice: 16 cells per thread where the rows allow it
+            for (int z = 0; z < cur.n[2]; ++z)
+                for (int y = 0; y < cur.n[1]; ++y)
+                    for (int x0 = 0; x0 < cur.n[0]; x0 += 16) octreePass2Active16(cur, par, x0, y, z);
+            for (int z = 0; z < cur.n[2]; ++z)
+                for (int y = 0; y < cur.n[1]; ++y)
+                    for (int x0 = 0; x0 < cur.n[0]; x0 += 16) octreePass3_16(cur, par, x0, y, z);
+        } else {
+            FOR_CELLS(cur, octreePass2Active(cur, par, x, y, z, idx))
+            FOR_CELLS(cur, octreePass3(cur, par, x, y, z, idx))
+        }
     }
     {
         Grid3<uint8_t> &top = S.label[L - 1];   // k_octree_top, setTopLevel (OG.cpp:843-875)

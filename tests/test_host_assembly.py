@@ -79,7 +79,7 @@ def build_harness():
     B.host_classify.restype = None
     B.host_classify.argtypes = [C.POINTER(HostSceneDesc), C.POINTER(HostField), C.POINTER(HostField)] + [C.c_void_p] * 4
     B.host_octree.restype = C.c_int
-    B.host_octree.argtypes = [C.POINTER(HostSceneDesc), C.POINTER(HostField), C.POINTER(HostField), C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    B.host_octree.argtypes = [C.POINTER(HostSceneDesc), C.POINTER(HostField), C.POINTER(HostField), C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_int]
     L.labels = B
     return L
 
@@ -196,13 +196,14 @@ def check_product_rows_against_reference(L, sc, p):
     # ---- stages 2 and 3: refinement mask + octree (cell labels of every level, number of levels built)
     pad = [1 << int(np.ceil(np.log2(n_))) if n_ > 1 else 1 for n_ in sc.res]
     alloc = max(1, min(int(p.octree_levels), min(int(np.log2(q)) for q in pad), MAX_LEVELS))
-    labs = [np.full(tuple(reversed([q >> l for q in pad])), 77, np.uint8) for l in range(alloc)]
-    allocated = C.c_int(0)
-    built = L.labels.host_octree(C.byref(d), C.byref(surf), C.byref(coll), int(p.octree_levels), int(p.fine_bandwidth),
-                                 (C.c_void_p * alloc)(*[x.ctypes.data for x in labs]), C.byref(allocated))
-    assert allocated.value == alloc and built == R.levels, (allocated.value, alloc, built, R.levels)
-    for l in range(R.levels):
-        assert np.array_equal(labs[l], R.labels(l)), f"cell labels, level {l}"
+    for scalar_passes in (0, 1):     # the 16-cells-per-thread pass functions where the rows allow it (the stage's choice) / the scalar ones
+        labs = [np.full(tuple(reversed([q >> l for q in pad])), 77, np.uint8) for l in range(alloc)]
+        allocated = C.c_int(0)
+        built = L.labels.host_octree(C.byref(d), C.byref(surf), C.byref(coll), int(p.octree_levels), int(p.fine_bandwidth),
+                                     (C.c_void_p * alloc)(*[x.ctypes.data for x in labs]), C.byref(allocated), scalar_passes)
+        assert allocated.value == alloc and built == R.levels, (allocated.value, alloc, built, R.levels)
+        for l in range(R.levels):
+            assert np.array_equal(labs[l], R.labels(l)), f"cell labels, level {l} (scalar passes: {scalar_passes})"
     # ---- stages 4 and 5: regular-grid, face, edge and centre labels from the reference's cell labels and weights
     reg = [np.full(tuple(reversed([sc.res[k] + (k == a) for k in range(3)])), 99, np.int8) for a in range(3)]
     faces, edges, centers = [], [], []
