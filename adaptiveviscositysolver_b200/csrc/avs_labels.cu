@@ -734,13 +734,9 @@ AVS_DEV __forceinline__ bool faceHasWeight(const DeviceScene &S, const I3 &face,
     return false;
 }
 
-// classifyRegularVelocityFaces (AV.cpp:1087-1165)
-__global__ void k_classify_regular(const __grid_constant__ DeviceScene S, int axis, Grid3<uint8_t> tiles, int zOff) {
-    const Grid3<int8_t> g = S.regular[axis];
-    forCellsZ(g.n, zOff, [&](int x, int y, int z, size_t idx, bool ok) {
-    const bool in = ok;
+// classifyRegularVelocityFaces (AV.cpp:1087-1165): label of one regular-grid face
+AVS_DEV __forceinline__ int8_t classifyRegular(const DeviceScene &S, int axis, const Grid3<uint8_t> &tiles, int x, int y, int z) {
     int8_t out = F_UNASSIGNED;
-    if (in) {
     I3 face = mk3(x, y, z);
     if (tileOccupied(tiles, x, y, z) && face[axis] - 1 >= 0 && face[axis] < S.N[axis]) {
         if (faceHasWeight(S, face, axis)) {
@@ -749,8 +745,12 @@ __global__ void k_classify_regular(const __grid_constant__ DeviceScene S, int ax
             out = (S.collision.value(p) > -S.extrap) ? F_SOLID : F_FLUID;
         }
     }
-    g.d[idx] = out;
-    }
+    return out;
+}
+__global__ void k_classify_regular(const __grid_constant__ DeviceScene S, int axis, Grid3<uint8_t> tiles, int zOff) {
+    const Grid3<int8_t> g = S.regular[axis];
+    forCellsZ(g.n, zOff, [&](int x, int y, int z, size_t idx, bool ok) {
+        if (ok) g.d[idx] = classifyRegular(S, axis, tiles, x, y, z);
     });
 }
 

@@ -3,11 +3,10 @@
 // Stages 1-5 of the CUDA library as far as they live in device FUNCTIONS of csrc/avs_labels.cu: the super-sampling weight sampler
 // (sdfWeightSample = computeSDFWeightsSampled, AV.cpp:712-791), the refinement mask / base labels and the octree passes (baseLabel,
 // octreePass1 / 2Down / 2Active / 3 = AV.cpp:839-860, OG.cpp:310-840) and the per-sample classification rules (faceHasWeight,
-// classifyFace, classifyEdge, classifyCenter = AV.cpp:1087-1443) -- compiled for the HOST (-DAVS_HOST_TEST) and run on the cell
+// classifyRegular, classifyFace, classifyEdge, classifyCenter = AV.cpp:1087-1443) -- compiled for the HOST (-DAVS_HOST_TEST) and run on the cell
 // labels of a run of the REFERENCE'S OWN CODE; the weights and the face / edge / centre / regular labels they produce are compared
 // with the reference's.  Not the product's code: the loops over samples, the marking of the occupied tiles (the kernels
-// k_mark_surface_tiles / k_tile_flags, restated below with the library's markTile) and the regular-face rule of k_classify_regular
-// (restated below); the sign-class shortcuts of the weight kernels and the vectorised octree passes only exist on the GPU.
+// k_mark_surface_tiles / k_tile_flags, restated below with the library's markTile); the sign-class shortcuts of the weight kernels and the vectorised octree passes only exist on the GPU.
 #ifndef AVS_HOST_TEST
 #error "compile with -DAVS_HOST_TEST"
 #endif
@@ -134,25 +133,14 @@ void host_classify(const HostSceneDesc *h, const HostField *surface, const HostF
                 const I3 c = mk3(x, y, z);
                 for (int a = 0; a < 3; ++a) { markTile(ft[a], c); markTile(ft[a], cellToFace(c, a, 1)); }
             }
-    // ---- regular-grid faces (k_classify_regular, classifyRegularVelocityFaces AV.cpp:1087-1165)
+    // ---- regular-grid faces (classifyRegular = classifyRegularVelocityFaces AV.cpp:1087-1165)
     for (int axis = 0; axis < 3; ++axis) {
         Grid3<int8_t> g;
         g.d = regularOut[axis];
         for (int k = 0; k < 3; ++k) g.n[k] = S.N[k] + (k == axis);
         for (int z = 0; z < g.n[2]; ++z)
             for (int y = 0; y < g.n[1]; ++y)
-                for (int x = 0; x < g.n[0]; ++x) {
-                    int8_t out = F_UNASSIGNED;
-                    const I3 face = mk3(x, y, z);
-                    if (tileOccupied(ft[axis], x, y, z) && face[axis] - 1 >= 0 && face[axis] < S.N[axis]) {
-                        if (faceHasWeight(S, face, axis)) {
-                            double p[3];
-                            S.facePos(face, axis, 0, p);
-                            out = (S.collision.value(p) > -S.extrap) ? F_SOLID : F_FLUID;
-                        }
-                    }
-                    g.d[g.lin(x, y, z)] = out;
-                }
+                for (int x = 0; x < g.n[0]; ++x) g.d[g.lin(x, y, z)] = classifyRegular(S, axis, ft[axis], x, y, z);
     }
     // ---- octree levels
     for (int l = 0; l < S.levels; ++l) {
