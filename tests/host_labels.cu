@@ -6,7 +6,7 @@
 // classifyRegular, classifyFace, classifyEdge, classifyCenter = AV.cpp:1087-1443) -- compiled for the HOST (-DAVS_HOST_TEST) and run on the cell
 // labels of a run of the REFERENCE'S OWN CODE; the weights and the face / edge / centre / regular labels they produce are compared
 // with the reference's.  Not the product's code: the loops over samples, the marking of the occupied tiles (the kernels
-// k_mark_surface_tiles / k_tile_flags, restated below with the library's markTile); the sign-class shortcuts of the weight kernels and the vectorised octree passes only exist on the GPU.
+// k_mark_surface_tiles / k_tile_flags, restated below with the library's markTile); the sign-class shortcuts of the weight kernels only exist on the GPU.
 #ifndef AVS_HOST_TEST
 #error "compile with -DAVS_HOST_TEST"
 #endif
