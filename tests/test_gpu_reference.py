@@ -145,7 +145,7 @@ def test_scene_outside_the_reference_contract_is_refused_not_executed(solver):
     from adaptiveviscositysolver_b200.solver import AvsError, Params
     fz = _fuzz()
     sc, op, _ = fz.fuzz_case(fz.OUT_OF_CONTRACT_SEED)
-    O = orc.OracleRun(sc, op)                      # the restated reference does emit out-of-range columns on this scene
+    O = orc.OracleRun(sc, op, stop_after_stage=9)  # (assembly only) the restated reference does emit out-of-range columns here
     assert O.csr()[1].min() < 0
     out = [v.data.copy() for v in sc.vel]
     with pytest.raises(AvsError) as e:

@@ -71,4 +71,4 @@ def test_liquid_at_the_grid_boundary_is_outside_the_reference_contract():
     c = subprocess.run([sys.executable, str(ROOT / "scripts" / "fuzz_reference_pin.py"), "--compare", str(seed)], capture_output=True, text=True, timeout=600)
     assert c.returncode == 0 and "OUT-OF-RANGE COLUMNS" in c.stdout, c.stdout[-500:] + c.stderr[-500:]
     sc, p, _ = fz.fuzz_case(seed)
-    assert orc.OracleRun(sc, p).csr()[1].min() < 0
+    assert orc.OracleRun(sc, p, stop_after_stage=9).csr()[1].min() < 0     # assembly only: no CG on a matrix with column -3
