@@ -186,6 +186,22 @@ def test_single_precision_oracle_against_the_reference_single_precision_build(na
         assert np.abs(R.out_velocity(a).astype(np.float64) - O.out_velocity(a)).max() < 1e-5 * scale
 
 
+@pytest.mark.parametrize("frame", [0, 3, 6, 9])
+def test_oracle_equals_reference_on_buckling_frames(frame):
+    """BASELINE configs[4] (C5): frames of the prescribed-geometry buckling sheet (free fall, contact, fold) at dx = 2 mm -- thin
+    liquid on a solid ground with variable viscosity.  All ten frames at the workload's own dx = 1 mm were compared once, off line
+    (profiles/r2_fuzz.md)."""
+    sc = scenes.buckling_sheet(frame=frame, dx=0.002)
+    p = orc.OracleParams(octree_levels=4, dt=1.0 / 120.0, tolerance=1e-6)
+    R, O = ref.RefRun(sc, p), orc.OracleRun(sc, p)
+    perm, Ar, Ao = assert_same_run(R, O, sc)
+    assert np.array_equal(Ar.data, Ao.data)
+    assert np.array_equal(R.rhs(), O.rhs()[perm]) and np.array_equal(R.x0(), O.x0()[perm])
+    assert abs(R.iterations - O.iterations) <= max(1, R.iterations // 100)
+    scale = max(1.0, np.abs(O.solution()).max())
+    assert np.abs(R.solution() - O.solution()[perm]).max() < 1e-6 * scale
+
+
 def test_reference_threaded_fan_out_gives_the_same_system():
     """UT_ThreadedAlgorithm stand-in with 4 jobs per THREADED_METHOD: labels and numbering identical (the reference numbers
     serially), matrix equal up to the order in which setFromTriplets sums a row's duplicates."""
