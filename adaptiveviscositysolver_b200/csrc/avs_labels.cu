@@ -1030,9 +1030,8 @@ static int avs_face_tile_maps(AvsContext *c, Grid3<uint8_t> t[3]) {   // allocat
 
 int avs_stage_regular_labels(AvsContext *c) {
     DeviceScene &S = c->S;
-    int res[3][3];
     for (int a = 0; a < 3; ++a) {
-        for (int k = 0; k < 3; ++k) { S.regular[a].n[k] = S.N[k] + (k == a); res[a][k] = S.Pad[k] + 1; }
+        for (int k = 0; k < 3; ++k) S.regular[a].n[k] = S.N[k] + (k == a);
         if (c->regular[a].reserve(S.regular[a].count())) return AVS_ERR_ALLOC;
         S.regular[a].d = c->regular[a].as<int8_t>();
     }
