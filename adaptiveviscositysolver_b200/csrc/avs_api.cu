@@ -33,6 +33,9 @@ static inline void enterContext(AvsContext *c) {
 // avs_last_error() returns on this thread; AVS_ERR_CUDA keeps the text of the failed CUDA call (avs_set_last_error)
 static inline int leaveContext(AvsContext *c, int rc) {
     if (rc != AVS_OK && rc != AVS_ERR_CUDA && !c->lastError.empty()) snprintf(g_lastError, sizeof(g_lastError), "%s", c->lastError.c_str());
+    // a stage that fails returns before the pipeline joins its copy stream: the caller's host arrays must not be in flight any more
+    // when the call returns (success paths have waited for evUploadDone / evDownloadDone already)
+    if (rc != AVS_OK && c->copyStream) { cudaStreamSynchronize(c->copyStream); cudaGetLastError(); }
     return rc;
 }
 
