@@ -171,12 +171,12 @@ def compare(sc, p):
     assert np.array_equal(R.rhs(), O.rhs()[perm]), "rhs"
     assert np.array_equal(R.x0(), O.x0()[perm]), "restricted velocity"
     # CG: the two loops are the same recurrence but sum their dot products in different orders, so after hundreds of iterations on
-    # an ill-conditioned system (mu = 5000 on rho = 1: seeds 105, 162, 272, 297 of the first 300) they stop up to 7 % apart.  What
-    # must hold exactly is checked above (matrix, rhs, initial guess); here: iteration counts exact below 100 iterations, within
-    # 1 % below 500 and within 10 % above, both solutions meet the tolerance on the TRUE
+    # an ill-conditioned system (high viscosity on rho = 1 with a long time step: seeds 105, 162, 272, 297, 424 of the first 800) they
+    # stop up to 8 % apart.  What must hold exactly is checked above (matrix, rhs, initial guess); here: iteration counts exact
+    # below 100 iterations and within 10 % above, both solutions meet the tolerance on the TRUE
     # residual (unless the iteration limit ended the loop), and the regular-grid outputs differ by no more than the solutions do
     # (+ one float32 rounding of the stored value).
-    slack = 0 if R.iterations < 100 else max(1, R.iterations // 100) if R.iterations < 500 else R.iterations // 10
+    slack = 0 if R.iterations < 100 else R.iterations // 10
     assert abs(R.iterations - O.iterations) <= slack, (R.iterations, O.iterations)
     scale = max(1.0, float(np.abs(O.solution()).max()))
     b = O.rhs()
@@ -185,8 +185,8 @@ def compare(sc, p):
         if run.iterations < p.max_iterations and bn > 0:
             assert np.linalg.norm(b[perm] - Ar @ x) <= (10.0 * p.tolerance + 1e-8) * bn, f"true residual of the {name}'s solution"   # 1e-8: drift of the recursive residual
     dsol = float(np.abs(R.solution() - O.solution()[perm]).max())
-    if R.iterations == O.iterations and R.iterations < 100:
-        assert dsol < 1e-9 * scale, "solution"
+    if R.iterations == O.iterations and R.iterations < 100:      # (seed 749: 90 iterations to 1e-3 on rho = 1 end 3e-6 apart)
+        assert dsol < max(1e-9, 0.01 * p.tolerance) * scale, "solution"
     for a in range(3):
         ro, oo = R.out_velocity(a).astype(np.float64), O.out_velocity(a).astype(np.float64)
         assert np.all(np.abs(ro - oo) <= 4.0 * dsol + 1e-9 * scale + 2.0 ** -22 * np.abs(oo)), f"output velocity, axis {a}"
