@@ -44,7 +44,8 @@ def fuzz_case(seed: int):
     """(scene, OracleParams, description) of one seed -- deterministic."""
     rng = np.random.default_rng(100000 + seed)
     variant = seed // 1000       # 0: grids of 16-48 cells; 1: 56-96 cells (deeper octrees); 2: as 0 with a distorted, noisy SDF;
-    #                              3: 96-144 cells, one large blob first (4-5 levels built; tens of seconds per seed)
+    #                              3: 96-144 cells, one large blob first (4-5 levels built; tens of seconds per seed);
+    #                              4: as 0, always with a solid whose velocity is a sampled field on a grid of its own
     sizes = {1: [56, 64, 72, 80, 96], 3: [96, 112, 128, 144]}.get(variant, [16, 20, 24, 28, 32, 36, 40, 48])
     res = tuple(int(v) for v in rng.choice(sizes, size=3))
     if rng.random() < 0.3:
@@ -92,7 +93,7 @@ def fuzz_case(seed: int):
         return (U * np.sin(k * x + ph[0]) * np.cos(k * y) + 0.0 * z, -U * np.cos(k * x) * np.sin(k * y + ph[1]) + 0.3 * U * z / ext[2],
                 0.5 * U * np.sin(k * z + ph[2]) + 0.0 * (x + y))
 
-    solid = rng.random()
+    solid = rng.random() * (0.55 if variant == 4 else 1.0)     # variant 4: always a solid (its velocity becomes a sampled field below)
     collision_fn, cvel = None, (0.0, 0.0, 0.0)
     if solid < 0.35:             # tilted ground plane
         n = np.array([rng.uniform(-0.3, 0.3), 1.0, rng.uniform(-0.3, 0.3)])
@@ -128,6 +129,22 @@ def fuzz_case(seed: int):
         xs, ys, zs = [corg[a] + cdx * np.arange(cres[a]) for a in range(3)]
         Z, Y, X = np.meshgrid(zs, ys, xs, indexing="ij", sparse=True)
         sc.collision = scenes.SampledField(np.ascontiguousarray(np.broadcast_to(collision_fn(X, Y, Z), (cres[2], cres[1], cres[0])).astype(np.float32)), corg, cdx)
+    if variant == 4:
+        # the solid's velocity as three dense fields on a grid of their own (the reference samples "collisionvel" by world position:
+        # boundary terms of the stencils AV.cpp:1896-1905, 1952-1961, and the solid faces of the write-back AV.cpp:2860-2890):
+        # rigid rotation about a random axis through the domain centre plus a translation
+        w = rng.uniform(-2.0, 2.0, 3)
+        t0 = rng.uniform(-0.5, 0.5, 3)
+        cc = lo + 0.5 * ext
+        vdx = dx * float(rng.choice([1.0, 1.7, 2.5]))
+        vres = tuple(int(np.ceil(e / vdx)) + 3 for e in ext)
+        vorg = tuple(float(o - 1.2 * vdx) for o in origin)
+        xs, ys, zs = [vorg[a] + vdx * np.arange(vres[a]) for a in range(3)]
+        Z, Y, X = np.meshgrid(zs, ys, xs, indexing="ij", sparse=True)
+        rx, ry, rz = X - cc[0], Y - cc[1], Z - cc[2]
+        comps = (t0[0] + w[1] * rz - w[2] * ry, t0[1] + w[2] * rx - w[0] * rz, t0[2] + w[0] * ry - w[1] * rx)
+        sc.collision_vel = [scenes.SampledField(np.ascontiguousarray(np.broadcast_to(c, (vres[2], vres[1], vres[0])).astype(np.float32)), vorg, vdx)
+                            for c in comps]
     p = orc.OracleParams(octree_levels=int(rng.integers(4, 8)) if variant == 3 else int(rng.integers(1, 7)), tolerance=float(rng.choice([1e-3, 1e-6, 1e-10])),
                          dt=float(rng.choice([1.0 / 24, 1.0 / 120, 0.5])), use_enhanced_gradients=bool(rng.random() < 0.75),
                          do_apply_solid_weights=bool(collision_fn is not None and rng.random() < 0.4),
@@ -135,7 +152,7 @@ def fuzz_case(seed: int):
                          extrapolation=float(rng.choice([0.5, 0.0, 1.0])), max_iterations=int(rng.choice([2500, 2500, 40])))
     if variant == 3:
         p.max_iterations = 40        # half a million rows: the reference's serial CG is not the subject of this variant
-    desc = (f"seed {seed}{['', ' (deep)', ' (distorted sdf)', ' (large)'][min(variant, 3)]}: res {res} dx {dx:g} origin {tuple(round(o, 4) for o in origin)} blobs {len(blobs)}{' TOUCHING-THE-BOUNDARY' if touch else ''} solid "
+    desc = (f"seed {seed}{['', ' (deep)', ' (distorted sdf)', ' (large)', ' (sampled solid velocity)'][min(variant, 4)]}: res {res} dx {dx:g} origin {tuple(round(o, 4) for o in origin)} blobs {len(blobs)}{' TOUCHING-THE-BOUNDARY' if touch else ''} solid "
             f"{'plane' if solid < 0.35 else 'sphere' if solid < 0.55 else 'none'} own-collision-grid {sc.collision.data is not None and sc.collision.dx != dx} "
             f"mu {'var' if callable(mu) else mu0} rho {'var' if callable(rho) else rho0} | levels {p.octree_levels} tol {p.tolerance:g} dt {p.dt:g} "
             f"enh {p.use_enhanced_gradients} solidw {p.do_apply_solid_weights} band {p.fine_bandwidth} ss {ss} extrap {p.extrapolation} maxit {p.max_iterations}")
