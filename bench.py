@@ -154,6 +154,33 @@ def dense_bytes(scene):
     return n
 
 
+def compiled_reference_check(orc, cores):
+    """The reference's OWN sources (oracle/_ref/libavs_ref.so: /root/reference/Source/*.cpp compiled unchanged, with the threading
+    its UT_ThreadedAlgorithm / UTparallelFor calls ask for on `cores` threads; its Eigen CG is serial, as upstream Eigen's is for a
+    column-major matrix) timed beside the OpenMP port on ONE WHOLE SOLVE of a bounded workload (C2 literal, ~0.5 M DOF): shows which
+    way the `kind: port` arm errs -- the port is the FASTER of the two, so every GPU/CPU ratio formed with it is conservative."""
+    try:
+        from oracle import avs_ref as ref
+        if not ref.available():
+            return {"unavailable": "oracle/_ref/libavs_ref.so not in this tree"}
+        w2 = WORKLOADS["c2lit"]
+        scene = make_scene(w2)
+        prm = orc.OracleParams(octree_levels=w2["L"], tolerance=w2["tol"], dt=1.0 / 24.0)
+        ref.set_threads(cores)
+        t = time.time(); r = ref.RefRun(scene, prm); t_ref = time.time() - t
+        n, it_ref, err_ref = int(r.n_face), int(r.iterations), float(r.error)
+        del r
+        ref.set_threads(1)
+        t = time.time(); o = orc.OracleRun(scene, prm); t_port = time.time() - t
+        it_port = int(o.iterations)
+        return {"workload": w2["desc"], "N": n, "threads": cores,
+                "reference": {"whole_solve_s": round(t_ref, 2), "iterations": it_ref, "rel_error": err_ref, "dof_iters_per_s": n * it_ref / t_ref},
+                "port": {"whole_solve_s": round(t_port, 2), "iterations": it_port, "dof_iters_per_s": n * it_port / t_port},
+                "port_over_reference": round(t_ref / t_port, 2)}
+    except Exception as e:  # the cross-check must never take the arm's line with it
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
 def run_reference(args, w):
     """CPU arm.  The reference's own sources DO compile here against Houdini / Eigen stand-ins (oracle/_ref, used by the parity
     tests), but single-threaded stand-ins at 512^3 would take minutes per solve, so the timed arm is the restated oracle --
@@ -205,7 +232,8 @@ def run_reference(args, w):
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": w["desc"], "N": int(n), "nnz": int(run.nnz), "levels": int(run.levels), "tolerance": w["tol"],
-                   "oracle_assembly_s": round(t_asm, 2), "cg_only": cg_only, "whole_solve": whole, "sample": sample},
+                   "oracle_assembly_s": round(t_asm, 2), "cg_only": cg_only, "whole_solve": whole, "sample": sample,
+                   "compiled_reference": compiled_reference_check(orc, cores)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
