@@ -25,7 +25,8 @@ _spec.loader.exec_module(fz)
 
 # solids (plane / sphere, own collision grid, solid weights), variable viscosity / density, non-cubic grids, shifted origins,
 # 1-4 built levels, every option away from its default somewhere
-SEEDS = [0, 4, 9, 15, 25, 29, 34, 43, 48, 57, 61, 70, 73, 77, 89, 100]
+# 4017 / 4022 / 4046: variant 4, the solid's velocity as sampled fields on a grid of their own (tests/test_zz_gpu_sampled_solid_velocity.py)
+SEEDS = [0, 4, 9, 15, 25, 29, 34, 43, 48, 57, 61, 70, 73, 77, 89, 100, 4017, 4022, 4046]
 
 
 @pytest.mark.parametrize("seed", SEEDS)
@@ -36,7 +37,7 @@ def test_oracle_equals_reference_on_a_random_scene(seed):
 
 
 FINGERPRINTS = {4: "78f7dd0c1e74c147", 23: "0ee5fad76c7d641f", 43: "a45f814aea087ffc", 135: "0dcb907ea1449a40", 192: "d1d035df3c89a34c",
-                1011: "b9a76be6749841c1", 2005: "14134869a31ba6d4", 3000: "df1b00fb6c5dbaf9"}
+                1011: "b9a76be6749841c1", 2005: "14134869a31ba6d4", 3000: "df1b00fb6c5dbaf9", 4022: "aa1c5d86a7598ab3"}
 
 
 def test_seeds_still_mean_the_same_scenes():
@@ -49,6 +50,8 @@ def test_seeds_still_mean_the_same_scenes():
         h.update(np.ascontiguousarray(sc.surface.data).tobytes())
         h.update(np.ascontiguousarray(sc.vel[1].data).tobytes())
         h.update(repr((sc.res, sc.dx, sc.origin, p)).encode())
+        if sc.collision_vel[0].data is not None:       # variant 4: the sampled solid velocity is part of what the seed means
+            h.update(np.ascontiguousarray(sc.collision_vel[0].data).tobytes())
         assert h.hexdigest()[:16] == want, seed
 
 
