@@ -1,0 +1,85 @@
+"""fp32 (USESINGLEPRECISION, HDK_Utilities.h:25-30; BASELINE configs[2]) on random scenes: the restated oracle's single-precision mode
+-- which the CUDA library's fp32 path follows -- against oracle/_ref/libavs_ref_f32.so, the REFERENCE's own sources compiled with
+-DUSESINGLEPRECISION (oracle/Makefile target ref-f32).  TEST INFRASTRUCTURE: CPU only, needs /root/reference.
+
+    python scripts/fuzz_reference_f32.py [first_seed] [count]
+
+Scenes and options are those of scripts/fuzz_reference_pin.py (same seeds); the tolerance is raised to what float conjugate
+gradients can reach (>= 1e-5).  Per seed, as tests/test_reference_pin.py::test_single_precision_oracle_against_the_reference_
+single_precision_build: numbering and sparsity identical; the reference's matrix is float (it sums float triplets in float), the
+oracle's is the double sum rounded once -- entries within 1e-6 of the largest, at most 10 % of them different at all; right-hand side
+and restricted velocity within 1e-6; iteration counts and solutions compared where both runs converged."""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "scripts"))
+import fuzz_reference_pin as fz  # noqa: E402
+from oracle import avs_oracle as orc  # noqa: E402
+from oracle import avs_ref as ref  # noqa: E402
+
+
+def compare_f32(sc, p):
+    """Returns a dict of what was measured; raises AssertionError on a difference beyond the bars above."""
+    R, O = ref.RefRun32(sc, p), orc.OracleRun(sc, p)
+    assert R.returned_true and not R.errors and R.n_face == O.n_face and R.levels == O.levels
+    if R.n_face == 0:
+        return None
+    assert np.array_equal(R.face_keys(), O.face_keys()), "numbering"
+    (rp, rc, rv), (op, oc, ov) = R.csr(), O.csr()
+    if rc.min() < 0:
+        return None                     # outside the reference's contract (profiles/r2_fuzz.md)
+    assert np.array_equal(rp, op) and np.array_equal(rc, oc), "sparsity"
+    assert np.array_equal(rv, rv.astype(np.float32).astype(np.float64)), "the reference's matrix is float"
+    rel = np.abs(rv - ov.astype(np.float32).astype(np.float64)) / np.abs(rv).max()
+    assert rel.max() < 1e-6, f"matrix values {rel.max():.3g}"
+    differing = float((rel > 0).mean())
+    assert differing < 0.10, f"{differing:.3f} of the entries differ"
+    bs = max(np.abs(O.rhs()).max(), 1e-300)
+    assert np.abs(R.rhs() - O.rhs()).max() <= 1e-6 * bs, "rhs"
+    assert np.abs(R.x0() - O.x0()).max() <= 1e-6 * max(1.0, np.abs(O.x0()).max()), "restricted velocity"
+    out = dict(levels=R.levels, n=R.n_face, it_ref=R.iterations, it_oracle=O.iterations, differing=differing, converged=False, dsol=None)
+    if R.iterations < p.max_iterations and O.iterations < p.max_iterations and R.error < p.tolerance and O.error < p.tolerance:
+        out["converged"] = True
+        slack = max(1, O.iterations // 50) if O.iterations < 100 else O.iterations // 10
+        assert abs(R.iterations - O.iterations) <= slack, (R.iterations, O.iterations)
+        scale = max(1.0, np.abs(O.solution()).max())
+        out["dsol"] = float(np.abs(R.solution() - O.solution()).max() / scale)
+    return out
+
+
+if __name__ == "__main__":
+    import subprocess
+    subprocess.run(["make", "-C", str(ROOT / "oracle"), "ref-f32"], check=True, capture_output=True)
+    first = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+    count = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+    ok, skipped, bad, worst, unconv = 0, [], [], 0.0, []
+    for seed in range(first, first + count):
+        sc, p, desc = fz.fuzz_case(seed)
+        if "TOUCHING-THE-BOUNDARY" in desc:
+            skipped.append(seed)
+            continue
+        p.single_precision = True
+        p.tolerance = max(p.tolerance, 1e-5)
+        try:
+            r = compare_f32(sc, p)
+        except AssertionError as e:
+            bad.append(seed)
+            print(f"FAIL {desc}\n     {str(e)[:300]}", flush=True)
+            continue
+        if r is None:
+            skipped.append(seed)
+            continue
+        ok += 1
+        if r["converged"]:
+            worst = max(worst, r["dsol"])
+        else:
+            unconv.append(seed)
+        print(f"ok   seed {seed}: levels {r['levels']} N {r['n']} iterations {r['it_ref']} / {r['it_oracle']} entries differing {r['differing']:.4f} "
+              f"solution distance {r['dsol']}", flush=True)
+    print(f"seeds {first}..{first + count - 1}: {ok} agree, {len(skipped)} skipped (empty / outside the reference's contract) {skipped}, failing: {bad}; "
+          f"largest solution distance where both converged {worst:.3g}; ended by the iteration limit or above tolerance: {unconv}")
+    sys.exit(1 if bad else 0)

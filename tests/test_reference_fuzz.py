@@ -25,7 +25,7 @@ _spec.loader.exec_module(fz)
 
 # solids (plane / sphere, own collision grid, solid weights), variable viscosity / density, non-cubic grids, shifted origins,
 # 1-4 built levels, every option away from its default somewhere
-# 4017 / 4022 / 4046: variant 4, the solid's velocity as sampled fields on a grid of their own (tests/test_zz_gpu_sampled_solid_velocity.py)
+# 4017 / 4022 / 4046: variant 4, the solid's velocity as sampled fields on a grid of their own (tests/test_zz_gpu_late_additions.py)
 SEEDS = [0, 4, 9, 15, 25, 29, 34, 43, 48, 57, 61, 70, 73, 77, 89, 100, 4017, 4022, 4046]
 
 

@@ -1,0 +1,92 @@
+"""CUDA path (through the C-ABI) against the REFERENCE'S OWN CODE (oracle/_ref/libavs_ref.so) on scenes whose solid velocity
+("collisionvel", AV.cpp:142) is three dense fields on a grid of their own origin and voxel size -- fuzz variant 4 of
+scripts/fuzz_reference_pin.py.  The reference samples it by world position in the boundary terms of the stress stencils
+(AV.cpp:1896-1905, 1952-1961) and on the solid faces of the write-back (AV.cpp:2860-2890); every other scene of the suite carries a
+constant solid velocity.  Same bars as tests/test_gpu_reference.py (labels, weights, DOF sets bit-exact; matrix and rhs 1e-12;
+iterations; solution 1e-7; regular-grid output 1e-6 with >= 98 % of the faces bit-equal).
+
+On the CPU the same seeds are held by tests/test_reference_fuzz.py (restated oracle) and by scripts/sweep_host_product_source.py
+(the library's device functions compiled for the host: seeds 4000-4099, 90 of 90 in-contract scenes bit for bit, profiles/r2_fuzz.md).
+Further down: the library's fp32 path against the reference's own USESINGLEPRECISION build (BASELINE configs[2]).
+
+Both groups were written after the round's GPU budget was spent: they are first executed by the driver's round-end run, hence a file of
+their own that sorts last (the fp32 test body was dry-run on the CPU with the oracle's fp32 mode standing in for the solver)."""
+import pytest
+
+from oracle import avs_oracle as orc
+from oracle import avs_ref as ref
+from tests.test_gpu_reference import _fuzz, check_cuda_against_reference
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libavs_ref.so was not shipped with this snapshot")]
+
+# 4017: solid sphere, velocity grid 1.7 x coarser than the scene; 4022: collision SDF AND velocity on grids of their own;
+# 4027: tilted plane + doApplySolidWeights, velocity grid 1.7 x coarser; 4046: a 65-entry row
+SEEDS = [4017, 4022, 4027, 4046]
+
+
+@pytest.fixture(scope="module")
+def solver():
+    from adaptiveviscositysolver_b200.solver import Solver
+    s = Solver(device=0)
+    yield s
+    s.close()
+
+
+@pytest.mark.parametrize("seed", SEEDS)
+def test_cuda_path_equals_compiled_reference_with_a_sampled_solid_velocity(solver, seed):
+    from adaptiveviscositysolver_b200.solver import Params
+    sc, op, _ = _fuzz().fuzz_case(seed)
+    assert all(v.data is not None for v in sc.collision_vel)
+    tol = 1e-10
+    kw = dict(octree_levels=op.octree_levels, tolerance=tol, dt=op.dt, use_enhanced_gradients=op.use_enhanced_gradients,
+              do_apply_solid_weights=op.do_apply_solid_weights, fine_bandwidth=op.fine_bandwidth,
+              number_super_samples=op.number_super_samples, extrapolation=op.extrapolation)
+    R = ref.RefRun(sc, orc.OracleParams(**kw))
+    check_cuda_against_reference(solver, sc, Params(**kw), R, tol)
+
+
+# ---- USESINGLEPRECISION (BASELINE configs[2]) against the reference's own fp32 build ------------------------------------------------
+# oracle/_ref/libavs_ref_f32.so = the reference's sources with -DUSESINGLEPRECISION (SolveType = fpreal32, HDK_Utilities.h:25-30): float
+# triplets summed in float, float right-hand side, float conjugate gradients.  The library's fp32 path assembles in double, rounds every
+# entry once and runs the CG on floats.  On the CPU (tests/test_reference_pin.py, scripts/fuzz_reference_f32.py) the oracle's fp32 mode
+# and the reference's fp32 build take the same number of iterations and end 0.5-1.4e-6 apart on these scenes at tolerance 1e-5, both
+# ~1.5e-5 from the fp64 solution; the bars here leave room for the GPU's different summation order: iterations within 5 % (at least 3),
+# solution and regular-grid output within 1e-4 (the older fp32 GPU tests only ask for 5e-3 against the fp64 oracle).
+F32_CASES = {
+    "sphere64_l5_noise": (dict(n=64, radius_cells=26, noise=0.01), 5),
+    "solid_ground32_l3_moving": (dict(n=32, radius_cells=9, center=(0.5, 0.34, 0.5), ground_height=0.125, ground_velocity=(0.1, 0.0, -0.2)), 3),
+    "padded_48x64x40_l5_varmu": (dict(n=64, radius_cells=14, res=(48, 64, 40), center=(0.375, 0.5, 0.3125), variable_viscosity=True,
+                                      variable_density=True), 5),
+}
+
+
+@pytest.mark.parametrize("name", list(F32_CASES))
+def test_cuda_single_precision_path_against_the_reference_single_precision_build(solver, name):
+    import numpy as np
+
+    from adaptiveviscositysolver_b200 import scenes
+    from adaptiveviscositysolver_b200.solver import Params
+    from tests.util import perm_gpu_to_oracle
+    if ref.build_f32() is None:
+        pytest.skip("oracle/_ref/libavs_ref_f32.so was not shipped with this snapshot")
+    kw, levels = F32_CASES[name]
+    sc = scenes.sphere_drop(**kw)
+    tol = 1e-5
+    R = ref.RefRun32(sc, orc.OracleParams(octree_levels=levels, tolerance=tol, single_precision=True))
+    assert R.returned_true and not R.errors and R.error < tol
+    out = [v.data.copy() for v in sc.vel]
+    info = solver.solve(sc, Params(octree_levels=levels, tolerance=tol, single_precision=True), out)
+    assert info.levels == R.levels
+    assert (info.octree_dofs, info.edge_dofs, info.center_dofs, info.regular_dofs) == (R.n_face, R.n_edge, R.n_center, R.regular_dofs)
+    assert info.error < tol
+    assert abs(info.iterations - R.iterations) <= max(3, R.iterations // 20), (info.iterations, R.iterations)
+    perm = perm_gpu_to_oracle(solver.keys(), R.face_keys())
+    xr = R.solution()[perm]
+    scale = max(1.0, float(np.abs(xr).max()))
+    assert np.abs(solver.solution() - xr).max() < 1e-4 * scale
+    for a in range(3):
+        ro = R.out_velocity(a)
+        assert np.abs(out[a].astype(np.float64) - ro.astype(np.float64)).max() < 1e-4 * scale
+        reg = R.regular_index(a)
+        untouched = (reg == orc.UNASSIGNED) | (reg == orc.OUTSIDE)
+        assert np.array_equal(out[a][untouched], sc.vel[a].data[untouched])   # AV.cpp:2843-2890
