@@ -200,7 +200,9 @@ def compare(sc, p):
     bn = float(np.linalg.norm(b))
     for name, run, x in (("reference", R, R.solution()), ("oracle", O, O.solution()[perm])):
         if run.iterations < p.max_iterations and bn > 0:
-            assert np.linalg.norm(b[perm] - Ar @ x) <= (10.0 * p.tolerance + 1e-8) * bn, f"true residual of the {name}'s solution"   # 1e-8: drift of the recursive residual
+            # 1e-7: drift of the recursive residual (seed 828 -- viscosity 5000, dt 0.5, tolerance 1e-10: reference and oracle both stop
+            # after 193 iterations with the SAME recursive error 8.98e-11 and the SAME true residual 4.7e-8)
+            assert np.linalg.norm(b[perm] - Ar @ x) <= (10.0 * p.tolerance + 1e-7) * bn, f"true residual of the {name}'s solution"
     dsol = float(np.abs(R.solution() - O.solution()[perm]).max())
     if R.iterations == O.iterations and R.iterations < 100:      # (seed 749: 90 iterations to 1e-3 on rho = 1 end 3e-6 apart)
         assert dsol < max(1e-9, 0.01 * p.tolerance) * scale, "solution"
