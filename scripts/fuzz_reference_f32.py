@@ -44,7 +44,10 @@ def compare_f32(sc, p):
     out = dict(levels=R.levels, n=R.n_face, it_ref=R.iterations, it_oracle=O.iterations, differing=differing, converged=False, dsol=None)
     if R.iterations < p.max_iterations and O.iterations < p.max_iterations and R.error < p.tolerance and O.error < p.tolerance:
         out["converged"] = True
-        slack = max(1, O.iterations // 50) if O.iterations < 100 else O.iterations // 10
+        # float conjugate gradients on ill-conditioned systems: beyond several hundred iterations the two runs -- same recurrence, float
+        # dot products summed in different orders -- stop up to 27 % apart (seeds 94, 105, 133 of the first 300: 924 / 813, 1487 / 1166,
+        # 872 / 780); below 100 iterations 140 of 142 seeds stop on the same iteration, the other two one apart
+        slack = max(1, O.iterations // 50) if O.iterations < 100 else (3 * O.iterations) // 10
         assert abs(R.iterations - O.iterations) <= slack, (R.iterations, O.iterations)
         scale = max(1.0, np.abs(O.solution()).max())
         out["dsol"] = float(np.abs(R.solution() - O.solution()).max() / scale)
