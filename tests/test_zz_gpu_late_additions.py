@@ -50,7 +50,8 @@ def test_cuda_path_equals_compiled_reference_with_a_sampled_solid_velocity(solve
 # triplets summed in float, float right-hand side, float conjugate gradients.  The library's fp32 path assembles in double, rounds every
 # entry once and runs the CG on floats.  On the CPU (tests/test_reference_pin.py, scripts/fuzz_reference_f32.py) the oracle's fp32 mode
 # and the reference's fp32 build take the same number of iterations and end 0.5-1.4e-6 apart on these scenes at tolerance 1e-5, both
-# ~1.5e-5 from the fp64 solution; the bars here leave room for the GPU's different summation order: iterations within 5 % (at least 3),
+# ~1.5e-5 from the fp64 solution; the bars here leave room for the GPU's different summation order (on the CPU, float runs of 100+ iterations stop up to 5 % apart on
+# well-conditioned random scenes, profiles/r2_fuzz.md): iterations within 10 % (at least 3),
 # solution and regular-grid output within 1e-4 (the older fp32 GPU tests only ask for 5e-3 against the fp64 oracle).
 F32_CASES = {
     "sphere64_l5_noise": (dict(n=64, radius_cells=26, noise=0.01), 5),
@@ -79,7 +80,7 @@ def test_cuda_single_precision_path_against_the_reference_single_precision_build
     assert info.levels == R.levels
     assert (info.octree_dofs, info.edge_dofs, info.center_dofs, info.regular_dofs) == (R.n_face, R.n_edge, R.n_center, R.regular_dofs)
     assert info.error < tol
-    assert abs(info.iterations - R.iterations) <= max(3, R.iterations // 20), (info.iterations, R.iterations)
+    assert abs(info.iterations - R.iterations) <= max(3, R.iterations // 10), (info.iterations, R.iterations)
     perm = perm_gpu_to_oracle(solver.keys(), R.face_keys())
     xr = R.solution()[perm]
     scale = max(1.0, float(np.abs(xr).max()))
