@@ -10,7 +10,7 @@ On the CPU the same seeds are held by tests/test_reference_fuzz.py (restated ora
 Further down: the library's fp32 path against the reference's own USESINGLEPRECISION build (BASELINE configs[2]).
 
 Both groups were written after the round's GPU budget was spent: they are first executed by the driver's round-end run, hence a file of
-their own that sorts last (the fp32 test body was dry-run on the CPU with the oracle's fp32 mode standing in for the solver)."""
+their own that sorts last (both test bodies were dry-run on the CPU, bars included, with the restated oracle standing in for the solver object)."""
 import pytest
 
 from oracle import avs_oracle as orc
