@@ -75,3 +75,20 @@ def test_liquid_at_the_grid_boundary_is_outside_the_reference_contract():
     assert c.returncode == 0 and "OUT-OF-RANGE COLUMNS" in c.stdout, c.stdout[-500:] + c.stderr[-500:]
     sc, p, _ = fz.fuzz_case(seed)
     assert orc.OracleRun(sc, p, stop_after_stage=9).csr()[1].min() < 0     # assembly only: no CG on a matrix with column -3
+
+
+@pytest.mark.parametrize("seed", [4, 7, 10, 79, 163])
+def test_single_precision_oracle_equals_reference_single_precision_build_on_a_random_scene(seed):
+    """USESINGLEPRECISION (BASELINE configs[2]) on multi-level random scenes: scripts/fuzz_reference_f32.py (swept over seeds 0-299,
+    profiles/r2_fuzz.md) -- numbering and sparsity identical, matrix within one float rounding, iteration counts and solutions where
+    both float runs converge."""
+    if ref.build_f32() is None:
+        pytest.skip("/root/reference not present (the fp32 reference build is made on demand)")
+    spec = importlib.util.spec_from_file_location("fuzz_reference_f32", ROOT / "scripts" / "fuzz_reference_f32.py")
+    f32 = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(f32)
+    sc, p, desc = fz.fuzz_case(seed)
+    p.single_precision = True
+    p.tolerance = max(p.tolerance, 1e-5)
+    r = f32.compare_f32(sc, p)
+    assert r is not None and r["levels"] >= 2 and r["converged"] and r["dsol"] < 2e-3, (desc, r)
