@@ -148,6 +148,41 @@ def test_reference_debug_build_passes_its_own_unit_tests(tmp_path):
     assert r.returncode == 0 and r.stdout.startswith("ok True"), r.stdout[-2000:] + r.stderr[-2000:]
 
 
+EDGE_OPTIONS = {
+    "no_iterations_allowed": dict(max_iterations=0),              # Eigen leaves the loop before the first step: the restricted velocity is returned
+    "one_iteration": dict(max_iterations=1),
+    "tolerance_met_by_the_initial_guess": dict(tolerance=10.0),
+    "tolerance_zero_ends_on_the_limit": dict(tolerance=0.0, max_iterations=30),
+    "one_level": dict(octree_levels=1),                           # uniform grid
+    "more_levels_than_the_grid_has": dict(octree_levels=9),       # capped by HDK_OctreeGrid::init (OG.cpp:18-60)
+    "no_fine_band": dict(fine_bandwidth=0),
+    "band_wider_than_the_liquid": dict(fine_bandwidth=12),
+    "one_super_sample": dict(number_super_samples=1),
+    "far_extrapolation": dict(extrapolation=3.0),
+    "tiny_time_step": dict(dt=1e-6),                              # mass dominates: one iteration
+    "huge_time_step": dict(dt=100.0),                             # viscosity dominates: 268 iterations
+}
+
+
+@pytest.mark.parametrize("name", list(EDGE_OPTIONS))
+def test_oracle_equals_reference_on_option_edge_values(name):
+    """DOP options at the ends of their ranges (HDK_AdaptiveViscosity.h:28-41, parm ranges AV.cpp:36-124): same labels, numbering, matrix,
+    right-hand side and restricted velocity bit for bit, same iteration count and relative error, same output."""
+    kw = dict(octree_levels=3, tolerance=1e-6)
+    kw.update(EDGE_OPTIONS[name])
+    sc, p = scenes.sphere_drop(32, 10, noise=0.01), orc.OracleParams(**kw)
+    R, O = ref.RefRun(sc, p), orc.OracleRun(sc, p)
+    assert R.returned_true and not R.errors
+    perm, Ar, Ao = assert_same_run(R, O, sc)
+    assert np.array_equal(Ar.data, Ao.data)
+    assert np.array_equal(R.rhs(), O.rhs()[perm]) and np.array_equal(R.x0(), O.x0()[perm])
+    check_solution(R, O, perm, sc)
+    if name in ("no_iterations_allowed", "tolerance_met_by_the_initial_guess"):
+        assert R.iterations == 0 and np.array_equal(R.solution(), R.x0())
+    if name == "more_levels_than_the_grid_has":
+        assert R.levels == 3
+
+
 @pytest.mark.parametrize("name", ["sphere32_l4", "solid_ground32_l3", "padded_48x64x40_l5_varmu", "sphere64_l5_tol1e-6"])
 def test_single_precision_oracle_against_the_reference_single_precision_build(name):
     """USESINGLEPRECISION (SolveType = fpreal32, HDK_Utilities.h:25-30; BASELINE configs[2]): the reference compiled with that define
