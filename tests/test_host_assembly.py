@@ -265,7 +265,8 @@ _spec.loader.exec_module(fz)
 
 # random scenes of scripts/fuzz_reference_pin.py (solids on their own collision grid, solid weights, variable viscosity / density,
 # non-cubic grids, shifted origins, 65-entry rows at 25 / 48 / 135, deep and distorted-SDF variants)
-SEEDS = [0, 4, 9, 15, 25, 29, 34, 43, 48, 57, 61, 70, 73, 77, 89, 100, 135, 192, 1003, 1011, 2005, 2010]
+# 4017 / 4022 / 4046: the solid's velocity as sampled fields on a grid of their own (variant 4)
+SEEDS = [0, 4, 9, 15, 25, 29, 34, 43, 48, 57, 61, 70, 73, 77, 89, 100, 135, 192, 1003, 1011, 2005, 2010, 4017, 4022, 4046]
 
 
 @pytest.mark.parametrize("seed", SEEDS)
@@ -279,3 +280,14 @@ def test_variants_of_the_options(harness):
     for kw in (dict(use_enhanced_gradients=False), dict(do_apply_solid_weights=True), dict(fine_bandwidth=4, number_super_samples=2)):
         sc = scenes.sphere_drop(32, 9, center=(0.5, 0.34, 0.5), ground_height=0.125, ground_velocity=(0.1, 0.0, -0.2))
         check_product_rows_against_reference(harness, sc, orc.OracleParams(octree_levels=3, max_iterations=1, **kw))
+
+
+def test_options_at_the_ends_of_their_ranges(harness):
+    """The library's device functions on the option edge values tests/test_reference_pin.py holds the oracle to (1 and 9 levels, fine
+    band 0 / 12, one super-sample, far extrapolation, dt 1e-6 / 100): weights, octree, labels, matrix, rhs, restriction, output bit for bit."""
+    sc = scenes.sphere_drop(32, 10, noise=0.01)
+    for kw in (dict(octree_levels=1), dict(octree_levels=9), dict(fine_bandwidth=0), dict(fine_bandwidth=12), dict(number_super_samples=1),
+               dict(extrapolation=3.0), dict(dt=1e-6), dict(dt=100.0)):
+        k = dict(octree_levels=3, tolerance=1e-6, max_iterations=1)
+        k.update(kw)
+        check_product_rows_against_reference(harness, sc, orc.OracleParams(**k))
