@@ -32,6 +32,11 @@ def test_reference_arm_prints_one_contract_line():
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     ws = d["config"]["whole_solve"]
     assert ws["iterations"] > 0 and ws["rel_error"] < 1e-3 and 0 < ws["dof_iters_per_s"] < d["value"] * 1.5
+    # the compiled reference timed beside the port on one whole C2-literal solve (only where oracle/_ref is present)
+    cr = d["config"]["compiled_reference"]
+    if "unavailable" not in cr:
+        assert cr["reference"]["iterations"] == cr["port"]["iterations"] == 161 and cr["N"] == 495108
+        assert cr["reference"]["whole_solve_s"] > 0 and cr["port"]["whole_solve_s"] > 0 and cr["port_over_reference"] > 0
 
 
 def test_reference_arm_only_rank0_works_under_torchrun_env():
